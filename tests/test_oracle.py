@@ -1,0 +1,264 @@
+"""Pins the CPU oracle against the reference's own pass criteria.
+
+Each test restates one reference test program (cited) on the oracle and applies the
+criterion the reference's postpro script applies.
+"""
+import math
+
+import numpy as np
+import pytest
+
+from oracle import fen_oracle as fo
+
+PI = fo.PI
+
+
+def _slope(N, e):
+    return -np.polyfit(np.log(N), np.log(e), 1)[0]
+
+
+# ---- test/small_test/fields/methods.f90:208-341 ---------------------------------------------
+def test_periodic_ghosts_and_operator_convergence():
+    errs_g, errs_l, N = [], [], [16, 32, 64]
+    for n in N:
+        G = fo.Grid(n, n, n, 1.0, 1.0, 1.0)
+        s = fo.Scalar(G, 1)
+        x = G.x[:, None, None]; y = G.y[None, :, None]; z = G.z[None, None, :]
+        ana = np.sin(2 * PI * x) * np.cos(2 * PI * y) * np.sin(2 * PI * z)
+        s.I[...] = ana[1:-1, 1:-1, 1:-1]
+        s.update_ghost_nodes()
+        assert np.abs(s.f - ana).max() < 1e-14          # global_mod small = 1e-14
+        g = fo.Vector(G, 0)
+        fo.gradient(s, g)
+        xf = (G.x[1:-1] + 0.5 * G.delta)[:, None, None]
+        gx = 2 * PI * np.cos(2 * PI * xf) * np.cos(2 * PI * y[:, 1:-1]) * np.sin(2 * PI * z[:, :, 1:-1])
+        errs_g.append(np.abs(g.x.I - gx).max())
+        lap = fo.Scalar(G, 0)
+        fo.laplacian_scalar(s, lap)
+        errs_l.append(np.abs(lap.I + 12 * PI * PI * ana[1:-1, 1:-1, 1:-1]).max())
+    assert _slope(N, errs_g) > 1.8
+    assert _slope(N, errs_l) > 1.8
+
+
+# ---- test/small_test/poisson/convergence_rate/convergence_rate.f90:103-223 ------------------
+_CASES_2D = {
+    "pp": (["Periodic"] * 4,
+           lambda x, y: -8 * PI * PI * np.sin(2 * PI * x) * np.cos(2 * PI * y),
+           lambda x, y: np.sin(2 * PI * x) * np.cos(2 * PI * y)),
+    "pn": (["Periodic", "Periodic", "Wall", "Wall"],
+           lambda x, y: -4 * PI * PI * (np.sin(2 * PI * x) + np.cos(2 * PI * y)),
+           lambda x, y: np.sin(2 * PI * x) + np.cos(2 * PI * y)),
+    "nn": (["Wall"] * 4,
+           lambda x, y: -8 * PI * PI * np.cos(2 * PI * x) * np.cos(2 * PI * y),
+           lambda x, y: np.cos(2 * PI * x) * np.cos(2 * PI * y)),
+}
+_CASES_3D = {
+    "ppp": (["Periodic"] * 6,
+            lambda x, y, z: -12 * PI * PI * np.sin(2 * PI * x) * np.cos(2 * PI * y) * np.sin(2 * PI * z),
+            lambda x, y, z: np.sin(2 * PI * x) * np.cos(2 * PI * y) * np.sin(2 * PI * z)),
+    "ppn": (["Periodic"] * 4 + ["Wall"] * 2,
+            lambda x, y, z: -4 * PI * PI * (np.sin(2 * PI * x) + np.sin(2 * PI * y) + np.cos(2 * PI * z)),
+            lambda x, y, z: np.sin(2 * PI * x) + np.sin(2 * PI * y) + np.cos(2 * PI * z)),
+    "npn": (["Wall", "Wall", "Periodic", "Periodic", "Wall", "Wall"],
+            lambda x, y, z: -12 * PI * PI * np.cos(2 * PI * x) * np.cos(2 * PI * y) * np.cos(2 * PI * z),
+            lambda x, y, z: np.cos(2 * PI * x) * np.cos(2 * PI * y) * np.cos(2 * PI * z)),
+    "nnn": (["Wall"] * 6,
+            lambda x, y, z: -12 * PI * PI * np.cos(2 * PI * x) * np.cos(2 * PI * y) * np.cos(2 * PI * z),
+            lambda x, y, z: np.cos(2 * PI * x) * np.cos(2 * PI * y) * np.cos(2 * PI * z)),
+}
+
+
+@pytest.mark.parametrize("variant", ["pp", "pn", "nn"])
+def test_poisson_convergence_2d(variant):
+    bc, rhs, sol = _CASES_2D[variant]
+    N, e = [16, 32, 64, 128, 256], []
+    for n in N:
+        G = fo.Grid(n, n, 1, 1.0, 1.0, 1.0 / n, bc=bc)
+        phi = fo.Scalar(G, 0)
+        x = G.x[1:-1, None, None]; y = G.y[None, 1:-1, None]
+        phi.I[...] = rhs(x, y)
+        ps = fo.PoissonSolver(phi)
+        assert ps.variant == variant
+        ps.solve(phi)
+        e.append(np.abs(phi.I - sol(x, y)).max())
+    assert _slope(N, e) > 1.8                            # postpro.py:28,64,100
+
+
+@pytest.mark.parametrize("variant", ["ppp", "ppn", "npn", "nnn"])
+def test_poisson_convergence_3d(variant):
+    bc, rhs, sol = _CASES_3D[variant]
+    N, e = [16, 32, 64], []
+    for n in N:
+        G = fo.Grid(n, n, n, 1.0, 1.0, 1.0, bc=bc)
+        phi = fo.Scalar(G, 0)
+        x = G.x[1:-1, None, None]; y = G.y[None, 1:-1, None]; z = G.z[None, None, 1:-1]
+        phi.I[...] = rhs(x, y, z)
+        ps = fo.PoissonSolver(phi)
+        assert ps.variant == variant
+        ps.solve(phi)
+        e.append(np.abs(phi.I - sol(x, y, z)).max())
+    assert _slope(N, e) > 1.8                            # postpro.py:136,172,208
+
+
+def test_poisson_unsupported_bc_combo_raises():
+    G = fo.Grid(16, 16, 16, 1.0, 1.0, 1.0, bc=["Periodic", "Periodic", "Wall", "Wall", "Periodic", "Periodic"])
+    with pytest.raises(RuntimeError):                     # poisson.f90:91-95 `stop`
+        fo.PoissonSolver(fo.Scalar(G, 0))
+
+
+# ---- test/small_test/poisson/projection/projection.f90:84-126 -------------------------------
+@pytest.mark.parametrize("case", ["ppp", "ppn"])
+def test_projection_divergence_free(case):
+    bc = ["Periodic"] * 6 if case == "ppp" else ["Periodic"] * 4 + ["Wall"] * 2
+    G = fo.Grid(32, 32, 32, 1.0, 1.0, 1.0, bc=bc)
+    v = fo.Vector(G, 1); div = fo.Scalar(G, 0); phi = fo.Scalar(G, 1); gphi = fo.Vector(G, 1)
+    if case == "ppn":
+        for f in ("front", "back"):
+            phi.bc_type[f] = 2
+            for c in v.comps:
+                c.bc_type[f] = 1
+    ps = fo.PoissonSolver(phi)
+    rng = np.random.default_rng(1234)
+    div_max = 0.0
+    for _ in range(10):                                   # reference: 100 draws
+        for c in v.comps:
+            c.I[...] = rng.random(G.shape)
+        v.update_ghost_nodes()
+        fo.divergence(v, div)
+        phi.I[...] = -div.I
+        ps.solve(phi)
+        phi.update_ghost_nodes()
+        fo.gradient(phi, gphi)
+        for c, g in zip(v.comps, gphi.comps):
+            c.f[...] = c.f + g.f
+        v.update_ghost_nodes()
+        fo.divergence(v, div)
+        div_max = max(div_max, abs(div.max_value()))
+    assert div_max <= 1e-11                               # projection.f90:125
+
+
+# ---- test/small_test/navier_stokes/advection/advection.f90:33-128 ---------------------------
+def test_advection_convergence():
+    N, e = [8, 16, 32, 64, 128], []
+    for n in N:
+        G = fo.Grid(n, n, 1, 2 * PI, 2 * PI, 2 * PI / n)
+        ns = fo.NavierStokes(G)
+        d = G.delta
+        i = np.arange(1, n + 1)[:, None, None]; j = np.arange(1, n + 1)[None, :, None]
+        ns.v.x.I[...] = np.sin(i * d) * np.cos((j - 0.5) * d)
+        ns.v.y.I[...] = -np.cos((i - 0.5) * d) * np.sin(j * d)
+        ns.v.update_ghost_nodes()
+        rhs = fo.Vector(G, 0)
+        ns.add_advection(rhs)
+        # -d(uu)/dx - d(uv)/dy for u = sin x cos y, v = -cos x sin y  ->  -sin x cos x
+        xu = i * d
+        ana = -np.sin(xu) * np.cos(xu) * np.ones((1, n, 1))
+        e.append(np.abs(rhs.x.I - ana).max())
+    assert _slope(N, e) > 1.8                            # advection/postpro.py:40
+
+
+# ---- test/small_test/navier_stokes/taylor_green_vortex ---------------------------------------
+def _tgv2d_error(n):
+    G = fo.Grid(n, n, 1, 2 * PI, 2 * PI, 2 * PI * fo._f32(1) / fo._f32(n))
+    ns = fo.NavierStokes(G)
+    fo.init_tgv2d(ns)
+    dt = ns.set_timestep(2.0)
+    t, step, md = 0.0, 0, 0.0
+    while t < 0.3:
+        step += 1
+        t += dt
+        dt = ns.navier_stokes_solver(step, dt)
+        md = max(md, abs(ns.maxdiv))
+    d = G.delta
+    i = np.arange(1, n + 1)[:, None]; j = np.arange(1, n + 1)[None, :]
+    sol = -np.cos(i * d) * np.sin((j - 0.5) * d) * math.exp(-2 * 0.3)   # postpro.py:48
+    u = ns.v.x.I[:, :, 0]
+    mask = sol > 1.0e-14
+    e = np.where(mask, np.abs(sol - u) / np.where(mask, sol, 1.0), 0.0)
+    return e.max(), md, step
+
+
+def test_tgv2d_convergence_config1_small():
+    """BASELINE config 1 at 16..128 (the full 16..256 sweep is the `slow` test below)."""
+    N = [16, 32, 64, 128]
+    res = [_tgv2d_error(n) for n in N]
+    assert all(r[1] < 1e-13 for r in res)                 # divergence at machine precision
+    assert _slope(N, [r[0] for r in res]) > 1.7
+
+
+@pytest.mark.slow
+def test_tgv2d_convergence_config1_full():
+    N = [16, 32, 64, 128, 256]
+    res = [_tgv2d_error(n) for n in N]
+    assert res[-1][2] == 3985
+    assert _slope(N, [r[0] for r in res]) > 1.8          # postpro.py:62 (measured: 1.83)
+
+
+# ---- test/small_test/navier_stokes/poiseuille ------------------------------------------------
+def test_poiseuille_convergence():
+    N, e = [8, 16, 32], []
+    for ny in N:
+        nx = 4
+        Ly = 1.0
+        Lx = Ly * fo._f32(nx) / fo._f32(ny)
+        G = fo.Grid(nx, ny, 1, Lx, Ly, Ly / ny, bc=["Periodic", "Periodic", "Wall", "Wall"])
+        ns = fo.NavierStokes(G)
+        ns.g[0] = 1.0
+        dt = ns.set_timestep(1.0)
+        uo = np.zeros_like(ns.v.x.f)
+        step = 0
+        while True:
+            step += 1
+            dt = ns.navier_stokes_solver(step, dt)
+            if (ns.v.x.f - uo).max() < 1e-8 and step > 2:
+                break
+            uo = ns.v.x.f.copy()
+            assert step < 200000
+        y = G.y[1:-1]
+        ana = 0.5 * y * (1.0 - y)                         # poiseuille/postpro.py:50
+        e.append(np.abs(ns.v.x.I[0, :, 0] - ana).max())
+    assert _slope(N, e) > 1.8                            # postpro.py:62
+
+
+# ---- test/large_test/ABC/ABC.f90 -------------------------------------------------------------
+def test_abc_flow_divergence_free_and_decay():
+    errs, N = [], [16, 32]
+    for n in N:
+        G = fo.Grid(n, n, n, 2 * PI, 2 * PI, 2 * PI)
+        ns = fo.NavierStokes(G)
+        ns.viscosity = 0.1                                 # ABC.f90:51 (set AFTER init_solver)
+        ns.mu.f[...] = 0.1                                 # later resolutions see mu = 0.1
+        dt = ns.set_timestep(2.0) / 2.0                    # ABC.f90:59-60
+        fo.init_abc(ns)
+        t, step = 0.0, 0
+        while t <= 0.1:
+            step += 1
+            t += dt
+            dt = ns.navier_stokes_solver(step, dt)
+            assert abs(ns.maxdiv) < 1e-12
+        x = G.x[1:-1, None, None]; y = G.y[None, 1:-1, None]; z = G.z[None, None, 1:-1]
+        xf = x + 0.5 * G.delta
+        ana = (np.sin(z) + np.cos(y) + 0 * xf) * math.exp(-0.1 * t)
+        errs.append(np.abs(ns.v.x.I - ana).max())
+    assert _slope(N, errs) > 1.5                          # ABC/postpro.py:42
+
+
+# ---- hazards ---------------------------------------------------------------------------------
+def test_ppn_zero_mode_pivot_is_exactly_zero():
+    """Hazard H5: the (0,0) Thomas pivot of the Neumann-folded system is exactly 0.0."""
+    for n in (16, 64, 128):
+        G = fo.Grid(n, n, n, 1.0, 1.0, 1.0, bc=["Periodic"] * 4 + ["Wall"] * 2)
+        ps = fo.PoissonSolver(fo.Scalar(G, 0))
+        a, b, c = ps.a, ps.b, ps.c
+        c1 = c[0] * (1.0 / (b[0] + ps.mwn_x[0] + ps.mwn_y[0]))
+        for k in range(1, n - 1):
+            c1 = c[k] * (1.0 / (b[k] + ps.mwn_x[0] + ps.mwn_y[0] - a[k] * c1))
+        assert b[n - 1] + ps.mwn_x[0] + ps.mwn_y[0] - a[n - 1] * c1 == 0.0
+
+
+def test_status_line_format():
+    G = fo.Grid(16, 16, 1, 1.0, 1.0, 1.0 / 16)
+    ns = fo.NavierStokes(G)
+    ns.maxdiv, ns.maxCFL = 1.5e-15, 0.25
+    line = ns.status_line(3, 0.125, 0.001)
+    assert line.startswith("step:       3 time:  0.125000E+00 dt:  0.100000E-02")
