@@ -1,0 +1,6 @@
+"""fen_b200 -- B200-native drop-in for FEN's fractional-step Navier-Stokes hot path.
+
+The product is ``libfen_gpu.so`` (hand-written sm_100a CUDA behind the C ABI of
+``include/fen_gpu.h``); this package is the thin host-side mirror of the reference's solver API."""
+from .api import (FenError, PoissonSolver, Solver, center_to_face, divergence, gradient, grid,  # noqa: F401
+                  laplacian, scalar, vector)

@@ -1,0 +1,576 @@
+// context.cu -- the C ABI of libfen_gpu.so (include/fen_gpu.h): context, field containers,
+// host<->device movement, module parameters and the navier_stokes_solver driver.
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+
+#include <algorithm>
+
+#include "fen_internal.cuh"
+
+namespace fen {
+
+static thread_local char g_err[512] = "";
+
+int set_error(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+int prof_begin(fen_ctx* c, const char* name) {
+    c->launches++;
+    if (!c->profiling) return -1;
+    int id = -1;
+    for (size_t i = 0; i < c->prof_names.size(); ++i)
+        if (c->prof_names[i] == name) { id = (int)i; break; }
+    if (id < 0) { id = (int)c->prof_names.size(); c->prof_names.push_back(name); }
+    ProfEntry e;
+    e.name_id = id;
+    cudaEventCreate(&e.e0);
+    cudaEventCreate(&e.e1);
+    cudaEventRecord(e.e0, c->stream);
+    c->prof_entries.push_back(e);
+    return (int)c->prof_entries.size() - 1;
+}
+void prof_end(fen_ctx* c, int token) {
+    if (token >= 0) cudaEventRecord(c->prof_entries[token].e1, c->stream);
+}
+
+int field_alloc(fen_ctx* c, Field& f) {
+    if (f.d) return FEN_OK;
+    FEN_CUDA(cudaMalloc(&f.d, c->L.elems * sizeof(double)));
+    FEN_CUDA(cudaMemsetAsync(f.d, 0, c->L.elems * sizeof(double), c->stream));   // scalar.f90:84
+    return FEN_OK;
+}
+
+static int fill_async(fen_ctx* c, double* d, double val);
+
+int field_check(fen_ctx* c, int id, Field** out, bool alloc) {
+    if (!c) return set_error(FEN_ERR_ARG, "null context");
+    if (id < 0 || id >= (int)c->fields.size() || !c->fields[id].exists)
+        return set_error(FEN_ERR_ARG, "unknown field id %d", id);
+    if (c->g.ndim == 2 && id < FEN_FIELD_USER && id >= FEN_VX && (id - FEN_VX) % 3 == 2)
+        return set_error(FEN_ERR_ARG, "z component (field %d) does not exist in 2-D (vector.f90:52-54)", id);
+    Field& f = c->fields[id];
+    if (alloc && !f.d) {
+        FEN_TRY(field_alloc(c, f));
+        // rho and mu are materialised lazily: they are uniform until the caller writes them
+        if (id == FEN_RHO) FEN_TRY(fill_async(c, f.d, c->rho_uniform));
+        if (id == FEN_MU) FEN_TRY(fill_async(c, f.d, c->mu_uniform));
+    }
+    *out = &f;
+    return FEN_OK;
+}
+
+__global__ void k_fill(double* d, size_t n, double v) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        d[i] = v;
+}
+static int fill_async(fen_ctx* c, double* d, double val) {
+    FEN_LAUNCH(c, "fill", k_fill<<<1184, 256, 0, c->stream>>>(d, c->L.elems, val));
+    FEN_CUDA(cudaGetLastError());
+    return FEN_OK;
+}
+
+static void free_field(Field& f) {
+    if (f.d) cudaFree(f.d);
+    f.d = nullptr;
+    for (int q = 0; q < 6; ++q) {
+        if (f.bc_plane[q]) cudaFree(f.bc_plane[q]);
+        f.bc_plane[q] = nullptr;
+        f.bc_mode[q] = BC_ZERO;
+        f.bc_value[q] = 0.0;
+    }
+}
+
+static void init_field(fen_ctx* c, int id, int gl, int loc) {
+    Field& f = c->fields[id];
+    free_field(f);
+    f.exists = true;
+    f.gl = gl;
+    f.loc = loc;
+    for (int q = 0; q < 6; ++q) f.bc_type[q] = FEN_PERIODIC;          // scalar.f90:109-116
+    if (c->g.nranks > 1 && c->g.ndim == 3) {                          // scalar.f90:125-128
+        if (c->g.rank > 0) f.bc_type[FEN_FRONT] = FEN_HALO;
+        if (c->g.rank < c->g.nranks - 1) f.bc_type[FEN_BACK] = FEN_HALO;
+    }
+}
+
+// copy between a Fortran-ordered host array with gl ghost layers and the padded device layout
+static int copy_field(fen_ctx* c, Field& f, double* host, int gl, bool to_device) {
+    if (gl != 0 && gl != 1) return set_error(FEN_ERR_ARG, "host ghost level must be 0 or 1 (got %d)", gl);
+    const Layout& L = c->L;
+    const size_t hx = (size_t)L.nx + 2 * gl, hy = (size_t)L.ny + 2 * gl, hz = (size_t)L.nzl + 2 * gl;
+    cudaMemcpy3DParms p;
+    memset(&p, 0, sizeof(p));
+    cudaPitchedPtr hp = make_cudaPitchedPtr(host, hx * sizeof(double), hx, hy);
+    cudaPitchedPtr dp = make_cudaPitchedPtr(f.d, (size_t)L.px * sizeof(double), (size_t)L.px, (size_t)L.ny + 2);
+    const cudaPos dpos = make_cudaPos((size_t)(L.xoff - gl) * sizeof(double), (size_t)(1 - gl), (size_t)(1 - gl));
+    if (to_device) {
+        p.srcPtr = hp; p.dstPtr = dp; p.dstPos = dpos; p.kind = cudaMemcpyHostToDevice;
+    } else {
+        p.srcPtr = dp; p.srcPos = dpos; p.dstPtr = hp; p.kind = cudaMemcpyDeviceToHost;
+    }
+    p.extent = make_cudaExtent(hx * sizeof(double), hy, hz);
+    FEN_CUDA(cudaMemcpy3DAsync(&p, c->stream));
+    return FEN_OK;
+}
+
+static const char* kFaceName[6] = {"left", "right", "bottom", "top", "front", "back"};
+
+// allocate_navier_stokes_fields BC wiring table, navier_stokes.f90:780-1017
+static void wire_bc(fen_ctx* c) {
+    const int nfaces = c->g.ndim == 3 ? 6 : 4;
+    for (int face = 0; face < nfaces; ++face) {
+        const int s = c->g.bc[face];
+        if (face == FEN_FRONT && s == FEN_BC_OUTFLOW) continue;   // not accepted (:961-987): stays 0
+        if (face == FEN_BACK && s == FEN_BC_INFLOW) continue;     // (:990-1016)
+        int tp, tr, tn, tt;
+        switch (s) {
+            case FEN_BC_PERIODIC: tp = 0; tr = 0; tn = 0; tt = 0; break;
+            case FEN_BC_WALL: tp = 2; tr = 2; tn = 1; tt = 1; break;
+            case FEN_BC_INFLOW: tp = 2; tr = 2; tn = 1; tt = (face <= FEN_RIGHT) ? 2 : 1; break;
+            case FEN_BC_OUTFLOW: tp = 1; tr = 2; tn = 2; tt = 2; break;
+            default:
+                fprintf(stderr, "ERROR: wrong bc on %s boundary\n", kFaceName[face]);   // :821
+                continue;
+        }
+        c->fields[FEN_P].bc_type[face] = tp;
+        c->fields[FEN_PHI].bc_type[face] = tp;
+        c->fields[FEN_RHO].bc_type[face] = tr;
+        c->fields[FEN_MU].bc_type[face] = tr;
+        for (int d = 0; d < c->g.ndim; ++d) c->fields[FEN_VX + d].bc_type[face] = (d == face / 2) ? tn : tt;
+    }
+    // rank-interior faces (:1044-1064)
+    if (c->g.nranks > 1 && c->g.ndim == 3) {
+        const int ids[7] = {FEN_P, FEN_PHI, FEN_RHO, FEN_MU, FEN_VX, FEN_VY, FEN_VZ};
+        for (int id : ids) {
+            if (c->g.rank > 0) c->fields[id].bc_type[FEN_FRONT] = FEN_HALO;
+            if (c->g.rank < c->g.nranks - 1) c->fields[id].bc_type[FEN_BACK] = FEN_HALO;
+        }
+    }
+}
+
+static int fetch_red(fen_ctx* c, int n) {
+    FEN_CUDA(cudaMemcpyAsync(c->h_red, c->d_red, n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    return FEN_OK;
+}
+
+}  // namespace fen
+
+using namespace fen;
+
+extern "C" {
+
+const char* fen_gpu_last_error(void) { return g_err; }
+int fen_gpu_version(void) { return 100; }
+
+int fen_gpu_create(const fen_grid_desc* d, fen_ctx** out) {
+    if (!d || !out) return set_error(FEN_ERR_ARG, "null argument");
+    *out = nullptr;
+    if (d->ndim != 2 && d->ndim != 3) return set_error(FEN_ERR_ARG, "ndim must be 2 or 3");
+    if (d->nx < 1 || d->ny < 1 || d->nz < 1) return set_error(FEN_ERR_ARG, "bad grid size");
+    if (d->ndim == 2 && d->nz != 1) return set_error(FEN_ERR_ARG, "2-D grids have nz = 1");
+    if (!(d->delta > 0.0)) return set_error(FEN_ERR_ARG, "delta must be positive");
+    if (d->nranks < 1 || d->rank < 0 || d->rank >= d->nranks) return set_error(FEN_ERR_ARG, "bad rank/nranks");
+    if (d->nranks > 1 && (d->ndim != 3 || d->nz % d->nranks))
+        return set_error(FEN_ERR_UNSUPPORTED, "slab decomposition needs ndim = 3 and nz divisible by nranks");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return set_error(FEN_ERR_CUDA, "no CUDA device: libfen_gpu has no CPU fallback (%s)",
+                         e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+    fen_ctx* c = new fen_ctx();
+    c->g = *d;
+    if (d->device >= 0) {
+        FEN_CUDA(cudaSetDevice(d->device));
+        c->device = d->device;
+    } else {
+        FEN_CUDA(cudaGetDevice(&c->device));
+    }
+    FEN_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    Layout& L = c->L;
+    L.nx = d->nx;
+    L.ny = d->ny;
+    L.nzl = d->nz / d->nranks;
+    L.xoff = 16;
+    L.px = (L.xoff + L.nx + 1 + 15) / 16 * 16;
+    L.sy = L.px;
+    L.sz = (long long)L.px * (L.ny + 2);
+    L.elems = (size_t)L.sz * (L.nzl + 2);
+    c->k0 = d->rank * L.nzl;
+    c->fields.resize(FEN_FIELD_USER);
+    c->prm.density = 1.0;                 // navier_stokes.f90:18
+    c->prm.viscosity = 1.0;
+    c->prm.g[0] = c->prm.g[1] = c->prm.g[2] = 0.0;     // :21
+    c->prm.CFL = 1.0;                     // :24
+    c->prm.dt_o = 0.0;
+    c->prm.constant_CFL = 0;              // :42
+    *out = c;
+    return FEN_OK;
+}
+
+int fen_gpu_destroy(fen_ctx* c) {
+    if (!c) return FEN_OK;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    poisson_destroy(c);
+    comm_destroy(c);
+    for (auto& f : c->fields) free_field(f);
+    for (int m = 0; m < 3; ++m) if (c->vnew[m]) cudaFree(c->vnew[m]);
+    if (c->d_red) cudaFree(c->d_red);
+    if (c->h_red) cudaFreeHost(c->h_red);
+    for (auto& e : c->prof_entries) { cudaEventDestroy(e.e0); cudaEventDestroy(e.e1); }
+    cudaStreamDestroy(c->stream);
+    delete c;
+    return FEN_OK;
+}
+
+int fen_gpu_synchronize(fen_ctx* c) {
+    if (!c) return set_error(FEN_ERR_ARG, "null context");
+    FEN_CUDA(cudaStreamSynchronize(c->stream));
+    return FEN_OK;
+}
+
+int fen_gpu_local_bounds(fen_ctx* c, int lo[3], int hi[3]) {
+    if (!c) return set_error(FEN_ERR_ARG, "null context");
+    lo[0] = 1; hi[0] = c->g.nx;
+    lo[1] = 1; hi[1] = c->g.ny;
+    lo[2] = c->k0 + 1; hi[2] = c->k0 + c->L.nzl;
+    return FEN_OK;
+}
+
+int fen_gpu_scalar_allocate(fen_ctx* c, int gl, int loc, int* field) {
+    if (!c || !field) return set_error(FEN_ERR_ARG, "null argument");
+    if (gl < 0 || gl > 1) return set_error(FEN_ERR_UNSUPPORTED, "only 0 or 1 ghost layers are supported");
+    if (loc < FEN_LOC_C || loc > FEN_LOC_Z) return set_error(FEN_ERR_ARG, "bad location tag");
+    int id = -1;
+    for (int i = FEN_FIELD_USER; i < (int)c->fields.size(); ++i)
+        if (!c->fields[i].exists) { id = i; break; }
+    if (id < 0) { id = (int)c->fields.size(); c->fields.emplace_back(); }
+    init_field(c, id, gl, loc);
+    FEN_TRY(field_alloc(c, c->fields[id]));
+    *field = id;
+    return FEN_OK;
+}
+
+int fen_gpu_scalar_destroy(fen_ctx* c, int id) {
+    Field* f;
+    FEN_TRY(field_check(c, id, &f, false));
+    if (id < FEN_FIELD_USER) return set_error(FEN_ERR_ARG, "solver fields are freed by destroy_solver");
+    FEN_CUDA(cudaStreamSynchronize(c->stream));
+    free_field(*f);
+    f->exists = false;
+    return FEN_OK;
+}
+
+int fen_gpu_push(fen_ctx* c, int id, const double* host, int gl) {
+    Field* f;
+    FEN_TRY(field_check(c, id, &f));
+    if (!host) return set_error(FEN_ERR_ARG, "null host pointer");
+    FEN_TRY(copy_field(c, *f, const_cast<double*>(host), gl, true));
+    if (id == FEN_RHO || id == FEN_MU) {
+        // hazard H11: rho / mu are fields; keep the uniform fast path only if what was pushed is uniform
+        bool ur, um;
+        double vr, vm;
+        Field *fr, *fm;
+        FEN_TRY(field_check(c, FEN_RHO, &fr));
+        FEN_TRY(field_check(c, FEN_MU, &fm));
+        FEN_TRY(field_is_uniform(c, fr->d, &ur, &vr));
+        FEN_TRY(field_is_uniform(c, fm->d, &um, &vm));
+        c->uniform_props = ur && um;
+        if (ur) c->rho_uniform = vr;
+        if (um) c->mu_uniform = vm;
+    }
+    if (id >= FEN_SX && id <= FEN_SZ) c->has_source = true;
+    return FEN_OK;
+}
+
+int fen_gpu_pull(fen_ctx* c, int id, double* host, int gl) {
+    Field* f;
+    FEN_TRY(field_check(c, id, &f));
+    if (!host) return set_error(FEN_ERR_ARG, "null host pointer");
+    FEN_TRY(copy_field(c, *f, host, gl, false));
+    FEN_CUDA(cudaStreamSynchronize(c->stream));
+    return FEN_OK;
+}
+
+int fen_gpu_set_to_value(fen_ctx* c, int id, double val) {
+    Field* f;
+    if ((id == FEN_RHO || id == FEN_MU) && c && c->uniform_props) {
+        FEN_TRY(field_check(c, id, &f, false));
+        (id == FEN_RHO ? c->rho_uniform : c->mu_uniform) = val;
+        if (!f->d) return FEN_OK;
+    }
+    FEN_TRY(field_check(c, id, &f));
+    if (id >= FEN_SX && id <= FEN_SZ && val != 0.0) c->has_source = true;
+    return fill_async(c, f->d, val);
+}
+
+int fen_gpu_set_bc_type(fen_ctx* c, int id, int face, int type) {
+    Field* f;
+    FEN_TRY(field_check(c, id, &f, false));
+    if (face < 0 || face > 5 || type < -1 || type > 2) return set_error(FEN_ERR_ARG, "bad face or bc type");
+    f->bc_type[face] = type;
+    return FEN_OK;
+}
+
+int fen_gpu_get_bc_type(fen_ctx* c, int id, int face, int* type) {
+    Field* f;
+    FEN_TRY(field_check(c, id, &f, false));
+    if (face < 0 || face > 5 || !type) return set_error(FEN_ERR_ARG, "bad face");
+    *type = f->bc_type[face];
+    return FEN_OK;
+}
+
+int fen_gpu_set_bc_plane(fen_ctx* c, int id, int face, const double* plane, int uniform) {
+    Field* f;
+    FEN_TRY(field_check(c, id, &f, false));
+    if (face < 0 || face > 5) return set_error(FEN_ERR_ARG, "bad face");
+    if (!plane) { f->bc_mode[face] = BC_ZERO; return FEN_OK; }
+    if (uniform) { f->bc_mode[face] = BC_UNIFORM; f->bc_value[face] = plane[0]; return FEN_OK; }
+    const Layout& L = c->L;
+    const size_t n0 = (face < 2) ? L.ny + 2 : L.nx + 2;
+    const size_t n1 = (face < 4) ? L.nzl + 2 : L.ny + 2;
+    if (!f->bc_plane[face]) FEN_CUDA(cudaMalloc(&f->bc_plane[face], n0 * n1 * sizeof(double)));
+    FEN_CUDA(cudaMemcpyAsync(f->bc_plane[face], plane, n0 * n1 * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    FEN_CUDA(cudaStreamSynchronize(c->stream));
+    f->bc_mode[face] = BC_PLANE;
+    return FEN_OK;
+}
+
+int fen_gpu_update_ghost_nodes(fen_ctx* c, int id, int ncomp) {
+    if (!c) return set_error(FEN_ERR_ARG, "null context");
+    return ghost_update(c, id, ncomp);
+}
+
+int fen_gpu_update_halos(fen_ctx* c, int id) {
+    Field* f;
+    FEN_TRY(field_check(c, id, &f));
+    if (c->g.nranks == 1) return FEN_OK;     // halo.f90 is only compiled with -DMPI
+    double* p[1] = {f->d};
+    return halo_exchange(c, p, 1);
+}
+
+int fen_gpu_max_value(fen_ctx* c, int id, double* out) {
+    Field* f;
+    FEN_TRY(field_check(c, id, &f));
+    FEN_TRY(reduce_field(c, f->d, 0, c->d_red));
+    if (c->g.nranks > 1) FEN_TRY(comm_allreduce(c, c->d_red, 1, 0));      // scalar.f90:194
+    FEN_TRY(fetch_red(c, 1));
+    FEN_CUDA(cudaStreamSynchronize(c->stream));
+    *out = c->h_red[0];
+    return FEN_OK;
+}
+
+int fen_gpu_integral(fen_ctx* c, int id, double* out) {
+    Field* f;
+    FEN_TRY(field_check(c, id, &f));
+    FEN_TRY(reduce_field(c, f->d, 1, c->d_red));
+    if (c->g.nranks > 1) FEN_TRY(comm_allreduce(c, c->d_red, 1, 1));      // scalar.f90:214
+    FEN_TRY(fetch_red(c, 1));
+    FEN_CUDA(cudaStreamSynchronize(c->stream));
+    const double d = c->g.delta;
+    *out = c->h_red[0] * (d * d * d);                                      // scalar.f90:217
+    return FEN_OK;
+}
+
+int fen_gpu_gradient(fen_ctx* c, int s, int vx) { return c ? op_gradient(c, s, vx) : set_error(FEN_ERR_ARG, "null context"); }
+int fen_gpu_divergence(fen_ctx* c, int vx, int s) { return c ? op_divergence(c, vx, s) : set_error(FEN_ERR_ARG, "null context"); }
+int fen_gpu_laplacian(fen_ctx* c, int vx, int ox) { return c ? op_laplacian(c, vx, ox) : set_error(FEN_ERR_ARG, "null context"); }
+int fen_gpu_center_to_face(fen_ctx* c, int s, int vx) { return c ? op_center_to_face(c, s, vx) : set_error(FEN_ERR_ARG, "null context"); }
+
+int fen_gpu_init_poisson_solver(fen_ctx* c) { return c ? poisson_init(c) : set_error(FEN_ERR_ARG, "null context"); }
+int fen_gpu_solve_poisson(fen_ctx* c, int id) {
+    Field* f;
+    FEN_TRY(field_check(c, id, &f));
+    return poisson_solve(c, f->d);
+}
+int fen_gpu_destroy_poisson_solver(fen_ctx* c) {
+    if (!c) return set_error(FEN_ERR_ARG, "null context");
+    cudaStreamSynchronize(c->stream);
+    poisson_destroy(c);
+    return FEN_OK;
+}
+const char* fen_gpu_poisson_variant(fen_ctx* c) { return c ? poisson_variant(c) : ""; }
+
+int fen_gpu_init_solver(fen_ctx* c) {
+    if (!c) return set_error(FEN_ERR_ARG, "null context");
+    // allocate_navier_stokes_fields, navier_stokes.f90:759-768 (device memory is committed lazily)
+    const int gl1[] = {FEN_P, FEN_PHI, FEN_RHO, FEN_MU, FEN_VX, FEN_VY, FEN_VZ};
+    for (int id : gl1) {
+        int loc = FEN_LOC_C;
+        if (id >= FEN_VX) loc = FEN_LOC_X + (id - FEN_VX);
+        init_field(c, id, 1, loc);
+    }
+    for (int id = FEN_DVX; id <= FEN_SZ; ++id) init_field(c, id, 0, FEN_LOC_X + (id - FEN_DVX) % 3);
+    c->rho_uniform = c->prm.density;       // rho%f = density   (:774)
+    c->mu_uniform = c->prm.viscosity;      // mu%f  = viscosity (:775)
+    c->uniform_props = true;
+    c->has_source = false;
+    wire_bc(c);
+    int r = poisson_init(c);               // solver.f90:61
+    if (r != FEN_OK) return r;
+    c->solver_init = true;
+    return FEN_OK;
+}
+
+int fen_gpu_destroy_solver(fen_ctx* c) {
+    if (!c) return set_error(FEN_ERR_ARG, "null context");
+    cudaStreamSynchronize(c->stream);
+    poisson_destroy(c);
+    for (int id = 0; id < FEN_FIELD_USER; ++id) { free_field(c->fields[id]); c->fields[id].exists = false; }
+    for (int m = 0; m < 3; ++m) { if (c->vnew[m]) cudaFree(c->vnew[m]); c->vnew[m] = nullptr; }
+    c->solver_init = false;
+    return FEN_OK;
+}
+
+int fen_gpu_get_params(fen_ctx* c, fen_ns_params* p) {
+    if (!c || !p) return set_error(FEN_ERR_ARG, "null argument");
+    *p = c->prm;
+    return FEN_OK;
+}
+int fen_gpu_set_params(fen_ctx* c, const fen_ns_params* p) {
+    if (!c || !p) return set_error(FEN_ERR_ARG, "null argument");
+    c->prm = *p;
+    return FEN_OK;
+}
+
+int fen_gpu_set_timestep(fen_ctx* c, double U, double* dt) {
+    if (!c || !dt) return set_error(FEN_ERR_ARG, "null argument");
+    const double d = c->g.delta;
+    fen_ns_params& p = c->prm;
+    p.dt_conv = p.CFL * d / U;                                            // navier_stokes.f90:641
+    p.dt_visc = 0.125 * d * d * p.density / p.viscosity;                  // :644
+    if (c->g.ndim == 3) p.dt_visc = (1.0 / 6.0) * d * d * p.density / p.viscosity;   // :650
+    *dt = std::min(p.dt_conv, p.dt_visc);                                 // :662
+    p.dt_o = *dt;                                                         // :664
+    return FEN_OK;
+}
+
+static int update_timestep(fen_ctx* c, double* dt) {
+    // navier_stokes.f90:670-730
+    fen_ns_params& p = c->prm;
+    p.dt_o = *dt;
+    FEN_TRY(ns_checks_launch(c, *dt));
+    FEN_TRY(fetch_red(c, 2));
+    FEN_CUDA(cudaStreamSynchronize(c->stream));
+    const double max_vel = std::max(0.0, c->h_red[1]);
+    p.dt_conv = max_vel > 0.0 ? p.CFL * c->g.delta / max_vel : 1.0;
+    *dt = std::min(p.dt_conv, p.dt_visc);
+    if (*dt > 1.1 * p.dt_o) *dt = 1.1 * p.dt_o;
+    return FEN_OK;
+}
+
+int fen_gpu_predicted_velocity_field(fen_ctx* c, double dt) {
+    if (!c || !c->solver_init) return set_error(FEN_ERR_STATE, "init_solver has not been called");
+    return ns_predict(c, dt);
+}
+int fen_gpu_correct_velocity_field(fen_ctx* c, double dt) {
+    if (!c || !c->solver_init) return set_error(FEN_ERR_STATE, "init_solver has not been called");
+    // correct_velocity_field + update_pressure share one kernel; see fen_gpu_update_pressure
+    return ns_correct(c, dt);
+}
+int fen_gpu_update_pressure(fen_ctx* c) {
+    if (!c || !c->solver_init) return set_error(FEN_ERR_STATE, "init_solver has not been called");
+    return FEN_OK;   // fused into correct_velocity_field (p += phi, then ghost update)
+}
+int fen_gpu_checks(fen_ctx* c, double dt) {
+    if (!c || !c->solver_init) return set_error(FEN_ERR_STATE, "init_solver has not been called");
+    FEN_TRY(ns_checks_launch(c, dt));
+    c->last_dt = dt;
+    return fetch_red(c, 2);
+}
+
+int fen_gpu_navier_stokes_solver(fen_ctx* c, int step, double* dt) {
+    (void)step;
+    if (!c || !dt) return set_error(FEN_ERR_ARG, "null argument");
+    if (!c->solver_init) return set_error(FEN_ERR_STATE, "init_solver has not been called");
+    if (!(c->prm.dt_o > 0.0)) return set_error(FEN_ERR_STATE, "dt_o is not set: call set_timestep first");
+    if (c->prm.constant_CFL) FEN_TRY(update_timestep(c, dt));             // navier_stokes.f90:78
+    FEN_TRY(ns_predict(c, *dt));                                          // :105
+    FEN_TRY(ns_poisson_rhs(c, *dt));                                      // :111-121
+    Field* phi;
+    FEN_TRY(field_check(c, FEN_PHI, &phi));
+    FEN_TRY(poisson_solve(c, phi->d));                                    // :123
+    FEN_TRY(ghost_update(c, FEN_PHI, 1));                                 // :124
+    FEN_TRY(ns_correct(c, *dt));                                          // :127, :130
+    FEN_TRY(ns_checks_launch(c, *dt));                                    // :134
+    c->last_dt = *dt;
+    return fetch_red(c, 2);
+}
+
+int fen_gpu_get_status(fen_ctx* c, double* maxdiv, double* maxCFL) {
+    if (!c) return set_error(FEN_ERR_ARG, "null context");
+    FEN_CUDA(cudaStreamSynchronize(c->stream));
+    if (c->h_red) {
+        c->maxdiv = c->h_red[0];
+        c->maxCFL = c->last_dt * std::max(0.0, c->h_red[1]) / c->g.delta;    // navier_stokes.f90:617
+    }
+    if (maxdiv) *maxdiv = c->maxdiv;
+    if (maxCFL) *maxCFL = c->maxCFL;
+    return FEN_OK;
+}
+
+int fen_gpu_status_line(fen_ctx* c, int step, double time, double dt, char* buf, int buflen) {
+    double md, mc;
+    FEN_TRY(fen_gpu_get_status(c, &md, &mc));
+    // format 10: A6,I7,1x,A6,E13.6,1x,A4,E13.6,1x,A8,E13.6,1x,A9,1x,E13.6 (navier_stokes.f90:746)
+    auto e13 = [](double x, char* o) {
+        if (x == 0.0) { snprintf(o, 16, "%13s", "0.000000E+00"); return; }
+        int ex = (int)floor(log10(fabs(x))) + 1;
+        double man = x / pow(10.0, ex);
+        if (fabs(round(man * 1e6) / 1e6) >= 1.0) { man /= 10.0; ex += 1; }
+        char t[32];
+        snprintf(t, sizeof(t), "%s0.%06lldE%+03d", man < 0 ? "-" : "", (long long)llround(fabs(man) * 1e6), ex);
+        snprintf(o, 16, "%13s", t);
+    };
+    char a[16], b[16], d[16], e[16];
+    e13(time, a); e13(dt, b); e13(md, d); e13(mc, e);
+    snprintf(buf, buflen, "step: %7d time: %s dt: %s maxdiv: %s maxCFL:  %s", step, a, b, d, e);
+    return FEN_OK;
+}
+
+int fen_gpu_add_advection(fen_ctx* c, int rhs_x) {
+    if (!c || !c->solver_init) return set_error(FEN_ERR_STATE, "init_solver has not been called");
+    return op_explicit_terms(c, rhs_x, true);
+}
+int fen_gpu_compute_explicit_terms(fen_ctx* c, int rhs_x) {
+    if (!c || !c->solver_init) return set_error(FEN_ERR_STATE, "init_solver has not been called");
+    return op_explicit_terms(c, rhs_x, false);
+}
+
+int fen_gpu_profile_enable(fen_ctx* c, int on) {
+    if (!c) return set_error(FEN_ERR_ARG, "null context");
+    cudaStreamSynchronize(c->stream);
+    for (auto& e : c->prof_entries) { cudaEventDestroy(e.e0); cudaEventDestroy(e.e1); }
+    c->prof_entries.clear();
+    c->profiling = on != 0;
+    return FEN_OK;
+}
+
+int fen_gpu_profile_read(fen_ctx* c, int max_entries, char names[][32], double* ms, int* launches, int* n_out) {
+    if (!c || !n_out) return set_error(FEN_ERR_ARG, "null argument");
+    FEN_CUDA(cudaStreamSynchronize(c->stream));
+    const int n = std::min<int>(max_entries, (int)c->prof_names.size());
+    for (int i = 0; i < n; ++i) {
+        snprintf(names[i], 32, "%s", c->prof_names[i].c_str());
+        ms[i] = 0.0;
+        launches[i] = 0;
+    }
+    for (auto& e : c->prof_entries) {
+        if (e.name_id >= n) continue;
+        float t = 0.f;
+        if (cudaEventElapsedTime(&t, e.e0, e.e1) == cudaSuccess) { ms[e.name_id] += t; launches[e.name_id]++; }
+    }
+    *n_out = n;
+    return FEN_OK;
+}
+
+long long fen_gpu_launch_count(fen_ctx* c) { return c ? c->launches : 0; }
+void* fen_gpu_stream(fen_ctx* c) { return c ? (void*)c->stream : nullptr; }
+
+}  // extern "C"

@@ -1,0 +1,141 @@
+// fen_internal.cuh -- internal types of libfen_gpu.so (not part of the C ABI).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/fen_gpu.h"
+
+namespace fen {
+
+// ---------------------------------------------------------------------------------------------
+// Device layout of every real field (HBM): the reference's ghosted x-pencil array
+// f(0:Nx+1, 0:Ny+1, lo3-1:hi3+1) (src/scalar.f90:79-81) with the x rows padded so that the first
+// INTERIOR element of every row sits on a 128-byte boundary:
+//     element (i, j, k), i in [0, nx+1], j in [0, ny+1], k in [0, nzl+1]  (k local to the slab)
+//     lives at  (xoff - 1 + i) + px * (j + (ny + 2) * k),   xoff = 16, px = roundup(xoff+nx+1, 16)
+// Fields the reference allocates without ghosts (gl = 0) use the same layout; their ghost cells
+// are simply never read.
+// ---------------------------------------------------------------------------------------------
+struct Layout {
+    int nx, ny, nzl;
+    int px, xoff;
+    long long sy, sz;
+    size_t elems;
+    __host__ __device__ __forceinline__ long long idx(int i, int j, int k) const {
+        return (long long)(xoff - 1 + i) + sy * j + sz * k;
+    }
+};
+
+enum BcMode { BC_ZERO = 0, BC_UNIFORM = 1, BC_PLANE = 2 };
+
+struct Field {
+    double* d = nullptr;
+    int gl = 0;
+    int loc = FEN_LOC_C;
+    bool exists = false;       // id handed out
+    int bc_type[6] = {0, 0, 0, 0, 0, 0};
+    int bc_mode[6] = {0, 0, 0, 0, 0, 0};
+    double bc_value[6] = {0, 0, 0, 0, 0, 0};
+    double* bc_plane[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+};
+
+struct ProfEntry {
+    int name_id;
+    cudaEvent_t e0, e1;
+};
+
+struct Poisson;   // poisson.cu
+struct Comm;      // comm.cu
+
+}  // namespace fen
+
+struct fen_ctx {
+    fen_grid_desc g{};
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    fen::Layout L{};
+    int k0 = 0;                 // global index of local plane k = 1 minus 1 (lo(3) - 1)
+    std::vector<fen::Field> fields;
+
+    // navier_stokes_mod state
+    bool solver_init = false;
+    fen_ns_params prm{};
+    double rho_uniform = 1.0, mu_uniform = 1.0;   // value of rho%f / mu%f while they are uniform
+    bool uniform_props = true;                    // rho and mu are uniform fields (hazard H11)
+    bool has_source = false;                      // S was written by the caller
+    double* vnew[3] = {nullptr, nullptr, nullptr};   // predictor output (ping-pong with v)
+    double maxdiv = 0.0, maxCFL = 0.0;
+    double last_dt = 0.0;
+    double* d_red = nullptr;     // device scratch for reductions (partials + results)
+    double* h_red = nullptr;     // pinned host mirror of the results
+    int red_blocks = 0;
+
+    fen::Poisson* ps = nullptr;
+    fen::Comm* comm = nullptr;
+
+    // measurement
+    long long launches = 0;
+    bool profiling = false;
+    std::vector<std::string> prof_names;
+    std::vector<fen::ProfEntry> prof_entries;
+};
+
+namespace fen {
+
+int set_error(int code, const char* fmt, ...);
+#define FEN_CUDA(call)                                                                       \
+    do {                                                                                     \
+        cudaError_t e__ = (call);                                                            \
+        if (e__ != cudaSuccess)                                                              \
+            return fen::set_error(FEN_ERR_CUDA, "%s failed: %s (%s:%d)", #call,              \
+                                  cudaGetErrorString(e__), __FILE__, __LINE__);              \
+    } while (0)
+#define FEN_TRY(call)                 \
+    do {                              \
+        int r__ = (call);             \
+        if (r__ != FEN_OK) return r__; \
+    } while (0)
+
+// RAII-less launch bracket: counts launches and, when profiling, brackets the launch with events.
+int prof_begin(fen_ctx* c, const char* name);
+void prof_end(fen_ctx* c, int token);
+#define FEN_LAUNCH(ctx, name, ...)               \
+    do {                                         \
+        int tok__ = fen::prof_begin(ctx, name);  \
+        __VA_ARGS__;                             \
+        fen::prof_end(ctx, tok__);               \
+    } while (0)
+
+int field_check(fen_ctx* c, int id, Field** out, bool alloc = true);
+int field_alloc(fen_ctx* c, Field& f);
+
+// ghost.cu
+int ghost_update(fen_ctx* c, int field, int ncomp);
+// comm.cu
+int halo_exchange(fen_ctx* c, double* const* f, int n);
+int comm_allreduce(fen_ctx* c, double* d_vals, int n, int op /*0 max, 1 sum*/);
+void comm_destroy(fen_ctx* c);
+int comm_transpose_fwd(fen_ctx* c);   // y-slab spectral layout -> z-pencil
+int comm_transpose_bwd(fen_ctx* c);
+// stencil.cu
+int ns_predict(fen_ctx* c, double dt);
+int ns_poisson_rhs(fen_ctx* c, double dt);
+int ns_correct(fen_ctx* c, double dt);
+int ns_checks_launch(fen_ctx* c, double dt);    // leaves (maxdiv, maxvel) in d_red[0..1]
+int op_gradient(fen_ctx* c, int s, int vx);
+int op_divergence(fen_ctx* c, int vx, int s);
+int op_laplacian(fen_ctx* c, int vx, int ox);
+int op_center_to_face(fen_ctx* c, int s, int vx);
+int op_explicit_terms(fen_ctx* c, int rhs_x, bool advection_only);
+int reduce_field(fen_ctx* c, const double* f, int op, double* d_out);   // op 0 max, 1 sum
+int field_is_uniform(fen_ctx* c, const double* f, bool* uniform, double* value);
+// poisson.cu
+int poisson_init(fen_ctx* c);
+int poisson_solve(fen_ctx* c, double* f);
+void poisson_destroy(fen_ctx* c);
+const char* poisson_variant(fen_ctx* c);
+
+}  // namespace fen

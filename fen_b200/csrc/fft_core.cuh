@@ -1,0 +1,158 @@
+// fft_core.cuh -- shared-memory Stockham FFT building blocks (fp64 complex, power-of-two lengths).
+//
+// Replaces FFTW's 1-D plans executed line by line in the reference (src/poisson.f90:148-151,
+// 635-674; executes :967,977,987,1010,1020,1030): unnormalised transforms, forward sign -1.
+//
+// A block transforms NL lines of length L that live in shared memory as s[idx * IS + line]
+// (IS >= NL, chosen so that both "8 threads = 8 lines, same idx" and "8 threads = 8 consecutive
+// idx, same line" are bank-conflict free: IS = 8 for strided lines, 9 for contiguous rows).
+// Each line is worked on by T = max(L/8, 1) threads; every stage is an autosort (Stockham)
+// radix-R pass:  read R inputs at stride L/R -> twiddle -> radix-R butterfly -> write at
+// stride Ns.  Reads and writes of one stage are separated by a block barrier, so the pass is
+// done in place.
+//
+// The functions are __host__ __device__ so that tests/cpu/test_fft_core.cu can run the same
+// index logic on the CPU (threads emulated by loops, barriers by phase boundaries).
+#pragma once
+#include <cuda_runtime.h>
+
+#ifndef FEN_HD
+#define FEN_HD __host__ __device__ __forceinline__
+#endif
+
+namespace fen {
+
+FEN_HD double2 cadd(double2 a, double2 b) { return make_double2(a.x + b.x, a.y + b.y); }
+FEN_HD double2 csub(double2 a, double2 b) { return make_double2(a.x - b.x, a.y - b.y); }
+FEN_HD double2 cmul(double2 a, double2 b) {
+    return make_double2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+}
+FEN_HD double2 cconj(double2 a) { return make_double2(a.x, -a.y); }
+// multiply by -i (DIR = -1, forward) or +i (DIR = +1, inverse)
+template <int DIR> FEN_HD double2 rot90(double2 a) {
+    return DIR < 0 ? make_double2(a.y, -a.x) : make_double2(-a.y, a.x);
+}
+template <int DIR> FEN_HD double2 twid(double2 w) { return DIR < 0 ? w : cconj(w); }
+
+// ---- radix butterflies (in registers) ------------------------------------------------------
+template <int DIR> FEN_HD void bfly2(double2& a, double2& b) {
+    double2 t = a;
+    a = cadd(t, b);
+    b = csub(t, b);
+}
+template <int DIR> FEN_HD void bfly4(double2& a0, double2& a1, double2& a2, double2& a3) {
+    // X[k] = sum_n a_n w^(nk), w = exp(DIR * 2 pi i / 4)
+    double2 s02 = cadd(a0, a2), d02 = csub(a0, a2);
+    double2 s13 = cadd(a1, a3), d13 = rot90<DIR>(csub(a1, a3));
+    a0 = cadd(s02, s13);
+    a2 = csub(s02, s13);
+    a1 = cadd(d02, d13);
+    a3 = csub(d02, d13);
+}
+template <int DIR> FEN_HD void bfly8(double2 (&v)[8]) {
+    const double h = 0.70710678118654752440;
+    // first layer: pairs (n, n+4)
+    double2 a0 = cadd(v[0], v[4]), b0 = csub(v[0], v[4]);
+    double2 a1 = cadd(v[1], v[5]), b1 = csub(v[1], v[5]);
+    double2 a2 = cadd(v[2], v[6]), b2 = csub(v[2], v[6]);
+    double2 a3 = cadd(v[3], v[7]), b3 = csub(v[3], v[7]);
+    // twiddles w8^n on the odd half: w8 = exp(DIR * i pi/4)
+    // b1 *= (1 + DIR*i) h ; b2 *= DIR*i ; b3 *= (-1 + DIR*i) h
+    b1 = DIR < 0 ? make_double2((b1.x + b1.y) * h, (b1.y - b1.x) * h)
+                 : make_double2((b1.x - b1.y) * h, (b1.y + b1.x) * h);
+    b2 = rot90<DIR>(b2);
+    b3 = DIR < 0 ? make_double2((b3.y - b3.x) * h, -(b3.x + b3.y) * h)
+                 : make_double2(-(b3.x + b3.y) * h, (b3.x - b3.y) * h);
+    bfly4<DIR>(a0, a1, a2, a3);   // even outputs 0,2,4,6
+    bfly4<DIR>(b0, b1, b2, b3);   // odd outputs 1,3,5,7
+    v[0] = a0; v[2] = a1; v[4] = a2; v[6] = a3;
+    v[1] = b0; v[3] = b1; v[5] = b2; v[7] = b3;
+}
+template <int R, int DIR> FEN_HD void bfly(double2 (&v)[R]) {
+    if constexpr (R == 2) bfly2<DIR>(v[0], v[1]);
+    if constexpr (R == 4) bfly4<DIR>(v[0], v[1], v[2], v[3]);
+    if constexpr (R == 8) bfly8<DIR>(v);
+}
+
+// ---- plan: radices per length -----------------------------------------------------------------
+template <int L> struct FftPlan {
+    static constexpr int T = (L >= 8) ? L / 8 : 1;          // threads per line
+    static constexpr int LOG2 = (L <= 1) ? 0 : 1 + FftPlan<L / 2>::LOG2;
+    static constexpr int N8 = (L >= 8) ? LOG2 / 3 : 0;      // number of radix-8 stages
+    static constexpr int REM = (L >= 8) ? (1 << (LOG2 - 3 * N8)) : L;   // trailing radix 1,2,4
+};
+template <> struct FftPlan<0> { static constexpr int LOG2 = 0; };
+
+// One Stockham stage, split at the barrier: load phase then compute+store phase.
+// v must hold 8 complex values (T threads x 8 = L elements).  For L < 8 only R = L values are used.
+template <int L, int R, int DIR>
+FEN_HD void stage_load(double2* v, const double2* s, int IS, int line, int t) {
+    constexpr int T = FftPlan<L>::T;
+    constexpr int NB = (L / R) / T;     // butterflies per thread
+#pragma unroll
+    for (int b = 0; b < NB; ++b) {
+        int j = t + b * T;
+#pragma unroll
+        for (int r = 0; r < R; ++r) v[b * R + r] = s[(j + r * (L / R)) * IS + line];
+    }
+}
+template <int L, int R, int DIR>
+FEN_HD void stage_store(double2* v, double2* s, int IS, int line, int t, int Ns, const double2* tw) {
+    constexpr int T = FftPlan<L>::T;
+    constexpr int NB = (L / R) / T;
+#pragma unroll
+    for (int b = 0; b < NB; ++b) {
+        int j = t + b * T;
+        int k = j & (Ns - 1);
+        double2 w[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) w[r] = v[b * R + r];
+        if (Ns > 1) {
+            int step = k * (L / (Ns * R));          // twiddle index of r = 1 in the length-L table
+#pragma unroll
+            for (int r = 1; r < R; ++r) {
+#ifdef __CUDA_ARCH__
+                double2 c = __ldg(&tw[step * r]);
+#else
+                double2 c = tw[step * r];
+#endif
+                w[r] = cmul(w[r], twid<DIR>(c));
+            }
+        }
+        bfly<R, DIR>(w);
+        int j0 = (j - k) * R + k;
+#pragma unroll
+        for (int r = 0; r < R; ++r) s[(j0 + r * Ns) * IS + line] = w[r];
+    }
+}
+
+// Full in-place transform of the block's lines (device only: every thread of the block must call
+// it, `active` false for threads that own no line so that barriers stay uniform).
+#ifdef __CUDACC__
+template <int L, int DIR>
+__device__ __forceinline__ void fft_lines(double2* s, int IS, int line, int t, bool active,
+                                          const double2* tw) {
+    if constexpr (L <= 1) return;
+    double2 v[8];
+    int Ns = 1;
+    if constexpr (L >= 8) {
+#pragma unroll
+        for (int st = 0; st < FftPlan<L>::N8; ++st) {
+            if (active) stage_load<L, 8, DIR>(v, s, IS, line, t);
+            __syncthreads();
+            if (active) stage_store<L, 8, DIR>(v, s, IS, line, t, Ns, tw);
+            __syncthreads();
+            Ns *= 8;
+        }
+    }
+    constexpr int REM = FftPlan<L>::REM;
+    if constexpr (REM > 1) {
+        if (active) stage_load<L, REM, DIR>(v, s, IS, line, t);
+        __syncthreads();
+        if (active) stage_store<L, REM, DIR>(v, s, IS, line, t, Ns, tw);
+        __syncthreads();
+    }
+}
+#endif
+
+}  // namespace fen

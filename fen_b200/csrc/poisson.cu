@@ -1,0 +1,636 @@
+// poisson.cu -- FEN's fast direct Poisson solver (src/poisson.f90) as hand-written sm_100a kernels.
+//
+// Reference pipeline (ppp, poisson.f90:941-1034): FFTW r2c along x line by line -> 2decomp
+// transpose -> c2c along y -> transpose -> c2c along z -> scale, divide by the modified
+// wavenumbers -> inverse chain.  ppn (:1038-1173) replaces the z transforms by a Thomas solve and
+// removes the mean.  2-D variants pp (:416-505) / pn (:306-412) are the same with nz = 1.
+//
+// Here the spectral field lives in ONE half-spectrum work array
+//     C[kx + PC * (j + ny * k)],  kx in [0, nx/2],  PC = roundup(nx/2 + 1, 8)  (128-byte rows)
+// and every pass reads it once and writes it once:
+//     k_fft_x_r2c     rows of the real field -> C          (x contiguous; 8 rows per block)
+//     k_fft_lines     c2c along y or z, in place           (strided lines; 8 kx = 128 B per block,
+//                                                            so the 2decomp x<->y / y<->z transposes
+//                                                            of the reference disappear on one GPU)
+//     k_fft_solve     forward c2c + spectral divide + inverse c2c along the last direction, fused
+//     k_thomas_fwd/bwd  Thomas algorithm along the last direction, one thread per (kx, j) system,
+//                     with the reference's operation order and no FMA contraction so that the
+//                     exactly-zero pivot of the singular mode (hazard H5) is preserved
+//     k_fft_x_c2r     C -> rows of the real field
+// cuFFT is not used here (tests/ cross-check against numpy/scipy and, on the GPU box, cuFFT).
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+
+#include "fen_internal.cuh"
+#include "fft_core.cuh"
+
+namespace fen {
+
+struct Poisson {
+    char variant[4] = {0, 0, 0, 0};
+    int nx = 0, ny = 0, nz = 0;     // global sizes
+    int nzl = 0;                    // local z planes (slab)
+    int nyl = 0;                    // local y lines in the z-pencil layout (multi-rank)
+    int M = 0;                      // nx / 2
+    int PC = 0;                     // complex row pitch
+    double2* C = nullptr;           // [PC][ny][nzl]
+    double2* Cz = nullptr;          // [PC][nyl][nz] (multi-rank only; == C on one rank)
+    double2 *tw_x = nullptr, *twr_x = nullptr, *tw_y = nullptr, *tw_z = nullptr;
+    double *mwn_x = nullptr, *mwn_y = nullptr, *mwn_z = nullptr;
+    double *ta = nullptr, *tb = nullptr, *tc = nullptr;   // tridiagonal a, b, c
+    double* c1 = nullptr;           // Thomas c1 table, indexed like the line layout
+    int tri_n = 0;
+};
+
+static inline double f32(long long n) { return (double)(float)n; }   // Fortran float(n), hazard H1
+
+// =================================================================================================
+// x direction: real <-> half-spectrum, rows contiguous
+// =================================================================================================
+struct XArgs {
+    Layout L;
+    double* f;            // real field (device layout)
+    double2* C;
+    int PC, ny, nrows;    // nrows = ny * nzl
+    const double2* tw;    // exp(-2 pi i m / M), m < M
+    const double2* twr;   // exp(-2 pi i k / N), k <= M
+    double scale;         // applied to the r2c output (1/float(nx) in ppn/pn, else 1)
+};
+
+constexpr int XR = 8;     // rows per block
+constexpr int XIS = 9;    // smem idx stride (see fft_core.cuh)
+
+template <int M>
+__global__ void __launch_bounds__(XR* FftPlan<M>::T) k_fft_x_r2c(XArgs a) {
+    extern __shared__ double2 s[];
+    constexpr int T = FftPlan<M>::T;
+    constexpr int NT = XR * T;
+    const int tid = threadIdx.x;
+    const int row0 = blockIdx.x * XR;
+    // load: thread e -> (row, idx), consecutive threads read consecutive 16-byte pairs of a row
+    for (int e = tid; e < XR * M; e += NT) {
+        const int row = e / M, idx = e - row * M;
+        const int r = row0 + row;
+        double2 z = make_double2(0.0, 0.0);
+        if (r < a.nrows) {
+            const int j = r % a.ny, k = r / a.ny;
+            const double2* src = reinterpret_cast<const double2*>(a.f + a.L.idx(1, j + 1, k + 1));
+            z = src[idx];
+        }
+        s[idx * XIS + row] = z;
+    }
+    __syncthreads();
+    fft_lines<M, -1>(s, XIS, tid % XR, tid / XR, true, a.tw);
+    // post-process pairs (k, M-k) and write X[0..M]
+    constexpr int NP = M / 2 + 1;
+    for (int e = tid; e < XR * NP; e += NT) {
+        const int row = e / NP, k = e - row * NP;
+        const int r = row0 + row;
+        if (r >= a.nrows) continue;
+        const int km = M - k;
+        const double2 zk = s[(k % M) * XIS + row];
+        const double2 zm = s[(km % M) * XIS + row];
+        double2* dst = a.C + (size_t)a.PC * r;
+        {   // X[k] = (Zk + conj Zm)/2 + w_k (Zk - conj Zm)/(2i)
+            const double2 E = make_double2(0.5 * (zk.x + zm.x), 0.5 * (zk.y - zm.y));
+            const double2 O = make_double2(0.5 * (zk.y + zm.y), -0.5 * (zk.x - zm.x));
+            const double2 w = __ldg(&a.twr[k]);
+            const double2 X = cadd(E, cmul(w, O));
+            dst[k] = make_double2(X.x * a.scale, X.y * a.scale);
+        }
+        if (km != k) {
+            const double2 E = make_double2(0.5 * (zm.x + zk.x), 0.5 * (zm.y - zk.y));
+            const double2 O = make_double2(0.5 * (zm.y + zk.y), -0.5 * (zm.x - zk.x));
+            const double2 w = __ldg(&a.twr[km]);
+            const double2 X = cadd(E, cmul(w, O));
+            dst[km] = make_double2(X.x * a.scale, X.y * a.scale);
+        }
+    }
+}
+
+template <int M>
+__global__ void __launch_bounds__(XR* FftPlan<M>::T) k_fft_x_c2r(XArgs a) {
+    extern __shared__ double2 s[];
+    constexpr int T = FftPlan<M>::T;
+    constexpr int NT = XR * T;
+    const int tid = threadIdx.x;
+    const int row0 = blockIdx.x * XR;
+    for (int e = tid; e < XR * (M + 1); e += NT) {
+        const int row = e / (M + 1), k = e - row * (M + 1);
+        const int r = row0 + row;
+        double2 x = make_double2(0.0, 0.0);
+        if (r < a.nrows) {
+            x = a.C[(size_t)a.PC * r + k];
+            if (k == 0 || k == M) x.y = 0.0;     // c2r ignores the imaginary part of DC / Nyquist
+        }
+        s[k * XIS + row] = x;
+    }
+    __syncthreads();
+    constexpr int NP = M / 2 + 1;
+    for (int e = tid; e < XR * NP; e += NT) {
+        const int row = e / NP, k = e - row * NP;
+        const int km = M - k;
+        const double2 xk = s[k * XIS + row];
+        const double2 xm = s[km * XIS + row];
+        // Z[k] = (Xk + conj Xm) + i conj(w_k) (Xk - conj Xm),  w_k = exp(-2 pi i k / N)
+        {
+            const double2 E = make_double2(xk.x + xm.x, xk.y - xm.y);
+            const double2 D = make_double2(xk.x - xm.x, xk.y + xm.y);
+            const double2 w = cconj(__ldg(&a.twr[k]));
+            const double2 O = cmul(w, D);
+            s[k * XIS + row] = make_double2(E.x - O.y, E.y + O.x);
+        }
+        if (km != k && km < M) {
+            const double2 E = make_double2(xm.x + xk.x, xm.y - xk.y);
+            const double2 D = make_double2(xm.x - xk.x, xm.y + xk.y);
+            const double2 w = cconj(__ldg(&a.twr[km]));
+            const double2 O = cmul(w, D);
+            s[km * XIS + row] = make_double2(E.x - O.y, E.y + O.x);
+        }
+    }
+    __syncthreads();
+    fft_lines<M, +1>(s, XIS, tid % XR, tid / XR, true, a.tw);
+    for (int e = tid; e < XR * M; e += NT) {
+        const int row = e / M, idx = e - row * M;
+        const int r = row0 + row;
+        if (r >= a.nrows) continue;
+        const int j = r % a.ny, k = r / a.ny;
+        double2* dst = reinterpret_cast<double2*>(a.f + a.L.idx(1, j + 1, k + 1));
+        dst[idx] = s[idx * XIS + row];
+    }
+}
+
+// =================================================================================================
+// strided directions (y, z): NL consecutive kx per block, lines of length Lf at stride sl
+// =================================================================================================
+struct LArgs {
+    double2* C;
+    long long sl, so;      // line element stride, outer stride (in complex elements)
+    int o0;                // global index of outer element 0 (for lam_o)
+    const double2* tw;
+    double scale;          // multiply after the forward transform (1/float(ny) in ppn)
+    // spectral divide (k_fft_solve only): lam = (lx[kx] + lo[o]) + ll[l]   (poisson.f90:998)
+    const double* lx; const double* lo; const double* ll;
+    double norm;           // float(nx*ny*nz)  (poisson.f90:992)
+};
+
+template <int Lf, int DIR, int NL>
+__global__ void __launch_bounds__(NL* FftPlan<Lf>::T) k_fft_lines(LArgs a) {
+    extern __shared__ double2 s[];
+    constexpr int T = FftPlan<Lf>::T;
+    const int tid = threadIdx.x;
+    const int line = tid % NL, t = tid / NL;
+    double2* base = a.C + (size_t)blockIdx.x * NL + line + a.so * blockIdx.y;
+    for (int idx = t; idx < Lf; idx += T) s[idx * NL + line] = base[a.sl * idx];
+    __syncthreads();
+    fft_lines<Lf, DIR>(s, NL, line, t, true, a.tw);
+    const double sc = a.scale;
+    for (int idx = t; idx < Lf; idx += T) {
+        double2 v = s[idx * NL + line];
+        base[a.sl * idx] = make_double2(v.x * sc, v.y * sc);
+    }
+}
+
+template <int Lf, int NL>
+__global__ void __launch_bounds__(NL* FftPlan<Lf>::T) k_fft_solve(LArgs a) {
+    extern __shared__ double2 s[];
+    constexpr int T = FftPlan<Lf>::T;
+    const int tid = threadIdx.x;
+    const int line = tid % NL, t = tid / NL;
+    const int kx = blockIdx.x * NL + line;
+    double2* base = a.C + kx + a.so * blockIdx.y;
+    for (int idx = t; idx < Lf; idx += T) s[idx * NL + line] = base[a.sl * idx];
+    __syncthreads();
+    fft_lines<Lf, -1>(s, NL, line, t, true, a.tw);
+    double lxo = a.lx[kx];
+    if (a.lo) lxo = lxo + a.lo[a.o0 + blockIdx.y];
+    for (int idx = t; idx < Lf; idx += T) {
+        const double lam = lxo + a.ll[idx];
+        double2 v = s[idx * NL + line];
+        if (lam == 0.0) {                      // poisson.f90:998-999
+            v = make_double2(0.0, 0.0);
+        } else {                               // :992 then :1001
+            v.x = (v.x / a.norm) / lam;
+            v.y = (v.y / a.norm) / lam;
+        }
+        s[idx * NL + line] = v;
+    }
+    __syncthreads();
+    fft_lines<Lf, +1>(s, NL, line, t, true, a.tw);
+    for (int idx = t; idx < Lf; idx += T) base[a.sl * idx] = s[idx * NL + line];
+}
+
+// =================================================================================================
+// Thomas algorithm along the last direction (poisson.f90:1092-1135 3-D form, :346-385 2-D form)
+// =================================================================================================
+struct TArgs {
+    double2* C;
+    double* c1;            // table, same indexing as C
+    long long sl, so;
+    int n, npc, nouter, o0;
+    const double* a; const double* b; const double* c;
+    const double* lx; const double* lo;     // lo == nullptr in 2-D
+    int form2d;
+};
+
+// pivot term shared by both sweeps: 3-D: ((b + lx) + lo) - a*c1prev ; 2-D uses its own groupings
+__device__ __forceinline__ double piv3(double b, double lx, double lo, double a, double c1p) {
+    return __dsub_rn(__dadd_rn(__dadd_rn(b, lx), lo), __dmul_rn(a, c1p));
+}
+
+// c1 table (depends only on the grid): computed once at init with the reference's arithmetic
+__global__ void k_thomas_c1(TArgs g) {
+    const int kx = blockIdx.x * blockDim.x + threadIdx.x;
+    const int o = blockIdx.y;
+    if (kx >= g.npc) return;
+    double* c1 = g.c1 + kx + g.so * o;
+    const double lx = g.lx[kx];
+    const double lo = g.lo ? g.lo[g.o0 + o] : 0.0;
+    double c1p;
+    if (g.form2d) c1p = __ddiv_rn(g.c[0], __dadd_rn(g.b[0], lx));                       // :350
+    else c1p = __dmul_rn(g.c[0], __ddiv_rn(1.0, __dadd_rn(__dadd_rn(g.b[0], lx), lo)));  // :1096-1097
+    c1[0] = c1p;
+    for (int l = 1; l < g.n - 1; ++l) {
+        if (g.form2d)   // c(j)/(b(j) - a(j)*c1(j-1) + mwn_x(i))  :357
+            c1p = __ddiv_rn(g.c[l], __dadd_rn(__dsub_rn(g.b[l], __dmul_rn(g.a[l], c1p)), lx));
+        else            // :1105-1106
+            c1p = __dmul_rn(g.c[l], __ddiv_rn(1.0, piv3(g.b[l], lx, lo, g.a[l], c1p)));
+        c1[g.sl * l] = c1p;
+    }
+    if (g.n > 1) c1[g.sl * (g.n - 1)] = 0.0;
+}
+
+__device__ __forceinline__ double2 c_scale(double2 v, double f) {
+    return make_double2(__dmul_rn(v.x, f), __dmul_rn(v.y, f));
+}
+__device__ __forceinline__ double2 c_div(double2 v, double f) {
+    return make_double2(__ddiv_rn(v.x, f), __ddiv_rn(v.y, f));
+}
+__device__ __forceinline__ double2 c_sub_ad(double2 r, double a, double2 d) {   // r - a*d
+    return make_double2(__dsub_rn(r.x, __dmul_rn(a, d.x)), __dsub_rn(r.y, __dmul_rn(a, d.y)));
+}
+
+__global__ void __launch_bounds__(128) k_thomas_fwd(TArgs g) {
+    const int kx = blockIdx.x * blockDim.x + threadIdx.x;
+    const int o = blockIdx.y;
+    if (kx >= g.npc) return;
+    double2* C = g.C + kx + g.so * o;
+    const double* c1t = g.c1 + kx + g.so * o;
+    const double lx = g.lx[kx];
+    const double lo = g.lo ? g.lo[g.o0 + o] : 0.0;
+    const int n = g.n;
+    double2 d;
+    {
+        const double2 r = C[0];
+        if (g.form2d) d = c_div(r, __dadd_rn(g.b[0], lx));                                    // :351
+        else d = c_scale(r, __ddiv_rn(1.0, __dadd_rn(__dadd_rn(g.b[0], lx), lo)));            // :1098
+        C[0] = d;
+    }
+    constexpr int U = 8;
+    for (int l0 = 1; l0 < n - 1; l0 += U) {
+        double2 r[U];
+        double cp[U];
+#pragma unroll
+        for (int q = 0; q < U; ++q)
+            if (l0 + q < n - 1) {
+                r[q] = C[g.sl * (l0 + q)];
+                cp[q] = c1t[g.sl * (l0 + q - 1)];
+            }
+#pragma unroll
+        for (int q = 0; q < U; ++q) {
+            const int l = l0 + q;
+            if (l < n - 1) {
+                const double a = g.a[l];
+                if (g.form2d)   // (rhs - a*d1)/(b + mwn_x - a*c1)   :358
+                    d = c_div(c_sub_ad(r[q], a, d),
+                              __dsub_rn(__dadd_rn(g.b[l], lx), __dmul_rn(a, cp[q])));
+                else            // (rhs - a*d1)*factor               :1105-1107
+                    d = c_scale(c_sub_ad(r[q], a, d), __ddiv_rn(1.0, piv3(g.b[l], lx, lo, a, cp[q])));
+                C[g.sl * l] = d;
+            }
+        }
+    }
+    if (n > 1) {   // last row, exact-zero pivot guard  :1112-1121 / :362-371
+        const int l = n - 1;
+        const double a = g.a[l];
+        const double c1p = c1t[g.sl * (l - 1)];
+        const double fr = g.form2d ? __dsub_rn(__dadd_rn(g.b[l], lx), __dmul_rn(a, c1p))
+                                   : piv3(g.b[l], lx, lo, a, c1p);
+        const double2 r = C[g.sl * l];
+        if (fr != 0.0) d = c_div(c_sub_ad(r, a, d), fr);
+        else d = make_double2(0.0, 0.0);
+        C[g.sl * l] = d;
+    }
+}
+
+__global__ void __launch_bounds__(128) k_thomas_bwd(TArgs g) {
+    const int kx = blockIdx.x * blockDim.x + threadIdx.x;
+    const int o = blockIdx.y;
+    if (kx >= g.npc) return;
+    double2* C = g.C + kx + g.so * o;
+    const double* c1t = g.c1 + kx + g.so * o;
+    const int n = g.n;
+    double2 x = C[g.sl * (n - 1)];                                  // :1124-1128
+    constexpr int U = 8;
+    for (int l0 = n - 2; l0 >= 0; l0 -= U) {
+        double2 d[U];
+        double cc[U];
+#pragma unroll
+        for (int q = 0; q < U; ++q)
+            if (l0 - q >= 0) {
+                d[q] = C[g.sl * (l0 - q)];
+                cc[q] = c1t[g.sl * (l0 - q)];
+            }
+#pragma unroll
+        for (int q = 0; q < U; ++q)
+            if (l0 - q >= 0) {                                      // x = d1 - c1*x(k+1)  :1132
+                x = make_double2(__dsub_rn(d[q].x, __dmul_rn(cc[q], x.x)),
+                                 __dsub_rn(d[q].y, __dmul_rn(cc[q], x.y)));
+                C[g.sl * (l0 - q)] = x;
+            }
+    }
+}
+
+// mean removal (poisson.f90:1159-1171, :398-410, :491-503): the mean of phi over the domain equals
+// the average along the last direction of the (kx, ky) = (0, 0) spectral line, so it is subtracted
+// there (O(n) work) instead of sweeping the real field twice (hazard H4).
+__global__ void k_remove_mean_line(double2* C, long long sl, int n) {
+    __shared__ double sh[32];
+    double acc = 0.0;
+    for (int l = threadIdx.x; l < n; l += blockDim.x) acc += C[sl * l].x;
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    double tot = 0.0;
+    for (int q = 0; q < (int)blockDim.x / 32; ++q) tot += sh[q];
+    const double mean = tot / (double)n;
+    for (int l = threadIdx.x; l < n; l += blockDim.x) C[sl * l].x -= mean;
+}
+
+// =================================================================================================
+// host side
+// =================================================================================================
+static bool pow2(int n) { return n > 0 && (n & (n - 1)) == 0; }
+
+template <typename T> static int upload(T** dptr, const std::vector<T>& h) {
+    FEN_CUDA(cudaMalloc(dptr, h.size() * sizeof(T)));
+    FEN_CUDA(cudaMemcpy(*dptr, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice));
+    return FEN_OK;
+}
+
+static std::vector<double2> twiddles(int n, int count, int denom) {
+    // exp(-2 pi i m / denom), m < count, evaluated in long double
+    std::vector<double2> t((size_t)std::max(count, 1));
+    const long double two_pi = 6.283185307179586476925286766559005768L;
+    for (int m = 0; m < count; ++m) {
+        long double ang = -two_pi * (long double)m / (long double)denom;
+        t[m] = make_double2((double)cosl(ang), (double)sinl(ang));
+    }
+    (void)n;
+    return t;
+}
+
+static std::vector<double> mwn(int n, double delta, int pad) {
+    // modified wavenumbers 2(cos(2 pi (i-1)/float(n)) - 1)/delta**2   (poisson.f90:627-629)
+    const double pi = std::acos(-1.0);      // global.f90:14
+    std::vector<double> m((size_t)std::max(n, pad), 1.0);   // padding entries: harmless non-zero
+    for (int i = 0; i < n; ++i) m[i] = 2.0 * (std::cos(2.0 * pi * (double)i / f32(n)) - 1.0) / (delta * delta);
+    return m;
+}
+
+void poisson_destroy(fen_ctx* c) {
+    Poisson* p = c->ps;
+    if (!p) return;
+    if (p->Cz && p->Cz != p->C) cudaFree(p->Cz);
+    for (void* q : {(void*)p->C, (void*)p->tw_x, (void*)p->twr_x, (void*)p->tw_y, (void*)p->tw_z,
+                    (void*)p->mwn_x, (void*)p->mwn_y, (void*)p->mwn_z, (void*)p->ta, (void*)p->tb,
+                    (void*)p->tc, (void*)p->c1})
+        if (q) cudaFree(q);
+    delete p;
+    c->ps = nullptr;
+}
+
+const char* poisson_variant(fen_ctx* c) { return c->ps ? c->ps->variant : ""; }
+
+template <int M> static int set_smem_x() {
+    const int bytes = (M + 1) * XIS * (int)sizeof(double2);
+    if (bytes > 48 * 1024) {
+        FEN_CUDA(cudaFuncSetAttribute(k_fft_x_r2c<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+        FEN_CUDA(cudaFuncSetAttribute(k_fft_x_c2r<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    }
+    return FEN_OK;
+}
+
+template <int M> static int launch_x(fen_ctx* c, const XArgs& a, bool fwd) {
+    constexpr int T = FftPlan<M>::T;
+    const int bytes = (M + 1) * XIS * (int)sizeof(double2);
+    static bool attr_done = false;
+    if (!attr_done) { FEN_TRY(set_smem_x<M>()); attr_done = true; }
+    dim3 grid((a.nrows + XR - 1) / XR), block(XR * T);
+    if (fwd) FEN_LAUNCH(c, "fft_x_r2c", k_fft_x_r2c<M><<<grid, block, bytes, c->stream>>>(a));
+    else FEN_LAUNCH(c, "fft_x_c2r", k_fft_x_c2r<M><<<grid, block, bytes, c->stream>>>(a));
+    FEN_CUDA(cudaGetLastError());
+    return FEN_OK;
+}
+
+static int dispatch_x(fen_ctx* c, int M, const XArgs& a, bool fwd) {
+    switch (M) {
+#define FEN_CASE(m) case m: return launch_x<m>(c, a, fwd);
+        FEN_CASE(1) FEN_CASE(2) FEN_CASE(4) FEN_CASE(8) FEN_CASE(16) FEN_CASE(32) FEN_CASE(64)
+        FEN_CASE(128) FEN_CASE(256) FEN_CASE(512) FEN_CASE(1024)
+#undef FEN_CASE
+    }
+    return set_error(FEN_ERR_UNSUPPORTED, "x FFT length %d not supported (power of two, 2..2048)", 2 * M);
+}
+
+// mode 0: forward, 1: inverse, 2: fused solve
+template <int Lf, int NL> static int launch_lines(fen_ctx* c, const LArgs& a, int mode, int nchunks, int nouter) {
+    constexpr int T = FftPlan<Lf>::T;
+    const int bytes = Lf * NL * (int)sizeof(double2);
+    static bool attr_done = false;
+    if (!attr_done) {
+        if (bytes > 48 * 1024) {
+            FEN_CUDA(cudaFuncSetAttribute(k_fft_lines<Lf, -1, NL>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+            FEN_CUDA(cudaFuncSetAttribute(k_fft_lines<Lf, +1, NL>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+            FEN_CUDA(cudaFuncSetAttribute(k_fft_solve<Lf, NL>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+        }
+        attr_done = true;
+    }
+    dim3 grid(nchunks, nouter), block(NL * T);
+    if (mode == 0) FEN_LAUNCH(c, "fft_lines_fwd", k_fft_lines<Lf, -1, NL><<<grid, block, bytes, c->stream>>>(a));
+    if (mode == 1) FEN_LAUNCH(c, "fft_lines_inv", k_fft_lines<Lf, +1, NL><<<grid, block, bytes, c->stream>>>(a));
+    if (mode == 2) FEN_LAUNCH(c, "fft_solve", k_fft_solve<Lf, NL><<<grid, block, bytes, c->stream>>>(a));
+    FEN_CUDA(cudaGetLastError());
+    return FEN_OK;
+}
+
+static int dispatch_lines(fen_ctx* c, int Lf, const LArgs& a, int mode, int PC, int nouter) {
+    switch (Lf) {
+#define FEN_CASE(l) case l: return launch_lines<l, 8>(c, a, mode, PC / 8, nouter);
+        FEN_CASE(1) FEN_CASE(2) FEN_CASE(4) FEN_CASE(8) FEN_CASE(16) FEN_CASE(32) FEN_CASE(64)
+        FEN_CASE(128) FEN_CASE(256) FEN_CASE(512) FEN_CASE(1024)
+#undef FEN_CASE
+        case 2048: return launch_lines<2048, 4>(c, a, mode, PC / 4, nouter);
+    }
+    return set_error(FEN_ERR_UNSUPPORTED, "FFT length %d not supported (power of two, 1..2048)", Lf);
+}
+
+int poisson_init(fen_ctx* c) {
+    if (c->ps) poisson_destroy(c);
+    const fen_grid_desc& g = c->g;
+    // variant from periodic_bc only (poisson.f90:68-111)
+    bool per[3];
+    per[0] = g.bc[0] == FEN_BC_PERIODIC && g.bc[1] == FEN_BC_PERIODIC;
+    per[1] = g.bc[2] == FEN_BC_PERIODIC && g.bc[3] == FEN_BC_PERIODIC;
+    per[2] = g.ndim == 3 ? (g.bc[4] == FEN_BC_PERIODIC && g.bc[5] == FEN_BC_PERIODIC) : true;
+    const char* var = nullptr;
+    if (g.ndim == 3) {
+        if (per[0] && per[1] && per[2]) var = "ppp";
+        else if (per[0] && per[1] && !per[2]) var = "ppn";
+        else if (!per[0] && per[1] && !per[2]) var = "npn";
+        else if (!per[0] && !per[1] && !per[2]) var = "nnn";
+    } else {
+        if (per[0] && per[1]) var = "pp";
+        else if (per[0] && !per[1]) var = "pn";
+        else if (!per[0] && !per[1]) var = "nn";
+    }
+    if (!var)
+        return set_error(FEN_ERR_UNSUPPORTED, "Unable to find the proper poisson solver with the selected "
+                                              "boundary conditions");          // poisson.f90:91-95
+    if (var[0] == 'n')
+        return set_error(FEN_ERR_UNSUPPORTED, "Poisson variant %s (DCT in x) is a 'next' row (SURVEY.md 8f-2), "
+                                              "not built yet", var);
+    if (!pow2(g.nx) || g.nx < 2 || g.nx > 2048 || !pow2(g.ny) || g.ny > 2048 ||
+        (g.ndim == 3 && (!pow2(g.nz) || g.nz > 2048)))
+        return set_error(FEN_ERR_UNSUPPORTED, "FFT sizes must be powers of two in 2..2048 (got %d %d %d)", g.nx,
+                         g.ny, g.nz);
+    Poisson* p = new Poisson();
+    c->ps = p;
+    snprintf(p->variant, sizeof(p->variant), "%s", var);
+    p->nx = g.nx; p->ny = g.ny; p->nz = g.nz; p->nzl = c->L.nzl;
+    p->M = g.nx / 2;
+    p->PC = ((g.nx / 2 + 1) + 7) / 8 * 8;
+    const size_t nC = (size_t)p->PC * g.ny * p->nzl;
+    FEN_CUDA(cudaMalloc(&p->C, nC * sizeof(double2)));
+    FEN_CUDA(cudaMemsetAsync(p->C, 0, nC * sizeof(double2), c->stream));
+    p->Cz = p->C;
+    p->nyl = g.ny;
+    if (g.nranks > 1 && g.ndim == 3) {
+        if (g.ny % g.nranks) return set_error(FEN_ERR_UNSUPPORTED, "ny must be divisible by the number of ranks");
+        p->nyl = g.ny / g.nranks;
+        const size_t nZ = (size_t)p->PC * p->nyl * g.nz;
+        FEN_CUDA(cudaMalloc(&p->Cz, nZ * sizeof(double2)));
+        FEN_CUDA(cudaMemsetAsync(p->Cz, 0, nZ * sizeof(double2), c->stream));
+    }
+    const double d = g.delta;
+    FEN_TRY(upload(&p->tw_x, twiddles(p->M, p->M, p->M)));
+    FEN_TRY(upload(&p->twr_x, twiddles(g.nx, p->M + 1, g.nx)));
+    FEN_TRY(upload(&p->mwn_x, mwn(g.nx, d, p->PC)));
+    const bool tri_y = !strcmp(var, "pn"), tri_z = !strcmp(var, "ppn");
+    if (!tri_y) {
+        FEN_TRY(upload(&p->tw_y, twiddles(g.ny, g.ny, g.ny)));
+        FEN_TRY(upload(&p->mwn_y, mwn(g.ny, d, 0)));
+    }
+    if (!strcmp(var, "ppp")) {
+        FEN_TRY(upload(&p->tw_z, twiddles(g.nz, g.nz, g.nz)));
+        FEN_TRY(upload(&p->mwn_z, mwn(g.nz, d, 0)));
+    }
+    if (tri_y || tri_z) {
+        // poisson.f90:219-232 / :744-757
+        const int n = tri_y ? g.ny : g.nz;
+        const int lo_face = tri_y ? 2 : 4;
+        p->tri_n = n;
+        std::vector<double> a((size_t)n, 1.0 / (d * d)), b((size_t)n, -2.0 / (d * d)), cc((size_t)n, 1.0 / (d * d));
+        b[0] = b[0] + a[0];
+        if (g.bc[lo_face] == FEN_BC_INFLOW && g.bc[lo_face + 1] == FEN_BC_OUTFLOW) b[n - 1] = b[n - 1] - cc[n - 1];
+        else b[n - 1] = b[n - 1] + cc[n - 1];
+        a[0] = 0.0;
+        cc[n - 1] = 0.0;
+        FEN_TRY(upload(&p->ta, a));
+        FEN_TRY(upload(&p->tb, b));
+        FEN_TRY(upload(&p->tc, cc));
+        TArgs t;
+        t.C = nullptr;
+        t.n = n; t.npc = p->PC; t.a = p->ta; t.b = p->tb; t.c = p->tc; t.lx = p->mwn_x;
+        if (tri_y) {
+            t.sl = p->PC; t.so = 0; t.nouter = 1; t.o0 = 0; t.lo = nullptr; t.form2d = 1;
+            FEN_CUDA(cudaMalloc(&p->c1, (size_t)p->PC * n * sizeof(double)));
+        } else {
+            t.sl = (long long)p->PC * p->nyl; t.so = p->PC; t.nouter = p->nyl; t.o0 = g.rank * p->nyl;
+            t.lo = p->mwn_y; t.form2d = 0;
+            FEN_CUDA(cudaMalloc(&p->c1, (size_t)p->PC * p->nyl * n * sizeof(double)));
+        }
+        t.c1 = p->c1;
+        dim3 grid((p->PC + 127) / 128, t.nouter), block(128);
+        FEN_LAUNCH(c, "thomas_c1", k_thomas_c1<<<grid, block, 0, c->stream>>>(t));
+        FEN_CUDA(cudaGetLastError());
+    }
+    return FEN_OK;
+}
+
+int poisson_solve(fen_ctx* c, double* f) {
+    Poisson* p = c->ps;
+    if (!p) return set_error(FEN_ERR_STATE, "solve_poisson before init_poisson_solver");
+    const fen_grid_desc& g = c->g;
+    const bool ppp = !strcmp(p->variant, "ppp"), ppn = !strcmp(p->variant, "ppn");
+    const bool pp = !strcmp(p->variant, "pp"), pn = !strcmp(p->variant, "pn");
+    const bool multi = g.nranks > 1 && g.ndim == 3;
+    XArgs xa;
+    xa.L = c->L; xa.f = f; xa.C = p->C; xa.PC = p->PC; xa.ny = g.ny; xa.nrows = g.ny * p->nzl;
+    xa.tw = p->tw_x; xa.twr = p->twr_x;
+    xa.scale = (ppn || pn) ? 1.0 / f32(g.nx) : 1.0;           // poisson.f90:1074, :341
+    FEN_TRY(dispatch_x(c, p->M, xa, true));
+
+    LArgs la;
+    la.lx = p->mwn_x; la.lo = nullptr; la.ll = nullptr; la.norm = 1.0; la.o0 = 0;
+    if (pp) {
+        // forward y + divide + inverse y fused (poisson.f90:451-478)
+        la.C = p->C; la.sl = p->PC; la.so = 0; la.tw = p->tw_y; la.scale = 1.0;
+        la.ll = p->mwn_y; la.norm = f32((long long)g.nx * g.ny);
+        FEN_TRY(dispatch_lines(c, g.ny, la, 2, p->PC, 1));
+    } else if (pn) {
+        TArgs t;
+        t.C = p->C; t.c1 = p->c1; t.sl = p->PC; t.so = 0; t.n = g.ny; t.npc = p->PC; t.nouter = 1; t.o0 = 0;
+        t.a = p->ta; t.b = p->tb; t.c = p->tc; t.lx = p->mwn_x; t.lo = nullptr; t.form2d = 1;
+        dim3 grid((p->PC + 127) / 128, 1), block(128);
+        FEN_LAUNCH(c, "thomas_fwd", k_thomas_fwd<<<grid, block, 0, c->stream>>>(t));
+        FEN_LAUNCH(c, "thomas_bwd", k_thomas_bwd<<<grid, block, 0, c->stream>>>(t));
+        FEN_LAUNCH(c, "mean_line", k_remove_mean_line<<<1, 256, 0, c->stream>>>(p->C, p->PC, g.ny));
+    } else {
+        // y forward (poisson.f90:975-979 / :1080-1087)
+        la.C = p->C; la.sl = p->PC; la.so = (long long)p->PC * g.ny; la.tw = p->tw_y;
+        la.scale = ppn ? 1.0 / f32(g.ny) : 1.0;
+        FEN_TRY(dispatch_lines(c, g.ny, la, 0, p->PC, p->nzl));
+        if (multi) FEN_TRY(comm_transpose_fwd(c));             // transpose_y_to_z (:982 / :1090)
+        double2* Z = p->Cz;
+        const long long slz = (long long)p->PC * p->nyl;
+        if (ppp) {
+            la.C = Z; la.sl = slz; la.so = p->PC; la.tw = p->tw_z; la.scale = 1.0; la.o0 = multi ? g.rank * p->nyl : 0;
+            la.lo = p->mwn_y; la.ll = p->mwn_z; la.norm = f32((long long)g.nx * g.ny * g.nz);
+            FEN_TRY(dispatch_lines(c, g.nz, la, 2, p->PC, p->nyl));
+        } else {
+            TArgs t;
+            t.C = Z; t.c1 = p->c1; t.sl = slz; t.so = p->PC; t.n = g.nz; t.npc = p->PC; t.nouter = p->nyl;
+            t.o0 = multi ? g.rank * p->nyl : 0;
+            t.a = p->ta; t.b = p->tb; t.c = p->tc; t.lx = p->mwn_x; t.lo = p->mwn_y; t.form2d = 0;
+            dim3 grid((p->PC + 127) / 128, p->nyl), block(128);
+            FEN_LAUNCH(c, "thomas_fwd", k_thomas_fwd<<<grid, block, 0, c->stream>>>(t));
+            FEN_LAUNCH(c, "thomas_bwd", k_thomas_bwd<<<grid, block, 0, c->stream>>>(t));
+            if (!multi || g.rank == 0)
+                FEN_LAUNCH(c, "mean_line", k_remove_mean_line<<<1, 256, 0, c->stream>>>(Z, slz, g.nz));
+        }
+        FEN_CUDA(cudaGetLastError());
+        if (multi) FEN_TRY(comm_transpose_bwd(c));             // transpose_z_to_y (:1015 / :1138)
+        // y inverse (:1018-1022 / :1141-1145)
+        la.C = p->C; la.sl = p->PC; la.so = (long long)p->PC * g.ny; la.tw = p->tw_y; la.scale = 1.0;
+        la.lo = nullptr; la.ll = nullptr;
+        FEN_TRY(dispatch_lines(c, g.ny, la, 1, p->PC, p->nzl));
+    }
+    FEN_CUDA(cudaGetLastError());
+    xa.scale = 1.0;
+    FEN_TRY(dispatch_x(c, p->M, xa, false));                   // :1028-1032
+    return FEN_OK;
+}
+
+}  // namespace fen

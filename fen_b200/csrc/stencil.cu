@@ -1,0 +1,655 @@
+// stencil.cu -- the staggered-grid finite-difference kernels of the fractional step.
+//
+//   k_pred   : predicted_velocity_field (src/navier_stokes.f90:140-213) with everything it calls
+//              fused into one pass: center_to_face (fields.f90:175), add_advection (:261-353),
+//              add_diffusion const-mu branch (:384-404 -> fields.f90:298-343), body force (:245-255),
+//              gradient(p) (fields.f90:31), RHS assembly (:169-172), v += dt*RHS (:187-198),
+//              dv_o = dv (:201-205).  Reads u,v,w,p,dv_o once, writes u*,v*,w*,dv_o once
+//              (104 B/cell in the uniform-property case).
+//   k_rhs    : divergence(v, phi); phi = phi*rho/dt      (fields.f90:120-153, navier_stokes.f90:111-121)
+//   k_corr   : gradient(phi); v -= grad*dt/rhof; p += phi (navier_stokes.f90:505-541, 550-561)
+//   k_check  : maxdiv (signed max) and max(|u|+|v|+|w|)   (navier_stokes.f90:570-619)
+// plus the stand-alone field operators of src/fields.f90 used by the reference's unit tests.
+//
+// All kernels map threadIdx.x to the x (fastest) index so every warp reads/writes contiguous
+// 256-byte runs; a block owns a (TX x TY) column of cells and marches KZ planes in z so that the
+// three z-planes a stencil needs stay in L1 while the 126 MB L2 holds the neighbouring tiles.
+#include "fen_internal.cuh"
+
+namespace fen {
+
+constexpr int TX = 64, TY = 4, KZ = 16;
+
+struct StArgs {
+    Layout L;
+    const double* u; const double* v; const double* w; const double* p;
+    const double* rho; const double* mu;           // fields (general path) or nullptr
+    const double* sx; const double* sy_; const double* sz_;
+    double* dvox; double* dvoy; double* dvoz;
+    double* un; double* vn; double* wn;
+    double rho0, mu0;                               // uniform values
+    double idelta, idelta2, dt, A, B, g0, g1, g2;
+};
+
+__device__ __forceinline__ double sq(double x) { return x * x; }
+
+// explicit terms dv (advection + diffusion [+ source]) at one cell; also returns rhof.
+template <bool D3, bool GEN, bool ADV_ONLY>
+__device__ __forceinline__ void explicit_terms(const StArgs& a, long long c, double& dvx, double& dvy,
+                                               double& dvz, double& rfx, double& rfy, double& rfz) {
+    const long long sy = a.L.sy, sz = a.L.sz;
+    const double id = a.idelta, id2 = a.idelta2;
+    const double* __restrict__ u = a.u;
+    const double* __restrict__ v = a.v;
+    const double* __restrict__ w = a.w;
+    const double u0 = u[c], uip = u[c + 1], uim = u[c - 1], ujp = u[c + sy], ujm = u[c - sy];
+    const double v0 = v[c], vip = v[c + 1], vim = v[c - 1], vjp = v[c + sy], vjm = v[c - sy];
+    const double uimjp = u[c - 1 + sy], vipjm = v[c + 1 - sy];
+    // ---- advection, navier_stokes.f90:297-347 -------------------------------------------------
+    double uuip = 0.25 * sq(uip + u0);
+    double uuim = 0.25 * sq(uim + u0);
+    double uvjp = (ujp + u0) * (vip + v0) * 0.25;
+    double uvjm = (u0 + ujm) * (vipjm + vjm) * 0.25;
+    dvx = 0.0 - (uuip - uuim) * id - (uvjp - uvjm) * id;
+    double vuip = (vip + v0) * (ujp + u0) * 0.25;
+    double vuim = (v0 + vim) * (uimjp + uim) * 0.25;
+    double vvjp = 0.25 * sq(vjp + v0);
+    double vvjm = 0.25 * sq(vjm + v0);
+    dvy = 0.0 - (vuip - vuim) * id - (vvjp - vvjm) * id;
+    dvz = 0.0;
+    double ukp = 0, ukm = 0, vkp = 0, vkm = 0, w0 = 0, wip = 0, wim = 0, wjp = 0, wjm = 0, wkp = 0, wkm = 0;
+    if (D3) {
+        ukp = u[c + sz]; ukm = u[c - sz]; vkp = v[c + sz]; vkm = v[c - sz];
+        w0 = w[c]; wip = w[c + 1]; wim = w[c - 1]; wjp = w[c + sy]; wjm = w[c - sy];
+        wkp = w[c + sz]; wkm = w[c - sz];
+        const double wipkm = w[c + 1 - sz], wjpkm = w[c + sy - sz];
+        const double uimkp = u[c - 1 + sz], vjmkp = v[c - sy + sz];
+        double uwkp = (ukp + u0) * (wip + w0) * 0.25;
+        double uwkm = (u0 + ukm) * (wipkm + wkm) * 0.25;
+        dvx = dvx - (uwkp - uwkm) * id;
+        double vwkp = (vkp + v0) * (wjp + w0) * 0.25;
+        double vwkm = (v0 + vkm) * (wjpkm + wkm) * 0.25;
+        dvy = dvy - (vwkp - vwkm) * id;
+        double wuip = (w0 + wip) * (u0 + ukp) * 0.25;
+        double wuim = (w0 + wim) * (uim + uimkp) * 0.25;
+        double wvjp = (w0 + wjp) * (v0 + vkp) * 0.25;
+        double wvjm = (w0 + wjm) * (vjm + vjmkp) * 0.25;
+        double wwkp = (w0 + wkp) * (w0 + wkp) * 0.25;
+        double wwkm = (w0 + wkm) * (w0 + wkm) * 0.25;
+        dvz = 0.0 - (wuip - wuim) * id - (wvjp - wvjm) * id - (wwkp - wwkm) * id;
+    }
+    if (ADV_ONLY) return;
+    // ---- face densities, fields.f90:197-200 ---------------------------------------------------
+    double mu;
+    if (GEN) {
+        const double* __restrict__ rho = a.rho;
+        const double r0 = rho[c];
+        rfx = 0.5 * (rho[c + 1] + r0);
+        rfy = 0.5 * (rho[c + sy] + r0);
+        rfz = D3 ? 0.5 * (rho[c + sz] + r0) : 1.0;
+        mu = a.mu[c];
+    } else {
+        rfx = rfy = rfz = 0.5 * (a.rho0 + a.rho0);
+        mu = a.mu0;
+    }
+    // ---- diffusion, fields.f90:326-337 + navier_stokes.f90:394-397 ------------------------------
+    double lx = ((uip - 2.0 * u0 + uim) + (ujp - 2.0 * u0 + ujm)) * id2;
+    double ly = ((vip - 2.0 * v0 + vim) + (vjp - 2.0 * v0 + vjm)) * id2;
+    if (D3) {
+        lx = lx + (ukp - 2.0 * u0 + ukm) * id2;
+        ly = ly + (vkp - 2.0 * v0 + vkm) * id2;
+        double lz = ((wip - 2.0 * w0 + wim) + (wjp - 2.0 * w0 + wjm) + (wkp - 2.0 * w0 + wkm)) * id2;
+        dvz = dvz + mu * lz / rfz;
+    }
+    dvx = dvx + mu * lx / rfx;
+    dvy = dvy + mu * ly / rfy;
+    // ---- body force, navier_stokes.f90:248-251 -------------------------------------------------
+    if (GEN && a.sx) {
+        dvx = dvx + a.sx[c] / rfx;
+        dvy = dvy + a.sy_[c] / rfy;
+        if (D3) dvz = dvz + a.sz_[c] / rfz;
+    }
+}
+
+template <bool D3, bool GEN>
+__global__ void __launch_bounds__(TX* TY) k_pred(StArgs a) {
+    const int i = blockIdx.x * TX + threadIdx.x + 1;
+    const int j = blockIdx.y * TY + threadIdx.y + 1;
+    if (i > a.L.nx || j > a.L.ny) return;
+    const int kb = blockIdx.z * KZ + 1;
+    const int ke = min(kb + KZ - 1, a.L.nzl);
+    const double id = a.idelta, dt = a.dt;
+    const double* __restrict__ p = a.p;
+    for (int k = kb; k <= ke; ++k) {
+        const long long c = a.L.idx(i, j, k);
+        double dvx, dvy, dvz, rfx, rfy, rfz;
+        explicit_terms<D3, GEN, false>(a, c, dvx, dvy, dvz, rfx, rfy, rfz);
+        const double p0 = p[c];
+        // RHS = -grad_p/rhof + A*dv + B*dv_o + g  (navier_stokes.f90:169-172)
+        double gx = (p[c + 1] - p0) * id;
+        double gy = (p[c + a.L.sy] - p0) * id;
+        double rx = -gx / rfx + a.A * dvx + a.B * a.dvox[c] + a.g0;
+        double ry = -gy / rfy + a.A * dvy + a.B * a.dvoy[c] + a.g1;
+        a.un[c] = a.u[c] + dt * rx;
+        a.vn[c] = a.v[c] + dt * ry;
+        a.dvox[c] = dvx;
+        a.dvoy[c] = dvy;
+        if (D3) {
+            double gz = (p[c + a.L.sz] - p0) * id;
+            double rz = -gz / rfz + a.A * dvz + a.B * a.dvoz[c] + a.g2;
+            a.wn[c] = a.w[c] + dt * rz;
+            a.dvoz[c] = dvz;
+        }
+    }
+}
+
+// compute_explicit_terms / add_advection as stand-alone operators (reference tests call them)
+template <bool D3, bool GEN, bool ADV_ONLY>
+__global__ void __launch_bounds__(TX* TY) k_explicit(StArgs a) {
+    const int i = blockIdx.x * TX + threadIdx.x + 1;
+    const int j = blockIdx.y * TY + threadIdx.y + 1;
+    if (i > a.L.nx || j > a.L.ny) return;
+    const int kb = blockIdx.z * KZ + 1;
+    const int ke = min(kb + KZ - 1, a.L.nzl);
+    for (int k = kb; k <= ke; ++k) {
+        const long long c = a.L.idx(i, j, k);
+        double dvx, dvy, dvz, rfx, rfy, rfz;
+        explicit_terms<D3, GEN, ADV_ONLY>(a, c, dvx, dvy, dvz, rfx, rfy, rfz);
+        if (ADV_ONLY) {   // add_advection accumulates into RHS (navier_stokes.f90:305)
+            a.un[c] += dvx;
+            a.vn[c] += dvy;
+            if (D3) a.wn[c] += dvz;
+        } else {
+            a.un[c] = dvx;
+            a.vn[c] = dvy;
+            if (D3) a.wn[c] = dvz;
+        }
+    }
+}
+
+struct RhsArgs {
+    Layout L;
+    const double* u; const double* v; const double* w;
+    const double* rho; double rho0;
+    double* phi;
+    double idelta, dt;
+    int scale;     // 1: phi = div * rho / dt ; 0: plain divergence
+};
+
+template <bool D3>
+__device__ __forceinline__ double div_at(const Layout& L, const double* __restrict__ u,
+                                         const double* __restrict__ v, const double* __restrict__ w,
+                                         long long c, double id) {
+    // fields.f90:144-147
+    double d = (u[c] - u[c - 1]) * id + (v[c] - v[c - L.sy]) * id;
+    if (D3) d = d + (w[c] - w[c - L.sz]) * id;
+    return d;
+}
+
+template <bool D3>
+__global__ void __launch_bounds__(TX* TY) k_rhs(RhsArgs a) {
+    const int i = blockIdx.x * TX + threadIdx.x + 1;
+    const int j = blockIdx.y * TY + threadIdx.y + 1;
+    if (i > a.L.nx || j > a.L.ny) return;
+    const int kb = blockIdx.z * KZ + 1;
+    const int ke = min(kb + KZ - 1, a.L.nzl);
+    for (int k = kb; k <= ke; ++k) {
+        const long long c = a.L.idx(i, j, k);
+        double d = div_at<D3>(a.L, a.u, a.v, a.w, c, a.idelta);
+        if (a.scale) {
+            double r = a.rho ? a.rho[c] : a.rho0;
+            d = d * r / a.dt;      // navier_stokes.f90:118
+        }
+        a.phi[c] = d;
+    }
+}
+
+struct CorrArgs {
+    Layout L;
+    double* u; double* v; double* w; double* p;
+    const double* phi;
+    const double* rho; double rho0;
+    double idelta, dt;
+};
+
+template <bool D3>
+__global__ void __launch_bounds__(TX* TY) k_corr(CorrArgs a) {
+    const int i = blockIdx.x * TX + threadIdx.x + 1;
+    const int j = blockIdx.y * TY + threadIdx.y + 1;
+    if (i > a.L.nx || j > a.L.ny) return;
+    const int kb = blockIdx.z * KZ + 1;
+    const int ke = min(kb + KZ - 1, a.L.nzl);
+    const double* __restrict__ phi = a.phi;
+    const double id = a.idelta, dt = a.dt;
+    for (int k = kb; k <= ke; ++k) {
+        const long long c = a.L.idx(i, j, k);
+        const double f0 = phi[c];
+        double rfx, rfy, rfz;
+        if (a.rho) {
+            const double r0 = a.rho[c];
+            rfx = 0.5 * (a.rho[c + 1] + r0);
+            rfy = 0.5 * (a.rho[c + a.L.sy] + r0);
+            rfz = D3 ? 0.5 * (a.rho[c + a.L.sz] + r0) : 1.0;
+        } else {
+            rfx = rfy = rfz = 0.5 * (a.rho0 + a.rho0);
+        }
+        // v = v - grad_p*dt/rhof   (navier_stokes.f90:533-536)
+        a.u[c] = a.u[c] - ((phi[c + 1] - f0) * id) * dt / rfx;
+        a.v[c] = a.v[c] - ((phi[c + a.L.sy] - f0) * id) * dt / rfy;
+        if (D3) a.w[c] = a.w[c] - ((phi[c + a.L.sz] - f0) * id) * dt / rfz;
+        a.p[c] = a.p[c] + f0;      // navier_stokes.f90:561 (ghosts are refreshed right after)
+    }
+}
+
+// ---- reductions --------------------------------------------------------------------------------
+__device__ __forceinline__ double warp_max(double x) {
+    for (int o = 16; o > 0; o >>= 1) x = fmax(x, __shfl_xor_sync(0xffffffffu, x, o));
+    return x;
+}
+__device__ __forceinline__ double warp_sum(double x) {
+    for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+    return x;
+}
+
+struct CheckArgs {
+    Layout L;
+    const double* u; const double* v; const double* w;
+    double idelta;
+    double* partial;    // [2 * nblocks]
+};
+
+template <bool D3>
+__global__ void __launch_bounds__(TX* TY) k_check(CheckArgs a) {
+    const int i = blockIdx.x * TX + threadIdx.x + 1;
+    const int j = blockIdx.y * TY + threadIdx.y + 1;
+    double md = -1.0e300, mv = 0.0;
+    if (i <= a.L.nx && j <= a.L.ny) {
+        const int kb = blockIdx.z * KZ + 1;
+        const int ke = min(kb + KZ - 1, a.L.nzl);
+        for (int k = kb; k <= ke; ++k) {
+            const long long c = a.L.idx(i, j, k);
+            md = fmax(md, div_at<D3>(a.L, a.u, a.v, a.w, c, a.idelta));   // signed max (H6)
+            double vel = fabs(a.u[c]) + fabs(a.v[c]);
+            if (D3) vel += fabs(a.w[c]);
+            mv = fmax(mv, vel);
+        }
+    }
+    __shared__ double s0[TX * TY / 32], s1[TX * TY / 32];
+    const int tid = threadIdx.y * TX + threadIdx.x;
+    md = warp_max(md);
+    mv = warp_max(mv);
+    if ((tid & 31) == 0) { s0[tid >> 5] = md; s1[tid >> 5] = mv; }
+    __syncthreads();
+    if (tid == 0) {
+        for (int q = 1; q < TX * TY / 32; ++q) { md = fmax(md, s0[q]); mv = fmax(mv, s1[q]); }
+        const long long b = blockIdx.x + (long long)gridDim.x * (blockIdx.y + (long long)gridDim.y * blockIdx.z);
+        a.partial[2 * b] = md;
+        a.partial[2 * b + 1] = mv;
+    }
+}
+
+// final pass over per-block partials: out[q] = reduce(partial[q + nq*b])
+template <int OP>
+__global__ void k_reduce_final(const double* partial, long long nb, int nq, double* out) {
+    __shared__ double s[32];
+    for (int q = 0; q < nq; ++q) {
+        double x = OP == 0 ? -1.0e300 : 0.0;
+        for (long long b = threadIdx.x; b < nb; b += blockDim.x) {
+            double y = partial[nq * b + q];
+            x = OP == 0 ? fmax(x, y) : x + y;
+        }
+        x = OP == 0 ? warp_max(x) : warp_sum(x);
+        if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = x;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            for (int r = 1; r < (int)blockDim.x / 32; ++r) x = OP == 0 ? fmax(x, s[r]) : x + s[r];
+            out[q] = x;
+        }
+        __syncthreads();
+    }
+}
+
+template <int OP>
+__global__ void __launch_bounds__(TX* TY) k_reduce_field(Layout L, const double* f, double* partial) {
+    const int i = blockIdx.x * TX + threadIdx.x + 1;
+    const int j = blockIdx.y * TY + threadIdx.y + 1;
+    double x = OP == 0 ? -1.0e300 : 0.0;
+    double mn = 1.0e300;
+    if (i <= L.nx && j <= L.ny) {
+        const int kb = blockIdx.z * KZ + 1;
+        const int ke = min(kb + KZ - 1, L.nzl);
+        for (int k = kb; k <= ke; ++k) {
+            double y = f[L.idx(i, j, k)];
+            x = OP == 0 ? fmax(x, y) : x + y;
+            mn = fmin(mn, y);
+        }
+    }
+    __shared__ double s0[TX * TY / 32], s1[TX * TY / 32];
+    const int tid = threadIdx.y * TX + threadIdx.x;
+    x = OP == 0 ? warp_max(x) : warp_sum(x);
+    mn = -warp_max(-mn);
+    if ((tid & 31) == 0) { s0[tid >> 5] = x; s1[tid >> 5] = -mn; }
+    __syncthreads();
+    if (tid == 0) {
+        double m2 = -mn;
+        for (int q = 1; q < TX * TY / 32; ++q) {
+            x = OP == 0 ? fmax(x, s0[q]) : x + s0[q];
+            m2 = fmax(m2, s1[q]);
+        }
+        const long long b = blockIdx.x + (long long)gridDim.x * (blockIdx.y + (long long)gridDim.y * blockIdx.z);
+        partial[2 * b] = x;
+        partial[2 * b + 1] = m2;     // max of (-f): -(min f), reduced with max when OP == 0
+    }
+}
+
+// ---- generic field operators (fields.f90) ----------------------------------------------------------
+struct OpArgs {
+    Layout L;
+    const double* a0; const double* a1; const double* a2;
+    double* o0; double* o1; double* o2;
+    double idelta, idelta2;
+};
+// MODE 0 gradient of scalar a0 -> (o0,o1,o2); 1 laplacian of vector; 2 center_to_face
+template <bool D3, int MODE>
+__global__ void __launch_bounds__(TX* TY) k_op(OpArgs a) {
+    const int i = blockIdx.x * TX + threadIdx.x + 1;
+    const int j = blockIdx.y * TY + threadIdx.y + 1;
+    if (i > a.L.nx || j > a.L.ny) return;
+    const int kb = blockIdx.z * KZ + 1;
+    const int ke = min(kb + KZ - 1, a.L.nzl);
+    const long long sy = a.L.sy, sz = a.L.sz;
+    for (int k = kb; k <= ke; ++k) {
+        const long long c = a.L.idx(i, j, k);
+        if (MODE == 0) {
+            const double s0 = a.a0[c];
+            a.o0[c] = (a.a0[c + 1] - s0) * a.idelta;
+            a.o1[c] = (a.a0[c + sy] - s0) * a.idelta;
+            if (D3) a.o2[c] = (a.a0[c + sz] - s0) * a.idelta;
+        } else if (MODE == 2) {
+            const double s0 = a.a0[c];
+            a.o0[c] = 0.5 * (a.a0[c + 1] + s0);
+            a.o1[c] = 0.5 * (a.a0[c + sy] + s0);
+            if (D3) a.o2[c] = 0.5 * (a.a0[c + sz] + s0);
+        } else {
+            const double* in[3] = {a.a0, a.a1, a.a2};
+            double* out[3] = {a.o0, a.o1, a.o2};
+            for (int m = 0; m < (D3 ? 3 : 2); ++m) {
+                const double* f = in[m];
+                const double f0 = f[c];
+                double lx = f[c + 1] - 2.0 * f0 + f[c - 1];
+                double ly = f[c + sy] - 2.0 * f0 + f[c - sy];
+                double r;
+                if (D3) {
+                    double lz = f[c + sz] - 2.0 * f0 + f[c - sz];
+                    r = (m == 2) ? (lx + ly + lz) * a.idelta2 : (lx + ly) * a.idelta2 + lz * a.idelta2;
+                } else {
+                    r = (lx + ly) * a.idelta2;
+                }
+                out[m][c] = r;
+            }
+        }
+    }
+}
+
+static dim3 st_grid(const Layout& L) {
+    return dim3((L.nx + TX - 1) / TX, (L.ny + TY - 1) / TY, (L.nzl + KZ - 1) / KZ);
+}
+static long long st_blocks(const Layout& L) {
+    dim3 g = st_grid(L);
+    return (long long)g.x * g.y * g.z;
+}
+
+static int fill_props(fen_ctx* c, const double** rho, const double** mu, double* rho0, double* mu0) {
+    *rho0 = c->rho_uniform;
+    *mu0 = c->mu_uniform;
+    *rho = nullptr;
+    *mu = nullptr;
+    if (!c->uniform_props) {
+        Field *fr, *fm;
+        FEN_TRY(field_check(c, FEN_RHO, &fr));
+        FEN_TRY(field_check(c, FEN_MU, &fm));
+        *rho = fr->d;
+        *mu = fm->d;
+    }
+    return FEN_OK;
+}
+
+static int fill_st(fen_ctx* c, StArgs& a) {
+    const bool d3 = c->g.ndim == 3;
+    Field *u, *v, *w = nullptr, *p;
+    FEN_TRY(field_check(c, FEN_VX, &u));
+    FEN_TRY(field_check(c, FEN_VY, &v));
+    if (d3) FEN_TRY(field_check(c, FEN_VZ, &w));
+    FEN_TRY(field_check(c, FEN_P, &p));
+    a.L = c->L;
+    a.u = u->d; a.v = v->d; a.w = w ? w->d : nullptr; a.p = p->d;
+    FEN_TRY(fill_props(c, &a.rho, &a.mu, &a.rho0, &a.mu0));
+    a.sx = a.sy_ = a.sz_ = nullptr;
+    if (c->has_source) {
+        Field *sx, *sy, *sz = nullptr;
+        FEN_TRY(field_check(c, FEN_SX, &sx));
+        FEN_TRY(field_check(c, FEN_SY, &sy));
+        if (d3) FEN_TRY(field_check(c, FEN_SZ, &sz));
+        a.sx = sx->d; a.sy_ = sy->d; a.sz_ = sz ? sz->d : nullptr;
+    }
+    a.idelta = 1.0 / c->g.delta;
+    a.idelta2 = 1.0 / (c->g.delta * c->g.delta);     // fields.f90:313: 1/delta**2
+    return FEN_OK;
+}
+
+static bool general_path(fen_ctx* c) { return !c->uniform_props || c->has_source; }
+
+// the general kernels read rho/mu as fields: materialise them if only the source term is general
+static int ensure_general_fields(fen_ctx* c, StArgs& a) {
+    if (a.rho) return FEN_OK;
+    Field *fr, *fm;
+    FEN_TRY(field_check(c, FEN_RHO, &fr));
+    FEN_TRY(field_check(c, FEN_MU, &fm));
+    a.rho = fr->d;
+    a.mu = fm->d;
+    return FEN_OK;
+}
+
+int ns_predict(fen_ctx* c, double dt) {
+    const bool d3 = c->g.ndim == 3;
+    StArgs a;
+    FEN_TRY(fill_st(c, a));
+    Field *dx, *dy, *dz = nullptr;
+    FEN_TRY(field_check(c, FEN_DVOX, &dx));
+    FEN_TRY(field_check(c, FEN_DVOY, &dy));
+    if (d3) FEN_TRY(field_check(c, FEN_DVOZ, &dz));
+    a.dvox = dx->d; a.dvoy = dy->d; a.dvoz = dz ? dz->d : nullptr;
+    for (int m = 0; m < (d3 ? 3 : 2); ++m)
+        if (!c->vnew[m]) {
+            FEN_CUDA(cudaMalloc(&c->vnew[m], c->L.elems * sizeof(double)));
+            FEN_CUDA(cudaMemsetAsync(c->vnew[m], 0, c->L.elems * sizeof(double), c->stream));
+        }
+    a.un = c->vnew[0]; a.vn = c->vnew[1]; a.wn = c->vnew[2];
+    a.dt = dt;
+    a.A = 1.0 + 0.5 * dt / c->prm.dt_o;      // navier_stokes.f90:157
+    a.B = -0.5 * dt / c->prm.dt_o;           // navier_stokes.f90:158
+    a.g0 = c->prm.g[0]; a.g1 = c->prm.g[1]; a.g2 = c->prm.g[2];
+    const bool gen = general_path(c);
+    if (gen) FEN_TRY(ensure_general_fields(c, a));
+    dim3 grid = st_grid(c->L), block(TX, TY);
+    if (d3) {
+        if (gen) FEN_LAUNCH(c, "pred", k_pred<true, true><<<grid, block, 0, c->stream>>>(a));
+        else FEN_LAUNCH(c, "pred", k_pred<true, false><<<grid, block, 0, c->stream>>>(a));
+    } else {
+        if (gen) FEN_LAUNCH(c, "pred", k_pred<false, true><<<grid, block, 0, c->stream>>>(a));
+        else FEN_LAUNCH(c, "pred", k_pred<false, false><<<grid, block, 0, c->stream>>>(a));
+    }
+    FEN_CUDA(cudaGetLastError());
+    // v now lives in the freshly written buffers; the old ones become the next scratch
+    for (int m = 0; m < (d3 ? 3 : 2); ++m) std::swap(c->fields[FEN_VX + m].d, c->vnew[m]);
+    return ghost_update(c, FEN_VX, d3 ? 3 : 2);      // navier_stokes.f90:208
+}
+
+int op_explicit_terms(fen_ctx* c, int rhs_x, bool advection_only) {
+    const bool d3 = c->g.ndim == 3;
+    StArgs a;
+    FEN_TRY(fill_st(c, a));
+    Field* o[3] = {nullptr, nullptr, nullptr};
+    for (int m = 0; m < (d3 ? 3 : 2); ++m) FEN_TRY(field_check(c, rhs_x + m, &o[m]));
+    a.un = o[0]->d; a.vn = o[1]->d; a.wn = o[2] ? o[2]->d : nullptr;
+    a.dvox = a.dvoy = a.dvoz = nullptr;
+    a.dt = a.A = a.B = a.g0 = a.g1 = a.g2 = 0.0;
+    const bool gen = general_path(c) && !advection_only;
+    if (gen) FEN_TRY(ensure_general_fields(c, a));
+    dim3 grid = st_grid(c->L), block(TX, TY);
+#define FEN_EXPL(D3, GEN, ADV) FEN_LAUNCH(c, "explicit", k_explicit<D3, GEN, ADV><<<grid, block, 0, c->stream>>>(a))
+    if (advection_only) { if (d3) FEN_EXPL(true, false, true); else FEN_EXPL(false, false, true); }
+    else if (gen) { if (d3) FEN_EXPL(true, true, false); else FEN_EXPL(false, true, false); }
+    else { if (d3) FEN_EXPL(true, false, false); else FEN_EXPL(false, false, false); }
+#undef FEN_EXPL
+    FEN_CUDA(cudaGetLastError());
+    return FEN_OK;
+}
+
+static int launch_rhs(fen_ctx* c, int vx, int s, bool scale, double dt) {
+    const bool d3 = c->g.ndim == 3;
+    Field *u, *v, *w = nullptr, *o;
+    FEN_TRY(field_check(c, vx, &u));
+    FEN_TRY(field_check(c, vx + 1, &v));
+    if (d3) FEN_TRY(field_check(c, vx + 2, &w));
+    FEN_TRY(field_check(c, s, &o));
+    RhsArgs a;
+    a.L = c->L;
+    a.u = u->d; a.v = v->d; a.w = w ? w->d : nullptr;
+    const double* mu;
+    double mu0;
+    FEN_TRY(fill_props(c, &a.rho, &mu, &a.rho0, &mu0));
+    a.phi = o->d;
+    a.idelta = 1.0 / c->g.delta;
+    a.dt = dt;
+    a.scale = scale ? 1 : 0;
+    dim3 grid = st_grid(c->L), block(TX, TY);
+    if (d3) FEN_LAUNCH(c, scale ? "poisson_rhs" : "divergence", k_rhs<true><<<grid, block, 0, c->stream>>>(a));
+    else FEN_LAUNCH(c, scale ? "poisson_rhs" : "divergence", k_rhs<false><<<grid, block, 0, c->stream>>>(a));
+    FEN_CUDA(cudaGetLastError());
+    return FEN_OK;
+}
+
+int ns_poisson_rhs(fen_ctx* c, double dt) { return launch_rhs(c, FEN_VX, FEN_PHI, true, dt); }
+int op_divergence(fen_ctx* c, int vx, int s) { return launch_rhs(c, vx, s, false, 1.0); }
+
+int ns_correct(fen_ctx* c, double dt) {
+    const bool d3 = c->g.ndim == 3;
+    Field *u, *v, *w = nullptr, *p, *phi;
+    FEN_TRY(field_check(c, FEN_VX, &u));
+    FEN_TRY(field_check(c, FEN_VY, &v));
+    if (d3) FEN_TRY(field_check(c, FEN_VZ, &w));
+    FEN_TRY(field_check(c, FEN_P, &p));
+    FEN_TRY(field_check(c, FEN_PHI, &phi));
+    CorrArgs a;
+    a.L = c->L;
+    a.u = u->d; a.v = v->d; a.w = w ? w->d : nullptr; a.p = p->d; a.phi = phi->d;
+    const double* mu;
+    double mu0;
+    FEN_TRY(fill_props(c, &a.rho, &mu, &a.rho0, &mu0));
+    a.idelta = 1.0 / c->g.delta;
+    a.dt = dt;
+    dim3 grid = st_grid(c->L), block(TX, TY);
+    if (d3) FEN_LAUNCH(c, "corr", k_corr<true><<<grid, block, 0, c->stream>>>(a));
+    else FEN_LAUNCH(c, "corr", k_corr<false><<<grid, block, 0, c->stream>>>(a));
+    FEN_CUDA(cudaGetLastError());
+    FEN_TRY(ghost_update(c, FEN_VX, d3 ? 3 : 2));     // navier_stokes.f90:544
+    return ghost_update(c, FEN_P, 1);                  // navier_stokes.f90:564
+}
+
+static int ensure_red(fen_ctx* c) {
+    const long long nb = st_blocks(c->L);
+    if (c->d_red && c->red_blocks >= nb) return FEN_OK;
+    if (c->d_red) cudaFree(c->d_red);
+    c->red_blocks = (int)nb;
+    FEN_CUDA(cudaMalloc(&c->d_red, (size_t)(2 * nb + 16) * sizeof(double)));
+    if (!c->h_red) FEN_CUDA(cudaMallocHost(&c->h_red, 16 * sizeof(double)));
+    return FEN_OK;
+}
+
+int ns_checks_launch(fen_ctx* c, double dt) {
+    const bool d3 = c->g.ndim == 3;
+    (void)dt;
+    Field *u, *v, *w = nullptr;
+    FEN_TRY(field_check(c, FEN_VX, &u));
+    FEN_TRY(field_check(c, FEN_VY, &v));
+    if (d3) FEN_TRY(field_check(c, FEN_VZ, &w));
+    FEN_TRY(ensure_red(c));
+    CheckArgs a;
+    a.L = c->L;
+    a.u = u->d; a.v = v->d; a.w = w ? w->d : nullptr;
+    a.idelta = 1.0 / c->g.delta;
+    a.partial = c->d_red + 16;
+    dim3 grid = st_grid(c->L), block(TX, TY);
+    if (d3) FEN_LAUNCH(c, "check", k_check<true><<<grid, block, 0, c->stream>>>(a));
+    else FEN_LAUNCH(c, "check", k_check<false><<<grid, block, 0, c->stream>>>(a));
+    FEN_LAUNCH(c, "reduce", k_reduce_final<0><<<1, 256, 0, c->stream>>>(c->d_red + 16, st_blocks(c->L), 2, c->d_red));
+    FEN_CUDA(cudaGetLastError());
+    if (c->g.nranks > 1) FEN_TRY(comm_allreduce(c, c->d_red, 2, 0));   // navier_stokes.f90:614, scalar.f90:194
+    return FEN_OK;
+}
+
+// reduce the interior of f: d_out[0] = max or sum, d_out[1] = max(-f) = -(min f)
+int reduce_field(fen_ctx* c, const double* f, int op, double* d_out) {
+    FEN_TRY(ensure_red(c));
+    dim3 grid = st_grid(c->L), block(TX, TY);
+    if (op == 0) {
+        FEN_LAUNCH(c, "reduce", k_reduce_field<0><<<grid, block, 0, c->stream>>>(c->L, f, c->d_red + 16));
+        FEN_LAUNCH(c, "reduce", k_reduce_final<0><<<1, 256, 0, c->stream>>>(c->d_red + 16, st_blocks(c->L), 2, d_out));
+    } else {
+        FEN_LAUNCH(c, "reduce", k_reduce_field<1><<<grid, block, 0, c->stream>>>(c->L, f, c->d_red + 16));
+        // sum for slot 0; slot 1 (max of -f) is not meaningful under a sum-final, callers ignore it
+        FEN_LAUNCH(c, "reduce", k_reduce_final<1><<<1, 256, 0, c->stream>>>(c->d_red + 16, st_blocks(c->L), 2, d_out));
+    }
+    FEN_CUDA(cudaGetLastError());
+    return FEN_OK;
+}
+
+int field_is_uniform(fen_ctx* c, const double* f, bool* uniform, double* value) {
+    FEN_TRY(ensure_red(c));
+    FEN_TRY(reduce_field(c, f, 0, c->d_red));
+    if (c->g.nranks > 1) FEN_TRY(comm_allreduce(c, c->d_red, 2, 0));
+    FEN_CUDA(cudaMemcpyAsync(c->h_red, c->d_red, 2 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    FEN_CUDA(cudaStreamSynchronize(c->stream));
+    *uniform = (c->h_red[0] == -c->h_red[1]);
+    *value = c->h_red[0];
+    return FEN_OK;
+}
+
+static int launch_op(fen_ctx* c, int mode, int in0, int nin, int out0) {
+    const bool d3 = c->g.ndim == 3;
+    const int nc = d3 ? 3 : 2;
+    OpArgs a;
+    a.L = c->L;
+    const double* in[3] = {nullptr, nullptr, nullptr};
+    double* out[3] = {nullptr, nullptr, nullptr};
+    for (int m = 0; m < nin; ++m) {
+        Field* f;
+        FEN_TRY(field_check(c, in0 + m, &f));
+        if (f->gl < 1) return set_error(FEN_ERR_ARG, "operator input field %d needs ghost nodes", in0 + m);
+        in[m] = f->d;
+    }
+    for (int m = 0; m < nc; ++m) {
+        Field* f;
+        FEN_TRY(field_check(c, out0 + m, &f));
+        out[m] = f->d;
+    }
+    a.a0 = in[0]; a.a1 = in[1]; a.a2 = in[2];
+    a.o0 = out[0]; a.o1 = out[1]; a.o2 = out[2];
+    a.idelta = 1.0 / c->g.delta;
+    a.idelta2 = 1.0 / (c->g.delta * c->g.delta);
+    dim3 grid = st_grid(c->L), block(TX, TY);
+#define FEN_OP(D3, M, NAME) FEN_LAUNCH(c, NAME, k_op<D3, M><<<grid, block, 0, c->stream>>>(a))
+    if (mode == 0) { if (d3) FEN_OP(true, 0, "gradient"); else FEN_OP(false, 0, "gradient"); }
+    if (mode == 1) { if (d3) FEN_OP(true, 1, "laplacian"); else FEN_OP(false, 1, "laplacian"); }
+    if (mode == 2) { if (d3) FEN_OP(true, 2, "center_to_face"); else FEN_OP(false, 2, "center_to_face"); }
+#undef FEN_OP
+    FEN_CUDA(cudaGetLastError());
+    return FEN_OK;
+}
+
+int op_gradient(fen_ctx* c, int s, int vx) { return launch_op(c, 0, s, 1, vx); }
+int op_laplacian(fen_ctx* c, int vx, int ox) { return launch_op(c, 1, vx, c->g.ndim == 3 ? 3 : 2, ox); }
+int op_center_to_face(fen_ctx* c, int s, int vx) { return launch_op(c, 2, s, 1, vx); }
+
+}  // namespace fen

@@ -1,0 +1,68 @@
+// Host-side emulation of the shared-memory Stockham FFT index logic in fen_b200/csrc/fft_core.cuh:
+// threads are loops, the barrier between stage_load and stage_store is the loop boundary.
+// Built and run by tests/test_host_logic.py (no GPU needed).  Prints max abs error vs an O(L^2) DFT.
+#include <cmath>
+#include <cstdio>
+#include <vector>
+#include "../../fen_b200/csrc/fft_core.cuh"
+using namespace fen;
+
+template <int L, int R, int DIR>
+static void run_stage(std::vector<double2>& s, int IS, int NL, int Ns, const double2* tw) {
+    constexpr int T = FftPlan<L>::T;
+    std::vector<double2> regs((size_t)NL * T * 8);
+    for (int line = 0; line < NL; ++line)
+        for (int t = 0; t < T; ++t) stage_load<L, R, DIR>(&regs[((size_t)line * T + t) * 8], s.data(), IS, line, t);
+    for (int line = 0; line < NL; ++line)
+        for (int t = 0; t < T; ++t)
+            stage_store<L, R, DIR>(&regs[((size_t)line * T + t) * 8], s.data(), IS, line, t, Ns, tw);
+}
+
+template <int L, int DIR> static double check(int IS, int NL) {
+    std::vector<double2> tw(L > 0 ? L : 1);
+    for (int m = 0; m < L; ++m) tw[m] = make_double2(cos(-2.0 * M_PI * m / L), sin(-2.0 * M_PI * m / L));
+    std::vector<double2> s((size_t)L * IS, make_double2(0, 0)), in((size_t)L * NL);
+    unsigned seed = 12345u + L;
+    for (int line = 0; line < NL; ++line)
+        for (int i = 0; i < L; ++i) {
+            seed = seed * 1664525u + 1013904223u; double a = (seed >> 8) / 16777216.0 - 0.5;
+            seed = seed * 1664525u + 1013904223u; double b = (seed >> 8) / 16777216.0 - 0.5;
+            in[(size_t)line * L + i] = make_double2(a, b);
+            s[(size_t)i * IS + line] = make_double2(a, b);
+        }
+    int Ns = 1;
+    if constexpr (L >= 8) {
+        for (int st = 0; st < FftPlan<L>::N8; ++st) { run_stage<L, 8, DIR>(s, IS, NL, Ns, tw.data()); Ns *= 8; }
+    }
+    constexpr int REM = FftPlan<L>::REM;
+    if constexpr (REM > 1) run_stage<L, REM, DIR>(s, IS, NL, Ns, tw.data());
+    double emax = 0;
+    for (int line = 0; line < NL; ++line)
+        for (int k = 0; k < L; ++k) {
+            double re = 0, im = 0;
+            for (int n = 0; n < L; ++n) {
+                double ang = DIR * 2.0 * M_PI * (double)((long long)n * k % L) / L;
+                double2 x = in[(size_t)line * L + n];
+                re += x.x * cos(ang) - x.y * sin(ang);
+                im += x.x * sin(ang) + x.y * cos(ang);
+            }
+            double2 y = s[(size_t)k * IS + line];
+            emax = fmax(emax, fmax(fabs(y.x - re), fabs(y.y - im)));
+        }
+    return emax;
+}
+
+template <int L> static int both() {
+    double ef = check<L, -1>(8, 8), eb = check<L, +1>(9, 8);
+    printf("L=%d fwd=%.3e inv=%.3e\n", L, ef, eb);
+    return (ef < 1e-11 && eb < 1e-11) ? 0 : 1;
+}
+
+int main() {
+    int bad = 0;
+    bad += both<2>(); bad += both<4>(); bad += both<8>(); bad += both<16>(); bad += both<32>();
+    bad += both<64>(); bad += both<128>(); bad += both<256>(); bad += both<512>(); bad += both<1024>();
+    bad += both<2048>();
+    printf(bad ? "FAIL\n" : "OK\n");
+    return bad;
+}

@@ -1,0 +1,371 @@
+"""GPU parity tests: the CUDA path (through the C ABI of libfen_gpu.so) against the CPU oracle.
+
+Tolerances are BASELINE.json's: relative L2 <= 1e-12 on u, v, w, p after one step, <= 1e-9 after
+100 steps of a laminar Taylor-Green case, divergence at machine precision.
+"""
+import numpy as np
+import pytest
+
+import fen_b200 as fb
+from oracle import fen_oracle as fo
+
+pytestmark = pytest.mark.gpu
+PI = fo.PI
+
+
+def rel_l2(a, b):
+    n = np.linalg.norm(b.ravel())
+    return np.linalg.norm((a - b).ravel()) / (n if n > 0 else 1.0)
+
+
+def make_pair(n, bc=None, ndim=3, L=1.0):
+    nz = n[2]
+    Go = fo.Grid(n[0], n[1], nz, L, L * n[1] / n[0], L * nz / n[0], bc=bc, ndim=ndim)
+    Gg = fb.grid().setup(n[0], n[1], nz, L, L * n[1] / n[0], L * nz / n[0], bc=bc, ndim=ndim)
+    assert Gg.delta == Go.delta
+    return Go, Gg
+
+
+BC_SETS_3D = {
+    "periodic": ["Periodic"] * 6,
+    "zwalls": ["Periodic"] * 4 + ["Wall", "Wall"],
+}
+
+
+# ---- scalar%update_ghost_nodes ---------------------------------------------------------------
+@pytest.mark.parametrize("types", [(0, 0, 0, 0, 0, 0), (1, 1, 2, 2, 1, 2), (2, 1, 1, 1, 2, 2), (0, 0, 1, 1, 2, 1)])
+@pytest.mark.parametrize("loc", ["c", "x", "y", "z"])
+def test_ghost_nodes_all_bc_types(types, loc):
+    Go, Gg = make_pair((16, 12, 8))
+    rng = np.random.default_rng(7)
+    so = fo.Scalar(Go, 1, loc)
+    sg = fb.scalar(Gg, 1, loc)
+    so.f[...] = rng.standard_normal(so.f.shape)
+    sg.f[...] = so.f
+    for face, t in zip(fo.FACES, types):
+        so.bc_type[face] = t
+        sg.set_bc_type(face, t)
+        plane = rng.standard_normal(so.bc[face].shape)
+        so.bc[face][...] = plane
+        sg.set_bc(face, plane)
+    so.update_ghost_nodes()
+    sg.push()
+    sg.update_ghost_nodes()
+    sg.pull()
+    assert np.array_equal(sg.f, so.f)          # pure copies / 2*bc - f: bit exact
+    Gg.destroy()
+
+
+def test_ghost_nodes_uniform_bc_value_and_2d():
+    Go, Gg = make_pair((16, 16, 1), bc=["Periodic", "Periodic", "Wall", "Wall"], ndim=2)
+    so = fo.Scalar(Go, 1, "x")
+    sg = fb.scalar(Gg, 1, "x")
+    so.f[...] = np.random.default_rng(3).standard_normal(so.f.shape)
+    sg.f[...] = so.f
+    for face, t in (("bottom", 1), ("top", 1)):
+        so.bc_type[face] = t
+        sg.set_bc_type(face, t)
+    so.bc["top"][...] = 1.5                      # lid_driven.f90:59  v%x%bc%top = U
+    sg.set_bc("top", 1.5)
+    so.update_ghost_nodes()
+    sg.push().update_ghost_nodes()
+    sg.pull()
+    assert np.array_equal(sg.f, so.f)
+    Gg.destroy()
+
+
+# ---- fields_mod operators --------------------------------------------------------------------
+@pytest.mark.parametrize("n,ndim", [((16, 16, 16), 3), ((32, 16, 1), 2)])
+def test_field_operators(n, ndim):
+    Go, Gg = make_pair(n, ndim=ndim)
+    rng = np.random.default_rng(11)
+    vo, vg = fo.Vector(Go, 1), fb.vector(Gg, 1)
+    so, sg = fo.Scalar(Go, 1), fb.scalar(Gg, 1)
+    for co, cg in zip(vo.comps + [so], vg.comps + [sg]):
+        co.I[...] = rng.standard_normal(co.I.shape)
+        co.update_ghost_nodes()
+        cg.f[...] = co.f
+        cg.push()
+    go, gg = fo.Vector(Go, 0), fb.vector(Gg, 0)
+    fo.gradient(so, go); fb.gradient(sg, gg); gg.pull()
+    do, dg = fo.Scalar(Go, 0), fb.scalar(Gg, 0)
+    fo.divergence(vo, do); fb.divergence(vg, dg); dg.pull()
+    lo, lg = fo.Vector(Go, 1), fb.vector(Gg, 1)
+    fo.laplacian_vector(vo, lo); fb.laplacian(vg, lg); lg.pull()
+    co_, cg_ = fo.Vector(Go, 0), fb.vector(Gg, 0)
+    fo.center_to_face(so, co_); fb.center_to_face(sg, cg_); cg_.pull()
+    for a, b in zip(gg.comps + [dg] + cg_.comps, go.comps + [do] + co_.comps):
+        assert rel_l2(a.I, b.I) < 1e-14
+    for a, b in zip(lg.comps, lo.comps):
+        assert rel_l2(a.I, b.I) < 1e-13
+    assert abs(dg.max_value() - do.max_value()) <= 1e-13 * abs(do.max_value())
+    assert abs(dg.integral() - do.integral()) <= 1e-10 * max(1.0, abs(do.integral()))
+    Gg.destroy()
+
+
+# ---- poisson_mod -----------------------------------------------------------------------------
+POISSON_CASES = [
+    ("ppp", (32, 32, 32), ["Periodic"] * 6, 3),
+    ("ppp", (64, 16, 32), ["Periodic"] * 6, 3),
+    ("ppp", (8, 128, 16), ["Periodic"] * 6, 3),
+    ("ppn", (32, 32, 32), ["Periodic"] * 4 + ["Wall", "Wall"], 3),
+    ("ppn", (16, 64, 128), ["Periodic"] * 4 + ["Wall", "Wall"], 3),
+    ("ppn", (32, 16, 16), ["Periodic"] * 4 + ["Inflow", "Outflow"], 3),
+    ("pp", (64, 64, 1), ["Periodic"] * 4, 2),
+    ("pp", (256, 32, 1), ["Periodic"] * 4, 2),
+    ("pn", (64, 64, 1), ["Periodic", "Periodic", "Wall", "Wall"], 2),
+    ("pn", (4, 32, 1), ["Periodic", "Periodic", "Wall", "Wall"], 2),
+    ("pn", (16, 16, 1), ["Periodic", "Periodic", "Inflow", "Outflow"], 2),
+]
+
+
+@pytest.mark.parametrize("variant,n,bc,ndim", POISSON_CASES)
+def test_poisson_variants_match_oracle(variant, n, bc, ndim):
+    Go, Gg = make_pair(n, bc=bc, ndim=ndim)
+    rng = np.random.default_rng(5)
+    rhs = rng.standard_normal(n)
+    if variant in ("ppp", "pp"):
+        rhs -= rhs.mean()
+    po, pg = fo.Scalar(Go, 1), fb.scalar(Gg, 1)
+    po.I[...] = rhs
+    pg.I[...] = rhs
+    pso, psg = fo.PoissonSolver(po), fb.PoissonSolver(pg)
+    assert psg.variant == pso.variant == variant
+    pso.solve(po)
+    pg.push()
+    psg.solve(pg)
+    pg.pull()
+    assert rel_l2(pg.I, po.I) < 1e-12
+    # solving twice gives the same answer (no state carried between solves)
+    pg.I[...] = rhs
+    pg.push(); psg.solve(pg); pg.pull()
+    assert rel_l2(pg.I, po.I) < 1e-12
+    Gg.destroy()
+
+
+def test_poisson_unsupported_bc_combo_is_an_error():
+    Gg = fb.grid().setup(16, 16, 16, 1.0, 1.0, 1.0,
+                         bc=["Periodic", "Periodic", "Wall", "Wall", "Periodic", "Periodic"])
+    phi = fb.scalar(Gg, 1)
+    with pytest.raises(fb.FenError):            # poisson.f90:91-95 `stop`
+        fb.PoissonSolver(phi)
+    Gg.destroy()
+
+
+@pytest.mark.parametrize("case", ["ppp", "ppn"])
+def test_projection_makes_velocity_divergence_free(case):
+    """test/small_test/poisson/projection/projection.f90: random 32^3 field, max div <= 1e-11."""
+    bc = ["Periodic"] * 6 if case == "ppp" else ["Periodic"] * 4 + ["Wall", "Wall"]
+    Gg = fb.grid().setup(32, 32, 32, 1.0, 1.0, 1.0, bc=bc)
+    v, div, phi, gphi = fb.vector(Gg, 1), fb.scalar(Gg, 0), fb.scalar(Gg, 1), fb.vector(Gg, 1)
+    if case == "ppn":
+        for f in ("front", "back"):
+            phi.set_bc_type(f, 2)
+            for c in v.comps:
+                c.set_bc_type(f, 1)
+    ps = fb.PoissonSolver(phi)
+    rng = np.random.default_rng(99)
+    div_max = 0.0
+    for _ in range(5):
+        for c in v.comps:
+            c.I[...] = rng.random(c.I.shape)
+            c.push()
+        v.update_ghost_nodes()
+        fb.divergence(v, div)
+        div.pull()
+        phi.I[...] = -div.I
+        phi.push()
+        ps.solve(phi)
+        phi.update_ghost_nodes()
+        fb.gradient(phi, gphi)
+        v.pull(); gphi.pull()
+        for c, g in zip(v.comps, gphi.comps):
+            c.f[...] = c.f + g.f
+            c.push()
+        v.update_ghost_nodes()
+        fb.divergence(v, div)
+        div_max = max(div_max, abs(div.max_value()))
+    assert div_max <= 1e-11
+    Gg.destroy()
+
+
+# ---- navier_stokes_solver --------------------------------------------------------------------
+def _mirror_state(nso, nsg):
+    for a, b in ((nso.p, nsg.p), (nso.v.x, nsg.v.x), (nso.v.y, nsg.v.y)):
+        b.f[...] = a.f
+        b.push()
+    if nso.G.ndim == 3:
+        nsg.v.z.f[...] = nso.v.z.f
+        nsg.v.z.push()
+
+
+def _compare(nso, nsg, tol):
+    nsg.v.pull(); nsg.p.pull()
+    errs = {}
+    for name, a, b in [("u", nsg.v.x, nso.v.x), ("v", nsg.v.y, nso.v.y), ("p", nsg.p, nso.p)] + \
+            ([("w", nsg.v.z, nso.v.z)] if nso.G.ndim == 3 else []):
+        if np.linalg.norm(b.I) == 0.0:
+            errs[name] = np.abs(a.I).max()
+        else:
+            errs[name] = rel_l2(a.f, b.f)          # ghosts included
+    assert all(e <= tol for e in errs.values()), errs
+    return errs
+
+
+def _setup_ns(n, bc, ndim, L, nu, init, U, g=None):
+    Go, Gg = make_pair(n, bc=bc, ndim=ndim, L=L)
+    nso = fo.NavierStokes(Go, 1.0, nu)
+    nsg = fb.Solver(Gg, 1.0, nu).init_solver()
+    if g is not None:
+        nso.g = list(g)
+        nsg.g = list(g)
+    init(nso)
+    _mirror_state(nso, nsg)
+    dt = nso.set_timestep(U)
+    dtg = nsg.set_timestep(U)
+    assert dtg == dt
+    return Go, Gg, nso, nsg, dt
+
+
+@pytest.mark.parametrize("n", [(32, 32, 32), (64, 64, 64), (128, 32, 64)])
+def test_one_step_tgv3d_matches_oracle(n):
+    Go, Gg, nso, nsg, dt = _setup_ns(n, ["Periodic"] * 6, 3, 2 * PI, 0.01, fo.init_tgv3d, 1.0)
+    assert nsg.poisson_variant == "ppp"
+    nso.navier_stokes_solver(1, dt)
+    nsg.navier_stokes_solver(1, dt)
+    _compare(nso, nsg, 1e-12)
+    md, mc = nsg.status()
+    assert abs(md) < 1e-12 and abs(mc - nso.maxCFL) < 1e-12
+    Gg.destroy()
+
+
+def test_100_steps_tgv3d_matches_oracle():
+    Go, Gg, nso, nsg, dt = _setup_ns((64, 64, 64), ["Periodic"] * 6, 3, 2 * PI, 0.01, fo.init_tgv3d, 1.0)
+    for step in range(1, 101):
+        nso.navier_stokes_solver(step, dt)
+        nsg.navier_stokes_solver(step, dt)
+    _compare(nso, nsg, 1e-9)
+    md, _ = nsg.status()
+    assert abs(md) < 1e-11            # reference bound, projection.f90:125
+    assert abs(md) < 5e-13            # machine precision at this size
+    Gg.destroy()
+
+
+def test_steps_tgv2d_matches_oracle_config1():
+    """BASELINE config 1 (2-D Taylor-Green, pp Poisson) at 64^2: 250 steps to t = 0.3."""
+    n = 64
+    Go, Gg, nso, nsg, dt = _setup_ns((n, n, 1), ["Periodic"] * 4, 2, 2 * PI, 1.0, fo.init_tgv2d, 2.0)
+    assert nsg.poisson_variant == "pp"
+    nso.navier_stokes_solver(1, dt)
+    nsg.navier_stokes_solver(1, dt)
+    _compare(nso, nsg, 1e-12)
+    t, step = dt, 1
+    while t < 0.3:
+        step += 1
+        t += dt
+        nso.navier_stokes_solver(step, dt)
+        nsg.navier_stokes_solver(step, dt)
+    assert step == 250
+    _compare(nso, nsg, 1e-9)
+    # the reference's own check: compare u with the analytic solution (postpro.py:48)
+    d = Go.delta
+    i = np.arange(1, n + 1)[:, None]; j = np.arange(1, n + 1)[None, :]
+    sol = -np.cos(i * d) * np.sin((j - 0.5) * d) * np.exp(-0.6)
+    assert np.abs(nsg.v.x.I[:, :, 0] - sol).max() < 5e-3
+    Gg.destroy()
+
+
+def test_channel_ppn_steps_match_oracle():
+    """BASELINE config 3 shape in miniature: walls in z, body force, ppn Poisson."""
+    n = (32, 32, 16)
+    bc = ["Periodic"] * 4 + ["Wall", "Wall"]
+    Go, Gg, nso, nsg, dt = _setup_ns(n, bc, 3, 2.0, 0.05, fo.init_channel, 1.0, g=(1.0, 0.0, 0.0))
+    assert nsg.poisson_variant == "ppn"
+    nso.navier_stokes_solver(1, dt)
+    nsg.navier_stokes_solver(1, dt)
+    _compare(nso, nsg, 1e-12)
+    for step in range(2, 21):
+        nso.navier_stokes_solver(step, dt)
+        nsg.navier_stokes_solver(step, dt)
+    _compare(nso, nsg, 1e-10)
+    assert abs(nsg.maxdiv) < 1e-12
+    Gg.destroy()
+
+
+def test_poiseuille_pn_steps_match_oracle():
+    """test/small_test/navier_stokes/poiseuille: nx = 4, walls in y, g(1) = 1, pn Poisson."""
+    ny = 16
+    Lx = 1.0 * fo._f32(4) / fo._f32(ny)
+    Go = fo.Grid(4, ny, 1, Lx, 1.0, 1.0 / ny, bc=["Periodic", "Periodic", "Wall", "Wall"])
+    Gg = fb.grid().setup(4, ny, 1, Lx, 1.0, 1.0 / ny, bc=["Periodic", "Periodic", "Wall", "Wall"])
+    nso = fo.NavierStokes(Go)
+    nsg = fb.Solver(Gg).init_solver()
+    nso.g[0] = 1.0
+    nsg.g = [1.0, 0.0, 0.0]
+    dt = nso.set_timestep(1.0)
+    assert nsg.set_timestep(1.0) == dt
+    for step in range(1, 51):
+        nso.navier_stokes_solver(step, dt)
+        nsg.navier_stokes_solver(step, dt)
+    _compare(nso, nsg, 1e-10)
+    Gg.destroy()
+
+
+def test_general_property_path_matches_uniform_and_oracle():
+    """rho, mu pushed as (non-uniform) fields and a source S: the general kernels (hazard H11)."""
+    n = (32, 32, 32)
+    Go, Gg, nso, nsg, dt = _setup_ns(n, ["Periodic"] * 6, 3, 2 * PI, 0.05, fo.init_tgv3d, 1.0)
+    x = Go.x[:, None, None]; y = Go.y[None, :, None]; z = Go.z[None, None, :]
+    nso.rho.f[...] = 1.0 + 0.2 * np.sin(x) * np.cos(y) * np.cos(z)
+    nso.mu.f[...] = 0.05 * (1.0 + 0.3 * np.cos(x) * np.sin(z))
+    nso.S.x.f[...] = 0.1 * np.sin(y[:, 1:-1, :]) * np.ones((n[0], 1, n[2]))
+    for a, b in ((nso.rho, nsg.rho), (nso.mu, nsg.mu), (nso.S.x, nsg.S.x), (nso.S.y, nsg.S.y), (nso.S.z, nsg.S.z)):
+        b.f[...] = a.f
+        b.push()
+    for step in (1, 2, 3):
+        nso.navier_stokes_solver(step, dt)
+        nsg.navier_stokes_solver(step, dt)
+    _compare(nso, nsg, 1e-11)
+    Gg.destroy()
+
+
+def test_constant_cfl_timestep_control():
+    Go, Gg, nso, nsg, dt = _setup_ns((32, 32, 32), ["Periodic"] * 6, 3, 2 * PI, 0.01, fo.init_tgv3d, 1.0)
+    nso.constant_CFL = True
+    nsg.constant_CFL = True
+    nso.CFL = 0.5
+    nsg.CFL = 0.5
+    dto, dtg = dt, dt
+    for step in range(1, 6):
+        dto = nso.navier_stokes_solver(step, dto)
+        dtg = nsg.navier_stokes_solver(step, dtg)
+        assert abs(dtg - dto) <= 1e-13 * dto
+    _compare(nso, nsg, 1e-11)
+    Gg.destroy()
+
+
+def test_advection_operator_matches_oracle():
+    """test/small_test/navier_stokes/advection/advection.f90 calls add_advection directly."""
+    Go, Gg, nso, nsg, dt = _setup_ns((32, 32, 1), ["Periodic"] * 4, 2, 2 * PI, 1.0, fo.init_tgv2d, 2.0)
+    ro, rg = fo.Vector(Go, 0), fb.vector(Gg, 0)
+    nso.add_advection(ro)
+    nsg.add_advection(rg)
+    rg.pull()
+    for a, b in zip(rg.comps, ro.comps):
+        assert rel_l2(a.I, b.I) < 1e-13
+    Gg.destroy()
+
+
+def test_status_line_and_errors():
+    Gg = fb.grid().setup(16, 16, 16, 1.0, 1.0, 1.0)
+    ns = fb.Solver(Gg)
+    with pytest.raises(fb.FenError):            # step before init_solver
+        ns.navier_stokes_solver(1, 1e-3)
+    ns.init_solver()
+    with pytest.raises(fb.FenError):            # dt_o unset: set_timestep not called
+        ns.navier_stokes_solver(1, 1e-3)
+    dt = ns.set_timestep(1.0)
+    ns.navier_stokes_solver(1, dt)
+    line = ns.print_solver_status(1, dt, dt)
+    assert line.startswith("step:       1 time: ") and "maxdiv:" in line and "maxCFL:" in line
+    Gg.destroy()

@@ -1,0 +1,64 @@
+"""CPU-only checks of the product's host side: the C-ABI library builds, loads, exports every symbol
+include/fen_gpu.h declares, fails loudly without a device, and the FFT index logic is right."""
+import os
+import re
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from fen_b200 import build, _lib
+    build.build()
+    return _lib.load()
+
+
+def test_every_declared_symbol_is_exported_and_bound(lib):
+    from fen_b200 import _lib
+    hdr = open(os.path.join(ROOT, "include", "fen_gpu.h")).read()
+    declared = set(re.findall(r"\b(fen_gpu_[a-z_0-9]+)\s*\(", hdr))
+    assert declared, "no declarations parsed"
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    for name in declared:
+        assert hasattr(lib, name)
+    out = subprocess.run(["nm", "-D", "--defined-only", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    exported = set(re.findall(r" T (fen_gpu_[a-z_0-9]+)", out))
+    assert declared <= exported
+
+
+def test_library_is_sm100a_and_has_no_torch_dependency(lib):
+    from fen_b200 import _lib
+    out = subprocess.run(["cuobjdump", "-lelf", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    assert "sm_100a" in out
+    ldd = subprocess.run(["ldd", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    assert "torch" not in ldd and "libcufft" not in ldd
+
+
+def test_no_cpu_fallback_without_device(lib):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a device is present")
+    import fen_b200 as fb
+    with pytest.raises(fb.FenError) as e:
+        fb.grid().setup(16, 16, 16, 1.0, 1.0, 1.0)
+    assert "no CPU fallback" in str(e.value)
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "fen_b200")
+    for dp, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                assert "oracle" not in open(os.path.join(dp, f)).read().replace("oracle's", ""), f
+
+
+def test_fft_core_index_logic_on_cpu():
+    exe = os.path.join(ROOT, "build", "test_fft_core")
+    os.makedirs(os.path.dirname(exe), exist_ok=True)
+    subprocess.run(["nvcc", "-std=c++17", "-O1", "-Wno-deprecated-gpu-targets", "-o", exe,
+                    os.path.join(ROOT, "tests", "cpu", "test_fft_core.cu")], check=True)
+    r = subprocess.run([exe], capture_output=True, text=True)
+    assert r.returncode == 0 and "OK" in r.stdout, r.stdout
