@@ -1,0 +1,364 @@
+#!/usr/bin/env python
+"""bench.py -- NS timestep throughput (Mcell-updates/s) of the B200 path, BASELINE.json's metric.
+
+    python bench.py --gpus N --steps K --warmup W              # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K ...    # CPU restatement of the reference
+
+A "step" is one full ``navier_stokes_solver`` call (predictor + Poisson RHS + Poisson solve +
+correction + pressure update + checks) on the workload named in ``config.workload``:
+BASELINE.json configs[1] (3-D periodic Taylor-Green vortex 512^3, fp64, ppp Poisson) at N = 1, and
+z-slabs of the same case (512^3 per GPU, weak scaling) at N > 1.
+
+One JSON line is printed by rank 0.  ``value`` = device-resident throughput (fields already in
+HBM), ``e2e`` = the same step driven through the public API with HOST (pinned) arrays: every step
+pushes u, v, w, p to the device and pulls them back.  ``roofline`` is for the dominant kernel,
+timed live with CUDA events on the library's stream; ``cpu_baseline`` times the CPU oracle on a
+bounded sample of the same workload on this box's host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+PI = float(np.arccos(-1.0))
+# algorithmic bytes per cell per launch
+KERNEL_BYTES_PER_CELL = {
+    "pred": 104.0, "poisson_rhs": 32.0, "corr": 72.0, "check": 24.0,
+    "fft_x_r2c": 16.0, "fft_x_c2r": 16.0, "fft_lines_fwd": 16.0, "fft_lines_inv": 16.0,
+    "fft_solve": 16.0, "thomas_fwd": 16.0, "thomas_bwd": 16.0,
+}
+STEP_BYTES_PER_CELL = 312.0
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons while the timed region runs."""
+
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.index, self.rows, self._stop, self._t = index, [], threading.Event(), None
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True,
+                                     timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            self._stop.wait(0.2)
+
+    def __enter__(self):
+        self._t = threading.Thread(target=self._run, daemon=True)
+        self._t.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        self._t.join(timeout=6)
+
+    def summary(self):
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx = float(r[1])
+                for n, v in zip(names, r[2:6]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                continue
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def init_tgv3d_slab(shape, delta, k0, pinned):
+    """Taylor-Green initial condition of config 2 on one z-slab (global plane offset k0), with ghosts
+    left to update_ghost_nodes.  Returns host arrays (nx+2, ny+2, nzl+2), Fortran order."""
+    import torch
+    nx, ny, nzl = shape
+
+    def alloc():
+        n = (nx + 2) * (ny + 2) * (nzl + 2)
+        t = torch.empty(n, dtype=torch.float64, pin_memory=pinned)
+        return t, t.numpy().reshape((nx + 2, ny + 2, nzl + 2), order="F")
+
+    i = np.arange(1, nx + 1, dtype=np.float64)
+    j = np.arange(1, ny + 1, dtype=np.float64)
+    k = np.arange(1, nzl + 1, dtype=np.float64) + k0
+    sx, cxh = np.sin(i * delta), np.cos((i - 0.5) * delta)
+    cyh, sy = np.cos((j - 0.5) * delta), np.sin(j * delta)
+    czh = np.cos((k - 0.5) * delta)
+    keep, out = [], []
+    for m in range(4):
+        t, a = alloc()
+        a[...] = 0.0
+        keep.append(t)
+        out.append(a)
+    u, v, w, p = out
+    # plane by plane to keep temporaries small
+    uxy = sx[:, None] * cyh[None, :]
+    vxy = -cxh[:, None] * sy[None, :]
+    pxy = np.cos(2.0 * (i - 0.5) * delta)[:, None] + np.cos(2.0 * (j - 0.5) * delta)[None, :]
+    for kk in range(nzl):
+        u[1:-1, 1:-1, kk + 1] = uxy * czh[kk]
+        v[1:-1, 1:-1, kk + 1] = vxy * czh[kk]
+        p[1:-1, 1:-1, kk + 1] = (1.0 / 16.0) * pxy * (np.cos(2.0 * (k[kk] - 0.5) * delta) + 2.0)
+    return keep, (u, v, w, p)
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the CPU restatement of the reference (oracle/), all host threads."""
+    if rank != 0:
+        return
+    from oracle import fen_oracle as fo
+    n = args.cpu_size
+    cores = os.cpu_count() or 1
+    fo.set_workers(cores)
+    G = fo.Grid(n, n, n, 2 * PI, 2 * PI, 2 * PI)
+    ns = fo.NavierStokes(G, 1.0, 0.01)
+    fo.init_tgv3d(ns)
+    ns.CFL = 0.25
+    dt = ns.set_timestep(1.0)
+    for s in range(args.warmup):
+        ns.navier_stokes_solver(s + 1, dt)
+    t0 = time.perf_counter()
+    for s in range(args.steps):
+        ns.navier_stokes_solver(args.warmup + s + 1, dt)
+    t = time.perf_counter() - t0
+    val = n ** 3 * args.steps / t / 1e6
+    sample = "%d^3 slab-free sample of the 512^3 Taylor-Green case, %d steps" % (n, args.steps)
+    line = {
+        "impl": "reference", "metric": "NS timestep Mcell-updates/s", "value": val, "unit": "Mcell-updates/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "3D periodic Taylor-Green vortex 512^3 fp64, ppp Poisson (CPU arm: bounded %d^3 "
+                               "sample)" % n, "grid": [n, n, n], "nu": 0.01, "CFL": 0.25},
+        "cpu_baseline": {"value": val, "unit": "Mcell-updates/s", "cores": cores, "kind": "port", "sample": sample,
+                         "note": "numpy/scipy restatement of the reference's CPU path (oracle/), not the "
+                                 "gfortran/FFTW/2decomp binary (no Fortran toolchain in this image)"},
+        "e2e": {"value": val, "unit": "Mcell-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def cpu_baseline(budget_s=20.0):
+    from oracle import fen_oracle as fo
+    cores = os.cpu_count() or 1
+    fo.set_workers(cores)
+    n = 128
+    G = fo.Grid(n, n, n, 2 * PI, 2 * PI, 2 * PI)
+    ns = fo.NavierStokes(G, 1.0, 0.01)
+    fo.init_tgv3d(ns)
+    ns.CFL = 0.25
+    dt = ns.set_timestep(1.0)
+    ns.navier_stokes_solver(1, dt)
+    t0 = time.perf_counter()
+    steps = 0
+    while steps < 3 or (time.perf_counter() - t0 < budget_s and steps < 12):
+        steps += 1
+        ns.navier_stokes_solver(steps + 1, dt)
+    t = time.perf_counter() - t0
+    return {"value": n ** 3 * steps / t / 1e6, "unit": "Mcell-updates/s", "cores": cores, "kind": "port",
+            "sample": "%d steps of the same Taylor-Green case at %d^3 (1 warm-up), numpy/scipy oracle" % (steps, n)}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--size", type=int, default=512, help="cells per direction per GPU (config 2: 512)")
+    ap.add_argument("--cpu-size", type=int, default=128)
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else max(args.warmup, 1)
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    import fen_b200 as fb
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the B200 path has no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    if world != args.gpus:
+        raise SystemExit("bench.py: --gpus %d but WORLD_SIZE %d (launch with torch.distributed.run)" % (args.gpus, world))
+
+    n = args.size
+    nx, ny, nz = n, n, n * world          # weak scaling: 512^3 per GPU, slabs in z
+    L = 2 * PI
+    G = fb.grid().setup(nx, ny, nz, L, L, L * world, pcol=world, rank=rank, device=local_rank)
+    if world > 1:
+        def all_gather(b):
+            out = [None] * world
+            dist.all_gather_object(out, b)
+            return out
+        G.connect(all_gather)
+    ns = fb.Solver(G, 1.0, 0.01).init_solver()
+    ns.CFL = 0.25
+    dt = ns.set_timestep(1.0)
+    keep, (u, v, w, p) = init_tgv3d_slab(G.nloc, G.delta, G.lo[2] - 1, pinned=True)
+    ns.v.x.f, ns.v.y.f, ns.v.z.f, ns.p.f = u, v, w, p
+    ns.v.push(); ns.p.push()
+    ns.v.update_ghost_nodes(); ns.p.update_ghost_nodes()
+    G.synchronize()
+    stream = torch.cuda.ExternalStream(G.lib.fen_gpu_stream(G.ctx))
+    ncell = nx * ny * nz
+
+    def barrier():
+        G.synchronize()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        G.synchronize()
+        torch.cuda.synchronize()
+
+    def timed(fn, k):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for s in range(k):
+            fn(s)
+        e1.record(stream)
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
+    step_no = [0]
+
+    def dev_step(_):
+        step_no[0] += 1
+        ns.navier_stokes_solver(step_no[0], dt)
+
+    for s in range(args.warmup):
+        dev_step(s)
+    l0 = ns.launch_count()
+    with ClockSampler(local_rank) as cs:
+        ms = timed(dev_step, args.steps)
+    launches = ns.launch_count() - l0
+    clocks = cs.summary()
+    maxdiv, maxcfl = ns.status()
+    value = ncell * args.steps / (ms * 1e-3) / 1e6
+
+    # ---- per-kernel timing with CUDA events on the launching stream (same steps, profiled) ----
+    ns.profile(True)
+    for s in range(min(args.steps, 5)):
+        dev_step(s)
+    prof = ns.profile_read()
+    ns.profile(False)
+    peak, peak_src = load_peaks()
+    ncell_loc = G.nloc[0] * G.nloc[1] * G.nloc[2]
+    kernels = []
+    for name, (tms, cnt) in prof.items():
+        if cnt == 0:
+            continue
+        per = tms / cnt
+        bpc = KERNEL_BYTES_PER_CELL.get(name)
+        gbs = (bpc * ncell_loc / (per * 1e-3) / 1e9) if bpc else None
+        kernels.append({"kernel": name, "launches_per_step": cnt / min(args.steps, 5), "ms_per_launch": per,
+                        "ms_per_step": tms / min(args.steps, 5), "alg_bytes_per_cell": bpc,
+                        "achieved_GBs": gbs, "frac": (gbs / peak) if gbs else None})
+    kernels.sort(key=lambda d: -d["ms_per_step"])
+    poisson_ms = sum(d["ms_per_step"] for d in kernels
+                     if d["kernel"].startswith(("fft_", "thomas_", "mean_line")))
+    dom = next((d for d in kernels if d["achieved_GBs"]), None)
+    roofline = None
+    if dom:
+        roofline = {"bound": "hbm", "kernel": dom["kernel"], "achieved": dom["achieved_GBs"], "peak": peak,
+                    "unit": "GB/s", "frac": dom["frac"], "traffic": None, "peak_source": peak_src,
+                    "alg_bytes_per_launch": dom["alg_bytes_per_cell"] * ncell_loc,
+                    "step_achieved": STEP_BYTES_PER_CELL * ncell_loc / (ms / args.steps * 1e-3) / 1e9,
+                    "step_frac": STEP_BYTES_PER_CELL * ncell_loc / (ms / args.steps * 1e-3) / 1e9 / peak}
+
+    # ---- end to end: host (pinned) arrays in, host arrays out, every step -----------------------
+    e2e = None
+    if not args.no_e2e:
+        fields = [ns.v.x, ns.v.y, ns.v.z, ns.p]
+        nbytes = sum(f.f.nbytes for f in fields)
+
+        def e2e_step(_):
+            for f in fields:
+                f.push()
+            step_no[0] += 1
+            ns.navier_stokes_solver(step_no[0], dt)
+            for f in fields:
+                f.pull()
+            ns.status()
+
+        ns.v.pull(); ns.p.pull()
+        e2e_step(0)
+        ms_e = timed(e2e_step, args.e2e_steps)
+        e2e = {"value": ncell * args.e2e_steps / (ms_e * 1e-3) / 1e6, "unit": "Mcell-updates/s",
+               "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": nbytes + 16, "ms_per_step": ms_e / args.e2e_steps,
+               "what": "push u,v,w,p from pinned host arrays + navier_stokes_solver + pull u,v,w,p + status, "
+                       "every step (dv_o stays on the device: no driver touches it)"}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu = cpu_baseline()
+
+    if rank == 0:
+        line = {
+            "metric": "NS timestep Mcell-updates/s", "value": value, "unit": "Mcell-updates/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "3D periodic Taylor-Green vortex %d^3 per GPU fp64, ppp FFT Poisson "
+                                   "(BASELINE configs[1])" % n, "grid": [nx, ny, nz], "decomposition": "z-slabs x%d" % world,
+                       "nu": 0.01, "CFL": 0.25, "dt": dt, "l2": "working set (>= 12 GB) exceeds the 126 MB L2; no flush needed"},
+            "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
+            "cpu_baseline": cpu, "kernels": kernels,
+            "poisson_solve_ms": poisson_ms,
+            "check": {"maxdiv": maxdiv, "maxCFL": maxcfl},
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    G.destroy()
+
+
+if __name__ == "__main__":
+    main()

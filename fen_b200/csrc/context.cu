@@ -358,6 +358,7 @@ int fen_gpu_update_halos(fen_ctx* c, int id) {
 int fen_gpu_max_value(fen_ctx* c, int id, double* out) {
     Field* f;
     FEN_TRY(field_check(c, id, &f));
+    FEN_TRY(ensure_red(c));
     FEN_TRY(reduce_field(c, f->d, 0, c->d_red));
     if (c->g.nranks > 1) FEN_TRY(comm_allreduce(c, c->d_red, 1, 0));      // scalar.f90:194
     FEN_TRY(fetch_red(c, 1));
@@ -369,6 +370,7 @@ int fen_gpu_max_value(fen_ctx* c, int id, double* out) {
 int fen_gpu_integral(fen_ctx* c, int id, double* out) {
     Field* f;
     FEN_TRY(field_check(c, id, &f));
+    FEN_TRY(ensure_red(c));
     FEN_TRY(reduce_field(c, f->d, 1, c->d_red));
     if (c->g.nranks > 1) FEN_TRY(comm_allreduce(c, c->d_red, 1, 1));      // scalar.f90:214
     FEN_TRY(fetch_red(c, 1));

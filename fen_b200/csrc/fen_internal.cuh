@@ -130,6 +130,7 @@ int op_divergence(fen_ctx* c, int vx, int s);
 int op_laplacian(fen_ctx* c, int vx, int ox);
 int op_center_to_face(fen_ctx* c, int s, int vx);
 int op_explicit_terms(fen_ctx* c, int rhs_x, bool advection_only);
+int ensure_red(fen_ctx* c);
 int reduce_field(fen_ctx* c, const double* f, int op, double* d_out);   // op 0 max, 1 sum
 int field_is_uniform(fen_ctx* c, const double* f, bool* uniform, double* value);
 // poisson.cu

@@ -557,7 +557,7 @@ int ns_correct(fen_ctx* c, double dt) {
     return ghost_update(c, FEN_P, 1);                  // navier_stokes.f90:564
 }
 
-static int ensure_red(fen_ctx* c) {
+int ensure_red(fen_ctx* c) {
     const long long nb = st_blocks(c->L);
     if (c->d_red && c->red_blocks >= nb) return FEN_OK;
     if (c->d_red) cudaFree(c->d_red);

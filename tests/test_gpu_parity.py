@@ -212,10 +212,12 @@ def _compare(nso, nsg, tol):
     return errs
 
 
-def _setup_ns(n, bc, ndim, L, nu, init, U, g=None):
+def _setup_ns(n, bc, ndim, L, nu, init, U, g=None, cfl=1.0):
     Go, Gg = make_pair(n, bc=bc, ndim=ndim, L=L)
     nso = fo.NavierStokes(Go, 1.0, nu)
     nsg = fb.Solver(Gg, 1.0, nu).init_solver()
+    nso.CFL = cfl
+    nsg.CFL = cfl
     if g is not None:
         nso.g = list(g)
         nsg.g = list(g)
@@ -240,7 +242,12 @@ def test_one_step_tgv3d_matches_oracle(n):
 
 
 def test_100_steps_tgv3d_matches_oracle():
-    Go, Gg, nso, nsg, dt = _setup_ns((64, 64, 64), ["Periodic"] * 6, 3, 2 * PI, 0.01, fo.init_tgv3d, 1.0)
+    """100 steps of the laminar Taylor-Green case of BASELINE config 2.  At 64^3 the time step is set
+    to the one the 512^3 grid gets from set_timestep(U=1) (CFL = 1/8 here), i.e. the same physical
+    horizon t = 1.23: at CFL = 1 on a 64^3 grid AB2 itself amplifies round-off by ~2x per step (in the
+    oracle as much as here), which says nothing about parity."""
+    Go, Gg, nso, nsg, dt = _setup_ns((64, 64, 64), ["Periodic"] * 6, 3, 2 * PI, 0.01, fo.init_tgv3d, 1.0,
+                                     cfl=0.125)
     for step in range(1, 101):
         nso.navier_stokes_solver(step, dt)
         nsg.navier_stokes_solver(step, dt)
@@ -279,15 +286,15 @@ def test_channel_ppn_steps_match_oracle():
     """BASELINE config 3 shape in miniature: walls in z, body force, ppn Poisson."""
     n = (32, 32, 16)
     bc = ["Periodic"] * 4 + ["Wall", "Wall"]
-    Go, Gg, nso, nsg, dt = _setup_ns(n, bc, 3, 2.0, 0.05, fo.init_channel, 1.0, g=(1.0, 0.0, 0.0))
+    Go, Gg, nso, nsg, dt = _setup_ns(n, bc, 3, 2.0, 0.05, fo.init_channel, 1.0, g=(1.0, 0.0, 0.0), cfl=0.05)
     assert nsg.poisson_variant == "ppn"
     nso.navier_stokes_solver(1, dt)
     nsg.navier_stokes_solver(1, dt)
     _compare(nso, nsg, 1e-12)
-    for step in range(2, 21):
+    for step in range(2, 41):
         nso.navier_stokes_solver(step, dt)
         nsg.navier_stokes_solver(step, dt)
-    _compare(nso, nsg, 1e-10)
+    _compare(nso, nsg, 1e-12)
     assert abs(nsg.maxdiv) < 1e-12
     Gg.destroy()
 
