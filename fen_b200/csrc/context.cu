@@ -50,6 +50,7 @@ static int fill_async(fen_ctx* c, double* d, double val);
 
 int field_check(fen_ctx* c, int id, Field** out, bool alloc) {
     if (!c) return set_error(FEN_ERR_ARG, "null context");
+    cudaSetDevice(c->device);      // one context per GPU; callers may drive several from one thread
     if (id < 0 || id >= (int)c->fields.size() || !c->fields[id].exists)
         return set_error(FEN_ERR_ARG, "unknown field id %d", id);
     if (c->g.ndim == 2 && id < FEN_FIELD_USER && id >= FEN_VX && (id - FEN_VX) % 3 == 2)
@@ -209,6 +210,7 @@ int fen_gpu_create(const fen_grid_desc* d, fen_ctx** out) {
     c->prm.CFL = 1.0;                     // :24
     c->prm.dt_o = 0.0;
     c->prm.constant_CFL = 0;              // :42
+    FEN_TRY(ensure_red(c));               // reduction scratch: nothing is allocated inside a step
     *out = c;
     return FEN_OK;
 }
@@ -218,7 +220,7 @@ int fen_gpu_destroy(fen_ctx* c) {
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     poisson_destroy(c);
-    comm_destroy(c);
+    comm_destroy(c);     // multi-rank: the caller barriers first so that no peer is still storing here
     for (auto& f : c->fields) free_field(f);
     for (int m = 0; m < 3; ++m) if (c->vnew[m]) cudaFree(c->vnew[m]);
     if (c->d_red) cudaFree(c->d_red);
@@ -231,8 +233,9 @@ int fen_gpu_destroy(fen_ctx* c) {
 
 int fen_gpu_synchronize(fen_ctx* c) {
     if (!c) return set_error(FEN_ERR_ARG, "null context");
+    FEN_CUDA(cudaSetDevice(c->device));
     FEN_CUDA(cudaStreamSynchronize(c->stream));
-    return FEN_OK;
+    return comm_check(c);
 }
 
 int fen_gpu_local_bounds(fen_ctx* c, int lo[3], int hi[3]) {
@@ -295,7 +298,7 @@ int fen_gpu_pull(fen_ctx* c, int id, double* host, int gl) {
     if (!host) return set_error(FEN_ERR_ARG, "null host pointer");
     FEN_TRY(copy_field(c, *f, host, gl, false));
     FEN_CUDA(cudaStreamSynchronize(c->stream));
-    return FEN_OK;
+    return comm_check(c);
 }
 
 int fen_gpu_set_to_value(fen_ctx* c, int id, double val) {
@@ -385,7 +388,11 @@ int fen_gpu_divergence(fen_ctx* c, int vx, int s) { return c ? op_divergence(c, 
 int fen_gpu_laplacian(fen_ctx* c, int vx, int ox) { return c ? op_laplacian(c, vx, ox) : set_error(FEN_ERR_ARG, "null context"); }
 int fen_gpu_center_to_face(fen_ctx* c, int s, int vx) { return c ? op_center_to_face(c, s, vx) : set_error(FEN_ERR_ARG, "null context"); }
 
-int fen_gpu_init_poisson_solver(fen_ctx* c) { return c ? poisson_init(c) : set_error(FEN_ERR_ARG, "null context"); }
+int fen_gpu_init_poisson_solver(fen_ctx* c) {
+    if (!c) return set_error(FEN_ERR_ARG, "null context");
+    FEN_CUDA(cudaSetDevice(c->device));
+    return poisson_init(c);
+}
 int fen_gpu_solve_poisson(fen_ctx* c, int id) {
     Field* f;
     FEN_TRY(field_check(c, id, &f));
@@ -401,6 +408,7 @@ const char* fen_gpu_poisson_variant(fen_ctx* c) { return c ? poisson_variant(c) 
 
 int fen_gpu_init_solver(fen_ctx* c) {
     if (!c) return set_error(FEN_ERR_ARG, "null context");
+    FEN_CUDA(cudaSetDevice(c->device));
     // allocate_navier_stokes_fields, navier_stokes.f90:759-768 (device memory is committed lazily)
     const int gl1[] = {FEN_P, FEN_PHI, FEN_RHO, FEN_MU, FEN_VX, FEN_VY, FEN_VZ};
     for (int id : gl1) {
@@ -416,6 +424,20 @@ int fen_gpu_init_solver(fen_ctx* c) {
     wire_bc(c);
     int r = poisson_init(c);               // solver.f90:61
     if (r != FEN_OK) return r;
+    // everything the time step touches is allocated here, so that navier_stokes_solver itself never
+    // calls cudaMalloc (a device-wide synchronisation that must not happen while a peer rank waits on us)
+    const int nc = c->g.ndim;
+    Field* f;
+    FEN_TRY(field_check(c, FEN_P, &f));
+    FEN_TRY(field_check(c, FEN_PHI, &f));
+    for (int m = 0; m < nc; ++m) {
+        FEN_TRY(field_check(c, FEN_VX + m, &f));
+        FEN_TRY(field_check(c, FEN_DVOX + m, &f));
+        if (!c->vnew[m]) {
+            FEN_CUDA(cudaMalloc(&c->vnew[m], c->L.elems * sizeof(double)));
+            FEN_CUDA(cudaMemsetAsync(c->vnew[m], 0, c->L.elems * sizeof(double), c->stream));
+        }
+    }
     c->solver_init = true;
     return FEN_OK;
 }
@@ -507,7 +529,9 @@ int fen_gpu_navier_stokes_solver(fen_ctx* c, int step, double* dt) {
 
 int fen_gpu_get_status(fen_ctx* c, double* maxdiv, double* maxCFL) {
     if (!c) return set_error(FEN_ERR_ARG, "null context");
+    FEN_CUDA(cudaSetDevice(c->device));
     FEN_CUDA(cudaStreamSynchronize(c->stream));
+    FEN_TRY(comm_check(c));
     if (c->h_red) {
         c->maxdiv = c->h_red[0];
         c->maxCFL = c->last_dt * std::max(0.0, c->h_red[1]) / c->g.delta;    // navier_stokes.f90:617

@@ -2,11 +2,14 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <map>
 #include <string>
 #include <vector>
 
 #include "../../include/fen_gpu.h"
+
+#define FEN_MAX_RANKS 16
 
 namespace fen {
 
@@ -118,8 +121,11 @@ int ghost_update(fen_ctx* c, int field, int ncomp);
 int halo_exchange(fen_ctx* c, double* const* f, int n);
 int comm_allreduce(fen_ctx* c, double* d_vals, int n, int op /*0 max, 1 sum*/);
 void comm_destroy(fen_ctx* c);
-int comm_transpose_fwd(fen_ctx* c);   // y-slab spectral layout -> z-pencil
-int comm_transpose_bwd(fen_ctx* c);
+int comm_transpose_fwd(fen_ctx* c);   // completes the y-slab -> z-pencil transpose pushed by the y FFT
+int comm_transpose_bwd(fen_ctx* c);   // completes the z-pencil -> y-slab transpose pushed by the z stage
+int comm_spectral(fen_ctx* c, double2** peerC, double2** peerCz);   // mapped spectral arrays of all ranks
+int comm_check(fen_ctx* c);           // FEN_ERR_COMM if a peer wait timed out (call after a stream sync)
+int spectral_pitch(int nx);           // complex row pitch of the half-spectrum arrays
 // stencil.cu
 int ns_predict(fen_ctx* c, double dt);
 int ns_poisson_rhs(fen_ctx* c, double dt);

@@ -41,7 +41,23 @@ struct Poisson {
     double *ta = nullptr, *tb = nullptr, *tc = nullptr;   // tridiagonal a, b, c
     double* c1 = nullptr;           // Thomas c1 table, indexed like the line layout
     int tri_n = 0;
+    bool multi = false;             // C / Cz live in the comm arena and the transposes are peer stores
+    double2* peerC[FEN_MAX_RANKS] = {};
+    double2* peerCz[FEN_MAX_RANKS] = {};
 };
+
+// Destination of the fused transposes (C3 in SURVEY.md: transpose_y_to_z / z_to_y, poisson.f90:982,1015):
+// element `idx` of the line a block has just transformed belongs to rank idx / blk; it is stored straight
+// into that rank's array (mapped peer memory, comm.cu) at the position the next stage reads it from.
+struct ScArgs {
+    double2* peer[FEN_MAX_RANKS];
+    int sh, mask;          // blk = 1 << sh
+    long long dsl, dso;    // strides of (idx % blk) and of the outer index in the destination
+    int o0;                // global offset of this rank's outer index in the destination
+};
+__device__ __forceinline__ double2* sc_dst(const ScArgs& q, int kx, int idx, int outer) {
+    return q.peer[idx >> q.sh] + kx + q.dsl * (idx & q.mask) + q.dso * (q.o0 + outer);
+}
 
 static inline double f32(long long n) { return (double)(float)n; }   // Fortran float(n), hazard H1
 
@@ -175,25 +191,28 @@ struct LArgs {
     double norm;           // float(nx*ny*nz)  (poisson.f90:992)
 };
 
-template <int Lf, int DIR, int NL>
-__global__ void __launch_bounds__(NL* FftPlan<Lf>::T) k_fft_lines(LArgs a) {
+template <int Lf, int DIR, int NL, bool SC>
+__global__ void __launch_bounds__(NL* FftPlan<Lf>::T) k_fft_lines(LArgs a, ScArgs q) {
     extern __shared__ double2 s[];
     constexpr int T = FftPlan<Lf>::T;
     const int tid = threadIdx.x;
     const int line = tid % NL, t = tid / NL;
-    double2* base = a.C + (size_t)blockIdx.x * NL + line + a.so * blockIdx.y;
+    const int kx = blockIdx.x * NL + line;
+    double2* base = a.C + kx + a.so * blockIdx.y;
     for (int idx = t; idx < Lf; idx += T) s[idx * NL + line] = base[a.sl * idx];
     __syncthreads();
     fft_lines<Lf, DIR>(s, NL, line, t, true, a.tw);
     const double sc = a.scale;
     for (int idx = t; idx < Lf; idx += T) {
         double2 v = s[idx * NL + line];
-        base[a.sl * idx] = make_double2(v.x * sc, v.y * sc);
+        v = make_double2(v.x * sc, v.y * sc);
+        if (SC) *sc_dst(q, kx, idx, blockIdx.y) = v;
+        else base[a.sl * idx] = v;
     }
 }
 
-template <int Lf, int NL>
-__global__ void __launch_bounds__(NL* FftPlan<Lf>::T) k_fft_solve(LArgs a) {
+template <int Lf, int NL, bool SC>
+__global__ void __launch_bounds__(NL* FftPlan<Lf>::T) k_fft_solve(LArgs a, ScArgs q) {
     extern __shared__ double2 s[];
     constexpr int T = FftPlan<Lf>::T;
     const int tid = threadIdx.x;
@@ -218,7 +237,10 @@ __global__ void __launch_bounds__(NL* FftPlan<Lf>::T) k_fft_solve(LArgs a) {
     }
     __syncthreads();
     fft_lines<Lf, +1>(s, NL, line, t, true, a.tw);
-    for (int idx = t; idx < Lf; idx += T) base[a.sl * idx] = s[idx * NL + line];
+    for (int idx = t; idx < Lf; idx += T) {
+        if (SC) *sc_dst(q, kx, idx, blockIdx.y) = s[idx * NL + line];
+        else base[a.sl * idx] = s[idx * NL + line];
+    }
 }
 
 // =================================================================================================
@@ -232,6 +254,7 @@ struct TArgs {
     const double* a; const double* b; const double* c;
     const double* lx; const double* lo;     // lo == nullptr in 2-D
     int form2d;
+    int mean;              // subtract the mean of phi (pn, ppn): see k_thomas_bwd
 };
 
 // pivot term shared by both sweeps: 3-D: ((b + lx) + lo) - a*c1prev ; 2-D uses its own groupings
@@ -324,48 +347,53 @@ __global__ void __launch_bounds__(128) k_thomas_fwd(TArgs g) {
     }
 }
 
-__global__ void __launch_bounds__(128) k_thomas_bwd(TArgs g) {
+// Back substitution.  SC: the solution is stored straight into the rank that owns the z plane (fused
+// transpose_z_to_y).  Mean removal (poisson.f90:1159-1171, :398-410): the mean of phi over the domain
+// equals the average along the last direction of the (kx, ky) = (0, 0) spectral line, so the one thread
+// that owns that line subtracts it there -- O(n) work instead of two sweeps over the real field
+// (hazard H4).
+template <bool SC>
+__global__ void __launch_bounds__(128) k_thomas_bwd(TArgs g, ScArgs q) {
     const int kx = blockIdx.x * blockDim.x + threadIdx.x;
     const int o = blockIdx.y;
     if (kx >= g.npc) return;
     double2* C = g.C + kx + g.so * o;
     const double* c1t = g.c1 + kx + g.so * o;
     const int n = g.n;
+    const bool mean_line = g.mean && kx == 0 && (g.o0 + o) == 0;
+    const bool direct = SC && !mean_line;
     double2 x = C[g.sl * (n - 1)];                                  // :1124-1128
+    double acc = x.x;
+    if (direct) *sc_dst(q, kx, n - 1, o) = x;
     constexpr int U = 8;
     for (int l0 = n - 2; l0 >= 0; l0 -= U) {
         double2 d[U];
         double cc[U];
 #pragma unroll
-        for (int q = 0; q < U; ++q)
-            if (l0 - q >= 0) {
-                d[q] = C[g.sl * (l0 - q)];
-                cc[q] = c1t[g.sl * (l0 - q)];
+        for (int r = 0; r < U; ++r)
+            if (l0 - r >= 0) {
+                d[r] = C[g.sl * (l0 - r)];
+                cc[r] = c1t[g.sl * (l0 - r)];
             }
 #pragma unroll
-        for (int q = 0; q < U; ++q)
-            if (l0 - q >= 0) {                                      // x = d1 - c1*x(k+1)  :1132
-                x = make_double2(__dsub_rn(d[q].x, __dmul_rn(cc[q], x.x)),
-                                 __dsub_rn(d[q].y, __dmul_rn(cc[q], x.y)));
-                C[g.sl * (l0 - q)] = x;
+        for (int r = 0; r < U; ++r)
+            if (l0 - r >= 0) {                                      // x = d1 - c1*x(k+1)  :1132
+                x = make_double2(__dsub_rn(d[r].x, __dmul_rn(cc[r], x.x)),
+                                 __dsub_rn(d[r].y, __dmul_rn(cc[r], x.y)));
+                acc += x.x;
+                if (direct) *sc_dst(q, kx, l0 - r, o) = x;
+                else C[g.sl * (l0 - r)] = x;
             }
     }
-}
-
-// mean removal (poisson.f90:1159-1171, :398-410, :491-503): the mean of phi over the domain equals
-// the average along the last direction of the (kx, ky) = (0, 0) spectral line, so it is subtracted
-// there (O(n) work) instead of sweeping the real field twice (hazard H4).
-__global__ void k_remove_mean_line(double2* C, long long sl, int n) {
-    __shared__ double sh[32];
-    double acc = 0.0;
-    for (int l = threadIdx.x; l < n; l += blockDim.x) acc += C[sl * l].x;
-    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = acc;
-    __syncthreads();
-    double tot = 0.0;
-    for (int q = 0; q < (int)blockDim.x / 32; ++q) tot += sh[q];
-    const double mean = tot / (double)n;
-    for (int l = threadIdx.x; l < n; l += blockDim.x) C[sl * l].x -= mean;
+    if (mean_line) {
+        const double mean = acc / (double)n;
+        for (int l = 0; l < n; ++l) {
+            double2 v = C[g.sl * l];
+            v.x -= mean;
+            if (SC) *sc_dst(q, kx, l, o) = v;
+            else C[g.sl * l] = v;
+        }
+    }
 }
 
 // =================================================================================================
@@ -402,8 +430,11 @@ static std::vector<double> mwn(int n, double delta, int pad) {
 void poisson_destroy(fen_ctx* c) {
     Poisson* p = c->ps;
     if (!p) return;
-    if (p->Cz && p->Cz != p->C) cudaFree(p->Cz);
-    for (void* q : {(void*)p->C, (void*)p->tw_x, (void*)p->twr_x, (void*)p->tw_y, (void*)p->tw_z,
+    if (!p->multi) {
+        if (p->Cz && p->Cz != p->C) cudaFree(p->Cz);
+        if (p->C) cudaFree(p->C);
+    }
+    for (void* q : {(void*)p->tw_x, (void*)p->twr_x, (void*)p->tw_y, (void*)p->tw_z,
                     (void*)p->mwn_x, (void*)p->mwn_y, (void*)p->mwn_z, (void*)p->ta, (void*)p->tb,
                     (void*)p->tc, (void*)p->c1})
         if (q) cudaFree(q);
@@ -444,37 +475,46 @@ static int dispatch_x(fen_ctx* c, int M, const XArgs& a, bool fwd) {
     return set_error(FEN_ERR_UNSUPPORTED, "x FFT length %d not supported (power of two, 2..2048)", 2 * M);
 }
 
-// mode 0: forward, 1: inverse, 2: fused solve
-template <int Lf, int NL> static int launch_lines(fen_ctx* c, const LArgs& a, int mode, int nchunks, int nouter) {
+// mode 0: forward, 1: inverse, 2: fused solve; sc != nullptr: scatter the result to the owning ranks
+template <int Lf, int NL> static int launch_lines(fen_ctx* c, const LArgs& a, int mode, int nchunks, int nouter,
+                                                  const ScArgs* sc) {
     constexpr int T = FftPlan<Lf>::T;
     const int bytes = Lf * NL * (int)sizeof(double2);
     static bool attr_done = false;
     if (!attr_done) {
         if (bytes > 48 * 1024) {
-            FEN_CUDA(cudaFuncSetAttribute(k_fft_lines<Lf, -1, NL>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-            FEN_CUDA(cudaFuncSetAttribute(k_fft_lines<Lf, +1, NL>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-            FEN_CUDA(cudaFuncSetAttribute(k_fft_solve<Lf, NL>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+            FEN_CUDA(cudaFuncSetAttribute(k_fft_lines<Lf, -1, NL, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+            FEN_CUDA(cudaFuncSetAttribute(k_fft_lines<Lf, -1, NL, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+            FEN_CUDA(cudaFuncSetAttribute(k_fft_lines<Lf, +1, NL, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+            FEN_CUDA(cudaFuncSetAttribute(k_fft_solve<Lf, NL, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+            FEN_CUDA(cudaFuncSetAttribute(k_fft_solve<Lf, NL, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
         }
         attr_done = true;
     }
     dim3 grid(nchunks, nouter), block(NL * T);
-    if (mode == 0) FEN_LAUNCH(c, "fft_lines_fwd", k_fft_lines<Lf, -1, NL><<<grid, block, bytes, c->stream>>>(a));
-    if (mode == 1) FEN_LAUNCH(c, "fft_lines_inv", k_fft_lines<Lf, +1, NL><<<grid, block, bytes, c->stream>>>(a));
-    if (mode == 2) FEN_LAUNCH(c, "fft_solve", k_fft_solve<Lf, NL><<<grid, block, bytes, c->stream>>>(a));
+    ScArgs none;
+    memset(&none, 0, sizeof(none));
+    if (mode == 0 && !sc) FEN_LAUNCH(c, "fft_lines_fwd", k_fft_lines<Lf, -1, NL, false><<<grid, block, bytes, c->stream>>>(a, none));
+    if (mode == 0 && sc) FEN_LAUNCH(c, "fft_lines_fwd_a2a", k_fft_lines<Lf, -1, NL, true><<<grid, block, bytes, c->stream>>>(a, *sc));
+    if (mode == 1) FEN_LAUNCH(c, "fft_lines_inv", k_fft_lines<Lf, +1, NL, false><<<grid, block, bytes, c->stream>>>(a, none));
+    if (mode == 2 && !sc) FEN_LAUNCH(c, "fft_solve", k_fft_solve<Lf, NL, false><<<grid, block, bytes, c->stream>>>(a, none));
+    if (mode == 2 && sc) FEN_LAUNCH(c, "fft_solve_a2a", k_fft_solve<Lf, NL, true><<<grid, block, bytes, c->stream>>>(a, *sc));
     FEN_CUDA(cudaGetLastError());
     return FEN_OK;
 }
 
-static int dispatch_lines(fen_ctx* c, int Lf, const LArgs& a, int mode, int PC, int nouter) {
+static int dispatch_lines(fen_ctx* c, int Lf, const LArgs& a, int mode, int PC, int nouter, const ScArgs* sc = nullptr) {
     switch (Lf) {
-#define FEN_CASE(l) case l: return launch_lines<l, 8>(c, a, mode, PC / 8, nouter);
+#define FEN_CASE(l) case l: return launch_lines<l, 8>(c, a, mode, PC / 8, nouter, sc);
         FEN_CASE(1) FEN_CASE(2) FEN_CASE(4) FEN_CASE(8) FEN_CASE(16) FEN_CASE(32) FEN_CASE(64)
         FEN_CASE(128) FEN_CASE(256) FEN_CASE(512) FEN_CASE(1024)
 #undef FEN_CASE
-        case 2048: return launch_lines<2048, 4>(c, a, mode, PC / 4, nouter);
+        case 2048: return launch_lines<2048, 4>(c, a, mode, PC / 4, nouter, sc);
     }
     return set_error(FEN_ERR_UNSUPPORTED, "FFT length %d not supported (power of two, 1..2048)", Lf);
 }
+
+static int log2i(int n) { int s = 0; while ((1 << s) < n) ++s; return s; }
 
 int poisson_init(fen_ctx* c) {
     if (c->ps) poisson_destroy(c);
@@ -510,18 +550,22 @@ int poisson_init(fen_ctx* c) {
     snprintf(p->variant, sizeof(p->variant), "%s", var);
     p->nx = g.nx; p->ny = g.ny; p->nz = g.nz; p->nzl = c->L.nzl;
     p->M = g.nx / 2;
-    p->PC = ((g.nx / 2 + 1) + 7) / 8 * 8;
-    const size_t nC = (size_t)p->PC * g.ny * p->nzl;
-    FEN_CUDA(cudaMalloc(&p->C, nC * sizeof(double2)));
-    FEN_CUDA(cudaMemsetAsync(p->C, 0, nC * sizeof(double2), c->stream));
-    p->Cz = p->C;
+    p->PC = spectral_pitch(g.nx);
     p->nyl = g.ny;
     if (g.nranks > 1 && g.ndim == 3) {
-        if (g.ny % g.nranks) return set_error(FEN_ERR_UNSUPPORTED, "ny must be divisible by the number of ranks");
+        // the spectral arrays live in the comm arena so that the peers can store into them
+        if (g.ny % g.nranks || !pow2(g.nranks))
+            return set_error(FEN_ERR_UNSUPPORTED, "the number of ranks must be a power of two dividing ny and nz");
+        FEN_TRY(comm_spectral(c, p->peerC, p->peerCz));
+        p->multi = true;
         p->nyl = g.ny / g.nranks;
-        const size_t nZ = (size_t)p->PC * p->nyl * g.nz;
-        FEN_CUDA(cudaMalloc(&p->Cz, nZ * sizeof(double2)));
-        FEN_CUDA(cudaMemsetAsync(p->Cz, 0, nZ * sizeof(double2), c->stream));
+        p->C = p->peerC[g.rank];
+        p->Cz = p->peerCz[g.rank];
+    } else {
+        const size_t nC = (size_t)p->PC * g.ny * p->nzl;
+        FEN_CUDA(cudaMalloc(&p->C, nC * sizeof(double2)));
+        FEN_CUDA(cudaMemsetAsync(p->C, 0, nC * sizeof(double2), c->stream));
+        p->Cz = p->C;
     }
     const double d = g.delta;
     FEN_TRY(upload(&p->tw_x, twiddles(p->M, p->M, p->M)));
@@ -551,7 +595,7 @@ int poisson_init(fen_ctx* c) {
         FEN_TRY(upload(&p->tb, b));
         FEN_TRY(upload(&p->tc, cc));
         TArgs t;
-        t.C = nullptr;
+        t.C = nullptr; t.mean = 0;
         t.n = n; t.npc = p->PC; t.a = p->ta; t.b = p->tb; t.c = p->tc; t.lx = p->mwn_x;
         if (tri_y) {
             t.sl = p->PC; t.so = 0; t.nouter = 1; t.o0 = 0; t.lo = nullptr; t.form2d = 1;
@@ -592,33 +636,44 @@ int poisson_solve(fen_ctx* c, double* f) {
     } else if (pn) {
         TArgs t;
         t.C = p->C; t.c1 = p->c1; t.sl = p->PC; t.so = 0; t.n = g.ny; t.npc = p->PC; t.nouter = 1; t.o0 = 0;
-        t.a = p->ta; t.b = p->tb; t.c = p->tc; t.lx = p->mwn_x; t.lo = nullptr; t.form2d = 1;
+        t.a = p->ta; t.b = p->tb; t.c = p->tc; t.lx = p->mwn_x; t.lo = nullptr; t.form2d = 1; t.mean = 1;
         dim3 grid((p->PC + 127) / 128, 1), block(128);
+        ScArgs none;
+        memset(&none, 0, sizeof(none));
         FEN_LAUNCH(c, "thomas_fwd", k_thomas_fwd<<<grid, block, 0, c->stream>>>(t));
-        FEN_LAUNCH(c, "thomas_bwd", k_thomas_bwd<<<grid, block, 0, c->stream>>>(t));
-        FEN_LAUNCH(c, "mean_line", k_remove_mean_line<<<1, 256, 0, c->stream>>>(p->C, p->PC, g.ny));
+        FEN_LAUNCH(c, "thomas_bwd", k_thomas_bwd<false><<<grid, block, 0, c->stream>>>(t, none));
     } else {
-        // y forward (poisson.f90:975-979 / :1080-1087)
+        // y forward (poisson.f90:975-979 / :1080-1087); multi-rank: the result is stored straight into the
+        // z-pencil arrays of the owning ranks (transpose_y_to_z, :982 / :1090)
+        ScArgs sf, sb;
+        memset(&sf, 0, sizeof(sf));
+        memset(&sb, 0, sizeof(sb));
+        if (multi) {
+            for (int r = 0; r < g.nranks; ++r) { sf.peer[r] = p->peerCz[r]; sb.peer[r] = p->peerC[r]; }
+            sf.sh = log2i(p->nyl); sf.mask = p->nyl - 1;
+            sf.dsl = p->PC; sf.dso = (long long)p->PC * p->nyl; sf.o0 = g.rank * p->nzl;
+            sb.sh = log2i(p->nzl); sb.mask = p->nzl - 1;
+            sb.dsl = (long long)p->PC * g.ny; sb.dso = p->PC; sb.o0 = g.rank * p->nyl;
+        }
         la.C = p->C; la.sl = p->PC; la.so = (long long)p->PC * g.ny; la.tw = p->tw_y;
         la.scale = ppn ? 1.0 / f32(g.ny) : 1.0;
-        FEN_TRY(dispatch_lines(c, g.ny, la, 0, p->PC, p->nzl));
-        if (multi) FEN_TRY(comm_transpose_fwd(c));             // transpose_y_to_z (:982 / :1090)
+        FEN_TRY(dispatch_lines(c, g.ny, la, 0, p->PC, p->nzl, multi ? &sf : nullptr));
+        if (multi) FEN_TRY(comm_transpose_fwd(c));
         double2* Z = p->Cz;
         const long long slz = (long long)p->PC * p->nyl;
         if (ppp) {
             la.C = Z; la.sl = slz; la.so = p->PC; la.tw = p->tw_z; la.scale = 1.0; la.o0 = multi ? g.rank * p->nyl : 0;
             la.lo = p->mwn_y; la.ll = p->mwn_z; la.norm = f32((long long)g.nx * g.ny * g.nz);
-            FEN_TRY(dispatch_lines(c, g.nz, la, 2, p->PC, p->nyl));
+            FEN_TRY(dispatch_lines(c, g.nz, la, 2, p->PC, p->nyl, multi ? &sb : nullptr));
         } else {
             TArgs t;
             t.C = Z; t.c1 = p->c1; t.sl = slz; t.so = p->PC; t.n = g.nz; t.npc = p->PC; t.nouter = p->nyl;
             t.o0 = multi ? g.rank * p->nyl : 0;
-            t.a = p->ta; t.b = p->tb; t.c = p->tc; t.lx = p->mwn_x; t.lo = p->mwn_y; t.form2d = 0;
+            t.a = p->ta; t.b = p->tb; t.c = p->tc; t.lx = p->mwn_x; t.lo = p->mwn_y; t.form2d = 0; t.mean = 1;
             dim3 grid((p->PC + 127) / 128, p->nyl), block(128);
             FEN_LAUNCH(c, "thomas_fwd", k_thomas_fwd<<<grid, block, 0, c->stream>>>(t));
-            FEN_LAUNCH(c, "thomas_bwd", k_thomas_bwd<<<grid, block, 0, c->stream>>>(t));
-            if (!multi || g.rank == 0)
-                FEN_LAUNCH(c, "mean_line", k_remove_mean_line<<<1, 256, 0, c->stream>>>(Z, slz, g.nz));
+            if (multi) FEN_LAUNCH(c, "thomas_bwd_a2a", k_thomas_bwd<true><<<grid, block, 0, c->stream>>>(t, sb));
+            else FEN_LAUNCH(c, "thomas_bwd", k_thomas_bwd<false><<<grid, block, 0, c->stream>>>(t, sb));
         }
         FEN_CUDA(cudaGetLastError());
         if (multi) FEN_TRY(comm_transpose_bwd(c));             // transpose_z_to_y (:1015 / :1138)

@@ -460,10 +460,7 @@ int ns_predict(fen_ctx* c, double dt) {
     if (d3) FEN_TRY(field_check(c, FEN_DVOZ, &dz));
     a.dvox = dx->d; a.dvoy = dy->d; a.dvoz = dz ? dz->d : nullptr;
     for (int m = 0; m < (d3 ? 3 : 2); ++m)
-        if (!c->vnew[m]) {
-            FEN_CUDA(cudaMalloc(&c->vnew[m], c->L.elems * sizeof(double)));
-            FEN_CUDA(cudaMemsetAsync(c->vnew[m], 0, c->L.elems * sizeof(double), c->stream));
-        }
+        if (!c->vnew[m]) return set_error(FEN_ERR_STATE, "init_solver has not allocated the predictor buffers");
     a.un = c->vnew[0]; a.vn = c->vnew[1]; a.wn = c->vnew[2];
     a.dt = dt;
     a.A = 1.0 + 0.5 * dt / c->prm.dt_o;      // navier_stokes.f90:157

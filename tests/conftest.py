@@ -3,6 +3,10 @@ import sys
 
 import pytest
 
+# kernels of different ranks must be able to start while a flag-wait kernel spins (tests/ranks.py runs several
+# ranks on one device): no lazy module loading.  Must be set before the CUDA runtime initialises.
+os.environ.setdefault("CUDA_MODULE_LOADING", "EAGER")
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)

@@ -1,0 +1,198 @@
+"""Multi-rank (z-slab) parity: P ranks must give the SAME BITS as one rank.
+
+The reference never asserts rank-count invariance; here it is exact because the
+decomposition only moves data: the halos are copies, the fused transposes deliver every spectral
+coefficient to the rank that needs it unchanged, the max-reductions are exact and the mean of the ppn
+solver is taken on the one rank that owns the (kx, ky) = (0, 0) line.  Ranks run as threads of this
+process on one device (tests/ranks.py); tests/test_gpu_multiprocess.py repeats the step with one process
+per GPU over CUDA IPC when the box has at least two GPUs.
+"""
+import numpy as np
+import pytest
+
+import fen_b200 as fb
+from oracle import fen_oracle as fo
+from tests.ranks import gather_interior, run_ranks, slab_grid, slab_of
+
+pytestmark = pytest.mark.gpu
+PI = fo.PI
+ZWALLS = ["Periodic"] * 4 + ["Wall", "Wall"]
+
+
+@pytest.mark.parametrize("P", [2, 4])
+@pytest.mark.parametrize("bc", [None, ZWALLS])
+def test_ghost_nodes_match_single_rank(P, bc):
+    n = (16, 8, 16)
+    rng = np.random.default_rng(5)
+    glob = [np.asfortranarray(rng.random((n[0] + 2, n[1] + 2, n[2] + 2))) for _ in range(3)]
+    L = (1.0, 0.5, 1.0)
+
+    def program(rank, P, comm):
+        G = slab_grid(rank, P, comm, n, L, bc)
+        v = fb.vector(G, 1)
+        if bc is not None:
+            # what allocate_navier_stokes_fields wires for Wall faces (Dirichlet), on the ranks that own them
+            for c in v.comps:
+                if rank == 0:
+                    c.set_bc_type("front", 1)
+                if rank == P - 1:
+                    c.set_bc_type("back", 1)
+        for c, g in zip(v.comps, glob):
+            c.f[...] = slab_of(g, rank, P, 1)
+            c.push()
+        G.synchronize()
+        comm.sync()
+        v.update_ghost_nodes()
+        mx = v.x.max_value()
+        v.pull()
+        out = [c.f.copy() for c in v.comps]
+        comm.sync()
+        G.destroy()
+        return out, mx
+
+    one = run_ranks(1, program)[0]
+    many = run_ranks(P, program)
+    nzl = n[2] // P
+    for r in range(P):
+        for m in range(3):
+            want = one[0][m][:, :, r * nzl: r * nzl + nzl + 2]
+            assert np.array_equal(many[r][0][m], want), (r, m)
+        assert many[r][1] == one[1]
+
+
+def _poisson_program(n, L, bc, rhs):
+    def program(rank, P, comm):
+        G = slab_grid(rank, P, comm, n, L, bc)
+        phi = fb.scalar(G, 1)
+        if bc is not None:
+            if rank == 0:
+                phi.set_bc_type("front", 2)
+            if rank == P - 1:
+                phi.set_bc_type("back", 2)
+        ps = fb.PoissonSolver(phi)
+        phi.f[...] = slab_of(rhs, rank, P, 1)
+        phi.push()
+        G.synchronize()
+        comm.sync()
+        ps.solve(phi)
+        phi.update_ghost_nodes()
+        phi.pull()
+        out = phi.f.copy()
+        var = ps.variant
+        comm.sync()
+        G.destroy()
+        return out, var
+    return program
+
+
+@pytest.mark.parametrize("P", [2, 4])
+@pytest.mark.parametrize("bc,variant", [(None, "ppp"), (ZWALLS, "ppn")])
+def test_poisson_matches_single_rank_and_oracle(P, bc, variant):
+    n = (32, 16, 16)
+    L = (2.0, 1.0, 1.0)
+    rng = np.random.default_rng(11)
+    rhs = np.zeros((n[0] + 2, n[1] + 2, n[2] + 2), order="F")
+    rhs[1:-1, 1:-1, 1:-1] = rng.standard_normal(n)
+    rhs[1:-1, 1:-1, 1:-1] -= rhs[1:-1, 1:-1, 1:-1].mean()
+    prog = _poisson_program(n, L, bc, rhs)
+    one = run_ranks(1, prog)[0]
+    many = run_ranks(P, prog)
+    assert one[1] == variant and all(m[1] == variant for m in many)
+    got = gather_interior([m[0] for m in many], 1)
+    assert np.array_equal(got, one[0][1:-1, 1:-1, 1:-1])
+    # and the single-rank answer is the oracle's
+    Go = fo.Grid(n[0], n[1], n[2], L[0], L[1], L[2], bc=bc)
+    po = fo.Scalar(Go, 1)
+    if bc is not None:
+        po.bc_type["front"] = po.bc_type["back"] = 2
+    po.f[...] = rhs
+    fo.PoissonSolver(po).solve(po)
+    ref = po.I
+    assert np.linalg.norm(got - ref) <= 1e-12 * np.linalg.norm(ref)
+
+
+def _ns_program(n, L, bc, nu, init, U, g, cfl, steps, constant_cfl=False):
+    Go = fo.Grid(n[0], n[1], n[2], L[0], L[1], L[2], bc=bc)
+    nso = fo.NavierStokes(Go, 1.0, nu)
+    if g is not None:
+        nso.g = list(g)
+    init(nso)
+    state = [a.f.copy() for a in (nso.v.x, nso.v.y, nso.v.z, nso.p)]
+
+    def program(rank, P, comm):
+        G = slab_grid(rank, P, comm, n, L, bc)
+        ns = fb.Solver(G, 1.0, nu)
+        if g is not None:
+            ns.g = list(g)
+        ns.init_solver()
+        ns.CFL = cfl
+        ns.constant_CFL = constant_cfl
+        dt = ns.set_timestep(U)
+        for a, s in zip((ns.v.x, ns.v.y, ns.v.z, ns.p), state):
+            a.f[...] = slab_of(s, rank, P, 1)
+            a.push()
+        G.synchronize()
+        comm.sync()
+        ns.v.update_ghost_nodes()
+        ns.p.update_ghost_nodes()
+        hist = []
+        for step in range(1, steps + 1):
+            dt = ns.navier_stokes_solver(step, dt)
+            hist.append((dt,) + ns.status())
+        ns.v.pull(); ns.p.pull()
+        out = [a.f.copy() for a in (ns.v.x, ns.v.y, ns.v.z, ns.p)]
+        comm.sync()
+        G.destroy()
+        return out, hist
+    return program, nso
+
+
+@pytest.mark.parametrize("P", [2, 4])
+def test_ns_steps_tgv3d_rank_count_invariant(P):
+    n = (32, 32, 32)
+    prog, nso = _ns_program(n, (2 * PI,) * 3, None, 0.01, fo.init_tgv3d, 1.0, None, 0.25, 5)
+    one = run_ranks(1, prog)[0]
+    many = run_ranks(P, prog)
+    nzl = n[2] // P
+    for r in range(P):
+        for m in range(4):
+            assert np.array_equal(many[r][0][m], one[0][m][:, :, r * nzl: r * nzl + nzl + 2]), (r, m)
+        assert many[r][1] == one[1]          # dt, maxdiv, maxCFL of every step: identical on all ranks
+    # the oracle agrees to the one-step tolerance
+    nso.CFL = 0.25
+    dt = nso.set_timestep(1.0)
+    for step in range(1, 6):
+        nso.navier_stokes_solver(step, dt)
+    for m, a in enumerate((nso.v.x, nso.v.y, nso.v.z, nso.p)):
+        got = gather_interior([x[0][m] for x in many], 1)
+        nrm = np.linalg.norm(a.I)
+        assert np.linalg.norm(got - a.I) <= 1e-12 * max(nrm, 1.0)
+
+
+@pytest.mark.parametrize("P", [2, 4])
+def test_ns_steps_channel_ppn_rank_count_invariant(P):
+    n = (32, 16, 16)
+    prog, _ = _ns_program(n, (2.0, 1.0, 1.0), ZWALLS, 0.05, fo.init_channel, 1.0, (1.0, 0.0, 0.0), 0.05, 6)
+    one = run_ranks(1, prog)[0]
+    many = run_ranks(P, prog)
+    nzl = n[2] // P
+    for r in range(P):
+        for m in range(4):
+            assert np.array_equal(many[r][0][m], one[0][m][:, :, r * nzl: r * nzl + nzl + 2]), (r, m)
+        assert many[r][1] == one[1]
+
+
+def test_constant_cfl_allreduce_multirank():
+    """update_timestep's max-velocity all-reduce (navier_stokes.f90:712) with 2 ranks."""
+    n = (32, 32, 32)
+    prog, _ = _ns_program(n, (2 * PI,) * 3, None, 0.01, fo.init_tgv3d, 1.0, None, 0.25, 4, constant_cfl=True)
+    one = run_ranks(1, prog)[0]
+    many = run_ranks(2, prog)
+    assert many[0][1] == one[1] and many[1][1] == one[1]
+
+
+def test_missing_connect_is_an_error():
+    G = fb.grid().setup(16, 16, 16, 1.0, 1.0, 1.0, pcol=2, rank=0)
+    with pytest.raises(fb.FenError):
+        fb.Solver(G).init_solver()
+    G.destroy()
