@@ -1,8 +1,10 @@
 // fen_internal.cuh -- internal types of libfen_gpu.so (not part of the C ABI).
 #pragma once
+#include <cuda.h>
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <tuple>
 #include <map>
 #include <string>
 #include <vector>
@@ -50,6 +52,13 @@ struct ProfEntry {
     cudaEvent_t e0, e1;
 };
 
+// cache key of a field's TMA descriptor: buffer and box shape
+struct TmapKey {
+    const double* base;
+    int bx, by;
+    bool operator<(const TmapKey& o) const { return std::tie(base, bx, by) < std::tie(o.base, o.bx, o.by); }
+};
+
 struct Poisson;   // poisson.cu
 struct Comm;      // comm.cu
 
@@ -78,6 +87,7 @@ struct fen_ctx {
 
     fen::Poisson* ps = nullptr;
     fen::Comm* comm = nullptr;
+    std::map<fen::TmapKey, CUtensorMap> tmaps;      // TMA descriptors of the field buffers (tma.cu)
 
     // measurement
     long long launches = 0;
@@ -115,6 +125,8 @@ void prof_end(fen_ctx* c, int token);
 int field_check(fen_ctx* c, int id, Field** out, bool alloc = true);
 int field_alloc(fen_ctx* c, Field& f);
 
+// tma.cu
+int field_tmap(fen_ctx* c, const double* base, int box_x, int box_y, CUtensorMap** out);
 // ghost.cu
 int ghost_update(fen_ctx* c, int field, int ncomp);
 // comm.cu

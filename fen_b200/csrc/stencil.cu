@@ -15,6 +15,7 @@
 // 256-byte runs; a block owns a (TX x TY) column of cells and marches KZ planes in z so that the
 // three z-planes a stencil needs stay in L1 while the 126 MB L2 holds the neighbouring tiles.
 #include "fen_internal.cuh"
+#include "tma.cuh"
 
 namespace fen {
 
@@ -33,77 +34,98 @@ struct StArgs {
 
 __device__ __forceinline__ double sq(double x) { return x * x; }
 
-// explicit terms dv (advection + diffusion [+ source]) at one cell; also returns rhof.
+// The 27 velocity values the explicit terms of one cell read.
+struct Sten {
+    double u0, uip, uim, ujp, ujm, ukp, ukm, uimjp, uimkp;
+    double v0, vip, vim, vjp, vjm, vkp, vkm, vipjm, vjmkp;
+    double w0, wip, wim, wjp, wjm, wkp, wkm, wipkm, wjpkm;
+};
+
+// advection (navier_stokes.f90:297-347) + diffusion (fields.f90:326-337, navier_stokes.f90:394-397) from the
+// stencil values; the one place where this arithmetic lives.  UNIT: rhof == 1 exactly, x/1 == x, so the
+// divisions are dropped without changing a bit.
+template <bool D3, bool ADV_ONLY, bool UNIT>
+__device__ __forceinline__ void explicit_from(const Sten& s, double id, double id2, double mu, double rfx, double rfy,
+                                              double rfz, double& dvx, double& dvy, double& dvz) {
+    double uuip = 0.25 * sq(s.uip + s.u0);
+    double uuim = 0.25 * sq(s.uim + s.u0);
+    double uvjp = (s.ujp + s.u0) * (s.vip + s.v0) * 0.25;
+    double uvjm = (s.u0 + s.ujm) * (s.vipjm + s.vjm) * 0.25;
+    dvx = 0.0 - (uuip - uuim) * id - (uvjp - uvjm) * id;
+    double vuip = (s.vip + s.v0) * (s.ujp + s.u0) * 0.25;
+    double vuim = (s.v0 + s.vim) * (s.uimjp + s.uim) * 0.25;
+    double vvjp = 0.25 * sq(s.vjp + s.v0);
+    double vvjm = 0.25 * sq(s.vjm + s.v0);
+    dvy = 0.0 - (vuip - vuim) * id - (vvjp - vvjm) * id;
+    dvz = 0.0;
+    if (D3) {
+        double uwkp = (s.ukp + s.u0) * (s.wip + s.w0) * 0.25;
+        double uwkm = (s.u0 + s.ukm) * (s.wipkm + s.wkm) * 0.25;
+        dvx = dvx - (uwkp - uwkm) * id;
+        double vwkp = (s.vkp + s.v0) * (s.wjp + s.w0) * 0.25;
+        double vwkm = (s.v0 + s.vkm) * (s.wjpkm + s.wkm) * 0.25;
+        dvy = dvy - (vwkp - vwkm) * id;
+        double wuip = (s.w0 + s.wip) * (s.u0 + s.ukp) * 0.25;
+        double wuim = (s.w0 + s.wim) * (s.uim + s.uimkp) * 0.25;
+        double wvjp = (s.w0 + s.wjp) * (s.v0 + s.vkp) * 0.25;
+        double wvjm = (s.w0 + s.wjm) * (s.vjm + s.vjmkp) * 0.25;
+        double wwkp = (s.w0 + s.wkp) * (s.w0 + s.wkp) * 0.25;
+        double wwkm = (s.w0 + s.wkm) * (s.w0 + s.wkm) * 0.25;
+        dvz = 0.0 - (wuip - wuim) * id - (wvjp - wvjm) * id - (wwkp - wwkm) * id;
+    }
+    if (ADV_ONLY) return;
+    double lx = ((s.uip - 2.0 * s.u0 + s.uim) + (s.ujp - 2.0 * s.u0 + s.ujm)) * id2;
+    double ly = ((s.vip - 2.0 * s.v0 + s.vim) + (s.vjp - 2.0 * s.v0 + s.vjm)) * id2;
+    if (D3) {
+        lx = lx + (s.ukp - 2.0 * s.u0 + s.ukm) * id2;
+        ly = ly + (s.vkp - 2.0 * s.v0 + s.vkm) * id2;
+        double lz = ((s.wip - 2.0 * s.w0 + s.wim) + (s.wjp - 2.0 * s.w0 + s.wjm) + (s.wkp - 2.0 * s.w0 + s.wkm)) * id2;
+        dvz = dvz + (UNIT ? mu * lz : mu * lz / rfz);
+    }
+    dvx = dvx + (UNIT ? mu * lx : mu * lx / rfx);
+    dvy = dvy + (UNIT ? mu * ly : mu * ly / rfy);
+}
+
+// explicit terms dv (advection + diffusion [+ source]) at one cell, values read from global memory
+// (general-property / 2-D / stand-alone operator path); also returns rhof.
 template <bool D3, bool GEN, bool ADV_ONLY>
 __device__ __forceinline__ void explicit_terms(const StArgs& a, long long c, double& dvx, double& dvy,
                                                double& dvz, double& rfx, double& rfy, double& rfz) {
     const long long sy = a.L.sy, sz = a.L.sz;
-    const double id = a.idelta, id2 = a.idelta2;
     const double* __restrict__ u = a.u;
     const double* __restrict__ v = a.v;
     const double* __restrict__ w = a.w;
-    const double u0 = u[c], uip = u[c + 1], uim = u[c - 1], ujp = u[c + sy], ujm = u[c - sy];
-    const double v0 = v[c], vip = v[c + 1], vim = v[c - 1], vjp = v[c + sy], vjm = v[c - sy];
-    const double uimjp = u[c - 1 + sy], vipjm = v[c + 1 - sy];
-    // ---- advection, navier_stokes.f90:297-347 -------------------------------------------------
-    double uuip = 0.25 * sq(uip + u0);
-    double uuim = 0.25 * sq(uim + u0);
-    double uvjp = (ujp + u0) * (vip + v0) * 0.25;
-    double uvjm = (u0 + ujm) * (vipjm + vjm) * 0.25;
-    dvx = 0.0 - (uuip - uuim) * id - (uvjp - uvjm) * id;
-    double vuip = (vip + v0) * (ujp + u0) * 0.25;
-    double vuim = (v0 + vim) * (uimjp + uim) * 0.25;
-    double vvjp = 0.25 * sq(vjp + v0);
-    double vvjm = 0.25 * sq(vjm + v0);
-    dvy = 0.0 - (vuip - vuim) * id - (vvjp - vvjm) * id;
-    dvz = 0.0;
-    double ukp = 0, ukm = 0, vkp = 0, vkm = 0, w0 = 0, wip = 0, wim = 0, wjp = 0, wjm = 0, wkp = 0, wkm = 0;
+    Sten s;
+    s.u0 = u[c]; s.uip = u[c + 1]; s.uim = u[c - 1]; s.ujp = u[c + sy]; s.ujm = u[c - sy];
+    s.v0 = v[c]; s.vip = v[c + 1]; s.vim = v[c - 1]; s.vjp = v[c + sy]; s.vjm = v[c - sy];
+    s.uimjp = u[c - 1 + sy]; s.vipjm = v[c + 1 - sy];
+    s.ukp = s.ukm = s.vkp = s.vkm = s.uimkp = s.vjmkp = 0.0;
+    s.w0 = s.wip = s.wim = s.wjp = s.wjm = s.wkp = s.wkm = s.wipkm = s.wjpkm = 0.0;
     if (D3) {
-        ukp = u[c + sz]; ukm = u[c - sz]; vkp = v[c + sz]; vkm = v[c - sz];
-        w0 = w[c]; wip = w[c + 1]; wim = w[c - 1]; wjp = w[c + sy]; wjm = w[c - sy];
-        wkp = w[c + sz]; wkm = w[c - sz];
-        const double wipkm = w[c + 1 - sz], wjpkm = w[c + sy - sz];
-        const double uimkp = u[c - 1 + sz], vjmkp = v[c - sy + sz];
-        double uwkp = (ukp + u0) * (wip + w0) * 0.25;
-        double uwkm = (u0 + ukm) * (wipkm + wkm) * 0.25;
-        dvx = dvx - (uwkp - uwkm) * id;
-        double vwkp = (vkp + v0) * (wjp + w0) * 0.25;
-        double vwkm = (v0 + vkm) * (wjpkm + wkm) * 0.25;
-        dvy = dvy - (vwkp - vwkm) * id;
-        double wuip = (w0 + wip) * (u0 + ukp) * 0.25;
-        double wuim = (w0 + wim) * (uim + uimkp) * 0.25;
-        double wvjp = (w0 + wjp) * (v0 + vkp) * 0.25;
-        double wvjm = (w0 + wjm) * (vjm + vjmkp) * 0.25;
-        double wwkp = (w0 + wkp) * (w0 + wkp) * 0.25;
-        double wwkm = (w0 + wkm) * (w0 + wkm) * 0.25;
-        dvz = 0.0 - (wuip - wuim) * id - (wvjp - wvjm) * id - (wwkp - wwkm) * id;
+        s.ukp = u[c + sz]; s.ukm = u[c - sz]; s.vkp = v[c + sz]; s.vkm = v[c - sz];
+        s.w0 = w[c]; s.wip = w[c + 1]; s.wim = w[c - 1]; s.wjp = w[c + sy]; s.wjm = w[c - sy];
+        s.wkp = w[c + sz]; s.wkm = w[c - sz];
+        s.wipkm = w[c + 1 - sz]; s.wjpkm = w[c + sy - sz];
+        s.uimkp = u[c - 1 + sz]; s.vjmkp = v[c - sy + sz];
     }
+    // face densities, fields.f90:197-200
+    double mu = a.mu0;
+    rfx = rfy = rfz = 1.0;
+    if (!ADV_ONLY) {
+        if (GEN) {
+            const double* __restrict__ rho = a.rho;
+            const double r0 = rho[c];
+            rfx = 0.5 * (rho[c + 1] + r0);
+            rfy = 0.5 * (rho[c + sy] + r0);
+            rfz = D3 ? 0.5 * (rho[c + sz] + r0) : 1.0;
+            mu = a.mu[c];
+        } else {
+            rfx = rfy = rfz = 0.5 * (a.rho0 + a.rho0);
+        }
+    }
+    explicit_from<D3, ADV_ONLY, false>(s, a.idelta, a.idelta2, mu, rfx, rfy, rfz, dvx, dvy, dvz);
     if (ADV_ONLY) return;
-    // ---- face densities, fields.f90:197-200 ---------------------------------------------------
-    double mu;
-    if (GEN) {
-        const double* __restrict__ rho = a.rho;
-        const double r0 = rho[c];
-        rfx = 0.5 * (rho[c + 1] + r0);
-        rfy = 0.5 * (rho[c + sy] + r0);
-        rfz = D3 ? 0.5 * (rho[c + sz] + r0) : 1.0;
-        mu = a.mu[c];
-    } else {
-        rfx = rfy = rfz = 0.5 * (a.rho0 + a.rho0);
-        mu = a.mu0;
-    }
-    // ---- diffusion, fields.f90:326-337 + navier_stokes.f90:394-397 ------------------------------
-    double lx = ((uip - 2.0 * u0 + uim) + (ujp - 2.0 * u0 + ujm)) * id2;
-    double ly = ((vip - 2.0 * v0 + vim) + (vjp - 2.0 * v0 + vjm)) * id2;
-    if (D3) {
-        lx = lx + (ukp - 2.0 * u0 + ukm) * id2;
-        ly = ly + (vkp - 2.0 * v0 + vkm) * id2;
-        double lz = ((wip - 2.0 * w0 + wim) + (wjp - 2.0 * w0 + wjm) + (wkp - 2.0 * w0 + wkm)) * id2;
-        dvz = dvz + mu * lz / rfz;
-    }
-    dvx = dvx + mu * lx / rfx;
-    dvy = dvy + mu * ly / rfy;
-    // ---- body force, navier_stokes.f90:248-251 -------------------------------------------------
+    // body force, navier_stokes.f90:248-251
     if (GEN && a.sx) {
         dvx = dvx + a.sx[c] / rfx;
         dvy = dvy + a.sy_[c] / rfy;
@@ -140,6 +162,109 @@ __global__ void __launch_bounds__(TX* TY) k_pred(StArgs a) {
             a.wn[c] = a.w[c] + dt * rz;
             a.dvoz[c] = dvz;
         }
+    }
+}
+
+// ---- 3-D uniform-property predictor with TMA-staged tiles --------------------------------------------
+// A block owns a PX x PY column of cells and marches PKZ planes in z.  For every plane the copy engine
+// drops the (PX+4) x (PY+2) box (tile + halo; the box must start on a 16-byte boundary -- measured with
+// scripts/probes/tma_probe.cu: an odd fp64 start coordinate is an illegal instruction -- so it starts two
+// cells left of the tile) of u, v and w into a 4-deep shared-memory ring
+// (cp.async.bulk.tensor, one elected thread, mbarrier completion), two planes ahead of the arithmetic, so
+// the 27 stencil values of a cell are shared-memory reads and each of u, v, w leaves HBM once.  p and dv_o
+// are plain coalesced loads, prefetched one plane ahead in registers.
+constexpr int PX = 64, PY = 8, PKZ = 32;
+constexpr int PTW = PX + 4, PTH = PY + 2;
+constexpr int PTILE = PTW * PTH;                                  // doubles per box
+constexpr int PTILE_B = (PTILE * 8 + 127) / 128 * 128;            // bytes per box slot (128-byte aligned for TMA)
+constexpr int PRED_SMEM = 12 * PTILE_B + 64;
+
+template <bool UNIT>
+__global__ void __launch_bounds__(PX* PY, 2)
+k_pred_tma(const __grid_constant__ CUtensorMap mu_, const __grid_constant__ CUtensorMap mv_,
+           const __grid_constant__ CUtensorMap mw_, StArgs a) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem + 12 * PTILE_B);
+    const int tx = threadIdx.x, ty = threadIdx.y;
+    const int tid = ty * PX + tx;
+    const int i = blockIdx.x * PX + tx + 1;
+    const int j = blockIdx.y * PY + ty + 1;
+    const int kb = blockIdx.z * PKZ + 1;
+    const int ke = min(kb + PKZ - 1, a.L.nzl);
+    const int x0 = a.L.xoff - 2 + blockIdx.x * PX;     // box origin: cell (i0 - 2, j0 - 1), an even element index
+    const int y0 = blockIdx.y * PY;
+    if (tid == 0) {
+        for (int q = 0; q < 4; ++q) mbar_init(bar + q, 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+    auto slot = [&](int q, int f) { return reinterpret_cast<double*>(smem + (size_t)((q & 3) * 3 + f) * PTILE_B); };
+    auto issue = [&](int plane) {          // plane: local z index kb-1 .. ke+1
+        const int q = plane - (kb - 1);
+        uint64_t* b = bar + (q & 3);
+        mbar_expect_tx(b, 3u * PTILE * 8u);
+        tma_load_3d(slot(q, 0), &mu_, x0, y0, plane, b);
+        tma_load_3d(slot(q, 1), &mv_, x0, y0, plane, b);
+        tma_load_3d(slot(q, 2), &mw_, x0, y0, plane, b);
+    };
+    if (tid == 0) {
+        issue(kb - 1);
+        issue(kb);
+        issue(kb + 1);
+    }
+    const bool active = i <= a.L.nx && j <= a.L.ny;
+    const long long sy = a.L.sy, sz = a.L.sz;
+    long long c = a.L.idx(active ? i : 1, active ? j : 1, kb);
+    const double* __restrict__ p = a.p;
+    const double id = a.idelta, id2 = a.idelta2, dt = a.dt;
+    const double rf = 0.5 * (a.rho0 + a.rho0);
+    // own-column values prefetched one plane ahead
+    double p0 = p[c], pkp = p[c + sz];
+    double pip = p[c + 1], pjp = p[c + sy];
+    double dox = a.dvox[c], doy = a.dvoy[c], doz = a.dvoz[c];
+    mbar_wait(bar + 0, 0);
+    mbar_wait(bar + 1, 0);
+    const int o = (ty + 1) * PTW + tx + 2;             // my cell inside a box
+    for (int k = kb; k <= ke; ++k) {
+        const int q = k - (kb - 1);                    // ring position of the centre plane
+        mbar_wait(bar + ((q + 1) & 3), ((q + 1) >> 2) & 1);
+        __syncthreads();                               // everybody is done with plane k-2: its slot is free
+        if (tid == 0 && k + 2 <= ke + 1) issue(k + 2);
+        // next plane's streamed values
+        double n_pkp = 0.0, n_pip = 0.0, n_pjp = 0.0, n_dox = 0.0, n_doy = 0.0, n_doz = 0.0;
+        if (k < ke) {
+            const long long cn = c + sz;
+            n_pkp = p[cn + sz]; n_pip = p[cn + 1]; n_pjp = p[cn + sy];
+            n_dox = a.dvox[cn]; n_doy = a.dvoy[cn]; n_doz = a.dvoz[cn];
+        }
+        const double* um = slot(q - 1, 0); const double* uc = slot(q, 0); const double* up = slot(q + 1, 0);
+        const double* vm = slot(q - 1, 1); const double* vc = slot(q, 1); const double* vp = slot(q + 1, 1);
+        const double* wm = slot(q - 1, 2); const double* wc = slot(q, 2); const double* wp = slot(q + 1, 2);
+        Sten s;
+        s.u0 = uc[o]; s.uip = uc[o + 1]; s.uim = uc[o - 1]; s.ujp = uc[o + PTW]; s.ujm = uc[o - PTW];
+        s.uimjp = uc[o - 1 + PTW]; s.ukp = up[o]; s.ukm = um[o]; s.uimkp = up[o - 1];
+        s.v0 = vc[o]; s.vip = vc[o + 1]; s.vim = vc[o - 1]; s.vjp = vc[o + PTW]; s.vjm = vc[o - PTW];
+        s.vipjm = vc[o + 1 - PTW]; s.vkp = vp[o]; s.vkm = vm[o]; s.vjmkp = vp[o - PTW];
+        s.w0 = wc[o]; s.wip = wc[o + 1]; s.wim = wc[o - 1]; s.wjp = wc[o + PTW]; s.wjm = wc[o - PTW];
+        s.wkp = wp[o]; s.wkm = wm[o]; s.wipkm = wm[o + 1]; s.wjpkm = wm[o + PTW];
+        double dvx, dvy, dvz;
+        explicit_from<true, false, UNIT>(s, id, id2, a.mu0, rf, rf, rf, dvx, dvy, dvz);
+        // RHS = -grad_p/rhof + A*dv + B*dv_o + g  (navier_stokes.f90:169-172); v += dt*RHS (:187-198)
+        const double gx = (pip - p0) * id, gy = (pjp - p0) * id, gz = (pkp - p0) * id;
+        const double rx = (UNIT ? -gx : -gx / rf) + a.A * dvx + a.B * dox + a.g0;
+        const double ry = (UNIT ? -gy : -gy / rf) + a.A * dvy + a.B * doy + a.g1;
+        const double rz = (UNIT ? -gz : -gz / rf) + a.A * dvz + a.B * doz + a.g2;
+        if (active) {
+            a.un[c] = s.u0 + dt * rx;
+            a.vn[c] = s.v0 + dt * ry;
+            a.wn[c] = s.w0 + dt * rz;
+            a.dvox[c] = dvx;                           // dv_o = dv (:201-205)
+            a.dvoy[c] = dvy;
+            a.dvoz[c] = dvz;
+        }
+        p0 = pkp; pkp = n_pkp; pip = n_pip; pjp = n_pjp;
+        dox = n_dox; doy = n_doy; doz = n_doz;
+        c += sz;
     }
 }
 
@@ -469,9 +594,21 @@ int ns_predict(fen_ctx* c, double dt) {
     const bool gen = general_path(c);
     if (gen) FEN_TRY(ensure_general_fields(c, a));
     dim3 grid = st_grid(c->L), block(TX, TY);
-    if (d3) {
-        if (gen) FEN_LAUNCH(c, "pred", k_pred<true, true><<<grid, block, 0, c->stream>>>(a));
-        else FEN_LAUNCH(c, "pred", k_pred<true, false><<<grid, block, 0, c->stream>>>(a));
+    if (d3 && !gen) {
+        // TMA-staged kernel: tensor maps of the three velocity buffers (cached per buffer)
+        CUtensorMap* m[3];
+        for (int q = 0; q < 3; ++q) FEN_TRY(field_tmap(c, q == 0 ? a.u : (q == 1 ? a.v : a.w), PTW, PTH, &m[q]));
+        static bool attr_done = false;
+        if (!attr_done) {
+            FEN_CUDA(cudaFuncSetAttribute(k_pred_tma<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, PRED_SMEM));
+            FEN_CUDA(cudaFuncSetAttribute(k_pred_tma<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, PRED_SMEM));
+            attr_done = true;
+        }
+        dim3 pg((c->L.nx + PX - 1) / PX, (c->L.ny + PY - 1) / PY, (c->L.nzl + PKZ - 1) / PKZ), pb(PX, PY);
+        if (a.rho0 == 1.0) FEN_LAUNCH(c, "pred", k_pred_tma<true><<<pg, pb, PRED_SMEM, c->stream>>>(*m[0], *m[1], *m[2], a));
+        else FEN_LAUNCH(c, "pred", k_pred_tma<false><<<pg, pb, PRED_SMEM, c->stream>>>(*m[0], *m[1], *m[2], a));
+    } else if (d3) {
+        FEN_LAUNCH(c, "pred", k_pred<true, true><<<grid, block, 0, c->stream>>>(a));
     } else {
         if (gen) FEN_LAUNCH(c, "pred", k_pred<false, true><<<grid, block, 0, c->stream>>>(a));
         else FEN_LAUNCH(c, "pred", k_pred<false, false><<<grid, block, 0, c->stream>>>(a));
