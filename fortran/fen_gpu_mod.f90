@@ -1,0 +1,444 @@
+!> fen_gpu_mod -- ISO_C_BINDING layer between FEN's Fortran drivers and libfen_gpu.so.
+!>
+!> SOURCE ONLY: the build image has no Fortran compiler (gfortran / flang / nvfortran / mpif90 are
+!> all absent), so this file is not compiled or run by the test-suite.  It is kept mechanical: part 1
+!> declares the bind(C) interfaces of include/fen_gpu.h one to one, part 2 wraps them in procedures
+!> that carry the reference's own names and argument lists, so a driver program switches over by
+!> changing its `use` lines (INTEGRATION.md).  The same call sequences are exercised through the
+!> C ABI by fen_b200/api.py in tests/.
+!>
+!> Reference interfaces mirrored (paths relative to the FEN repository):
+!>   solver_mod        init_solver(comp_grid)                        src/solver.f90:34
+!>                     advance_solution(comp_grid, step, dt)         src/solver.f90:13-19,28
+!>                     print_solver_status(log_id, step, time, dt)   src/solver.f90:21-25,29
+!>                     destroy_solver()                              src/solver.f90:333
+!>   navier_stokes_mod navier_stokes_solver(comp_grid, step, dt)     src/navier_stokes.f90:50
+!>                     set_timestep(comp_grid, dt, U)                src/navier_stokes.f90:623
+!>                     module scalars density, viscosity, g, CFL ... src/navier_stokes.f90:18-45
+!>   poisson_mod       init_poisson_solver(phi), solve_poisson(phi), destroy_poisson_solver(phi)
+!>                                                                   src/poisson.f90:51-52,57,1456
+!>   halo_mod          update_halos(f, G, l)                         src/halo.f90:12
+!>   scalar / vector   update_ghost_nodes                            src/scalar.f90:223, src/vector.f90:82
+module fen_gpu_mod
+
+    use, intrinsic :: iso_c_binding
+    use precision_mod, only : dp
+    use grid_mod     , only : grid
+    use scalar_mod   , only : scalar
+    use vector_mod   , only : vector
+
+    implicit none
+
+    ! enum fen_field (include/fen_gpu.h)
+    integer(c_int), parameter :: FEN_P = 0, FEN_PHI = 1, FEN_RHO = 2, FEN_MU = 3
+    integer(c_int), parameter :: FEN_VX = 4, FEN_VY = 5, FEN_VZ = 6
+    integer(c_int), parameter :: FEN_DVOX = 10, FEN_DVOY = 11, FEN_DVOZ = 12
+    integer(c_int), parameter :: FEN_SX = 16, FEN_SY = 17, FEN_SZ = 18
+
+    type, bind(C) :: fen_grid_desc
+        integer(c_int) :: nx, ny, nz
+        integer(c_int) :: ndim
+        real(c_double) :: delta
+        integer(c_int) :: bc(6)
+        integer(c_int) :: rank, nranks
+        integer(c_int) :: device
+    end type fen_grid_desc
+
+    type, bind(C) :: fen_ns_params
+        real(c_double) :: density, viscosity
+        real(c_double) :: g(3)
+        real(c_double) :: CFL
+        real(c_double) :: dt_o
+        real(c_double) :: dt_visc, dt_conv
+        integer(c_int) :: constant_CFL
+    end type fen_ns_params
+
+    !---------------------------------------------------------------------------------------------
+    ! Part 1: the C ABI, one interface per function of include/fen_gpu.h
+    !---------------------------------------------------------------------------------------------
+    interface
+        function fen_gpu_last_error() bind(C, name='fen_gpu_last_error') result(msg)
+            import :: c_ptr
+            type(c_ptr) :: msg
+        end function
+        function fen_gpu_create(desc, ctx) bind(C, name='fen_gpu_create') result(ierr)
+            import :: c_int, c_ptr, fen_grid_desc
+            type(fen_grid_desc), intent(in) :: desc
+            type(c_ptr), intent(out) :: ctx
+            integer(c_int) :: ierr
+        end function
+        function fen_gpu_destroy(ctx) bind(C, name='fen_gpu_destroy') result(ierr)
+            import :: c_int, c_ptr
+            type(c_ptr), value :: ctx
+            integer(c_int) :: ierr
+        end function
+        function fen_gpu_comm_handle_bytes() bind(C, name='fen_gpu_comm_handle_bytes') result(n)
+            import :: c_int
+            integer(c_int) :: n
+        end function
+        function fen_gpu_comm_export(ctx, handle) bind(C, name='fen_gpu_comm_export') result(ierr)
+            import :: c_int, c_ptr
+            type(c_ptr), value :: ctx, handle
+            integer(c_int) :: ierr
+        end function
+        function fen_gpu_comm_connect(ctx, all_handles) bind(C, name='fen_gpu_comm_connect') result(ierr)
+            import :: c_int, c_ptr
+            type(c_ptr), value :: ctx, all_handles
+            integer(c_int) :: ierr
+        end function
+        function fen_gpu_push(ctx, field, host, gl) bind(C, name='fen_gpu_push') result(ierr)
+            import :: c_int, c_ptr
+            type(c_ptr), value :: ctx, host
+            integer(c_int), value :: field, gl
+            integer(c_int) :: ierr
+        end function
+        function fen_gpu_pull(ctx, field, host, gl) bind(C, name='fen_gpu_pull') result(ierr)
+            import :: c_int, c_ptr
+            type(c_ptr), value :: ctx, host
+            integer(c_int), value :: field, gl
+            integer(c_int) :: ierr
+        end function
+        function fen_gpu_scalar_allocate(ctx, gl, loc, field) bind(C, name='fen_gpu_scalar_allocate') result(ierr)
+            import :: c_int, c_ptr
+            type(c_ptr), value :: ctx
+            integer(c_int), value :: gl, loc
+            integer(c_int), intent(out) :: field
+            integer(c_int) :: ierr
+        end function
+        function fen_gpu_scalar_destroy(ctx, field) bind(C, name='fen_gpu_scalar_destroy') result(ierr)
+            import :: c_int, c_ptr
+            type(c_ptr), value :: ctx
+            integer(c_int), value :: field
+            integer(c_int) :: ierr
+        end function
+        function fen_gpu_set_bc_type(ctx, field, face, bctype) bind(C, name='fen_gpu_set_bc_type') result(ierr)
+            import :: c_int, c_ptr
+            type(c_ptr), value :: ctx
+            integer(c_int), value :: field, face, bctype
+            integer(c_int) :: ierr
+        end function
+        function fen_gpu_set_bc_plane(ctx, field, face, plane, uniform) bind(C, name='fen_gpu_set_bc_plane') result(ierr)
+            import :: c_int, c_ptr
+            type(c_ptr), value :: ctx, plane
+            integer(c_int), value :: field, face, uniform
+            integer(c_int) :: ierr
+        end function
+        function fen_gpu_update_ghost_nodes(ctx, field, ncomp) bind(C, name='fen_gpu_update_ghost_nodes') result(ierr)
+            import :: c_int, c_ptr
+            type(c_ptr), value :: ctx
+            integer(c_int), value :: field, ncomp
+            integer(c_int) :: ierr
+        end function
+        function fen_gpu_update_halos(ctx, field) bind(C, name='fen_gpu_update_halos') result(ierr)
+            import :: c_int, c_ptr
+            type(c_ptr), value :: ctx
+            integer(c_int), value :: field
+            integer(c_int) :: ierr
+        end function
+        function fen_gpu_init_poisson_solver(ctx) bind(C, name='fen_gpu_init_poisson_solver') result(ierr)
+            import :: c_int, c_ptr
+            type(c_ptr), value :: ctx
+            integer(c_int) :: ierr
+        end function
+        function fen_gpu_solve_poisson(ctx, field) bind(C, name='fen_gpu_solve_poisson') result(ierr)
+            import :: c_int, c_ptr
+            type(c_ptr), value :: ctx
+            integer(c_int), value :: field
+            integer(c_int) :: ierr
+        end function
+        function fen_gpu_destroy_poisson_solver(ctx) bind(C, name='fen_gpu_destroy_poisson_solver') result(ierr)
+            import :: c_int, c_ptr
+            type(c_ptr), value :: ctx
+            integer(c_int) :: ierr
+        end function
+        function fen_gpu_init_solver(ctx) bind(C, name='fen_gpu_init_solver') result(ierr)
+            import :: c_int, c_ptr
+            type(c_ptr), value :: ctx
+            integer(c_int) :: ierr
+        end function
+        function fen_gpu_destroy_solver(ctx) bind(C, name='fen_gpu_destroy_solver') result(ierr)
+            import :: c_int, c_ptr
+            type(c_ptr), value :: ctx
+            integer(c_int) :: ierr
+        end function
+        function fen_gpu_get_params(ctx, p) bind(C, name='fen_gpu_get_params') result(ierr)
+            import :: c_int, c_ptr, fen_ns_params
+            type(c_ptr), value :: ctx
+            type(fen_ns_params), intent(out) :: p
+            integer(c_int) :: ierr
+        end function
+        function fen_gpu_set_params(ctx, p) bind(C, name='fen_gpu_set_params') result(ierr)
+            import :: c_int, c_ptr, fen_ns_params
+            type(c_ptr), value :: ctx
+            type(fen_ns_params), intent(in) :: p
+            integer(c_int) :: ierr
+        end function
+        function fen_gpu_set_timestep(ctx, U, dt) bind(C, name='fen_gpu_set_timestep') result(ierr)
+            import :: c_int, c_ptr, c_double
+            type(c_ptr), value :: ctx
+            real(c_double), value :: U
+            real(c_double), intent(out) :: dt
+            integer(c_int) :: ierr
+        end function
+        function fen_gpu_navier_stokes_solver(ctx, step, dt) bind(C, name='fen_gpu_navier_stokes_solver') result(ierr)
+            import :: c_int, c_ptr, c_double
+            type(c_ptr), value :: ctx
+            integer(c_int), value :: step
+            real(c_double), intent(inout) :: dt
+            integer(c_int) :: ierr
+        end function
+        function fen_gpu_get_status(ctx, maxdiv, maxCFL) bind(C, name='fen_gpu_get_status') result(ierr)
+            import :: c_int, c_ptr, c_double
+            type(c_ptr), value :: ctx
+            real(c_double), intent(out) :: maxdiv, maxCFL
+            integer(c_int) :: ierr
+        end function
+    end interface
+
+    !---------------------------------------------------------------------------------------------
+    ! Part 2: the reference's names.  Module state mirrors navier_stokes_mod's public scalars; the
+    ! fields p, v, ... stay the reference's own module-global host arrays (navier_stokes.f90:36-38).
+    !---------------------------------------------------------------------------------------------
+    type(c_ptr), save :: ctx = c_null_ptr        !< one solver instance per process, as in the reference
+    integer, save     :: gpu_ndim = 3
+
+    ! same procedure-pointer interface as solver_mod (src/solver.f90:13-29)
+    abstract interface
+        subroutine advance_solver(comp_grid, step, dt)
+            import :: dp, grid
+            type(grid), intent(in   ) :: comp_grid
+            integer   , intent(in   ) :: step
+            real(dp)  , intent(inout) :: dt
+        end subroutine advance_solver
+    end interface
+    procedure(advance_solver), pointer :: advance_solution => Null()
+
+contains
+
+    !> prints like IO.f90:12 print_error_message and continues, as the reference does
+    subroutine gpu_check(ierr, where)
+        use IO_mod, only : print_error_message
+        integer(c_int), intent(in) :: ierr
+        character(*)  , intent(in) :: where
+        character(kind=c_char), pointer :: cmsg(:)
+        character(len=512) :: msg
+        integer :: n
+        if (ierr == 0) return
+        call c_f_pointer(fen_gpu_last_error(), cmsg, [512])
+        msg = ' '
+        do n = 1, 512
+            if (cmsg(n) == c_null_char) exit
+            msg(n:n) = cmsg(n)
+        end do
+        call print_error_message('ERROR: '//where//': '//trim(msg))
+        ! the one hard stop of the reference: unsupported Poisson BC combination (poisson.f90:91-95)
+        if (ierr == 3 .and. index(where, 'init') > 0) stop
+    end subroutine gpu_check
+
+    integer(c_int) function bc_code(s)
+        character(*), intent(in) :: s
+        select case (trim(s))
+        case ('Periodic'); bc_code = 0
+        case ('Wall');     bc_code = 1
+        case ('Inflow');   bc_code = 2
+        case ('Outflow');  bc_code = 3
+        case default;      bc_code = -1
+        end select
+    end function bc_code
+
+    !> grid%setup has already run (src/grid.f90:67): hand its result to the device library.
+    !> G%prow must be 1 (slabs); G%rank / G%nranks select the z slab and the GPU.
+    subroutine gpu_attach_grid(G, device)
+        type(grid), intent(in) :: G
+        integer   , intent(in), optional :: device
+        type(fen_grid_desc) :: d
+        integer :: n
+        d%nx = G%Nx; d%ny = G%Ny; d%nz = G%Nz
+#if DIM==3
+        d%ndim = 3
+#else
+        d%ndim = 2
+#endif
+        gpu_ndim = d%ndim
+        d%delta = G%delta                                   ! = Lx/float(Nx), grid.f90:140
+        d%bc = 0
+        do n = 1, 2*d%ndim
+            d%bc(n) = bc_code(G%boundary_conditions(n))
+        end do
+        d%rank = G%rank; d%nranks = G%nranks
+        d%device = -1
+        if (present(device)) d%device = device
+        call gpu_check(fen_gpu_create(d, ctx), 'grid setup')
+    end subroutine gpu_attach_grid
+
+    !> multi-GPU wiring (replaces decomp_2d_init's communicator set-up, grid.f90:125): all-gather of
+    !> the exported handles with the MPI the driver already has.
+    subroutine gpu_connect(comm)
+        use mpi
+        integer, intent(in) :: comm
+        integer :: nb, np, ierr
+        character(kind=c_char), allocatable, target :: mine(:), everyone(:)
+        call mpi_comm_size(comm, np, ierr)
+        if (np == 1) return
+        nb = fen_gpu_comm_handle_bytes()
+        allocate(mine(nb), everyone(nb*np))
+        call gpu_check(fen_gpu_comm_export(ctx, c_loc(mine)), 'comm export')
+        call mpi_allgather(mine, nb, mpi_byte, everyone, nb, mpi_byte, comm, ierr)
+        call gpu_check(fen_gpu_comm_connect(ctx, c_loc(everyone)), 'comm connect')
+    end subroutine gpu_connect
+
+    !> host -> device / device -> host for one reference scalar (the explicit transfer points)
+    subroutine gpu_push(s, field)
+        type(scalar), intent(in), target :: s
+        integer(c_int), intent(in) :: field
+        call gpu_check(fen_gpu_push(ctx, field, c_loc(s%f), int(s%gl, c_int)), 'push')
+    end subroutine gpu_push
+
+    subroutine gpu_pull(s, field)
+        type(scalar), intent(inout), target :: s
+        integer(c_int), intent(in) :: field
+        call gpu_check(fen_gpu_pull(ctx, field, c_loc(s%f), int(s%gl, c_int)), 'pull')
+    end subroutine gpu_pull
+
+    !> bc%type_<face> and bc%<face> planes of a reference scalar -> device (call after the driver has
+    !> set them, e.g. v%x%bc%top = U in lid_driven.f90:59)
+    subroutine gpu_push_bc(s, field)
+        type(scalar), intent(in), target :: s
+        integer(c_int), intent(in) :: field
+        call gpu_check(fen_gpu_set_bc_type(ctx, field, 0_c_int, int(s%bc%type_left  , c_int)), 'bc')
+        call gpu_check(fen_gpu_set_bc_type(ctx, field, 1_c_int, int(s%bc%type_right , c_int)), 'bc')
+        call gpu_check(fen_gpu_set_bc_type(ctx, field, 2_c_int, int(s%bc%type_bottom, c_int)), 'bc')
+        call gpu_check(fen_gpu_set_bc_type(ctx, field, 3_c_int, int(s%bc%type_top   , c_int)), 'bc')
+        call gpu_check(fen_gpu_set_bc_plane(ctx, field, 0_c_int, c_loc(s%bc%left)  , 0_c_int), 'bc')
+        call gpu_check(fen_gpu_set_bc_plane(ctx, field, 1_c_int, c_loc(s%bc%right) , 0_c_int), 'bc')
+        call gpu_check(fen_gpu_set_bc_plane(ctx, field, 2_c_int, c_loc(s%bc%bottom), 0_c_int), 'bc')
+        call gpu_check(fen_gpu_set_bc_plane(ctx, field, 3_c_int, c_loc(s%bc%top)   , 0_c_int), 'bc')
+#if DIM==3
+        call gpu_check(fen_gpu_set_bc_type(ctx, field, 4_c_int, int(s%bc%type_front, c_int)), 'bc')
+        call gpu_check(fen_gpu_set_bc_type(ctx, field, 5_c_int, int(s%bc%type_back , c_int)), 'bc')
+        call gpu_check(fen_gpu_set_bc_plane(ctx, field, 4_c_int, c_loc(s%bc%front), 0_c_int), 'bc')
+        call gpu_check(fen_gpu_set_bc_plane(ctx, field, 5_c_int, c_loc(s%bc%back) , 0_c_int), 'bc')
+#endif
+    end subroutine gpu_push_bc
+
+    !> module scalars of navier_stokes_mod -> device (density, viscosity, g, CFL, constant_CFL, dt_o)
+    subroutine gpu_push_params()
+        use navier_stokes_mod, only : density, viscosity, g, CFL, constant_CFL, dt_o, dt_visc, dt_conv
+        type(fen_ns_params) :: p
+        p%density = density; p%viscosity = viscosity
+        p%g = 0.0_dp
+        p%g(1:gpu_ndim) = g(1:gpu_ndim)
+        p%CFL = CFL; p%dt_o = dt_o; p%dt_visc = dt_visc; p%dt_conv = dt_conv
+        p%constant_CFL = merge(1_c_int, 0_c_int, constant_CFL)
+        call gpu_check(fen_gpu_set_params(ctx, p), 'set params')
+    end subroutine gpu_push_params
+
+    !=============================================================================================
+    !> init_solver(comp_grid), src/solver.f90:34.  The host fields are still allocated by the
+    !> reference routine (drivers poke them); the device side gets the same fields, BC wiring table
+    !> and Poisson variant.
+    subroutine init_solver(comp_grid)
+        use navier_stokes_mod, only : allocate_navier_stokes_fields
+        type(grid), intent(in) :: comp_grid
+        call allocate_navier_stokes_fields(comp_grid)            ! host mirrors, navier_stokes.f90:752
+        if (.not. c_associated(ctx)) call gpu_attach_grid(comp_grid)
+        call gpu_push_params()
+        call gpu_check(fen_gpu_init_solver(ctx), 'init_solver')  ! device fields + init_poisson_solver
+        advance_solution => navier_stokes_solver
+    end subroutine init_solver
+
+    !> push the initial condition and BC planes the driver wrote after init_solver
+    subroutine gpu_push_state()
+        use navier_stokes_mod, only : p, v
+        call gpu_push_params()
+        call gpu_push_bc(p, FEN_P);     call gpu_push(p, FEN_P)
+        call gpu_push_bc(v%x, FEN_VX);  call gpu_push(v%x, FEN_VX)
+        call gpu_push_bc(v%y, FEN_VY);  call gpu_push(v%y, FEN_VY)
+#if DIM==3
+        call gpu_push_bc(v%z, FEN_VZ);  call gpu_push(v%z, FEN_VZ)
+#endif
+    end subroutine gpu_push_state
+
+    !> pull p and v back into the reference's host arrays (before output / post-processing)
+    subroutine gpu_pull_state()
+        use navier_stokes_mod, only : p, v
+        call gpu_pull(p, FEN_P)
+        call gpu_pull(v%x, FEN_VX)
+        call gpu_pull(v%y, FEN_VY)
+#if DIM==3
+        call gpu_pull(v%z, FEN_VZ)
+#endif
+    end subroutine gpu_pull_state
+
+    !> set_timestep(comp_grid, dt, U), src/navier_stokes.f90:623 (also sets dt_o = dt, :664)
+    subroutine set_timestep(comp_grid, dt, U)
+        use navier_stokes_mod, only : dt_o
+        type(grid), intent(in   ) :: comp_grid
+        real(dp)  , intent(  out) :: dt
+        real(dp)  , intent(in   ) :: U
+        call gpu_push_params()
+        call gpu_check(fen_gpu_set_timestep(ctx, U, dt), 'set_timestep')
+        dt_o = dt
+    end subroutine set_timestep
+
+    !> navier_stokes_solver(comp_grid, step, dt), src/navier_stokes.f90:50 == advance_solution
+    subroutine navier_stokes_solver(comp_grid, step, dt)
+        use navier_stokes_mod, only : maxdiv, maxCFL
+        type(grid), intent(in   ) :: comp_grid
+        integer   , intent(in   ) :: step
+        real(dp)  , intent(inout) :: dt
+        call gpu_check(fen_gpu_navier_stokes_solver(ctx, int(step, c_int), dt), 'navier_stokes_solver')
+        call gpu_check(fen_gpu_get_status(ctx, maxdiv, maxCFL), 'checks')
+    end subroutine navier_stokes_solver
+
+    !> destroy_solver, src/solver.f90:333
+    subroutine destroy_solver()
+        call gpu_check(fen_gpu_destroy_solver(ctx), 'destroy_solver')
+        call gpu_check(fen_gpu_destroy(ctx), 'destroy')
+        ctx = c_null_ptr
+    end subroutine destroy_solver
+
+    !=============================================================================================
+    ! poisson_mod (src/poisson.f90:51-52): phi is the reference's host scalar; the solve runs on the
+    ! device copy of FEN_PHI.
+    subroutine init_poisson_solver(phi)
+        type(scalar), intent(in) :: phi
+        if (.not. c_associated(ctx)) call gpu_attach_grid(phi%G)
+        call gpu_check(fen_gpu_init_poisson_solver(ctx), 'init_poisson_solver')
+    end subroutine init_poisson_solver
+
+    subroutine solve_poisson(phi)
+        type(scalar), intent(inout) :: phi
+        call gpu_push(phi, FEN_PHI)
+        call gpu_check(fen_gpu_solve_poisson(ctx, FEN_PHI), 'solve_poisson')
+        call gpu_pull(phi, FEN_PHI)
+    end subroutine solve_poisson
+
+    subroutine destroy_poisson_solver(phi)
+        type(scalar), intent(in) :: phi
+        call gpu_check(fen_gpu_destroy_poisson_solver(ctx), 'destroy_poisson_solver')
+    end subroutine destroy_poisson_solver
+
+    !=============================================================================================
+    !> update_halos(f, G, l), src/halo.f90:12 -- same explicit-shape dummy as the reference.
+    !> Stand-alone use (tests/fields): round trip through a scratch device field.
+    subroutine update_halos(f, G, l)
+        integer   , intent(in   ) :: l
+        type(grid), intent(in   ) :: G
+        real(dp)  , intent(inout), target :: f(G%lo(1)-l:G%hi(1)+l, G%lo(2)-l:G%hi(2)+l, G%lo(3)-l:G%hi(3)+l)
+        integer(c_int) :: id
+        call gpu_check(fen_gpu_scalar_allocate(ctx, int(l, c_int), 0_c_int, id), 'update_halos')
+        call gpu_check(fen_gpu_push(ctx, id, c_loc(f), int(l, c_int)), 'update_halos')
+        call gpu_check(fen_gpu_update_halos(ctx, id), 'update_halos')
+        call gpu_check(fen_gpu_pull(ctx, id, c_loc(f), int(l, c_int)), 'update_halos')
+        call gpu_check(fen_gpu_scalar_destroy(ctx, id), 'update_halos')
+    end subroutine update_halos
+
+    !> scalar%update_ghost_nodes on the device copy of a solver field (src/scalar.f90:223)
+    subroutine update_ghost_nodes(field, ncomp)
+        integer(c_int), intent(in) :: field
+        integer       , intent(in) :: ncomp
+        call gpu_check(fen_gpu_update_ghost_nodes(ctx, field, int(ncomp, c_int)), 'update_ghost_nodes')
+    end subroutine update_ghost_nodes
+
+end module fen_gpu_mod
