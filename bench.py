@@ -36,7 +36,32 @@ KERNEL_BYTES_PER_CELL = {
     "pred": 104.0, "poisson_rhs": 32.0, "corr": 72.0, "check": 24.0,
     "fft_x_r2c": 16.0, "fft_x_c2r": 16.0, "fft_lines_fwd": 16.0, "fft_lines_inv": 16.0,
     "fft_solve": 16.0, "thomas_fwd": 16.0, "thomas_bwd": 16.0,
+    # fused kernels carry the algorithmic bytes of everything they replace (fusing K-DIV / K-CHECK
+    # by recompute does not change the denominator)
+    "corr_check": 96.0,        # corr 72 + check 24
+    "fft_x_r2c_div": 48.0,     # poisson_rhs 32 + fft_x_r2c 16
 }
+# ncu kernel-name fragment of each timed family, for roofline.traffic (profiles/ncu_traffic.json)
+NCU_NAME = {"pred": "k_pred_tma", "corr_check": "k_corr_tma", "corr": "k_corr<", "fft_x_r2c_div": "k_fft_x_r2c_r",
+            "fft_solve": "k_fft_solve_r", "fft_lines_fwd": "k_fft_lines_r", "fft_lines_inv": "k_fft_lines_r",
+            "fft_x_c2r": "k_fft_x_c2r_r", "poisson_rhs": "k_rhs", "check": "k_check"}
+
+
+def load_traffic(kernel, size):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel` from the committed ncu --set full
+    summary of this same command (profiles/ncu_traffic.json, written by scripts/ncu_summary.py); None if absent."""
+    p = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    try:
+        t = json.load(open(p))
+        if t.get("size") != size:
+            return None
+        frag = NCU_NAME.get(kernel, kernel)
+        for name, b in t["kernels"].items():
+            if frag in name:
+                return b
+    except Exception:
+        pass
+    return None
 STEP_BYTES_PER_CELL = 312.0
 
 
@@ -308,10 +333,30 @@ def main():
     roofline = None
     if dom:
         roofline = {"bound": "hbm", "kernel": dom["kernel"], "achieved": dom["achieved_GBs"], "peak": peak,
-                    "unit": "GB/s", "frac": dom["frac"], "traffic": None, "peak_source": peak_src,
+                    "unit": "GB/s", "frac": dom["frac"], "traffic": load_traffic(dom["kernel"], n) if world == 1 else None,
+                    "traffic_unit": "bytes per launch (ncu dram__bytes_read.sum + dram__bytes_write.sum)",
+                    "peak_source": peak_src,
                     "alg_bytes_per_launch": dom["alg_bytes_per_cell"] * ncell_loc,
                     "step_achieved": STEP_BYTES_PER_CELL * ncell_loc / (ms / args.steps * 1e-3) / 1e9,
                     "step_frac": STEP_BYTES_PER_CELL * ncell_loc / (ms / args.steps * 1e-3) / 1e9 / peak}
+
+    # ---- transposes over NVLink (N > 1): bytes each GPU stores into its peers / time of the fused kernel ----
+    nvlink = None
+    if world > 1:
+        from fen_b200 import decomp
+        sent = decomp.alltoall_bytes_per_gpu(nx, ny, nz, world)
+        tk = {d["kernel"]: d["ms_per_step"] for d in kernels}
+        fwd = tk.get("fft_lines_fwd_a2a", 0.0) + tk.get("a2a_fwd_sync", 0.0)
+        bwd = tk.get("fft_solve_a2a", 0.0) + tk.get("thomas_bwd_a2a", 0.0) + tk.get("a2a_bwd_sync", 0.0)
+        nvlink = {"a2a_bytes_sent_per_gpu": sent, "peak_GBs_per_dir": 900.0,
+                  "fwd_ms": fwd, "fwd_bus_GBs": sent / (fwd * 1e-3) / 1e9 if fwd else None,
+                  "bwd_ms": bwd, "bwd_bus_GBs": sent / (bwd * 1e-3) / 1e9 if bwd else None,
+                  "note": "the y<->z transposes are the epilogues of the y-FFT / z-solve kernels (stores to mapped "
+                          "peer memory); time = fused kernel + flag handshake on this rank, so the figure is a "
+                          "lower bound of the link rate (it includes the FFT itself)"}
+        for kname in ("fwd", "bwd"):
+            v = nvlink[kname + "_bus_GBs"]
+            nvlink[kname + "_frac"] = v / 900.0 if v else None
 
     # ---- end to end: host (pinned) arrays in, host arrays out, every step -----------------------
     e2e = None
@@ -349,7 +394,7 @@ def main():
                                    "(BASELINE configs[1])" % n, "grid": [nx, ny, nz], "decomposition": "z-slabs x%d" % world,
                        "nu": 0.01, "CFL": 0.25, "dt": dt, "l2": "working set (>= 12 GB) exceeds the 126 MB L2; no flush needed"},
             "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
-            "cpu_baseline": cpu, "kernels": kernels,
+            "cpu_baseline": cpu, "kernels": kernels, "nvlink": nvlink,
             "poisson_solve_ms": poisson_ms,
             "check": {"maxdiv": maxdiv, "maxCFL": maxcfl},
         }

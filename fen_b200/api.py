@@ -87,7 +87,8 @@ class grid:
         n = self.lib.fen_gpu_comm_handle_bytes()
         buf = C.create_string_buffer(n)
         check(self.lib.fen_gpu_comm_export(self.ctx, buf))
-        allh = b"".join(all_gather(buf.raw))
+        from .decomp import gather_handles
+        allh = gather_handles(all_gather, buf.raw, self.nranks)
         check(self.lib.fen_gpu_comm_connect(self.ctx, C.c_char_p(allh)))
 
     def synchronize(self):

@@ -516,13 +516,18 @@ int fen_gpu_navier_stokes_solver(fen_ctx* c, int step, double* dt) {
     if (!(c->prm.dt_o > 0.0)) return set_error(FEN_ERR_STATE, "dt_o is not set: call set_timestep first");
     if (c->prm.constant_CFL) FEN_TRY(update_timestep(c, dt));             // navier_stokes.f90:78
     FEN_TRY(ns_predict(c, *dt));                                          // :105
-    FEN_TRY(ns_poisson_rhs(c, *dt));                                      // :111-121
     Field* phi;
     FEN_TRY(field_check(c, FEN_PHI, &phi));
-    FEN_TRY(poisson_solve(c, phi->d));                                    // :123
-    FEN_TRY(ghost_update(c, FEN_PHI, 1));                                 // :124
-    FEN_TRY(ns_correct(c, *dt));                                          // :127, :130
-    FEN_TRY(ns_checks_launch(c, *dt));                                    // :134
+    if (poisson_can_fuse_rhs(c)) {
+        FEN_TRY(poisson_solve(c, phi->d, true, *dt));                     // :111-123, rhs computed by the x pass
+    } else {
+        FEN_TRY(ns_poisson_rhs(c, *dt));                                  // :111-121
+        FEN_TRY(poisson_solve(c, phi->d));                                // :123
+    }
+    FEN_TRY(ghost_update(c, FEN_PHI, 1, true));                           // :124 (x ghosts written by the c2r pass)
+    bool checks_done = false;
+    FEN_TRY(ns_correct(c, *dt, &checks_done));                            // :127, :130 (+ :134 when fused)
+    if (!checks_done) FEN_TRY(ns_checks_launch(c, *dt));                  // :134
     c->last_dt = *dt;
     return fetch_red(c, 2);
 }

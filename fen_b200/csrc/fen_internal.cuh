@@ -128,7 +128,7 @@ int field_alloc(fen_ctx* c, Field& f);
 // tma.cu
 int field_tmap(fen_ctx* c, const double* base, int box_x, int box_y, CUtensorMap** out);
 // ghost.cu
-int ghost_update(fen_ctx* c, int field, int ncomp);
+int ghost_update(fen_ctx* c, int field, int ncomp, bool x_done = false);   // x_done: producer wrote periodic x ghosts
 // comm.cu
 int halo_exchange(fen_ctx* c, double* const* f, int n);
 int comm_allreduce(fen_ctx* c, double* d_vals, int n, int op /*0 max, 1 sum*/);
@@ -141,7 +141,7 @@ int spectral_pitch(int nx);           // complex row pitch of the half-spectrum 
 // stencil.cu
 int ns_predict(fen_ctx* c, double dt);
 int ns_poisson_rhs(fen_ctx* c, double dt);
-int ns_correct(fen_ctx* c, double dt);
+int ns_correct(fen_ctx* c, double dt, bool* checks_done = nullptr);   // checks_done: fused checks ran
 int ns_checks_launch(fen_ctx* c, double dt);    // leaves (maxdiv, maxvel) in d_red[0..1]
 int op_gradient(fen_ctx* c, int s, int vx);
 int op_divergence(fen_ctx* c, int vx, int s);
@@ -153,7 +153,9 @@ int reduce_field(fen_ctx* c, const double* f, int op, double* d_out);   // op 0 
 int field_is_uniform(fen_ctx* c, const double* f, bool* uniform, double* value);
 // poisson.cu
 int poisson_init(fen_ctx* c);
-int poisson_solve(fen_ctx* c, double* f);
+// fuse_rhs: the x pass computes rhs = div(v) rho/dt from the velocity field itself instead of reading f
+int poisson_solve(fen_ctx* c, double* f, bool fuse_rhs = false, double dt = 0.0);
+bool poisson_can_fuse_rhs(fen_ctx* c);
 void poisson_destroy(fen_ctx* c);
 const char* poisson_variant(fen_ctx* c);
 

@@ -96,8 +96,9 @@ FEN_HD void stage_load(double2* v, const double2* s, int IS, int line, int t) {
         for (int r = 0; r < R; ++r) v[b * R + r] = s[(j + r * (L / R)) * IS + line];
     }
 }
+// twiddle + butterfly of one stage, in place on v[b * R + r]
 template <int L, int R, int DIR>
-FEN_HD void stage_store(double2* v, double2* s, int IS, int line, int t, int Ns, const double2* tw) {
+FEN_HD void stage_compute(double2* v, int t, int Ns, const double2* tw) {
     constexpr int T = FftPlan<L>::T;
     constexpr int NB = (L / R) / T;
 #pragma unroll
@@ -120,9 +121,41 @@ FEN_HD void stage_store(double2* v, double2* s, int IS, int line, int t, int Ns,
             }
         }
         bfly<R, DIR>(w);
+#pragma unroll
+        for (int r = 0; r < R; ++r) v[b * R + r] = w[r];
+    }
+}
+// autosort scatter of one stage's results
+template <int L, int R>
+FEN_HD void stage_write(const double2* v, double2* s, int IS, int line, int t, int Ns) {
+    constexpr int T = FftPlan<L>::T;
+    constexpr int NB = (L / R) / T;
+#pragma unroll
+    for (int b = 0; b < NB; ++b) {
+        int j = t + b * T;
+        int k = j & (Ns - 1);
         int j0 = (j - k) * R + k;
 #pragma unroll
-        for (int r = 0; r < R; ++r) s[(j0 + r * Ns) * IS + line] = w[r];
+        for (int r = 0; r < R; ++r) s[(j0 + r * Ns) * IS + line] = v[b * R + r];
+    }
+}
+template <int L, int R, int DIR>
+FEN_HD void stage_store(double2* v, double2* s, int IS, int line, int t, int Ns, const double2* tw) {
+    stage_compute<L, R, DIR>(v, t, Ns, tw);
+    stage_write<L, R>(v, s, IS, line, t, Ns);
+}
+// After the LAST stage (Ns = L / R) the value in v[b * R + r] is output element t + (b + r * (8 / R)) * (L / 8)
+// (for L >= 64, T = L / 8): bring the registers to "natural" order v[m] = X[t + m * L / 8], which is also the
+// order a first radix-8 stage consumes -- so transforms chain through registers.
+template <int R> FEN_HD void last_permute(double2* v) {
+    if constexpr (R != 8) {
+        double2 w[8];
+#pragma unroll
+        for (int b = 0; b < 8 / R; ++b)
+#pragma unroll
+            for (int r = 0; r < R; ++r) w[b + r * (8 / R)] = v[b * R + r];
+#pragma unroll
+        for (int m = 0; m < 8; ++m) v[m] = w[m];
     }
 }
 
@@ -151,6 +184,43 @@ __device__ __forceinline__ void fft_lines(double2* s, int IS, int line, int t, b
         __syncthreads();
         if (active) stage_store<L, REM, DIR>(v, s, IS, line, t, Ns, tw);
         __syncthreads();
+    }
+}
+
+// Register-to-register transform for L >= 64 (T = L / 8 threads per line, 8 values per thread).
+// In:  v[m] = x[t + m * L / 8].  Out (OUT_REG): v[m] = X[t + m * L / 8]; otherwise the result is left in shared
+// memory (s[idx * IS + line], barrier done).  The first stage takes its inputs and the last stage leaves its outputs
+// in registers, so a 512-point transform costs 4 shared-memory passes and 3 block barriers instead of 8 and 8.
+// On return no thread still reads shared memory written before the call's last barrier, so the caller may start
+// the next transform (e.g. the inverse of the fused solve) without another barrier.
+template <int L, int DIR, bool OUT_REG>
+__device__ __forceinline__ void fft_regs(double2 (&v)[8], double2* s, int IS, int line, int t, const double2* tw) {
+    static_assert(L >= 64, "fft_regs needs T = L / 8 >= 8 threads per line");
+    constexpr int N8 = FftPlan<L>::N8, REM = FftPlan<L>::REM;
+    constexpr int NST = N8 + (REM > 1 ? 1 : 0);
+    int Ns = 1;
+#pragma unroll
+    for (int st = 0; st < N8; ++st) {
+        if (st > 0) {
+            stage_load<L, 8, DIR>(v, s, IS, line, t);
+            __syncthreads();
+        }
+        stage_compute<L, 8, DIR>(v, t, Ns, tw);
+        if (OUT_REG && st == NST - 1) return;
+        stage_write<L, 8>(v, s, IS, line, t, Ns);
+        __syncthreads();
+        Ns *= 8;
+    }
+    if constexpr (REM > 1) {
+        stage_load<L, REM, DIR>(v, s, IS, line, t);
+        __syncthreads();
+        stage_compute<L, REM, DIR>(v, t, Ns, tw);
+        if (OUT_REG) {
+            last_permute<REM>(v);
+        } else {
+            stage_write<L, REM>(v, s, IS, line, t, Ns);
+            __syncthreads();
+        }
     }
 }
 #endif

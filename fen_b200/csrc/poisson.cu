@@ -20,6 +20,7 @@
 // cuFFT is not used here (tests/ cross-check against numpy/scipy and, on the GPU box, cuFFT).
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include "fen_internal.cuh"
@@ -74,11 +75,33 @@ struct XArgs {
     double scale;         // applied to the r2c output (1/float(nx) in ppn/pn, else 1)
 };
 
+// Poisson right-hand side computed on the fly by the x pass (navier_stokes.f90:111-121 fused into
+// poisson.f90:965-969): rhs = ((u-u_im)*id + (v-v_jm)*id + (w-w_km)*id) * rho / dt, uniform rho.
+struct DivArgs {
+    const double* u; const double* v; const double* w;
+    double idelta, rho0, dt;
+};
+// rhs of the two cells (2*idx+1, 2*idx+2) of the row whose first interior element is c0
+__device__ __forceinline__ double2 div_pair(const DivArgs& dv, const Layout& L, long long c) {
+    const double id = dv.idelta;
+    const double2 u2 = *reinterpret_cast<const double2*>(dv.u + c);
+    const double um = dv.u[c - 1];
+    const double2 v2 = *reinterpret_cast<const double2*>(dv.v + c);
+    const double2 vm = *reinterpret_cast<const double2*>(dv.v + c - L.sy);
+    const double2 w2 = *reinterpret_cast<const double2*>(dv.w + c);
+    const double2 wm = *reinterpret_cast<const double2*>(dv.w + c - L.sz);
+    double d0 = (u2.x - um) * id + (v2.x - vm.x) * id;      // fields.f90:144-147
+    d0 = d0 + (w2.x - wm.x) * id;
+    double d1 = (u2.y - u2.x) * id + (v2.y - vm.y) * id;
+    d1 = d1 + (w2.y - wm.y) * id;
+    return make_double2(d0 * dv.rho0 / dv.dt, d1 * dv.rho0 / dv.dt);   // navier_stokes.f90:118
+}
+
 constexpr int XR = 8;     // rows per block
 constexpr int XIS = 9;    // smem idx stride (see fft_core.cuh)
 
-template <int M>
-__global__ void __launch_bounds__(XR* FftPlan<M>::T) k_fft_x_r2c(XArgs a) {
+template <int M, bool DIV>
+__global__ void __launch_bounds__(XR* FftPlan<M>::T) k_fft_x_r2c(XArgs a, DivArgs dv) {
     extern __shared__ double2 s[];
     constexpr int T = FftPlan<M>::T;
     constexpr int NT = XR * T;
@@ -91,8 +114,9 @@ __global__ void __launch_bounds__(XR* FftPlan<M>::T) k_fft_x_r2c(XArgs a) {
         double2 z = make_double2(0.0, 0.0);
         if (r < a.nrows) {
             const int j = r % a.ny, k = r / a.ny;
-            const double2* src = reinterpret_cast<const double2*>(a.f + a.L.idx(1, j + 1, k + 1));
-            z = src[idx];
+            const long long c0 = a.L.idx(1, j + 1, k + 1);
+            if (DIV) z = div_pair(dv, a.L, c0 + 2 * idx);
+            else z = reinterpret_cast<const double2*>(a.f + c0)[idx];
         }
         s[idx * XIS + row] = z;
     }
@@ -172,8 +196,12 @@ __global__ void __launch_bounds__(XR* FftPlan<M>::T) k_fft_x_c2r(XArgs a) {
         const int r = row0 + row;
         if (r >= a.nrows) continue;
         const int j = r % a.ny, k = r / a.ny;
-        double2* dst = reinterpret_cast<double2*>(a.f + a.L.idx(1, j + 1, k + 1));
-        dst[idx] = s[idx * XIS + row];
+        double* frow = a.f + a.L.idx(1, j + 1, k + 1);
+        const double2 val = s[idx * XIS + row];
+        reinterpret_cast<double2*>(frow)[idx] = val;
+        // periodic x ghosts of the row (scalar.f90:257,276): every variant built here is periodic in x
+        if (idx == 0) frow[2 * M] = val.x;
+        if (idx == M - 1) frow[-1] = val.y;
     }
 }
 
@@ -189,6 +217,7 @@ struct LArgs {
     // spectral divide (k_fft_solve only): lam = (lx[kx] + lo[o]) + ll[l]   (poisson.f90:998)
     const double* lx; const double* lo; const double* ll;
     double norm;           // float(nx*ny*nz)  (poisson.f90:992)
+    int cx0;               // first kx group of this launch (L2-resident chunking, see poisson_solve)
 };
 
 template <int Lf, int DIR, int NL, bool SC>
@@ -197,7 +226,7 @@ __global__ void __launch_bounds__(NL* FftPlan<Lf>::T) k_fft_lines(LArgs a, ScArg
     constexpr int T = FftPlan<Lf>::T;
     const int tid = threadIdx.x;
     const int line = tid % NL, t = tid / NL;
-    const int kx = blockIdx.x * NL + line;
+    const int kx = (blockIdx.x + a.cx0) * NL + line;
     double2* base = a.C + kx + a.so * blockIdx.y;
     for (int idx = t; idx < Lf; idx += T) s[idx * NL + line] = base[a.sl * idx];
     __syncthreads();
@@ -217,7 +246,7 @@ __global__ void __launch_bounds__(NL* FftPlan<Lf>::T) k_fft_solve(LArgs a, ScArg
     constexpr int T = FftPlan<Lf>::T;
     const int tid = threadIdx.x;
     const int line = tid % NL, t = tid / NL;
-    const int kx = blockIdx.x * NL + line;
+    const int kx = (blockIdx.x + a.cx0) * NL + line;
     double2* base = a.C + kx + a.so * blockIdx.y;
     for (int idx = t; idx < Lf; idx += T) s[idx * NL + line] = base[a.sl * idx];
     __syncthreads();
@@ -240,6 +269,209 @@ __global__ void __launch_bounds__(NL* FftPlan<Lf>::T) k_fft_solve(LArgs a, ScArg
     for (int idx = t; idx < Lf; idx += T) {
         if (SC) *sc_dst(q, kx, idx, blockIdx.y) = s[idx * NL + line];
         else base[a.sl * idx] = s[idx * NL + line];
+    }
+}
+
+// =================================================================================================
+// Register-path kernels (transform length >= 64): the first radix-8 stage takes its operands straight from
+// global memory and the last one stores straight back (fft_core.cuh: fft_regs), so a pass costs 4 shared
+// memory sweeps and 3 barriers instead of 8 and 8, and every thread has 8 independent 16-byte loads in
+// flight before the first butterfly.
+// =================================================================================================
+
+template <int M, bool DIV>
+__global__ void __launch_bounds__(XR* FftPlan<M>::T, (XR * FftPlan<M>::T <= 1024) ? 1024 / (XR * FftPlan<M>::T) : 1) k_fft_x_r2c_r(XArgs a, DivArgs dv) {
+    extern __shared__ double2 s[];
+    constexpr int T = FftPlan<M>::T;
+    constexpr int NT = XR * T;
+    const int tid = threadIdx.x;
+    const int row = tid % XR, t = tid / XR;
+    const int row0 = blockIdx.x * XR;
+    double2 v[8];
+    {
+        const int r = row0 + row;
+        const bool valid = r < a.nrows;
+        const int j = valid ? r % a.ny : 0, k = valid ? r / a.ny : 0;
+        const long long c0 = a.L.idx(1, j + 1, k + 1);
+        if (DIV) {
+#pragma unroll
+            for (int m = 0; m < 8; ++m)
+                v[m] = valid ? div_pair(dv, a.L, c0 + 2 * (t + m * T)) : make_double2(0.0, 0.0);
+        } else {
+            const double2* src = reinterpret_cast<const double2*>(a.f + c0);
+#pragma unroll
+            for (int m = 0; m < 8; ++m) v[m] = valid ? src[t + m * T] : make_double2(0.0, 0.0);
+        }
+    }
+    fft_regs<M, -1, false>(v, s, XIS, row, t, a.tw);
+    // post-process pairs (k, M-k) and write X[0..M]
+    constexpr int NP = M / 2 + 1;
+    for (int e = tid; e < XR * NP; e += NT) {
+        const int rw = e / NP, k = e - rw * NP;
+        const int r = row0 + rw;
+        if (r >= a.nrows) continue;
+        const int km = M - k;
+        const double2 zk = s[(k % M) * XIS + rw];
+        const double2 zm = s[(km % M) * XIS + rw];
+        double2* dst = a.C + (size_t)a.PC * r;
+        {   // X[k] = (Zk + conj Zm)/2 + w_k (Zk - conj Zm)/(2i)
+            const double2 E = make_double2(0.5 * (zk.x + zm.x), 0.5 * (zk.y - zm.y));
+            const double2 O = make_double2(0.5 * (zk.y + zm.y), -0.5 * (zk.x - zm.x));
+            const double2 w = __ldg(&a.twr[k]);
+            const double2 X = cadd(E, cmul(w, O));
+            dst[k] = make_double2(X.x * a.scale, X.y * a.scale);
+        }
+        if (km != k) {
+            const double2 E = make_double2(0.5 * (zm.x + zk.x), 0.5 * (zm.y - zk.y));
+            const double2 O = make_double2(0.5 * (zm.y + zk.y), -0.5 * (zm.x - zk.x));
+            const double2 w = __ldg(&a.twr[km]);
+            const double2 X = cadd(E, cmul(w, O));
+            dst[km] = make_double2(X.x * a.scale, X.y * a.scale);
+        }
+    }
+}
+
+template <int M>
+__global__ void __launch_bounds__(XR* FftPlan<M>::T, (XR * FftPlan<M>::T <= 1024) ? 1024 / (XR * FftPlan<M>::T) : 1) k_fft_x_c2r_r(XArgs a) {
+    extern __shared__ double2 s[];
+    constexpr int T = FftPlan<M>::T;
+    const int tid = threadIdx.x;
+    const int row = tid % XR, t = tid / XR;
+    const int r = blockIdx.x * XR + row;
+    const bool valid = r < a.nrows;
+    const double2* X = a.C + (size_t)a.PC * (valid ? r : 0);
+    double2 v[8];
+#pragma unroll
+    for (int m = 0; m < 8; ++m) {
+        // Z[k] = (Xk + conj Xm) + i conj(w_k) (Xk - conj Xm),  m = M - k, w_k = exp(-2 pi i k / N)
+        const int k = t + m * T;
+        double2 xk = X[k], xm = X[M - k];
+        if (k == 0) { xk.y = 0.0; xm.y = 0.0; }        // c2r ignores the imaginary part of DC / Nyquist
+        const double2 E = make_double2(xk.x + xm.x, xk.y - xm.y);
+        const double2 D = make_double2(xk.x - xm.x, xk.y + xm.y);
+        const double2 O = cmul(cconj(__ldg(&a.twr[k])), D);
+        v[m] = make_double2(E.x - O.y, E.y + O.x);
+    }
+    fft_regs<M, +1, true>(v, s, XIS, row, t, a.tw);
+    if (!valid) return;
+    const int j = r % a.ny, k3 = r / a.ny;
+    double* frow = a.f + a.L.idx(1, j + 1, k3 + 1);
+#pragma unroll
+    for (int m = 0; m < 8; ++m) {
+        const int idx = t + m * T;
+        reinterpret_cast<double2*>(frow)[idx] = v[m];
+        // periodic x ghosts of the row (scalar.f90:257,276): every variant built here is periodic in x
+        if (idx == 0) frow[2 * M] = v[m].x;
+        if (idx == M - 1) frow[-1] = v[m].y;
+    }
+}
+
+// c2r with a coalesced staging load: rows of C -> shared memory, the pair pre-pass reads (k, M-k) from there
+// into registers, the transform runs register-to-register and the real row is stored straight from registers.
+template <int M>
+__global__ void __launch_bounds__(XR* FftPlan<M>::T, (XR * FftPlan<M>::T <= 1024) ? 1024 / (XR * FftPlan<M>::T) : 1)
+k_fft_x_c2r_s(XArgs a) {
+    extern __shared__ double2 s[];
+    constexpr int T = FftPlan<M>::T;
+    constexpr int NT = XR * T;
+    const int tid = threadIdx.x;
+    const int row0 = blockIdx.x * XR;
+    for (int e = tid; e < XR * (M + 1); e += NT) {
+        const int rw = e / (M + 1), k = e - rw * (M + 1);
+        const int r = row0 + rw;
+        double2 x = make_double2(0.0, 0.0);
+        if (r < a.nrows) {
+            x = a.C[(size_t)a.PC * r + k];
+            if (k == 0 || k == M) x.y = 0.0;     // c2r ignores the imaginary part of DC / Nyquist
+        }
+        s[k * XIS + rw] = x;
+    }
+    __syncthreads();
+    const int row = tid % XR, t = tid / XR;
+    double2 v[8];
+#pragma unroll
+    for (int m = 0; m < 8; ++m) {
+        const int k = t + m * T;
+        const double2 xk = s[k * XIS + row], xm = s[(M - k) * XIS + row];
+        const double2 E = make_double2(xk.x + xm.x, xk.y - xm.y);
+        const double2 D = make_double2(xk.x - xm.x, xk.y + xm.y);
+        const double2 O = cmul(cconj(__ldg(&a.twr[k])), D);
+        v[m] = make_double2(E.x - O.y, E.y + O.x);
+    }
+    __syncthreads();                              // the first stage overwrites the staged rows
+    fft_regs<M, +1, true>(v, s, XIS, row, t, a.tw);
+    const int r = row0 + row;
+    if (r >= a.nrows) return;
+    const int j = r % a.ny, k3 = r / a.ny;
+    double* frow = a.f + a.L.idx(1, j + 1, k3 + 1);
+#pragma unroll
+    for (int m = 0; m < 8; ++m) {
+        const int idx = t + m * T;
+        reinterpret_cast<double2*>(frow)[idx] = v[m];
+        if (idx == 0) frow[2 * M] = v[m].x;       // periodic x ghosts (scalar.f90:257,276)
+        if (idx == M - 1) frow[-1] = v[m].y;
+    }
+}
+
+template <int Lf, int DIR, int NL, bool SC>
+__global__ void __launch_bounds__(NL* FftPlan<Lf>::T, (NL * FftPlan<Lf>::T <= 1024) ? 1024 / (NL * FftPlan<Lf>::T) : 1) k_fft_lines_r(LArgs a, ScArgs q) {
+    extern __shared__ double2 s[];
+    constexpr int T = FftPlan<Lf>::T;
+    const int tid = threadIdx.x;
+    const int line = tid % NL, t = tid / NL;
+    const int kx = (blockIdx.x + a.cx0) * NL + line;
+    double2* base = a.C + kx + a.so * blockIdx.y;
+    double2 v[8];
+#pragma unroll
+    for (int m = 0; m < 8; ++m) v[m] = base[a.sl * (t + m * T)];
+    fft_regs<Lf, DIR, true>(v, s, NL, line, t, a.tw);
+    const double sc = a.scale;
+#pragma unroll
+    for (int m = 0; m < 8; ++m) {
+        const int idx = t + m * T;
+        const double2 o = make_double2(v[m].x * sc, v[m].y * sc);
+        if (SC) *sc_dst(q, kx, idx, blockIdx.y) = o;
+        else base[a.sl * idx] = o;
+    }
+}
+
+template <int Lf, int NL, bool SC>
+__global__ void __launch_bounds__(NL* FftPlan<Lf>::T, (NL * FftPlan<Lf>::T <= 1024) ? 1024 / (NL * FftPlan<Lf>::T) : 1) k_fft_solve_r(LArgs a, ScArgs q) {
+    extern __shared__ double2 s[];
+    constexpr int T = FftPlan<Lf>::T;
+    const int tid = threadIdx.x;
+    const int line = tid % NL, t = tid / NL;
+    double2 v[8];
+    {
+        const double2* base = a.C + ((blockIdx.x + a.cx0) * NL + line) + a.so * blockIdx.y;
+#pragma unroll
+        for (int m = 0; m < 8; ++m) v[m] = base[a.sl * (t + m * T)];
+    }
+    fft_regs<Lf, -1, true>(v, s, NL, line, t, a.tw);
+    // poisson.f90:992 then :998-1001.  norm = float(nx*ny*nz) is a power of two here (power-of-two transform
+    // lengths), so x/norm == x*(1/norm) exactly; the division by lambda is one rounded reciprocal and a
+    // multiply (<= 1 ulp from x/lambda, far inside the 1e-12 parity bound) instead of four fp64 divisions.
+    {
+        const int kx = (blockIdx.x + a.cx0) * NL + line;
+        double lxo = __ldg(&a.lx[kx]);
+        if (a.lo) lxo = lxo + __ldg(&a.lo[a.o0 + blockIdx.y]);
+        const double inorm = 1.0 / a.norm;
+#pragma unroll
+        for (int m = 0; m < 8; ++m) {
+            const double lam = lxo + __ldg(&a.ll[t + m * T]);
+            const double rl = lam == 0.0 ? 0.0 : inorm / lam;
+            v[m].x *= rl;
+            v[m].y *= rl;
+        }
+    }
+    fft_regs<Lf, +1, true>(v, s, NL, line, t, a.tw);
+    const int kx = (blockIdx.x + a.cx0) * NL + line;
+    double2* base = a.C + kx + a.so * blockIdx.y;
+#pragma unroll
+    for (int m = 0; m < 8; ++m) {
+        const int idx = t + m * T;
+        if (SC) *sc_dst(q, kx, idx, blockIdx.y) = v[m];
+        else base[a.sl * idx] = v[m];
     }
 }
 
@@ -447,27 +679,57 @@ const char* poisson_variant(fen_ctx* c) { return c->ps ? c->ps->variant : ""; }
 template <int M> static int set_smem_x() {
     const int bytes = (M + 1) * XIS * (int)sizeof(double2);
     if (bytes > 48 * 1024) {
-        FEN_CUDA(cudaFuncSetAttribute(k_fft_x_r2c<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+        FEN_CUDA(cudaFuncSetAttribute(k_fft_x_r2c<M, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+        FEN_CUDA(cudaFuncSetAttribute(k_fft_x_r2c<M, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
         FEN_CUDA(cudaFuncSetAttribute(k_fft_x_c2r<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+        if constexpr (M >= 64) {
+            FEN_CUDA(cudaFuncSetAttribute(k_fft_x_r2c_r<M, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+            FEN_CUDA(cudaFuncSetAttribute(k_fft_x_r2c_r<M, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+            FEN_CUDA(cudaFuncSetAttribute(k_fft_x_c2r_r<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+            FEN_CUDA(cudaFuncSetAttribute(k_fft_x_c2r_s<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+        }
     }
     return FEN_OK;
 }
 
-template <int M> static int launch_x(fen_ctx* c, const XArgs& a, bool fwd) {
+// tuning switches (defaults = the fastest measured at 512^3, profiles/):
+//   FEN_X_R2C: 0 register path   1 staged (coalesced load / rhs compute into shared memory)
+//   FEN_X_C2R: 0 register path   1 fully staged   2 staged load + register output
+static int x_variant(const char* name, int dflt) {
+    const char* e = getenv(name);
+    return e ? atoi(e) : dflt;
+}
+
+template <int M> static int launch_x(fen_ctx* c, const XArgs& a, bool fwd, const DivArgs* dv) {
     constexpr int T = FftPlan<M>::T;
     const int bytes = (M + 1) * XIS * (int)sizeof(double2);
     static bool attr_done = false;
     if (!attr_done) { FEN_TRY(set_smem_x<M>()); attr_done = true; }
+    static const int vr2c = x_variant("FEN_X_R2C", 0), vc2r = x_variant("FEN_X_C2R", 0);
     dim3 grid((a.nrows + XR - 1) / XR), block(XR * T);
-    if (fwd) FEN_LAUNCH(c, "fft_x_r2c", k_fft_x_r2c<M><<<grid, block, bytes, c->stream>>>(a));
-    else FEN_LAUNCH(c, "fft_x_c2r", k_fft_x_c2r<M><<<grid, block, bytes, c->stream>>>(a));
+    DivArgs none{};
+    bool done = false;
+    if constexpr (M >= 64) {
+        if (fwd && vr2c == 0) {
+            if (dv) FEN_LAUNCH(c, "fft_x_r2c_div", k_fft_x_r2c_r<M, true><<<grid, block, bytes, c->stream>>>(a, *dv));
+            else FEN_LAUNCH(c, "fft_x_r2c", k_fft_x_r2c_r<M, false><<<grid, block, bytes, c->stream>>>(a, none));
+            done = true;
+        }
+        if (!fwd && vc2r == 0) { FEN_LAUNCH(c, "fft_x_c2r", k_fft_x_c2r_r<M><<<grid, block, bytes, c->stream>>>(a)); done = true; }
+        if (!fwd && vc2r == 2) { FEN_LAUNCH(c, "fft_x_c2r", k_fft_x_c2r_s<M><<<grid, block, bytes, c->stream>>>(a)); done = true; }
+    }
+    if (!done) {
+        if (fwd && dv) FEN_LAUNCH(c, "fft_x_r2c_div", k_fft_x_r2c<M, true><<<grid, block, bytes, c->stream>>>(a, *dv));
+        else if (fwd) FEN_LAUNCH(c, "fft_x_r2c", k_fft_x_r2c<M, false><<<grid, block, bytes, c->stream>>>(a, none));
+        else FEN_LAUNCH(c, "fft_x_c2r", k_fft_x_c2r<M><<<grid, block, bytes, c->stream>>>(a));
+    }
     FEN_CUDA(cudaGetLastError());
     return FEN_OK;
 }
 
-static int dispatch_x(fen_ctx* c, int M, const XArgs& a, bool fwd) {
+static int dispatch_x(fen_ctx* c, int M, const XArgs& a, bool fwd, const DivArgs* dv = nullptr) {
     switch (M) {
-#define FEN_CASE(m) case m: return launch_x<m>(c, a, fwd);
+#define FEN_CASE(m) case m: return launch_x<m>(c, a, fwd, dv);
         FEN_CASE(1) FEN_CASE(2) FEN_CASE(4) FEN_CASE(8) FEN_CASE(16) FEN_CASE(32) FEN_CASE(64)
         FEN_CASE(128) FEN_CASE(256) FEN_CASE(512) FEN_CASE(1024)
 #undef FEN_CASE
@@ -483,27 +745,51 @@ template <int Lf, int NL> static int launch_lines(fen_ctx* c, const LArgs& a, in
     static bool attr_done = false;
     if (!attr_done) {
         if (bytes > 48 * 1024) {
-            FEN_CUDA(cudaFuncSetAttribute(k_fft_lines<Lf, -1, NL, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-            FEN_CUDA(cudaFuncSetAttribute(k_fft_lines<Lf, -1, NL, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-            FEN_CUDA(cudaFuncSetAttribute(k_fft_lines<Lf, +1, NL, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-            FEN_CUDA(cudaFuncSetAttribute(k_fft_solve<Lf, NL, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-            FEN_CUDA(cudaFuncSetAttribute(k_fft_solve<Lf, NL, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+            if constexpr (Lf >= 64) {
+                FEN_CUDA(cudaFuncSetAttribute(k_fft_lines_r<Lf, -1, NL, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+                FEN_CUDA(cudaFuncSetAttribute(k_fft_lines_r<Lf, -1, NL, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+                FEN_CUDA(cudaFuncSetAttribute(k_fft_lines_r<Lf, +1, NL, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+                FEN_CUDA(cudaFuncSetAttribute(k_fft_solve_r<Lf, NL, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+                FEN_CUDA(cudaFuncSetAttribute(k_fft_solve_r<Lf, NL, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+            } else {
+                FEN_CUDA(cudaFuncSetAttribute(k_fft_lines<Lf, -1, NL, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+                FEN_CUDA(cudaFuncSetAttribute(k_fft_lines<Lf, -1, NL, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+                FEN_CUDA(cudaFuncSetAttribute(k_fft_lines<Lf, +1, NL, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+                FEN_CUDA(cudaFuncSetAttribute(k_fft_solve<Lf, NL, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+                FEN_CUDA(cudaFuncSetAttribute(k_fft_solve<Lf, NL, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+            }
         }
         attr_done = true;
     }
     dim3 grid(nchunks, nouter), block(NL * T);
     ScArgs none;
     memset(&none, 0, sizeof(none));
-    if (mode == 0 && !sc) FEN_LAUNCH(c, "fft_lines_fwd", k_fft_lines<Lf, -1, NL, false><<<grid, block, bytes, c->stream>>>(a, none));
-    if (mode == 0 && sc) FEN_LAUNCH(c, "fft_lines_fwd_a2a", k_fft_lines<Lf, -1, NL, true><<<grid, block, bytes, c->stream>>>(a, *sc));
-    if (mode == 1) FEN_LAUNCH(c, "fft_lines_inv", k_fft_lines<Lf, +1, NL, false><<<grid, block, bytes, c->stream>>>(a, none));
-    if (mode == 2 && !sc) FEN_LAUNCH(c, "fft_solve", k_fft_solve<Lf, NL, false><<<grid, block, bytes, c->stream>>>(a, none));
-    if (mode == 2 && sc) FEN_LAUNCH(c, "fft_solve_a2a", k_fft_solve<Lf, NL, true><<<grid, block, bytes, c->stream>>>(a, *sc));
+    if constexpr (Lf >= 64) {
+        if (mode == 0 && !sc) FEN_LAUNCH(c, "fft_lines_fwd", k_fft_lines_r<Lf, -1, NL, false><<<grid, block, bytes, c->stream>>>(a, none));
+        if (mode == 0 && sc) FEN_LAUNCH(c, "fft_lines_fwd_a2a", k_fft_lines_r<Lf, -1, NL, true><<<grid, block, bytes, c->stream>>>(a, *sc));
+        if (mode == 1) FEN_LAUNCH(c, "fft_lines_inv", k_fft_lines_r<Lf, +1, NL, false><<<grid, block, bytes, c->stream>>>(a, none));
+        if (mode == 2 && !sc) FEN_LAUNCH(c, "fft_solve", k_fft_solve_r<Lf, NL, false><<<grid, block, bytes, c->stream>>>(a, none));
+        if (mode == 2 && sc) FEN_LAUNCH(c, "fft_solve_a2a", k_fft_solve_r<Lf, NL, true><<<grid, block, bytes, c->stream>>>(a, *sc));
+    } else {
+        if (mode == 0 && !sc) FEN_LAUNCH(c, "fft_lines_fwd", k_fft_lines<Lf, -1, NL, false><<<grid, block, bytes, c->stream>>>(a, none));
+        if (mode == 0 && sc) FEN_LAUNCH(c, "fft_lines_fwd_a2a", k_fft_lines<Lf, -1, NL, true><<<grid, block, bytes, c->stream>>>(a, *sc));
+        if (mode == 1) FEN_LAUNCH(c, "fft_lines_inv", k_fft_lines<Lf, +1, NL, false><<<grid, block, bytes, c->stream>>>(a, none));
+        if (mode == 2 && !sc) FEN_LAUNCH(c, "fft_solve", k_fft_solve<Lf, NL, false><<<grid, block, bytes, c->stream>>>(a, none));
+        if (mode == 2 && sc) FEN_LAUNCH(c, "fft_solve_a2a", k_fft_solve<Lf, NL, true><<<grid, block, bytes, c->stream>>>(a, *sc));
+    }
     FEN_CUDA(cudaGetLastError());
     return FEN_OK;
 }
 
 static int dispatch_lines(fen_ctx* c, int Lf, const LArgs& a, int mode, int PC, int nouter, const ScArgs* sc = nullptr) {
+    // tuning switch: 4 lines (64 B) per block instead of 8 -- more, smaller blocks per SM
+    static const bool nl4 = getenv("FEN_FFT_NL4") != nullptr;
+    if (nl4 && (Lf == 512 || Lf == 1024)) {
+        LArgs b = a;
+        b.cx0 = a.cx0 * 2;       // cx0 counts blocks of NL columns
+        if (Lf == 512) return launch_lines<512, 4>(c, b, mode, PC / 4, nouter, sc);
+        return launch_lines<1024, 4>(c, b, mode, PC / 4, nouter, sc);
+    }
     switch (Lf) {
 #define FEN_CASE(l) case l: return launch_lines<l, 8>(c, a, mode, PC / 8, nouter, sc);
         FEN_CASE(1) FEN_CASE(2) FEN_CASE(4) FEN_CASE(8) FEN_CASE(16) FEN_CASE(32) FEN_CASE(64)
@@ -613,9 +899,27 @@ int poisson_init(fen_ctx* c) {
     return FEN_OK;
 }
 
-int poisson_solve(fen_ctx* c, double* f) {
+// the x pass can compute the right-hand side div(v*) rho/dt itself (uniform rho, 3-D, register-path lengths)
+bool poisson_can_fuse_rhs(fen_ctx* c) {
+    static const bool off = getenv("FEN_NO_FUSED_RHS") != nullptr;     // tuning switch
+    return !off && c->ps && c->g.ndim == 3 && c->uniform_props;
+}
+
+int poisson_solve(fen_ctx* c, double* f, bool fuse_rhs, double dt) {
     Poisson* p = c->ps;
     if (!p) return set_error(FEN_ERR_STATE, "solve_poisson before init_poisson_solver");
+    DivArgs dv{};
+    if (fuse_rhs) {
+        if (!poisson_can_fuse_rhs(c)) return set_error(FEN_ERR_STATE, "fused Poisson right-hand side not available");
+        Field *u, *v, *w;
+        FEN_TRY(field_check(c, FEN_VX, &u));
+        FEN_TRY(field_check(c, FEN_VY, &v));
+        FEN_TRY(field_check(c, FEN_VZ, &w));
+        dv.u = u->d; dv.v = v->d; dv.w = w->d;
+        dv.idelta = 1.0 / c->g.delta;
+        dv.rho0 = c->rho_uniform;
+        dv.dt = dt;
+    }
     const fen_grid_desc& g = c->g;
     const bool ppp = !strcmp(p->variant, "ppp"), ppn = !strcmp(p->variant, "ppn");
     const bool pp = !strcmp(p->variant, "pp"), pn = !strcmp(p->variant, "pn");
@@ -624,10 +928,10 @@ int poisson_solve(fen_ctx* c, double* f) {
     xa.L = c->L; xa.f = f; xa.C = p->C; xa.PC = p->PC; xa.ny = g.ny; xa.nrows = g.ny * p->nzl;
     xa.tw = p->tw_x; xa.twr = p->twr_x;
     xa.scale = (ppn || pn) ? 1.0 / f32(g.nx) : 1.0;           // poisson.f90:1074, :341
-    FEN_TRY(dispatch_x(c, p->M, xa, true));
+    FEN_TRY(dispatch_x(c, p->M, xa, true, fuse_rhs ? &dv : nullptr));
 
     LArgs la;
-    la.lx = p->mwn_x; la.lo = nullptr; la.ll = nullptr; la.norm = 1.0; la.o0 = 0;
+    la.lx = p->mwn_x; la.lo = nullptr; la.ll = nullptr; la.norm = 1.0; la.o0 = 0; la.cx0 = 0;
     if (pp) {
         // forward y + divide + inverse y fused (poisson.f90:451-478)
         la.C = p->C; la.sl = p->PC; la.so = 0; la.tw = p->tw_y; la.scale = 1.0;
@@ -657,6 +961,28 @@ int poisson_solve(fen_ctx* c, double* f) {
         }
         la.C = p->C; la.sl = p->PC; la.so = (long long)p->PC * g.ny; la.tw = p->tw_y;
         la.scale = ppn ? 1.0 / f32(g.ny) : 1.0;
+        // L2-resident chunking (one rank, ppp): the y-forward, z-solve and y-inverse passes of ONE group of kx
+        // columns touch the same ny*nz*NL*16 bytes (33.5 MB at 512^2 x 8), which fit the 126 MB L2; running the
+        // three passes chunk by chunk turns 3 reads + 3 writes of the spectral array through HBM into 1 + 1.
+        static const int chunk_groups = getenv("FEN_FFT_CHUNK") ? atoi(getenv("FEN_FFT_CHUNK")) : 0;
+        if (chunk_groups > 0 && ppp && !multi && g.ny >= 64 && g.nz >= 64) {
+            const int ngroups = p->PC / 8;
+            LArgs ly = la, lz = la;
+            lz.C = p->Cz; lz.sl = (long long)p->PC * p->nyl; lz.so = p->PC; lz.tw = p->tw_z; lz.scale = 1.0; lz.o0 = 0;
+            lz.lo = p->mwn_y; lz.ll = p->mwn_z; lz.norm = f32((long long)g.nx * g.ny * g.nz);
+            for (int g0 = 0; g0 < ngroups; g0 += chunk_groups) {
+                const int ng = std::min(chunk_groups, ngroups - g0);
+                ly.cx0 = lz.cx0 = g0;
+                ly.scale = la.scale;
+                FEN_TRY(dispatch_lines(c, g.ny, ly, 0, ng * 8, p->nzl));
+                FEN_TRY(dispatch_lines(c, g.nz, lz, 2, ng * 8, p->nyl));
+                ly.scale = 1.0;
+                FEN_TRY(dispatch_lines(c, g.ny, ly, 1, ng * 8, p->nzl));
+            }
+            xa.scale = 1.0;
+            FEN_TRY(dispatch_x(c, p->M, xa, false));
+            return FEN_OK;
+        }
         FEN_TRY(dispatch_lines(c, g.ny, la, 0, p->PC, p->nzl, multi ? &sf : nullptr));
         if (multi) FEN_TRY(comm_transpose_fwd(c));
         double2* Z = p->Cz;

@@ -14,6 +14,8 @@
 // All kernels map threadIdx.x to the x (fastest) index so every warp reads/writes contiguous
 // 256-byte runs; a block owns a (TX x TY) column of cells and marches KZ planes in z so that the
 // three z-planes a stencil needs stay in L1 while the 126 MB L2 holds the neighbouring tiles.
+#include <cstdlib>
+
 #include "fen_internal.cuh"
 #include "tma.cuh"
 
@@ -30,6 +32,7 @@ struct StArgs {
     double* un; double* vn; double* wn;
     double rho0, mu0;                               // uniform values
     double idelta, idelta2, dt, A, B, g0, g1, g2;
+    int xper;                                       // x periodic: the kernel also writes the x ghosts of its rows
 };
 
 __device__ __forceinline__ double sq(double x) { return x * x; }
@@ -179,7 +182,7 @@ constexpr int PTILE = PTW * PTH;                                  // doubles per
 constexpr int PTILE_B = (PTILE * 8 + 127) / 128 * 128;            // bytes per box slot (128-byte aligned for TMA)
 constexpr int PRED_SMEM = 12 * PTILE_B + 64;
 
-template <bool UNIT>
+template <bool UNIT, bool XG>
 __global__ void __launch_bounds__(PX* PY, 2)
 k_pred_tma(const __grid_constant__ CUtensorMap mu_, const __grid_constant__ CUtensorMap mv_,
            const __grid_constant__ CUtensorMap mw_, StArgs a) {
@@ -225,6 +228,7 @@ k_pred_tma(const __grid_constant__ CUtensorMap mu_, const __grid_constant__ CUte
     mbar_wait(bar + 0, 0);
     mbar_wait(bar + 1, 0);
     const int o = (ty + 1) * PTW + tx + 2;             // my cell inside a box
+    const int goff = !XG ? 0 : (i == 1 ? a.L.nx : (i == a.L.nx ? -a.L.nx : 0));   // my periodic image, if any
     for (int k = kb; k <= ke; ++k) {
         const int q = k - (kb - 1);                    // ring position of the centre plane
         mbar_wait(bar + ((q + 1) & 3), ((q + 1) >> 2) & 1);
@@ -261,6 +265,11 @@ k_pred_tma(const __grid_constant__ CUtensorMap mu_, const __grid_constant__ CUte
             a.dvox[c] = dvx;                           // dv_o = dv (:201-205)
             a.dvoy[c] = dvy;
             a.dvoz[c] = dvz;
+            if (XG && goff != 0) {                     // periodic x ghosts (scalar.f90:257,276)
+                a.un[c + goff] = s.u0 + dt * rx;
+                a.vn[c + goff] = s.v0 + dt * ry;
+                a.wn[c + goff] = s.w0 + dt * rz;
+            }
         }
         p0 = pkp; pkp = n_pkp; pip = n_pip; pjp = n_pjp;
         dox = n_dox; doy = n_doy; doz = n_doz;
@@ -363,6 +372,145 @@ __global__ void __launch_bounds__(TX* TY) k_corr(CorrArgs a) {
         a.v[c] = a.v[c] - ((phi[c + a.L.sy] - f0) * id) * dt / rfy;
         if (D3) a.w[c] = a.w[c] - ((phi[c + a.L.sz] - f0) * id) * dt / rfz;
         a.p[c] = a.p[c] + f0;      // navier_stokes.f90:561 (ghosts are refreshed right after)
+    }
+}
+
+// ---- 3-D uniform-property correction + pressure update + checks, TMA-staged ---------------------------
+// correct_velocity_field (navier_stokes.f90:505-546), update_pressure (:550-566) and checks (:570-619) in one
+// pass: reads phi, u*, v*, w*, p once and writes u, v, w, p once (72 B/cell); the divergence and velocity maxima
+// of `checks` come out of the same registers, so the 24 B/cell re-read of u, v, w disappears.
+// The divergence of the corrected field at (i,j,k) needs u(i-1), v(j-1), w(k-1): u(i-1) and v(j-1) are
+// recomputed from the staged tiles with the same rounded operations the owning thread uses (corr_val, no FMA
+// contraction), so they are bit-identical to the stored values; w(k-1) is the thread's own previous plane.
+// Valid when x and y are periodic (ghost = periodic image, which the formula reproduces from the ghosts of u*
+// and phi); z may be periodic, a rank boundary, or a wall with a zero/uniform normal velocity (w is then the
+// wall value on the boundary faces, scalar.f90:355,377-378).  Output goes to the ping-pong buffers because
+// neighbouring blocks still read u* from the halo of their boxes.
+constexpr int CKZ = 32;
+constexpr int CORR_SMEM = 16 * PTILE_B + 64;
+
+struct CorrTArgs {
+    Layout L;
+    const double* p; double* pn;                   // p is updated in place (own cell only)
+    double* un; double* vn; double* wn;
+    double rho0, idelta, dt;
+    int xper;                                      // also write the periodic x ghosts of u, v, w, p
+    int wall_lo, wall_hi;                          // this rank owns the z wall on that side
+    double wlo, whi;                               // wall-normal velocity there
+    double* partial;                               // [2 * nblocks] (maxdiv, maxvel)
+};
+
+// v - ((phi_hi - phi_lo) * id) * dt / rhof   (navier_stokes.f90:533-536), every operation rounded once
+template <bool UNIT>
+__device__ __forceinline__ double corr_val(double vstar, double phi_hi, double phi_lo, double id, double dt, double rf) {
+    double g = __dmul_rn(__dmul_rn(__dsub_rn(phi_hi, phi_lo), id), dt);
+    if (!UNIT) g = __ddiv_rn(g, rf);
+    return __dsub_rn(vstar, g);
+}
+
+template <bool UNIT>
+__global__ void __launch_bounds__(PX* PY, 2)
+k_corr_tma(const __grid_constant__ CUtensorMap mf_, const __grid_constant__ CUtensorMap mu_,
+           const __grid_constant__ CUtensorMap mv_, const __grid_constant__ CUtensorMap mw_, CorrTArgs a) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem + 16 * PTILE_B);
+    const int tx = threadIdx.x, ty = threadIdx.y;
+    const int tid = ty * PX + tx;
+    const int i = blockIdx.x * PX + tx + 1;
+    const int j = blockIdx.y * PY + ty + 1;
+    const int kb = blockIdx.z * CKZ + 1;
+    const int ke = min(kb + CKZ - 1, a.L.nzl);
+    const int x0 = a.L.xoff - 2 + blockIdx.x * PX;     // box origin: cell (i0 - 2, j0 - 1)
+    const int y0 = blockIdx.y * PY;
+    if (tid == 0) {
+        for (int q = 0; q < 4; ++q) mbar_init(bar + q, 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+    auto slot = [&](int q, int f) { return reinterpret_cast<double*>(smem + (size_t)((q & 3) * 4 + f) * PTILE_B); };
+    // plane set z in [kb-1, ke+1]: phi always; w* for z <= ke; u*, v* for kb <= z <= ke
+    auto issue = [&](int z) {
+        const int q = z - (kb - 1);
+        uint64_t* b = bar + (q & 3);
+        const bool mid = z >= kb && z <= ke;
+        mbar_expect_tx(b, (uint32_t)((mid ? 4 : (z < kb ? 2 : 1)) * PTILE * 8));
+        tma_load_3d(slot(q, 0), &mf_, x0, y0, z, b);
+        if (z <= ke) tma_load_3d(slot(q, 3), &mw_, x0, y0, z, b);
+        if (mid) {
+            tma_load_3d(slot(q, 1), &mu_, x0, y0, z, b);
+            tma_load_3d(slot(q, 2), &mv_, x0, y0, z, b);
+        }
+    };
+    if (tid == 0) {
+        issue(kb - 1);
+        issue(kb);
+        issue(kb + 1);
+        if (kb + 2 <= ke + 1) issue(kb + 2);
+    }
+    const bool active = i <= a.L.nx && j <= a.L.ny;
+    const long long sz = a.L.sz;
+    long long c = a.L.idx(active ? i : 1, active ? j : 1, kb);
+    const double id = a.idelta, dt = a.dt;
+    const double rf = 0.5 * (a.rho0 + a.rho0);
+    const int o = (ty + 1) * PTW + tx + 2;             // my cell inside a box
+    double p0 = a.p[c];
+    mbar_wait(bar + 0, 0);
+    mbar_wait(bar + 1, 0);
+    // w(k-1) of the first plane: recomputed, or the wall value
+    double wkm;
+    {
+        const double* fm = slot(0, 0); const double* fc = slot(1, 0); const double* wm = slot(0, 3);
+        wkm = corr_val<UNIT>(wm[o], fc[o], fm[o], id, dt, rf);
+        if (a.wall_lo && kb == 1) wkm = a.wlo;
+    }
+    double md = -1.0e300, mv = 0.0;
+    for (int k = kb; k <= ke; ++k) {
+        const int q = k - (kb - 1);                    // ring position of plane k
+        mbar_wait(bar + ((q + 1) & 3), ((q + 1) >> 2) & 1);
+        __syncthreads();                               // everybody is done with plane k-1: its slot is free
+        if (tid == 0 && k + 3 <= ke + 1) issue(k + 3);
+        double n_p = 0.0;
+        if (k < ke) n_p = a.p[c + sz];
+        const double* fc = slot(q, 0); const double* fp = slot(q + 1, 0);
+        const double* us = slot(q, 1); const double* vs = slot(q, 2); const double* ws = slot(q, 3);
+        const double f0 = fc[o];
+        const double un = corr_val<UNIT>(us[o], fc[o + 1], f0, id, dt, rf);
+        const double vn = corr_val<UNIT>(vs[o], fc[o + PTW], f0, id, dt, rf);
+        double wn = corr_val<UNIT>(ws[o], fp[o], f0, id, dt, rf);
+        if (a.wall_hi && k == a.L.nzl) wn = a.whi;     // scalar.f90:377: the last interior face is the wall
+        const double uim = corr_val<UNIT>(us[o - 1], f0, fc[o - 1], id, dt, rf);
+        const double vjm = corr_val<UNIT>(vs[o - PTW], f0, fc[o - PTW], id, dt, rf);
+        if (active) {
+            a.un[c] = un;
+            a.vn[c] = vn;
+            a.wn[c] = wn;
+            a.pn[c] = p0 + f0;                         // navier_stokes.f90:561
+            if (a.xper) {                              // periodic x ghosts (scalar.f90:257,276)
+                if (i == 1) { const long long gh = c + a.L.nx; a.un[gh] = un; a.vn[gh] = vn; a.wn[gh] = wn; a.pn[gh] = p0 + f0; }
+                if (i == a.L.nx) { const long long gh = c - a.L.nx; a.un[gh] = un; a.vn[gh] = vn; a.wn[gh] = wn; a.pn[gh] = p0 + f0; }
+            }
+            // checks (:587-617): divergence as fields.f90:144-147, signed max (H6)
+            double d = (un - uim) * id + (vn - vjm) * id;
+            d = d + (wn - wkm) * id;
+            md = fmax(md, d);
+            mv = fmax(mv, fabs(un) + fabs(vn) + fabs(wn));
+        }
+        wkm = wn;
+        p0 = n_p;
+        c += sz;
+    }
+    __shared__ double s0[PX * PY / 32], s1[PX * PY / 32];
+    for (int o2 = 16; o2 > 0; o2 >>= 1) {
+        md = fmax(md, __shfl_xor_sync(0xffffffffu, md, o2));
+        mv = fmax(mv, __shfl_xor_sync(0xffffffffu, mv, o2));
+    }
+    if ((tid & 31) == 0) { s0[tid >> 5] = md; s1[tid >> 5] = mv; }
+    __syncthreads();
+    if (tid == 0) {
+        for (int q = 1; q < PX * PY / 32; ++q) { md = fmax(md, s0[q]); mv = fmax(mv, s1[q]); }
+        const long long b = blockIdx.x + (long long)gridDim.x * (blockIdx.y + (long long)gridDim.y * blockIdx.z);
+        a.partial[2 * b] = md;
+        a.partial[2 * b + 1] = mv;
     }
 }
 
@@ -594,19 +742,33 @@ int ns_predict(fen_ctx* c, double dt) {
     const bool gen = general_path(c);
     if (gen) FEN_TRY(ensure_general_fields(c, a));
     dim3 grid = st_grid(c->L), block(TX, TY);
+    bool x_done = false;
+    a.xper = 0;
     if (d3 && !gen) {
+        x_done = true;
+        for (int q = 0; q < 3; ++q)
+            x_done = x_done && c->fields[FEN_VX + q].bc_type[FEN_LEFT] == FEN_PERIODIC &&
+                     c->fields[FEN_VX + q].bc_type[FEN_RIGHT] == FEN_PERIODIC;
+        a.xper = x_done ? 1 : 0;
         // TMA-staged kernel: tensor maps of the three velocity buffers (cached per buffer)
         CUtensorMap* m[3];
         for (int q = 0; q < 3; ++q) FEN_TRY(field_tmap(c, q == 0 ? a.u : (q == 1 ? a.v : a.w), PTW, PTH, &m[q]));
         static bool attr_done = false;
         if (!attr_done) {
-            FEN_CUDA(cudaFuncSetAttribute(k_pred_tma<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, PRED_SMEM));
-            FEN_CUDA(cudaFuncSetAttribute(k_pred_tma<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, PRED_SMEM));
+            FEN_CUDA(cudaFuncSetAttribute(k_pred_tma<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, PRED_SMEM));
+            FEN_CUDA(cudaFuncSetAttribute(k_pred_tma<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, PRED_SMEM));
+            FEN_CUDA(cudaFuncSetAttribute(k_pred_tma<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, PRED_SMEM));
+            FEN_CUDA(cudaFuncSetAttribute(k_pred_tma<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, PRED_SMEM));
             attr_done = true;
         }
+        static const bool xg_env = !getenv("FEN_PRED_XG") || atoi(getenv("FEN_PRED_XG")) != 0;
+        x_done = x_done && xg_env;
         dim3 pg((c->L.nx + PX - 1) / PX, (c->L.ny + PY - 1) / PY, (c->L.nzl + PKZ - 1) / PKZ), pb(PX, PY);
-        if (a.rho0 == 1.0) FEN_LAUNCH(c, "pred", k_pred_tma<true><<<pg, pb, PRED_SMEM, c->stream>>>(*m[0], *m[1], *m[2], a));
-        else FEN_LAUNCH(c, "pred", k_pred_tma<false><<<pg, pb, PRED_SMEM, c->stream>>>(*m[0], *m[1], *m[2], a));
+        const bool unit = a.rho0 == 1.0;
+        if (unit && x_done) FEN_LAUNCH(c, "pred", k_pred_tma<true, true><<<pg, pb, PRED_SMEM, c->stream>>>(*m[0], *m[1], *m[2], a));
+        else if (unit) FEN_LAUNCH(c, "pred", k_pred_tma<true, false><<<pg, pb, PRED_SMEM, c->stream>>>(*m[0], *m[1], *m[2], a));
+        else if (x_done) FEN_LAUNCH(c, "pred", k_pred_tma<false, true><<<pg, pb, PRED_SMEM, c->stream>>>(*m[0], *m[1], *m[2], a));
+        else FEN_LAUNCH(c, "pred", k_pred_tma<false, false><<<pg, pb, PRED_SMEM, c->stream>>>(*m[0], *m[1], *m[2], a));
     } else if (d3) {
         FEN_LAUNCH(c, "pred", k_pred<true, true><<<grid, block, 0, c->stream>>>(a));
     } else {
@@ -616,7 +778,7 @@ int ns_predict(fen_ctx* c, double dt) {
     FEN_CUDA(cudaGetLastError());
     // v now lives in the freshly written buffers; the old ones become the next scratch
     for (int m = 0; m < (d3 ? 3 : 2); ++m) std::swap(c->fields[FEN_VX + m].d, c->vnew[m]);
-    return ghost_update(c, FEN_VX, d3 ? 3 : 2);      // navier_stokes.f90:208
+    return ghost_update(c, FEN_VX, d3 ? 3 : 2, x_done);      // navier_stokes.f90:208
 }
 
 int op_explicit_terms(fen_ctx* c, int rhs_x, bool advection_only) {
@@ -628,6 +790,7 @@ int op_explicit_terms(fen_ctx* c, int rhs_x, bool advection_only) {
     a.un = o[0]->d; a.vn = o[1]->d; a.wn = o[2] ? o[2]->d : nullptr;
     a.dvox = a.dvoy = a.dvoz = nullptr;
     a.dt = a.A = a.B = a.g0 = a.g1 = a.g2 = 0.0;
+    a.xper = 0;
     const bool gen = general_path(c) && !advection_only;
     if (gen) FEN_TRY(ensure_general_fields(c, a));
     dim3 grid = st_grid(c->L), block(TX, TY);
@@ -667,14 +830,75 @@ static int launch_rhs(fen_ctx* c, int vx, int s, bool scale, double dt) {
 int ns_poisson_rhs(fen_ctx* c, double dt) { return launch_rhs(c, FEN_VX, FEN_PHI, true, dt); }
 int op_divergence(fen_ctx* c, int vx, int s) { return launch_rhs(c, vx, s, false, 1.0); }
 
-int ns_correct(fen_ctx* c, double dt) {
+// the fused correction + checks kernel applies (see k_corr_tma): 3-D, uniform properties, x and y periodic for
+// every field it touches, and in z either periodic / rank boundary or a wall with a zero or uniform w
+static bool corr_fused_ok(fen_ctx* c) {
+    if (c->g.ndim != 3 || !c->uniform_props) return false;
+    const int ids[5] = {FEN_VX, FEN_VY, FEN_VZ, FEN_P, FEN_PHI};
+    for (int id : ids)
+        for (int face = 0; face < 4; ++face)
+            if (c->fields[id].bc_type[face] != FEN_PERIODIC) return false;
+    const Field& w = c->fields[FEN_VZ];
+    for (int face = FEN_FRONT; face <= FEN_BACK; ++face) {
+        const int t = w.bc_type[face];
+        if (t == FEN_PERIODIC || t == FEN_HALO) continue;
+        if (t == FEN_DIRICHLET && w.bc_mode[face] != BC_PLANE) continue;
+        return false;
+    }
+    return true;
+}
+
+int ns_correct(fen_ctx* c, double dt, bool* checks_done) {
     const bool d3 = c->g.ndim == 3;
+    if (checks_done) *checks_done = false;
     Field *u, *v, *w = nullptr, *p, *phi;
     FEN_TRY(field_check(c, FEN_VX, &u));
     FEN_TRY(field_check(c, FEN_VY, &v));
     if (d3) FEN_TRY(field_check(c, FEN_VZ, &w));
     FEN_TRY(field_check(c, FEN_P, &p));
     FEN_TRY(field_check(c, FEN_PHI, &phi));
+    if (corr_fused_ok(c) && c->vnew[0] && c->vnew[1] && c->vnew[2]) {
+        CUtensorMap* m[4];
+        const double* src[4] = {phi->d, u->d, v->d, w->d};
+        for (int q = 0; q < 4; ++q) FEN_TRY(field_tmap(c, src[q], PTW, PTH, &m[q]));
+        static bool attr_done = false;
+        if (!attr_done) {
+            FEN_CUDA(cudaFuncSetAttribute(k_corr_tma<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, CORR_SMEM));
+            FEN_CUDA(cudaFuncSetAttribute(k_corr_tma<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, CORR_SMEM));
+            attr_done = true;
+        }
+        FEN_TRY(ensure_red(c));
+        CorrTArgs a;
+        a.L = c->L;
+        a.p = p->d; a.pn = p->d;
+        a.un = c->vnew[0]; a.vn = c->vnew[1]; a.wn = c->vnew[2];
+        a.rho0 = c->rho_uniform;
+        a.idelta = 1.0 / c->g.delta;
+        a.dt = dt;
+        a.xper = 1;                                        // corr_fused_ok: x is periodic for u, v, w, p
+        a.wall_lo = w->bc_type[FEN_FRONT] == FEN_DIRICHLET;
+        a.wall_hi = w->bc_type[FEN_BACK] == FEN_DIRICHLET;
+        a.wlo = w->bc_mode[FEN_FRONT] == BC_UNIFORM ? w->bc_value[FEN_FRONT] : 0.0;
+        a.whi = w->bc_mode[FEN_BACK] == BC_UNIFORM ? w->bc_value[FEN_BACK] : 0.0;
+        a.partial = c->d_red + 16;
+        dim3 cg((c->L.nx + PX - 1) / PX, (c->L.ny + PY - 1) / PY, (c->L.nzl + CKZ - 1) / CKZ), cb(PX, PY);
+        if (a.rho0 == 1.0)
+            FEN_LAUNCH(c, "corr_check", k_corr_tma<true><<<cg, cb, CORR_SMEM, c->stream>>>(*m[0], *m[1], *m[2], *m[3], a));
+        else
+            FEN_LAUNCH(c, "corr_check", k_corr_tma<false><<<cg, cb, CORR_SMEM, c->stream>>>(*m[0], *m[1], *m[2], *m[3], a));
+        FEN_CUDA(cudaGetLastError());
+        for (int q = 0; q < 3; ++q) std::swap(c->fields[FEN_VX + q].d, c->vnew[q]);
+        FEN_TRY(ghost_update(c, FEN_VX, 3, true));         // navier_stokes.f90:544
+        FEN_TRY(ghost_update(c, FEN_P, 1, true));          // navier_stokes.f90:564
+        if (checks_done) {
+            const long long nb = (long long)cg.x * cg.y * cg.z;
+            FEN_LAUNCH(c, "reduce", k_reduce_final<0><<<1, 256, 0, c->stream>>>(c->d_red + 16, nb, 2, c->d_red));
+            FEN_CUDA(cudaGetLastError());
+            if (c->g.nranks > 1) FEN_TRY(comm_allreduce(c, c->d_red, 2, 0));   // navier_stokes.f90:614, scalar.f90:194
+            *checks_done = true;
+        }
+        return FEN_OK;
+    }
     CorrArgs a;
     a.L = c->L;
     a.u = u->d; a.v = v->d; a.w = w ? w->d : nullptr; a.p = p->d; a.phi = phi->d;

@@ -1,0 +1,68 @@
+"""Host-side slab decomposition logic (no GPU, no numpy on the hot path): FEN's own 2decomp layout with
+``(prow, pcol) = (1, P)`` (src/grid.f90:125,168-173; test/small_test/fields/methods.f90:21).
+
+These are the rules the CUDA library applies internally (context.cu / comm.cu / poisson.cu); they are
+restated here so that launchers (bench.py, tests, a Fortran/MPI driver) can size and place per-rank data, and
+so that the N > 1 host logic can be tested with ``gloo`` on machines without a GPU.
+"""
+from __future__ import annotations
+
+
+def slab_bounds(nx: int, ny: int, nz: int, nranks: int, rank: int):
+    """x-pencil bounds ``lo(3), hi(3)`` (1-based, inclusive) of `rank`: x and y whole, z in equal slabs."""
+    if nranks < 1 or not 0 <= rank < nranks:
+        raise ValueError("bad rank %d of %d" % (rank, nranks))
+    if nz % nranks:
+        raise ValueError("nz = %d is not divisible by the number of ranks %d" % (nz, nranks))
+    nzl = nz // nranks
+    return (1, 1, rank * nzl + 1), (nx, ny, (rank + 1) * nzl)
+
+
+def zpencil_bounds(nx: int, ny: int, nz: int, nranks: int, rank: int):
+    """Bounds of `rank` in the z-pencil layout of the Poisson solver's last-direction stage: z whole, y split
+    (src/grid.f90:172-173 with prow = 1)."""
+    if ny % nranks:
+        raise ValueError("ny = %d is not divisible by the number of ranks %d" % (ny, nranks))
+    nyl = ny // nranks
+    return (1, rank * nyl + 1, 1), (nx, (rank + 1) * nyl, nz)
+
+
+def z_neighbours(nranks: int, rank: int, periodic: bool):
+    """(front, back) neighbour ranks of a slab, -1 at a non-periodic domain end (2decomp update_halo wraps
+    around when the direction was declared periodic in decomp_2d_init, src/halo.f90:33)."""
+    lo, hi = rank - 1, rank + 1
+    if lo < 0:
+        lo = nranks - 1 if periodic else -1
+    if hi >= nranks:
+        hi = 0 if periodic else -1
+    return lo, hi
+
+
+def transpose_blocks(ny: int, nz: int, nranks: int, rank: int):
+    """Blocks `rank` sends in the y-slab -> z-pencil transpose (transpose_y_to_z, src/poisson.f90:982):
+    list of ``(dest, (j_lo, j_hi), (k_lo, k_hi))``, 1-based inclusive global index ranges."""
+    (_, _, k0), (_, _, k1) = slab_bounds(1, ny, nz, nranks, rank)
+    out = []
+    for dest in range(nranks):
+        (_, j0, _), (_, j1, _) = zpencil_bounds(1, ny, nz, nranks, dest)
+        out.append((dest, (j0, j1), (k0, k1)))
+    return out
+
+
+def alltoall_bytes_per_gpu(nx: int, ny: int, nz: int, nranks: int) -> int:
+    """Bytes one GPU sends over NVLink per transpose: half-spectrum complex, the (P-1)/P off-rank share."""
+    local = (nx // 2 + 1) * ny * (nz // nranks) * 16
+    return local * (nranks - 1) // nranks
+
+
+def gather_handles(all_gather, blob: bytes, nranks: int) -> bytes:
+    """Concatenation of every rank's exported handle in RANK ORDER, as fen_gpu_comm_connect expects.
+    ``all_gather(obj) -> list`` is any collective (torch.distributed.all_gather_object, MPI, threads)."""
+    parts = list(all_gather(blob))
+    if len(parts) != nranks:
+        raise ValueError("all_gather returned %d parts for %d ranks" % (len(parts), nranks))
+    n = len(blob)
+    for r, p in enumerate(parts):
+        if len(p) != n:
+            raise ValueError("rank %d exported %d bytes, expected %d" % (r, len(p), n))
+    return b"".join(parts)

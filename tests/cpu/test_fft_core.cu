@@ -58,8 +58,76 @@ template <int L> static int both() {
     return (ef < 1e-11 && eb < 1e-11) ? 0 : 1;
 }
 
+// register-to-register flow of fft_regs<L, DIR, true> (L >= 64): inputs and outputs live in the threads'
+// registers, v[m] <-> element t + m * L / 8; barriers are the boundaries between the thread loops
+template <int L, int DIR> static double check_regs(int IS, int NL) {
+    constexpr int T = FftPlan<L>::T, N8 = FftPlan<L>::N8, REM = FftPlan<L>::REM;
+    constexpr int NST = N8 + (REM > 1 ? 1 : 0);
+    std::vector<double2> tw(L);
+    for (int m = 0; m < L; ++m) tw[m] = make_double2(cos(-2.0 * M_PI * m / L), sin(-2.0 * M_PI * m / L));
+    std::vector<double2> s((size_t)L * IS, make_double2(0, 0)), in((size_t)L * NL);
+    std::vector<double2> regs((size_t)NL * T * 8);
+    unsigned seed = 777u + L;
+    for (int line = 0; line < NL; ++line)
+        for (int i = 0; i < L; ++i) {
+            seed = seed * 1664525u + 1013904223u; double a = (seed >> 8) / 16777216.0 - 0.5;
+            seed = seed * 1664525u + 1013904223u; double b = (seed >> 8) / 16777216.0 - 0.5;
+            in[(size_t)line * L + i] = make_double2(a, b);
+        }
+    auto R = [&](int line, int t) { return &regs[((size_t)line * T + t) * 8]; };
+    for (int line = 0; line < NL; ++line)
+        for (int t = 0; t < T; ++t)
+            for (int m = 0; m < 8; ++m) R(line, t)[m] = in[(size_t)line * L + t + m * (L / 8)];
+    int Ns = 1;
+    bool done = false;
+    for (int st = 0; st < N8 && !done; ++st) {
+        if (st > 0)
+            for (int line = 0; line < NL; ++line)
+                for (int t = 0; t < T; ++t) stage_load<L, 8, DIR>(R(line, t), s.data(), IS, line, t);
+        for (int line = 0; line < NL; ++line)
+            for (int t = 0; t < T; ++t) {
+                stage_compute<L, 8, DIR>(R(line, t), t, Ns, tw.data());
+                if (st != NST - 1) stage_write<L, 8>(R(line, t), s.data(), IS, line, t, Ns);
+            }
+        if (st == NST - 1) done = true;
+        Ns *= 8;
+    }
+    if constexpr (REM > 1) {
+        for (int line = 0; line < NL; ++line)
+            for (int t = 0; t < T; ++t) stage_load<L, REM, DIR>(R(line, t), s.data(), IS, line, t);
+        for (int line = 0; line < NL; ++line)
+            for (int t = 0; t < T; ++t) {
+                stage_compute<L, REM, DIR>(R(line, t), t, Ns, tw.data());
+                last_permute<REM>(R(line, t));
+            }
+    }
+    double emax = 0;
+    for (int line = 0; line < NL; ++line)
+        for (int k = 0; k < L; ++k) {
+            double re = 0, im = 0;
+            for (int n = 0; n < L; ++n) {
+                double ang = DIR * 2.0 * M_PI * (double)((long long)n * k % L) / L;
+                double2 x = in[(size_t)line * L + n];
+                re += x.x * cos(ang) - x.y * sin(ang);
+                im += x.x * sin(ang) + x.y * cos(ang);
+            }
+            const int t = k % (L / 8), m = k / (L / 8);
+            double2 y = R(line, t)[m];
+            emax = fmax(emax, fmax(fabs(y.x - re), fabs(y.y - im)));
+        }
+    return emax;
+}
+
+template <int L> static int both_regs() {
+    double ef = check_regs<L, -1>(8, 8), eb = check_regs<L, +1>(9, 4);
+    printf("L=%d regs fwd=%.3e inv=%.3e\n", L, ef, eb);
+    return (ef < 1e-11 && eb < 1e-11) ? 0 : 1;
+}
+
 int main() {
     int bad = 0;
+    bad += both_regs<64>(); bad += both_regs<128>(); bad += both_regs<256>(); bad += both_regs<512>();
+    bad += both_regs<1024>(); bad += both_regs<2048>();
     bad += both<2>(); bad += both<4>(); bad += both<8>(); bad += both<16>(); bad += both<32>();
     bad += both<64>(); bad += both<128>(); bad += both<256>(); bad += both<512>(); bad += both<1024>();
     bad += both<2048>();
