@@ -38,6 +38,7 @@ struct Poisson {
     double2* C = nullptr;           // [PC][ny][nzl]
     double2* Cz = nullptr;          // [PC][nyl][nz] (multi-rank only; == C on one rank)
     double2 *tw_x = nullptr, *twr_x = nullptr, *tw_y = nullptr, *tw_z = nullptr;
+    double2 *twq_x = nullptr, *twq_y = nullptr;   // exp(-i pi k / (2n)): DCT half-sample phases (Neumann directions)
     double *mwn_x = nullptr, *mwn_y = nullptr, *mwn_z = nullptr;
     double *ta = nullptr, *tb = nullptr, *tc = nullptr;   // tridiagonal a, b, c
     double* c1 = nullptr;           // Thomas c1 table, indexed like the line layout
@@ -217,7 +218,7 @@ struct LArgs {
     // spectral divide (k_fft_solve only): lam = (lx[kx] + lo[o]) + ll[l]   (poisson.f90:998)
     const double* lx; const double* lo; const double* ll;
     double norm;           // float(nx*ny*nz)  (poisson.f90:992)
-    int cx0;               // first kx group of this launch (L2-resident chunking, see poisson_solve)
+    int cx0;               // first kx group of this launch (0 unless a caller splits the kx range)
 };
 
 template <int Lf, int DIR, int NL, bool SC>
@@ -476,6 +477,96 @@ __global__ void __launch_bounds__(NL* FftPlan<Lf>::T, (NL * FftPlan<Lf>::T <= 10
 }
 
 // =================================================================================================
+// Neumann directions: FFTW REDFT10 / REDFT01 (DCT-II / DCT-III, poisson.f90:272-275, :801-804, :888-909)
+// through one complex transform of the same length (Makhoul's reordering):
+//   DCT-II :  v[n] = x[2n], v[N-1-n] = x[2n+1];  V = FFT(v);  Y[k] = 2 Re(exp(-i pi k / 2N) V[k])
+//   DCT-III:  W[k] = (X[k] - i X[N-k]) exp(+i pi k / 2N), X[N] = 0;  v = FFT^-1(W) (unnormalised);
+//             y[2n] = Re v[n], y[2n+1] = Re v[N-1-n]
+// (checked against scipy.fft.dct types 2 / 3 = FFTW's definitions in tests/).  The data of these variants is
+// real; it is carried in the real part of a full-width complex work array C[i + PC*(j + ny*k)], PC =
+// roundup(nx, 8), so that the y transforms and the Thomas kernels are the same ones the periodic variants use.
+// =================================================================================================
+struct DArgs {
+    Layout L;
+    double* f;
+    double2* C;
+    int PC, ny, nrows;
+    const double2* tw;     // exp(-2 pi i m / N)
+    const double2* twq;    // exp(-i pi k / (2N))
+    double scale;
+};
+__device__ __forceinline__ int dct_perm(int i, int N) { return (i & 1) ? N - 1 - (i >> 1) : (i >> 1); }
+
+template <int N, int DIR>
+__global__ void __launch_bounds__(XR* FftPlan<N>::T) k_dct_x(DArgs a) {
+    extern __shared__ double2 s[];
+    constexpr int T = FftPlan<N>::T;
+    constexpr int NT = XR * T;
+    const int tid = threadIdx.x;
+    const int row0 = blockIdx.x * XR;
+    for (int e = tid; e < XR * N; e += NT) {
+        const int row = e / N, i = e - row * N;
+        const int r = row0 + row;
+        double2 z = make_double2(0.0, 0.0);
+        if (r < a.nrows) {
+            if (DIR < 0) {
+                const int j = r % a.ny, k = r / a.ny;
+                z.x = a.f[a.L.idx(1 + i, j + 1, k + 1)];
+                s[dct_perm(i, N) * XIS + row] = z;
+                continue;
+            }
+            const double2* X = a.C + (size_t)a.PC * r;
+            const double xk = X[i].x, xm = i > 0 ? X[N - i].x : 0.0;
+            z = cmul(make_double2(xk, -xm), cconj(__ldg(&a.twq[i])));
+        }
+        s[(DIR < 0 ? dct_perm(i, N) : i) * XIS + row] = z;
+    }
+    __syncthreads();
+    fft_lines<N, DIR>(s, XIS, tid % XR, tid / XR, true, a.tw);
+    for (int e = tid; e < XR * N; e += NT) {
+        const int row = e / N, i = e - row * N;
+        const int r = row0 + row;
+        if (r >= a.nrows) continue;
+        if (DIR < 0) {
+            const double2 V = s[i * XIS + row], q = __ldg(&a.twq[i]);
+            a.C[(size_t)a.PC * r + i] = make_double2(2.0 * (V.x * q.x - V.y * q.y) * a.scale, 0.0);
+        } else {
+            const int j = r % a.ny, k = r / a.ny;
+            a.f[a.L.idx(1 + i, j + 1, k + 1)] = s[dct_perm(i, N) * XIS + row].x * a.scale;
+        }
+    }
+}
+
+// DCT along a strided direction, in place on the real parts of C (nnn: y direction)
+template <int Lf, int DIR, int NL>
+__global__ void __launch_bounds__(NL* FftPlan<Lf>::T) k_dct_lines(LArgs a, const double2* twq) {
+    extern __shared__ double2 s[];
+    constexpr int T = FftPlan<Lf>::T;
+    const int tid = threadIdx.x;
+    const int line = tid % NL, t = tid / NL;
+    const int kx = (blockIdx.x + a.cx0) * NL + line;
+    double2* base = a.C + kx + a.so * blockIdx.y;
+    for (int i = t; i < Lf; i += T) {
+        if (DIR < 0) {
+            s[dct_perm(i, Lf) * NL + line] = make_double2(base[a.sl * i].x, 0.0);
+        } else {
+            const double xk = base[a.sl * i].x, xm = i > 0 ? base[a.sl * (Lf - i)].x : 0.0;
+            s[i * NL + line] = cmul(make_double2(xk, -xm), cconj(__ldg(&twq[i])));
+        }
+    }
+    __syncthreads();
+    fft_lines<Lf, DIR>(s, NL, line, t, true, a.tw);
+    for (int i = t; i < Lf; i += T) {
+        if (DIR < 0) {
+            const double2 V = s[i * NL + line], q = __ldg(&twq[i]);
+            base[a.sl * i] = make_double2(2.0 * (V.x * q.x - V.y * q.y) * a.scale, 0.0);
+        } else {
+            base[a.sl * i] = make_double2(s[dct_perm(i, Lf) * NL + line].x * a.scale, 0.0);
+        }
+    }
+}
+
+// =================================================================================================
 // Thomas algorithm along the last direction (poisson.f90:1092-1135 3-D form, :346-385 2-D form)
 // =================================================================================================
 struct TArgs {
@@ -659,6 +750,25 @@ static std::vector<double> mwn(int n, double delta, int pad) {
     return m;
 }
 
+static std::vector<double> mwn_neumann(int n, double delta, int pad) {
+    // 2(cos(pi (i-1)/float(n)) - 1)/delta**2   (poisson.f90:265, :794, :881, :899)
+    const double pi = std::acos(-1.0);
+    std::vector<double> m((size_t)std::max(n, pad), 1.0);
+    for (int i = 0; i < n; ++i) m[i] = 2.0 * (std::cos(1.0 * pi * (double)i / f32(n)) - 1.0) / (delta * delta);
+    return m;
+}
+
+static std::vector<double2> half_phases(int n) {
+    // exp(-i pi k / (2n)), k < n, evaluated in long double
+    std::vector<double2> t((size_t)n);
+    const long double pi = 3.141592653589793238462643383279502884L;
+    for (int k = 0; k < n; ++k) {
+        long double ang = -pi * (long double)k / (2.0L * (long double)n);
+        t[k] = make_double2((double)cosl(ang), (double)sinl(ang));
+    }
+    return t;
+}
+
 void poisson_destroy(fen_ctx* c) {
     Poisson* p = c->ps;
     if (!p) return;
@@ -666,7 +776,7 @@ void poisson_destroy(fen_ctx* c) {
         if (p->Cz && p->Cz != p->C) cudaFree(p->Cz);
         if (p->C) cudaFree(p->C);
     }
-    for (void* q : {(void*)p->tw_x, (void*)p->twr_x, (void*)p->tw_y, (void*)p->tw_z,
+    for (void* q : {(void*)p->tw_x, (void*)p->twr_x, (void*)p->tw_y, (void*)p->tw_z, (void*)p->twq_x, (void*)p->twq_y,
                     (void*)p->mwn_x, (void*)p->mwn_y, (void*)p->mwn_z, (void*)p->ta, (void*)p->tb,
                     (void*)p->tc, (void*)p->c1})
         if (q) cudaFree(q);
@@ -692,9 +802,11 @@ template <int M> static int set_smem_x() {
     return FEN_OK;
 }
 
-// tuning switches (defaults = the fastest measured at 512^3, profiles/):
-//   FEN_X_R2C: 0 register path   1 staged (coalesced load / rhs compute into shared memory)
-//   FEN_X_C2R: 0 register path   1 fully staged   2 staged load + register output
+// tuning switches; defaults = the fastest measured at 512^3 (profiles/r01f_variants.txt):
+//   FEN_X_R2C: 0 register path   1 staged (coalesced load / rhs compute into shared memory)   [1: 0.91 vs 1.69 ms]
+//   FEN_X_C2R: 0 register path   1 fully staged   2 staged load + register output            [2: 0.72 vs 0.95 ms]
+// Rows are contiguous, so a cooperative coalesced load (one 512-byte run per warp) beats the register path's
+// 64-byte-per-row gathers; the strided y/z passes are the other way round (86 % of HBM with the register path).
 static int x_variant(const char* name, int dflt) {
     const char* e = getenv(name);
     return e ? atoi(e) : dflt;
@@ -705,7 +817,7 @@ template <int M> static int launch_x(fen_ctx* c, const XArgs& a, bool fwd, const
     const int bytes = (M + 1) * XIS * (int)sizeof(double2);
     static bool attr_done = false;
     if (!attr_done) { FEN_TRY(set_smem_x<M>()); attr_done = true; }
-    static const int vr2c = x_variant("FEN_X_R2C", 0), vc2r = x_variant("FEN_X_C2R", 0);
+    static const int vr2c = x_variant("FEN_X_R2C", 1), vc2r = x_variant("FEN_X_C2R", 2);
     dim3 grid((a.nrows + XR - 1) / XR), block(XR * T);
     DivArgs none{};
     bool done = false;
@@ -800,6 +912,60 @@ static int dispatch_lines(fen_ctx* c, int Lf, const LArgs& a, int mode, int PC, 
     return set_error(FEN_ERR_UNSUPPORTED, "FFT length %d not supported (power of two, 1..2048)", Lf);
 }
 
+template <int N> static int launch_dct_x(fen_ctx* c, const DArgs& a, bool fwd) {
+    constexpr int T = FftPlan<N>::T;
+    const int bytes = N * XIS * (int)sizeof(double2);
+    static bool attr_done = false;
+    if (!attr_done) {
+        if (bytes > 48 * 1024) {
+            FEN_CUDA(cudaFuncSetAttribute(k_dct_x<N, -1>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+            FEN_CUDA(cudaFuncSetAttribute(k_dct_x<N, +1>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+        }
+        attr_done = true;
+    }
+    dim3 grid((a.nrows + XR - 1) / XR), block(XR * T);
+    if (fwd) FEN_LAUNCH(c, "dct_x_fwd", k_dct_x<N, -1><<<grid, block, bytes, c->stream>>>(a));
+    else FEN_LAUNCH(c, "dct_x_inv", k_dct_x<N, +1><<<grid, block, bytes, c->stream>>>(a));
+    FEN_CUDA(cudaGetLastError());
+    return FEN_OK;
+}
+static int dispatch_dct_x(fen_ctx* c, int N, const DArgs& a, bool fwd) {
+    switch (N) {
+#define FEN_CASE(m) case m: return launch_dct_x<m>(c, a, fwd);
+        FEN_CASE(2) FEN_CASE(4) FEN_CASE(8) FEN_CASE(16) FEN_CASE(32) FEN_CASE(64) FEN_CASE(128) FEN_CASE(256)
+        FEN_CASE(512) FEN_CASE(1024)
+#undef FEN_CASE
+    }
+    return set_error(FEN_ERR_UNSUPPORTED, "DCT length %d not supported (power of two, 2..1024)", N);
+}
+template <int Lf> static int launch_dct_lines(fen_ctx* c, const LArgs& a, const double2* twq, bool fwd, int nchunks,
+                                              int nouter) {
+    constexpr int T = FftPlan<Lf>::T;
+    const int bytes = Lf * 8 * (int)sizeof(double2);
+    static bool attr_done = false;
+    if (!attr_done) {
+        if (bytes > 48 * 1024) {
+            FEN_CUDA(cudaFuncSetAttribute(k_dct_lines<Lf, -1, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+            FEN_CUDA(cudaFuncSetAttribute(k_dct_lines<Lf, +1, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+        }
+        attr_done = true;
+    }
+    dim3 grid(nchunks, nouter), block(8 * T);
+    if (fwd) FEN_LAUNCH(c, "dct_lines_fwd", k_dct_lines<Lf, -1, 8><<<grid, block, bytes, c->stream>>>(a, twq));
+    else FEN_LAUNCH(c, "dct_lines_inv", k_dct_lines<Lf, +1, 8><<<grid, block, bytes, c->stream>>>(a, twq));
+    FEN_CUDA(cudaGetLastError());
+    return FEN_OK;
+}
+static int dispatch_dct_lines(fen_ctx* c, int Lf, const LArgs& a, const double2* twq, bool fwd, int PC, int nouter) {
+    switch (Lf) {
+#define FEN_CASE(l) case l: return launch_dct_lines<l>(c, a, twq, fwd, PC / 8, nouter);
+        FEN_CASE(2) FEN_CASE(4) FEN_CASE(8) FEN_CASE(16) FEN_CASE(32) FEN_CASE(64) FEN_CASE(128) FEN_CASE(256)
+        FEN_CASE(512) FEN_CASE(1024)
+#undef FEN_CASE
+    }
+    return set_error(FEN_ERR_UNSUPPORTED, "DCT length %d not supported (power of two, 2..1024)", Lf);
+}
+
 static int log2i(int n) { int s = 0; while ((1 << s) < n) ++s; return s; }
 
 int poisson_init(fen_ctx* c) {
@@ -824,19 +990,21 @@ int poisson_init(fen_ctx* c) {
     if (!var)
         return set_error(FEN_ERR_UNSUPPORTED, "Unable to find the proper poisson solver with the selected "
                                               "boundary conditions");          // poisson.f90:91-95
-    if (var[0] == 'n')
-        return set_error(FEN_ERR_UNSUPPORTED, "Poisson variant %s (DCT in x) is a 'next' row (SURVEY.md 8f-2), "
-                                              "not built yet", var);
+    const bool dctx = var[0] == 'n', dcty = g.ndim == 3 && var[1] == 'n';
+    if (dctx && g.nranks > 1)
+        return set_error(FEN_ERR_UNSUPPORTED, "Poisson variant %s (DCT in x) runs on one rank only for now", var);
     if (!pow2(g.nx) || g.nx < 2 || g.nx > 2048 || !pow2(g.ny) || g.ny > 2048 ||
         (g.ndim == 3 && (!pow2(g.nz) || g.nz > 2048)))
         return set_error(FEN_ERR_UNSUPPORTED, "FFT sizes must be powers of two in 2..2048 (got %d %d %d)", g.nx,
                          g.ny, g.nz);
+    if ((dctx && g.nx > 1024) || (dcty && g.ny > 1024))
+        return set_error(FEN_ERR_UNSUPPORTED, "DCT directions are limited to 1024 points (got %d %d)", g.nx, g.ny);
     Poisson* p = new Poisson();
     c->ps = p;
     snprintf(p->variant, sizeof(p->variant), "%s", var);
     p->nx = g.nx; p->ny = g.ny; p->nz = g.nz; p->nzl = c->L.nzl;
     p->M = g.nx / 2;
-    p->PC = spectral_pitch(g.nx);
+    p->PC = dctx ? (g.nx + 7) / 8 * 8 : spectral_pitch(g.nx);
     p->nyl = g.ny;
     if (g.nranks > 1 && g.ndim == 3) {
         // the spectral arrays live in the comm arena so that the peers can store into them
@@ -854,13 +1022,25 @@ int poisson_init(fen_ctx* c) {
         p->Cz = p->C;
     }
     const double d = g.delta;
-    FEN_TRY(upload(&p->tw_x, twiddles(p->M, p->M, p->M)));
-    FEN_TRY(upload(&p->twr_x, twiddles(g.nx, p->M + 1, g.nx)));
-    FEN_TRY(upload(&p->mwn_x, mwn(g.nx, d, p->PC)));
-    const bool tri_y = !strcmp(var, "pn"), tri_z = !strcmp(var, "ppn");
+    if (dctx) {
+        FEN_TRY(upload(&p->tw_x, twiddles(g.nx, g.nx, g.nx)));
+        FEN_TRY(upload(&p->twq_x, half_phases(g.nx)));
+        FEN_TRY(upload(&p->mwn_x, mwn_neumann(g.nx, d, p->PC)));
+    } else {
+        FEN_TRY(upload(&p->tw_x, twiddles(p->M, p->M, p->M)));
+        FEN_TRY(upload(&p->twr_x, twiddles(g.nx, p->M + 1, g.nx)));
+        FEN_TRY(upload(&p->mwn_x, mwn(g.nx, d, p->PC)));
+    }
+    const bool tri_y = !strcmp(var, "pn") || !strcmp(var, "nn");
+    const bool tri_z = !strcmp(var, "ppn") || !strcmp(var, "npn") || !strcmp(var, "nnn");
     if (!tri_y) {
         FEN_TRY(upload(&p->tw_y, twiddles(g.ny, g.ny, g.ny)));
-        FEN_TRY(upload(&p->mwn_y, mwn(g.ny, d, 0)));
+        if (dcty) {
+            FEN_TRY(upload(&p->twq_y, half_phases(g.ny)));
+            FEN_TRY(upload(&p->mwn_y, mwn_neumann(g.ny, d, 0)));
+        } else {
+            FEN_TRY(upload(&p->mwn_y, mwn(g.ny, d, 0)));
+        }
     }
     if (!strcmp(var, "ppp")) {
         FEN_TRY(upload(&p->tw_z, twiddles(g.nz, g.nz, g.nz)));
@@ -924,6 +1104,45 @@ int poisson_solve(fen_ctx* c, double* f, bool fuse_rhs, double dt) {
     const bool ppp = !strcmp(p->variant, "ppp"), ppn = !strcmp(p->variant, "ppn");
     const bool pp = !strcmp(p->variant, "pp"), pn = !strcmp(p->variant, "pn");
     const bool multi = g.nranks > 1 && g.ndim == 3;
+    if (p->variant[0] == 'n') {
+        // Neumann in x: nn (poisson.f90:509-596), npn (:1177-1312), nnn (:1316-1451)
+        if (fuse_rhs) return set_error(FEN_ERR_STATE, "fused Poisson right-hand side needs a periodic x direction");
+        const bool nn = !strcmp(p->variant, "nn"), npn = !strcmp(p->variant, "npn");
+        DArgs da;
+        da.L = c->L; da.f = f; da.C = p->C; da.PC = p->PC; da.ny = g.ny; da.nrows = g.ny * p->nzl;
+        da.tw = p->tw_x; da.twq = p->twq_x;
+        da.scale = nn ? 1.0 : 1.0 / (double)(2 * g.nx);                  // :1213, :1352 (real(nx*2, dp))
+        FEN_TRY(dispatch_dct_x(c, g.nx, da, true));
+        TArgs t;
+        t.C = p->C; t.c1 = p->c1; t.npc = p->PC; t.a = p->ta; t.b = p->tb; t.c = p->tc; t.lx = p->mwn_x;
+        t.mean = 0;                                                      // npn / nnn compute the mean but do not
+        ScArgs none;                                                     // subtract it (:1310, :1449); nn has none
+        memset(&none, 0, sizeof(none));
+        LArgs la;
+        la.C = p->C; la.sl = p->PC; la.so = (long long)p->PC * g.ny; la.tw = p->tw_y; la.o0 = 0; la.cx0 = 0;
+        la.lx = nullptr; la.lo = nullptr; la.ll = nullptr; la.norm = 1.0;
+        if (nn) {
+            t.sl = p->PC; t.so = 0; t.n = g.ny; t.nouter = 1; t.o0 = 0; t.lo = nullptr; t.form2d = 1;
+        } else {
+            la.scale = npn ? 1.0 / (double)g.ny : 1.0 / (double)(2 * g.ny);    // :1226, :1365
+            if (npn) FEN_TRY(dispatch_lines(c, g.ny, la, 0, p->PC, p->nzl));   // full c2c of real data == r2c
+            else FEN_TRY(dispatch_dct_lines(c, g.ny, la, p->twq_y, true, p->PC, p->nzl));
+            t.sl = (long long)p->PC * g.ny; t.so = p->PC; t.n = g.nz; t.nouter = g.ny; t.o0 = 0;
+            t.lo = p->mwn_y; t.form2d = 0;
+        }
+        dim3 tgrid((p->PC + 127) / 128, t.nouter), tblock(128);
+        FEN_LAUNCH(c, "thomas_fwd", k_thomas_fwd<<<tgrid, tblock, 0, c->stream>>>(t));
+        FEN_LAUNCH(c, "thomas_bwd", k_thomas_bwd<false><<<tgrid, tblock, 0, c->stream>>>(t, none));
+        FEN_CUDA(cudaGetLastError());
+        if (!nn) {
+            la.scale = 1.0;
+            if (npn) FEN_TRY(dispatch_lines(c, g.ny, la, 1, p->PC, p->nzl));
+            else FEN_TRY(dispatch_dct_lines(c, g.ny, la, p->twq_y, false, p->PC, p->nzl));
+        }
+        da.scale = nn ? 1.0 / f32(2LL * g.nx) : 1.0;                     // :594 phi/float(nx*2)
+        FEN_TRY(dispatch_dct_x(c, g.nx, da, false));
+        return FEN_OK;
+    }
     XArgs xa;
     xa.L = c->L; xa.f = f; xa.C = p->C; xa.PC = p->PC; xa.ny = g.ny; xa.nrows = g.ny * p->nzl;
     xa.tw = p->tw_x; xa.twr = p->twr_x;
@@ -961,28 +1180,6 @@ int poisson_solve(fen_ctx* c, double* f, bool fuse_rhs, double dt) {
         }
         la.C = p->C; la.sl = p->PC; la.so = (long long)p->PC * g.ny; la.tw = p->tw_y;
         la.scale = ppn ? 1.0 / f32(g.ny) : 1.0;
-        // L2-resident chunking (one rank, ppp): the y-forward, z-solve and y-inverse passes of ONE group of kx
-        // columns touch the same ny*nz*NL*16 bytes (33.5 MB at 512^2 x 8), which fit the 126 MB L2; running the
-        // three passes chunk by chunk turns 3 reads + 3 writes of the spectral array through HBM into 1 + 1.
-        static const int chunk_groups = getenv("FEN_FFT_CHUNK") ? atoi(getenv("FEN_FFT_CHUNK")) : 0;
-        if (chunk_groups > 0 && ppp && !multi && g.ny >= 64 && g.nz >= 64) {
-            const int ngroups = p->PC / 8;
-            LArgs ly = la, lz = la;
-            lz.C = p->Cz; lz.sl = (long long)p->PC * p->nyl; lz.so = p->PC; lz.tw = p->tw_z; lz.scale = 1.0; lz.o0 = 0;
-            lz.lo = p->mwn_y; lz.ll = p->mwn_z; lz.norm = f32((long long)g.nx * g.ny * g.nz);
-            for (int g0 = 0; g0 < ngroups; g0 += chunk_groups) {
-                const int ng = std::min(chunk_groups, ngroups - g0);
-                ly.cx0 = lz.cx0 = g0;
-                ly.scale = la.scale;
-                FEN_TRY(dispatch_lines(c, g.ny, ly, 0, ng * 8, p->nzl));
-                FEN_TRY(dispatch_lines(c, g.nz, lz, 2, ng * 8, p->nyl));
-                ly.scale = 1.0;
-                FEN_TRY(dispatch_lines(c, g.ny, ly, 1, ng * 8, p->nzl));
-            }
-            xa.scale = 1.0;
-            FEN_TRY(dispatch_x(c, p->M, xa, false));
-            return FEN_OK;
-        }
         FEN_TRY(dispatch_lines(c, g.ny, la, 0, p->PC, p->nzl, multi ? &sf : nullptr));
         if (multi) FEN_TRY(comm_transpose_fwd(c));
         double2* Z = p->Cz;

@@ -14,8 +14,8 @@ echo "smoke exit $?" >> $OUT/smoke_$TAG.log
 tail -3 $OUT/smoke_$TAG.log
 timeout 900 python bench.py --steps 20 --warmup 3 > $OUT/bench_$TAG.json 2> $OUT/bench_$TAG.err
 echo "bench exit $?"; python scripts/show_bench.py $OUT/bench_$TAG.json
-FEN_FFT_NL4=1 timeout 900 python bench.py --steps 10 --warmup 3 --no-e2e --no-cpu-baseline > $OUT/bench_nl4_$TAG.json 2>> $OUT/bench_$TAG.err
-echo "bench NL4:"; python scripts/show_bench.py $OUT/bench_nl4_$TAG.json
+
+
 if [ -n "$QUICK" ]; then exit 0; fi
 timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > $OUT/bench_ref_$TAG.json 2>> $OUT/bench_$TAG.err
 # launch list (cold-cache, serialised: shares only)

@@ -30,7 +30,7 @@ def main():
 
     two_pi = 2.0 * fo.PI
     if case == "ppp":
-        n, L, bc, nu, g, U, cfl, init = (64, 32, 32), (two_pi, two_pi / 2, two_pi / 2), None, 0.01, None, 1.0, 0.25, fo.init_tgv3d
+        n, L, bc, nu, g, U, cfl, init = (128, 64, 64), (two_pi, two_pi / 2, two_pi / 2), None, 0.01, None, 1.0, 0.25, fo.init_tgv3d
     else:
         n, L, bc, nu, g, U, cfl, init = (32, 32, 16), (2.0, 2.0, 1.0), ["Periodic"] * 4 + ["Wall", "Wall"], 0.05, (1.0, 0.0, 0.0), 1.0, 0.05, fo.init_channel
     Go = fo.Grid(n[0], n[1], n[2], L[0], L[1], L[2], bc=bc)

@@ -86,10 +86,10 @@ def _poisson_program(n, L, bc, rhs):
 
 
 @pytest.mark.parametrize("P", [2, 4])
+@pytest.mark.parametrize("n,L", [((32, 16, 16), (2.0, 1.0, 1.0)),
+                                 ((128, 64, 64), (2.0, 1.0, 1.0))])     # second: register-path transforms + fused transposes
 @pytest.mark.parametrize("bc,variant", [(None, "ppp"), (ZWALLS, "ppn")])
-def test_poisson_matches_single_rank_and_oracle(P, bc, variant):
-    n = (32, 16, 16)
-    L = (2.0, 1.0, 1.0)
+def test_poisson_matches_single_rank_and_oracle(P, bc, variant, n, L):
     rng = np.random.default_rng(11)
     rhs = np.zeros((n[0] + 2, n[1] + 2, n[2] + 2), order="F")
     rhs[1:-1, 1:-1, 1:-1] = rng.standard_normal(n)
@@ -147,9 +147,9 @@ def _ns_program(n, L, bc, nu, init, U, g, cfl, steps, constant_cfl=False):
     return program, nso
 
 
-@pytest.mark.parametrize("P", [2, 4])
-def test_ns_steps_tgv3d_rank_count_invariant(P):
-    n = (32, 32, 32)
+@pytest.mark.parametrize("P,n", [(2, (32, 32, 32)), (4, (32, 32, 32)), (2, (128, 64, 64))])
+def test_ns_steps_tgv3d_rank_count_invariant(P, n):
+    # (128, 64, 64): register-path FFTs, rhs fused into the x pass, fused correction + checks across a rank boundary
     prog, nso = _ns_program(n, (2 * PI,) * 3, None, 0.01, fo.init_tgv3d, 1.0, None, 0.25, 5)
     one = run_ranks(1, prog)[0]
     many = run_ranks(P, prog)
