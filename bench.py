@@ -157,6 +157,39 @@ def init_tgv3d_slab(shape, delta, k0, pinned):
     return keep, (u, v, w, p)
 
 
+def init_channel_slab(shape, gshape, delta, k0, pinned):
+    """Channel initial condition of config 3 (oracle/fen_oracle.py: init_channel) on one z-slab: laminar
+    Poiseuille profile between the z walls plus a deterministic sinusoidal perturbation."""
+    import torch
+    nx, ny, nzl = shape
+    gnx, gny, gnz = gshape
+    amp = 0.05
+    Lz = gnz * delta
+    i = np.arange(1, nx + 1, dtype=np.float64)
+    j = np.arange(1, ny + 1, dtype=np.float64)
+    k = np.arange(1, nzl + 1, dtype=np.float64) + k0
+    zc = (k - 0.5) * delta
+    kx, ky, kz = 2.0 * PI / (gnx * delta), 2.0 * PI / (gny * delta), PI / Lz
+    prof = 4.0 * zc * (Lz - zc) / (Lz * Lz)
+    keep, out = [], []
+    for m in range(4):
+        t = torch.empty((nx + 2) * (ny + 2) * (nzl + 2), dtype=torch.float64, pin_memory=pinned)
+        a = t.numpy().reshape((nx + 2, ny + 2, nzl + 2), order="F")
+        a[...] = 0.0
+        keep.append(t)
+        out.append(a)
+    u, v, w, p = out
+    uxy = np.sin(kx * i * delta)[:, None] * np.cos(ky * (j - 0.5) * delta)[None, :]
+    vxy = np.cos(kx * (i - 0.5) * delta)[:, None] * np.sin(ky * j * delta)[None, :]
+    wxy = np.cos(kx * (i - 0.5) * delta)[:, None] * np.cos(ky * (j - 0.5) * delta)[None, :]
+    for kk in range(nzl):
+        u[1:-1, 1:-1, kk + 1] = prof[kk] + amp * uxy * np.sin(kz * zc[kk])
+        v[1:-1, 1:-1, kk + 1] = amp * vxy * np.sin(kz * zc[kk])
+        if int(k[kk]) != gnz:
+            w[1:-1, 1:-1, kk + 1] = amp * wxy * np.sin(2.0 * kz * (k[kk] * delta))
+    return keep, (u, v, w, p)
+
+
 def run_reference(args, rank, world):
     """--impl reference: the CPU restatement of the reference (oracle/), all host threads."""
     if rank != 0:
@@ -225,6 +258,8 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--case", default="tgv", choices=["tgv", "channel"],
+                    help="tgv: BASELINE configs[1] (headline, weak scaling); channel: configs[2], 2n x 2n x n walls in z")
     ap.add_argument("--mode", default="ns", choices=["ns", "poisson"],
                     help="ns: full navier_stokes_solver step (headline); poisson: solve_poisson only (config 4)")
     args = ap.parse_args()
@@ -251,19 +286,34 @@ def main():
         raise SystemExit("bench.py: --gpus %d but WORLD_SIZE %d (launch with torch.distributed.run)" % (args.gpus, world))
 
     n = args.size
-    nx, ny, nz = n, n, n * world          # weak scaling: 512^3 per GPU, slabs in z
-    L = 2 * PI
-    G = fb.grid().setup(nx, ny, nz, L, L, L * world, pcol=world, rank=rank, device=local_rank)
+    channel = args.case == "channel"
+    if channel:
+        # BASELINE configs[2]: turbulent-channel shape 1024 x 1024 x 512 (FEN orientation: walls in z, FFT in x/y,
+        # tridiagonal in z), the WHOLE grid split over the ranks (strong scaling); --size scales it down
+        nx, ny, nz = 2 * n, 2 * n, n
+        Lc = 2.0
+        G = fb.grid().setup(nx, ny, nz, Lc, Lc, Lc / 2, pcol=world, rank=rank, device=local_rank,
+                            bc=["Periodic"] * 4 + ["Wall", "Wall"])
+    else:
+        nx, ny, nz = n, n, n * world          # weak scaling: 512^3 per GPU, slabs in z
+        L = 2 * PI
+        G = fb.grid().setup(nx, ny, nz, L, L, L * world, pcol=world, rank=rank, device=local_rank)
     if world > 1:
         def all_gather(b):
             out = [None] * world
             dist.all_gather_object(out, b)
             return out
         G.connect(all_gather)
-    ns = fb.Solver(G, 1.0, 0.01).init_solver()
+    ns = fb.Solver(G, 1.0, 0.01 if not channel else 1.0e-3)
+    if channel:
+        ns.g = [1.0, 0.0, 0.0]
+    ns.init_solver()
     ns.CFL = 0.25
-    dt = ns.set_timestep(1.0)
-    keep, (u, v, w, p) = init_tgv3d_slab(G.nloc, G.delta, G.lo[2] - 1, pinned=True)
+    dt = ns.set_timestep(1.0 if not channel else 1.5)
+    if channel:
+        keep, (u, v, w, p) = init_channel_slab(G.nloc, (nx, ny, nz), G.delta, G.lo[2] - 1, pinned=True)
+    else:
+        keep, (u, v, w, p) = init_tgv3d_slab(G.nloc, G.delta, G.lo[2] - 1, pinned=True)
     ns.v.x.f, ns.v.y.f, ns.v.z.f, ns.p.f = u, v, w, p
     ns.v.push(); ns.p.push()
     ns.v.update_ghost_nodes(); ns.p.update_ghost_nodes()
@@ -298,12 +348,16 @@ def main():
         # BASELINE config 4: Poisson-only (ppp), 512^3 per GPU; rhs = the reference's analytic test rhs
         # (test/small_test/poisson/convergence_rate/convergence_rate.f90:174-176) already resident in phi
         phi = ns.phi                                    # navier_stokes_mod's phi
-        x = (np.arange(1, nx + 1) - 0.5) / nx
-        y = (np.arange(1, ny + 1) - 0.5) / ny
-        z = (np.arange(G.lo[2], G.hi[2] + 1) - 0.5) / nz
-        sxy = np.sin(2 * PI * x)[:, None] * np.cos(2 * PI * y)[None, :]
+        # rhs = lap(f) for f = sin(x) cos(y) sin(kz z) on the (2 pi, 2 pi, 2 pi world) box: the analytic test
+        # function of the reference's convergence test on this bench's grid
+        d = G.delta
+        x = (np.arange(1, nx + 1) - 0.5) * d
+        y = (np.arange(1, ny + 1) - 0.5) * d
+        z = (np.arange(G.lo[2], G.hi[2] + 1) - 0.5) * d
+        kz = 1.0 / world
+        sxy = np.sin(x)[:, None] * np.cos(y)[None, :]
         for kk in range(G.nloc[2]):
-            phi.f[1:-1, 1:-1, kk + 1] = -12.0 * PI * PI * sxy * np.sin(2 * PI * z[kk])
+            phi.f[1:-1, 1:-1, kk + 1] = -(2.0 + kz * kz) * sxy * np.sin(kz * z[kk])
         rhs_keep = phi.f.copy()
         phi.push()
         G.synchronize()
@@ -318,6 +372,7 @@ def main():
         with ClockSampler(local_rank) as cs:
             ms = timed(solve, args.steps)
         launches = ns.launch_count() - l0
+        barrier()
         ns.profile(True)
         for s in range(min(args.steps, 5)):
             solve(s)
@@ -334,7 +389,7 @@ def main():
         phi.push(); solve(0); phi.pull()
         sol = np.empty_like(phi.f[1:-1, 1:-1, 1:-1])
         for kk in range(G.nloc[2]):
-            sol[:, :, kk] = sxy * np.sin(2 * PI * z[kk])
+            sol[:, :, kk] = sxy * np.sin(kz * z[kk])
         err = float(np.abs(phi.f[1:-1, 1:-1, 1:-1] - sol).max())
         if rank == 0:
             print(json.dumps({
@@ -347,7 +402,7 @@ def main():
                 "roofline": {"bound": "hbm", "kernel": "poisson solve (5 passes)", "achieved": ach, "peak": peak,
                              "unit": "GB/s", "frac": ach / peak, "traffic": None, "peak_source": peak_src,
                              "alg_bytes_per_launch": 80.0 * ncell_loc},
-                "kernels": kernels, "check": {"max_error_vs_analytic": err, "second_order_bound": 40.0 / n ** 2}}))
+                "kernels": kernels, "check": {"max_error_vs_analytic": err, "second_order_bound": 4.0 * d * d}}))
         if world > 1:
             dist.barrier()
             dist.destroy_process_group()
@@ -371,6 +426,7 @@ def main():
     value = ncell * args.steps / (ms * 1e-3) / 1e6
 
     # ---- per-kernel timing with CUDA events on the launching stream (same steps, profiled) ----
+    barrier()
     ns.profile(True)
     for s in range(min(args.steps, 5)):
         dev_step(s)
@@ -451,10 +507,15 @@ def main():
         line = {
             "metric": "NS timestep Mcell-updates/s", "value": value, "unit": "Mcell-updates/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "3D periodic Taylor-Green vortex %d^3 per GPU fp64, ppp FFT Poisson "
-                                   "(BASELINE configs[1])" % n, "grid": [nx, ny, nz], "decomposition": "z-slabs x%d" % world,
-                       "nu": 0.01, "CFL": 0.25, "dt": dt, "l2": "working set (>= 12 GB) exceeds the 126 MB L2; no flush needed"},
+            "higher_is_better": True, "scaling": "strong" if channel else "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic",
+            "config": {"workload": ("channel %dx%dx%d fp64, walls in z, ppn Poisson: FFT x/y + Thomas z "
+                                    "(BASELINE configs[2])" % (nx, ny, nz)) if channel else
+                                   ("3D periodic Taylor-Green vortex %d^3 per GPU fp64, ppp FFT Poisson "
+                                    "(BASELINE configs[1])" % n), "grid": [nx, ny, nz],
+                       "decomposition": "z-slabs x%d" % world,
+                       "nu": 1.0e-3 if channel else 0.01, "CFL": 0.25, "dt": dt,
+                       "l2": "working set (>= 12 GB) exceeds the 126 MB L2; no flush needed"},
             "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
             "cpu_baseline": cpu, "kernels": kernels, "nvlink": nvlink,
             "poisson_solve_ms": poisson_ms,

@@ -1082,7 +1082,7 @@ int poisson_init(fen_ctx* c) {
 // the x pass can compute the right-hand side div(v*) rho/dt itself (uniform rho, 3-D, register-path lengths)
 bool poisson_can_fuse_rhs(fen_ctx* c) {
     static const bool off = getenv("FEN_NO_FUSED_RHS") != nullptr;     // tuning switch
-    return !off && c->ps && c->g.ndim == 3 && c->uniform_props;
+    return !off && c->ps && c->ps->variant[0] == 'p' && c->g.ndim == 3 && c->uniform_props;
 }
 
 int poisson_solve(fen_ctx* c, double* f, bool fuse_rhs, double dt) {
