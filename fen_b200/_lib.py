@@ -36,6 +36,8 @@ _D = C.c_double
 _PD = C.POINTER(C.c_double)
 _PI = C.POINTER(C.c_int)
 
+FORCING_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int, C.c_double)     # fen_forcing_fn
+
 # name -> (restype, argtypes); every symbol include/fen_gpu.h declares
 SIGNATURES = {
     "fen_gpu_last_error": (C.c_char_p, []),
@@ -81,6 +83,12 @@ SIGNATURES = {
     "fen_gpu_correct_velocity_field": (_I, [_P, _D]),
     "fen_gpu_update_pressure": (_I, [_P]),
     "fen_gpu_checks": (_I, [_P, _D]),
+    "fen_gpu_scalar_write": (_I, [_P, _I, C.c_char_p]),
+    "fen_gpu_scalar_read": (_I, [_P, _I, C.c_char_p]),
+    "fen_gpu_save_state": (_I, [_P, C.c_char_p]),
+    "fen_gpu_load_state": (_I, [_P, C.c_char_p]),
+    "fen_gpu_save_fields": (_I, [_P, _I, C.c_char_p]),
+    "fen_gpu_set_forcing_hook": (_I, [_P, FORCING_FN, _P]),
     "fen_gpu_profile_enable": (_I, [_P, _I]),
     "fen_gpu_profile_read": (_I, [_P, _I, _P, _PD, _PI, _PI]),
     "fen_gpu_launch_count": (C.c_longlong, [_P]),

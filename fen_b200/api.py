@@ -179,9 +179,13 @@ class scalar:
         return out.value
 
     def write(self, filename):
-        """scalar%write (scalar.f90:428): raw interior, x fastest (single rank)."""
-        self.pull()
-        np.ascontiguousarray(self.I.transpose(2, 1, 0)).tofile(filename)
+        """scalar%write (scalar.f90:428): the global interior array, x fastest, real(dp), no header; every rank
+        writes its own z-slab range of the file."""
+        check(self.G.lib.fen_gpu_scalar_write(self.G.ctx, self.id, str(filename).encode()))
+
+    def read(self, filename):
+        """scalar%read (scalar.f90:400) into the device field (interior; ghosts are not touched)."""
+        check(self.G.lib.fen_gpu_scalar_read(self.G.ctx, self.id, str(filename).encode()))
 
     def destroy(self):
         if self.id is not None and self._owned and self.G is not None and self.G.ctx is not None:
@@ -365,6 +369,40 @@ class Solver:
     def destroy_solver(self):
         check(self.G.lib.fen_gpu_destroy_solver(self.G.ctx))
         self._ready = False
+
+    # ---- solver_mod output / restart (solver.f90:103-329) -----------------------------------
+    def save_state(self, step, dirname="data"):
+        """save_state(step): ``<dirname>/state_<step7>.raw`` = p, v_x, v_y, dv_o_x, dv_o_y, [v_z, dv_o_z]."""
+        path = "%s/state_%07d.raw" % (dirname, int(step))
+        check(self.G.lib.fen_gpu_save_state(self.G.ctx, path.encode()))
+        return path
+
+    def load_state(self, step, dirname="data"):
+        path = "%s/state_%07d.raw" % (dirname, int(step))
+        check(self.G.lib.fen_gpu_load_state(self.G.ctx, path.encode()))
+        return path
+
+    def save_fields(self, step, dirname="data"):
+        """save_fields(step): cell-centred vx_, vy_, [vz_] and p_ raw files."""
+        check(self.G.lib.fen_gpu_save_fields(self.G.ctx, int(step), str(dirname).encode()))
+
+    def set_forcing_hook(self, fn):
+        """Host callback ``fn(step, dt)`` between the predictor and the Poisson solve -- where the reference calls
+        apply_ibm_forcing(v, dt) (navier_stokes.f90:106-108).  ``None`` removes it."""
+        if fn is None:
+            self._hook = None
+            check(self.G.lib.fen_gpu_set_forcing_hook(self.G.ctx, _lib.FORCING_FN(0), None))
+            return
+
+        def tramp(_user, step, dt):
+            try:
+                fn(step, dt)
+                return 0
+            except Exception as e:          # noqa: BLE001 -- reported through the C return code
+                print("forcing hook failed: %r" % (e,), file=sys.stderr)
+                return 1
+        self._hook = _lib.FORCING_FN(tramp)      # keep the trampoline alive
+        check(self.G.lib.fen_gpu_set_forcing_hook(self.G.ctx, self._hook, None))
 
     # ---- measurement -----------------------------------------------------------------------
     def profile(self, on=True):

@@ -100,23 +100,41 @@ static void init_field(fen_ctx* c, int id, int gl, int loc) {
     }
 }
 
-// copy between a Fortran-ordered host array with gl ghost layers and the padded device layout
+// contiguous (hx, hy, hz) box <-> the same box inside the padded device layout, starting at cell (1-gl, 1-gl, 1-gl)
+template <bool TO_PADDED>
+__global__ void __launch_bounds__(256) k_repitch(double* padded, double* flat, Layout L, int gl, int hx, int hy, int hz) {
+    const int j = blockIdx.y, k = blockIdx.z;
+    if (j >= hy || k >= hz) return;
+    double* prow = padded + L.idx(1 - gl, j + 1 - gl, k + 1 - gl);
+    double* frow = flat + ((size_t)k * hy + j) * hx;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < hx; i += gridDim.x * blockDim.x) {
+        if (TO_PADDED) prow[i] = frow[i];
+        else frow[i] = prow[i];
+    }
+}
+
+// copy between a Fortran-ordered host array with gl ghost layers and the padded device layout.  The transfer
+// itself is one FLAT DMA between the host array and a contiguous staging buffer (55 GB/s measured on this box,
+// against 33 GB/s for a pitched cudaMemcpy3D host-to-device, scripts/probes/copy_probe.py); a small kernel moves
+// the rows between the staging buffer and the padded layout (2 x 1 GB through HBM: 0.4 ms against a 20 ms copy).
 static int copy_field(fen_ctx* c, Field& f, double* host, int gl, bool to_device) {
     if (gl != 0 && gl != 1) return set_error(FEN_ERR_ARG, "host ghost level must be 0 or 1 (got %d)", gl);
     const Layout& L = c->L;
-    const size_t hx = (size_t)L.nx + 2 * gl, hy = (size_t)L.ny + 2 * gl, hz = (size_t)L.nzl + 2 * gl;
-    cudaMemcpy3DParms p;
-    memset(&p, 0, sizeof(p));
-    cudaPitchedPtr hp = make_cudaPitchedPtr(host, hx * sizeof(double), hx, hy);
-    cudaPitchedPtr dp = make_cudaPitchedPtr(f.d, (size_t)L.px * sizeof(double), (size_t)L.px, (size_t)L.ny + 2);
-    const cudaPos dpos = make_cudaPos((size_t)(L.xoff - gl) * sizeof(double), (size_t)(1 - gl), (size_t)(1 - gl));
-    if (to_device) {
-        p.srcPtr = hp; p.dstPtr = dp; p.dstPos = dpos; p.kind = cudaMemcpyHostToDevice;
-    } else {
-        p.srcPtr = dp; p.srcPos = dpos; p.dstPtr = hp; p.kind = cudaMemcpyDeviceToHost;
+    const int hx = L.nx + 2 * gl, hy = L.ny + 2 * gl, hz = L.nzl + 2 * gl;
+    const size_t n = (size_t)hx * hy * hz;
+    if (!c->stage) {
+        const size_t cap = (size_t)(L.nx + 2) * (L.ny + 2) * (L.nzl + 2);
+        FEN_CUDA(cudaMalloc(&c->stage, cap * sizeof(double)));
     }
-    p.extent = make_cudaExtent(hx * sizeof(double), hy, hz);
-    FEN_CUDA(cudaMemcpy3DAsync(&p, c->stream));
+    dim3 grid((hx + 255) / 256, hy, hz), block(256);
+    if (to_device) {
+        FEN_CUDA(cudaMemcpyAsync(c->stage, host, n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+        FEN_LAUNCH(c, "repitch", k_repitch<true><<<grid, block, 0, c->stream>>>(f.d, c->stage, L, gl, hx, hy, hz));
+    } else {
+        FEN_LAUNCH(c, "repitch", k_repitch<false><<<grid, block, 0, c->stream>>>(f.d, c->stage, L, gl, hx, hy, hz));
+        FEN_CUDA(cudaMemcpyAsync(host, c->stage, n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    }
+    FEN_CUDA(cudaGetLastError());
     return FEN_OK;
 }
 
@@ -224,6 +242,7 @@ int fen_gpu_destroy(fen_ctx* c) {
     for (auto& f : c->fields) free_field(f);
     for (int m = 0; m < 3; ++m) if (c->vnew[m]) cudaFree(c->vnew[m]);
     if (c->d_red) cudaFree(c->d_red);
+    if (c->stage) cudaFree(c->stage);
     if (c->h_red) cudaFreeHost(c->h_red);
     for (auto& e : c->prof_entries) { cudaEventDestroy(e.e0); cudaEventDestroy(e.e1); }
     cudaStreamDestroy(c->stream);
@@ -438,6 +457,10 @@ int fen_gpu_init_solver(fen_ctx* c) {
             FEN_CUDA(cudaMemsetAsync(c->vnew[m], 0, c->L.elems * sizeof(double), c->stream));
         }
     }
+    if (!c->stage) {     // push / pull staging buffer: allocated here so that transfers between steps never call cudaMalloc
+        const size_t cap = (size_t)(c->L.nx + 2) * (c->L.ny + 2) * (c->L.nzl + 2);
+        FEN_CUDA(cudaMalloc(&c->stage, cap * sizeof(double)));
+    }
     c->solver_init = true;
     return FEN_OK;
 }
@@ -510,12 +533,17 @@ int fen_gpu_checks(fen_ctx* c, double dt) {
 }
 
 int fen_gpu_navier_stokes_solver(fen_ctx* c, int step, double* dt) {
-    (void)step;
     if (!c || !dt) return set_error(FEN_ERR_ARG, "null argument");
     if (!c->solver_init) return set_error(FEN_ERR_STATE, "init_solver has not been called");
     if (!(c->prm.dt_o > 0.0)) return set_error(FEN_ERR_STATE, "dt_o is not set: call set_timestep first");
     if (c->prm.constant_CFL) FEN_TRY(update_timestep(c, dt));             // navier_stokes.f90:78
     FEN_TRY(ns_predict(c, *dt));                                          // :105
+    if (c->forcing) {                                                     // :106-108 apply_ibm_forcing(v, dt)
+        FEN_CUDA(cudaStreamSynchronize(c->stream));
+        const int hr = c->forcing(c->forcing_user, step, *dt);
+        if (hr != 0) return set_error(FEN_ERR_STATE, "the forcing hook returned %d", hr);
+        FEN_TRY(ghost_update(c, FEN_VX, c->g.ndim));
+    }
     Field* phi;
     FEN_TRY(field_check(c, FEN_PHI, &phi));
     if (poisson_can_fuse_rhs(c)) {

@@ -81,9 +81,13 @@ struct fen_ctx {
     double* vnew[3] = {nullptr, nullptr, nullptr};   // predictor output (ping-pong with v)
     double maxdiv = 0.0, maxCFL = 0.0;
     double last_dt = 0.0;
+    double* stage = nullptr;     // contiguous staging buffer of push / pull (context.cu: copy_field)
     double* d_red = nullptr;     // device scratch for reductions (partials + results)
     double* h_red = nullptr;     // pinned host mirror of the results
     int red_blocks = 0;
+
+    fen_forcing_fn forcing = nullptr;   // host hook after the predictor (io.cu)
+    void* forcing_user = nullptr;
 
     fen::Poisson* ps = nullptr;
     fen::Comm* comm = nullptr;

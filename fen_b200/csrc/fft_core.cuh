@@ -83,9 +83,18 @@ template <int L> struct FftPlan {
 };
 template <> struct FftPlan<0> { static constexpr int LOG2 = 0; };
 
+// Shared-memory position of element idx of line `line`.  Default: idx-major, s[idx * IS + line] (8 threads = 8
+// lines of one idx -> one 128-byte wavefront).  PR ("padded rows"): line-major with one pad slot every 8 elements,
+// s[line * IS + idx + idx / 8], for kernels whose warps own ONE line each (contiguous rows): the Stockham read
+// (consecutive idx) and write (idx = 8 j + r, or consecutive) patterns of 8 neighbouring threads then both fall
+// into 8 distinct 16-byte bank groups.
+template <bool PR> FEN_HD int spos(int idx, int IS, int line) {
+    return PR ? line * IS + idx + (idx >> 3) : idx * IS + line;
+}
+
 // One Stockham stage, split at the barrier: load phase then compute+store phase.
 // v must hold 8 complex values (T threads x 8 = L elements).  For L < 8 only R = L values are used.
-template <int L, int R, int DIR>
+template <int L, int R, int DIR, bool PR = false>
 FEN_HD void stage_load(double2* v, const double2* s, int IS, int line, int t) {
     constexpr int T = FftPlan<L>::T;
     constexpr int NB = (L / R) / T;     // butterflies per thread
@@ -93,11 +102,13 @@ FEN_HD void stage_load(double2* v, const double2* s, int IS, int line, int t) {
     for (int b = 0; b < NB; ++b) {
         int j = t + b * T;
 #pragma unroll
-        for (int r = 0; r < R; ++r) v[b * R + r] = s[(j + r * (L / R)) * IS + line];
+        for (int r = 0; r < R; ++r) v[b * R + r] = s[spos<PR>(j + r * (L / R), IS, line)];
     }
 }
-// twiddle + butterfly of one stage, in place on v[b * R + r]
-template <int L, int R, int DIR>
+// twiddle + butterfly of one stage, in place on v[b * R + r].
+// TWP (radix 8 only): load w, w^2, w^4 and form w^3, w^5, w^6, w^7 as products (3 table loads instead of 7;
+// the products are within ~2 ulp of the table values).
+template <int L, int R, int DIR, bool TWP = false>
 FEN_HD void stage_compute(double2* v, int t, int Ns, const double2* tw) {
     constexpr int T = FftPlan<L>::T;
     constexpr int NB = (L / R) / T;
@@ -110,14 +121,27 @@ FEN_HD void stage_compute(double2* v, int t, int Ns, const double2* tw) {
         for (int r = 0; r < R; ++r) w[r] = v[b * R + r];
         if (Ns > 1) {
             int step = k * (L / (Ns * R));          // twiddle index of r = 1 in the length-L table
-#pragma unroll
-            for (int r = 1; r < R; ++r) {
+            if constexpr (TWP && R == 8) {
 #ifdef __CUDA_ARCH__
-                double2 c = __ldg(&tw[step * r]);
+                const double2 c1 = twid<DIR>(__ldg(&tw[step])), c2 = twid<DIR>(__ldg(&tw[step * 2])),
+                              c4 = twid<DIR>(__ldg(&tw[step * 4]));
 #else
-                double2 c = tw[step * r];
+                const double2 c1 = twid<DIR>(tw[step]), c2 = twid<DIR>(tw[step * 2]), c4 = twid<DIR>(tw[step * 4]);
 #endif
-                w[r] = cmul(w[r], twid<DIR>(c));
+                const double2 c3 = cmul(c1, c2), c5 = cmul(c1, c4), c6 = cmul(c2, c4);
+                const double2 c7 = cmul(c3, c4);
+                w[1] = cmul(w[1], c1); w[2] = cmul(w[2], c2); w[3] = cmul(w[3], c3); w[4] = cmul(w[4], c4);
+                w[5] = cmul(w[5], c5); w[6] = cmul(w[6], c6); w[7] = cmul(w[7], c7);
+            } else {
+#pragma unroll
+                for (int r = 1; r < R; ++r) {
+#ifdef __CUDA_ARCH__
+                    double2 c = __ldg(&tw[step * r]);
+#else
+                    double2 c = tw[step * r];
+#endif
+                    w[r] = cmul(w[r], twid<DIR>(c));
+                }
             }
         }
         bfly<R, DIR>(w);
@@ -126,7 +150,7 @@ FEN_HD void stage_compute(double2* v, int t, int Ns, const double2* tw) {
     }
 }
 // autosort scatter of one stage's results
-template <int L, int R>
+template <int L, int R, bool PR = false>
 FEN_HD void stage_write(const double2* v, double2* s, int IS, int line, int t, int Ns) {
     constexpr int T = FftPlan<L>::T;
     constexpr int NB = (L / R) / T;
@@ -136,7 +160,7 @@ FEN_HD void stage_write(const double2* v, double2* s, int IS, int line, int t, i
         int k = j & (Ns - 1);
         int j0 = (j - k) * R + k;
 #pragma unroll
-        for (int r = 0; r < R; ++r) s[(j0 + r * Ns) * IS + line] = v[b * R + r];
+        for (int r = 0; r < R; ++r) s[spos<PR>(j0 + r * Ns, IS, line)] = v[b * R + r];
     }
 }
 template <int L, int R, int DIR>
@@ -193,7 +217,7 @@ __device__ __forceinline__ void fft_lines(double2* s, int IS, int line, int t, b
 // in registers, so a 512-point transform costs 4 shared-memory passes and 3 block barriers instead of 8 and 8.
 // On return no thread still reads shared memory written before the call's last barrier, so the caller may start
 // the next transform (e.g. the inverse of the fused solve) without another barrier.
-template <int L, int DIR, bool OUT_REG>
+template <int L, int DIR, bool OUT_REG, bool TWP = false, bool PR = false>
 __device__ __forceinline__ void fft_regs(double2 (&v)[8], double2* s, int IS, int line, int t, const double2* tw) {
     static_assert(L >= 64, "fft_regs needs T = L / 8 >= 8 threads per line");
     constexpr int N8 = FftPlan<L>::N8, REM = FftPlan<L>::REM;
@@ -202,23 +226,23 @@ __device__ __forceinline__ void fft_regs(double2 (&v)[8], double2* s, int IS, in
 #pragma unroll
     for (int st = 0; st < N8; ++st) {
         if (st > 0) {
-            stage_load<L, 8, DIR>(v, s, IS, line, t);
+            stage_load<L, 8, DIR, PR>(v, s, IS, line, t);
             __syncthreads();
         }
-        stage_compute<L, 8, DIR>(v, t, Ns, tw);
+        stage_compute<L, 8, DIR, TWP>(v, t, Ns, tw);
         if (OUT_REG && st == NST - 1) return;
-        stage_write<L, 8>(v, s, IS, line, t, Ns);
+        stage_write<L, 8, PR>(v, s, IS, line, t, Ns);
         __syncthreads();
         Ns *= 8;
     }
     if constexpr (REM > 1) {
-        stage_load<L, REM, DIR>(v, s, IS, line, t);
+        stage_load<L, REM, DIR, PR>(v, s, IS, line, t);
         __syncthreads();
         stage_compute<L, REM, DIR>(v, t, Ns, tw);
         if (OUT_REG) {
             last_permute<REM>(v);
         } else {
-            stage_write<L, REM>(v, s, IS, line, t, Ns);
+            stage_write<L, REM, PR>(v, s, IS, line, t, Ns);
             __syncthreads();
         }
     }

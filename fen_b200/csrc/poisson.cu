@@ -123,17 +123,15 @@ __global__ void __launch_bounds__(XR* FftPlan<M>::T) k_fft_x_r2c(XArgs a, DivArg
     }
     __syncthreads();
     fft_lines<M, -1>(s, XIS, tid % XR, tid / XR, true, a.tw);
-    // post-process pairs (k, M-k) and write X[0..M]
-    constexpr int NP = M / 2 + 1;
-    for (int e = tid; e < XR * NP; e += NT) {
-        const int row = e / NP, k = e - row * NP;
+    // post-process pairs (k, M-k) and write X[0..M]:  X[k] = (Zk + conj Zm)/2 + w_k (Zk - conj Zm)/(2i)
+    auto pair_out = [&](int row, int k) {
         const int r = row0 + row;
-        if (r >= a.nrows) continue;
+        if (r >= a.nrows) return;
         const int km = M - k;
         const double2 zk = s[(k % M) * XIS + row];
         const double2 zm = s[(km % M) * XIS + row];
         double2* dst = a.C + (size_t)a.PC * r;
-        {   // X[k] = (Zk + conj Zm)/2 + w_k (Zk - conj Zm)/(2i)
+        {
             const double2 E = make_double2(0.5 * (zk.x + zm.x), 0.5 * (zk.y - zm.y));
             const double2 O = make_double2(0.5 * (zk.y + zm.y), -0.5 * (zk.x - zm.x));
             const double2 w = __ldg(&a.twr[k]);
@@ -147,6 +145,17 @@ __global__ void __launch_bounds__(XR* FftPlan<M>::T) k_fft_x_r2c(XArgs a, DivArg
             const double2 X = cadd(E, cmul(w, O));
             dst[km] = make_double2(X.x * a.scale, X.y * a.scale);
         }
+    };
+    if constexpr (M >= 16) {
+        // NT == M threads: thread -> pair k = tid % (M/2) of rows (tid / (M/2)) + 2q; fully unrolled, no divisions;
+        // the self-paired middle element k = M/2 of row q is done by thread q
+        const int k = tid % (M / 2), rg = tid / (M / 2);
+#pragma unroll
+        for (int q = 0; q < XR / 2; ++q) pair_out(rg + 2 * q, k);
+        if (tid < XR) pair_out(tid, M / 2);
+    } else {
+        constexpr int NP = M / 2 + 1;
+        for (int e = tid; e < XR * NP; e += NT) pair_out(e / NP, e % NP);
     }
 }
 
@@ -367,6 +376,113 @@ __global__ void __launch_bounds__(XR* FftPlan<M>::T, (XR * FftPlan<M>::T <= 1024
     }
 }
 
+// ---- x passes with one warp per row ("padded rows", fft_core.cuh: spos<true>) --------------------------------
+// Thread (row, t) owns elements t + m*T of its row, so every global access of a warp is one contiguous 512-byte
+// run AND the transform runs on the register path; the line-major padded shared-memory layout keeps the Stockham
+// exchanges bank-conflict free (proved by tests/cpu/test_fft_core.cu).
+template <int M, bool DIV>
+__global__ void __launch_bounds__(XR* FftPlan<M>::T, (XR * FftPlan<M>::T <= 1024) ? 1024 / (XR * FftPlan<M>::T) : 1)
+k_fft_x_r2c_w(XArgs a, DivArgs dv) {
+    extern __shared__ double2 s[];
+    constexpr int T = FftPlan<M>::T;
+    constexpr int RS = M + M / 8 + 1;
+    const int tid = threadIdx.x;
+    const int row = tid / T, t = tid % T;
+    const int row0 = blockIdx.x * XR;
+    double2 v[8];
+    {
+        const int r = row0 + row;
+        const bool valid = r < a.nrows;
+        const int j = valid ? r % a.ny : 0, k = valid ? r / a.ny : 0;
+        const long long c0 = a.L.idx(1, j + 1, k + 1);
+#pragma unroll
+        for (int m = 0; m < 8; ++m) {
+            if (DIV) v[m] = div_pair(dv, a.L, c0 + 2 * (t + m * T));
+            else v[m] = reinterpret_cast<const double2*>(a.f + c0)[t + m * T];
+            if (!valid) v[m] = make_double2(0.0, 0.0);
+        }
+    }
+    fft_regs<M, -1, false, false, true>(v, s, RS, row, t, a.tw);
+    // pairs (k, M-k):  X[k] = (Zk + conj Zm)/2 + w_k (Zk - conj Zm)/(2i)
+    auto pair_out = [&](int rw, int k) {
+        const int r = row0 + rw;
+        if (r >= a.nrows) return;
+        const int km = M - k;
+        const double2 zk = s[spos<true>(k % M, RS, rw)];
+        const double2 zm = s[spos<true>(km % M, RS, rw)];
+        double2* dst = a.C + (size_t)a.PC * r;
+        {
+            const double2 E = make_double2(0.5 * (zk.x + zm.x), 0.5 * (zk.y - zm.y));
+            const double2 O = make_double2(0.5 * (zk.y + zm.y), -0.5 * (zk.x - zm.x));
+            const double2 X = cadd(E, cmul(__ldg(&a.twr[k]), O));
+            dst[k] = make_double2(X.x * a.scale, X.y * a.scale);
+        }
+        if (km != k) {
+            const double2 E = make_double2(0.5 * (zm.x + zk.x), 0.5 * (zm.y - zk.y));
+            const double2 O = make_double2(0.5 * (zm.y + zk.y), -0.5 * (zm.x - zk.x));
+            const double2 X = cadd(E, cmul(__ldg(&a.twr[km]), O));
+            dst[km] = make_double2(X.x * a.scale, X.y * a.scale);
+        }
+    };
+    const int k = tid % (M / 2), rg = tid / (M / 2);
+#pragma unroll
+    for (int q = 0; q < XR / 2; ++q) pair_out(rg + 2 * q, k);
+    if (tid < XR) pair_out(tid, M / 2);
+}
+
+template <int M>
+__global__ void __launch_bounds__(XR* FftPlan<M>::T, (XR * FftPlan<M>::T <= 1024) ? 1024 / (XR * FftPlan<M>::T) : 1)
+k_fft_x_c2r_w(XArgs a) {
+    extern __shared__ double2 s[];
+    constexpr int T = FftPlan<M>::T;
+    constexpr int RS = M + M / 8 + 1;
+    const int tid = threadIdx.x;
+    const int row0 = blockIdx.x * XR;
+    {
+        double2 x[XR];
+#pragma unroll
+        for (int rw = 0; rw < XR; ++rw) {
+            const int r = row0 + rw;
+            x[rw] = r < a.nrows ? a.C[(size_t)a.PC * r + tid] : make_double2(0.0, 0.0);
+        }
+        double2 xn = make_double2(0.0, 0.0);
+        if (tid < XR && row0 + tid < a.nrows) xn = a.C[(size_t)a.PC * (row0 + tid) + M];
+        if (tid == 0) {
+#pragma unroll
+            for (int rw = 0; rw < XR; ++rw) x[rw].y = 0.0;     // c2r ignores the imaginary part of DC / Nyquist
+        }
+#pragma unroll
+        for (int rw = 0; rw < XR; ++rw) s[spos<true>(tid, RS, rw)] = x[rw];
+        if (tid < XR) s[spos<true>(M, RS, tid)] = make_double2(xn.x, 0.0);
+    }
+    __syncthreads();
+    const int row = tid / T, t = tid % T;
+    double2 v[8];
+#pragma unroll
+    for (int m = 0; m < 8; ++m) {
+        // Z[k] = (Xk + conj Xm) + i conj(w_k) (Xk - conj Xm),  m = M - k, w_k = exp(-2 pi i k / N)
+        const int k = t + m * T;
+        const double2 xk = s[spos<true>(k, RS, row)], xm = s[spos<true>(M - k, RS, row)];
+        const double2 E = make_double2(xk.x + xm.x, xk.y - xm.y);
+        const double2 D = make_double2(xk.x - xm.x, xk.y + xm.y);
+        const double2 O = cmul(cconj(__ldg(&a.twr[k])), D);
+        v[m] = make_double2(E.x - O.y, E.y + O.x);
+    }
+    __syncthreads();                              // the first stage overwrites the staged rows
+    fft_regs<M, +1, true, false, true>(v, s, RS, row, t, a.tw);
+    const int r = row0 + row;
+    if (r >= a.nrows) return;
+    const int j = r % a.ny, k3 = r / a.ny;
+    double* frow = a.f + a.L.idx(1, j + 1, k3 + 1);
+#pragma unroll
+    for (int m = 0; m < 8; ++m) {
+        const int idx = t + m * T;
+        reinterpret_cast<double2*>(frow)[idx] = v[m];
+        if (idx == 0) frow[2 * M] = v[m].x;       // periodic x ghosts (scalar.f90:257,276)
+        if (idx == M - 1) frow[-1] = v[m].y;
+    }
+}
+
 // c2r with a coalesced staging load: rows of C -> shared memory, the pair pre-pass reads (k, M-k) from there
 // into registers, the transform runs register-to-register and the real row is stored straight from registers.
 template <int M>
@@ -377,15 +493,24 @@ k_fft_x_c2r_s(XArgs a) {
     constexpr int NT = XR * T;
     const int tid = threadIdx.x;
     const int row0 = blockIdx.x * XR;
-    for (int e = tid; e < XR * (M + 1); e += NT) {
-        const int rw = e / (M + 1), k = e - rw * (M + 1);
-        const int r = row0 + rw;
-        double2 x = make_double2(0.0, 0.0);
-        if (r < a.nrows) {
-            x = a.C[(size_t)a.PC * r + k];
-            if (k == 0 || k == M) x.y = 0.0;     // c2r ignores the imaginary part of DC / Nyquist
+    {
+        // NT == M threads: thread k loads X[k] of the 8 rows (8 independent coalesced loads in flight), thread q < 8
+        // also the Nyquist element X[M] of row q
+        double2 x[XR];
+#pragma unroll
+        for (int rw = 0; rw < XR; ++rw) {
+            const int r = row0 + rw;
+            x[rw] = r < a.nrows ? a.C[(size_t)a.PC * r + tid] : make_double2(0.0, 0.0);
         }
-        s[k * XIS + rw] = x;
+        double2 xn = make_double2(0.0, 0.0);
+        if (tid < XR && row0 + tid < a.nrows) xn = a.C[(size_t)a.PC * (row0 + tid) + M];
+        if (tid == 0) {
+#pragma unroll
+            for (int rw = 0; rw < XR; ++rw) x[rw].y = 0.0;     // c2r ignores the imaginary part of DC / Nyquist
+        }
+#pragma unroll
+        for (int rw = 0; rw < XR; ++rw) s[tid * XIS + rw] = x[rw];
+        if (tid < XR) s[M * XIS + tid] = make_double2(xn.x, 0.0);
     }
     __syncthreads();
     const int row = tid % XR, t = tid / XR;
@@ -436,7 +561,7 @@ __global__ void __launch_bounds__(NL* FftPlan<Lf>::T, (NL * FftPlan<Lf>::T <= 10
     }
 }
 
-template <int Lf, int NL, bool SC>
+template <int Lf, int NL, bool SC, bool TWP = false>
 __global__ void __launch_bounds__(NL* FftPlan<Lf>::T, (NL * FftPlan<Lf>::T <= 1024) ? 1024 / (NL * FftPlan<Lf>::T) : 1) k_fft_solve_r(LArgs a, ScArgs q) {
     extern __shared__ double2 s[];
     constexpr int T = FftPlan<Lf>::T;
@@ -448,7 +573,7 @@ __global__ void __launch_bounds__(NL* FftPlan<Lf>::T, (NL * FftPlan<Lf>::T <= 10
 #pragma unroll
         for (int m = 0; m < 8; ++m) v[m] = base[a.sl * (t + m * T)];
     }
-    fft_regs<Lf, -1, true>(v, s, NL, line, t, a.tw);
+    fft_regs<Lf, -1, true, TWP>(v, s, NL, line, t, a.tw);
     // poisson.f90:992 then :998-1001.  norm = float(nx*ny*nz) is a power of two here (power-of-two transform
     // lengths), so x/norm == x*(1/norm) exactly; the division by lambda is one rounded reciprocal and a
     // multiply (<= 1 ulp from x/lambda, far inside the 1e-12 parity bound) instead of four fp64 divisions.
@@ -465,7 +590,7 @@ __global__ void __launch_bounds__(NL* FftPlan<Lf>::T, (NL * FftPlan<Lf>::T <= 10
             v[m].y *= rl;
         }
     }
-    fft_regs<Lf, +1, true>(v, s, NL, line, t, a.tw);
+    fft_regs<Lf, +1, true, TWP>(v, s, NL, line, t, a.tw);
     const int kx = (blockIdx.x + a.cx0) * NL + line;
     double2* base = a.C + kx + a.so * blockIdx.y;
 #pragma unroll
@@ -797,6 +922,9 @@ template <int M> static int set_smem_x() {
             FEN_CUDA(cudaFuncSetAttribute(k_fft_x_r2c_r<M, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
             FEN_CUDA(cudaFuncSetAttribute(k_fft_x_c2r_r<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
             FEN_CUDA(cudaFuncSetAttribute(k_fft_x_c2r_s<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+            FEN_CUDA(cudaFuncSetAttribute(k_fft_x_r2c_w<M, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+            FEN_CUDA(cudaFuncSetAttribute(k_fft_x_r2c_w<M, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+            FEN_CUDA(cudaFuncSetAttribute(k_fft_x_c2r_w<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
         }
     }
     return FEN_OK;
@@ -805,6 +933,7 @@ template <int M> static int set_smem_x() {
 // tuning switches; defaults = the fastest measured at 512^3 (profiles/r01f_variants.txt):
 //   FEN_X_R2C: 0 register path   1 staged (coalesced load / rhs compute into shared memory)   [1: 0.91 vs 1.69 ms]
 //   FEN_X_C2R: 0 register path   1 fully staged   2 staged load + register output            [2: 0.72 vs 0.95 ms]
+//   3 (both): one warp per row, padded-row shared-memory layout -- coalesced AND register path  [c2r 0.58 ms; r2c 0.89]
 // Rows are contiguous, so a cooperative coalesced load (one 512-byte run per warp) beats the register path's
 // 64-byte-per-row gathers; the strided y/z passes are the other way round (86 % of HBM with the register path).
 static int x_variant(const char* name, int dflt) {
@@ -817,7 +946,7 @@ template <int M> static int launch_x(fen_ctx* c, const XArgs& a, bool fwd, const
     const int bytes = (M + 1) * XIS * (int)sizeof(double2);
     static bool attr_done = false;
     if (!attr_done) { FEN_TRY(set_smem_x<M>()); attr_done = true; }
-    static const int vr2c = x_variant("FEN_X_R2C", 1), vc2r = x_variant("FEN_X_C2R", 2);
+    static const int vr2c = x_variant("FEN_X_R2C", 1), vc2r = x_variant("FEN_X_C2R", 3);
     dim3 grid((a.nrows + XR - 1) / XR), block(XR * T);
     DivArgs none{};
     bool done = false;
@@ -829,6 +958,12 @@ template <int M> static int launch_x(fen_ctx* c, const XArgs& a, bool fwd, const
         }
         if (!fwd && vc2r == 0) { FEN_LAUNCH(c, "fft_x_c2r", k_fft_x_c2r_r<M><<<grid, block, bytes, c->stream>>>(a)); done = true; }
         if (!fwd && vc2r == 2) { FEN_LAUNCH(c, "fft_x_c2r", k_fft_x_c2r_s<M><<<grid, block, bytes, c->stream>>>(a)); done = true; }
+        if (!fwd && vc2r == 3) { FEN_LAUNCH(c, "fft_x_c2r", k_fft_x_c2r_w<M><<<grid, block, bytes, c->stream>>>(a)); done = true; }
+        if (fwd && vr2c == 3) {
+            if (dv) FEN_LAUNCH(c, "fft_x_r2c_div", k_fft_x_r2c_w<M, true><<<grid, block, bytes, c->stream>>>(a, *dv));
+            else FEN_LAUNCH(c, "fft_x_r2c", k_fft_x_r2c_w<M, false><<<grid, block, bytes, c->stream>>>(a, none));
+            done = true;
+        }
     }
     if (!done) {
         if (fwd && dv) FEN_LAUNCH(c, "fft_x_r2c_div", k_fft_x_r2c<M, true><<<grid, block, bytes, c->stream>>>(a, *dv));

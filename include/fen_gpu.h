@@ -171,6 +171,23 @@ int fen_gpu_correct_velocity_field(fen_ctx* ctx, double dt);           /* navier
 int fen_gpu_update_pressure(fen_ctx* ctx);                             /* navier_stokes.f90:550 */
 int fen_gpu_checks(fen_ctx* ctx, double dt);                           /* navier_stokes.f90:570 */
 
+/* ---- raw field files in the reference's on-disk format (global interior array, x fastest, real(dp), no header;
+ * 2decomp MPI-IO).  Collective over the ranks; every rank reads / writes its own z-slab byte range. ------------- */
+int fen_gpu_scalar_write(fen_ctx* ctx, int field, const char* filename);   /* scalar%write, scalar.f90:428 */
+int fen_gpu_scalar_read(fen_ctx* ctx, int field, const char* filename);    /* scalar%read,  scalar.f90:400 */
+/* save_state / load_state (solver.f90:160, :244): p, v_x, v_y, dv_o_x, dv_o_y, [v_z, dv_o_z] in one file; load also
+ * updates the ghost nodes of p and v.  dt and dt_o are not stored (the driver re-derives them, test_NS.f90:54-63). */
+int fen_gpu_save_state(fen_ctx* ctx, const char* filename);
+int fen_gpu_load_state(fen_ctx* ctx, const char* filename);
+/* save_fields(step) (solver.f90:103): <dir>/vx_<step>.raw, vy_, [vz_] (cell-centred, fields.f90:210) and p_ */
+int fen_gpu_save_fields(fen_ctx* ctx, int step, const char* dir);
+
+/* ---- host hook between the predictor and the Poisson right-hand side: the place of apply_ibm_forcing(v, dt)
+ * (navier_stokes.f90:106-108).  The callback may pull v, force it on the host and push it back; the library then
+ * refreshes the ghost nodes of v.  A non-zero return aborts the step.  NULL removes the hook. ------------------- */
+typedef int (*fen_forcing_fn)(void* user, int step, double dt);
+int fen_gpu_set_forcing_hook(fen_ctx* ctx, fen_forcing_fn fn, void* user);
+
 /* ---- measurement helpers (no reference analogue: FEN has no timers) --- */
 /* per-kernel-family CUDA-event timing of the next steps; names/ms arrays sized by the caller */
 int fen_gpu_profile_enable(fen_ctx* ctx, int on);

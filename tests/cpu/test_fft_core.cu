@@ -60,12 +60,12 @@ template <int L> static int both() {
 
 // register-to-register flow of fft_regs<L, DIR, true> (L >= 64): inputs and outputs live in the threads'
 // registers, v[m] <-> element t + m * L / 8; barriers are the boundaries between the thread loops
-template <int L, int DIR> static double check_regs(int IS, int NL) {
+template <int L, int DIR, bool PR = false> static double check_regs(int IS, int NL) {
     constexpr int T = FftPlan<L>::T, N8 = FftPlan<L>::N8, REM = FftPlan<L>::REM;
     constexpr int NST = N8 + (REM > 1 ? 1 : 0);
     std::vector<double2> tw(L);
     for (int m = 0; m < L; ++m) tw[m] = make_double2(cos(-2.0 * M_PI * m / L), sin(-2.0 * M_PI * m / L));
-    std::vector<double2> s((size_t)L * IS, make_double2(0, 0)), in((size_t)L * NL);
+    std::vector<double2> s(PR ? (size_t)NL * IS : (size_t)L * IS, make_double2(0, 0)), in((size_t)L * NL);
     std::vector<double2> regs((size_t)NL * T * 8);
     unsigned seed = 777u + L;
     for (int line = 0; line < NL; ++line)
@@ -83,18 +83,18 @@ template <int L, int DIR> static double check_regs(int IS, int NL) {
     for (int st = 0; st < N8 && !done; ++st) {
         if (st > 0)
             for (int line = 0; line < NL; ++line)
-                for (int t = 0; t < T; ++t) stage_load<L, 8, DIR>(R(line, t), s.data(), IS, line, t);
+                for (int t = 0; t < T; ++t) stage_load<L, 8, DIR, PR>(R(line, t), s.data(), IS, line, t);
         for (int line = 0; line < NL; ++line)
             for (int t = 0; t < T; ++t) {
                 stage_compute<L, 8, DIR>(R(line, t), t, Ns, tw.data());
-                if (st != NST - 1) stage_write<L, 8>(R(line, t), s.data(), IS, line, t, Ns);
+                if (st != NST - 1) stage_write<L, 8, PR>(R(line, t), s.data(), IS, line, t, Ns);
             }
         if (st == NST - 1) done = true;
         Ns *= 8;
     }
     if constexpr (REM > 1) {
         for (int line = 0; line < NL; ++line)
-            for (int t = 0; t < T; ++t) stage_load<L, REM, DIR>(R(line, t), s.data(), IS, line, t);
+            for (int t = 0; t < T; ++t) stage_load<L, REM, DIR, PR>(R(line, t), s.data(), IS, line, t);
         for (int line = 0; line < NL; ++line)
             for (int t = 0; t < T; ++t) {
                 stage_compute<L, REM, DIR>(R(line, t), t, Ns, tw.data());
@@ -118,10 +118,39 @@ template <int L, int DIR> static double check_regs(int IS, int NL) {
     return emax;
 }
 
+// padded-row layout: 8 neighbouring threads of one line (an aligned group = one 128-byte shared-memory wavefront of
+// 16-byte accesses) must hit 8 distinct 16-byte bank groups (position mod 8) in every stage read and write
+template <int L, int R> static int conflicts_stage(int Ns, int IS) {
+    constexpr int T = FftPlan<L>::T, NB = (L / R) / T;
+    int bad = 0;
+    for (int b = 0; b < NB; ++b)
+        for (int r = 0; r < R; ++r)
+            for (int t0 = 0; t0 < T; t0 += 8) {
+                int seen_r = 0, seen_w = 0;
+                for (int q = 0; q < 8; ++q) {
+                    const int j = t0 + q + b * T, k = j & (Ns - 1), j0 = (j - k) * R + k;
+                    seen_r |= 1 << (spos<true>(j + r * (L / R), IS, 0) & 7);
+                    seen_w |= 1 << (spos<true>(j0 + r * Ns, IS, 0) & 7);
+                }
+                bad += (seen_r != 0xff) + (seen_w != 0xff);
+            }
+    return bad;
+}
+template <int L> static int conflicts() {
+    constexpr int N8 = FftPlan<L>::N8, REM = FftPlan<L>::REM;
+    const int IS = L + L / 8 + 1;
+    int bad = 0, Ns = 1;
+    for (int st = 0; st < N8; ++st) { bad += conflicts_stage<L, 8>(Ns, IS); Ns *= 8; }
+    if constexpr (REM > 1) bad += conflicts_stage<L, REM>(Ns, IS);
+    return bad;
+}
+
 template <int L> static int both_regs() {
     double ef = check_regs<L, -1>(8, 8), eb = check_regs<L, +1>(9, 4);
-    printf("L=%d regs fwd=%.3e inv=%.3e\n", L, ef, eb);
-    return (ef < 1e-11 && eb < 1e-11) ? 0 : 1;
+    double pf = check_regs<L, -1, true>(L + L / 8 + 1, 8), pb = check_regs<L, +1, true>(L + L / 8 + 1, 3);
+    const int bc = conflicts<L>();
+    printf("L=%d regs fwd=%.3e inv=%.3e  padded rows fwd=%.3e inv=%.3e bank-conflicting groups=%d\n", L, ef, eb, pf, pb, bc);
+    return (ef < 1e-11 && eb < 1e-11 && pf < 1e-11 && pb < 1e-11 && bc == 0) ? 0 : 1;
 }
 
 int main() {
