@@ -295,9 +295,16 @@ def main():
         G = fb.grid().setup(nx, ny, nz, Lc, Lc, Lc / 2, pcol=world, rank=rank, device=local_rank,
                             bc=["Periodic"] * 4 + ["Wall", "Wall"])
     else:
-        nx, ny, nz = n, n, n * world          # weak scaling: 512^3 per GPU, slabs in z
+        # weak scaling, 512^3 cells per GPU, the shapes of BASELINE configs[3] / SURVEY.md 8(d) config 4:
+        # 512^3 (1), 1024x512x512 (2), 1024x1024x512 (4), 1024^3 (8) -- x, then y, then z doubles; z-slabs
+        dims = [n, n, n]
+        for q in range(max(world, 1).bit_length() - 1):
+            dims[q % 3] *= 2
+        if dims[0] * dims[1] * dims[2] != n ** 3 * world:
+            raise SystemExit("bench.py: --gpus must be a power of two (got %d)" % world)
+        nx, ny, nz = dims
         L = 2 * PI
-        G = fb.grid().setup(nx, ny, nz, L, L, L * world, pcol=world, rank=rank, device=local_rank)
+        G = fb.grid().setup(nx, ny, nz, L * nx / n, L * ny / n, L * nz / n, pcol=world, rank=rank, device=local_rank)
     if world > 1:
         def all_gather(b):
             out = [None] * world
@@ -348,16 +355,16 @@ def main():
         # BASELINE config 4: Poisson-only (ppp), 512^3 per GPU; rhs = the reference's analytic test rhs
         # (test/small_test/poisson/convergence_rate/convergence_rate.f90:174-176) already resident in phi
         phi = ns.phi                                    # navier_stokes_mod's phi
-        # rhs = lap(f) for f = sin(x) cos(y) sin(kz z) on the (2 pi, 2 pi, 2 pi world) box: the analytic test
-        # function of the reference's convergence test on this bench's grid
+        # rhs = lap(f) for f = sin(kx x) cos(ky y) sin(kz z), one wave per box side: the analytic test function of
+        # the reference's convergence test on this bench's grid
         d = G.delta
         x = (np.arange(1, nx + 1) - 0.5) * d
         y = (np.arange(1, ny + 1) - 0.5) * d
         z = (np.arange(G.lo[2], G.hi[2] + 1) - 0.5) * d
-        kz = 1.0 / world
-        sxy = np.sin(x)[:, None] * np.cos(y)[None, :]
+        kxw, kyw, kz = float(n) / nx, float(n) / ny, float(n) / nz      # one wave per box side
+        sxy = np.sin(kxw * x)[:, None] * np.cos(kyw * y)[None, :]
         for kk in range(G.nloc[2]):
-            phi.f[1:-1, 1:-1, kk + 1] = -(2.0 + kz * kz) * sxy * np.sin(kz * z[kk])
+            phi.f[1:-1, 1:-1, kk + 1] = -(kxw * kxw + kyw * kyw + kz * kz) * sxy * np.sin(kz * z[kk])
         rhs_keep = phi.f.copy()
         phi.push()
         G.synchronize()
