@@ -260,6 +260,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--case", default="tgv", choices=["tgv", "channel"],
                     help="tgv: BASELINE configs[1] (headline, weak scaling); channel: configs[2], 2n x 2n x n walls in z")
+    ap.add_argument("--grid", default="", help="explicit global grid nx,ny,nz for --case tgv (tuning aid)")
     ap.add_argument("--mode", default="ns", choices=["ns", "poisson"],
                     help="ns: full navier_stokes_solver step (headline); poisson: solve_poisson only (config 4)")
     args = ap.parse_args()
@@ -303,6 +304,8 @@ def main():
         if dims[0] * dims[1] * dims[2] != n ** 3 * world:
             raise SystemExit("bench.py: --gpus must be a power of two (got %d)" % world)
         nx, ny, nz = dims
+        if args.grid:        # tuning aid: an explicit global grid (e.g. the 1024x1024x128 slab one GPU owns at N = 8)
+            nx, ny, nz = [int(v) for v in args.grid.split(",")]
         L = 2 * PI
         G = fb.grid().setup(nx, ny, nz, L * nx / n, L * ny / n, L * nz / n, pcol=world, rank=rank, device=local_rank)
     if world > 1:

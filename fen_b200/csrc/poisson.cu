@@ -946,7 +946,8 @@ template <int M> static int launch_x(fen_ctx* c, const XArgs& a, bool fwd, const
     const int bytes = (M + 1) * XIS * (int)sizeof(double2);
     static bool attr_done = false;
     if (!attr_done) { FEN_TRY(set_smem_x<M>()); attr_done = true; }
-    static const int vr2c = x_variant("FEN_X_R2C", 1), vc2r = x_variant("FEN_X_C2R", 3);
+    // c2r: the warp-per-row kernel wins at M = 256 (0.58 vs 0.61 ms), the staged one at M >= 512 (0.66 vs 0.71 ms)
+    static const int vr2c = x_variant("FEN_X_R2C", 1), vc2r = x_variant("FEN_X_C2R", M >= 512 ? 2 : 3);
     dim3 grid((a.nrows + XR - 1) / XR), block(XR * T);
     DivArgs none{};
     bool done = false;
@@ -1031,7 +1032,12 @@ template <int Lf, int NL> static int launch_lines(fen_ctx* c, const LArgs& a, in
 static int dispatch_lines(fen_ctx* c, int Lf, const LArgs& a, int mode, int PC, int nouter, const ScArgs* sc = nullptr) {
     // tuning switch: 4 lines (64 B) per block instead of 8 -- more, smaller blocks per SM
     static const bool nl4 = getenv("FEN_FFT_NL4") != nullptr;
-    if (nl4 && (Lf == 512 || Lf == 1024)) {
+    static const bool nl4_1024 = getenv("FEN_FFT_NL4_1024") != nullptr;
+    // 1024-point lines: 8 columns per block need 1024 threads and the whole register file (one block per SM);
+    // 4 columns give two 512-thread blocks per SM -- measured 0.59 vs 0.62 ms on a 1024x1024x128 slab
+    static const bool nl8_1024 = getenv("FEN_FFT_NL8_1024") != nullptr;
+    (void)nl4_1024;
+    if ((nl4 && Lf == 512) || (Lf == 1024 && !nl8_1024)) {
         LArgs b = a;
         b.cx0 = a.cx0 * 2;       // cx0 counts blocks of NL columns
         if (Lf == 512) return launch_lines<512, 4>(c, b, mode, PC / 4, nouter, sc);

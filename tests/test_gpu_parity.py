@@ -454,3 +454,62 @@ def test_status_line_and_errors():
     line = ns.print_solver_status(1, dt, dt)
     assert line.startswith("step:       1 time: ") and "maxdiv:" in line and "maxCFL:" in line
     Gg.destroy()
+
+
+# ---- BASELINE full size: size-independent properties -------------------------------------------
+def test_full_size_512_properties():
+    """BASELINE configs[1] at its full size (512^3, ppp): checked through properties that need no oracle run --
+    the discrete Laplacian of the Poisson solution gives the right-hand side back, the solve is linear, a
+    Navier-Stokes step leaves a divergence-free field and conserves momentum in the periodic box."""
+    n = 512
+    Gg = fb.grid().setup(n, n, n, 2 * PI, 2 * PI, 2 * PI)
+    d = Gg.delta
+    ns = fb.Solver(Gg, 1.0, 0.01).init_solver()
+    phi = ns.phi
+    rng = np.random.default_rng(2026)
+    rhs = rng.standard_normal((n, n, n))
+    rhs -= rhs.mean()
+    phi.I[...] = rhs
+    phi.push()
+    ps = fb.PoissonSolver(phi)
+    assert ps.variant == "ppp"
+    ps.solve(phi)
+    phi.pull()
+    sol = phi.I.copy()
+    lap = -6.0 * sol
+    for ax in range(3):
+        lap += np.roll(sol, 1, axis=ax) + np.roll(sol, -1, axis=ax)
+    lap /= d * d
+    assert np.linalg.norm(lap - rhs) <= 1e-10 * np.linalg.norm(rhs)
+    # linearity: solve(-2.5 rhs) == -2.5 solve(rhs)
+    phi.I[...] = -2.5 * rhs
+    phi.push(); ps.solve(phi); phi.pull()
+    assert np.linalg.norm(phi.I + 2.5 * sol) <= 1e-13 * np.linalg.norm(2.5 * sol)
+    del lap, sol, rhs
+    # three steps of the Taylor-Green case
+    i = np.arange(1, n + 1, dtype=np.float64)
+    sx, cxh = np.sin(i * d), np.cos((i - 0.5) * d)
+    for kk in range(n):
+        cz = np.cos((kk + 0.5) * d)
+        ns.v.x.I[:, :, kk] = (sx[:, None] * cxh[None, :]) * cz
+        ns.v.y.I[:, :, kk] = (-cxh[:, None] * sx[None, :]) * cz
+    ns.v.z.I[...] = 0.0
+    ns.p.I[...] = 0.0
+    ns.v.push(); ns.p.push()
+    ns.v.update_ghost_nodes(); ns.p.update_ghost_nodes()
+    ns.CFL = 0.25
+    dt = ns.set_timestep(1.0)
+    mom0 = [float(c.I.sum()) for c in ns.v.comps]
+    ke0 = sum(float((c.I ** 2).sum()) for c in ns.v.comps)
+    for s in range(1, 4):
+        ns.navier_stokes_solver(s, dt)
+    md, mc = ns.status()
+    assert abs(md) < 1e-12 and 0.0 < mc < 0.3
+    assert _unfused_checks(ns, dt) == (md, mc)
+    ns.v.pull()
+    scale = float(np.abs(ns.v.x.I).sum())
+    for c, m0 in zip(ns.v.comps, mom0):
+        assert abs(float(c.I.sum()) - m0) <= 1e-9 * scale           # momentum is conserved in the periodic box
+    ke1 = sum(float((c.I ** 2).sum()) for c in ns.v.comps)
+    assert 0.99 * ke0 < ke1 < ke0                                   # viscous decay, no blow-up
+    Gg.destroy()
