@@ -190,36 +190,75 @@ def init_channel_slab(shape, gshape, delta, k0, pinned):
     return keep, (u, v, w, p)
 
 
-def run_reference(args, rank, world):
-    """--impl reference: the CPU restatement of the reference (oracle/), all host threads."""
-    if rank != 0:
-        return
-    from oracle import fen_oracle as fo
-    n = args.cpu_size
+def _tgv_ic(n, delta):
+    """ghosted Fortran-ordered u, v, p of the 3-D Taylor-Green case (w = 0), periodic ghosts filled analytically"""
+    i = np.arange(0, n + 2, dtype=np.float64)
+    s_f, c_c = np.sin(i * delta), np.cos((i - 0.5) * delta)
+    c2 = np.cos(2.0 * (i - 0.5) * delta)
+    u = np.asfortranarray(s_f[:, None, None] * c_c[None, :, None] * c_c[None, None, :])
+    v = np.asfortranarray(-(c_c[:, None, None] * s_f[None, :, None] * c_c[None, None, :]))
+    p = np.asfortranarray((1.0 / 16.0) * (c2[:, None, None] + c2[None, :, None]) * (c2[None, None, :] + 2.0))
+    return u, v, p
+
+
+def cpu_port(n, steps, warmup, threads=0):
+    """Times the CPU restatement of the reference on an n^3 sample of the Taylor-Green workload with all host
+    threads.  Preferred: the plain-C/OpenMP restatement (oracle/fen_oracle_c.c); fallback: the numpy/scipy oracle.
+    Returns (Mcell-updates/s, seconds per step, cores, description)."""
     cores = os.cpu_count() or 1
+    try:
+        from oracle import fen_oracle_c as foc
+        delta = 2 * PI / float(np.float32(n))
+        c = foc.NavierStokesC(n, n, n, delta, 1.0, 0.01, threads=threads or cores)
+        u, v, p = _tgv_ic(n, delta)
+        c.set(foc.U, u); c.set(foc.V, v); c.set(foc.P, p)
+        dt = min(0.25 * delta / 1.0, (1.0 / 6.0) * delta * delta / 0.01)      # set_timestep(U = 1), CFL = 0.25
+        c.dt_o = dt
+        for s in range(warmup):
+            c.navier_stokes_solver(s + 1, dt)
+        t0 = time.perf_counter()
+        for s in range(steps):
+            c.navier_stokes_solver(warmup + s + 1, dt)
+        t = time.perf_counter() - t0
+        used = c.threads
+        assert abs(c.maxdiv) < 1e-10
+        c.destroy()
+        return n ** 3 * steps / t / 1e6, t / steps, used, "plain-C/OpenMP restatement (oracle/fen_oracle_c.c)"
+    except Exception as e:   # no C compiler on the box: the numpy oracle still gives a baseline
+        sys.stderr.write("bench.py: C oracle unavailable (%r), timing the numpy oracle\n" % (e,))
+    from oracle import fen_oracle as fo
     fo.set_workers(cores)
     G = fo.Grid(n, n, n, 2 * PI, 2 * PI, 2 * PI)
     ns = fo.NavierStokes(G, 1.0, 0.01)
     fo.init_tgv3d(ns)
     ns.CFL = 0.25
     dt = ns.set_timestep(1.0)
-    for s in range(args.warmup):
+    for s in range(warmup):
         ns.navier_stokes_solver(s + 1, dt)
     t0 = time.perf_counter()
-    for s in range(args.steps):
-        ns.navier_stokes_solver(args.warmup + s + 1, dt)
+    for s in range(steps):
+        ns.navier_stokes_solver(warmup + s + 1, dt)
     t = time.perf_counter() - t0
-    val = n ** 3 * args.steps / t / 1e6
-    sample = "%d^3 slab-free sample of the 512^3 Taylor-Green case, %d steps" % (n, args.steps)
+    return n ** 3 * steps / t / 1e6, t / steps, cores, "numpy/scipy oracle (oracle/fen_oracle.py)"
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the CPU restatement of the reference (oracle/), all host threads, on a bounded sample of
+    the same workload (the reference's own Fortran/MPI/FFTW build does not exist in this image)."""
+    if rank != 0:
+        return
+    n = args.cpu_size
+    val, sec, cores, what = cpu_port(n, args.steps, args.warmup)
+    sample = "%d^3 sample of the 512^3 Taylor-Green case, %d steps, %s" % (n, args.steps, what)
     line = {
         "impl": "reference", "metric": "NS timestep Mcell-updates/s", "value": val, "unit": "Mcell-updates/s",
-        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps,
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sec,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": "3D periodic Taylor-Green vortex 512^3 fp64, ppp Poisson (CPU arm: bounded %d^3 "
                                "sample)" % n, "grid": [n, n, n], "nu": 0.01, "CFL": 0.25},
         "cpu_baseline": {"value": val, "unit": "Mcell-updates/s", "cores": cores, "kind": "port", "sample": sample,
-                         "note": "numpy/scipy restatement of the reference's CPU path (oracle/), not the "
-                                 "gfortran/FFTW/2decomp binary (no Fortran toolchain in this image)"},
+                         "note": "restatement of the reference's CPU path (oracle/), not the gfortran/FFTW/2decomp "
+                                 "binary (no Fortran toolchain in this image)"},
         "e2e": {"value": val, "unit": "Mcell-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -227,24 +266,13 @@ def run_reference(args, rank, world):
 
 
 def cpu_baseline(budget_s=20.0):
-    from oracle import fen_oracle as fo
-    cores = os.cpu_count() or 1
-    fo.set_workers(cores)
-    n = 128
-    G = fo.Grid(n, n, n, 2 * PI, 2 * PI, 2 * PI)
-    ns = fo.NavierStokes(G, 1.0, 0.01)
-    fo.init_tgv3d(ns)
-    ns.CFL = 0.25
-    dt = ns.set_timestep(1.0)
-    ns.navier_stokes_solver(1, dt)
-    t0 = time.perf_counter()
-    steps = 0
-    while steps < 3 or (time.perf_counter() - t0 < budget_s and steps < 12):
-        steps += 1
-        ns.navier_stokes_solver(steps + 1, dt)
-    t = time.perf_counter() - t0
-    return {"value": n ** 3 * steps / t / 1e6, "unit": "Mcell-updates/s", "cores": cores, "kind": "port",
-            "sample": "%d steps of the same Taylor-Green case at %d^3 (1 warm-up), numpy/scipy oracle" % (steps, n)}
+    n = 256
+    # one probing step decides how many steps fit the budget
+    _, sec, _, _ = cpu_port(n, 1, 1)
+    steps = int(max(3, min(40, budget_s / max(sec, 1e-3))))
+    val, sec, cores, what = cpu_port(n, steps, 1)
+    return {"value": val, "unit": "Mcell-updates/s", "cores": cores, "kind": "port",
+            "sample": "%d steps of the same Taylor-Green case at %d^3 (1 warm-up), %s" % (steps, n, what)}
 
 
 def main():
@@ -254,7 +282,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--size", type=int, default=512, help="cells per direction per GPU (config 2: 512)")
-    ap.add_argument("--cpu-size", type=int, default=128)
+    ap.add_argument("--cpu-size", type=int, default=256)
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
