@@ -335,6 +335,8 @@ def main():
         if args.grid:        # tuning aid: an explicit global grid (e.g. the 1024x1024x128 slab one GPU owns at N = 8)
             nx, ny, nz = [int(v) for v in args.grid.split(",")]
         L = 2 * PI
+        if args.grid:
+            n = min(nx, ny, nz)      # every box side stays a whole number of Taylor-Green wavelengths
         G = fb.grid().setup(nx, ny, nz, L * nx / n, L * ny / n, L * nz / n, pcol=world, rank=rank, device=local_rank)
     if world > 1:
         def all_gather(b):

@@ -2,6 +2,7 @@
 // host<->device movement, module parameters and the navier_stokes_solver driver.
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include <algorithm>
@@ -173,6 +174,12 @@ static void wire_bc(fen_ctx* c) {
     }
 }
 
+void step_graphs_clear(fen_ctx* c) {
+    for (auto& kv : c->step_graphs)
+        if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
+    c->step_graphs.clear();
+}
+
 static int fetch_red(fen_ctx* c, int n) {
     FEN_CUDA(cudaMemcpyAsync(c->h_red, c->d_red, n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     return FEN_OK;
@@ -237,6 +244,7 @@ int fen_gpu_destroy(fen_ctx* c) {
     if (!c) return FEN_OK;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
+    step_graphs_clear(c);
     poisson_destroy(c);
     comm_destroy(c);     // multi-rank: the caller barriers first so that no peer is still storing here
     for (auto& f : c->fields) free_field(f);
@@ -468,6 +476,7 @@ int fen_gpu_init_solver(fen_ctx* c) {
 int fen_gpu_destroy_solver(fen_ctx* c) {
     if (!c) return set_error(FEN_ERR_ARG, "null context");
     cudaStreamSynchronize(c->stream);
+    step_graphs_clear(c);
     poisson_destroy(c);
     for (int id = 0; id < FEN_FIELD_USER; ++id) { free_field(c->fields[id]); c->fields[id].exists = false; }
     for (int m = 0; m < 3; ++m) { if (c->vnew[m]) cudaFree(c->vnew[m]); c->vnew[m] = nullptr; }
@@ -532,11 +541,8 @@ int fen_gpu_checks(fen_ctx* c, double dt) {
     return fetch_red(c, 2);
 }
 
-int fen_gpu_navier_stokes_solver(fen_ctx* c, int step, double* dt) {
-    if (!c || !dt) return set_error(FEN_ERR_ARG, "null argument");
-    if (!c->solver_init) return set_error(FEN_ERR_STATE, "init_solver has not been called");
-    if (!(c->prm.dt_o > 0.0)) return set_error(FEN_ERR_STATE, "dt_o is not set: call set_timestep first");
-    if (c->prm.constant_CFL) FEN_TRY(update_timestep(c, dt));             // navier_stokes.f90:78
+// everything navier_stokes_solver enqueues after the time-step control (navier_stokes.f90:105-134)
+static int step_enqueue(fen_ctx* c, int step, double* dt) {
     FEN_TRY(ns_predict(c, *dt));                                          // :105
     if (c->forcing) {                                                     // :106-108 apply_ibm_forcing(v, dt)
         FEN_CUDA(cudaStreamSynchronize(c->stream));
@@ -556,8 +562,89 @@ int fen_gpu_navier_stokes_solver(fen_ctx* c, int step, double* dt) {
     bool checks_done = false;
     FEN_TRY(ns_correct(c, *dt, &checks_done));                            // :127, :130 (+ :134 when fused)
     if (!checks_done) FEN_TRY(ns_checks_launch(c, *dt));                  // :134
-    c->last_dt = *dt;
     return fetch_red(c, 2);
+}
+
+// Signature of everything a captured step bakes into its kernel arguments: time steps, module scalars, buffer
+// addresses (ping-pong parity included), property mode and the boundary-condition tables of the solver fields.
+static unsigned long long step_signature(fen_ctx* c, double dt) {
+    unsigned long long h = 1469598103934665603ull;
+    auto mix = [&](const void* p, size_t n) {
+        const unsigned char* b = static_cast<const unsigned char*>(p);
+        for (size_t i = 0; i < n; ++i) { h ^= b[i]; h *= 1099511628211ull; }
+    };
+    mix(&dt, sizeof(dt));
+    mix(&c->prm, sizeof(c->prm));
+    mix(&c->rho_uniform, sizeof(double));
+    mix(&c->mu_uniform, sizeof(double));
+    const int flags = (c->uniform_props ? 1 : 0) | (c->has_source ? 2 : 0);
+    mix(&flags, sizeof(flags));
+    for (int id = 0; id <= FEN_SZ; ++id) {
+        const Field& f = c->fields[id];
+        mix(&f.d, sizeof(f.d));
+        if (id <= FEN_VZ) {
+            mix(f.bc_type, sizeof(f.bc_type));
+            mix(f.bc_mode, sizeof(f.bc_mode));
+            mix(f.bc_value, sizeof(f.bc_value));
+            mix(f.bc_plane, sizeof(f.bc_plane));
+        }
+    }
+    mix(c->vnew, sizeof(c->vnew));
+    mix(&c->ps, sizeof(c->ps));
+    mix(&c->d_red, sizeof(c->d_red));
+    return h;
+}
+
+
+int fen_gpu_navier_stokes_solver(fen_ctx* c, int step, double* dt) {
+    if (!c || !dt) return set_error(FEN_ERR_ARG, "null argument");
+    if (!c->solver_init) return set_error(FEN_ERR_STATE, "init_solver has not been called");
+    if (!(c->prm.dt_o > 0.0)) return set_error(FEN_ERR_STATE, "dt_o is not set: call set_timestep first");
+    FEN_CUDA(cudaSetDevice(c->device));
+    if (c->prm.constant_CFL) FEN_TRY(update_timestep(c, dt));             // navier_stokes.f90:78
+    c->last_dt = *dt;
+    // The step is a fixed sequence of ~16 launches with no host decision inside: after it has run once eagerly it is
+    // captured into a CUDA graph and replayed (one launch per step instead of sixteen -- what matters on the small
+    // grids of the reference's own tests, where the step is launch-bound).  Not with a host hook (it synchronises),
+    // per-kernel profiling, or several ranks (the exchange kernels carry a per-call epoch in their arguments).
+    static const bool env_off = getenv("FEN_NO_GRAPH") != nullptr;
+    const bool graph_ok = !env_off && !c->graphs_off && !c->forcing && !c->profiling && c->g.nranks == 1;
+    if (!graph_ok) return step_enqueue(c, step, dt);
+    if (c->step_graphs.size() > 16) step_graphs_clear(c);
+    StepGraph& g = c->step_graphs[step_signature(c, *dt)];
+    if (!g.exec) {
+        if (g.seen++ == 0) return step_enqueue(c, step, dt);             // first time: eager (also warms the statics)
+        double* const u_before = c->fields[FEN_VX].d;
+        const long long l0 = c->launches;
+        cudaGraph_t graph = nullptr;
+        cudaError_t e = cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal);
+        int r = FEN_OK;
+        if (e == cudaSuccess) {
+            r = step_enqueue(c, step, dt);
+            e = cudaStreamEndCapture(c->stream, &graph);
+        }
+        if (e == cudaSuccess && r == FEN_OK) e = cudaGraphInstantiate(&g.exec, graph, 0);
+        if (graph) cudaGraphDestroy(graph);
+        g.launches = c->launches - l0;
+        g.net_swap = c->fields[FEN_VX].d != u_before;
+        if (e != cudaSuccess || r != FEN_OK) {
+            // nothing has run: undo the host-side ping-pong and fall back to eager launches for good
+            cudaGetLastError();
+            if (g.net_swap)
+                for (int m = 0; m < c->g.ndim; ++m) std::swap(c->fields[FEN_VX + m].d, c->vnew[m]);
+            c->launches = l0;
+            g.exec = nullptr;
+            c->graphs_off = true;
+            return step_enqueue(c, step, dt);
+        }
+        FEN_CUDA(cudaGraphLaunch(g.exec, c->stream));
+        return FEN_OK;
+    }
+    FEN_CUDA(cudaGraphLaunch(g.exec, c->stream));
+    c->launches += g.launches;
+    if (g.net_swap)
+        for (int m = 0; m < c->g.ndim; ++m) std::swap(c->fields[FEN_VX + m].d, c->vnew[m]);
+    return FEN_OK;
 }
 
 int fen_gpu_get_status(fen_ctx* c, double* maxdiv, double* maxCFL) {

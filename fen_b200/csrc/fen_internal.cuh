@@ -59,6 +59,14 @@ struct TmapKey {
     bool operator<(const TmapKey& o) const { return std::tie(base, bx, by) < std::tie(o.base, o.bx, o.by); }
 };
 
+// one captured navier_stokes_solver step (context.cu): replayed while the step's inputs keep the same signature
+struct StepGraph {
+    cudaGraphExec_t exec = nullptr;
+    long long launches = 0;    // kernels inside, for fen_gpu_launch_count
+    bool net_swap = false;     // the step leaves v in the other ping-pong buffer
+    int seen = 0;
+};
+
 struct Poisson;   // poisson.cu
 struct Comm;      // comm.cu
 
@@ -86,6 +94,8 @@ struct fen_ctx {
     double* h_red = nullptr;     // pinned host mirror of the results
     int red_blocks = 0;
 
+    std::map<unsigned long long, fen::StepGraph> step_graphs;   // CUDA graphs of the step, keyed by its signature
+    bool graphs_off = false;            // capture failed once, or FEN_NO_GRAPH: always enqueue eagerly
     fen_forcing_fn forcing = nullptr;   // host hook after the predictor (io.cu)
     void* forcing_user = nullptr;
 
