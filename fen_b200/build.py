@@ -10,7 +10,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "csrc", "_obj")
 LIB = os.path.join(HERE, "libfen_gpu.so")
-SOURCES = ["context.cu", "ghost.cu", "stencil.cu", "poisson.cu", "comm.cu", "tma.cu", "io.cu"]
+SOURCES = ["context.cu", "ghost.cu", "stencil.cu", "poisson.cu", "comm.cu", "tma.cu", "io.cu", "multiphase.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-std=c++17", "-O3", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
          "-Xcompiler", "-fPIC", "-Xptxas", "-v"]

@@ -54,7 +54,7 @@ int field_check(fen_ctx* c, int id, Field** out, bool alloc) {
     cudaSetDevice(c->device);      // one context per GPU; callers may drive several from one thread
     if (id < 0 || id >= (int)c->fields.size() || !c->fields[id].exists)
         return set_error(FEN_ERR_ARG, "unknown field id %d", id);
-    if (c->g.ndim == 2 && id < FEN_FIELD_USER && id >= FEN_VX && (id - FEN_VX) % 3 == 2)
+    if (c->g.ndim == 2 && ((id <= FEN_SZ && id >= FEN_VX && (id - FEN_VX) % 3 == 2) || id == FEN_NORMZ || id == FEN_LZ))
         return set_error(FEN_ERR_ARG, "z component (field %d) does not exist in 2-D (vector.f90:52-54)", id);
     Field& f = c->fields[id];
     if (alloc && !f.d) {
@@ -77,7 +77,7 @@ static int fill_async(fen_ctx* c, double* d, double val) {
     return FEN_OK;
 }
 
-static void free_field(Field& f) {
+void free_field(Field& f) {
     if (f.d) cudaFree(f.d);
     f.d = nullptr;
     for (int q = 0; q < 6; ++q) {
@@ -88,7 +88,7 @@ static void free_field(Field& f) {
     }
 }
 
-static void init_field(fen_ctx* c, int id, int gl, int loc) {
+void init_field(fen_ctx* c, int id, int gl, int loc) {
     Field& f = c->fields[id];
     free_field(f);
     f.exists = true;
@@ -180,7 +180,7 @@ void step_graphs_clear(fen_ctx* c) {
     c->step_graphs.clear();
 }
 
-static int fetch_red(fen_ctx* c, int n) {
+int fetch_red(fen_ctx* c, int n) {
     FEN_CUDA(cudaMemcpyAsync(c->h_red, c->d_red, n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     return FEN_OK;
 }
@@ -246,6 +246,7 @@ int fen_gpu_destroy(fen_ctx* c) {
     cudaStreamSynchronize(c->stream);
     step_graphs_clear(c);
     poisson_destroy(c);
+    mf_destroy(c);
     comm_destroy(c);     // multi-rank: the caller barriers first so that no peer is still storing here
     for (auto& f : c->fields) free_field(f);
     for (int m = 0; m < 3; ++m) if (c->vnew[m]) cudaFree(c->vnew[m]);
@@ -311,7 +312,7 @@ int fen_gpu_push(fen_ctx* c, int id, const double* host, int gl) {
         FEN_TRY(field_check(c, FEN_MU, &fm));
         FEN_TRY(field_is_uniform(c, fr->d, &ur, &vr));
         FEN_TRY(field_is_uniform(c, fm->d, &um, &vm));
-        c->uniform_props = ur && um;
+        c->uniform_props = ur && um && !mf_active(c);
         if (ur) c->rho_uniform = vr;
         if (um) c->mu_uniform = vm;
     }
@@ -478,6 +479,7 @@ int fen_gpu_destroy_solver(fen_ctx* c) {
     cudaStreamSynchronize(c->stream);
     step_graphs_clear(c);
     poisson_destroy(c);
+    mf_destroy(c);                         // destroy_vof, p_hat, p_o (solver.f90:347-352)
     for (int id = 0; id < FEN_FIELD_USER; ++id) { free_field(c->fields[id]); c->fields[id].exists = false; }
     for (int m = 0; m < 3; ++m) { if (c->vnew[m]) cudaFree(c->vnew[m]); c->vnew[m] = nullptr; }
     c->solver_init = false;
@@ -497,6 +499,7 @@ int fen_gpu_set_params(fen_ctx* c, const fen_ns_params* p) {
 
 int fen_gpu_set_timestep(fen_ctx* c, double U, double* dt) {
     if (!c || !dt) return set_error(FEN_ERR_ARG, "null argument");
+    if (mf_active(c)) return mf_set_timestep(c, U, dt);                   // -DMF: navier_stokes.f90:655-661
     const double d = c->g.delta;
     fen_ns_params& p = c->prm;
     p.dt_conv = p.CFL * d / U;                                            // navier_stokes.f90:641
@@ -517,6 +520,7 @@ static int update_timestep(fen_ctx* c, double* dt) {
     const double max_vel = std::max(0.0, c->h_red[1]);
     p.dt_conv = max_vel > 0.0 ? p.CFL * c->g.delta / max_vel : 1.0;
     *dt = std::min(p.dt_conv, p.dt_visc);
+    if (mf_active(c)) *dt = std::min(*dt, c->mf->prm.dt_surf);            // :724 (hazard H16)
     if (*dt > 1.1 * p.dt_o) *dt = 1.1 * p.dt_o;
     return FEN_OK;
 }
@@ -543,7 +547,13 @@ int fen_gpu_checks(fen_ctx* c, double dt) {
 
 // everything navier_stokes_solver enqueues after the time-step control (navier_stokes.f90:105-134)
 static int step_enqueue(fen_ctx* c, int step, double* dt) {
-    FEN_TRY(ns_predict(c, *dt));                                          // :105
+    const bool mf = mf_active(c);
+    if (mf) {
+        FEN_TRY(mf_step_front(c, *dt));                                   // :80-96 advect_interface, rho / mu, p_hat
+        FEN_TRY(mf_predict(c, *dt));                                      // :105 with the MF terms
+    } else {
+        FEN_TRY(ns_predict(c, *dt));                                      // :105
+    }
     if (c->forcing) {                                                     // :106-108 apply_ibm_forcing(v, dt)
         FEN_CUDA(cudaStreamSynchronize(c->stream));
         const int hr = c->forcing(c->forcing_user, step, *dt);
@@ -552,7 +562,10 @@ static int step_enqueue(fen_ctx* c, int step, double* dt) {
     }
     Field* phi;
     FEN_TRY(field_check(c, FEN_PHI, &phi));
-    if (poisson_can_fuse_rhs(c)) {
+    if (mf) {
+        FEN_TRY(mf_poisson_rhs(c, *dt));                                  // :111-113 phi*rhomin/dt
+        FEN_TRY(poisson_solve(c, phi->d));                                // :123
+    } else if (poisson_can_fuse_rhs(c)) {
         FEN_TRY(poisson_solve(c, phi->d, true, *dt));                     // :111-123, rhs computed by the x pass
     } else {
         FEN_TRY(ns_poisson_rhs(c, *dt));                                  // :111-121
@@ -560,7 +573,8 @@ static int step_enqueue(fen_ctx* c, int step, double* dt) {
     }
     FEN_TRY(ghost_update(c, FEN_PHI, 1, true));                           // :124 (x ghosts written by the c2r pass)
     bool checks_done = false;
-    FEN_TRY(ns_correct(c, *dt, &checks_done));                            // :127, :130 (+ :134 when fused)
+    if (mf) FEN_TRY(mf_correct(c, *dt));                                  // :127, :130 with 1/rhomin and p_o = p
+    else FEN_TRY(ns_correct(c, *dt, &checks_done));                       // :127, :130 (+ :134 when fused)
     if (!checks_done) FEN_TRY(ns_checks_launch(c, *dt));                  // :134
     return fetch_red(c, 2);
 }
@@ -579,10 +593,11 @@ static unsigned long long step_signature(fen_ctx* c, double dt) {
     mix(&c->mu_uniform, sizeof(double));
     const int flags = (c->uniform_props ? 1 : 0) | (c->has_source ? 2 : 0);
     mix(&flags, sizeof(flags));
-    for (int id = 0; id <= FEN_SZ; ++id) {
+    if (mf_active(c)) mix(&c->mf->prm, sizeof(c->mf->prm));              // x_first and the BC types of vof included
+    for (int id = 0; id < FEN_FIELD_USER; ++id) {
         const Field& f = c->fields[id];
         mix(&f.d, sizeof(f.d));
-        if (id <= FEN_VZ) {
+        if (id <= FEN_VZ || id >= FEN_VOF) {
             mix(f.bc_type, sizeof(f.bc_type));
             mix(f.bc_mode, sizeof(f.bc_mode));
             mix(f.bc_value, sizeof(f.bc_value));
@@ -616,6 +631,7 @@ int fen_gpu_navier_stokes_solver(fen_ctx* c, int step, double* dt) {
         if (g.seen++ == 0) return step_enqueue(c, step, dt);             // first time: eager (also warms the statics)
         double* const u_before = c->fields[FEN_VX].d;
         const long long l0 = c->launches;
+        const int xf0 = mf_active(c) ? c->mf->prm.x_first : 0;
         cudaGraph_t graph = nullptr;
         cudaError_t e = cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal);
         int r = FEN_OK;
@@ -632,6 +648,7 @@ int fen_gpu_navier_stokes_solver(fen_ctx* c, int step, double* dt) {
             cudaGetLastError();
             if (g.net_swap)
                 for (int m = 0; m < c->g.ndim; ++m) std::swap(c->fields[FEN_VX + m].d, c->vnew[m]);
+            if (mf_active(c)) c->mf->prm.x_first = xf0;
             c->launches = l0;
             g.exec = nullptr;
             c->graphs_off = true;
@@ -642,8 +659,10 @@ int fen_gpu_navier_stokes_solver(fen_ctx* c, int step, double* dt) {
     }
     FEN_CUDA(cudaGraphLaunch(g.exec, c->stream));
     c->launches += g.launches;
+    // host-side effects of the step that the graph does not replay: ping-pong parity and advect_vof's x_first toggle
     if (g.net_swap)
         for (int m = 0; m < c->g.ndim; ++m) std::swap(c->fields[FEN_VX + m].d, c->vnew[m]);
+    if (mf_active(c)) c->mf->prm.x_first = c->mf->prm.x_first ? 0 : 1;
     return FEN_OK;
 }
 

@@ -70,6 +70,13 @@ struct StepGraph {
 struct Poisson;   // poisson.cu
 struct Comm;      // comm.cu
 
+// state of volume_of_fluid_mod / multiphase_mod (multiphase.cu); allocated by fen_gpu_allocate_vof_fields
+struct Multiphase {
+    fen_mf_params prm{};
+    bool vof_fields = false;   // allocate_vof_fields has run
+    bool ns = false;           // init_solver_mf has run: the step takes the -DMF branches
+};
+
 }  // namespace fen
 
 struct fen_ctx {
@@ -101,6 +108,7 @@ struct fen_ctx {
 
     fen::Poisson* ps = nullptr;
     fen::Comm* comm = nullptr;
+    fen::Multiphase* mf = nullptr;
     std::map<fen::TmapKey, CUtensorMap> tmaps;      // TMA descriptors of the field buffers (tma.cu)
 
     // measurement
@@ -138,6 +146,9 @@ void prof_end(fen_ctx* c, int token);
 
 int field_check(fen_ctx* c, int id, Field** out, bool alloc = true);
 int field_alloc(fen_ctx* c, Field& f);
+void init_field(fen_ctx* c, int id, int gl, int loc);     // scalar%allocate defaults (scalar.f90:63-133)
+void free_field(Field& f);
+int fetch_red(fen_ctx* c, int n);                          // async copy of d_red[0..n) to h_red
 
 // tma.cu
 int field_tmap(fen_ctx* c, const double* base, int box_x, int box_y, CUtensorMap** out);
@@ -172,5 +183,13 @@ int poisson_solve(fen_ctx* c, double* f, bool fuse_rhs = false, double dt = 0.0)
 bool poisson_can_fuse_rhs(fen_ctx* c);
 void poisson_destroy(fen_ctx* c);
 const char* poisson_variant(fen_ctx* c);
+// multiphase.cu
+inline bool mf_active(const fen_ctx* c) { return c->mf && c->mf->ns; }
+int mf_step_front(fen_ctx* c, double dt);      // advect_interface, material properties, p_hat (navier_stokes.f90:80-96)
+int mf_predict(fen_ctx* c, double dt);         // predicted_velocity_field with the MF terms (:140-213, :405-501)
+int mf_poisson_rhs(fen_ctx* c, double dt);     // phi = div(v) rhomin/dt (:111-113)
+int mf_correct(fen_ctx* c, double dt);         // correct_velocity_field + update_pressure, MF branches (:526-531, :553-564)
+int mf_set_timestep(fen_ctx* c, double U, double* dt);
+void mf_destroy(fen_ctx* c);
 
 }  // namespace fen

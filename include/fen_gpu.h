@@ -63,6 +63,13 @@ enum fen_field {
     FEN_DVOX = 10, FEN_DVOY = 11, FEN_DVOZ = 12,    /* dv_o    */
     FEN_GPX = 13, FEN_GPY = 14, FEN_GPZ = 15,       /* grad_p  */
     FEN_SX = 16, FEN_SY = 17, FEN_SZ = 18,          /* S       */
+    /* two-phase build (-DMF): module fields of volume_of_fluid_mod (volume_of_fluid.f90:21-22) and of
+     * multiphase_mod (multiphase.f90:26); they exist after fen_gpu_allocate_vof_fields / fen_gpu_init_solver_mf */
+    FEN_VOF = 19, FEN_H = 20, FEN_D = 21, FEN_CURV = 22,
+    FEN_NORMX = 23, FEN_NORMY = 24, FEN_NORMZ = 25, /* norm    */
+    FEN_LX = 26, FEN_LY = 27, FEN_LZ = 28,          /* l       */
+    FEN_PHAT = 29, FEN_PO = 30,                     /* p_hat, p_o */
+    FEN_VOF1 = 31,                                  /* advect_vof's temporary vof1 (volume_of_fluid.f90:445) */
     FEN_FIELD_USER = 32
 };
 
@@ -187,6 +194,43 @@ int fen_gpu_save_fields(fen_ctx* ctx, int step, const char* dir);
  * refreshes the ghost nodes of v.  A non-zero return aborts the step.  NULL removes the hook. ------------------- */
 typedef int (*fen_forcing_fn)(void* user, int step, double dt);
 int fen_gpu_set_forcing_hook(fen_ctx* ctx, fen_forcing_fn fn, void* user);
+
+/* ---- two-phase path: volume_of_fluid_mod (MTHINC VoF, src/volume_of_fluid.f90), multiphase_mod
+ * (src/multiphase.f90) and the `#ifdef MF` branches of navier_stokes_mod / solver_mod.  As in the reference this
+ * path is 2-D only (ndim = 2): compute_norm, compute_flux and the variable-viscosity stress divergence have no z
+ * terms (volume_of_fluid.f90:307-396, 558-642; navier_stokes.f90:405-452).  The reference selects it at compile time
+ * (-DMF); here fen_gpu_init_solver_mf selects it per context, after which fen_gpu_set_timestep and
+ * fen_gpu_navier_stokes_solver take the MF branches. ------------------------------------------------------------- */
+typedef struct fen_mf_params {
+    double rho_0, rho_1, mu_0, mu_1;   /* multiphase.f90:18 */
+    double sigma;                      /* multiphase.f90:21 */
+    double beta;                       /* volume_of_fluid.f90:24 sharpness */
+    double cut;                        /* volume_of_fluid.f90:37 */
+    int quadratic;                     /* volume_of_fluid.f90:27 */
+    int x_first;                       /* volume_of_fluid.f90:30 (toggled by every advect_vof) */
+    double dt_surf;                    /* navier_stokes.f90:29; set by set_timestep when sigma > 0, +inf before */
+    double rhomin, irhomin;            /* multiphase.f90:29; set by init_solver_mf (solver.f90:92-93) */
+} fen_mf_params;
+int fen_gpu_mf_get_params(fen_ctx* ctx, fen_mf_params* p);
+int fen_gpu_mf_set_params(fen_ctx* ctx, const fen_mf_params* p);
+/* allocate_vof_fields (volume_of_fluid.f90:54): vof, h, d, curv, norm, l with one ghost layer, Periodic -> 0 and
+ * Wall -> Neumann on the four faces.  Usable without init_solver (the reference's VoF-only tests do that). */
+int fen_gpu_allocate_vof_fields(fen_ctx* ctx);
+/* get_vof_from_distance (volume_of_fluid.f90:676): `fn` is the reference's `distance` procedure pointer (:40-46).  It
+ * is evaluated on the host at the cell centre and the four Gauss points of every cell; the tanh profile, the
+ * quadrature and the ghost update run on the device.  NULL -> FEN_ERR_ARG ('ERROR: distance function not defined.') */
+typedef double (*fen_distance_fn)(void* user, double x, double y);
+int fen_gpu_get_vof_from_distance(fen_ctx* ctx, fen_distance_fn fn, void* user, double x0, double y0);
+int fen_gpu_get_h_from_vof(fen_ctx* ctx);                                   /* volume_of_fluid.f90:228 */
+int fen_gpu_advect_vof(fen_ctx* ctx, int vector_x, double dt);              /* volume_of_fluid.f90:434 */
+int fen_gpu_check_vof_integral(fen_ctx* ctx, double* int_phase_1, double* int_phase_2);   /* :722 */
+int fen_gpu_destroy_vof(fen_ctx* ctx);                                      /* volume_of_fluid.f90:758 */
+int fen_gpu_update_material_properties(fen_ctx* ctx);                       /* multiphase.f90:121 */
+/* init_solver compiled with -DMF (solver.f90:34-99): fen_gpu_init_solver + constant_viscosity = .false. +
+ * allocate_vof_fields + allocate_multiphase_fields (multiphase.f90:46) + get_vof_from_distance (skipped with the
+ * reference's error message when fn is NULL: push FEN_VOF and call fen_gpu_update_material_properties instead) +
+ * update_material_properties + rhomin.  (x0, y0) = grid origin (grid%x(i) = x0 + (i - 1/2) delta, grid.f90:155). */
+int fen_gpu_init_solver_mf(fen_ctx* ctx, fen_distance_fn fn, void* user, double x0, double y0);
 
 /* ---- measurement helpers (no reference analogue: FEN has no timers) --- */
 /* per-kernel-family CUDA-event timing of the next steps; names/ms arrays sized by the caller */
