@@ -63,6 +63,11 @@ def load_traffic(kernel, size):
         pass
     return None
 STEP_BYTES_PER_CELL = 312.0
+# two-phase step, 2-D (fen_b200/csrc/multiphase.cu header): algorithmic bytes per cell per launch
+MF_KERNEL_BYTES_PER_CELL = {"vof_recon": 64.0, "vof_sweep": 72.0, "mf_props": 48.0, "mf_pred": 112.0,
+                            "poisson_rhs": 24.0, "corr": 64.0, "check": 16.0}
+# sum over one step: 2 recon + 2 sweeps + props + pred + rhs + Poisson pn (r2c 16, Thomas 2 x 16, c2r 16) + corr + check
+MF_STEP_BYTES_PER_CELL = 2 * 64.0 + (64.0 + 80.0) + 48.0 + 112.0 + 24.0 + 64.0 + 64.0 + 16.0
 
 
 def load_peaks():
@@ -275,6 +280,132 @@ def cpu_baseline(budget_s=20.0):
             "sample": "%d steps of the same Taylor-Green case at %d^3 (1 warm-up), %s" % (steps, n, what)}
 
 
+def run_wave2d(args, local_rank):
+    """--case wave2d: the two-phase step (MTHINC VoF + one-fluid NS with pressure splitting) on a
+    2-D gravity wave between fluids of density ratio 850 -- the 2-D analogue of BASELINE configs[4], which the
+    reference cannot express in 3-D (its VoF and variable-viscosity terms have no z part).  One GPU."""
+    import math
+    import torch
+    import fen_b200 as fb
+    nx, ny = 2048, 4096         # x is an FFT direction (<= 2048 points); y is solved by the Thomas algorithm
+    if args.grid:
+        nx, ny = [int(q) for q in args.grid.split(",")][:2]
+    Lx, Ly = 1.0, float(ny) / nx
+    G = fb.grid().setup(nx, ny, 1, Lx, Ly, Lx / nx, bc=["Periodic", "Periodic", "Wall", "Wall"], device=local_rank)
+    ns = fb.MultiphaseSolver(G)
+    g = 9.80665
+    ns.rho_0 = 1000.0
+    ns.rho_1 = 1000.0 / 850.0
+    ns.mu_0 = 1000.0 * Lx * math.sqrt(g * Lx) / 1.0e4
+    ns.mu_1 = ns.mu_0 * 1.9e-2
+    ns.sigma = 0.07
+    ns.g = [0.0, -g, 0.0]
+    ns.init_solver(None)        # synthetic initial vof pushed below (a Python distance callback per cell is no bench)
+    d = G.delta
+    x = ((np.arange(0, nx + 2) - 0.5) * d)[:, None]
+    y = ((np.arange(0, ny + 2) - 0.5) * d)[None, :]
+    a, wn = 0.02, 2.0 * PI / Lx
+    ns.vof.f[:, :, 1] = 0.5 * (1.0 + np.tanh(1.0 * (y - a * np.cos(wn * x) - Ly / 2.0) / d))
+    ns.vof.push()
+    ns.vof.update_ghost_nodes()
+    ns.update_material_properties()
+    om = math.sqrt(g * wn)
+    f = ns.vof.f[:, :, 1]
+    xs, ys = x + 0.5 * d, y - Ly / 2.0
+    ns.v.x.f[:, :, 1] = ((1.0 - f) * np.exp(np.minimum(wn * ys, 0.0)) - f * np.exp(np.minimum(-wn * ys, 0.0))) * a * om * np.cos(wn * xs)
+    xs, ys = x, y + 0.5 * d - Ly / 2.0
+    ns.v.y.f[:, :, 1] = ((1.0 - f) * np.exp(np.minimum(wn * ys, 0.0)) + f * np.exp(np.minimum(-wn * ys, 0.0))) * a * om * np.sin(wn * xs)
+    ns.v.push()
+    ns.v.update_ghost_nodes()
+    dt = 0.1 * ns.set_timestep(1.0)
+    G.synchronize()
+    stream = torch.cuda.ExternalStream(G.lib.fen_gpu_stream(G.ctx))
+    step_no = [0]
+
+    def dev_step(_):
+        step_no[0] += 1
+        ns.navier_stokes_solver(step_no[0], dt)
+
+    def timed(fn, k):
+        G.synchronize(); torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for q in range(k):
+            fn(q)
+        e1.record(stream)
+        G.synchronize(); torch.cuda.synchronize()
+        return e0.elapsed_time(e1)
+
+    for q in range(max(args.warmup, 6)):      # x_first alternates: both step graphs are captured during warm-up
+        dev_step(q)
+    l0 = ns.launch_count()
+    with ClockSampler(local_rank) as cs:
+        ms = timed(dev_step, args.steps)
+    launches = ns.launch_count() - l0
+    maxdiv, maxcfl = ns.status()
+    i1, i2 = ns.check_vof_integral()
+    ncell = nx * ny
+    ns.profile(True)
+    nprof = min(args.steps, 4)
+    for q in range(nprof):
+        dev_step(q)
+    prof = ns.profile_read()
+    ns.profile(False)
+    peak, peak_src = load_peaks()
+    kernels = []
+    for name, (tms, cnt) in prof.items():
+        if cnt == 0:
+            continue
+        per = tms / cnt
+        bpc = MF_KERNEL_BYTES_PER_CELL.get(name)
+        gbs = (bpc * ncell / (per * 1e-3) / 1e9) if bpc else None
+        kernels.append({"kernel": name, "launches_per_step": cnt / nprof, "ms_per_launch": per,
+                        "ms_per_step": tms / nprof, "alg_bytes_per_cell": bpc, "achieved_GBs": gbs,
+                        "frac": (gbs / peak) if gbs else None})
+    kernels.sort(key=lambda k: -k["ms_per_step"])
+    dom = next((k for k in kernels if k["achieved_GBs"]), None)
+    per_step = ms / args.steps
+    step_gbs = MF_STEP_BYTES_PER_CELL * ncell / (per_step * 1e-3) / 1e9
+    e2e = None
+    if not args.no_e2e:
+        fields = [ns.v.x, ns.v.y, ns.p, ns.vof]
+        nbytes = sum(q.f.nbytes for q in fields)
+        for q in fields:
+            q.pull()
+
+        def e2e_step(_):
+            for q in fields:
+                q.push()
+            dev_step(0)
+            for q in fields:
+                q.pull()
+            ns.status()
+        e2e_step(0)
+        ms_e = timed(e2e_step, args.e2e_steps)
+        e2e = {"value": ncell * args.e2e_steps / (ms_e * 1e-3) / 1e6, "unit": "Mcell-updates/s",
+               "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": nbytes + 16, "ms_per_step": ms_e / args.e2e_steps,
+               "what": "push u, v, p, vof from host arrays + two-phase step + pull them + status, every step"}
+    print(json.dumps({
+        "metric": "two-phase NS timestep Mcell-updates/s", "value": ncell * args.steps / (ms * 1e-3) / 1e6,
+        "unit": "Mcell-updates/s", "n_gpus": 1, "steps": args.steps, "warmup": max(args.warmup, 6),
+        "ms_per_step": per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic",
+        "config": {"workload": "2-D two-phase gravity wave %dx%d fp64 (MTHINC VoF, density ratio 850, constant-"
+                               "coefficient pressure splitting, pn Poisson): the 2-D analogue of BASELINE configs[4]"
+                               % (nx, ny), "grid": [nx, ny, 1], "dt": dt,
+                   "l2": "working set (%d fields x %.0f MB) exceeds the 126 MB L2" % (27, ncell * 8 / 1e6)},
+        "e2e": e2e, "gpu_launches": int(launches), "clocks": cs.summary(),
+        "roofline": {"bound": "hbm", "kernel": dom["kernel"] if dom else None,
+                     "achieved": dom["achieved_GBs"] if dom else None, "peak": peak, "unit": "GB/s",
+                     "frac": dom["frac"] if dom else None, "traffic": None, "peak_source": peak_src,
+                     "alg_bytes_per_launch": dom["alg_bytes_per_cell"] * ncell if dom else None,
+                     "step_alg_bytes_per_cell": MF_STEP_BYTES_PER_CELL, "step_achieved": step_gbs,
+                     "step_frac": step_gbs / peak},
+        "cpu_baseline": None, "kernels": kernels,
+        "check": {"maxdiv": maxdiv, "maxCFL": maxcfl, "phase_integrals": [i1, i2]}}))
+    G.destroy()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -286,7 +417,7 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--case", default="tgv", choices=["tgv", "channel"],
+    ap.add_argument("--case", default="tgv", choices=["tgv", "channel", "wave2d"],
                     help="tgv: BASELINE configs[1] (headline, weak scaling); channel: configs[2], 2n x 2n x n walls in z")
     ap.add_argument("--grid", default="", help="explicit global grid nx,ny,nz for --case tgv (tuning aid)")
     ap.add_argument("--mode", default="ns", choices=["ns", "poisson"],
@@ -314,6 +445,11 @@ def main():
     if world != args.gpus:
         raise SystemExit("bench.py: --gpus %d but WORLD_SIZE %d (launch with torch.distributed.run)" % (args.gpus, world))
 
+    if args.case == "wave2d":
+        if world != 1:
+            raise SystemExit("bench.py: --case wave2d is a one-GPU case (2-D grids are not decomposed)")
+        run_wave2d(args, local_rank)
+        return
     n = args.size
     channel = args.case == "channel"
     if channel:

@@ -30,6 +30,13 @@ class NsParams(C.Structure):
                 ("dt_conv", C.c_double), ("constant_CFL", C.c_int)]
 
 
+class MfParams(C.Structure):
+    _fields_ = [("rho_0", C.c_double), ("rho_1", C.c_double), ("mu_0", C.c_double), ("mu_1", C.c_double),
+                ("sigma", C.c_double), ("beta", C.c_double), ("cut", C.c_double),
+                ("quadratic", C.c_int), ("x_first", C.c_int),
+                ("dt_surf", C.c_double), ("rhomin", C.c_double), ("irhomin", C.c_double)]
+
+
 _P = C.c_void_p
 _I = C.c_int
 _D = C.c_double
@@ -37,6 +44,7 @@ _PD = C.POINTER(C.c_double)
 _PI = C.POINTER(C.c_int)
 
 FORCING_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int, C.c_double)     # fen_forcing_fn
+DISTANCE_FN = C.CFUNCTYPE(C.c_double, C.c_void_p, C.c_double, C.c_double)   # fen_distance_fn
 
 # name -> (restype, argtypes); every symbol include/fen_gpu.h declares
 SIGNATURES = {
@@ -89,6 +97,16 @@ SIGNATURES = {
     "fen_gpu_load_state": (_I, [_P, C.c_char_p]),
     "fen_gpu_save_fields": (_I, [_P, _I, C.c_char_p]),
     "fen_gpu_set_forcing_hook": (_I, [_P, FORCING_FN, _P]),
+    "fen_gpu_mf_get_params": (_I, [_P, C.POINTER(MfParams)]),
+    "fen_gpu_mf_set_params": (_I, [_P, C.POINTER(MfParams)]),
+    "fen_gpu_allocate_vof_fields": (_I, [_P]),
+    "fen_gpu_get_vof_from_distance": (_I, [_P, DISTANCE_FN, _P, _D, _D]),
+    "fen_gpu_get_h_from_vof": (_I, [_P]),
+    "fen_gpu_advect_vof": (_I, [_P, _I, _D]),
+    "fen_gpu_check_vof_integral": (_I, [_P, _PD, _PD]),
+    "fen_gpu_destroy_vof": (_I, [_P]),
+    "fen_gpu_update_material_properties": (_I, [_P]),
+    "fen_gpu_init_solver_mf": (_I, [_P, DISTANCE_FN, _P, _D, _D]),
     "fen_gpu_profile_enable": (_I, [_P, _I]),
     "fen_gpu_profile_read": (_I, [_P, _I, _P, _PD, _PI, _PI]),
     "fen_gpu_launch_count": (C.c_longlong, [_P]),

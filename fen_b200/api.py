@@ -22,7 +22,7 @@ import sys
 import numpy as np
 
 from . import _lib
-from ._lib import FenError, GridDesc, NsParams, check
+from ._lib import FenError, GridDesc, MfParams, NsParams, check
 
 _BC_CODE = {"Periodic": 0, "Wall": 1, "Inflow": 2, "Outflow": 3}
 _FACES = ("left", "right", "bottom", "top", "front", "back")
@@ -30,6 +30,7 @@ _LOC = {"c": 0, "x": 1, "y": 2, "z": 3}
 
 # enum fen_field
 P, PHI, RHO, MU, VX, VY, VZ, DVX, DVY, DVZ, DVOX, DVOY, DVOZ, GPX, GPY, GPZ, SX, SY, SZ = range(19)
+VOF, H, D, CURV, NORMX, NORMY, NORMZ, LX, LY, LZ, PHAT, PO, VOF1 = range(19, 32)
 
 
 def _f32(n):
@@ -419,3 +420,126 @@ class Solver:
 
     def launch_count(self):
         return int(self.G.lib.fen_gpu_launch_count(self.G.ctx))
+
+
+# ---------------------------------------------------------------------------------------------------
+# two-phase build (-DMF): volume_of_fluid_mod, multiphase_mod and the MF branches of navier_stokes_mod
+# ---------------------------------------------------------------------------------------------------
+class _MfState:
+    """Module variables of multiphase_mod / volume_of_fluid_mod as attributes (rho_0, rho_1, mu_0, mu_1, sigma,
+    beta, cut, quadratic, x_first, dt_surf, rhomin, irhomin)."""
+
+    _MF = tuple(n for n, _ in MfParams._fields_)
+
+    def _mf_get(self):
+        p = MfParams()
+        check(self.G.lib.fen_gpu_mf_get_params(self.G.ctx, C.byref(p)))
+        return p
+
+    def _mf_attr(self, name):
+        v = getattr(self._mf_get(), name)
+        return bool(v) if name in ("quadratic", "x_first") else v
+
+    def _mf_setattr(self, name, value):
+        p = self._mf_get()
+        setattr(p, name, int(bool(value)) if name in ("quadratic", "x_first") else float(value))
+        check(self.G.lib.fen_gpu_mf_set_params(self.G.ctx, C.byref(p)))
+
+    def _mf_fields(self):
+        G = self.G
+        self.vof = scalar(G, 1, "c", VOF)
+        self.h = scalar(G, 1, "c", H)
+        self.d = scalar(G, 1, "c", D)
+        self.curv = scalar(G, 1, "c", CURV)
+        self.norm = vector(G, 1, NORMX)
+        self.l = vector(G, 1, LX)
+
+    def _tramp(self, distance):
+        def tramp(_user, x, y):
+            return float(distance(x, y))
+        self._dist = _lib.DISTANCE_FN(tramp)             # keep the trampoline alive
+        return self._dist
+
+    # volume_of_fluid_mod procedures
+    def get_vof_from_distance(self, distance):
+        """``distance => f; call get_vof_from_distance`` (volume_of_fluid.f90:676); f(x, y) -> signed distance."""
+        G = self.G
+        check(G.lib.fen_gpu_get_vof_from_distance(G.ctx, self._tramp(distance), None, G.origin[0], G.origin[1]))
+
+    def get_h_from_vof(self):
+        check(self.G.lib.fen_gpu_get_h_from_vof(self.G.ctx))
+
+    def advect_vof(self, v: vector, dt):
+        check(self.G.lib.fen_gpu_advect_vof(self.G.ctx, v.x.id, float(dt)))
+
+    def check_vof_integral(self):
+        a, b = C.c_double(), C.c_double()
+        check(self.G.lib.fen_gpu_check_vof_integral(self.G.ctx, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+
+class VoF(_MfState):
+    """volume_of_fluid_mod on its own, as the reference's VoF-only tests use it (allocate_vof_fields +
+    get_vof_from_distance + advect_vof with a prescribed velocity; test/small_test/volume_of_fluid/*)."""
+
+    def __init__(self, G: grid):
+        object.__setattr__(self, "G", G)
+        check(G.lib.fen_gpu_allocate_vof_fields(G.ctx))
+        self._mf_fields()
+
+    def __getattr__(self, name):
+        if name in _MfState._MF:
+            return self._mf_attr(name)
+        raise AttributeError(name)
+
+    def __setattr__(self, name, value):
+        if name in _MfState._MF:
+            self._mf_setattr(name, value)
+        else:
+            object.__setattr__(self, name, value)
+
+    def destroy_vof(self):
+        check(self.G.lib.fen_gpu_destroy_vof(self.G.ctx))
+
+
+class MultiphaseSolver(Solver, _MfState):
+    """solver_mod + navier_stokes_mod compiled with -DMF.  Set rho_0, rho_1, mu_0, mu_1, sigma, beta (module
+    variables) before ``init_solver(distance)``, exactly as the reference's drivers do
+    (test/small_test/multiphase/viscous_decay/viscous_decay.f90:40-53)."""
+
+    def __init__(self, G: grid):
+        Solver.__init__(self, G, 1.0, 1.0)
+
+    def __getattr__(self, name):
+        if name in _MfState._MF:
+            return self._mf_attr(name)
+        return Solver.__getattr__(self, name)
+
+    def __setattr__(self, name, value):
+        if name in _MfState._MF:
+            self._mf_setattr(name, value)
+        else:
+            Solver.__setattr__(self, name, value)
+
+    def init_solver(self, distance=None):
+        """init_solver (solver.f90:34-99, MF).  ``distance`` is the reference's ``distance`` procedure pointer; with
+        None the vof field is left zero (the reference prints an error): push ``vof`` and call
+        ``update_material_properties`` instead."""
+        G = self.G
+        fn = self._tramp(distance) if distance is not None else _lib.DISTANCE_FN(0)
+        check(G.lib.fen_gpu_init_solver_mf(G.ctx, fn, None, G.origin[0], G.origin[1]))
+        self.p = scalar(G, 1, "c", P)
+        self.phi = scalar(G, 1, "c", PHI)
+        self.rho = scalar(G, 1, "c", RHO)
+        self.mu = scalar(G, 1, "c", MU)
+        self.v = vector(G, 1, VX)
+        self.dv_o = vector(G, 0, DVOX)
+        self.S = vector(G, 0, SX)
+        self.p_hat = scalar(G, 1, "c", PHAT)
+        self.p_o = scalar(G, 1, "c", PO)
+        self._mf_fields()
+        self._ready = True
+        return self
+
+    def update_material_properties(self):
+        check(self.G.lib.fen_gpu_update_material_properties(self.G.ctx))

@@ -1134,8 +1134,12 @@ int poisson_init(fen_ctx* c) {
     const bool dctx = var[0] == 'n', dcty = g.ndim == 3 && var[1] == 'n';
     if (dctx && g.nranks > 1)
         return set_error(FEN_ERR_UNSUPPORTED, "Poisson variant %s (DCT in x) runs on one rank only for now", var);
-    if (!pow2(g.nx) || g.nx < 2 || g.nx > 2048 || !pow2(g.ny) || g.ny > 2048 ||
-        (g.ndim == 3 && (!pow2(g.nz) || g.nz > 2048)))
+    // the last direction of the *n variants is solved by the Thomas algorithm: any length (the reference has no
+    // restriction either); FFT / DCT directions are powers of two up to 2048
+    const bool thomas_last = var[g.ndim - 1] == 'n';
+    const bool y_fft = !(g.ndim == 2 && thomas_last), z_fft = g.ndim == 3 && !thomas_last;
+    if (!pow2(g.nx) || g.nx < 2 || g.nx > 2048 || (y_fft && (!pow2(g.ny) || g.ny > 2048)) ||
+        (z_fft && (!pow2(g.nz) || g.nz > 2048)))
         return set_error(FEN_ERR_UNSUPPORTED, "FFT sizes must be powers of two in 2..2048 (got %d %d %d)", g.nx,
                          g.ny, g.nz);
     if ((dctx && g.nx > 1024) || (dcty && g.ny > 1024))

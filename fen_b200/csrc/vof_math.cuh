@@ -1,8 +1,8 @@
 // vof_math.cuh -- per-cell arithmetic of FEN's MTHINC volume-of-fluid method (src/volume_of_fluid.f90, Ii et al.
 // JCP 2012) and of the two-phase momentum terms (src/navier_stokes.f90, -DMF branches), written once as
 // __host__ __device__ functions in the reference's operation order.  The kernels of multiphase.cu call them on the
-// device; tests/cpu/vof_math_host.cu calls the same functions from host loops so the transcription can be held against
-// the oracle without a GPU (tests/test_host_logic.py).
+// device; tests/cpu/vof_math_host.cpp calls the same functions from host loops so that the transcription can be checked
+// on a machine without a GPU (tests/test_vof_math_host.py).
 #pragma once
 #include <cmath>
 

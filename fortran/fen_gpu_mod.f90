@@ -19,6 +19,10 @@
 !>                                                                   src/poisson.f90:51-52,57,1456
 !>   halo_mod          update_halos(f, G, l)                         src/halo.f90:12
 !>   scalar / vector   update_ghost_nodes                            src/scalar.f90:223, src/vector.f90:82
+!>   -DMF builds (2-D): volume_of_fluid_mod  allocate_vof_fields, get_vof_from_distance, get_h_from_vof,
+!>                     advect_vof(v, dt), check_vof_integral         src/volume_of_fluid.f90:54,676,228,434,722
+!>                     multiphase_mod  update_material_properties    src/multiphase.f90:121
+!>                     init_solver with the MF wiring                src/solver.f90:87-98
 module fen_gpu_mod
 
     use, intrinsic :: iso_c_binding
@@ -34,6 +38,9 @@ module fen_gpu_mod
     integer(c_int), parameter :: FEN_VX = 4, FEN_VY = 5, FEN_VZ = 6
     integer(c_int), parameter :: FEN_DVOX = 10, FEN_DVOY = 11, FEN_DVOZ = 12
     integer(c_int), parameter :: FEN_SX = 16, FEN_SY = 17, FEN_SZ = 18
+    integer(c_int), parameter :: FEN_VOF = 19, FEN_H = 20, FEN_D = 21, FEN_CURV = 22
+    integer(c_int), parameter :: FEN_NORMX = 23, FEN_NORMY = 24, FEN_LX = 26, FEN_LY = 27
+    integer(c_int), parameter :: FEN_PHAT = 29, FEN_PO = 30
 
     type, bind(C) :: fen_grid_desc
         integer(c_int) :: nx, ny, nz
@@ -52,6 +59,17 @@ module fen_gpu_mod
         real(c_double) :: dt_visc, dt_conv
         integer(c_int) :: constant_CFL
     end type fen_ns_params
+
+    type, bind(C) :: fen_mf_params
+        real(c_double) :: rho_0, rho_1, mu_0, mu_1
+        real(c_double) :: sigma
+        real(c_double) :: beta
+        real(c_double) :: cut
+        integer(c_int) :: quadratic
+        integer(c_int) :: x_first
+        real(c_double) :: dt_surf
+        real(c_double) :: rhomin, irhomin
+    end type fen_mf_params
 
     !---------------------------------------------------------------------------------------------
     ! Part 1: the C ABI, one interface per function of include/fen_gpu.h
@@ -191,6 +209,62 @@ module fen_gpu_mod
             import :: c_int, c_ptr, c_double
             type(c_ptr), value :: ctx
             real(c_double), intent(out) :: maxdiv, maxCFL
+            integer(c_int) :: ierr
+        end function
+        ! ---- two-phase path (-DMF) ----
+        function fen_gpu_mf_get_params(ctx, p) bind(C, name='fen_gpu_mf_get_params') result(ierr)
+            import :: c_int, c_ptr, fen_mf_params
+            type(c_ptr), value :: ctx
+            type(fen_mf_params), intent(out) :: p
+            integer(c_int) :: ierr
+        end function
+        function fen_gpu_mf_set_params(ctx, p) bind(C, name='fen_gpu_mf_set_params') result(ierr)
+            import :: c_int, c_ptr, fen_mf_params
+            type(c_ptr), value :: ctx
+            type(fen_mf_params), intent(in) :: p
+            integer(c_int) :: ierr
+        end function
+        function fen_gpu_allocate_vof_fields(ctx) bind(C, name='fen_gpu_allocate_vof_fields') result(ierr)
+            import :: c_int, c_ptr
+            type(c_ptr), value :: ctx
+            integer(c_int) :: ierr
+        end function
+        function fen_gpu_get_vof_from_distance(ctx, fn, user, x0, y0) &
+                bind(C, name='fen_gpu_get_vof_from_distance') result(ierr)
+            import :: c_int, c_ptr, c_funptr, c_double
+            type(c_ptr), value :: ctx, user
+            type(c_funptr), value :: fn
+            real(c_double), value :: x0, y0
+            integer(c_int) :: ierr
+        end function
+        function fen_gpu_get_h_from_vof(ctx) bind(C, name='fen_gpu_get_h_from_vof') result(ierr)
+            import :: c_int, c_ptr
+            type(c_ptr), value :: ctx
+            integer(c_int) :: ierr
+        end function
+        function fen_gpu_advect_vof(ctx, vector_x, dt) bind(C, name='fen_gpu_advect_vof') result(ierr)
+            import :: c_int, c_ptr, c_double
+            type(c_ptr), value :: ctx
+            integer(c_int), value :: vector_x
+            real(c_double), value :: dt
+            integer(c_int) :: ierr
+        end function
+        function fen_gpu_check_vof_integral(ctx, i1, i2) bind(C, name='fen_gpu_check_vof_integral') result(ierr)
+            import :: c_int, c_ptr, c_double
+            type(c_ptr), value :: ctx
+            real(c_double), intent(out) :: i1, i2
+            integer(c_int) :: ierr
+        end function
+        function fen_gpu_update_material_properties(ctx) bind(C, name='fen_gpu_update_material_properties') result(ierr)
+            import :: c_int, c_ptr
+            type(c_ptr), value :: ctx
+            integer(c_int) :: ierr
+        end function
+        function fen_gpu_init_solver_mf(ctx, fn, user, x0, y0) bind(C, name='fen_gpu_init_solver_mf') result(ierr)
+            import :: c_int, c_ptr, c_funptr, c_double
+            type(c_ptr), value :: ctx, user
+            type(c_funptr), value :: fn
+            real(c_double), value :: x0, y0
             integer(c_int) :: ierr
         end function
     end interface
@@ -339,13 +413,87 @@ contains
     !> and Poisson variant.
     subroutine init_solver(comp_grid)
         use navier_stokes_mod, only : allocate_navier_stokes_fields
+#ifdef MF
+        use volume_of_fluid_mod, only : allocate_vof_fields
+        use multiphase_mod     , only : allocate_multiphase_fields
+#endif
         type(grid), intent(in) :: comp_grid
         call allocate_navier_stokes_fields(comp_grid)            ! host mirrors, navier_stokes.f90:752
         if (.not. c_associated(ctx)) call gpu_attach_grid(comp_grid)
         call gpu_push_params()
+#ifdef MF
+        ! solver.f90:83-98: host mirrors of the VoF / multiphase fields, then the device does the rest
+        call allocate_vof_fields(comp_grid)
+        call allocate_multiphase_fields(comp_grid)
+        call gpu_push_mf_params()
+        call gpu_check(fen_gpu_init_solver_mf(ctx, c_funloc(gpu_distance), c_null_ptr, &
+                                              comp_grid%origin(1), comp_grid%origin(2)), 'init_solver')
+        call gpu_pull_mf_params()                                ! rhomin, irhomin
+#else
         call gpu_check(fen_gpu_init_solver(ctx), 'init_solver')  ! device fields + init_poisson_solver
+#endif
         advance_solution => navier_stokes_solver
     end subroutine init_solver
+
+#ifdef MF
+    !> C-callable trampoline for the reference's `distance` procedure pointer (volume_of_fluid.f90:40-46)
+    function gpu_distance(user, x, y) bind(C) result(d)
+        use volume_of_fluid_mod, only : distance
+        type(c_ptr), value :: user
+        real(c_double), value :: x, y
+        real(c_double) :: d
+        d = distance(x, y)
+    end function gpu_distance
+
+    !> module variables of multiphase_mod / volume_of_fluid_mod -> device
+    subroutine gpu_push_mf_params()
+        use multiphase_mod     , only : rho_0, rho_1, mu_0, mu_1, sigma
+        use volume_of_fluid_mod, only : beta, cut, quadratic, x_first
+        type(fen_mf_params) :: p
+        call gpu_check(fen_gpu_mf_get_params(ctx, p), 'mf params')
+        p%rho_0 = rho_0; p%rho_1 = rho_1; p%mu_0 = mu_0; p%mu_1 = mu_1; p%sigma = sigma
+        p%beta = beta; p%cut = cut
+        p%quadratic = merge(1_c_int, 0_c_int, quadratic)
+        p%x_first = merge(1_c_int, 0_c_int, x_first)
+        call gpu_check(fen_gpu_mf_set_params(ctx, p), 'mf params')
+    end subroutine gpu_push_mf_params
+
+    subroutine gpu_pull_mf_params()
+        use multiphase_mod     , only : rhomin, irhomin
+        use navier_stokes_mod  , only : dt_surf
+        use volume_of_fluid_mod, only : x_first
+        type(fen_mf_params) :: p
+        call gpu_check(fen_gpu_mf_get_params(ctx, p), 'mf params')
+        rhomin = p%rhomin; irhomin = p%irhomin; dt_surf = p%dt_surf
+        x_first = p%x_first /= 0
+    end subroutine gpu_pull_mf_params
+
+    !> advect_vof(v, dt), volume_of_fluid.f90:434, for drivers that advect with their own velocity field
+    !> (test/small_test/volume_of_fluid/reversed/reversed.f90:63): vfield = device id of v%x
+    subroutine advect_vof(vfield, dt)
+        integer(c_int), intent(in) :: vfield
+        real(dp)      , intent(in) :: dt
+        call gpu_check(fen_gpu_advect_vof(ctx, vfield, dt), 'advect_vof')
+    end subroutine advect_vof
+
+    subroutine get_h_from_vof()
+        call gpu_check(fen_gpu_get_h_from_vof(ctx), 'get_h_from_vof')
+    end subroutine get_h_from_vof
+
+    subroutine check_vof_integral(int_phase_1, int_phase_2)
+        real(dp), intent(out) :: int_phase_1, int_phase_2
+        call gpu_check(fen_gpu_check_vof_integral(ctx, int_phase_1, int_phase_2), 'check_vof_integral')
+    end subroutine check_vof_integral
+
+    !> pull vof (and rho, mu for output) into the reference's host arrays
+    subroutine gpu_pull_vof()
+        use volume_of_fluid_mod, only : vof
+        use navier_stokes_mod  , only : rho, mu
+        call gpu_pull(vof, FEN_VOF)
+        call gpu_pull(rho, FEN_RHO)
+        call gpu_pull(mu, FEN_MU)
+    end subroutine gpu_pull_vof
+#endif
 
     !> push the initial condition and BC planes the driver wrote after init_solver
     subroutine gpu_push_state()

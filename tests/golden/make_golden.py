@@ -60,6 +60,43 @@ def poisson_case(name, n, bc, seed):
     print(name, ps.variant)
 
 
+def mf_case(name, Nx, Ny, sigma, steps):
+    """Two-phase wave (density ratio 850, gravity, optional surface tension): freezes the two-phase oracle
+    (oracle/fen_oracle_mf.py).  The initial vof, u, v are stored so that the GPU test needs no oracle."""
+    from oracle import fen_oracle_mf as mf
+    import math
+    Lx, Ly = 1.0, float(Ny) / Nx
+    G = fo.Grid(Nx, Ny, 1, Lx, Ly, Lx / Nx, bc=["Periodic", "Periodic", "Wall", "Wall"])
+    rho_0 = 1000.0
+    mu_0 = rho_0 * Lx * math.sqrt(mf.GRAVITY * Lx) / 1.0e4
+    ns = mf.MultiphaseNavierStokes(G, rho_0, rho_0 / 850.0, mu_0, mu_0 * 1.9e-2, sigma,
+                                   distance=lambda x, y: y - 0.05 * np.cos(2.0 * PI * x / Lx) - Ly / 2.0)
+    ns.g[1] = -mf.GRAVITY
+    i = np.arange(1, Nx + 1)[:, None]
+    j = np.arange(1, Ny + 1)[None, :]
+    d = G.delta
+    # init_velocity of viscous_decay.f90:104-131 (potential-flow wave, amplitude 0.05)
+    wn = 2.0 * PI / Lx
+    om = math.sqrt(mf.GRAVITY * wn)
+    F = ns.vof.sh
+    x, y = i * d, (j - 0.5) * d - Ly / 2.0
+    f = ((F(1, 0) + F()) * 0.5)[..., 0]
+    ns.v.x.I[..., 0] = (1.0 - f) * 0.05 * om * np.exp(wn * y) * np.cos(wn * x) - f * 0.05 * om * np.exp(-wn * y) * np.cos(wn * x)
+    x, y = (i - 0.5) * d, j * d - Ly / 2.0
+    f = ((F(0, 1) + F()) * 0.5)[..., 0]
+    ns.v.y.I[..., 0] = (1.0 - f) * 0.05 * om * np.exp(wn * y) * np.sin(wn * x) + f * 0.05 * om * np.exp(-wn * y) * np.sin(wn * x)
+    ns.v.update_ghost_nodes()
+    dt = 0.1 * ns.set_timestep(1.0)          # as the reference's driver does (viscous_decay.f90:56-57); dt_o stays
+    ins = {"vof0": ns.vof.f.copy(), "u0": ns.v.x.f.copy(), "v0": ns.v.y.f.copy(),
+           "props": np.array([ns.rho_0, ns.rho_1, ns.mu_0, ns.mu_1])}
+    for s in range(1, steps + 1):
+        ns.navier_stokes_solver(s, dt)
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), n=np.array([Nx, Ny]), sigma=sigma, steps=steps, dt=dt,
+                        u=ns.v.x.f.copy(), v=ns.v.y.f.copy(), p=ns.p.f.copy(), vof=ns.vof.f.copy(),
+                        rho=ns.rho.f.copy(), curv=ns.vf.curv.f.copy(), maxdiv=ns.maxdiv, maxCFL=ns.maxCFL, **ins)
+    print(name, "maxdiv %.3e maxCFL %.6f" % (ns.maxdiv, ns.maxCFL))
+
+
 if __name__ == "__main__":
     P6, P4 = ["Periodic"] * 6, ["Periodic"] * 4
     ns_case("ns_tgv3d_16_2steps", (16, 16, 16), P6, (2 * PI,) * 3, 0.01, fo.init_tgv3d, 1.0, 2, cfl=0.25)
@@ -70,3 +107,4 @@ if __name__ == "__main__":
     poisson_case("poisson_ppn_8x16x16", (8, 16, 16), P4 + ["Wall", "Wall"], 2)
     poisson_case("poisson_pp_32x16", (32, 16, 1), P4, 3)
     poisson_case("poisson_pn_16x32", (16, 32, 1), ["Periodic", "Periodic", "Wall", "Wall"], 4)
+    mf_case("mf_wave_16x32_3steps", 16, 32, 0.07, 3)

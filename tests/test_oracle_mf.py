@@ -1,0 +1,146 @@
+"""Pins oracle/fen_oracle_mf.py (the CPU restatement of FEN's two-phase path) before anything is compared with it.
+
+The reference holds ONE known-answer data set for this path: Prosperetti's analytic capillary-wave amplitude
+(test/small_test/multiphase/capillary_wave/prosperetti.csv; committed as tests/golden/prosperetti_capillary.npz by
+tests/golden/make_prosperetti.py).  Its post-processing (capillary_wave/postpro.py:92-101) takes the largest error of
+the maximum interface amplitude over ~80 snapshots and plots it against the guide lines 0.4/N and 4/N^2; the case is
+replayed here at N = 8, 16, 32.  The VoF-only tests of the reference are plot-only; their properties are asserted:
+phase-volume conservation and the return of the reversed-vortex drop (volume_of_fluid/reversed).
+"""
+import math
+import os
+
+import numpy as np
+import pytest
+
+from oracle import fen_oracle as fo
+from oracle import fen_oracle_mf as mf
+
+PI = fo.PI
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def capillary_error(Nx):
+    """capillary.f90 + postpro.py at one resolution; returns the L1 (max) amplitude error."""
+    pros = np.load(os.path.join(GOLD, "prosperetti_capillary.npz"))["curve"]
+    a, lam = 0.01, 1.0
+    wn = 2.0 * PI / lam
+    Ny = 3 * Nx
+    G = fo.Grid(Nx, Ny, 1, lam, 3.0 * lam, lam / Nx, x0=(0.0, -1.5 * lam, 0.0),
+                bc=["Periodic", "Periodic", "Wall", "Wall"])
+    dl = G.delta
+
+    def wave(x, y):                                       # capillary.f90:117-135
+        x1 = x - dl / 2.0; y1 = a * np.cos(wn * x1)
+        x2 = x + dl / 2.0; y2 = a * np.cos(wn * x2)
+        return -((x2 - x1) * (y1 - y) - (x1 - x) * (y2 - y1)) / np.sqrt((x2 - x1) ** 2 + (y2 - y1) ** 2)
+    ns = mf.MultiphaseNavierStokes(G, 1.0, 1.0, 0.0182571749236, 0.0182571749236, 1.0, distance=wave)
+    assert ns.poisson.variant == "pn"
+    dt = ns.set_timestep(1.0)
+    assert dt == ns.dt_surf                               # the capillary limit is the active one (:657-660)
+    Tmax = 25.0 / 11.1366559937
+    nprint = int(Tmax / 80 / dt)
+    omega0 = math.sqrt(1.0 * wn ** 3 / 2.0)
+    Y = G.y[1:Ny + 1]
+    t, step, L1 = 0.0, 0, 0.0
+    while t < Tmax:
+        step += 1
+        t += dt
+        ns.navier_stokes_solver(step, dt)
+        if step % nprint == 0:
+            vof = ns.vof.I[:, :, 0]
+            amp = np.array([np.interp(0.5, vof[i, :], Y) for i in range(Nx)])
+            L1 = max(L1, abs(np.abs(amp).max() - np.interp(t * omega0, pros[:, 0], pros[:, 1])))
+    assert abs(ns.maxdiv) < 1e-12
+    return L1
+
+
+def test_capillary_wave_converges_to_prosperetti():
+    errs = {N: capillary_error(N) for N in (8, 16, 32)}
+    for N, e in errs.items():
+        assert e < 0.4 / N, errs                          # below the N^-1 guide line of postpro.py:120
+    assert errs[32] < errs[16] < errs[8], errs
+    assert errs[32] < 0.15 * 0.01, errs                   # within 15 % of the initial amplitude at N = 32
+
+
+def _reversed(N, T):
+    G = fo.Grid(N, N, 1, PI, PI, PI / N)
+    vf = mf.VoF(G)
+    x0, y0, r = 0.5 * PI, 0.2 * (PI + 1.0), 0.2 * PI      # reversed.f90:100-113
+    vf.distance = lambda x, y: np.sqrt((x - x0) ** 2 + (y - y0) ** 2) - r
+    vf.get_vof_from_distance()
+    v = fo.Vector(G, 1)
+    i = np.arange(1, N + 1)[:, None]
+    j = np.arange(1, N + 1)[None, :]
+    d = G.delta
+    v.x.I[..., 0] = np.sin(i * d) * np.cos((j - 0.5) * d)  # reversed.f90:117-140
+    v.y.I[..., 0] = -np.cos((i - 0.5) * d) * np.sin(j * d)
+    v.update_ghost_nodes()
+    f0 = vf.vof.I.copy()
+    m0 = vf.check_vof_integral()
+    dt = 0.00125 * PI * 200 / N                            # the reference's CFL (reversed.f90:48 at N = 200)
+    nstep = int(T / dt)
+    for s in range(1, nstep + 1):
+        vf.advect_vof(v, dt)
+        if s == nstep // 2:
+            v.x.f *= -1.0
+            v.y.f *= -1.0
+            v.update_ghost_nodes()
+    m1 = vf.check_vof_integral()
+    return f0, vf, m0, m1, np.abs(vf.vof.I - f0).sum() * d * d / (PI * r * r)
+
+
+def test_reversed_vortex_conserves_and_returns():
+    f0, vf, m0, m1, e64 = _reversed(64, 2.0 * PI)
+    assert abs(m1[0] - m0[0]) < 1e-12 * m0[0] and abs(m1[1] - m0[1]) < 1e-12 * m0[1]
+    assert vf.vof.I.min() > -1e-6 and vf.vof.I.max() < 1.0 + 1e-6
+    _, _, _, _, e32 = _reversed(32, 2.0 * PI)
+    assert e64 < 0.03 and e64 < 0.7 * e32, (e32, e64)      # relative L1 shape error, shrinking with resolution
+
+
+def test_vof_assignment_resets_boundary_types():
+    """Hazard H13: `vof = vof1` (volume_of_fluid.f90:470) carries vof1's default boundary types."""
+    G = fo.Grid(16, 16, 1, 1.0, 1.0, 1.0 / 16, bc=["Wall"] * 4)
+    vf = mf.VoF(G)
+    assert all(vf.vof.bc_type[f] == 2 for f in fo.FACES[:4])
+    vf.distance = lambda x, y: np.sqrt((x - 0.5) ** 2 + (y - 0.5) ** 2) - 0.25
+    vf.get_vof_from_distance()
+    v = fo.Vector(G, 1)
+    vf.advect_vof(v, 0.01)
+    assert all(vf.vof.bc_type[f] == 0 for f in fo.FACES[:4])
+    assert all(vf.h.bc_type[f] == 2 for f in fo.FACES[:4])
+    assert vf.x_first is False
+
+
+def test_flat_interface_properties_and_timestep():
+    """update_material_properties (multiphase.f90:121-137) and the MF time-step limits (navier_stokes.f90:655-661)."""
+    G = fo.Grid(16, 32, 1, 1.0, 2.0, 1.0 / 16, bc=["Periodic", "Periodic", "Wall", "Wall"])
+    ns = mf.MultiphaseNavierStokes(G, 1000.0, 2.0, 1.0, 0.1, 0.5, distance=lambda x, y: y - 1.0)
+    assert ns.rhomin == 2.0 and ns.irhomin == 0.5
+    f = ns.vof.I
+    assert np.allclose(ns.rho.I, 2.0 * f + 1000.0 * (1.0 - f), rtol=0, atol=0)
+    assert np.array_equal(ns.rho.f[:, 0, :], ns.rho.f[:, 1, :])            # Neumann at the wall
+    dt = ns.set_timestep(1.0)
+    d = G.delta
+    assert ns.dt_visc == 0.125 * d * d * min(1000.0 / 1.0, 2.0 / 0.1)
+    assert ns.dt_surf == math.sqrt(0.5 * 1002.0 * d ** 3 / (PI * 0.5 + 1.0e-16))
+    assert dt == min(ns.dt_conv, ns.dt_visc, ns.dt_surf) and ns.dt_o == dt
+
+
+def test_oracle_reproduces_mf_golden():
+    g = np.load(os.path.join(GOLD, "mf_wave_16x32_3steps.npz"))
+    Nx, Ny = [int(x) for x in g["n"]]
+    G = fo.Grid(Nx, Ny, 1, 1.0, float(Ny) / Nx, 1.0 / Nx, bc=["Periodic", "Periodic", "Wall", "Wall"])
+    r0, r1, m0, m1 = [float(x) for x in g["props"]]
+    ns = mf.MultiphaseNavierStokes(G, r0, r1, m0, m1, float(g["sigma"]),
+                                   distance=lambda x, y: y - 0.05 * np.cos(2.0 * PI * x) - float(Ny) / Nx / 2.0)
+    ns.g[1] = -mf.GRAVITY
+    assert np.abs(ns.vof.f - g["vof0"]).max() < 1e-15
+    ns.v.x.f[...] = g["u0"]
+    ns.v.y.f[...] = g["v0"]
+    dt = 0.1 * ns.set_timestep(1.0)
+    assert dt == float(g["dt"])
+    for s in range(1, int(g["steps"]) + 1):
+        ns.navier_stokes_solver(s, dt)
+    for k, a in (("u", ns.v.x.f), ("v", ns.v.y.f), ("p", ns.p.f), ("vof", ns.vof.f), ("rho", ns.rho.f)):
+        assert np.linalg.norm((a - g[k]).ravel()) <= 1e-12 * np.linalg.norm(g[k].ravel()), k
