@@ -7,6 +7,7 @@
 // no collective, no gather.
 //   scalar%write / read          scalar.f90:428 / :400
 //   save_state / load_state      solver.f90:160 / :244   order: p, v_x, v_y, dv_o_x, dv_o_y, [v_z, dv_o_z]
+//                                                        two-phase build: + vof, rho, mu, p_o (:204-209, :288-297)
 //   save_fields                  solver.f90:103          cell-centred velocities (face_to_center, fields.f90:210) and p
 #include <fcntl.h>
 #include <sys/stat.h>
@@ -109,12 +110,13 @@ static int state_fields(fen_ctx* c, int* ids) {
     int n = 0;
     ids[n++] = FEN_P; ids[n++] = FEN_VX; ids[n++] = FEN_VY; ids[n++] = FEN_DVOX; ids[n++] = FEN_DVOY;
     if (c->g.ndim == 3) { ids[n++] = FEN_VZ; ids[n++] = FEN_DVOZ; }
+    if (mf_active(c)) { ids[n++] = FEN_VOF; ids[n++] = FEN_RHO; ids[n++] = FEN_MU; ids[n++] = FEN_PO; }   // solver.f90:204-209
     return n;
 }
 
 int fen_gpu_save_state(fen_ctx* c, const char* filename) {
     if (!c || !c->solver_init) return set_error(FEN_ERR_STATE, "init_solver has not been called");
-    int ids[8];
+    int ids[12];
     const int n = state_fields(c, ids);
     int fd = -1;
     IoBuf b;
@@ -126,7 +128,7 @@ int fen_gpu_save_state(fen_ctx* c, const char* filename) {
 
 int fen_gpu_load_state(fen_ctx* c, const char* filename) {
     if (!c || !c->solver_init) return set_error(FEN_ERR_STATE, "init_solver has not been called");
-    int ids[8];
+    int ids[12];
     const int n = state_fields(c, ids);
     int fd = -1;
     IoBuf b;
@@ -141,7 +143,13 @@ int fen_gpu_load_state(fen_ctx* c, const char* filename) {
     if (fd >= 0) close(fd);
     if (r != FEN_OK) return r;
     FEN_TRY(ghost_update(c, FEN_P, 1));                       // solver.f90:283-284
-    return ghost_update(c, FEN_VX, c->g.ndim);
+    FEN_TRY(ghost_update(c, FEN_VX, c->g.ndim));
+    if (mf_active(c)) {                                       // solver.f90:293-296
+        FEN_TRY(ghost_update(c, FEN_VOF, 1));
+        FEN_TRY(ghost_update(c, FEN_RHO, 2));
+        FEN_TRY(ghost_update(c, FEN_PO, 1));
+    }
+    return FEN_OK;
 }
 
 // save_fields(step): <dir>/vx_<step7>.raw, vy_, [vz_], p_  (solver.f90:103-156)
@@ -168,6 +176,10 @@ int fen_gpu_save_fields(fen_ctx* c, int step, const char* dir) {
     if (r == FEN_OK) {
         snprintf(path, sizeof(path), "%s/p_%07d.raw", dir, step);
         r = fen_gpu_scalar_write(c, FEN_P, path);
+    }
+    if (r == FEN_OK && mf_active(c)) {                        // solver.f90:145-148
+        snprintf(path, sizeof(path), "%s/vof_%07d.raw", dir, step);
+        r = fen_gpu_scalar_write(c, FEN_VOF, path);
     }
     fen_gpu_scalar_destroy(c, tmp);
     return r;

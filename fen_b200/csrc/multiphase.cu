@@ -350,6 +350,7 @@ int mf_predict(fen_ctx* c, double dt) {
     a.k.B = -0.5 * dt / c->prm.dt_o;                  // :158
     a.k.g0 = c->prm.g[0]; a.k.g1 = c->prm.g[1];
     a.k.sigma = m.sigma; a.k.irhomin = m.irhomin;
+    a.k.has_source = c->has_source ? 1 : 0;
     FEN_LAUNCH(c, "mf_pred", k_mf_pred<<<mf_grid(c->L), dim3(MTX, MTY), 0, c->stream>>>(a));
     FEN_CUDA(cudaGetLastError());
     for (int q = 0; q < 2; ++q) std::swap(c->fields[FEN_VX + q].d, c->vnew[q]);

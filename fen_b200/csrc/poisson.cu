@@ -844,6 +844,116 @@ __global__ void __launch_bounds__(128) k_thomas_bwd(TArgs g, ScArgs q) {
     }
 }
 
+// ---- Thomas for FEW, LONG systems (2-D pn / nn: only nx/2+1 systems of ny unknowns) -------------------------------
+// k_thomas_fwd/bwd give each system one thread; with ~1000 systems of 4096 unknowns that is 9 blocks whose threads
+// wait a full DRAM round trip every 8 rows (measured: 2.6 + 1.3 ms at 2048 x 4096, the bulk of the two-phase step).
+// Here a block is ONE warp owning 32 neighbouring kx (one 512-byte run of C and one 256-byte run of c1 per row), and
+// every thread streams its own column through a private shared-memory ring with cp.async, LPR - LPG rows (~86 KB per
+// warp) in flight, so that ~33 warps keep ~3 MB of loads outstanding.  Threads only read what they copied
+// themselves, so cp.async.wait_group is the only synchronisation.  The dependent chain of the forward sweep is cut
+// from (mul, sub, div) to (mul, sub, mul) by taking the reciprocal pivot from the c1 table: 1/den_l = c1_l / c_l.
+// That rounds differently from the reference's division by at most 1-2 ulp per row; the last row -- the one whose
+// pivot is exactly zero for the singular mode (hazard H5) -- keeps the reference's expression and its zero test.
+constexpr int LPG = 16, LPS = 8, LPR = LPG * LPS;
+struct LpSmem {
+    double2 c[LPR][32];
+    double k[LPR][32];
+};
+
+__device__ __forceinline__ void cp_async16(void* sdst, const void* gsrc) {
+    const unsigned sa = (unsigned)__cvta_generic_to_shared(sdst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async8(void* sdst, const void* gsrc) {
+    const unsigned sa = (unsigned)__cvta_generic_to_shared(sdst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(sa), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
+// BWD false: forward elimination (rows 1 .. n-2 pipelined, rows 0 and n-1 as in k_thomas_fwd);
+// BWD true : back substitution (rows n-2 .. 0) + mean removal on the (0, 0) line.
+template <bool BWD>
+__global__ void __launch_bounds__(32) k_thomas_lp(TArgs g, double cinv) {
+    extern __shared__ __align__(16) unsigned char lp_raw[];
+    LpSmem& s = *reinterpret_cast<LpSmem*>(lp_raw);
+    const int lane = threadIdx.x;
+    const bool active = blockIdx.x * 32 + lane < g.npc;
+    const int kx = active ? blockIdx.x * 32 + lane : g.npc - 1;     // idle lanes shadow the last column, never store
+    double2* C = g.C + kx;
+    const double* c1t = g.c1 + kx;
+    const long long sl = g.sl;
+    const int n = g.n;
+    const int m = BWD ? n - 1 : n - 2;                               // rows that go through the ring
+    const int ng = m > 0 ? (m + LPG - 1) / LPG : 0;
+    auto row_of = [&](int p) { return BWD ? n - 2 - p : p + 1; };
+    auto issue = [&](int gi) {
+        if (gi < ng) {
+#pragma unroll
+            for (int q = 0; q < LPG; ++q) {
+                const int p = gi * LPG + q;
+                if (p < m) {
+                    const long long o = sl * row_of(p);
+                    cp_async16(&s.c[p % LPR][lane], C + o);
+                    cp_async8(&s.k[p % LPR][lane], c1t + o);
+                }
+            }
+        }
+        cp_async_commit();
+    };
+    for (int gi = 0; gi < LPS - 1; ++gi) issue(gi);
+    const double lx = g.lx[kx];
+    double2 d;
+    double acc = 0.0;
+    if (!BWD) {
+        d = c_div(C[0], __dadd_rn(g.b[0], lx));                      // poisson.f90:351
+        if (active) C[0] = d;
+    } else {
+        d = C[sl * (n - 1)];                                          // :374 x(n) = d1(n)
+        acc = d.x;
+    }
+    for (int gi = 0; gi < ng; ++gi) {
+        issue(gi + LPS - 1);
+        cp_async_wait<LPS - 1>();
+#pragma unroll
+        for (int q = 0; q < LPG; ++q) {
+            const int p = gi * LPG + q;
+            if (p < m) {
+                const int l = row_of(p);
+                const double2 r = s.c[p % LPR][lane];
+                const double k = s.k[p % LPR][lane];
+                if (!BWD) {       // d1(j) = (rhs - a d1(j-1)) / den_j, den_j = c_j / c1_j                :358
+                    d = c_scale(c_sub_ad(r, g.a[l], d), __dmul_rn(k, cinv));
+                } else {          // x(j) = d1(j) - c1(j) x(j+1)                                           :376
+                    d = make_double2(__dsub_rn(r.x, __dmul_rn(k, d.x)), __dsub_rn(r.y, __dmul_rn(k, d.y)));
+                    acc += d.x;
+                }
+                if (active) C[sl * l] = d;
+            }
+        }
+    }
+    cp_async_wait<0>();
+    if (!BWD) {
+        if (n > 1) {   // last row with the reference's own pivot and exact-zero guard, :362-371
+            const int l = n - 1;
+            const double a = g.a[l];
+            const double fr = __dsub_rn(__dadd_rn(g.b[l], lx), __dmul_rn(a, c1t[sl * (l - 1)]));
+            const double2 r = C[sl * l];
+            if (fr != 0.0) d = c_div(c_sub_ad(r, a, d), fr);
+            else d = make_double2(0.0, 0.0);
+            if (active) C[sl * l] = d;
+        }
+    } else if (g.mean && blockIdx.x == 0) {
+        // mean(phi) = average of the (0, 0) spectral line (see k_thomas_bwd); the whole warp subtracts it
+        __syncwarp();
+        const double mean = __shfl_sync(0xffffffffu, acc, 0) / (double)n;
+        double2* C0 = g.C;
+        for (int l = lane; l < n; l += 32) C0[sl * l].x -= mean;
+    }
+}
+
 // =================================================================================================
 // host side
 // =================================================================================================
@@ -1230,6 +1340,34 @@ bool poisson_can_fuse_rhs(fen_ctx* c) {
     return !off && c->ps && c->ps->variant[0] == 'p' && c->g.ndim == 3 && c->uniform_props;
 }
 
+// Thomas along y of a 2-D problem (pn, nn): few long systems -> the warp-per-32-columns streaming kernels.
+// FEN_THOMAS_LP=0 selects the thread-per-system kernels (tuning / cross-check switch).
+static int thomas_2d(fen_ctx* c, const TArgs& t) {
+    static const bool lp = !getenv("FEN_THOMAS_LP") || atoi(getenv("FEN_THOMAS_LP")) != 0;
+    if (!lp) {
+        dim3 grid((t.npc + 127) / 128, 1), block(128);
+        ScArgs none;
+        memset(&none, 0, sizeof(none));
+        FEN_LAUNCH(c, "thomas_fwd", k_thomas_fwd<<<grid, block, 0, c->stream>>>(t));
+        FEN_LAUNCH(c, "thomas_bwd", k_thomas_bwd<false><<<grid, block, 0, c->stream>>>(t, none));
+        FEN_CUDA(cudaGetLastError());
+        return FEN_OK;
+    }
+    static bool attr_done = false;
+    if (!attr_done) {
+        FEN_CUDA(cudaFuncSetAttribute(k_thomas_lp<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LpSmem)));
+        FEN_CUDA(cudaFuncSetAttribute(k_thomas_lp<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LpSmem)));
+        attr_done = true;
+    }
+    const double d = c->g.delta;
+    const double cinv = 1.0 / (1.0 / (d * d));      // 1 / c_j, c_j = 1/delta**2 for every pipelined row (poisson.f90:219-232)
+    dim3 grid((t.npc + 31) / 32), block(32);
+    FEN_LAUNCH(c, "thomas_fwd", k_thomas_lp<false><<<grid, block, sizeof(LpSmem), c->stream>>>(t, cinv));
+    FEN_LAUNCH(c, "thomas_bwd", k_thomas_lp<true><<<grid, block, sizeof(LpSmem), c->stream>>>(t, cinv));
+    FEN_CUDA(cudaGetLastError());
+    return FEN_OK;
+}
+
 int poisson_solve(fen_ctx* c, double* f, bool fuse_rhs, double dt) {
     Poisson* p = c->ps;
     if (!p) return set_error(FEN_ERR_STATE, "solve_poisson before init_poisson_solver");
@@ -1275,10 +1413,14 @@ int poisson_solve(fen_ctx* c, double* f, bool fuse_rhs, double dt) {
             t.sl = (long long)p->PC * g.ny; t.so = p->PC; t.n = g.nz; t.nouter = g.ny; t.o0 = 0;
             t.lo = p->mwn_y; t.form2d = 0;
         }
-        dim3 tgrid((p->PC + 127) / 128, t.nouter), tblock(128);
-        FEN_LAUNCH(c, "thomas_fwd", k_thomas_fwd<<<tgrid, tblock, 0, c->stream>>>(t));
-        FEN_LAUNCH(c, "thomas_bwd", k_thomas_bwd<false><<<tgrid, tblock, 0, c->stream>>>(t, none));
-        FEN_CUDA(cudaGetLastError());
+        if (nn) {
+            FEN_TRY(thomas_2d(c, t));
+        } else {
+            dim3 tgrid((p->PC + 127) / 128, t.nouter), tblock(128);
+            FEN_LAUNCH(c, "thomas_fwd", k_thomas_fwd<<<tgrid, tblock, 0, c->stream>>>(t));
+            FEN_LAUNCH(c, "thomas_bwd", k_thomas_bwd<false><<<tgrid, tblock, 0, c->stream>>>(t, none));
+            FEN_CUDA(cudaGetLastError());
+        }
         if (!nn) {
             la.scale = 1.0;
             if (npn) FEN_TRY(dispatch_lines(c, g.ny, la, 1, p->PC, p->nzl));
@@ -1305,11 +1447,7 @@ int poisson_solve(fen_ctx* c, double* f, bool fuse_rhs, double dt) {
         TArgs t;
         t.C = p->C; t.c1 = p->c1; t.sl = p->PC; t.so = 0; t.n = g.ny; t.npc = p->PC; t.nouter = 1; t.o0 = 0;
         t.a = p->ta; t.b = p->tb; t.c = p->tc; t.lx = p->mwn_x; t.lo = nullptr; t.form2d = 1; t.mean = 1;
-        dim3 grid((p->PC + 127) / 128, 1), block(128);
-        ScArgs none;
-        memset(&none, 0, sizeof(none));
-        FEN_LAUNCH(c, "thomas_fwd", k_thomas_fwd<<<grid, block, 0, c->stream>>>(t));
-        FEN_LAUNCH(c, "thomas_bwd", k_thomas_bwd<false><<<grid, block, 0, c->stream>>>(t, none));
+        FEN_TRY(thomas_2d(c, t));
     } else {
         // y forward (poisson.f90:975-979 / :1080-1087); multi-rank: the result is stored straight into the
         // z-pencil arrays of the owning ranks (transpose_y_to_z, :982 / :1090)

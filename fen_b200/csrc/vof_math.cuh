@@ -28,6 +28,14 @@ FEN_HD VofRecon vof_norm(const double f[3][3], double delta, double idelta, doub
     const double fmm = f[0][0], f0m = f[0][1], fpm = f[0][2];
     const double fm0 = f[1][0], f00 = f[1][1], fp0 = f[1][2];
     const double fmp = f[2][0], f0p = f[2][1], fpp = f[2][2];
+    if (fmm == f00 && f0m == f00 && fpm == f00 && fm0 == f00 && fp0 == f00 && fmp == f00 && f0p == f00 && fpp == f00) {
+        // uniform patch (every cell away from the interface band): all eight corner gradients are exactly zero and
+        // the expressions below evaluate to exactly these values -- skip their 5 square roots and 10 divisions
+        VofRecon z;
+        z.nx = 0.0; z.ny = 0.0; z.lx = 0.0; z.ly = 0.0;
+        z.curv = -(z.lx + z.ly) * idelta2;
+        return z;
+    }
     double mx[4], my[4];
     mx[0] = 0.5 * (f0m + f00 - fmm - fm0) * idelta;      // i-1/2, j-1/2
     mx[1] = 0.5 * (f00 + f0p - fm0 - fmp) * idelta;      // i-1/2, j+1/2
@@ -193,6 +201,7 @@ struct MfCell {
 };
 struct MfPrm {
     double id, dt, A, B, g0, g1, sigma, irhomin;
+    int has_source;                     // S was written by the caller (it is identically zero otherwise)
 };
 FEN_HD void mf_predict_cell(const MfCell& q, const MfPrm& k, double& un, double& vn, double& dvx, double& dvy) {
     const double rfx = 0.5 * (q.rhoip + q.rho0);                                  // center_to_face, fields.f90:197-198
@@ -202,10 +211,14 @@ FEN_HD void mf_predict_cell(const MfCell& q, const MfPrm& k, double& un, double&
     mf_stress_div(q.m, q.u, q.v, k.id, sdx, sdy);
     dvx = dvx + sdx / rfx;                                                        // :430
     dvy = dvy + sdy / rfy;                                                        // :442
-    dvx = dvx + k.sigma * 0.5 * (q.cip + q.c0) * (q.fip - q.f0) * k.id / rfx;    // :486-487
-    dvy = dvy + k.sigma * 0.5 * (q.cjp + q.c0) * (q.fjp - q.f0) * k.id / rfy;    // :488-489
-    dvx = dvx + q.sx / rfx;                                                       // :248-249
-    dvy = dvy + q.sy / rfy;
+    if (k.sigma != 0.0) {             // the term is an exact zero otherwise
+        dvx = dvx + k.sigma * 0.5 * (q.cip + q.c0) * (q.fip - q.f0) * k.id / rfx;    // :486-487
+        dvy = dvy + k.sigma * 0.5 * (q.cjp + q.c0) * (q.fjp - q.f0) * k.id / rfy;    // :488-489
+    }
+    if (k.has_source) {
+        dvx = dvx + q.sx / rfx;                                                   // :248-249
+        dvy = dvy + q.sy / rfy;
+    }
     const double gx = (q.pip - q.p0) * k.id, gy = (q.pjp - q.p0) * k.id;          // gradient(p), fields.f90:55-56
     const double hx = (q.hip - q.h0) * k.id, hy = (q.hjp - q.h0) * k.id;          // gradient(p_hat)
     double rx = -gx / rfx + k.A * dvx + k.B * q.dvox + k.g0;                      // :169

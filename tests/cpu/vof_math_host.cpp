@@ -59,7 +59,7 @@ void host_predict(int nx, int ny, const double* u, const double* v, const double
                   const double* sy, const double* dvox, const double* dvoy, double id, double dt, double A, double B,
                   double g0, double g1, double sigma, double irhomin, double* un, double* vn, double* odvx,
                   double* odvy) {
-    MfPrm k{id, dt, A, B, g0, g1, sigma, irhomin};
+    MfPrm k{id, dt, A, B, g0, g1, sigma, irhomin, 1};
     for (int j = 1; j <= ny; ++j)
         for (int i = 1; i <= nx; ++i) {
             MfCell q;
