@@ -35,7 +35,7 @@ struct ReconArgs {
     int quadratic;
 };
 
-__global__ void __launch_bounds__(MTX* MTY) k_vof_recon(ReconArgs a) {
+__global__ void __launch_bounds__(MTX* MTY, 4) k_vof_recon(ReconArgs a) {
     const int i = blockIdx.x * MTX + threadIdx.x + 1;
     const int j = blockIdx.y * MTY + threadIdx.y + 1;
     if (i > a.L.nx || j > a.L.ny) return;
@@ -138,7 +138,7 @@ struct MfPredArgs {
     double *dvox, *dvoy, *un, *vn;
     MfPrm k;
 };
-__global__ void __launch_bounds__(MTX* MTY) k_mf_pred(MfPredArgs a) {
+__global__ void __launch_bounds__(MTX* MTY, 4) k_mf_pred(MfPredArgs a) {
     const int i = blockIdx.x * MTX + threadIdx.x + 1;
     const int j = blockIdx.y * MTY + threadIdx.y + 1;
     if (i > a.L.nx || j > a.L.ny) return;

@@ -875,8 +875,11 @@ template <int N> __device__ __forceinline__ void cp_async_wait() {
 
 // BWD false: forward elimination (rows 1 .. n-2 pipelined, rows 0 and n-1 as in k_thomas_fwd);
 // BWD true : back substitution (rows n-2 .. 0) + mean removal on the (0, 0) line.
+// A warp is alone on its SM, so nothing hides a stall: full groups of LPG rows take a branch-free path that first
+// pulls the whole group from shared memory into registers, then runs the dependent chain (2 fp64 operations per row
+// backward, 3 forward), then stores; only the last, partial group goes row by row.
 template <bool BWD>
-__global__ void __launch_bounds__(32) k_thomas_lp(TArgs g, double cinv) {
+__global__ void __launch_bounds__(32) k_thomas_lp(TArgs g, double cinv, double amid) {
     extern __shared__ __align__(16) unsigned char lp_raw[];
     LpSmem& s = *reinterpret_cast<LpSmem*>(lp_raw);
     const int lane = threadIdx.x;
@@ -888,16 +891,23 @@ __global__ void __launch_bounds__(32) k_thomas_lp(TArgs g, double cinv) {
     const int n = g.n;
     const int m = BWD ? n - 1 : n - 2;                               // rows that go through the ring
     const int ng = m > 0 ? (m + LPG - 1) / LPG : 0;
-    auto row_of = [&](int p) { return BWD ? n - 2 - p : p + 1; };
+    const long long step = BWD ? -sl : sl;                           // row p lives at (first + p * step)
+    const long long first = BWD ? sl * (n - 2) : sl;
     auto issue = [&](int gi) {
         if (gi < ng) {
+            const int p0 = gi * LPG;
+            const double2* gc = C + first + step * p0;
+            const double* gk = c1t + first + step * p0;
+            if (p0 + LPG <= m) {
 #pragma unroll
-            for (int q = 0; q < LPG; ++q) {
-                const int p = gi * LPG + q;
-                if (p < m) {
-                    const long long o = sl * row_of(p);
-                    cp_async16(&s.c[p % LPR][lane], C + o);
-                    cp_async8(&s.k[p % LPR][lane], c1t + o);
+                for (int q = 0; q < LPG; ++q) {
+                    cp_async16(&s.c[(p0 + q) % LPR][lane], gc + step * q);
+                    cp_async8(&s.k[(p0 + q) % LPR][lane], gk + step * q);
+                }
+            } else {
+                for (int q = 0; p0 + q < m; ++q) {
+                    cp_async16(&s.c[(p0 + q) % LPR][lane], gc + step * q);
+                    cp_async8(&s.k[(p0 + q) % LPR][lane], gk + step * q);
                 }
             }
         }
@@ -917,20 +927,42 @@ __global__ void __launch_bounds__(32) k_thomas_lp(TArgs g, double cinv) {
     for (int gi = 0; gi < ng; ++gi) {
         issue(gi + LPS - 1);
         cp_async_wait<LPS - 1>();
+        const int p0 = gi * LPG;
+        double2* out = C + first + step * p0;
+        if (p0 + LPG <= m) {
+            double2 r[LPG];
+            double k[LPG];
 #pragma unroll
-        for (int q = 0; q < LPG; ++q) {
-            const int p = gi * LPG + q;
-            if (p < m) {
-                const int l = row_of(p);
-                const double2 r = s.c[p % LPR][lane];
-                const double k = s.k[p % LPR][lane];
-                if (!BWD) {       // d1(j) = (rhs - a d1(j-1)) / den_j, den_j = c_j / c1_j                :358
-                    d = c_scale(c_sub_ad(r, g.a[l], d), __dmul_rn(k, cinv));
+            for (int q = 0; q < LPG; ++q) {
+                r[q] = s.c[(p0 + q) % LPR][lane];
+                k[q] = s.k[(p0 + q) % LPR][lane];
+                if (!BWD) k[q] = __dmul_rn(k[q], cinv);              // 1/den_j = c1_j / c_j, off the dependent chain
+            }
+#pragma unroll
+            for (int q = 0; q < LPG; ++q) {
+                if (!BWD) {       // d1(j) = (rhs - a d1(j-1)) / den_j                                     :358
+                    d = c_scale(c_sub_ad(r[q], amid, d), k[q]);
                 } else {          // x(j) = d1(j) - c1(j) x(j+1)                                           :376
+                    d = make_double2(__dsub_rn(r[q].x, __dmul_rn(k[q], d.x)), __dsub_rn(r[q].y, __dmul_rn(k[q], d.y)));
+                    acc += d.x;
+                }
+                r[q] = d;
+            }
+            if (active) {
+#pragma unroll
+                for (int q = 0; q < LPG; ++q) out[step * q] = r[q];
+            }
+        } else {
+            for (int q = 0; p0 + q < m; ++q) {
+                const double2 r = s.c[(p0 + q) % LPR][lane];
+                const double k = s.k[(p0 + q) % LPR][lane];
+                if (!BWD) {
+                    d = c_scale(c_sub_ad(r, amid, d), __dmul_rn(k, cinv));
+                } else {
                     d = make_double2(__dsub_rn(r.x, __dmul_rn(k, d.x)), __dsub_rn(r.y, __dmul_rn(k, d.y)));
                     acc += d.x;
                 }
-                if (active) C[sl * l] = d;
+                if (active) out[step * q] = d;
             }
         }
     }
@@ -949,9 +981,36 @@ __global__ void __launch_bounds__(32) k_thomas_lp(TArgs g, double cinv) {
         // mean(phi) = average of the (0, 0) spectral line (see k_thomas_bwd); the whole warp subtracts it
         __syncwarp();
         const double mean = __shfl_sync(0xffffffffu, acc, 0) / (double)n;
-        double2* C0 = g.C;
-        for (int l = lane; l < n; l += 32) C0[sl * l].x -= mean;
+        double* C0 = reinterpret_cast<double*>(g.C);
+        for (int l0 = lane; l0 < n; l0 += 32 * 8) {
+            double v[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q)
+                if (l0 + 32 * q < n) v[q] = C0[2 * sl * (l0 + 32 * q)];
+#pragma unroll
+            for (int q = 0; q < 8; ++q)
+                if (l0 + 32 * q < n) C0[2 * sl * (l0 + 32 * q)] = v[q] - mean;
+        }
     }
+}
+
+// z-pencil -> y-slab transpose (transpose_z_to_y, poisson.f90:1138) after the Thomas back substitution, as its own
+// kernel.  The back substitution walks z from the top plane down in every system at once, so when its stores go
+// straight to the owning ranks (k_thomas_bwd<true>) ALL ranks write to the SAME destination at any moment: the
+// receiver's NVLink ingress is shared by P-1 senders (measured at 8 GPUs: 261 GB/s per GPU against 654 GB/s for the
+// forward transpose, whose FFT epilogue spreads its stores over all destinations).  Here the substitution stays in
+// local HBM and this kernel copies rows of PC complex values with consecutive blocks cycling over the destination
+// ranks, starting one past the sender -- every link of the switch is busy all the time, for one extra local read of
+// the spectral array (16 B/cell against the 8 x slower link).
+__global__ void __launch_bounds__(256) k_a2a_scatter(const double2* __restrict__ Z, long long slz, int PC, int P,
+                                                     int rank, int nzl, ScArgs q) {
+    const int bx = blockIdx.x;                       // 0 .. P * nzl - 1
+    const int dest = (rank + 1 + bx % P) % P;
+    const int z = dest * nzl + bx / P;               // global z plane, owned by `dest`
+    const int o = blockIdx.y;                        // local y index of this rank's z-pencil
+    const double2* src = Z + slz * z + (long long)PC * o;
+    double2* dst = sc_dst(q, 0, z, o);
+    for (int kx = threadIdx.x; kx < PC; kx += blockDim.x) dst[kx] = src[kx];
 }
 
 // =================================================================================================
@@ -1362,8 +1421,9 @@ static int thomas_2d(fen_ctx* c, const TArgs& t) {
     const double d = c->g.delta;
     const double cinv = 1.0 / (1.0 / (d * d));      // 1 / c_j, c_j = 1/delta**2 for every pipelined row (poisson.f90:219-232)
     dim3 grid((t.npc + 31) / 32), block(32);
-    FEN_LAUNCH(c, "thomas_fwd", k_thomas_lp<false><<<grid, block, sizeof(LpSmem), c->stream>>>(t, cinv));
-    FEN_LAUNCH(c, "thomas_bwd", k_thomas_lp<true><<<grid, block, sizeof(LpSmem), c->stream>>>(t, cinv));
+    const double amid = 1.0 / (d * d);              // a_j of every row but the first (:219-232)
+    FEN_LAUNCH(c, "thomas_fwd", k_thomas_lp<false><<<grid, block, sizeof(LpSmem), c->stream>>>(t, cinv, amid));
+    FEN_LAUNCH(c, "thomas_bwd", k_thomas_lp<true><<<grid, block, sizeof(LpSmem), c->stream>>>(t, cinv, amid));
     FEN_CUDA(cudaGetLastError());
     return FEN_OK;
 }
@@ -1478,8 +1538,16 @@ int poisson_solve(fen_ctx* c, double* f, bool fuse_rhs, double dt) {
             t.a = p->ta; t.b = p->tb; t.c = p->tc; t.lx = p->mwn_x; t.lo = p->mwn_y; t.form2d = 0; t.mean = 1;
             dim3 grid((p->PC + 127) / 128, p->nyl), block(128);
             FEN_LAUNCH(c, "thomas_fwd", k_thomas_fwd<<<grid, block, 0, c->stream>>>(t));
-            if (multi) FEN_LAUNCH(c, "thomas_bwd_a2a", k_thomas_bwd<true><<<grid, block, 0, c->stream>>>(t, sb));
-            else FEN_LAUNCH(c, "thomas_bwd", k_thomas_bwd<false><<<grid, block, 0, c->stream>>>(t, sb));
+            // FEN_THOMAS_FUSED_A2A=1: the back substitution stores straight to the peers (kept for A/B measurements)
+            static const bool fused_a2a = getenv("FEN_THOMAS_FUSED_A2A") && atoi(getenv("FEN_THOMAS_FUSED_A2A")) != 0;
+            if (multi && fused_a2a) {
+                FEN_LAUNCH(c, "thomas_bwd_a2a", k_thomas_bwd<true><<<grid, block, 0, c->stream>>>(t, sb));
+            } else {
+                FEN_LAUNCH(c, "thomas_bwd", k_thomas_bwd<false><<<grid, block, 0, c->stream>>>(t, sb));
+                if (multi)
+                    FEN_LAUNCH(c, "a2a_scatter", k_a2a_scatter<<<dim3(g.nz, p->nyl), 256, 0, c->stream>>>(
+                                                     Z, slz, p->PC, g.nranks, g.rank, p->nzl, sb));
+            }
         }
         FEN_CUDA(cudaGetLastError());
         if (multi) FEN_TRY(comm_transpose_bwd(c));             // transpose_z_to_y (:1015 / :1138)
