@@ -61,6 +61,8 @@ SIGNATURES = {
     "fen_gpu_scalar_destroy": (_I, [_P, _I]),
     "fen_gpu_push": (_I, [_P, _I, _P, _I]),
     "fen_gpu_pull": (_I, [_P, _I, _P, _I]),
+    "fen_gpu_pull_async": (_I, [_P, _I, _P, _I]),
+    "fen_gpu_pull_wait": (_I, [_P]),
     "fen_gpu_set_to_value": (_I, [_P, _I, _D]),
     "fen_gpu_set_bc_type": (_I, [_P, _I, _I, _I]),
     "fen_gpu_get_bc_type": (_I, [_P, _I, _I, _PI]),

@@ -95,6 +95,9 @@ class grid:
     def synchronize(self):
         check(self.lib.fen_gpu_synchronize(self.ctx))
 
+    def pull_wait(self):
+        check(self.lib.fen_gpu_pull_wait(self.ctx))
+
     def destroy(self):
         if self.ctx is not None:
             self.lib.fen_gpu_destroy(self.ctx)
@@ -142,6 +145,11 @@ class scalar:
 
     def pull(self):
         check(self.G.lib.fen_gpu_pull(self.G.ctx, self.id, self.f.ctypes.data_as(C.c_void_p), self.gl))
+        return self
+
+    def pull_async(self):
+        """pull() that does not wait: ``f`` is valid after ``G.pull_wait()`` / ``G.synchronize()``."""
+        check(self.G.lib.fen_gpu_pull_async(self.G.ctx, self.id, self.f.ctypes.data_as(C.c_void_p), self.gl))
         return self
 
     def setToValue(self, val):

@@ -76,12 +76,18 @@ __attribute__((constructor)) static void fen_request_eager_loading() { setenv("C
 static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 int spectral_pitch(int nx) { return ((nx / 2 + 1) + 7) / 8 * 8; }
+// complex row pitch of the Poisson work arrays of this grid: the half spectrum when x is periodic (r2c), the full
+// width when x is a Neumann direction (the DCT variants carry real data in a full-width complex array)
+int spectral_pitch_grid(const fen_grid_desc& g) {
+    const bool perx = g.bc[0] == FEN_BC_PERIODIC && g.bc[1] == FEN_BC_PERIODIC;
+    return perx ? spectral_pitch(g.nx) : (g.nx + 7) / 8 * 8;
+}
 
 static void comm_layout(fen_ctx* c, Comm* m) {
     const Layout& L = c->L;
     const int P = c->g.nranks;
     m->plane = (size_t)L.sz;
-    const int PC = spectral_pitch(c->g.nx);
+    const int PC = spectral_pitch_grid(c->g);
     m->nC = (size_t)PC * c->g.ny * L.nzl;
     m->nCz = (size_t)PC * (c->g.ny / P) * c->g.nz;
     size_t o = 0;

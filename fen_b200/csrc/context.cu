@@ -80,6 +80,7 @@ static int fill_async(fen_ctx* c, double* d, double val) {
 void free_field(Field& f) {
     if (f.d) cudaFree(f.d);
     f.d = nullptr;
+    f.pull_event = nullptr;
     for (int q = 0; q < 6; ++q) {
         if (f.bc_plane[q]) cudaFree(f.bc_plane[q]);
         f.bc_plane[q] = nullptr;
@@ -129,6 +130,9 @@ static int copy_field(fen_ctx* c, Field& f, double* host, int gl, bool to_device
     }
     dim3 grid((hx + 255) / 256, hy, hz), block(256);
     if (to_device) {
+        // an asynchronous pull of this field may still be reading it / writing the same host array
+        if (f.pull_event) FEN_CUDA(cudaStreamWaitEvent(c->stream, f.pull_event, 0));
+        f.pull_event = nullptr;
         FEN_CUDA(cudaMemcpyAsync(c->stage, host, n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
         FEN_LAUNCH(c, "repitch", k_repitch<true><<<grid, block, 0, c->stream>>>(f.d, c->stage, L, gl, hx, hy, hz));
     } else {
@@ -136,6 +140,38 @@ static int copy_field(fen_ctx* c, Field& f, double* host, int gl, bool to_device
         FEN_CUDA(cudaMemcpyAsync(host, c->stage, n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     }
     FEN_CUDA(cudaGetLastError());
+    return FEN_OK;
+}
+
+// device -> host without blocking the compute stream: repitch into one of four staging buffers on the compute stream,
+// copy out on the d2h stream.  The host array is valid after fen_gpu_pull_wait / fen_gpu_synchronize; a later push
+// of the same field waits for the copy on the device side (copy_field).
+static int pull_field_async(fen_ctx* c, Field& f, double* host, int gl) {
+    if (gl != 0 && gl != 1) return set_error(FEN_ERR_ARG, "host ghost level must be 0 or 1 (got %d)", gl);
+    const Layout& L = c->L;
+    const int hx = L.nx + 2 * gl, hy = L.ny + 2 * gl, hz = L.nzl + 2 * gl;
+    const size_t n = (size_t)hx * hy * hz;
+    if (!c->d2h) {
+        FEN_CUDA(cudaStreamCreateWithFlags(&c->d2h, cudaStreamNonBlocking));
+        const size_t cap = (size_t)(L.nx + 2) * (L.ny + 2) * (L.nzl + 2);
+        for (int b = 0; b < 4; ++b) {
+            FEN_CUDA(cudaMalloc(&c->stage_out[b], cap * sizeof(double)));
+            FEN_CUDA(cudaEventCreateWithFlags(&c->ev_ready[b], cudaEventDisableTiming));
+            FEN_CUDA(cudaEventCreateWithFlags(&c->ev_free[b], cudaEventDisableTiming));
+        }
+    }
+    const int b = c->out_next;
+    c->out_next = (b + 1) % 4;
+    if (c->ev_free_set[b]) FEN_CUDA(cudaStreamWaitEvent(c->stream, c->ev_free[b], 0));   // its previous copy is out
+    dim3 grid((hx + 255) / 256, hy, hz), block(256);
+    FEN_LAUNCH(c, "repitch", k_repitch<false><<<grid, block, 0, c->stream>>>(f.d, c->stage_out[b], L, gl, hx, hy, hz));
+    FEN_CUDA(cudaGetLastError());
+    FEN_CUDA(cudaEventRecord(c->ev_ready[b], c->stream));
+    FEN_CUDA(cudaStreamWaitEvent(c->d2h, c->ev_ready[b], 0));
+    FEN_CUDA(cudaMemcpyAsync(host, c->stage_out[b], n * sizeof(double), cudaMemcpyDeviceToHost, c->d2h));
+    FEN_CUDA(cudaEventRecord(c->ev_free[b], c->d2h));
+    c->ev_free_set[b] = true;
+    f.pull_event = c->ev_free[b];
     return FEN_OK;
 }
 
@@ -252,6 +288,15 @@ int fen_gpu_destroy(fen_ctx* c) {
     for (int m = 0; m < 3; ++m) if (c->vnew[m]) cudaFree(c->vnew[m]);
     if (c->d_red) cudaFree(c->d_red);
     if (c->stage) cudaFree(c->stage);
+    if (c->d2h) {
+        cudaStreamSynchronize(c->d2h);
+        for (int b = 0; b < 4; ++b) {
+            if (c->stage_out[b]) cudaFree(c->stage_out[b]);
+            if (c->ev_ready[b]) cudaEventDestroy(c->ev_ready[b]);
+            if (c->ev_free[b]) cudaEventDestroy(c->ev_free[b]);
+        }
+        cudaStreamDestroy(c->d2h);
+    }
     if (c->h_red) cudaFreeHost(c->h_red);
     for (auto& e : c->prof_entries) { cudaEventDestroy(e.e0); cudaEventDestroy(e.e1); }
     cudaStreamDestroy(c->stream);
@@ -263,6 +308,7 @@ int fen_gpu_synchronize(fen_ctx* c) {
     if (!c) return set_error(FEN_ERR_ARG, "null context");
     FEN_CUDA(cudaSetDevice(c->device));
     FEN_CUDA(cudaStreamSynchronize(c->stream));
+    if (c->d2h) FEN_CUDA(cudaStreamSynchronize(c->d2h));
     return comm_check(c);
 }
 
@@ -326,6 +372,20 @@ int fen_gpu_pull(fen_ctx* c, int id, double* host, int gl) {
     if (!host) return set_error(FEN_ERR_ARG, "null host pointer");
     FEN_TRY(copy_field(c, *f, host, gl, false));
     FEN_CUDA(cudaStreamSynchronize(c->stream));
+    return comm_check(c);
+}
+
+int fen_gpu_pull_async(fen_ctx* c, int id, double* host, int gl) {
+    Field* f;
+    FEN_TRY(field_check(c, id, &f));
+    if (!host) return set_error(FEN_ERR_ARG, "null host pointer");
+    return pull_field_async(c, *f, host, gl);
+}
+
+int fen_gpu_pull_wait(fen_ctx* c) {
+    if (!c) return set_error(FEN_ERR_ARG, "null context");
+    FEN_CUDA(cudaSetDevice(c->device));
+    if (c->d2h) FEN_CUDA(cudaStreamSynchronize(c->d2h));
     return comm_check(c);
 }
 

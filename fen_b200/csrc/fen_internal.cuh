@@ -45,6 +45,7 @@ struct Field {
     int bc_mode[6] = {0, 0, 0, 0, 0, 0};
     double bc_value[6] = {0, 0, 0, 0, 0, 0};
     double* bc_plane[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t pull_event = nullptr;   // fen_gpu_pull_async: the host copy of this field is still in flight until it fires
 };
 
 struct ProfEntry {
@@ -97,6 +98,14 @@ struct fen_ctx {
     double maxdiv = 0.0, maxCFL = 0.0;
     double last_dt = 0.0;
     double* stage = nullptr;     // contiguous staging buffer of push / pull (context.cu: copy_field)
+    // fen_gpu_pull_async: device-to-host copies on their own stream, four staging buffers in rotation, so that the
+    // download of one field overlaps the repitch of the next and -- PCIe being full duplex -- later uploads
+    cudaStream_t d2h = nullptr;
+    double* stage_out[4] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t ev_ready[4] = {nullptr, nullptr, nullptr, nullptr};   // repitch into stage_out[b] done (compute stream)
+    cudaEvent_t ev_free[4] = {nullptr, nullptr, nullptr, nullptr};    // host copy out of stage_out[b] done (d2h stream)
+    bool ev_free_set[4] = {false, false, false, false};
+    int out_next = 0;
     double* d_red = nullptr;     // device scratch for reductions (partials + results)
     double* h_red = nullptr;     // pinned host mirror of the results
     int red_blocks = 0;
@@ -163,6 +172,7 @@ int comm_transpose_bwd(fen_ctx* c);   // completes the z-pencil -> y-slab transp
 int comm_spectral(fen_ctx* c, double2** peerC, double2** peerCz);   // mapped spectral arrays of all ranks
 int comm_check(fen_ctx* c);           // FEN_ERR_COMM if a peer wait timed out (call after a stream sync)
 int spectral_pitch(int nx);           // complex row pitch of the half-spectrum arrays
+int spectral_pitch_grid(const fen_grid_desc& g);   // ... of this grid's Poisson variant (full width for DCT in x)
 // stencil.cu
 int ns_predict(fen_ctx* c, double dt);
 int ns_poisson_rhs(fen_ctx* c, double dt);

@@ -1002,15 +1002,17 @@ __global__ void __launch_bounds__(32) k_thomas_lp(TArgs g, double cinv, double a
 // local HBM and this kernel copies rows of PC complex values with consecutive blocks cycling over the destination
 // ranks, starting one past the sender -- every link of the switch is busy all the time, for one extra local read of
 // the spectral array (16 B/cell against the 8 x slower link).
-__global__ void __launch_bounds__(256) k_a2a_scatter(const double2* __restrict__ Z, long long slz, int PC, int P,
-                                                     int rank, int nzl, ScArgs q) {
-    const int bx = blockIdx.x;                       // 0 .. P * nzl - 1
+__global__ void __launch_bounds__(256) k_a2a_scatter(const double2* __restrict__ src, long long s_idx,
+                                                     long long s_outer, int PC, int P, int rank, int blk, ScArgs q) {
+    // rows (idx, outer) of PC complex values; idx is the transposed index, owned by rank idx / blk.  The same kernel
+    // does transpose_y_to_z (idx = j, blk = ny / P) for the variants whose y pass has no fused epilogue.
+    const int bx = blockIdx.x;                       // 0 .. P * blk - 1
     const int dest = (rank + 1 + bx % P) % P;
-    const int z = dest * nzl + bx / P;               // global z plane, owned by `dest`
-    const int o = blockIdx.y;                        // local y index of this rank's z-pencil
-    const double2* src = Z + slz * z + (long long)PC * o;
-    double2* dst = sc_dst(q, 0, z, o);
-    for (int kx = threadIdx.x; kx < PC; kx += blockDim.x) dst[kx] = src[kx];
+    const int idx = dest * blk + bx / P;
+    const int o = blockIdx.y;
+    const double2* s = src + s_idx * idx + s_outer * o;
+    double2* dst = sc_dst(q, 0, idx, o);
+    for (int kx = threadIdx.x; kx < PC; kx += blockDim.x) dst[kx] = s[kx];
 }
 
 // =================================================================================================
@@ -1301,8 +1303,6 @@ int poisson_init(fen_ctx* c) {
         return set_error(FEN_ERR_UNSUPPORTED, "Unable to find the proper poisson solver with the selected "
                                               "boundary conditions");          // poisson.f90:91-95
     const bool dctx = var[0] == 'n', dcty = g.ndim == 3 && var[1] == 'n';
-    if (dctx && g.nranks > 1)
-        return set_error(FEN_ERR_UNSUPPORTED, "Poisson variant %s (DCT in x) runs on one rank only for now", var);
     // the last direction of the *n variants is solved by the Thomas algorithm: any length (the reference has no
     // restriction either); FFT / DCT directions are powers of two up to 2048
     const bool thomas_last = var[g.ndim - 1] == 'n';
@@ -1318,12 +1318,14 @@ int poisson_init(fen_ctx* c) {
     snprintf(p->variant, sizeof(p->variant), "%s", var);
     p->nx = g.nx; p->ny = g.ny; p->nz = g.nz; p->nzl = c->L.nzl;
     p->M = g.nx / 2;
-    p->PC = dctx ? (g.nx + 7) / 8 * 8 : spectral_pitch(g.nx);
+    p->PC = spectral_pitch_grid(g);
     p->nyl = g.ny;
     if (g.nranks > 1 && g.ndim == 3) {
         // the spectral arrays live in the comm arena so that the peers can store into them
-        if (g.ny % g.nranks || !pow2(g.nranks))
-            return set_error(FEN_ERR_UNSUPPORTED, "the number of ranks must be a power of two dividing ny and nz");
+        if (g.ny % g.nranks || !pow2(g.nranks) || !pow2(g.ny / g.nranks) || !pow2(c->L.nzl))
+            return set_error(FEN_ERR_UNSUPPORTED, "slab transposes need a power-of-two number of ranks and "
+                                                  "power-of-two ny / nranks, nz / nranks (got %d, %d, %d)",
+                             g.nranks, g.ny, g.nz);
         FEN_TRY(comm_spectral(c, p->peerC, p->peerCz));
         p->multi = true;
         p->nyl = g.ny / g.nranks;
@@ -1464,13 +1466,34 @@ int poisson_solve(fen_ctx* c, double* f, bool fuse_rhs, double dt) {
         LArgs la;
         la.C = p->C; la.sl = p->PC; la.so = (long long)p->PC * g.ny; la.tw = p->tw_y; la.o0 = 0; la.cx0 = 0;
         la.lx = nullptr; la.lo = nullptr; la.ll = nullptr; la.norm = 1.0;
+        // slabs: the y <-> z transposes of these variants (poisson.f90:1229, :1279 / :1368, :1418) are separate
+        // staggered row copies to the owning ranks (k_a2a_scatter); built for coverage, not fused into the passes
+        ScArgs sf, sb;
+        memset(&sf, 0, sizeof(sf));
+        memset(&sb, 0, sizeof(sb));
+        if (multi) {
+            for (int r = 0; r < g.nranks; ++r) { sf.peer[r] = p->peerCz[r]; sb.peer[r] = p->peerC[r]; }
+            sf.sh = log2i(p->nyl); sf.mask = p->nyl - 1;
+            sf.dsl = p->PC; sf.dso = (long long)p->PC * p->nyl; sf.o0 = g.rank * p->nzl;
+            sb.sh = log2i(p->nzl); sb.mask = p->nzl - 1;
+            sb.dsl = (long long)p->PC * g.ny; sb.dso = p->PC; sb.o0 = g.rank * p->nyl;
+        }
         if (nn) {
             t.sl = p->PC; t.so = 0; t.n = g.ny; t.nouter = 1; t.o0 = 0; t.lo = nullptr; t.form2d = 1;
         } else {
             la.scale = npn ? 1.0 / (double)g.ny : 1.0 / (double)(2 * g.ny);    // :1226, :1365
             if (npn) FEN_TRY(dispatch_lines(c, g.ny, la, 0, p->PC, p->nzl));   // full c2c of real data == r2c
             else FEN_TRY(dispatch_dct_lines(c, g.ny, la, p->twq_y, true, p->PC, p->nzl));
-            t.sl = (long long)p->PC * g.ny; t.so = p->PC; t.n = g.nz; t.nouter = g.ny; t.o0 = 0;
+            if (multi) {
+                FEN_LAUNCH(c, "a2a_scatter", k_a2a_scatter<<<dim3(g.ny, p->nzl), 256, 0, c->stream>>>(
+                                                 p->C, (long long)p->PC, (long long)p->PC * g.ny, p->PC, g.nranks,
+                                                 g.rank, p->nyl, sf));
+                FEN_CUDA(cudaGetLastError());
+                FEN_TRY(comm_transpose_fwd(c));
+            }
+            t.C = p->Cz;
+            t.sl = (long long)p->PC * p->nyl; t.so = p->PC; t.n = g.nz; t.nouter = p->nyl;
+            t.o0 = multi ? g.rank * p->nyl : 0;
             t.lo = p->mwn_y; t.form2d = 0;
         }
         if (nn) {
@@ -1479,7 +1502,12 @@ int poisson_solve(fen_ctx* c, double* f, bool fuse_rhs, double dt) {
             dim3 tgrid((p->PC + 127) / 128, t.nouter), tblock(128);
             FEN_LAUNCH(c, "thomas_fwd", k_thomas_fwd<<<tgrid, tblock, 0, c->stream>>>(t));
             FEN_LAUNCH(c, "thomas_bwd", k_thomas_bwd<false><<<tgrid, tblock, 0, c->stream>>>(t, none));
+            if (multi)
+                FEN_LAUNCH(c, "a2a_scatter", k_a2a_scatter<<<dim3(g.nz, p->nyl), 256, 0, c->stream>>>(
+                                                 p->Cz, (long long)p->PC * p->nyl, (long long)p->PC, p->PC, g.nranks,
+                                                 g.rank, p->nzl, sb));
             FEN_CUDA(cudaGetLastError());
+            if (multi) FEN_TRY(comm_transpose_bwd(c));
         }
         if (!nn) {
             la.scale = 1.0;
@@ -1546,7 +1574,7 @@ int poisson_solve(fen_ctx* c, double* f, bool fuse_rhs, double dt) {
                 FEN_LAUNCH(c, "thomas_bwd", k_thomas_bwd<false><<<grid, block, 0, c->stream>>>(t, sb));
                 if (multi)
                     FEN_LAUNCH(c, "a2a_scatter", k_a2a_scatter<<<dim3(g.nz, p->nyl), 256, 0, c->stream>>>(
-                                                     Z, slz, p->PC, g.nranks, g.rank, p->nzl, sb));
+                                                     Z, slz, (long long)p->PC, p->PC, g.nranks, g.rank, p->nzl, sb));
             }
         }
         FEN_CUDA(cudaGetLastError());

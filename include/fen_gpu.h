@@ -109,6 +109,11 @@ int fen_gpu_scalar_destroy(fen_ctx* ctx, int field);
 /* host f(...) -> device, device -> host; gl = ghost layers of the HOST array (0 or 1) */
 int fen_gpu_push(fen_ctx* ctx, int field, const double* host, int gl);
 int fen_gpu_pull(fen_ctx* ctx, int field, double* host, int gl);
+/* pull without blocking: the copy runs on its own stream (PCIe is full duplex, so it overlaps later pushes); the host
+ * array is valid after fen_gpu_pull_wait or fen_gpu_synchronize.  A later push of the same field waits for it on the
+ * device side. */
+int fen_gpu_pull_async(fen_ctx* ctx, int field, double* host, int gl);
+int fen_gpu_pull_wait(fen_ctx* ctx);
 /* self%f = val (scalar%setToValue, scalar.f90:168) */
 int fen_gpu_set_to_value(fen_ctx* ctx, int field, double val);
 /* bc%type_<face> (scalar.f90:24-37) */

@@ -177,3 +177,42 @@ def test_forcing_hook_runs_between_predictor_and_poisson():
     ns.navier_stokes_solver(4, dt)
     assert len(calls) == 3
     G.destroy()
+
+
+def test_pull_async_and_push_ordering():
+    """fen_gpu_pull_async: the copy runs on its own stream; pull_wait makes the host array valid, and a push of the same
+    array right behind it waits for the download on the device side (the e2e loop of bench.py relies on both)."""
+    import torch
+    n = (64, 32, 16)
+    G = fb.grid().setup(n[0], n[1], n[2], 2.0, 1.0, 0.5)
+    rng = np.random.default_rng(3)
+    fields = [fb.scalar(G, 1) for _ in range(6)]
+    want = []
+    for s in fields:
+        # pinned host arrays, so that the copies really are asynchronous
+        t = torch.empty(s.f.size, dtype=torch.float64, pin_memory=True)
+        s.f = t.numpy().reshape(s.f.shape, order="F")
+        s._keep = t
+        s.f[...] = rng.standard_normal(s.f.shape)
+        want.append(s.f.copy())
+        s.push()
+    for s in fields:
+        s.f[...] = 0.0
+    for s in fields:                       # more pulls in flight than staging buffers (4)
+        s.pull_async()
+    G.pull_wait()
+    for s, w in zip(fields, want):
+        assert np.array_equal(s.f, w)
+    # download, then upload the same array without waiting on the host, twice round
+    for rep in range(2):
+        for s in fields:
+            s.pull_async()
+        for s in fields:
+            s.push()
+    G.synchronize()
+    for s in fields:
+        s.f[...] = -1.0
+        s.pull()
+    for s, w in zip(fields, want):
+        assert np.array_equal(s.f, w)
+    G.destroy()

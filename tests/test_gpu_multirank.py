@@ -65,6 +65,9 @@ def _poisson_program(n, L, bc, rhs):
         G = slab_grid(rank, P, comm, n, L, bc)
         phi = fb.scalar(G, 1)
         if bc is not None:
+            for face, s in zip(fo.FACES[:4], bc[:4]):
+                if s == "Wall":
+                    phi.set_bc_type(face, 2)
             if rank == 0:
                 phi.set_bc_type("front", 2)
             if rank == P - 1:
@@ -109,6 +112,35 @@ def test_poisson_matches_single_rank_and_oracle(P, bc, variant, n, L):
     fo.PoissonSolver(po).solve(po)
     ref = po.I
     assert np.linalg.norm(got - ref) <= 1e-12 * np.linalg.norm(ref)
+
+
+XZWALLS = ["Wall", "Wall", "Periodic", "Periodic", "Wall", "Wall"]
+ALLWALLS = ["Wall"] * 6
+
+
+@pytest.mark.parametrize("P", [2, 4])
+@pytest.mark.parametrize("bc,variant", [(XZWALLS, "npn"), (ALLWALLS, "nnn")])
+def test_poisson_dct_variants_on_slabs(P, bc, variant):
+    """The Neumann-in-x variants (DCT-II / III in x, and in y for nnn; poisson.f90:1177-1451) on z slabs: same bits
+    as one rank, and the oracle's answer."""
+    n, L = (32, 16, 16), (2.0, 1.0, 1.0)
+    rng = np.random.default_rng(13)
+    rhs = np.zeros((n[0] + 2, n[1] + 2, n[2] + 2), order="F")
+    rhs[1:-1, 1:-1, 1:-1] = rng.standard_normal(n)
+    rhs[1:-1, 1:-1, 1:-1] -= rhs[1:-1, 1:-1, 1:-1].mean()
+    prog = _poisson_program(n, L, bc, rhs)
+    one = run_ranks(1, prog)[0]
+    many = run_ranks(P, prog)
+    assert one[1] == variant and all(m[1] == variant for m in many)
+    got = gather_interior([m[0] for m in many], 1)
+    assert np.array_equal(got, one[0][1:-1, 1:-1, 1:-1])
+    Go = fo.Grid(n[0], n[1], n[2], L[0], L[1], L[2], bc=bc)
+    po = fo.Scalar(Go, 1)
+    po.f[...] = rhs
+    fo.PoissonSolver(po).solve(po)
+    ref = po.I
+    # npn / nnn do not remove the mean (poisson.f90:1310, :1449 are commented out): compare as computed
+    assert np.linalg.norm(got - ref) <= 1e-11 * np.linalg.norm(ref)
 
 
 def _ns_program(n, L, bc, nu, init, U, g, cfl, steps, constant_cfl=False):
@@ -180,6 +212,40 @@ def test_ns_steps_channel_ppn_rank_count_invariant(P):
         for m in range(4):
             assert np.array_equal(many[r][0][m], one[0][m][:, :, r * nzl: r * nzl + nzl + 2]), (r, m)
         assert many[r][1] == one[1]
+
+
+@pytest.mark.parametrize("bc,variant", [(XZWALLS, "npn"), (ALLWALLS, "nnn")])
+def test_ns_steps_closed_box_rank_count_invariant(bc, variant):
+    """A closed box driven by a body force (walls in x and z, or everywhere: the lid3D / cavity wiring without the
+    lid) on 2 slabs: Dirichlet / Neumann ghosts on the x and y walls of every rank, the DCT Poisson variants and
+    their slab transposes inside the full step."""
+    n = (32, 16, 16)
+
+    def init(ns):
+        i = np.arange(1, n[0] + 1)[:, None, None]
+        k = np.arange(1, n[2] + 1)[None, None, :]
+        ns.v.y.I[...] = 0.05 * np.sin(PI * (i - 0.5) / n[0]) * np.sin(PI * (k - 0.5) / n[2]) * np.ones((1, n[1], 1))
+        if variant == "nnn":
+            ns.v.y.I[:, -1, :] = 0.0          # the wall-normal component on the top wall face
+        ns.v.update_ghost_nodes()
+    prog, nso = _ns_program(n, (2.0, 1.0, 1.0), bc, 0.05, init, 1.0, (1.0, 0.5, 0.25), 0.2, 4)
+    one = run_ranks(1, prog)[0]
+    many = run_ranks(2, prog)
+    nzl = n[2] // 2
+    for r in range(2):
+        for m in range(4):
+            assert np.array_equal(many[r][0][m], one[0][m][:, :, r * nzl: r * nzl + nzl + 2]), (r, m)
+        assert many[r][1] == one[1]
+    nso.CFL = 0.2
+    dt = nso.set_timestep(1.0)
+    for step in range(1, 5):
+        nso.navier_stokes_solver(step, dt)
+    for m, a in enumerate((nso.v.x, nso.v.y, nso.v.z, nso.p)):
+        got = gather_interior([x[0][m] for x in many], 1)
+        ref = a.I
+        if m == 3:                                # npn / nnn leave the mean of the pressure undetermined
+            got, ref = got - got.mean(), ref - ref.mean()
+        assert np.linalg.norm(got - ref) <= 1e-11 * max(np.linalg.norm(ref), 1.0), m
 
 
 def test_constant_cfl_allreduce_multirank():
