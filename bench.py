@@ -415,7 +415,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--size", type=int, default=512, help="cells per direction per GPU (config 2: 512)")
     ap.add_argument("--cpu-size", type=int, default=256)
-    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--e2e-steps", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--case", default="tgv", choices=["tgv", "channel", "wave2d"],
