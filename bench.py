@@ -252,6 +252,21 @@ def run_reference(args, rank, world):
     the same workload (the reference's own Fortran/MPI/FFTW build does not exist in this image)."""
     if rank != 0:
         return
+    if args.case == "wave2d":
+        val, sec = cpu_port_wave2d(512, 1024, args.steps, args.warmup)
+        sample = "512 x 1024 sample of the 2048 x 4096 two-phase wave, %d steps, numpy restatement" % args.steps
+        print(json.dumps({
+            "impl": "reference", "metric": "two-phase NS timestep Mcell-updates/s", "value": val,
+            "unit": "Mcell-updates/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 * sec, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "2-D two-phase gravity wave fp64 (CPU arm: bounded 512 x 1024 sample)",
+                       "grid": [512, 1024, 1]},
+            "cpu_baseline": {"value": val, "unit": "Mcell-updates/s", "cores": os.cpu_count() or 1, "kind": "port",
+                             "sample": sample},
+            "e2e": {"value": val, "unit": "Mcell-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}))
+        return
     n = args.cpu_size
     val, sec, cores, what = cpu_port(n, args.steps, args.warmup)
     sample = "%d^3 sample of the 512^3 Taylor-Green case, %d steps, %s" % (n, args.steps, what)
@@ -278,6 +293,41 @@ def cpu_baseline(budget_s=20.0):
     val, sec, cores, what = cpu_port(n, steps, 1)
     return {"value": val, "unit": "Mcell-updates/s", "cores": cores, "kind": "port",
             "sample": "%d steps of the same Taylor-Green case at %d^3 (1 warm-up), %s" % (steps, n, what)}
+
+
+def cpu_port_wave2d(nx, ny, steps, warmup=1):
+    """The numpy restatement of the reference's two-phase step (oracle/fen_oracle_mf.py) on an nx x ny sample of the
+    wave2d workload.  Returns (Mcell-updates/s, seconds per step)."""
+    import math
+    from oracle import fen_oracle as fo
+    from oracle import fen_oracle_mf as mf
+    fo.set_workers(os.cpu_count() or 1)
+    Lx, Ly = 1.0, float(ny) / nx
+    G = fo.Grid(nx, ny, 1, Lx, Ly, Lx / nx, bc=["Periodic", "Periodic", "Wall", "Wall"])
+    g = 9.80665
+    mu0 = 1000.0 * Lx * math.sqrt(g * Lx) / 1.0e4
+    ns = mf.MultiphaseNavierStokes(G, 1000.0, 1000.0 / 850.0, mu0, mu0 * 1.9e-2, 0.07,
+                                   distance=lambda x, y: y - 0.02 * np.cos(2.0 * PI * x / Lx) - Ly / 2.0)
+    ns.g[1] = -g
+    dt = 0.1 * ns.set_timestep(1.0)
+    for s in range(warmup):
+        ns.navier_stokes_solver(s + 1, dt)
+    t0 = time.perf_counter()
+    for s in range(steps):
+        ns.navier_stokes_solver(warmup + s + 1, dt)
+    t = time.perf_counter() - t0
+    return nx * ny * steps / t / 1e6, t / steps
+
+
+def cpu_baseline_wave2d(budget_s=15.0):
+    nx, ny = 512, 1024
+    _, sec = cpu_port_wave2d(nx, ny, 1, 1)
+    steps = int(max(2, min(30, budget_s / max(sec, 1e-3))))
+    val, sec = cpu_port_wave2d(nx, ny, steps, 1)
+    return {"value": val, "unit": "Mcell-updates/s", "cores": os.cpu_count() or 1, "kind": "port",
+            "sample": "%d steps of the same two-phase wave at %d x %d (1 warm-up), numpy restatement of the "
+                      "reference's -DMF step (oracle/fen_oracle_mf.py; whole-array numpy, effectively one core "
+                      "outside scipy.fft)" % (steps, nx, ny)}
 
 
 def run_wave2d(args, local_rank):
@@ -402,7 +452,7 @@ def run_wave2d(args, local_rank):
                      "alg_bytes_per_launch": dom["alg_bytes_per_cell"] * ncell if dom else None,
                      "step_alg_bytes_per_cell": MF_STEP_BYTES_PER_CELL, "step_achieved": step_gbs,
                      "step_frac": step_gbs / peak},
-        "cpu_baseline": None, "kernels": kernels,
+        "cpu_baseline": None if args.no_cpu_baseline else cpu_baseline_wave2d(), "kernels": kernels,
         "check": {"maxdiv": maxdiv, "maxCFL": maxcfl, "phase_integrals": [i1, i2]}}))
     G.destroy()
 

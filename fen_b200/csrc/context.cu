@@ -587,12 +587,12 @@ static int update_timestep(fen_ctx* c, double* dt) {
 
 int fen_gpu_predicted_velocity_field(fen_ctx* c, double dt) {
     if (!c || !c->solver_init) return set_error(FEN_ERR_STATE, "init_solver has not been called");
-    return ns_predict(c, dt);
+    return mf_active(c) ? mf_predict(c, dt) : ns_predict(c, dt);     // -DMF: uses p_hat as it stands (:175)
 }
 int fen_gpu_correct_velocity_field(fen_ctx* c, double dt) {
     if (!c || !c->solver_init) return set_error(FEN_ERR_STATE, "init_solver has not been called");
     // correct_velocity_field + update_pressure share one kernel; see fen_gpu_update_pressure
-    return ns_correct(c, dt);
+    return mf_active(c) ? mf_correct(c, dt) : ns_correct(c, dt);
 }
 int fen_gpu_update_pressure(fen_ctx* c) {
     if (!c || !c->solver_init) return set_error(FEN_ERR_STATE, "init_solver has not been called");
@@ -765,6 +765,9 @@ int fen_gpu_add_advection(fen_ctx* c, int rhs_x) {
 }
 int fen_gpu_compute_explicit_terms(fen_ctx* c, int rhs_x) {
     if (!c || !c->solver_init) return set_error(FEN_ERR_STATE, "init_solver has not been called");
+    if (mf_active(c))
+        return set_error(FEN_ERR_UNSUPPORTED, "compute_explicit_terms is not a separate entry point of the two-phase "
+                                              "build: its terms live inside predicted_velocity_field (multiphase.cu)");
     return op_explicit_terms(c, rhs_x, false);
 }
 

@@ -163,6 +163,7 @@ int fetch_red(fen_ctx* c, int n);                          // async copy of d_re
 int field_tmap(fen_ctx* c, const double* base, int box_x, int box_y, CUtensorMap** out);
 // ghost.cu
 int ghost_update(fen_ctx* c, int field, int ncomp, bool x_done = false);   // x_done: producer wrote periodic x ghosts
+int ghost_update_list(fen_ctx* c, const int* ids, int n, bool x_done = false);   // up to 8 fields, one launch per direction
 // comm.cu
 int halo_exchange(fen_ctx* c, double* const* f, int n);
 int comm_allreduce(fen_ctx* c, double* d_vals, int n, int op /*0 max, 1 sum*/);

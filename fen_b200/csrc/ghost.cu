@@ -4,8 +4,8 @@
 // decomposition is (prow, pcol) = (1, nranks)), then the physical boundary conditions in the
 // reference's order x-left, x-right, y-bottom, y-top, z-front, z-back, each over the FULL
 // transverse extent (ghost rows/planes included) -- that order defines the edge and corner ghosts
-// the advection stencil reads (SURVEY.md hazard H3).  Up to three fields (the components of a
-// vector) are handled per launch.
+// the advection stencil reads (SURVEY.md hazard H3).  Up to eight fields are handled per launch (the
+// components of a vector, or the seven fields one VoF reconstruction refreshes).
 #include "fen_internal.cuh"
 
 namespace fen {
@@ -19,8 +19,9 @@ struct GhostField {
     const double* plo;     // value plane (incl. ghosts), Fortran order
     const double* phi;
 };
+constexpr int GHOST_MAX = 8;
 struct GhostArgs {
-    GhostField fld[3];
+    GhostField fld[GHOST_MAX];
     int n;
     Layout L;
 };
@@ -76,17 +77,24 @@ __global__ void k_ghost(GhostArgs a) {
 
 int ghost_update(fen_ctx* c, int field, int ncomp, bool x_done) {
     if (ncomp < 1 || ncomp > 3) return set_error(FEN_ERR_ARG, "update_ghost_nodes: ncomp must be 1..3");
-    Field* fp[3];
-    double* ptrs[3];
+    const int ids[3] = {field, field + 1, field + 2};
+    return ghost_update_list(c, ids, ncomp, x_done);
+}
+
+int ghost_update_list(fen_ctx* c, const int* ids, int ncomp, bool x_done) {
+    if (ncomp < 1 || ncomp > GHOST_MAX) return set_error(FEN_ERR_ARG, "update_ghost_nodes: 1..%d fields per call", GHOST_MAX);
+    Field* fp[GHOST_MAX];
+    double* ptrs[GHOST_MAX];
     for (int m = 0; m < ncomp; ++m) {
-        FEN_TRY(field_check(c, field + m, &fp[m]));
+        FEN_TRY(field_check(c, ids[m], &fp[m]));
         if (fp[m]->gl < 1)   // vector.f90:91-95 prints an error and skips
             return set_error(FEN_ERR_ARG, "Cannot update ghost nodes on a scalar without ghost nodes (field %d)",
-                             field + m);
+                             ids[m]);
         ptrs[m] = fp[m]->d;
     }
-    // 1. halo exchange with the z neighbours (scalar.f90:251 -> halo.f90:33)
-    if (c->g.nranks > 1) FEN_TRY(halo_exchange(c, ptrs, ncomp));
+    // 1. halo exchange with the z neighbours (scalar.f90:251 -> halo.f90:33), three fields per round
+    if (c->g.nranks > 1)
+        for (int m0 = 0; m0 < ncomp; m0 += 3) FEN_TRY(halo_exchange(c, ptrs + m0, std::min(3, ncomp - m0)));
 
     const Layout& L = c->L;
     const int ndir = (c->g.ndim == 3) ? 3 : 2;
@@ -117,7 +125,7 @@ int ghost_update(fen_ctx* c, int field, int ncomp, bool x_done) {
             g.phi = F.bc_plane[fhi];
             for (int t : {g.tlo, g.thi}) {
                 if (t < -1 || t > 2)
-                    return set_error(FEN_ERR_ARG, "wrong boundary condition type %d for field %d", t, field + m);
+                    return set_error(FEN_ERR_ARG, "wrong boundary condition type %d for field %d", t, ids[m]);
                 if (t != FEN_HALO) any = true;
             }
         }

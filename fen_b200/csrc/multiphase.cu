@@ -241,9 +241,9 @@ static int recon(fen_ctx* c, int src_id) {
     a.beta = m.beta; a.cut = m.cut; a.quadratic = m.quadratic;
     FEN_LAUNCH(c, "vof_recon", k_vof_recon<<<mf_grid(c->L), dim3(MTX, MTY), 0, c->stream>>>(a));
     FEN_CUDA(cudaGetLastError());
-    FEN_TRY(ghost_update(c, FEN_CURV, 3));       // curv, norm%x, norm%y (:392-393)
-    FEN_TRY(ghost_update(c, FEN_LX, 2));         // l (:394)
-    return ghost_update(c, FEN_H, 2);            // h, d (:299-300)
+    // curv, norm, l (:392-394) and h, d (:299-300): seven fields, one launch per direction
+    const int ids[7] = {FEN_CURV, FEN_NORMX, FEN_NORMY, FEN_LX, FEN_LY, FEN_H, FEN_D};
+    return ghost_update_list(c, ids, 7);
 }
 
 static int sweep(fen_ctx* c, int dir, bool final, int src_id, int out_id, int vx, double dt, bool x_first) {
@@ -316,9 +316,8 @@ static int material_properties(fen_ctx* c, bool with_phat, double dt) {
     a.p = p; a.p_o = po;
     FEN_LAUNCH(c, "mf_props", k_mf_props<<<mf_grid(c->L), dim3(MTX, MTY), 0, c->stream>>>(a));
     FEN_CUDA(cudaGetLastError());
-    FEN_TRY(ghost_update(c, FEN_RHO, 2));                                  // multiphase.f90:134-135
-    if (with_phat) FEN_TRY(ghost_update(c, FEN_PHAT, 1));                  // navier_stokes.f90:95
-    return FEN_OK;
+    const int ids[3] = {FEN_RHO, FEN_MU, FEN_PHAT};                        // multiphase.f90:134-135, navier_stokes.f90:95
+    return ghost_update_list(c, ids, with_phat ? 3 : 2);
 }
 
 int mf_step_front(fen_ctx* c, double dt) {
@@ -373,9 +372,9 @@ int mf_correct(fen_ctx* c, double dt) {
     FEN_LAUNCH(c, "corr", k_mf_corr<<<mf_grid(c->L), dim3(MTX, MTY), 0, c->stream>>>(
                               c->L, u, v, p, po, phi, 1.0 / c->g.delta, dt, c->mf->prm.irhomin));
     FEN_CUDA(cudaGetLastError());
-    FEN_TRY(ghost_update(c, FEN_VX, 2));              // :544
-    FEN_TRY(ghost_update(c, FEN_PO, 1));              // p_o%f = p%f copies p's ghosts too (:557); same types as p
-    return ghost_update(c, FEN_P, 1);                 // :564
+    // v (:544), p (:564) and p_o (p_o%f = p%f copies p's ghosts too, :557; same boundary types as p)
+    const int ids[4] = {FEN_VX, FEN_VY, FEN_PO, FEN_P};
+    return ghost_update_list(c, ids, 4);
 }
 
 int mf_set_timestep(fen_ctx* c, double U, double* dt) {
