@@ -144,3 +144,23 @@ def test_oracle_reproduces_mf_golden():
         ns.navier_stokes_solver(s, dt)
     for k, a in (("u", ns.v.x.f), ("v", ns.v.y.f), ("p", ns.p.f), ("vof", ns.vof.f), ("rho", ns.rho.f)):
         assert np.linalg.norm((a - g[k]).ravel()) <= 1e-12 * np.linalg.norm(g[k].ravel()), k
+
+
+def test_flat_interface_stays_at_rest():
+    """Hydrostatic balance: water under air (density ratio 850, gravity, surface tension switched on) with a flat
+    interface and zero velocity must stay at rest -- the constant-coefficient pressure splitting
+    (navier_stokes.f90:174-184) and the p_hat extrapolation balance gravity exactly once the pressure has built up."""
+    G = fo.Grid(32, 64, 1, 1.0, 2.0, 1.0 / 32, bc=["Periodic", "Periodic", "Wall", "Wall"])
+    ns = mf.MultiphaseNavierStokes(G, 1000.0, 1000.0 / 850.0, 0.313, 0.00595, 0.07, distance=lambda x, y: y - 1.0 + 0.0 * x)
+    ns.g[1] = -mf.GRAVITY
+    dt = 0.1 * ns.set_timestep(1.0)
+    vof0 = ns.vof.I.copy()
+    for s in range(1, 21):
+        ns.navier_stokes_solver(s, dt)
+    assert np.abs(ns.v.x.I).max() < 1e-13 and np.abs(ns.v.y.I).max() < 1e-13
+    assert np.abs(ns.vof.I - vof0).max() < 1e-13
+    assert abs(ns.maxdiv) < 1e-12
+    # in the light phase (rho = rhomin) the splitting is exact and the pressure is hydrostatic at once; the heavy
+    # phase builds its pressure up over many steps through p_hat = 2p - p_o, the projection removing the rest
+    p = ns.p.I[0, :, 0]
+    assert abs((p[60] - p[59]) / G.delta + 1000.0 / 850.0 * mf.GRAVITY) < 1e-9 * mf.GRAVITY
