@@ -513,3 +513,20 @@ def test_full_size_512_properties():
     ke1 = sum(float((c.I ** 2).sum()) for c in ns.v.comps)
     assert 0.99 * ke0 < ke1 < ke0                                   # viscous decay, no blow-up
     Gg.destroy()
+
+
+def test_c_driver_runs():
+    """examples/tgv_driver.c: the 2-D Taylor-Green case driven from plain C through the C ABI; the error against the
+    analytic solution is the second-order one the reference's test plots (postpro.py:48-62)."""
+    import re
+    import subprocess
+    from tests.test_host_logic import _build_c_driver
+    exe = _build_c_driver()
+    errs = []
+    for n in (32, 64):
+        r = subprocess.run([exe, str(n), "40"], capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0, r.stderr
+        assert "maxdiv" in r.stdout
+        errs.append(float(re.search(r"u_exact\| after 40 steps: ([0-9.eE+-]+)", r.stdout).group(1)))
+    # the oracle gives 2.4544e-3 and 1.0255e-3 for these two runs (dt = 0.125 delta^2, so t differs with N)
+    assert abs(errs[0] - 2.4544e-3) < 2e-6 and abs(errs[1] - 1.0255e-3) < 2e-6, errs

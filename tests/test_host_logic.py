@@ -62,3 +62,26 @@ def test_fft_core_index_logic_on_cpu():
                     os.path.join(ROOT, "tests", "cpu", "test_fft_core.cu")], check=True)
     r = subprocess.run([exe], capture_output=True, text=True)
     assert r.returncode == 0 and "OK" in r.stdout, r.stdout
+
+
+def _build_c_driver():
+    exe = os.path.join(ROOT, "build", "tgv_driver")
+    os.makedirs(os.path.dirname(exe), exist_ok=True)
+    from fen_b200 import _lib
+    libdir = os.path.dirname(_lib.LIB_PATH)
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(ROOT, "include"),
+                    os.path.join(ROOT, "examples", "tgv_driver.c"), "-L", libdir, "-lfen_gpu",
+                    "-Wl,-rpath," + libdir, "-lm", "-o", exe], check=True)
+    return exe
+
+
+def test_c_abi_header_is_plain_c_and_a_c_driver_links(lib):
+    """include/fen_gpu.h must be consumable from C (the Fortran shim binds the same symbols): a C99 driver with the
+    reference's Taylor-Green call sequence compiles with -pedantic -Werror and links; without a device it stops at
+    fen_gpu_create with the 'no CPU fallback' message."""
+    import torch
+    exe = _build_c_driver()
+    if torch.cuda.is_available():
+        pytest.skip("a device is present: the run itself is tests/test_gpu_parity.py::test_c_driver_runs")
+    r = subprocess.run([exe, "16", "1"], capture_output=True, text=True)
+    assert r.returncode == 2 and "no CPU fallback" in r.stderr
