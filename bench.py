@@ -100,7 +100,7 @@ class ClockSampler:
                     self.rows.append([x.strip() for x in out.split(",")])
             except Exception:
                 pass
-            self._stop.wait(0.2)
+            self._stop.wait(0.02)       # nvidia-smi itself takes ~40 ms: a few samples even in a 150 ms region
 
     def __enter__(self):
         self._t = threading.Thread(target=self._run, daemon=True)
