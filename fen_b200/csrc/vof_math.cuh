@@ -23,40 +23,39 @@ struct VofRecon {
     double nx, ny, lx, ly, curv;
 };
 
-// compute_norm, volume_of_fluid.f90:307-396.  f[b][a] = vof(i + a - 1, j + b - 1).
-FEN_HD VofRecon vof_norm(const double f[3][3], double delta, double idelta, double idelta2, bool quadratic) {
-    const double fmm = f[0][0], f0m = f[0][1], fpm = f[0][2];
-    const double fm0 = f[1][0], f00 = f[1][1], fp0 = f[1][2];
-    const double fmp = f[2][0], f0p = f[2][1], fpp = f[2][2];
-    if (fmm == f00 && f0m == f00 && fpm == f00 && fm0 == f00 && fp0 == f00 && fmp == f00 && f0p == f00 && fpp == f00) {
-        // uniform patch (every cell away from the interface band): all eight corner gradients are exactly zero and
-        // the expressions below evaluate to exactly these values -- skip their 5 square roots and 10 divisions
-        VofRecon z;
-        z.nx = 0.0; z.ny = 0.0; z.lx = 0.0; z.ly = 0.0;
-        z.curv = -(z.lx + z.ly) * idelta2;
-        return z;
+// One corner of compute_norm (volume_of_fluid.f90:327-356): the Youngs gradient at the corner shared by the cells
+// f00 = vof(i, j), f10 = vof(i+1, j), f01 = vof(i, j+1), f11 = vof(i+1, j+1), and its normalisation (:357-360).
+// The reference evaluates every corner from the four cells around it with the same operands in the same order, so
+// the value is bitwise shared (the tiled kernel computes it once).  A zero gradient gives 0 / sqrt(small) = 0 exactly.
+FEN_HD void vof_corner(double f00, double f10, double f01, double f11, double idelta, double& mx, double& my,
+                       double& nx, double& ny) {
+    mx = 0.5 * (f10 + f11 - f00 - f01) * idelta;
+    my = 0.5 * (f01 + f11 - f00 - f10) * idelta;
+    if (mx == 0.0 && my == 0.0) {
+        nx = 0.0;
+        ny = 0.0;
+        return;
     }
-    double mx[4], my[4];
-    mx[0] = 0.5 * (f0m + f00 - fmm - fm0) * idelta;      // i-1/2, j-1/2
-    mx[1] = 0.5 * (f00 + f0p - fm0 - fmp) * idelta;      // i-1/2, j+1/2
-    mx[2] = 0.5 * (fp0 + fpp - f00 - f0p) * idelta;      // i+1/2, j+1/2
-    mx[3] = 0.5 * (fpm + fp0 - f0m - f00) * idelta;      // i+1/2, j-1/2
-    const double mxc = 0.25 * (mx[0] + mx[1] + mx[2] + mx[3]);
-    my[0] = 0.5 * (fm0 + f00 - fmm - f0m) * idelta;
-    my[1] = 0.5 * (fmp + f0p - fm0 - f00) * idelta;
-    my[2] = 0.5 * (f0p + fpp - f00 - fp0) * idelta;
-    my[3] = 0.5 * (f00 + fp0 - f0m - fpm) * idelta;
-    const double myc = 0.25 * (my[0] + my[1] + my[2] + my[3]);
-    double nx[4], ny[4];
-    for (int c = 0; c < 4; ++c) {
-        const double r = sqrt(mx[c] * mx[c] + my[c] * my[c] + VOF_SMALL);
-        nx[c] = mx[c] / r;
-        ny[c] = my[c] / r;
-    }
+    const double r = sqrt(mx * mx + my * my + VOF_SMALL);
+    nx = mx / r;
+    ny = my / r;
+}
+
+// cell-centre part of compute_norm from the four corners (:338, :353, :361-373).  Corner order as in the reference:
+// 0 = (i-1/2, j-1/2), 1 = (i-1/2, j+1/2), 2 = (i+1/2, j+1/2), 3 = (i+1/2, j-1/2).
+FEN_HD VofRecon vof_norm_from_corners(const double mx[4], const double my[4], const double nx[4], const double ny[4],
+                                      double delta, double idelta2, bool quadratic) {
     VofRecon o;
-    const double rc = sqrt(mxc * mxc + myc * myc + VOF_SMALL);
-    o.nx = mxc / rc;
-    o.ny = myc / rc;
+    const double mxc = 0.25 * (mx[0] + mx[1] + mx[2] + mx[3]);
+    const double myc = 0.25 * (my[0] + my[1] + my[2] + my[3]);
+    if (mxc == 0.0 && myc == 0.0) {
+        o.nx = 0.0;
+        o.ny = 0.0;
+    } else {
+        const double rc = sqrt(mxc * mxc + myc * myc + VOF_SMALL);
+        o.nx = mxc / rc;
+        o.ny = myc / rc;
+    }
     if (quadratic) {
         o.lx = 0.5 * delta * (nx[3] + nx[2] - nx[1] - nx[0]);
         o.ly = 0.5 * delta * (ny[1] + ny[2] - ny[0] - ny[3]);
@@ -66,6 +65,56 @@ FEN_HD VofRecon vof_norm(const double f[3][3], double delta, double idelta, doub
     }
     o.curv = -(o.lx + o.ly) * idelta2;
     return o;
+}
+
+// compute_norm, volume_of_fluid.f90:307-396.  f[b][a] = vof(i + a - 1, j + b - 1).
+FEN_HD VofRecon vof_norm(const double f[3][3], double delta, double idelta, double idelta2, bool quadratic) {
+    double mx[4], my[4], nx[4], ny[4];
+    vof_corner(f[0][0], f[0][1], f[1][0], f[1][1], idelta, mx[0], my[0], nx[0], ny[0]);      // i-1/2, j-1/2
+    vof_corner(f[1][0], f[1][1], f[2][0], f[2][1], idelta, mx[1], my[1], nx[1], ny[1]);      // i-1/2, j+1/2
+    vof_corner(f[1][1], f[1][2], f[2][1], f[2][2], idelta, mx[2], my[2], nx[2], ny[2]);      // i+1/2, j+1/2
+    vof_corner(f[0][1], f[0][2], f[1][1], f[1][2], idelta, mx[3], my[3], nx[3], ny[3]);      // i+1/2, j-1/2
+    return vof_norm_from_corners(mx, my, nx, ny, delta, idelta2, quadratic);
+}
+
+// ---- the same reconstruction for a 64 x 4 tile of cells with the corners computed once -------------------------
+// Shared-memory tile: F = vof of the tile and its one-cell halo (66 x 6), then the 65 x 5 corners.  The three
+// phases are separated by block barriers in the kernel (multiphase.cu: k_vof_recon_tile); tests/cpu/vof_math_host.cpp
+// runs them from loops over tid, so the index logic is checked on a machine without a GPU.
+constexpr int VT_X = 64, VT_Y = 4, VT_N = VT_X * VT_Y;
+constexpr int VT_FW = VT_X + 2, VT_FH = VT_Y + 2, VT_CW = VT_X + 1, VT_CH = VT_Y + 1;
+struct VofTile {
+    double F[VT_FH][VT_FW];
+    double cmx[VT_CH][VT_CW], cmy[VT_CH][VT_CW], cnx[VT_CH][VT_CW], cny[VT_CH][VT_CW];
+};
+// phase 1: f points at vof(i0, j0), the tile's low halo corner; wa x hb values are inside the array
+FEN_HD void vof_tile_load(VofTile& T, int tid, const double* f, long long sy, int wa, int hb) {
+    for (int e = tid; e < VT_FW * VT_FH; e += VT_N) {
+        const int b = e / VT_FW, a = e - b * VT_FW;
+        T.F[b][a] = (a < wa && b < hb) ? f[a + sy * b] : 0.0;
+    }
+}
+// phase 2: corner (a, b) sits between tile cells (a, b), (a+1, b), (a, b+1), (a+1, b+1)
+FEN_HD void vof_tile_corners(VofTile& T, int tid, double idelta) {
+    for (int e = tid; e < VT_CW * VT_CH; e += VT_N) {
+        const int b = e / VT_CW, a = e - b * VT_CW;
+        vof_corner(T.F[b][a], T.F[b][a + 1], T.F[b + 1][a], T.F[b + 1][a + 1], idelta, T.cmx[b][a], T.cmy[b][a],
+                   T.cnx[b][a], T.cny[b][a]);
+    }
+}
+// phase 3: the cell (tx, ty) of the tile = tile cell (tx + 1, ty + 1)
+FEN_HD VofRecon vof_tile_cell(const VofTile& T, int tx, int ty, double delta, double idelta2, bool quadratic,
+                              double& vof00) {
+    const int a = tx + 1, b = ty + 1;
+    const int ca[4] = {a - 1, a - 1, a, a}, cb[4] = {b - 1, b, b, b - 1};
+    double mx[4], my[4], nx[4], ny[4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        mx[c] = T.cmx[cb[c]][ca[c]]; my[c] = T.cmy[cb[c]][ca[c]];
+        nx[c] = T.cnx[cb[c]][ca[c]]; ny[c] = T.cny[cb[c]][ca[c]];
+    }
+    vof00 = T.F[b][a];
+    return vof_norm_from_corners(mx, my, nx, ny, delta, idelta2, quadratic);
 }
 
 // coefficients of the quadratic surface, Eq. 12 of Ii et al. (volume_of_fluid.f90:254-266, 610-634)

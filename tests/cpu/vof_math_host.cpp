@@ -30,6 +30,31 @@ void host_recon(int nx, int ny, const double* vof, double delta, double beta, do
         }
 }
 
+// the tiled reconstruction (k_vof_recon_tile): blocks and threads are loops, the barriers are the phase boundaries
+void host_recon_tile(int nx, int ny, const double* vof, double delta, double beta, double cut, int quadratic,
+                     double* onx, double* ony, double* olx, double* oly, double* ocurv, double* oh, double* od) {
+    const double id = 1.0 / delta, id2 = 1.0 / (delta * delta);
+    const long long sy = nx + 2;
+    static VofTile T;
+    for (int by = 0; by < (ny + VT_Y - 1) / VT_Y; ++by)
+        for (int bx = 0; bx < (nx + VT_X - 1) / VT_X; ++bx) {
+            const int i0 = bx * VT_X, j0 = by * VT_Y;
+            const int wa = VT_FW < nx + 2 - i0 ? VT_FW : nx + 2 - i0, hb = VT_FH < ny + 2 - j0 ? VT_FH : ny + 2 - j0;
+            for (int tid = 0; tid < VT_N; ++tid) vof_tile_load(T, tid, vof + i0 + sy * j0, sy, wa, hb);
+            for (int tid = 0; tid < VT_N; ++tid) vof_tile_corners(T, tid, id);
+            for (int ty = 0; ty < VT_Y; ++ty)
+                for (int tx = 0; tx < VT_X; ++tx) {
+                    const int i = i0 + 1 + tx, j = j0 + 1 + ty;
+                    if (i > nx || j > ny) continue;
+                    double v00, h, d;
+                    const VofRecon r = vof_tile_cell(T, tx, ty, delta, id2, quadratic != 0, v00);
+                    vof_h_d(v00, r.nx, r.ny, r.lx, r.ly, beta, cut, h, d);
+                    I(onx, i, j) = r.nx; I(ony, i, j) = r.ny; I(olx, i, j) = r.lx; I(oly, i, j) = r.ly;
+                    I(ocurv, i, j) = r.curv; I(oh, i, j) = h; I(od, i, j) = d;
+                }
+        }
+}
+
 void host_sweep(int nx, int ny, int dir, int final_, int x_first, const double* src, const double* fnx,
                 const double* fny, const double* flx, const double* fly, const double* fd, const double* u,
                 const double* v, double dt, double delta, double beta, double cut, double* out) {

@@ -99,6 +99,30 @@ def test_reconstruction_matches_oracle(tag, extra):
 
 
 @pytest.mark.parametrize("tag,extra", VARIANTS)
+def test_tiled_reconstruction_is_bit_identical(tag, extra):
+    """k_vof_recon_tile's three phases (tile load, corners once per corner, cells) run from loops: the same bits as the
+    per-cell path on a grid that is not a multiple of the 64 x 4 tile, with walls, a noisy '1 +- eps' phase and exactly
+    uniform regions."""
+    lib = _build(tag, extra)
+    nx, ny = 150, 37
+    G = fo.Grid(nx, ny, 1, 1.0, float(ny) / nx, 1.0 / nx, bc=["Wall", "Wall", "Periodic", "Periodic"])
+    vf = mf.VoF(G)
+    vf.distance = lambda x, y: 0.11 - np.sqrt((x - 0.43) ** 2 + (y - 0.12) ** 2)
+    vf.get_vof_from_distance()
+    rng = np.random.default_rng(1)
+    noisy = vf.vof.I[..., 0] >= 1.0 - 1e-9
+    vf.vof.I[..., 0][noisy] *= 1.0 + 1e-16 * rng.integers(-3, 4, size=int(noisy.sum()))
+    vf.vof.update_ghost_nodes()
+    a = _host_recon(lib, G, vf, vf.vof)
+    b = [_i2(G) for _ in range(7)]
+    lib.host_recon_tile(G.Nx, G.Ny, _p(_g2(vf.vof)), C.c_double(G.delta), C.c_double(vf.beta), C.c_double(vf.cut),
+                        1 if vf.quadratic else 0, *[_p(o) for o in b])
+    for name, x, y in zip(("nx", "ny", "lx", "ly", "curv", "h", "d"), a, b):
+        assert np.array_equal(x, y), name
+    assert (np.abs(a[0]) > 0).sum() > 200 and (a[0] == 0).sum() > 200        # both kinds of cells were present
+
+
+@pytest.mark.parametrize("tag,extra", VARIANTS)
 def test_advect_vof_matches_oracle(tag, extra):
     """Twenty advect_vof calls (both sweep orders, the H13 boundary-type switch, negative and positive face
     velocities) driven with the host cell functions in the kernels' own sequence (multiphase.cu: advect_vof)."""
