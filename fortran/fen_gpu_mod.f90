@@ -1,7 +1,9 @@
 !> fen_gpu_mod -- ISO_C_BINDING layer between FEN's Fortran drivers and libfen_gpu.so.
 !>
 !> SOURCE ONLY: the build image has no Fortran compiler (gfortran / flang / nvfortran / mpif90 are
-!> all absent), so this file is not compiled or run by the test-suite.  It is kept mechanical: part 1
+!> all absent), so this file is not compiled or run by the test-suite; tests/test_fortran_shim.py checks it
+!> textually against include/fen_gpu.h (every function bound, argument counts, VALUE attributes, the
+!> bind(C) types member by member, the enum values).  It is kept mechanical: part 1
 !> declares the bind(C) interfaces of include/fen_gpu.h one to one, part 2 wraps them in procedures
 !> that carry the reference's own names and argument lists, so a driver program switches over by
 !> changing its `use` lines (INTEGRATION.md).  The same call sequences are exercised through the
@@ -266,6 +268,204 @@ module fen_gpu_mod
             type(c_funptr), value :: fn
             real(c_double), value :: x0, y0
             integer(c_int) :: ierr
+        end function
+        function fen_gpu_destroy_vof(ctx) bind(C, name='fen_gpu_destroy_vof') result(ierr)
+            import :: c_int, c_ptr
+            type(c_ptr), value :: ctx
+            integer(c_int) :: ierr
+        end function
+        ! ---- the rest of the header: containers, field operators, stage-level calls, IO, hook, measurement ----
+        function fen_gpu_version() bind(C, name='fen_gpu_version') result(v)
+            import :: c_int
+            integer(c_int) :: v
+        end function
+        function fen_gpu_synchronize(ctx) bind(C, name='fen_gpu_synchronize') result(ierr)
+            import :: c_int, c_ptr
+            type(c_ptr), value :: ctx
+            integer(c_int) :: ierr
+        end function
+        function fen_gpu_local_bounds(ctx, lo, hi) bind(C, name='fen_gpu_local_bounds') result(ierr)
+            import :: c_int, c_ptr
+            type(c_ptr), value :: ctx
+            integer(c_int), intent(out) :: lo(3), hi(3)
+            integer(c_int) :: ierr
+        end function
+        function fen_gpu_pull_async(ctx, field, host, gl) bind(C, name='fen_gpu_pull_async') result(ierr)
+            import :: c_int, c_ptr
+            type(c_ptr), value :: ctx, host
+            integer(c_int), value :: field, gl
+            integer(c_int) :: ierr
+        end function
+        function fen_gpu_pull_wait(ctx) bind(C, name='fen_gpu_pull_wait') result(ierr)
+            import :: c_int, c_ptr
+            type(c_ptr), value :: ctx
+            integer(c_int) :: ierr
+        end function
+        function fen_gpu_set_to_value(ctx, field, val) bind(C, name='fen_gpu_set_to_value') result(ierr)
+            import :: c_int, c_ptr, c_double
+            type(c_ptr), value :: ctx
+            integer(c_int), value :: field
+            real(c_double), value :: val
+            integer(c_int) :: ierr
+        end function
+        function fen_gpu_get_bc_type(ctx, field, face, bctype) bind(C, name='fen_gpu_get_bc_type') result(ierr)
+            import :: c_int, c_ptr
+            type(c_ptr), value :: ctx
+            integer(c_int), value :: field, face
+            integer(c_int), intent(out) :: bctype
+            integer(c_int) :: ierr
+        end function
+        function fen_gpu_max_value(ctx, field, val) bind(C, name='fen_gpu_max_value') result(ierr)
+            import :: c_int, c_ptr, c_double
+            type(c_ptr), value :: ctx
+            integer(c_int), value :: field
+            real(c_double), intent(out) :: val
+            integer(c_int) :: ierr
+        end function
+        function fen_gpu_integral(ctx, field, val) bind(C, name='fen_gpu_integral') result(ierr)
+            import :: c_int, c_ptr, c_double
+            type(c_ptr), value :: ctx
+            integer(c_int), value :: field
+            real(c_double), intent(out) :: val
+            integer(c_int) :: ierr
+        end function
+        function fen_gpu_gradient(ctx, scalar_in, vector_out_x) bind(C, name='fen_gpu_gradient') result(ierr)
+            import :: c_int, c_ptr
+            type(c_ptr), value :: ctx
+            integer(c_int), value :: scalar_in, vector_out_x
+            integer(c_int) :: ierr
+        end function
+        function fen_gpu_divergence(ctx, vector_in_x, scalar_out) bind(C, name='fen_gpu_divergence') result(ierr)
+            import :: c_int, c_ptr
+            type(c_ptr), value :: ctx
+            integer(c_int), value :: vector_in_x, scalar_out
+            integer(c_int) :: ierr
+        end function
+        function fen_gpu_laplacian(ctx, vector_in_x, vector_out_x) bind(C, name='fen_gpu_laplacian') result(ierr)
+            import :: c_int, c_ptr
+            type(c_ptr), value :: ctx
+            integer(c_int), value :: vector_in_x, vector_out_x
+            integer(c_int) :: ierr
+        end function
+        function fen_gpu_center_to_face(ctx, scalar_in, vector_out_x) bind(C, name='fen_gpu_center_to_face') result(ierr)
+            import :: c_int, c_ptr
+            type(c_ptr), value :: ctx
+            integer(c_int), value :: scalar_in, vector_out_x
+            integer(c_int) :: ierr
+        end function
+        function fen_gpu_poisson_variant(ctx) bind(C, name='fen_gpu_poisson_variant') result(msg)
+            import :: c_ptr
+            type(c_ptr), value :: ctx
+            type(c_ptr) :: msg
+        end function
+        function fen_gpu_status_line(ctx, step, time, dt, buf, buflen) bind(C, name='fen_gpu_status_line') result(ierr)
+            import :: c_int, c_ptr, c_double, c_char
+            type(c_ptr), value :: ctx
+            integer(c_int), value :: step, buflen
+            real(c_double), value :: time, dt
+            character(kind=c_char), intent(out) :: buf(*)
+            integer(c_int) :: ierr
+        end function
+        function fen_gpu_add_advection(ctx, rhs_vector_x) bind(C, name='fen_gpu_add_advection') result(ierr)
+            import :: c_int, c_ptr
+            type(c_ptr), value :: ctx
+            integer(c_int), value :: rhs_vector_x
+            integer(c_int) :: ierr
+        end function
+        function fen_gpu_compute_explicit_terms(ctx, rhs_vector_x) bind(C, name='fen_gpu_compute_explicit_terms') result(ierr)
+            import :: c_int, c_ptr
+            type(c_ptr), value :: ctx
+            integer(c_int), value :: rhs_vector_x
+            integer(c_int) :: ierr
+        end function
+        function fen_gpu_predicted_velocity_field(ctx, dt) bind(C, name='fen_gpu_predicted_velocity_field') result(ierr)
+            import :: c_int, c_ptr, c_double
+            type(c_ptr), value :: ctx
+            real(c_double), value :: dt
+            integer(c_int) :: ierr
+        end function
+        function fen_gpu_correct_velocity_field(ctx, dt) bind(C, name='fen_gpu_correct_velocity_field') result(ierr)
+            import :: c_int, c_ptr, c_double
+            type(c_ptr), value :: ctx
+            real(c_double), value :: dt
+            integer(c_int) :: ierr
+        end function
+        function fen_gpu_update_pressure(ctx) bind(C, name='fen_gpu_update_pressure') result(ierr)
+            import :: c_int, c_ptr
+            type(c_ptr), value :: ctx
+            integer(c_int) :: ierr
+        end function
+        function fen_gpu_checks(ctx, dt) bind(C, name='fen_gpu_checks') result(ierr)
+            import :: c_int, c_ptr, c_double
+            type(c_ptr), value :: ctx
+            real(c_double), value :: dt
+            integer(c_int) :: ierr
+        end function
+        function fen_gpu_scalar_write(ctx, field, filename) bind(C, name='fen_gpu_scalar_write') result(ierr)
+            import :: c_int, c_ptr, c_char
+            type(c_ptr), value :: ctx
+            integer(c_int), value :: field
+            character(kind=c_char), intent(in) :: filename(*)
+            integer(c_int) :: ierr
+        end function
+        function fen_gpu_scalar_read(ctx, field, filename) bind(C, name='fen_gpu_scalar_read') result(ierr)
+            import :: c_int, c_ptr, c_char
+            type(c_ptr), value :: ctx
+            integer(c_int), value :: field
+            character(kind=c_char), intent(in) :: filename(*)
+            integer(c_int) :: ierr
+        end function
+        function fen_gpu_save_state(ctx, filename) bind(C, name='fen_gpu_save_state') result(ierr)
+            import :: c_int, c_ptr, c_char
+            type(c_ptr), value :: ctx
+            character(kind=c_char), intent(in) :: filename(*)
+            integer(c_int) :: ierr
+        end function
+        function fen_gpu_load_state(ctx, filename) bind(C, name='fen_gpu_load_state') result(ierr)
+            import :: c_int, c_ptr, c_char
+            type(c_ptr), value :: ctx
+            character(kind=c_char), intent(in) :: filename(*)
+            integer(c_int) :: ierr
+        end function
+        function fen_gpu_save_fields(ctx, step, dir) bind(C, name='fen_gpu_save_fields') result(ierr)
+            import :: c_int, c_ptr, c_char
+            type(c_ptr), value :: ctx
+            integer(c_int), value :: step
+            character(kind=c_char), intent(in) :: dir(*)
+            integer(c_int) :: ierr
+        end function
+        function fen_gpu_set_forcing_hook(ctx, fn, user) bind(C, name='fen_gpu_set_forcing_hook') result(ierr)
+            import :: c_int, c_ptr, c_funptr
+            type(c_ptr), value :: ctx, user
+            type(c_funptr), value :: fn
+            integer(c_int) :: ierr
+        end function
+        function fen_gpu_profile_enable(ctx, on) bind(C, name='fen_gpu_profile_enable') result(ierr)
+            import :: c_int, c_ptr
+            type(c_ptr), value :: ctx
+            integer(c_int), value :: on
+            integer(c_int) :: ierr
+        end function
+        function fen_gpu_profile_read(ctx, max_entries, names, ms, launches, n_out) &
+                bind(C, name='fen_gpu_profile_read') result(ierr)
+            import :: c_int, c_ptr, c_double, c_char
+            type(c_ptr), value :: ctx
+            integer(c_int), value :: max_entries
+            character(kind=c_char), intent(out) :: names(32, *)
+            real(c_double), intent(out) :: ms(*)
+            integer(c_int), intent(out) :: launches(*)
+            integer(c_int), intent(out) :: n_out
+            integer(c_int) :: ierr
+        end function
+        function fen_gpu_launch_count(ctx) bind(C, name='fen_gpu_launch_count') result(n)
+            import :: c_long_long, c_ptr
+            type(c_ptr), value :: ctx
+            integer(c_long_long) :: n
+        end function
+        function fen_gpu_stream(ctx) bind(C, name='fen_gpu_stream') result(s)
+            import :: c_ptr
+            type(c_ptr), value :: ctx
+            type(c_ptr) :: s
         end function
     end interface
 
@@ -581,6 +781,108 @@ contains
         call gpu_check(fen_gpu_pull(ctx, id, c_loc(f), int(l, c_int)), 'update_halos')
         call gpu_check(fen_gpu_scalar_destroy(ctx, id), 'update_halos')
     end subroutine update_halos
+
+    !=============================================================================================
+    ! solver_mod output and restart (src/solver.f90:103-329): same files, written from the device fields
+    !=============================================================================================
+    !> C string from a Fortran one
+    pure function cstr(s) result(c)
+        character(*), intent(in) :: s
+        character(kind=c_char) :: c(len_trim(s) + 1)
+        integer :: n
+        do n = 1, len_trim(s)
+            c(n) = s(n:n)
+        end do
+        c(len_trim(s) + 1) = c_null_char
+    end function cstr
+
+    !> save_state(step), src/solver.f90:160: data/state_<step7>.raw
+    subroutine save_state(step)
+        integer, intent(in) :: step
+        character(len=7) :: sn
+        write(sn, '(I0.7)') step
+        call gpu_check(fen_gpu_save_state(ctx, cstr('data/state_'//sn//'.raw')), 'save_state')
+    end subroutine save_state
+
+    !> load_state(step), src/solver.f90:244 (also refreshes the ghost nodes, :283-297)
+    subroutine load_state(step)
+        integer, intent(in) :: step
+        character(len=7) :: sn
+        write(sn, '(I0.7)') step
+        call gpu_check(fen_gpu_load_state(ctx, cstr('data/state_'//sn//'.raw')), 'load_state')
+    end subroutine load_state
+
+    !> save_fields(step), src/solver.f90:103: data/vx_<step7>.raw, vy_, [vz_], p_, [vof_]
+    subroutine save_fields(step)
+        integer, intent(in) :: step
+        call gpu_check(fen_gpu_save_fields(ctx, int(step, c_int), cstr('data')), 'save_fields')
+    end subroutine save_fields
+
+    !> scalar%write / scalar%read of a device field (src/scalar.f90:428, :400)
+    subroutine gpu_scalar_write(field, filename)
+        integer(c_int), intent(in) :: field
+        character(*)  , intent(in) :: filename
+        call gpu_check(fen_gpu_scalar_write(ctx, field, cstr(filename)), 'scalar%write')
+    end subroutine gpu_scalar_write
+
+    subroutine gpu_scalar_read(field, filename)
+        integer(c_int), intent(in) :: field
+        character(*)  , intent(in) :: filename
+        call gpu_check(fen_gpu_scalar_read(ctx, field, cstr(filename)), 'scalar%read')
+    end subroutine gpu_scalar_read
+
+    !> print_solver_status(log_id, step, time, dt), src/navier_stokes.f90:734 (format :746)
+    subroutine print_solver_status(log_id, step, time, dt)
+        use global_mod, only : myrank
+        integer , intent(in) :: log_id, step
+        real(dp), intent(in) :: time, dt
+        character(kind=c_char) :: buf(256)
+        character(len=255) :: line
+        integer :: n
+        call gpu_check(fen_gpu_status_line(ctx, int(step, c_int), time, dt, buf, 256_c_int), 'print_solver_status')
+        line = ' '
+        do n = 1, 255
+            if (buf(n) == c_null_char) exit
+            line(n:n) = buf(n)
+        end do
+        if (myrank == 0) write(log_id, '(A)') trim(line)
+    end subroutine print_solver_status
+
+    !> host callback between the predictor and the Poisson solve: the call site of apply_ibm_forcing(v, dt)
+    !> (src/navier_stokes.f90:106-108).  `fn` is a bind(C) function (user, step, dt) -> integer(c_int); it may
+    !> gpu_pull(v%x, FEN_VX) ..., force the host arrays and gpu_push them back.
+    subroutine gpu_set_forcing_hook(fn)
+        type(c_funptr), intent(in) :: fn
+        call gpu_check(fen_gpu_set_forcing_hook(ctx, fn, c_null_ptr), 'set_forcing_hook')
+    end subroutine gpu_set_forcing_hook
+
+    !> fields_mod operators on device fields (src/fields.f90:31,120,298,175); arguments are device field ids
+    subroutine gpu_gradient(s, vx)
+        integer(c_int), intent(in) :: s, vx
+        call gpu_check(fen_gpu_gradient(ctx, s, vx), 'gradient')
+    end subroutine gpu_gradient
+    subroutine gpu_divergence(vx, s)
+        integer(c_int), intent(in) :: vx, s
+        call gpu_check(fen_gpu_divergence(ctx, vx, s), 'divergence')
+    end subroutine gpu_divergence
+    subroutine gpu_laplacian(vx, ox)
+        integer(c_int), intent(in) :: vx, ox
+        call gpu_check(fen_gpu_laplacian(ctx, vx, ox), 'laplacian')
+    end subroutine gpu_laplacian
+    subroutine gpu_center_to_face(s, vx)
+        integer(c_int), intent(in) :: s, vx
+        call gpu_check(fen_gpu_center_to_face(ctx, s, vx), 'center_to_face')
+    end subroutine gpu_center_to_face
+
+    !> scalar%max_value / scalar%integral of a device field, reduced over all ranks (src/scalar.f90:179, :201)
+    real(dp) function gpu_max_value(field)
+        integer(c_int), intent(in) :: field
+        call gpu_check(fen_gpu_max_value(ctx, field, gpu_max_value), 'max_value')
+    end function gpu_max_value
+    real(dp) function gpu_integral(field)
+        integer(c_int), intent(in) :: field
+        call gpu_check(fen_gpu_integral(ctx, field, gpu_integral), 'integral')
+    end function gpu_integral
 
     !> scalar%update_ghost_nodes on the device copy of a solver field (src/scalar.f90:223)
     subroutine update_ghost_nodes(field, ncomp)
