@@ -85,3 +85,23 @@ def test_c_abi_header_is_plain_c_and_a_c_driver_links(lib):
         pytest.skip("a device is present: the run itself is tests/test_gpu_parity.py::test_c_driver_runs")
     r = subprocess.run([exe, "16", "1"], capture_output=True, text=True)
     assert r.returncode == 2 and "no CPU fallback" in r.stderr
+
+
+def test_ctypes_signatures_match_the_header_prototypes():
+    """fen_b200/_lib.py: every argtypes list has the length of the C prototype, by-value ints / doubles are c_int /
+    c_double in the same positions, and pointer parameters are pointer-like ctypes."""
+    import ctypes as C
+    from fen_b200 import _lib
+    from tests.test_fortran_shim import c_prototypes
+    protos = c_prototypes()
+    assert set(protos) == set(_lib.SIGNATURES)
+    for name, (res, argtypes) in _lib.SIGNATURES.items():
+        params = protos[name]
+        assert len(params) == len(argtypes), (name, params, argtypes)
+        for (is_ptr, ctext), at in zip(params, argtypes):
+            if is_ptr:
+                assert at in (C.c_void_p, C.c_char_p) or hasattr(at, "contents") or hasattr(at, "_flags_"), (name, ctext, at)
+            elif re.match(r"(const\s+)?double\b", ctext):
+                assert at is C.c_double, (name, ctext, at)
+            else:
+                assert at is C.c_int, (name, ctext, at)
