@@ -16,7 +16,8 @@ Follows, in the reference's own operation order (paths relative to /root/referen
 The reference's VoF and variable-viscosity code is 2-D only (no z terms exist in compute_norm, compute_flux or the
 stress divergence), so this oracle is 2-D only.
 
-Parity pinning.  The reference ships one known-answer data set for this path,
+Parity pinning.  The reference ships two known-answer data sets for this path (the second, the rising-bubble
+benchmark curves of rising_bubble/com_ref.txt, is checked in tests/test_oracle_mf.py too).  The first is
 test/small_test/multiphase/capillary_wave/prosperetti.csv (Prosperetti's analytic capillary-wave amplitude), and its
 post-processing (capillary_wave/postpro.py:92-101) measures the error of the maximum interface amplitude against it;
 tests/test_oracle_mf.py replays that case and holds the error to the N^-1 guide line the script draws (0.4/N).  The

@@ -1,0 +1,29 @@
+"""Copies the reference's known-answer DATA for the two-phase path into fixtures.
+
+/root/reference does not exist on the GPU box, so the data sets the reference's own post-processing compares
+against travel as small .npz files.  They are data, not code:
+
+  prosperetti_capillary.npz   test/small_test/multiphase/capillary_wave/prosperetti.csv -- Prosperetti's analytic
+                              solution of the viscous capillary wave (omega_0 t, maximum interface amplitude); the
+                              curve capillary_wave/postpro.py:92-101 measures its result against.
+  rising_bubble_com_ref.npz   test/small_test/multiphase/rising_bubble/com_ref.txt -- the benchmark solution of the
+                              rising-bubble test case 1 (Hysing et al.): time, centre-of-mass height and rise velocity
+                              (columns 0, 3, 4), the curves rising_bubble/postpro.py:55-75 plots its result against.
+
+Usage (in the build container, where /root/reference is mounted):  python tests/golden/make_reference_data.py
+"""
+import os
+
+import numpy as np
+
+REF = "/root/reference/test/small_test/multiphase"
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+if __name__ == "__main__":
+    curve = np.genfromtxt(os.path.join(REF, "capillary_wave", "prosperetti.csv"), delimiter=",")
+    assert curve.shape == (738, 2)
+    np.savez_compressed(os.path.join(HERE, "prosperetti_capillary.npz"), curve=curve)
+    com = np.genfromtxt(os.path.join(REF, "rising_bubble", "com_ref.txt"))
+    assert com.shape == (2102, 5)
+    np.savez_compressed(os.path.join(HERE, "rising_bubble_com_ref.npz"), t=com[:, 0], yc=com[:, 3], uc=com[:, 4])
+    print("wrote", curve.shape, com.shape)

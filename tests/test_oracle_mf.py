@@ -2,7 +2,7 @@
 
 The reference holds ONE known-answer data set for this path: Prosperetti's analytic capillary-wave amplitude
 (test/small_test/multiphase/capillary_wave/prosperetti.csv; committed as tests/golden/prosperetti_capillary.npz by
-tests/golden/make_prosperetti.py).  Its post-processing (capillary_wave/postpro.py:92-101) takes the largest error of
+tests/golden/make_reference_data.py).  Its post-processing (capillary_wave/postpro.py:92-101) takes the largest error of
 the maximum interface amplitude over ~80 snapshots and plots it against the guide lines 0.4/N and 4/N^2; the case is
 replayed here at N = 8, 16, 32.  The VoF-only tests of the reference are plot-only; their properties are asserted:
 phase-volume conservation and the return of the reversed-vortex drop (volume_of_fluid/reversed).
@@ -164,3 +164,46 @@ def test_flat_interface_stays_at_rest():
     # phase builds its pressure up over many steps through p_hat = 2p - p_o, the projection removing the rest
     p = ns.p.I[0, :, 0]
     assert abs((p[60] - p[59]) / G.delta + 1000.0 / 850.0 * mf.GRAVITY) < 1e-9 * mf.GRAVITY
+
+
+def _rising_bubble(Nx):
+    """test/small_test/multiphase/rising_bubble/rising_bubble.f90, test case 1: walls all round (nn Poisson), free slip
+    on the side walls, density ratio 10, sigma = 24.5, beta = 2 set after init_solver (:75-81)."""
+    Ny = 2 * Nx
+    G = fo.Grid(Nx, Ny, 1, 1.0, 2.0, 1.0 / Nx, bc=["Wall"] * 4)
+    ns = mf.MultiphaseNavierStokes(G, 1000.0, 100.0, 10.0, 1.0, 24.5,
+                                   distance=lambda x, y: -(np.sqrt((x - 0.5) ** 2 + (y - 0.5) ** 2) - 0.25))
+    assert ns.poisson.variant == "nn"
+    ns.g[1] = -0.98
+    dt = ns.set_timestep(0.25)
+    ns.vf.beta = 2.0
+    ns.v.y.bc_type["left"] = ns.v.y.bc_type["right"] = 2
+    d = G.delta
+    y = ((np.arange(1, Ny + 1) - 0.5) * d)[None, :]
+    t, step, out = 0.0, 0, []
+    while t <= 3.0:
+        step += 1
+        t += dt
+        ns.navier_stokes_solver(step, dt)
+        f = ns.vof.I[..., 0]
+        iv = f.sum() * d * d                                                   # point_quantities, :131-165
+        out.append((t, (y * f).sum() * d * d / iv,
+                    (0.5 * ns.v.y.I[..., 0] * (ns.vof.sh(0, 1)[..., 0] + f)).sum() * d * d / iv, iv))
+    assert abs(ns.maxdiv) < 1e-12
+    return np.array(out)
+
+
+@pytest.mark.parametrize("Nx", [32, 64])
+def test_rising_bubble_follows_the_benchmark(Nx):
+    """The second data set the reference holds for this path: the rising-bubble benchmark solution
+    (rising_bubble/com_ref.txt, committed as tests/golden/rising_bubble_com_ref.npz).  The reference only plots its
+    curves against it (postpro.py:55-75); here the oracle's centre of mass must stay within 1.5 % of the domain
+    width of the benchmark over the whole run, its peak rise velocity within 2.5 %, with the bubble volume conserved."""
+    ref = np.load(os.path.join(GOLD, "rising_bubble_com_ref.npz"))
+    o = _rising_bubble(Nx)
+    yref = np.interp(o[:, 0], ref["t"], ref["yc"])
+    uref = np.interp(o[:, 0], ref["t"], ref["uc"])
+    assert np.abs(o[:, 1] - yref).max() < 0.015
+    assert abs(o[:, 2].max() - uref.max()) < 0.025 * uref.max()
+    assert np.abs(o[:, 2] - uref).max() < (0.012 if Nx == 32 else 0.007)        # and it tightens with resolution
+    assert abs(o[-1, 3] / o[0, 3] - 1.0) < 1e-12
