@@ -22,8 +22,8 @@ test/small_test/multiphase/capillary_wave/prosperetti.csv (Prosperetti's analyti
 post-processing (capillary_wave/postpro.py:92-101) measures the error of the maximum interface amplitude against it;
 tests/test_oracle_mf.py replays that case and holds the error to the N^-1 guide line the script draws (0.4/N).  The
 other reference tests of this path are plot-only (reversed vortex, Zalesak, reconstruction, viscous decay, rising
-bubble): their properties -- phase-volume conservation, return to the initial shape after flow reversal, viscous
-energy decay exp(-4 nu k^2 t) -- are asserted in the same test file.
+bubble shapes): their properties -- phase-volume conservation, return to the initial shape after flow reversal,
+a flat interface under gravity staying at rest -- are asserted in the same test file.
 
 Hazards reproduced on purpose (they change results):
   H13  ``vof = vof1`` (volume_of_fluid.f90:470,510) is an intrinsic derived-type assignment: it copies vof1's freshly

@@ -1,4 +1,4 @@
-"""Copies the reference's known-answer DATA for the two-phase path into fixtures.
+"""Copies the reference's known-answer DATA (literature / analytic curves its tests compare against) into fixtures.
 
 /root/reference does not exist on the GPU box, so the data sets the reference's own post-processing compares
 against travel as small .npz files.  They are data, not code:
@@ -9,6 +9,10 @@ against travel as small .npz files.  They are data, not code:
   rising_bubble_com_ref.npz   test/small_test/multiphase/rising_bubble/com_ref.txt -- the benchmark solution of the
                               rising-bubble test case 1 (Hysing et al.): time, centre-of-mass height and rise velocity
                               (columns 0, 3, 4), the curves rising_bubble/postpro.py:55-75 plots its result against.
+
+  ghia_cavity_re1000.npz      test/small_test/navier_stokes/lid_driven/uref, vref -- Ghia, Ghia & Shin's centreline
+                              velocities of the lid-driven cavity at Re = 1000 (17 points each, coordinate - 0.5), the
+                              points lid_driven/postpro.py:57-78 plots its profiles against.
 
 Usage (in the build container, where /root/reference is mounted):  python tests/golden/make_reference_data.py
 """
@@ -26,4 +30,8 @@ if __name__ == "__main__":
     com = np.genfromtxt(os.path.join(REF, "rising_bubble", "com_ref.txt"))
     assert com.shape == (2102, 5)
     np.savez_compressed(os.path.join(HERE, "rising_bubble_com_ref.npz"), t=com[:, 0], yc=com[:, 3], uc=com[:, 4])
-    print("wrote", curve.shape, com.shape)
+    lid = "/root/reference/test/small_test/navier_stokes/lid_driven"
+    uref, vref = np.genfromtxt(os.path.join(lid, "uref")), np.genfromtxt(os.path.join(lid, "vref"))
+    assert uref.shape == (17, 2) and vref.shape == (17, 2)
+    np.savez_compressed(os.path.join(HERE, "ghia_cavity_re1000.npz"), uref=uref, vref=vref)
+    print("wrote", curve.shape, com.shape, uref.shape, vref.shape)
