@@ -49,10 +49,21 @@ def transpose_blocks(ny: int, nz: int, nranks: int, rank: int):
     return out
 
 
-def alltoall_bytes_per_gpu(nx: int, ny: int, nz: int, nranks: int) -> int:
-    """Bytes one GPU sends over NVLink per transpose: half-spectrum complex, the (P-1)/P off-rank share."""
-    local = (nx // 2 + 1) * ny * (nz // nranks) * 16
+def alltoall_bytes_per_gpu(nx: int, ny: int, nz: int, nranks: int, x_periodic: bool = True) -> int:
+    """Bytes one GPU sends over NVLink per transpose, the (P-1)/P off-rank share of its slab: the half spectrum
+    (nx/2 + 1 complex per line) when x is periodic, the full width when x is a Neumann direction (the DCT variants
+    npn / nnn carry real data in a full-width complex array, poisson.cu)."""
+    width = nx // 2 + 1 if x_periodic else nx
+    local = width * ny * (nz // nranks) * 16
     return local * (nranks - 1) // nranks
+
+
+def scatter_schedule(nranks: int, rank: int, blk: int):
+    """Order in which the row-copy transpose kernel (poisson.cu: k_a2a_scatter) visits (destination, index) pairs:
+    consecutive blocks cycle over the destination ranks, starting one past the sender, so that at any moment every
+    rank is storing to a different peer.  Returns the list of ``(dest, idx)`` in block order."""
+    return [((rank + 1 + bx % nranks) % nranks, ((rank + 1 + bx % nranks) % nranks) * blk + bx // nranks)
+            for bx in range(nranks * blk)]
 
 
 def gather_handles(all_gather, blob: bytes, nranks: int) -> bytes:

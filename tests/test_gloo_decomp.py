@@ -85,6 +85,17 @@ def _worker(rank, world, port, q):
         assert float(t) == 10.0 + world - 1
         # 7. bytes of one all-to-all
         assert decomp.alltoall_bytes_per_gpu(1024, 1024, 1024, 8) == 513 * 1024 * 128 * 16 * 7 // 8
+        assert decomp.alltoall_bytes_per_gpu(64, 64, 64, 8, x_periodic=False) == 64 * 64 * 8 * 16 * 7 // 8
+        # 8. the row-copy transpose (k_a2a_scatter): every rank covers every (dest, index) pair exactly once, and at
+        #    every block position the ranks address pairwise different destinations (no receiver is shared)
+        blk = nz // world
+        sched = decomp.scatter_schedule(world, rank, blk)
+        assert sorted(i for _, i in sched) == list(range(nz))
+        assert all(dst == i // blk for dst, i in sched)
+        allsched = [None] * world
+        dist.all_gather_object(allsched, [dst for dst, _ in sched])
+        for pos in range(len(sched)):
+            assert len({allsched[r][pos] for r in range(world)}) == world
         q.put((rank, "ok"))
     except Exception as e:  # pragma: no cover
         import traceback
