@@ -247,6 +247,41 @@ def cpu_port(n, steps, warmup, threads=0):
     return n ** 3 * steps / t / 1e6, t / steps, cores, "numpy/scipy oracle (oracle/fen_oracle.py)"
 
 
+def cpu_port_channel(n, steps, warmup, threads=0):
+    """The plain-C/OpenMP restatement (oracle/fen_oracle_c.c, zwalls) on a 2n x 2n x n sample of the channel workload
+    (BASELINE configs[2]: walls in z, ppn Poisson).  Returns (Mcell-updates/s, seconds per step, threads)."""
+    from oracle import fen_oracle_c as foc
+    cores = os.cpu_count() or 1
+    nx, ny, nz = 2 * n, 2 * n, n
+    delta = 2.0 / float(np.float32(nx))
+    c = foc.NavierStokesC(nx, ny, nz, delta, 1.0, 1.0e-3, threads=threads or cores, zwalls=True)
+    _, (u, v, w, p) = init_channel_slab((nx, ny, nz), (nx, ny, nz), delta, 0, pinned=False)
+    # ghost cells of the initial condition: periodic in x / y, no-slip at the z walls (what update_ghost_nodes gives)
+    for a, kind in ((u, 1), (v, 1), (w, 2), (p, 0)):
+        a[0, :, :] = a[nx, :, :]; a[nx + 1, :, :] = a[1, :, :]
+        a[:, 0, :] = a[:, ny, :]; a[:, ny + 1, :] = a[:, 1, :]
+        if kind == 0:
+            a[:, :, 0] = a[:, :, 1]; a[:, :, nz + 1] = a[:, :, nz]
+        elif kind == 1:
+            a[:, :, 0] = -a[:, :, 1]; a[:, :, nz + 1] = -a[:, :, nz]
+        else:
+            a[:, :, 0] = 0.0; a[:, :, nz] = 0.0; a[:, :, nz + 1] = 0.0
+    c.set(foc.U, u); c.set(foc.V, v); c.set(foc.W, w); c.set(foc.P, p)
+    c.g = [1.0, 0.0, 0.0]
+    dt = min(0.25 * delta / 1.5, (1.0 / 6.0) * delta * delta / 1.0e-3)       # set_timestep(U = 1.5), CFL = 0.25
+    c.dt_o = dt
+    for s in range(warmup):
+        c.navier_stokes_solver(s + 1, dt)
+    t0 = time.perf_counter()
+    for s in range(steps):
+        c.navier_stokes_solver(warmup + s + 1, dt)
+    t = time.perf_counter() - t0
+    used = c.threads
+    assert abs(c.maxdiv) < 1e-9
+    c.destroy()
+    return nx * ny * nz * steps / t / 1e6, t / steps, used
+
+
 def run_reference(args, rank, world):
     """--impl reference: the CPU restatement of the reference (oracle/), all host threads, on a bounded sample of
     the same workload (the reference's own Fortran/MPI/FFTW build does not exist in this image)."""
@@ -264,6 +299,21 @@ def run_reference(args, rank, world):
                        "grid": [512, 1024, 1]},
             "cpu_baseline": {"value": val, "unit": "Mcell-updates/s", "cores": os.cpu_count() or 1, "kind": "port",
                              "sample": sample},
+            "e2e": {"value": val, "unit": "Mcell-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}))
+        return
+    if args.case == "channel":
+        n = min(args.cpu_size, 128)
+        val, sec, cores = cpu_port_channel(n, args.steps, args.warmup)
+        sample = ("%dx%dx%d sample of the 1024x1024x512 channel, %d steps, plain-C/OpenMP restatement "
+                  "(oracle/fen_oracle_c.c)" % (2 * n, 2 * n, n, args.steps))
+        print(json.dumps({
+            "impl": "reference", "metric": "NS timestep Mcell-updates/s", "value": val, "unit": "Mcell-updates/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sec,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "channel fp64, walls in z, ppn Poisson (CPU arm: bounded %dx%dx%d sample)"
+                                   % (2 * n, 2 * n, n), "grid": [2 * n, 2 * n, n], "nu": 1.0e-3, "CFL": 0.25},
+            "cpu_baseline": {"value": val, "unit": "Mcell-updates/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": val, "unit": "Mcell-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}))
         return
@@ -745,7 +795,15 @@ def main():
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cpu = cpu_baseline()
+        if channel:
+            _, sec, _ = cpu_port_channel(64, 1, 1)
+            ksteps = int(max(3, min(40, 15.0 / max(sec, 1e-3))))
+            val, sec, cores = cpu_port_channel(64, ksteps, 1)
+            cpu = {"value": val, "unit": "Mcell-updates/s", "cores": cores, "kind": "port",
+                   "sample": "%d steps of the same channel case at 128x128x64 (1 warm-up), plain-C/OpenMP restatement "
+                             "(oracle/fen_oracle_c.c)" % ksteps}
+        else:
+            cpu = cpu_baseline()
 
     if rank == 0:
         line = {

@@ -1,5 +1,6 @@
 /* fen_oracle_c.c -- plain C (C99 + OpenMP) restatement of FEN's single-phase 3-D fractional step on a fully
- * periodic box (the ppp path of BASELINE configs[1]).
+ * periodic box (the ppp path of BASELINE configs[1]) and, with foc_set_zwalls, on a channel: x and y periodic,
+ * walls in z, ppn Poisson = FFT in x / y + Thomas in z (BASELINE configs[2]).
  *
  * TEST INFRASTRUCTURE ONLY (same rules as oracle/fen_oracle.py): nothing under fen_b200/ may link or call this;
  * it is (1) a second, independent checker -- tests/test_oracle_c.py pins it against the numpy oracle and the
@@ -34,6 +35,8 @@ typedef struct FoC {
     double *mwn_x, *mwn_y, *mwn_z;  /* modified wavenumbers, poisson.f90:627-629, 645-647, 663-665 */
     cplx *tw_x, *tw_y, *tw_z;       /* exp(-2 pi i m / n) */
     double maxdiv, maxvel;
+    int zwall;                      /* bc(5:6) = 'Wall': Neumann p / phi, no-slip velocity, ppn Poisson */
+    double *ta, *tb, *tc;           /* tridiagonal coefficients, poisson.f90:744-757 */
 } FoC;
 
 #define IDX(s, i, j, k) ((long)(i) + (s)->sy * (long)(j) + (s)->sz * (long)(k))
@@ -118,7 +121,27 @@ void foc_destroy(FoC* s) {
                    s->lz, s->mwn_x, s->mwn_y, s->mwn_z};
     for (size_t q = 0; q < sizeof(f) / sizeof(f[0]); ++q) free(f[q]);
     free(s->C); free(s->tw_x); free(s->tw_y); free(s->tw_z);
+    free(s->ta); free(s->tb); free(s->tc);
     free(s);
+}
+
+/* grid%setup with bc(5:6) = 'Wall' + init_poisson_ppn's tridiagonal (poisson.f90:744-757): a = c = 1/delta**2,
+ * b = -2/delta**2, Neumann folding b(1) += a(1), b(nz) += c(nz), then a(1) = c(nz) = 0 */
+void foc_set_zwalls(FoC* s, int on) {
+    s->zwall = on ? 1 : 0;
+    free(s->ta); free(s->tb); free(s->tc);
+    s->ta = s->tb = s->tc = NULL;
+    if (!on) return;
+    const int n = s->nz;
+    const double d2 = s->delta * s->delta;
+    s->ta = (double*)malloc(sizeof(double) * (size_t)n);
+    s->tb = (double*)malloc(sizeof(double) * (size_t)n);
+    s->tc = (double*)malloc(sizeof(double) * (size_t)n);
+    for (int k = 0; k < n; ++k) { s->ta[k] = 1.0 / d2; s->tb[k] = -2.0 / d2; s->tc[k] = 1.0 / d2; }
+    s->tb[0] = s->tb[0] + s->ta[0];
+    s->tb[n - 1] = s->tb[n - 1] + s->tc[n - 1];
+    s->ta[0] = 0.0;
+    s->tc[n - 1] = 0.0;
 }
 /* 0 p, 1 phi, 2 u, 3 v, 4 w, 5..7 dv_o */
 double* foc_field(FoC* s, int id) {
@@ -155,8 +178,148 @@ void foc_update_ghosts(const FoC* s, double* f) {
         }
 }
 
+/* update_ghost_nodes with the channel's wiring (navier_stokes.f90:780-1017): x and y periodic as above; at the z
+ * walls kind 0 = p, phi: Neumann (scalar.f90:361-362, :384-385); kind 1 = u, v: Dirichlet 0 on a tangential component,
+ * ghost = 2 bc - f (:353-354, :375-376); kind 2 = w, the wall-normal component: ghost = bc and, on the back wall, the
+ * last interior face too (:355, :377-378; hazard H3).  Periodic box: all kinds are the periodic copy. */
+static void update_ghosts_kind(const FoC* s, double* f, int kind) {
+    if (!s->zwall) { foc_update_ghosts(s, f); return; }
+    const int nx = s->nx, ny = s->ny, nz = s->nz;
+#pragma omp parallel for schedule(static)
+    for (int k = 0; k <= nz + 1; ++k)
+        for (int j = 0; j <= ny + 1; ++j) {
+            f[IDX(s, 0, j, k)] = f[IDX(s, nx, j, k)];
+            f[IDX(s, nx + 1, j, k)] = f[IDX(s, 1, j, k)];
+        }
+#pragma omp parallel for schedule(static)
+    for (int k = 0; k <= nz + 1; ++k)
+        for (int i = 0; i <= nx + 1; ++i) {
+            f[IDX(s, i, 0, k)] = f[IDX(s, i, ny, k)];
+            f[IDX(s, i, ny + 1, k)] = f[IDX(s, i, 1, k)];
+        }
+    const double bc = 0.0;
+#pragma omp parallel for schedule(static)
+    for (int j = 0; j <= ny + 1; ++j)
+        for (int i = 0; i <= nx + 1; ++i) {
+            if (kind == 0) {
+                f[IDX(s, i, j, 0)] = f[IDX(s, i, j, 1)];
+                f[IDX(s, i, j, nz + 1)] = f[IDX(s, i, j, nz)];
+            } else if (kind == 1) {
+                f[IDX(s, i, j, 0)] = 2.0 * bc - f[IDX(s, i, j, 1)];
+                f[IDX(s, i, j, nz + 1)] = 2.0 * bc - f[IDX(s, i, j, nz)];
+            } else {
+                f[IDX(s, i, j, 0)] = bc;
+                f[IDX(s, i, j, nz)] = bc;
+                f[IDX(s, i, j, nz + 1)] = bc;
+            }
+        }
+}
+
+/* ---- Poisson: poisson_solver_ppn, src/poisson.f90:1038-1173 --------------------------------------------------- */
+static void poisson_solve_ppn(FoC* s, double* phi) {
+    const int nx = s->nx, ny = s->ny, nz = s->nz, mc = s->mc;
+    cplx* C = s->C;
+    const double fnx = f32(nx), fny = f32(ny);
+#pragma omp parallel
+    {
+        const int nmax = nx > ny ? (nx > nz ? nx : nz) : (ny > nz ? ny : nz);
+        cplx* line = (cplx*)malloc(sizeof(cplx) * (size_t)nmax);
+        cplx* d1 = (cplx*)malloc(sizeof(cplx) * (size_t)nz);
+        double* c1 = (double*)malloc(sizeof(double) * (size_t)nz);
+        /* r2c along x and outc_x = outc_x/float(nx)  (:1066-1074) */
+#pragma omp for collapse(2) schedule(static)
+        for (int k = 1; k <= nz; ++k)
+            for (int j = 1; j <= ny; ++j) {
+                const double* row = phi + IDX(s, 1, j, k);
+                for (int i = 0; i < nx; ++i) { line[i].re = row[i]; line[i].im = 0.0; }
+                fft(line, nx, -1, s->tw_x);
+                cplx* dst = C + (size_t)mc * ((size_t)(j - 1) + (size_t)ny * (k - 1));
+                for (int i = 0; i < mc; ++i) { dst[i].re = line[i].re / fnx; dst[i].im = line[i].im / fnx; }
+            }
+        /* c2c along y and /float(ny)  (:1080-1087) */
+#pragma omp for collapse(2) schedule(static)
+        for (int k = 0; k < nz; ++k)
+            for (int i = 0; i < mc; ++i) {
+                cplx* base = C + i + (size_t)mc * ny * k;
+                for (int j = 0; j < ny; ++j) line[j] = base[(size_t)mc * j];
+                fft(line, ny, -1, s->tw_y);
+                for (int j = 0; j < ny; ++j) { base[(size_t)mc * j].re = line[j].re / fny; base[(size_t)mc * j].im = line[j].im / fny; }
+            }
+        /* Thomas along z, one (i, j) system at a time, the reference's expressions (:1092-1135) */
+        const double *a = s->ta, *b = s->tb, *c = s->tc;
+#pragma omp for collapse(2) schedule(static)
+        for (int j = 0; j < ny; ++j)
+            for (int i = 0; i < mc; ++i) {
+                cplx* base = C + i + (size_t)mc * j;
+                const size_t st = (size_t)mc * ny;
+                const double mx = s->mwn_x[i], my = s->mwn_y[j];
+                double factor = 1.0 / (b[0] + mx + my);                                  /* :1096 */
+                c1[0] = c[0] * factor;
+                d1[0].re = base[0].re * factor; d1[0].im = base[0].im * factor;
+                for (int k = 1; k < nz - 1; ++k) {                                       /* :1102-1110 */
+                    factor = 1.0 / (b[k] + mx + my - a[k] * c1[k - 1]);
+                    c1[k] = c[k] * factor;
+                    d1[k].re = (base[st * k].re - a[k] * d1[k - 1].re) * factor;
+                    d1[k].im = (base[st * k].im - a[k] * d1[k - 1].im) * factor;
+                }
+                if (nz > 1) {                                                            /* :1112-1121 */
+                    const int k = nz - 1;
+                    factor = (b[k] + mx + my - a[k] * c1[k - 1]);
+                    if (factor != 0.0) {
+                        d1[k].re = (base[st * k].re - a[k] * d1[k - 1].re) / factor;
+                        d1[k].im = (base[st * k].im - a[k] * d1[k - 1].im) / factor;
+                    } else {
+                        d1[k].re = 0.0; d1[k].im = 0.0;                                  /* exact-zero pivot, hazard H5 */
+                    }
+                }
+                base[st * (nz - 1)] = d1[nz - 1];                                        /* :1124-1128 */
+                for (int k = nz - 2; k >= 0; --k) {                                      /* :1129-1135 */
+                    base[st * k].re = d1[k].re - c1[k] * base[st * (k + 1)].re;
+                    base[st * k].im = d1[k].im - c1[k] * base[st * (k + 1)].im;
+                }
+            }
+        /* inverse y (:1141-1145) */
+#pragma omp for collapse(2) schedule(static)
+        for (int k = 0; k < nz; ++k)
+            for (int i = 0; i < mc; ++i) {
+                cplx* base = C + i + (size_t)mc * ny * k;
+                for (int j = 0; j < ny; ++j) line[j] = base[(size_t)mc * j];
+                fft(line, ny, +1, s->tw_y);
+                for (int j = 0; j < ny; ++j) base[(size_t)mc * j] = line[j];
+            }
+        /* phi%f = 0, then c2r along x (:1151-1156) */
+#pragma omp for schedule(static)
+        for (long q = 0; q < s->n; ++q) phi[q] = 0.0;
+#pragma omp for collapse(2) schedule(static)
+        for (int k = 1; k <= nz; ++k)
+            for (int j = 1; j <= ny; ++j) {
+                const cplx* src = C + (size_t)mc * ((size_t)(j - 1) + (size_t)ny * (k - 1));
+                for (int i = 0; i < mc; ++i) line[i] = src[i];
+                line[0].im = 0.0;
+                line[nx / 2].im = 0.0;
+                for (int i = 1; i < nx - nx / 2; ++i) { line[nx - i].re = src[i].re; line[nx - i].im = -src[i].im; }
+                fft(line, nx, +1, s->tw_x);
+                double* row = phi + IDX(s, 1, j, k);
+                for (int i = 0; i < nx; ++i) row[i] = line[i].re;
+            }
+        free(line); free(d1); free(c1);
+    }
+    /* mean removal: the serial running sum of one rank, then phi%f = phi%f - mean/float(nx*ny*nz) over the WHOLE array
+     * (:1159-1171; hazards H4, H8) */
+    double mean_phi = 0.0;
+    for (int k = 1; k <= nz; ++k)
+        for (int j = 1; j <= ny; ++j) {
+            const double* row = phi + IDX(s, 1, j, k);
+            for (int i = 0; i < nx; ++i) mean_phi = mean_phi + row[i];
+        }
+    const double shift = mean_phi / f32((long)nx * ny * nz);
+#pragma omp parallel for schedule(static)
+    for (long q = 0; q < s->n; ++q) phi[q] = phi[q] - shift;
+}
+
 /* ---- Poisson: poisson_solver_ppp, src/poisson.f90:941-1034 -------------------------------------------------- */
 void foc_poisson_solve(FoC* s, double* phi) {
+    if (s->zwall) { poisson_solve_ppn(s, phi); return; }
     const int nx = s->nx, ny = s->ny, nz = s->nz, mc = s->mc;
     cplx* C = s->C;
     /* r2c along x, one line per (j, k)  (:965-969); only nx/2+1 outputs are defined (hazard H7) */
@@ -308,7 +471,7 @@ static void predicted_velocity_field(FoC* s, double dt) {
     t = s->u; s->u = s->lx; s->lx = t;
     t = s->v; s->v = s->ly; s->ly = t;
     t = s->w; s->w = s->lz; s->lz = t;
-    foc_update_ghosts(s, s->u); foc_update_ghosts(s, s->v); foc_update_ghosts(s, s->w);   /* :208 */
+    update_ghosts_kind(s, s->u, 1); update_ghosts_kind(s, s->v, 1); update_ghosts_kind(s, s->w, 2);   /* :208 */
 }
 
 /* navier_stokes_solver, navier_stokes.f90:50-136 (constant_CFL off) */
@@ -329,7 +492,7 @@ void foc_step(FoC* s, double dt) {
                 s->phi[c] = d * s->rho / dt;
             }
     foc_poisson_solve(s, s->phi);                                             /* :123 */
-    foc_update_ghosts(s, s->phi);                                             /* :124 */
+    update_ghosts_kind(s, s->phi, 0);                                         /* :124 */
     /* correct_velocity_field (:505-546): v -= grad(phi)*dt/rhof ; update_pressure (:550-566): p += phi */
     const double* f = s->phi;
 #pragma omp parallel for collapse(2) schedule(static)
@@ -342,8 +505,8 @@ void foc_step(FoC* s, double dt) {
                 s->w[c] = s->w[c] - ((f[c + sz] - f[c]) * id) * dt / rf;
                 s->p[c] = s->p[c] + f[c];
             }
-    foc_update_ghosts(s, s->u); foc_update_ghosts(s, s->v); foc_update_ghosts(s, s->w);   /* :544 */
-    foc_update_ghosts(s, s->p);                                               /* :564 */
+    update_ghosts_kind(s, s->u, 1); update_ghosts_kind(s, s->v, 1); update_ghosts_kind(s, s->w, 2);   /* :544 */
+    update_ghosts_kind(s, s->p, 0);                                           /* :564 */
     /* checks (:570-619): signed max of the divergence (H6), max |u|+|v|+|w| */
     double md = -1.0e300, mv = 0.0;
 #pragma omp parallel for collapse(2) schedule(static) reduction(max : md, mv)

@@ -1,4 +1,5 @@
-"""ctypes front end of the plain-C restatement (oracle/fen_oracle_c.c): the periodic-box (ppp) fractional step.
+"""ctypes front end of the plain-C restatement (oracle/fen_oracle_c.c): the periodic-box (ppp) fractional step and,
+with ``zwalls=True``, the channel (x / y periodic, walls in z, ppn Poisson).
 
 TEST INFRASTRUCTURE ONLY -- see the header of fen_oracle_c.c.  Mirrors the small part of fen_oracle.NavierStokes
 the checks and the CPU baseline need."""
@@ -32,6 +33,7 @@ def load():
         lib.foc_maxdiv.argtypes = [C.c_void_p]
         lib.foc_maxcfl.restype = C.c_double
         lib.foc_maxcfl.argtypes = [C.c_void_p, C.c_double]
+        lib.foc_set_zwalls.argtypes = [C.c_void_p, C.c_int]
         lib.foc_threads.restype = C.c_int
         lib.foc_set_threads.argtypes = [C.c_int]
         _lib = lib
@@ -39,9 +41,10 @@ def load():
 
 
 class NavierStokesC:
-    """Periodic 3-D single-phase solver state in C; fields go in and out as Fortran-ordered ghosted arrays."""
+    """3-D single-phase solver state in C (periodic box or channel); fields go in and out as Fortran-ordered ghosted
+    arrays."""
 
-    def __init__(self, nx, ny, nz, delta, density=1.0, viscosity=1.0, threads=0):
+    def __init__(self, nx, ny, nz, delta, density=1.0, viscosity=1.0, threads=0, zwalls=False):
         self.lib = load()
         if threads:
             self.lib.foc_set_threads(int(threads))
@@ -51,6 +54,8 @@ class NavierStokesC:
         assert self.lib.foc_field_size(self.h) == self.shape[0] * self.shape[1] * self.shape[2]
         self.dt_o = 0.0
         self.g = [0.0, 0.0, 0.0]
+        if zwalls:                       # channel: bc(5:6) = 'Wall' -> ppn Poisson, no-slip walls in z
+            self.lib.foc_set_zwalls(self.h, 1)
 
     @property
     def threads(self):

@@ -62,3 +62,59 @@ def test_c_steps_match_numpy_oracle_and_golden(threads):
         c.navier_stokes_solver(s, dt)
     assert rel(c.get(foc.U), nso.v.x.f) < 1e-12 and abs(c.maxdiv) < 1e-13
     c.destroy()
+
+
+ZWALLS = ["Periodic"] * 4 + ["Wall", "Wall"]
+
+
+@pytest.mark.parametrize("n", [(16, 16, 8), (32, 16, 24)])
+def test_c_poisson_ppn_matches_numpy_oracle(n):
+    """poisson_solver_ppn restated twice: explicit per-system Thomas loops in C vs whole-array numpy, incl. the
+    exactly-zero last pivot of the singular mode (hazard H5) and the mean removal."""
+    G = fo.Grid(n[0], n[1], n[2], 1.0, n[1] / n[0], n[2] / n[0], bc=ZWALLS)
+    rng = np.random.default_rng(6)
+    rhs = rng.standard_normal(n)
+    rhs -= rhs.mean()
+    po = fo.Scalar(G, 1)
+    po.I[...] = rhs
+    ps = fo.PoissonSolver(po)
+    assert ps.variant == "ppn"
+    ps.solve(po)
+    c = foc.NavierStokesC(n[0], n[1], n[2], G.delta, zwalls=True)
+    a = np.zeros((n[0] + 2, n[1] + 2, n[2] + 2), order="F")
+    a[1:-1, 1:-1, 1:-1] = rhs
+    c.solve_poisson(a)
+    assert rel(a[1:-1, 1:-1, 1:-1], po.I) < 1e-12
+    assert abs(a[1:-1, 1:-1, 1:-1].mean()) < 1e-14
+    c.destroy()
+
+
+@pytest.mark.parametrize("threads", [1, 4])
+def test_c_channel_steps_match_numpy_oracle_and_golden(threads):
+    """BASELINE configs[2] in miniature (the committed channel fixture): walls in z, body force, ppn Poisson."""
+    g = np.load(os.path.join(GOLD, "ns_channel_16x16x8_3steps.npz"))
+    n, L = [int(x) for x in g["n"]], [float(x) for x in g["L"]]
+    Go = fo.Grid(n[0], n[1], n[2], L[0], L[1], L[2], bc=[str(b) for b in g["bc"]])
+    nso = fo.NavierStokes(Go, 1.0, float(g["nu"]))
+    nso.g = [float(x) for x in g["g"]]
+    fo.init_channel(nso)
+    assert np.array_equal(nso.v.x.f, g["u0"])
+    dt = nso.set_timestep(float(g["U"]))
+    c = foc.NavierStokesC(n[0], n[1], n[2], Go.delta, 1.0, float(g["nu"]), threads=threads, zwalls=True)
+    c.dt_o = dt
+    c.g = list(nso.g)
+    for fid, f in ((foc.P, nso.p), (foc.U, nso.v.x), (foc.V, nso.v.y), (foc.W, nso.v.z)):
+        c.set(fid, f.f)
+    for s in range(1, int(g["steps"]) + 1):
+        nso.navier_stokes_solver(s, dt)
+        c.navier_stokes_solver(s, dt)
+    for key, fid, f in (("u", foc.U, nso.v.x), ("v", foc.V, nso.v.y), ("w", foc.W, nso.v.z), ("p", foc.P, nso.p)):
+        got = c.get(fid)
+        assert rel(got, f.f) < 1e-12, key                  # ghosts included: the wall wiring is the same
+        assert rel(got, g[key]) < 1e-12, key               # committed fixture
+    assert abs(c.maxCFL(dt) - nso.maxCFL) < 1e-13 and abs(c.maxdiv - nso.maxdiv) < 1e-13
+    for s in range(4, 10):
+        nso.navier_stokes_solver(s, dt)
+        c.navier_stokes_solver(s, dt)
+    assert rel(c.get(foc.U), nso.v.x.f) < 1e-12 and rel(c.get(foc.P), nso.p.f) < 1e-11
+    c.destroy()
