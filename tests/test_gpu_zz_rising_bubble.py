@@ -1,0 +1,113 @@
+"""GPU parity of the rising-bubble driver (test/small_test/multiphase/rising_bubble/rising_bubble.f90, test case 1):
+the only two-phase case of the reference with walls all round, i.e. the two-phase step over the `nn` Poisson variant
+(DCT in x, Thomas in y) with free-slip side walls.  Oracle: oracle/fen_oracle_mf.py, pinned against the benchmark
+data the reference ships (tests/test_oracle_mf.py::test_rising_bubble_follows_the_benchmark).
+
+FIRST-RUN STATUS: this file was written after the round's GPU budget was spent, so it has not executed on a B200 yet.
+It is marked xfail(strict=False) for that reason alone -- an XPASS in the report is the expected outcome, and the mark
+goes away with the first GPU session of the next round.  It sorts last among the GPU files so that nothing runs after
+it in the same process."""
+import numpy as np
+import pytest
+
+import fen_b200 as fb
+from oracle import fen_oracle as fo
+from oracle import fen_oracle_mf as mf
+
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.xfail(strict=False, reason="not yet run on a GPU (written after the round's GPU budget was "
+                                                     "spent): first run is round 2")]
+
+
+def rel_l2(a, b):
+    n = np.linalg.norm(b.ravel())
+    return np.linalg.norm((a - b).ravel()) / (n if n > 0 else 1.0)
+
+
+def bubble(x, y):                       # rising_bubble.f90:104-116 (positive inside the light phase)
+    return -(np.sqrt((x - 0.5) ** 2 + (y - 0.5) ** 2) - 0.25)
+
+
+def point_quantities(vof, vy, d):       # rising_bubble.f90:131-165: volume, centre of mass, rise velocity
+    Ny = vof.shape[1]
+    y = ((np.arange(1, Ny + 1) - 0.5) * d)[None, :]
+    iv = vof.sum() * d * d
+    fy = np.empty_like(vof)
+    fy[:, :-1] = 0.5 * (vof[:, 1:] + vof[:, :-1])
+    return iv, (y * vof).sum() * d * d / iv, fy
+
+
+def bubble_pair(Nx):
+    Ny = 2 * Nx
+    bc = ["Wall"] * 4
+    Go = fo.Grid(Nx, Ny, 1, 1.0, 2.0, 1.0 / Nx, bc=bc)
+    Gg = fb.grid().setup(Nx, Ny, 1, 1.0, 2.0, 1.0 / Nx, bc=bc)
+    ons = mf.MultiphaseNavierStokes(Go, 1000.0, 100.0, 10.0, 1.0, 24.5, distance=bubble)
+    ons.g[1] = -0.98
+    gns = fb.MultiphaseSolver(Gg)
+    gns.rho_0, gns.rho_1, gns.mu_0, gns.mu_1, gns.sigma = 1000.0, 100.0, 10.0, 1.0, 24.5
+    gns.g = [0.0, -0.98, 0.0]
+    gns.init_solver(lambda x, y: float(bubble(x, y)))
+    odt = ons.set_timestep(0.25)
+    gdt = gns.set_timestep(0.25)
+    assert gdt == odt
+    ons.vf.beta = 2.0                   # :75-81: beta and the free-slip side walls are set after init_solver
+    gns.beta = 2.0
+    for f in ("left", "right"):
+        ons.v.y.bc_type[f] = 2
+        gns.v.y.set_bc_type(f, 2)
+    return Go, Gg, ons, gns, odt
+
+
+def test_rising_bubble_steps_match_oracle():
+    Go, Gg, ons, gns, dt = bubble_pair(16)
+    assert gns.poisson_variant == "nn" and ons.poisson.variant == "nn"
+    for face in fo.FACES[:4]:
+        for a, b in ((gns.vof, ons.vof), (gns.p, ons.p), (gns.p_hat, ons.p_hat), (gns.rho, ons.rho),
+                     (gns.v.x, ons.v.x), (gns.v.y, ons.v.y)):
+            assert a.get_bc_type(face) == b.bc_type[face], face
+    tol = {1: 1e-12, 6: 1e-10}
+    for s in range(1, 7):
+        ons.navier_stokes_solver(s, dt)
+        gns.navier_stokes_solver(s, dt)
+        if s in tol:
+            gns.v.pull(); gns.p.pull(); gns.vof.pull()
+            # the bubble starts from rest: u, v are O(g dt) after one step, so their relative L2 is a fair measure
+            errs = {"u": rel_l2(gns.v.x.I, ons.v.x.I), "v": rel_l2(gns.v.y.I, ons.v.y.I),
+                    "p": rel_l2(gns.p.I, ons.p.I), "vof": float(np.abs(gns.vof.I - ons.vof.I).max())}
+            assert max(errs.values()) < tol[s], (s, errs)
+            md, mc = gns.status()
+            assert abs(md - ons.maxdiv) < 1e-9 and abs(mc - ons.maxCFL) <= 1e-10 * max(ons.maxCFL, 1e-300)
+    # the side walls are free slip (no tangential Dirichlet value was imposed) and impermeable
+    gns.v.x.pull(); gns.v.y.pull()
+    assert np.abs(gns.v.x.I[-1, :, 0]).max() == 0.0
+    assert np.array_equal(gns.v.y.f[0, 1:-1, 1], gns.v.y.f[1, 1:-1, 1])
+    # point quantities of the driver
+    d = Go.delta
+    ivg, ycg, _ = point_quantities(gns.vof.I[..., 0], gns.v.y.I[..., 0], d)
+    ivo, yco, _ = point_quantities(ons.vof.I[..., 0], ons.v.y.I[..., 0], d)
+    assert abs(ivg - ivo) < 1e-12 * ivo and abs(ycg - yco) < 1e-12
+    Gg.destroy()
+
+
+def test_rising_bubble_rises_and_keeps_its_volume():
+    """The property the reference plots (postpro.py:55-75), on the GPU path alone at 32 x 64 for 400 steps: the
+    bubble volume is conserved to round-off, its centre of mass moves up monotonically once the flow has started, and
+    the velocity stays divergence free."""
+    Go, Gg, ons, gns, dt = bubble_pair(32)
+    d = Go.delta
+    gns.vof.pull()
+    iv0, yc0, _ = point_quantities(gns.vof.I[..., 0].copy(), None, d)
+    ycs = [yc0]
+    for s in range(1, 401):
+        gns.navier_stokes_solver(s, dt)
+        if s % 100 == 0:
+            gns.vof.pull()
+            iv, yc, _ = point_quantities(gns.vof.I[..., 0], None, d)
+            assert abs(iv / iv0 - 1.0) < 1e-12
+            ycs.append(yc)
+            md, _ = gns.status()
+            assert abs(md) < 1e-9
+    assert all(b > a for a, b in zip(ycs, ycs[1:]))
+    assert ycs[-1] > yc0 + 1e-4
+    Gg.destroy()
