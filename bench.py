@@ -519,6 +519,38 @@ def run_wave2d(args, local_rank):
     G.destroy()
 
 
+def nccl_alltoall_reference(nx, ny, nz, world, x_periodic=True, iters=5):
+    """What one y<->z transpose of the Poisson solver costs when it is a separate library collective: NCCL
+    ``all_to_all_single`` over this rank's spectral slab in ``world`` equal blocks (the plain replacement of 2decomp's
+    transpose_y_to_z, src/poisson.f90:982,1015).  The pack / unpack passes such an implementation also needs are NOT
+    timed, so this is a lower bound of an NCCL-based transpose; the product's transposes are the epilogues of its own
+    FFT / Thomas kernels (poisson.cu), reported beside it.  Max over ranks, CUDA events on torch's current stream
+    (the stream NCCL is enqueued from)."""
+    import torch
+    import torch.distributed as dist
+    from fen_b200 import decomp
+    sent = decomp.alltoall_bytes_per_gpu(nx, ny, nz, world, x_periodic)
+    n = sent // (world - 1) // 8 * world          # doubles in the whole slab, a multiple of world
+    src = torch.zeros(n, dtype=torch.float64, device="cuda")
+    dst = torch.empty_like(src)
+    for _ in range(2):
+        dist.all_to_all_single(dst, src)
+    torch.cuda.synchronize()
+    dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        dist.all_to_all_single(dst, src)
+    e1.record()
+    torch.cuda.synchronize()
+    t = torch.tensor([e0.elapsed_time(e1) / iters], device="cuda", dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    del src, dst
+    return {"ms": ms, "bus_GBs": sent / (ms * 1e-3) / 1e9, "frac": sent / (ms * 1e-3) / 1e9 / 900.0,
+            "what": "torch.distributed all_to_all_single (NCCL) of the same slab, %d iterations, no pack/unpack" % iters}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -530,6 +562,8 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-nccl-baseline", action="store_true",
+                    help="N > 1: skip the NCCL all_to_all_single timing reported beside the fused transposes")
     ap.add_argument("--case", default="tgv", choices=["tgv", "channel", "wave2d"],
                     help="tgv: BASELINE configs[1] (headline, weak scaling); channel: configs[2], 2n x 2n x n walls in z")
     ap.add_argument("--grid", default="", help="explicit global grid nx,ny,nz for --case tgv (tuning aid)")
@@ -767,6 +801,11 @@ def main():
         for kname in ("fwd", "bwd"):
             v = nvlink[kname + "_bus_GBs"]
             nvlink[kname + "_frac"] = v / 900.0 if v else None
+        if not args.no_nccl_baseline:
+            try:
+                nvlink["nccl_alltoall"] = nccl_alltoall_reference(nx, ny, nz, world)
+            except Exception as exc:      # a reported baseline: never lose the bench line over it
+                nvlink["nccl_alltoall"] = {"unavailable": repr(exc)[:200]}
 
     # ---- end to end: host (pinned) arrays in, host arrays out, every step -----------------------
     e2e = None

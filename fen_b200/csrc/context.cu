@@ -245,15 +245,15 @@ int fen_gpu_create(const fen_grid_desc* d, fen_ctx** out) {
     if (e != cudaSuccess || ndev == 0)
         return set_error(FEN_ERR_CUDA, "no CUDA device: libfen_gpu has no CPU fallback (%s)",
                          e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
-    fen_ctx* c = new fen_ctx();
+    int device = d->device;
+    if (device >= 0) FEN_CUDA(cudaSetDevice(device));
+    else FEN_CUDA(cudaGetDevice(&device));
+    cudaStream_t stream = nullptr;
+    FEN_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+    fen_ctx* c = new fen_ctx();           // from here on a failure goes through fen_gpu_destroy: nothing leaks
     c->g = *d;
-    if (d->device >= 0) {
-        FEN_CUDA(cudaSetDevice(d->device));
-        c->device = d->device;
-    } else {
-        FEN_CUDA(cudaGetDevice(&c->device));
-    }
-    FEN_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    c->device = device;
+    c->stream = stream;
     Layout& L = c->L;
     L.nx = d->nx;
     L.ny = d->ny;
@@ -271,7 +271,8 @@ int fen_gpu_create(const fen_grid_desc* d, fen_ctx** out) {
     c->prm.CFL = 1.0;                     // :24
     c->prm.dt_o = 0.0;
     c->prm.constant_CFL = 0;              // :42
-    FEN_TRY(ensure_red(c));               // reduction scratch: nothing is allocated inside a step
+    const int r = ensure_red(c);          // reduction scratch: nothing is allocated inside a step
+    if (r != FEN_OK) { fen_gpu_destroy(c); return r; }
     *out = c;
     return FEN_OK;
 }

@@ -25,6 +25,7 @@
 
 #include "fen_internal.cuh"
 #include "fft_core.cuh"
+#include "fft_any.cuh"
 
 namespace fen {
 
@@ -38,6 +39,7 @@ struct Poisson {
     double2* C = nullptr;           // [PC][ny][nzl]
     double2* Cz = nullptr;          // [PC][nyl][nz] (multi-rank only; == C on one rank)
     double2 *tw_x = nullptr, *twr_x = nullptr, *tw_y = nullptr, *tw_z = nullptr;
+    double2* tw_xa = nullptr;       // exp(-2 pi i n / nx), n < nx: any-length path of a periodic x direction (fft_any.cuh)
     double2 *twq_x = nullptr, *twq_y = nullptr;   // exp(-i pi k / (2n)): DCT half-sample phases (Neumann directions)
     double *mwn_x = nullptr, *mwn_y = nullptr, *mwn_z = nullptr;
     double *ta = nullptr, *tb = nullptr, *tc = nullptr;   // tridiagonal a, b, c
@@ -1074,13 +1076,44 @@ void poisson_destroy(fen_ctx* c) {
     }
     for (void* q : {(void*)p->tw_x, (void*)p->twr_x, (void*)p->tw_y, (void*)p->tw_z, (void*)p->twq_x, (void*)p->twq_y,
                     (void*)p->mwn_x, (void*)p->mwn_y, (void*)p->mwn_z, (void*)p->ta, (void*)p->tb,
-                    (void*)p->tc, (void*)p->c1})
+                    (void*)p->tc, (void*)p->c1, (void*)p->tw_xa})
         if (q) cudaFree(q);
     delete p;
     c->ps = nullptr;
 }
 
 const char* poisson_variant(fen_ctx* c) { return c->ps ? c->ps->variant : ""; }
+
+// ---- any-length path (fft_any.cuh): lengths the tuned kernels do not cover -------------------------------------
+// tuned kernels: powers of two up to `maxn`; everything else any_supported() accepts goes through k_any<...>
+static bool tuned_len(int n, int maxn) { return pow2(n) && n <= maxn; }
+
+template <class K> static int launch_any(fen_ctx* c, const char* name, const typename K::Args& a, dim3 grid, int L, int nl) {
+    static bool attr_done = false;
+    if (!attr_done) {
+        FEN_CUDA(cudaFuncSetAttribute(k_any<K>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)any_smem_bytes(ANY_MAX_L, 1)));
+        attr_done = true;
+    }
+    FEN_LAUNCH(c, name, k_any<K><<<grid, ANY_THREADS, any_smem_bytes(L, nl), c->stream>>>(a, nl * L));
+    FEN_CUDA(cudaGetLastError());
+    return FEN_OK;
+}
+static AnyLayout any_layout(const Layout& L) {
+    AnyLayout l;
+    l.xoff = L.xoff; l.sy = L.sy; l.sz = L.sz;
+    return l;
+}
+static int any_rows(fen_ctx* c, const char* name, bool dct, int nx, const Layout& L, double* f, double2* C, int PC, int ny,
+                    int nrows, const double2* tw, const double2* twq, double scale, bool inverse) {
+    AnyRowsArgs a;
+    a.P = any_plan(nx);
+    if (a.P.L != nx || !tw) return set_error(FEN_ERR_UNSUPPORTED, "x transform length %d not supported", nx);
+    a.NR = any_lines_per_block(nx); a.inverse = inverse ? 1 : 0; a.lay = any_layout(L); a.f = f; a.C = C; a.PC = PC;
+    a.ny = ny; a.nrows = nrows; a.tw = tw; a.twq = twq; a.scale = scale;
+    const dim3 grid((nrows + a.NR - 1) / a.NR);
+    return dct ? launch_any<AnyRowsDct>(c, name, a, grid, nx, a.NR) : launch_any<AnyRowsC>(c, name, a, grid, nx, a.NR);
+}
 
 template <int M> static int set_smem_x() {
     const int bytes = (M + 1) * XIS * (int)sizeof(double2);
@@ -1147,6 +1180,11 @@ template <int M> static int launch_x(fen_ctx* c, const XArgs& a, bool fwd, const
 }
 
 static int dispatch_x(fen_ctx* c, int M, const XArgs& a, bool fwd, const DivArgs* dv = nullptr) {
+    if (!tuned_len(a.L.nx, 2048)) {
+        if (dv) return set_error(FEN_ERR_STATE, "the fused right-hand side needs a power-of-two x length");
+        return any_rows(c, fwd ? "fft_x_r2c_any" : "fft_x_c2r_any", false, a.L.nx, a.L, a.f, a.C, a.PC, a.ny, a.nrows,
+                        c->ps->tw_xa, nullptr, a.scale, !fwd);
+    }
     switch (M) {
 #define FEN_CASE(m) case m: return launch_x<m>(c, a, fwd, dv);
         FEN_CASE(1) FEN_CASE(2) FEN_CASE(4) FEN_CASE(8) FEN_CASE(16) FEN_CASE(32) FEN_CASE(64)
@@ -1201,6 +1239,16 @@ template <int Lf, int NL> static int launch_lines(fen_ctx* c, const LArgs& a, in
 }
 
 static int dispatch_lines(fen_ctx* c, int Lf, const LArgs& a, int mode, int PC, int nouter, const ScArgs* sc = nullptr) {
+    if (!tuned_len(Lf, 2048)) {
+        if (sc || a.cx0) return set_error(FEN_ERR_UNSUPPORTED, "any-length transforms (%d) run on one rank", Lf);
+        AnyLinesArgs q;
+        q.P = any_plan(Lf);
+        if (q.P.L != Lf) return set_error(FEN_ERR_UNSUPPORTED, "FFT length %d not supported", Lf);
+        q.NL = any_lines_per_block(Lf); q.mode = mode; q.C = a.C; q.sl = a.sl; q.so = a.so; q.o0 = a.o0; q.tw = a.tw;
+        q.scale = a.scale; q.lx = a.lx; q.lo = a.lo; q.ll = a.ll; q.norm = a.norm;
+        return launch_any<AnyLines>(c, mode == 0 ? "fft_lines_fwd_any" : (mode == 1 ? "fft_lines_inv_any" : "fft_solve_any"),
+                                    q, dim3(PC / q.NL, nouter), Lf, q.NL);
+    }
     // tuning switch: 4 lines (64 B) per block instead of 8 -- more, smaller blocks per SM
     static const bool nl4 = getenv("FEN_FFT_NL4") != nullptr;
     static const bool nl4_1024 = getenv("FEN_FFT_NL4_1024") != nullptr;
@@ -1242,6 +1290,9 @@ template <int N> static int launch_dct_x(fen_ctx* c, const DArgs& a, bool fwd) {
     return FEN_OK;
 }
 static int dispatch_dct_x(fen_ctx* c, int N, const DArgs& a, bool fwd) {
+    if (!tuned_len(N, 1024))
+        return any_rows(c, fwd ? "dct_x_fwd_any" : "dct_x_inv_any", true, N, a.L, a.f, a.C, a.PC, a.ny, a.nrows, a.tw,
+                        a.twq, a.scale, !fwd);
     switch (N) {
 #define FEN_CASE(m) case m: return launch_dct_x<m>(c, a, fwd);
         FEN_CASE(2) FEN_CASE(4) FEN_CASE(8) FEN_CASE(16) FEN_CASE(32) FEN_CASE(64) FEN_CASE(128) FEN_CASE(256)
@@ -1269,6 +1320,15 @@ template <int Lf> static int launch_dct_lines(fen_ctx* c, const LArgs& a, const 
     return FEN_OK;
 }
 static int dispatch_dct_lines(fen_ctx* c, int Lf, const LArgs& a, const double2* twq, bool fwd, int PC, int nouter) {
+    if (!tuned_len(Lf, 1024)) {
+        AnyLinesDctArgs q;
+        q.P = any_plan(Lf);
+        if (q.P.L != Lf) return set_error(FEN_ERR_UNSUPPORTED, "DCT length %d not supported", Lf);
+        q.NL = any_lines_per_block(Lf); q.inverse = fwd ? 0 : 1; q.C = a.C; q.sl = a.sl; q.so = a.so; q.tw = a.tw;
+        q.twq = twq; q.scale = a.scale;
+        return launch_any<AnyLinesDct>(c, fwd ? "dct_lines_fwd_any" : "dct_lines_inv_any", q, dim3(PC / q.NL, nouter), Lf,
+                                       q.NL);
+    }
     switch (Lf) {
 #define FEN_CASE(l) case l: return launch_dct_lines<l>(c, a, twq, fwd, PC / 8, nouter);
         FEN_CASE(2) FEN_CASE(4) FEN_CASE(8) FEN_CASE(16) FEN_CASE(32) FEN_CASE(64) FEN_CASE(128) FEN_CASE(256)
@@ -1307,12 +1367,18 @@ int poisson_init(fen_ctx* c) {
     // restriction either); FFT / DCT directions are powers of two up to 2048
     const bool thomas_last = var[g.ndim - 1] == 'n';
     const bool y_fft = !(g.ndim == 2 && thomas_last), z_fft = g.ndim == 3 && !thomas_last;
-    if (!pow2(g.nx) || g.nx < 2 || g.nx > 2048 || (y_fft && (!pow2(g.ny) || g.ny > 2048)) ||
-        (z_fft && (!pow2(g.nz) || g.nz > 2048)))
-        return set_error(FEN_ERR_UNSUPPORTED, "FFT sizes must be powers of two in 2..2048 (got %d %d %d)", g.nx,
-                         g.ny, g.nz);
-    if ((dctx && g.nx > 1024) || (dcty && g.ny > 1024))
-        return set_error(FEN_ERR_UNSUPPORTED, "DCT directions are limited to 1024 points (got %d %d)", g.nx, g.ny);
+    // Transformed directions: powers of two up to 2048 (cosine transforms: 1024) run the tuned register-path kernels,
+    // on any number of ranks; every other length whose prime factors are <= 31, up to 6144 points, runs the
+    // any-length kernels of fft_any.cuh on one rank (the reference's FFTW plans take any n, poisson.f90:148-151)
+    const bool multi_rank = g.nranks > 1 && g.ndim == 3;
+    const bool tx = tuned_len(g.nx, dctx ? 1024 : 2048), ty = !y_fft || tuned_len(g.ny, dcty ? 1024 : 2048),
+               tz = !z_fft || tuned_len(g.nz, 2048);
+    if (g.nx < 2 || (!tx && !any_supported(g.nx)) || (!ty && !any_supported(g.ny)) || (!tz && !any_supported(g.nz)))
+        return set_error(FEN_ERR_UNSUPPORTED, "transform sizes must be products of primes <= %d, 2..%d points "
+                                              "(got %d %d %d)", ANY_MAX_RADIX, ANY_MAX_L, g.nx, g.ny, g.nz);
+    if (multi_rank && !(tx && ty && tz))
+        return set_error(FEN_ERR_UNSUPPORTED, "on several ranks the transform sizes must be powers of two up to 2048 "
+                                              "(cosine transforms: 1024); got %d %d %d", g.nx, g.ny, g.nz);
     Poisson* p = new Poisson();
     c->ps = p;
     snprintf(p->variant, sizeof(p->variant), "%s", var);
@@ -1345,6 +1411,7 @@ int poisson_init(fen_ctx* c) {
     } else {
         FEN_TRY(upload(&p->tw_x, twiddles(p->M, p->M, p->M)));
         FEN_TRY(upload(&p->twr_x, twiddles(g.nx, p->M + 1, g.nx)));
+        if (!tx) FEN_TRY(upload(&p->tw_xa, twiddles(g.nx, g.nx, g.nx)));
         FEN_TRY(upload(&p->mwn_x, mwn(g.nx, d, p->PC)));
     }
     const bool tri_y = !strcmp(var, "pn") || !strcmp(var, "nn");
@@ -1398,7 +1465,7 @@ int poisson_init(fen_ctx* c) {
 // the x pass can compute the right-hand side div(v*) rho/dt itself (uniform rho, 3-D, register-path lengths)
 bool poisson_can_fuse_rhs(fen_ctx* c) {
     static const bool off = getenv("FEN_NO_FUSED_RHS") != nullptr;     // tuning switch
-    return !off && c->ps && c->ps->variant[0] == 'p' && c->g.ndim == 3 && c->uniform_props;
+    return !off && c->ps && c->ps->variant[0] == 'p' && c->g.ndim == 3 && c->uniform_props && tuned_len(c->g.nx, 2048);
 }
 
 // Thomas along y of a 2-D problem (pn, nn): few long systems -> the warp-per-32-columns streaming kernels.

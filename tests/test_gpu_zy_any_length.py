@@ -1,0 +1,130 @@
+"""GPU parity of the any-length Poisson path (fen_b200/csrc/fft_any.cuh): grid sizes that are not powers of two.
+
+The reference has no size restriction (FFTW plans of any n) and its own drivers use such grids: 96 x 96
+(test/small_test/fsi/Pan_Eulerian/Pan.f90:33-34), 16 x 48 (test/small_test/io/test_MF.f90), 3072 x 4608
+(test/large_test/startup_flow_cylinder/main.f90:37-38), 10^3 (test/small_test/fields/memory.f90).  Powers of two run
+the tuned register-path kernels; every other length whose prime factors are <= 31 runs the mixed-radix kernels, whose
+phases are executed on the CPU by tests/cpu/test_fft_any.cu (global indexing included).  Oracle: the numpy restatement,
+which takes any n like FFTW does.
+
+FIRST-RUN STATUS: written after the round's GPU budget was spent, so these tests have not executed on a B200 yet; they
+are marked xfail(strict=False) for that reason alone (an XPASS is the expected outcome) and sort after every other GPU
+file.  The mark goes away with the first GPU session of the next round."""
+import numpy as np
+import pytest
+
+import fen_b200 as fb
+from oracle import fen_oracle as fo
+from tests.test_gpu_parity import PI, _compare, _setup_ns, make_pair, rel_l2
+
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.xfail(strict=False, reason="not yet run on a GPU (written after the round's GPU budget was "
+                                                     "spent): first run is round 2")]
+
+P4, P6 = ["Periodic"] * 4, ["Periodic"] * 6
+ANY_CASES = [
+    ("pp", (96, 96, 1), P4, 2),                       # Pan.f90
+    ("pp", (48, 20, 1), P4, 2),
+    ("pp", (15, 9, 1), P4, 2),                        # odd lengths: no Nyquist mode
+    ("pp", (64, 100, 1), P4, 2),                      # tuned x pass + any-length fused y solve
+    ("pn", (12, 10, 1), P4[:2] + ["Wall", "Wall"], 2),
+    ("pn", (96, 48, 1), P4[:2] + ["Wall", "Wall"], 2),
+    ("nn", (48, 40, 1), ["Wall"] * 4, 2),
+    ("nn", (10, 16, 1), ["Wall", "Wall", "Inflow", "Outflow"], 2),
+    ("ppp", (24, 12, 20), P6, 3),
+    ("ppp", (10, 10, 10), P6, 3),                     # memory.f90's grid
+    ("ppp", (32, 6, 16), P6, 3),                      # only y goes through the any-length kernels
+    ("ppp", (16, 8, 22), P6, 3),                      # only the fused z solve does (prime factor 11)
+    ("ppn", (12, 24, 10), P4 + ["Wall", "Wall"], 3),
+    ("npn", (10, 6, 8), ["Wall", "Wall", "Periodic", "Periodic", "Wall", "Wall"], 3),
+    ("nnn", (12, 20, 6), ["Wall"] * 6, 3),
+    ("nnn", (16, 18, 8), ["Wall"] * 6, 3),            # tuned DCT in x, any-length DCT in y
+    ("pp", (3072, 8, 1), P4, 2),                      # startup_flow_cylinder's x length: one row per block
+    ("pn", (4608, 6, 1), P4[:2] + ["Wall", "Wall"], 2),
+]
+
+
+@pytest.mark.parametrize("variant,n,bc,ndim", ANY_CASES)
+def test_poisson_any_length_matches_oracle(variant, n, bc, ndim):
+    Go, Gg = make_pair(n, bc=bc, ndim=ndim)
+    rng = np.random.default_rng(5)
+    rhs = rng.standard_normal(n)
+    if variant in ("ppp", "pp"):
+        rhs -= rhs.mean()
+    po, pg = fo.Scalar(Go, 1), fb.scalar(Gg, 1)
+    po.I[...] = rhs
+    pg.I[...] = rhs
+    pso, psg = fo.PoissonSolver(po), fb.PoissonSolver(pg)
+    assert psg.variant == pso.variant == variant
+    pso.solve(po)
+    for _ in range(2):                                # twice: no state carried between solves
+        pg.I[...] = rhs
+        pg.push(); psg.solve(pg); pg.pull()
+        assert rel_l2(pg.I, po.I) < 1e-12
+    Gg.destroy()
+
+
+def test_unsupported_lengths_are_rejected_loudly():
+    """A prime factor above 31, or more than 6144 points, has no kernel: init_poisson_solver must say so (no silent
+    fallback), as must an any-length grid on several ranks (tests/test_gpu_multirank.py keeps to powers of two)."""
+    for n in ((74, 16, 1), (16, 2 * 37, 1)):
+        Gg = fb.grid().setup(n[0], n[1], 1, 1.0, 1.0 * n[1] / n[0], 1.0, bc=P4, ndim=2)
+        with pytest.raises(fb.FenError) as e:
+            fb.PoissonSolver(fb.scalar(Gg, 1))
+        assert "primes" in str(e.value)
+        Gg.destroy()
+
+
+def test_steps_tgv2d_96_match_oracle():
+    """The 2-D Taylor-Green driver of BASELINE config 1 on Pan.f90's 96 x 96 grid: 1e-12 after one step, 1e-10 after
+    forty, divergence at machine precision."""
+    n = 96
+    Go, Gg, nso, nsg, dt = _setup_ns((n, n, 1), P4, 2, 2 * PI, 1.0, fo.init_tgv2d, 2.0)
+    assert nsg.poisson_variant == "pp"
+    nso.navier_stokes_solver(1, dt)
+    nsg.navier_stokes_solver(1, dt)
+    _compare(nso, nsg, 1e-12)
+    for step in range(2, 41):
+        nso.navier_stokes_solver(step, dt)
+        nsg.navier_stokes_solver(step, dt)
+    _compare(nso, nsg, 1e-10)
+    assert abs(nsg.maxdiv) < 1e-12
+    Gg.destroy()
+
+
+def test_steps_tgv3d_24x48x24_match_oracle():
+    """The 3-D periodic step (BASELINE config 2's path) on a grid with a factor 3 in every direction: the fused right-hand side is
+    off (power-of-two x only), so this also covers the separate divergence kernel in front of the any-length x pass."""
+    n = (24, 48, 24)                  # box sides 2 pi x 4 pi x 2 pi: whole Taylor-Green wavelengths
+    Go, Gg, nso, nsg, dt = _setup_ns(n, P6, 3, 2 * PI, 0.01, fo.init_tgv3d, 1.0)
+    assert nsg.poisson_variant == "ppp"
+    nso.navier_stokes_solver(1, dt)
+    nsg.navier_stokes_solver(1, dt)
+    _compare(nso, nsg, 1e-12)
+    for step in range(2, 6):
+        nso.navier_stokes_solver(step, dt)
+        nsg.navier_stokes_solver(step, dt)
+    _compare(nso, nsg, 1e-11)
+    assert abs(nsg.maxdiv) < 1e-12
+    Gg.destroy()
+
+
+def test_steps_cavity_48x40_match_oracle():
+    """Lid-driven cavity (nn: any-length DCT in x, Thomas in y) on 48 x 40."""
+    bc = ["Wall"] * 4
+    Go = fo.Grid(48, 40, 1, 1.2, 1.0, 1.2 / 48, bc=bc)
+    Gg = fb.grid().setup(48, 40, 1, 1.2, 1.0, 1.2 / 48, bc=bc)
+    nso = fo.NavierStokes(Go, 1.0, 1.0e-2)
+    nsg = fb.Solver(Gg, 1.0, 1.0e-2).init_solver()
+    assert nsg.poisson_variant == "nn"
+    nso.v.x.bc["top"][...] = 1.0
+    nsg.v.x.set_bc("top", 1.0)
+    nso.CFL = nsg.CFL = 0.25
+    dt = nso.set_timestep(1.0)
+    assert nsg.set_timestep(1.0) == dt
+    for step in range(1, 21):
+        nso.navier_stokes_solver(step, dt)
+        nsg.navier_stokes_solver(step, dt)
+    _compare(nso, nsg, 1e-11)
+    assert abs(nsg.maxdiv) < 1e-11 and np.abs(nsg.v.x.I).max() > 1e-3
+    Gg.destroy()
