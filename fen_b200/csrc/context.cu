@@ -81,6 +81,7 @@ void free_field(Field& f) {
     if (f.d) cudaFree(f.d);
     f.d = nullptr;
     f.pull_event = nullptr;
+    f.pull_chunks = 0;
     for (int q = 0; q < 6; ++q) {
         if (f.bc_plane[q]) cudaFree(f.bc_plane[q]);
         f.bc_plane[q] = nullptr;
@@ -115,6 +116,21 @@ __global__ void __launch_bounds__(256) k_repitch(double* padded, double* flat, L
     }
 }
 
+// FEN_COPY_CHUNKS = K (1..8, default 1): asynchronous pulls leave in K pieces with one event each, and a push of the same
+// host array follows them piece by piece instead of waiting for the whole download -- in a loop that downloads and
+// re-uploads every field each step (bench.py's e2e region) the upload then trails the download by 1/K of an array
+// instead of a whole one.  Piece q covers elements [chunk_lo(n, K, q), chunk_lo(n, K, q + 1)).
+static int copy_chunks() {
+    static int k = 0;
+    if (!k) {
+        const char* e = getenv("FEN_COPY_CHUNKS");
+        k = e ? atoi(e) : 1;
+        k = std::max(1, std::min(8, k));
+    }
+    return k;
+}
+static size_t chunk_lo(size_t n, int K, int q) { return q >= K ? n : (n / K / 512 * 512) * (size_t)q; }
+
 // copy between a Fortran-ordered host array with gl ghost layers and the padded device layout.  The transfer
 // itself is one FLAT DMA between the host array and a contiguous staging buffer (55 GB/s measured on this box,
 // against 33 GB/s for a pitched cudaMemcpy3D host-to-device, scripts/probes/copy_probe.py); a small kernel moves
@@ -131,9 +147,22 @@ static int copy_field(fen_ctx* c, Field& f, double* host, int gl, bool to_device
     dim3 grid((hx + 255) / 256, hy, hz), block(256);
     if (to_device) {
         // an asynchronous pull of this field may still be reading it / writing the same host array
-        if (f.pull_event) FEN_CUDA(cudaStreamWaitEvent(c->stream, f.pull_event, 0));
+        if (f.pull_event && f.pull_chunks > 1 && f.pull_host == host && f.pull_n == n) {
+            // the download of this very array is leaving in pieces: follow it piece by piece
+            const int K = f.pull_chunks;
+            for (int q = 0; q < K; ++q) {
+                const size_t lo = chunk_lo(n, K, q), hi = chunk_lo(n, K, q + 1);
+                FEN_CUDA(cudaStreamWaitEvent(c->stream, c->ev_chunk[f.pull_buf][q], 0));
+                if (hi > lo)
+                    FEN_CUDA(cudaMemcpyAsync(c->stage + lo, host + lo, (hi - lo) * sizeof(double), cudaMemcpyHostToDevice,
+                                             c->stream));
+            }
+        } else {
+            if (f.pull_event) FEN_CUDA(cudaStreamWaitEvent(c->stream, f.pull_event, 0));
+            FEN_CUDA(cudaMemcpyAsync(c->stage, host, n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+        }
         f.pull_event = nullptr;
-        FEN_CUDA(cudaMemcpyAsync(c->stage, host, n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+        f.pull_chunks = 0;
         FEN_LAUNCH(c, "repitch", k_repitch<true><<<grid, block, 0, c->stream>>>(f.d, c->stage, L, gl, hx, hy, hz));
     } else {
         FEN_LAUNCH(c, "repitch", k_repitch<false><<<grid, block, 0, c->stream>>>(f.d, c->stage, L, gl, hx, hy, hz));
@@ -168,10 +197,26 @@ static int pull_field_async(fen_ctx* c, Field& f, double* host, int gl) {
     FEN_CUDA(cudaGetLastError());
     FEN_CUDA(cudaEventRecord(c->ev_ready[b], c->stream));
     FEN_CUDA(cudaStreamWaitEvent(c->d2h, c->ev_ready[b], 0));
-    FEN_CUDA(cudaMemcpyAsync(host, c->stage_out[b], n * sizeof(double), cudaMemcpyDeviceToHost, c->d2h));
+    const int K = copy_chunks();
+    if (K > 1) {
+        for (int q = 0; q < K; ++q) {
+            const size_t lo = chunk_lo(n, K, q), hi = chunk_lo(n, K, q + 1);
+            if (!c->ev_chunk[b][q]) FEN_CUDA(cudaEventCreateWithFlags(&c->ev_chunk[b][q], cudaEventDisableTiming));
+            if (hi > lo)
+                FEN_CUDA(cudaMemcpyAsync(host + lo, c->stage_out[b] + lo, (hi - lo) * sizeof(double),
+                                         cudaMemcpyDeviceToHost, c->d2h));
+            FEN_CUDA(cudaEventRecord(c->ev_chunk[b][q], c->d2h));
+        }
+    } else {
+        FEN_CUDA(cudaMemcpyAsync(host, c->stage_out[b], n * sizeof(double), cudaMemcpyDeviceToHost, c->d2h));
+    }
     FEN_CUDA(cudaEventRecord(c->ev_free[b], c->d2h));
     c->ev_free_set[b] = true;
     f.pull_event = c->ev_free[b];
+    f.pull_chunks = K;
+    f.pull_buf = b;
+    f.pull_host = host;
+    f.pull_n = n;
     return FEN_OK;
 }
 
@@ -295,6 +340,7 @@ int fen_gpu_destroy(fen_ctx* c) {
             if (c->stage_out[b]) cudaFree(c->stage_out[b]);
             if (c->ev_ready[b]) cudaEventDestroy(c->ev_ready[b]);
             if (c->ev_free[b]) cudaEventDestroy(c->ev_free[b]);
+            for (int q = 0; q < 8; ++q) if (c->ev_chunk[b][q]) cudaEventDestroy(c->ev_chunk[b][q]);
         }
         cudaStreamDestroy(c->d2h);
     }

@@ -46,6 +46,11 @@ struct Field {
     double bc_value[6] = {0, 0, 0, 0, 0, 0};
     double* bc_plane[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     cudaEvent_t pull_event = nullptr;   // fen_gpu_pull_async: the host copy of this field is still in flight until it fires
+    // chunked asynchronous pull (FEN_COPY_CHUNKS > 1): the copy went out in pull_chunks pieces, each with its own event, so
+    // that a later push of the same host array can follow it piece by piece (context.cu: copy_field)
+    int pull_chunks = 0, pull_buf = 0;
+    const double* pull_host = nullptr;
+    size_t pull_n = 0;
 };
 
 struct ProfEntry {
@@ -105,6 +110,7 @@ struct fen_ctx {
     cudaEvent_t ev_ready[4] = {nullptr, nullptr, nullptr, nullptr};   // repitch into stage_out[b] done (compute stream)
     cudaEvent_t ev_free[4] = {nullptr, nullptr, nullptr, nullptr};    // host copy out of stage_out[b] done (d2h stream)
     bool ev_free_set[4] = {false, false, false, false};
+    cudaEvent_t ev_chunk[4][8] = {};   // per staging buffer: piece q of its host copy is out (d2h stream)
     int out_next = 0;
     double* d_red = nullptr;     // device scratch for reductions (partials + results)
     double* h_red = nullptr;     // pinned host mirror of the results

@@ -111,3 +111,18 @@ def test_rising_bubble_rises_and_keeps_its_volume():
     assert all(b > a for a, b in zip(ycs, ycs[1:]))
     assert ycs[-1] > yc0 + 1e-4
     Gg.destroy()
+
+
+def test_chunked_async_pull_and_push_ordering():
+    """FEN_COPY_CHUNKS=4 (context.cu: downloads leave in pieces and a push of the same host array follows them piece by
+    piece): the ordering test of tests/test_gpu_io.py, in a child process because the switch is read once per process.
+    Opt-in until it has been measured: the default (1) is the path every other test runs."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, FEN_COPY_CHUNKS="4")
+    r = subprocess.run([sys.executable, "-m", "pytest", "-q", "-x", "-m", "gpu",
+                        "tests/test_gpu_io.py::test_pull_async_and_push_ordering"], cwd=root, env=env,
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
