@@ -1,0 +1,32 @@
+#!/bin/bash
+# First GPU call of round 2: run what was written after round 1's GPU budget was spent, before anything else changes.
+#   1. the whole GPU suite with the first-run files reported test by test (-rxX: XPASS = works, XFAIL = to fix);
+#   2. smoke + headline bench (unchanged path: must reproduce profiles/r01v_bench.json);
+#   3. A/B of the opt-in chunked host copies on the e2e figure (FEN_COPY_CHUNKS=4 vs default);
+#   4. the any-length Poisson path on a 384^3 grid (3 x 2^7 in every direction) next to 512^3: ms/step and kernels.
+# Usage (repo root, on the GPU box):  bash scripts/gpu_r02_first.sh [tag]
+TAG=${1:-r02a}
+OUT=gpurun_out
+mkdir -p $OUT
+nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw,memory.total --format=csv > $OUT/gpu_$TAG.txt 2>&1
+timeout 1500 python -m pytest tests -m gpu -q -rxX > $OUT/pytest_gpu_$TAG.log 2>&1
+echo "pytest exit $?" >> $OUT/pytest_gpu_$TAG.log
+tail -40 $OUT/pytest_gpu_$TAG.log
+timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > $OUT/smoke_$TAG.log 2>&1
+echo "smoke exit $?" >> $OUT/smoke_$TAG.log; tail -3 $OUT/smoke_$TAG.log
+timeout 900 python bench.py --steps 20 --warmup 3 > $OUT/bench_$TAG.json 2> $OUT/bench_$TAG.err
+echo "bench exit $?"; python scripts/show_bench.py $OUT/bench_$TAG.json
+FEN_COPY_CHUNKS=4 timeout 900 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > $OUT/bench_chunks4_$TAG.json 2> $OUT/bench_chunks4_$TAG.err
+FEN_COPY_CHUNKS=8 timeout 900 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > $OUT/bench_chunks8_$TAG.json 2> $OUT/bench_chunks8_$TAG.err
+python - <<PY
+import json
+for k in ("", "_chunks4", "_chunks8"):
+    try:
+        d = json.loads(open("gpurun_out/bench%s_%s.json" % (k, "$TAG")).read().strip().splitlines()[-1])
+        print("e2e%s: %.0f Mcell-updates/s, %.1f ms/step" % (k, d["e2e"]["value"], d["e2e"]["ms_per_step"]))
+    except Exception as exc:
+        print("e2e%s: no line (%r)" % (k, exc))
+PY
+timeout 600 python bench.py --grid 384,384,384 --steps 10 --warmup 3 --no-e2e --no-cpu-baseline > $OUT/bench_any384_$TAG.json 2> $OUT/bench_any384_$TAG.err
+echo "any-length 384^3 exit $?"; python scripts/show_bench.py $OUT/bench_any384_$TAG.json 2>/dev/null | head -20
+ls -la $OUT | tail -12

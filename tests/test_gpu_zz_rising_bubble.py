@@ -14,7 +14,7 @@ import fen_b200 as fb
 from oracle import fen_oracle as fo
 from oracle import fen_oracle_mf as mf
 
-pytestmark = [pytest.mark.gpu,
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(900),
               pytest.mark.xfail(strict=False, reason="not yet run on a GPU (written after the round's GPU budget was "
                                                      "spent): first run is round 2")]
 
