@@ -603,6 +603,56 @@ __global__ void __launch_bounds__(NL* FftPlan<Lf>::T, (NL * FftPlan<Lf>::T <= 10
     }
 }
 
+// Persistent, register-prefetching form of k_fft_solve_r (FEN_FFT_SOLVE_PERSIST=1; opt-in until measured): a block walks
+// the tiles blockIdx.x, blockIdx.x + gridDim.x, ... and issues the eight 16-byte loads of its NEXT tile before it
+// transforms the current one, so the HBM latency of a tile is hidden behind the two transforms of the previous tile
+// instead of being exposed at the top of every block (the r01v capture shows the fp64 pipe and DRAM each ~36 % busy:
+// the phases of the two resident blocks do not overlap well).  Same arithmetic in the same order as k_fft_solve_r.
+template <int Lf, int NL>
+__global__ void __launch_bounds__(NL* FftPlan<Lf>::T, 1) k_fft_solve_p(LArgs a, int nchunks, int ntiles) {
+    extern __shared__ double2 s[];
+    constexpr int T = FftPlan<Lf>::T;
+    const int tid = threadIdx.x;
+    const int line = tid % NL, t = tid / NL;
+    const double inorm = 1.0 / a.norm;
+    double2 nxt[8];
+    int tile = blockIdx.x;
+    if (tile < ntiles) {
+        const double2* b = a.C + ((tile % nchunks + a.cx0) * NL + line) + a.so * (tile / nchunks);
+#pragma unroll
+        for (int m = 0; m < 8; ++m) nxt[m] = b[a.sl * (t + m * T)];
+    }
+    for (; tile < ntiles; tile += gridDim.x) {
+        double2 v[8];
+#pragma unroll
+        for (int m = 0; m < 8; ++m) v[m] = nxt[m];
+        const int ahead = tile + gridDim.x;
+        if (ahead < ntiles) {
+            const double2* b = a.C + ((ahead % nchunks + a.cx0) * NL + line) + a.so * (ahead / nchunks);
+#pragma unroll
+            for (int m = 0; m < 8; ++m) nxt[m] = b[a.sl * (t + m * T)];
+        }
+        const int bx = tile % nchunks, by = tile / nchunks;
+        const int kx = (bx + a.cx0) * NL + line;
+        fft_regs<Lf, -1, true>(v, s, NL, line, t, a.tw);
+        {
+            double lxo = __ldg(&a.lx[kx]);
+            if (a.lo) lxo = lxo + __ldg(&a.lo[a.o0 + by]);
+#pragma unroll
+            for (int m = 0; m < 8; ++m) {
+                const double lam = lxo + __ldg(&a.ll[t + m * T]);
+                const double rl = lam == 0.0 ? 0.0 : inorm / lam;
+                v[m].x *= rl;
+                v[m].y *= rl;
+            }
+        }
+        fft_regs<Lf, +1, true>(v, s, NL, line, t, a.tw);
+        double2* base = a.C + kx + a.so * by;
+#pragma unroll
+        for (int m = 0; m < 8; ++m) base[a.sl * (t + m * T)] = v[m];
+    }
+}
+
 // =================================================================================================
 // Neumann directions: FFTW REDFT10 / REDFT01 (DCT-II / DCT-III, poisson.f90:272-275, :801-804, :888-909)
 // through one complex transform of the same length (Makhoul's reordering):
@@ -1225,6 +1275,22 @@ template <int Lf, int NL> static int launch_lines(fen_ctx* c, const LArgs& a, in
         if (mode == 0 && !sc) FEN_LAUNCH(c, "fft_lines_fwd", k_fft_lines_r<Lf, -1, NL, false><<<grid, block, bytes, c->stream>>>(a, none));
         if (mode == 0 && sc) FEN_LAUNCH(c, "fft_lines_fwd_a2a", k_fft_lines_r<Lf, -1, NL, true><<<grid, block, bytes, c->stream>>>(a, *sc));
         if (mode == 1) FEN_LAUNCH(c, "fft_lines_inv", k_fft_lines_r<Lf, +1, NL, false><<<grid, block, bytes, c->stream>>>(a, none));
+        // FEN_FFT_SOLVE_PERSIST=1: the persistent, prefetching form (one rank; tuning switch until measured)
+        static const bool persist = getenv("FEN_FFT_SOLVE_PERSIST") && atoi(getenv("FEN_FFT_SOLVE_PERSIST")) != 0;
+        if (mode == 2 && !sc && persist) {
+            static int per_sm = 0, sms = 0;
+            if (!per_sm) {
+                FEN_CUDA(cudaFuncSetAttribute(k_fft_solve_p<Lf, NL>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+                FEN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_fft_solve_p<Lf, NL>, NL * T, bytes));
+                FEN_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device));
+                if (per_sm < 1) per_sm = 1;
+            }
+            const int ntiles = nchunks * nouter;
+            const int nblocks = std::min(ntiles, per_sm * sms);
+            FEN_LAUNCH(c, "fft_solve", k_fft_solve_p<Lf, NL><<<nblocks, block, bytes, c->stream>>>(a, nchunks, ntiles));
+            FEN_CUDA(cudaGetLastError());
+            return FEN_OK;
+        }
         if (mode == 2 && !sc) FEN_LAUNCH(c, "fft_solve", k_fft_solve_r<Lf, NL, false><<<grid, block, bytes, c->stream>>>(a, none));
         if (mode == 2 && sc) FEN_LAUNCH(c, "fft_solve_a2a", k_fft_solve_r<Lf, NL, true><<<grid, block, bytes, c->stream>>>(a, *sc));
     } else {

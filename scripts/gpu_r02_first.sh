@@ -3,7 +3,8 @@
 #   1. the whole GPU suite with the first-run files reported test by test (-rxX: XPASS = works, XFAIL = to fix);
 #   2. smoke + headline bench (unchanged path: must reproduce profiles/r01v_bench.json);
 #   3. A/B of the opt-in chunked host copies on the e2e figure (FEN_COPY_CHUNKS=4 vs default);
-#   4. the any-length Poisson path on a 384^3 grid (3 x 2^7 in every direction) next to 512^3: ms/step and kernels.
+#   4. A/B of the persistent prefetching z-solve (FEN_FFT_SOLVE_PERSIST=1): the fft_solve row of the kernel table;
+#   5. the any-length Poisson path on a 384^3 grid (3 x 2^7 in every direction) next to 512^3: ms/step and kernels.
 # Usage (repo root, on the GPU box):  bash scripts/gpu_r02_first.sh [tag]
 TAG=${1:-r02a}
 OUT=gpurun_out
@@ -27,6 +28,8 @@ for k in ("", "_chunks4", "_chunks8"):
     except Exception as exc:
         print("e2e%s: no line (%r)" % (k, exc))
 PY
+FEN_FFT_SOLVE_PERSIST=1 timeout 600 python bench.py --steps 20 --warmup 3 --no-e2e --no-cpu-baseline > $OUT/bench_persist_$TAG.json 2> $OUT/bench_persist_$TAG.err
+echo "persistent fft_solve exit $?"; python scripts/show_bench.py $OUT/bench_persist_$TAG.json 2>/dev/null | head -12
 timeout 600 python bench.py --grid 384,384,384 --steps 10 --warmup 3 --no-e2e --no-cpu-baseline > $OUT/bench_any384_$TAG.json 2> $OUT/bench_any384_$TAG.err
 echo "any-length 384^3 exit $?"; python scripts/show_bench.py $OUT/bench_any384_$TAG.json 2>/dev/null | head -20
 ls -la $OUT | tail -12

@@ -126,3 +126,18 @@ def test_chunked_async_pull_and_push_ordering():
                         "tests/test_gpu_io.py::test_pull_async_and_push_ordering"], cwd=root, env=env,
                        capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+def test_persistent_fft_solve_matches_oracle():
+    """FEN_FFT_SOLVE_PERSIST=1 (poisson.cu: k_fft_solve_p, the persistent register-prefetching form of the fused
+    z-solve): the one-step Taylor-Green parity tests whose last direction has >= 64 points, and the 2-D config-1 run,
+    in a child process because the switch is read once per process.  Opt-in until it has been measured."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, FEN_FFT_SOLVE_PERSIST="1")
+    r = subprocess.run([sys.executable, "-m", "pytest", "-q", "-x", "-m", "gpu", "tests/test_gpu_parity.py", "-k",
+                        "one_step_tgv3d or tgv2d_matches_oracle_config1 or projection_makes"], cwd=root, env=env,
+                       capture_output=True, text=True, timeout=800)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
