@@ -17,6 +17,8 @@ the CUDA library; nothing here computes on the CPU.
 from __future__ import annotations
 
 import ctypes as C
+import math
+import os
 import sys
 
 import numpy as np
@@ -35,6 +37,40 @@ VOF, H, D, CURV, NORMX, NORMY, NORMZ, LX, LY, LZ, PHAT, PO, VOF1 = range(19, 32)
 
 def _f32(n):
     return float(np.float32(n))
+
+
+def _fortran_e(x, w=16, d=8):
+    """Fortran ``Ew.d`` edit descriptor: 0.dddddddd E+ee, right-justified in w columns (gfortran's output form)."""
+    x = float(x)
+    if x == 0.0:
+        body = "0." + "0" * d + "E+00"
+    else:
+        ex = int(math.floor(math.log10(abs(x)))) + 1
+        man = abs(x) / 10.0 ** ex
+        digits = int(round(man * 10 ** d))
+        if digits >= 10 ** d:                     # 0.99999999.. rounded up to 1.0
+            digits //= 10
+            ex += 1
+        body = ("-" if x < 0 else "") + "0.%0*d" % (d, digits) + "E%+03d" % ex
+    return body.rjust(w)
+
+
+def grid_json(Nx, Ny, Nz, origin, Lx, Ly, Lz):
+    """The text grid%print_json writes (grid.f90:246-257), line for line."""
+    e = _fortran_e
+    return "\n".join([
+        "{",
+        "    " + '"Grid": {',
+        "        " + '"Nx": ' + " " + "%7d" % Nx + ",",
+        "        " + '"Ny": ' + " " + "%7d" % Ny + ",",
+        "        " + '"Nz": ' + " " + "%7d" % Nz + ",",
+        "        " + '"origin": [' + " " + e(origin[0]) + "," + e(origin[1]) + "," + e(origin[2]) + "],",
+        "        " + '"Lx": ' + " " + e(Lx) + ",",
+        "        " + '"Ly": ' + " " + e(Ly) + ",",
+        "        " + '"Lz": ' + " " + e(Lz),
+        "    " + "  }",
+        "}",
+    ]) + "\n"
 
 
 class grid:
@@ -82,6 +118,20 @@ class grid:
         self.lo, self.hi = tuple(lo), tuple(hi)
         self.nloc = tuple(h - l + 1 for l, h in zip(self.lo, self.hi))
         return self
+
+    name = "grid"                                                         # grid.f90:57
+
+    def print_json(self, dirname="."):
+        """grid%print_json (grid.f90:233-264): ``<name>.json`` with Nx, Ny, Nz, origin, Lx, Ly, Lz in the reference's
+        own formats (I7, E16.8) -- the file every postpro.py of the reference opens first.  Rank 0 writes.  The
+        reference calls it at the end of ``setup`` (:198); here it is an explicit call so that creating a grid has no
+        side effect in the working directory."""
+        if getattr(self, "rank", 0) != 0:
+            return None
+        path = os.path.join(dirname, self.name + ".json")
+        with open(path, "w") as fh:
+            fh.write(grid_json(self.Nx, self.Ny, self.Nz, self.origin, self.Lx, self.Ly, self.Lz))
+        return path
 
     def connect(self, all_gather):
         """Wire the z-slab neighbours: ``all_gather(bytes) -> list[bytes]`` over all ranks."""

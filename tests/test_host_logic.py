@@ -118,3 +118,27 @@ def test_ctypes_signatures_match_the_header_prototypes():
                 assert at is C.c_double, (name, ctext, at)
             else:
                 assert at is C.c_int, (name, ctext, at)
+
+
+def test_grid_print_json_has_the_reference_format(tmp_path):
+    """grid%print_json (grid.f90:233-264): the file every postpro.py of the reference opens first (e.g.
+    test/large_test/lid3D/postpro.py:20-35).  Formats I7 / E16.8, line for line; json.load must read it back."""
+    import json
+    import math
+    from fen_b200 import api
+    text = api.grid_json(64, 128, 1, (0.0, -0.5, 0.0), 1.0, 2.0, 1.0 / 64)
+    lines = text.splitlines()
+    assert lines[0] == "{" and lines[1] == '    "Grid": {' and lines[-2] == "      }" and lines[-1] == "}"
+    assert lines[2] == '        "Nx":       64,' and lines[3] == '        "Ny":      128,'
+    assert lines[5] == '        "origin": [   0.00000000E+00, -0.50000000E+00,  0.00000000E+00],'
+    assert lines[6] == '        "Lx":    0.10000000E+01,' and lines[8] == '        "Lz":    0.15625000E-01'
+    g = json.loads(text)["Grid"]
+    assert (g["Nx"], g["Ny"], g["Nz"], g["Lx"], g["Ly"]) == (64, 128, 1, 1.0, 2.0) and g["origin"][1] == -0.5
+    assert api._fortran_e(2.0 * math.pi) == "  0.62831853E+01" and api._fortran_e(0.999999999) == "  0.10000000E+01"
+    # the method writes <name>.json on rank 0 only (no device needed: a bare instance with the grid attributes)
+    G = api.grid()
+    G.Nx, G.Ny, G.Nz, G.origin, G.Lx, G.Ly, G.Lz, G.rank = 16, 16, 16, (0.0, 0.0, 0.0), 1.0, 1.0, 1.0, 0
+    path = G.print_json(str(tmp_path))
+    assert os.path.basename(path) == "grid.json" and json.load(open(path))["Grid"]["Nz"] == 16
+    G.rank = 1
+    assert G.print_json(str(tmp_path)) is None
