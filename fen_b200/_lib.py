@@ -75,6 +75,9 @@ SIGNATURES = {
     "fen_gpu_divergence": (_I, [_P, _I, _I]),
     "fen_gpu_laplacian": (_I, [_P, _I, _I]),
     "fen_gpu_center_to_face": (_I, [_P, _I, _I]),
+    "fen_gpu_laplacian_scalar": (_I, [_P, _I, _I]),
+    "fen_gpu_face_to_center": (_I, [_P, _I, _I, _I]),
+    "fen_gpu_curl": (_I, [_P, _I, _I]),
     "fen_gpu_init_poisson_solver": (_I, [_P]),
     "fen_gpu_solve_poisson": (_I, [_P, _I]),
     "fen_gpu_destroy_poisson_solver": (_I, [_P]),

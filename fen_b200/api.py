@@ -301,8 +301,22 @@ def divergence(v: vector, div_v: scalar):
     check(v.G.lib.fen_gpu_divergence(v.G.ctx, v.x.id, div_v.id))
 
 
-def laplacian(v: vector, lap_v: vector):
-    check(v.G.lib.fen_gpu_laplacian(v.G.ctx, v.x.id, lap_v.x.id))
+def laplacian(v, lap_v):
+    """fields_mod's generic ``laplacian``: of a vector (fields.f90:298) or of a scalar (:256)."""
+    if isinstance(v, scalar):
+        check(v.G.lib.fen_gpu_laplacian_scalar(v.G.ctx, v.id, lap_v.id))
+    else:
+        check(v.G.lib.fen_gpu_laplacian(v.G.ctx, v.x.id, lap_v.x.id))
+
+
+def face_to_center(sf: scalar, sc: scalar, face: str):
+    """fields.f90:210-252; ``face`` is 'x', 'y' or 'z' as in the reference."""
+    check(sf.G.lib.fen_gpu_face_to_center(sf.G.ctx, sf.id, sc.id, "xyz".index(face)))
+
+
+def curl(v: vector, curl_v: vector):
+    """fields.f90:347-392 (2-D: the result is in ``curl_v.x``)."""
+    check(v.G.lib.fen_gpu_curl(v.G.ctx, v.x.id, curl_v.x.id))
 
 
 def center_to_face(s: scalar, v: vector):

@@ -522,6 +522,9 @@ int fen_gpu_gradient(fen_ctx* c, int s, int vx) { return c ? op_gradient(c, s, v
 int fen_gpu_divergence(fen_ctx* c, int vx, int s) { return c ? op_divergence(c, vx, s) : set_error(FEN_ERR_ARG, "null context"); }
 int fen_gpu_laplacian(fen_ctx* c, int vx, int ox) { return c ? op_laplacian(c, vx, ox) : set_error(FEN_ERR_ARG, "null context"); }
 int fen_gpu_center_to_face(fen_ctx* c, int s, int vx) { return c ? op_center_to_face(c, s, vx) : set_error(FEN_ERR_ARG, "null context"); }
+int fen_gpu_laplacian_scalar(fen_ctx* c, int s, int o) { return c ? op_laplacian_scalar(c, s, o) : set_error(FEN_ERR_ARG, "null context"); }
+int fen_gpu_face_to_center(fen_ctx* c, int sf, int sc, int dir) { return c ? op_face_to_center(c, sf, sc, dir) : set_error(FEN_ERR_ARG, "null context"); }
+int fen_gpu_curl(fen_ctx* c, int vx, int ox) { return c ? op_curl(c, vx, ox) : set_error(FEN_ERR_ARG, "null context"); }
 
 int fen_gpu_init_poisson_solver(fen_ctx* c) {
     if (!c) return set_error(FEN_ERR_ARG, "null context");

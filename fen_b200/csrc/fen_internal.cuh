@@ -189,6 +189,9 @@ int op_gradient(fen_ctx* c, int s, int vx);
 int op_divergence(fen_ctx* c, int vx, int s);
 int op_laplacian(fen_ctx* c, int vx, int ox);
 int op_center_to_face(fen_ctx* c, int s, int vx);
+int op_laplacian_scalar(fen_ctx* c, int s, int o);
+int op_face_to_center(fen_ctx* c, int sf, int sc, int dir);
+int op_curl(fen_ctx* c, int vx, int ox);
 int op_explicit_terms(fen_ctx* c, int rhs_x, bool advection_only);
 int ensure_red(fen_ctx* c);
 int reduce_field(fen_ctx* c, const double* f, int op, double* d_out);   // op 0 max, 1 sum

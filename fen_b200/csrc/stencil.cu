@@ -621,8 +621,10 @@ struct OpArgs {
     const double* a0; const double* a1; const double* a2;
     double* o0; double* o1; double* o2;
     double idelta, idelta2;
+    long long back;        // MODE 4: offset of the low-side neighbour in the averaging direction
 };
-// MODE 0 gradient of scalar a0 -> (o0,o1,o2); 1 laplacian of vector; 2 center_to_face
+// MODE 0 gradient of scalar a0 -> (o0,o1,o2); 1 laplacian of vector; 2 center_to_face; 3 laplacian of scalar a0 -> o0
+// (fields.f90:256-294); 4 face_to_center a0 -> o0 (:210-252); 5 curl (a0,a1,a2) -> (o0,o1,o2), 2-D: -> o0 (:347-392)
 template <bool D3, int MODE>
 __global__ void __launch_bounds__(TX* TY) k_op(OpArgs a) {
     const int i = blockIdx.x * TX + threadIdx.x + 1;
@@ -643,6 +645,24 @@ __global__ void __launch_bounds__(TX* TY) k_op(OpArgs a) {
             a.o0[c] = 0.5 * (a.a0[c + 1] + s0);
             a.o1[c] = 0.5 * (a.a0[c + sy] + s0);
             if (D3) a.o2[c] = 0.5 * (a.a0[c + sz] + s0);
+        } else if (MODE == 3) {
+            const double* f = a.a0;
+            const double f0 = f[c];
+            const double lx = f[c + 1] - 2.0 * f0 + f[c - 1];
+            const double ly = f[c + sy] - 2.0 * f0 + f[c - sy];
+            double r = (lx + ly) * a.idelta2;                                   // fields.f90:282-283
+            if (D3) r = r + (f[c + sz] - 2.0 * f0 + f[c - sz]) * a.idelta2;     // :285-286
+            a.o0[c] = r;
+        } else if (MODE == 4) {
+            a.o0[c] = 0.5 * (a.a0[c] + a.a0[c - a.back]);                       // fields.f90:225, :235, :245
+        } else if (MODE == 5) {
+            if (D3) {                                                           // fields.f90:374-379
+                a.o0[c] = (a.a2[c + sy] - a.a2[c]) * a.idelta - (a.a1[c + sz] - a.a1[c]) * a.idelta;
+                a.o1[c] = (a.a0[c + sz] - a.a0[c]) * a.idelta - (a.a2[c + 1] - a.a2[c]) * a.idelta;
+                a.o2[c] = (a.a1[c + 1] - a.a1[c]) * a.idelta - (a.a0[c + sy] - a.a0[c]) * a.idelta;
+            } else {                                                            // :383-384: z component in curl_v%x
+                a.o0[c] = (a.a1[c + 1] - a.a1[c]) * a.idelta - (a.a0[c + sy] - a.a0[c]) * a.idelta;
+            }
         } else {
             const double* in[3] = {a.a0, a.a1, a.a2};
             double* out[3] = {a.o0, a.o1, a.o2};
@@ -1004,6 +1024,52 @@ static int launch_op(fen_ctx* c, int mode, int in0, int nin, int out0) {
 #undef FEN_OP
     FEN_CUDA(cudaGetLastError());
     return FEN_OK;
+}
+
+// scalar -> scalar and vector -> vector operators of fields_mod that the time step itself does not use, kept for the
+// callers either side of it (the reference's own fields test calls laplacian(s, lap_s), its cavity driver curl(v, omega))
+static int launch_op2(fen_ctx* c, int mode, int in0, int nin, int out0, int nout, int dir) {
+    const bool d3 = c->g.ndim == 3;
+    OpArgs a;
+    a.L = c->L;
+    const double* in[3] = {nullptr, nullptr, nullptr};
+    double* out[3] = {nullptr, nullptr, nullptr};
+    for (int m = 0; m < nin; ++m) {
+        Field* f;
+        FEN_TRY(field_check(c, in0 + m, &f));
+        if (f->gl < 1) return set_error(FEN_ERR_ARG, "operator input field %d needs ghost nodes", in0 + m);
+        in[m] = f->d;
+    }
+    for (int m = 0; m < nout; ++m) {
+        Field* f;
+        FEN_TRY(field_check(c, out0 + m, &f));
+        for (int q = 0; q < nin; ++q)
+            if (f->d == in[q]) return set_error(FEN_ERR_ARG, "operator output field %d is also an input", out0 + m);
+        out[m] = f->d;
+    }
+    a.a0 = in[0]; a.a1 = in[1]; a.a2 = in[2];
+    a.o0 = out[0]; a.o1 = out[1]; a.o2 = out[2];
+    a.idelta = 1.0 / c->g.delta;
+    a.idelta2 = 1.0 / (c->g.delta * c->g.delta);
+    a.back = dir == 0 ? 1 : (dir == 1 ? c->L.sy : c->L.sz);
+    dim3 grid = st_grid(c->L), block(TX, TY);
+#define FEN_OP(D3, M, NAME) FEN_LAUNCH(c, NAME, k_op<D3, M><<<grid, block, 0, c->stream>>>(a))
+    if (mode == 3) { if (d3) FEN_OP(true, 3, "laplacian_s"); else FEN_OP(false, 3, "laplacian_s"); }
+    if (mode == 4) { if (d3) FEN_OP(true, 4, "face_to_center"); else FEN_OP(false, 4, "face_to_center"); }
+    if (mode == 5) { if (d3) FEN_OP(true, 5, "curl"); else FEN_OP(false, 5, "curl"); }
+#undef FEN_OP
+    FEN_CUDA(cudaGetLastError());
+    return FEN_OK;
+}
+int op_laplacian_scalar(fen_ctx* c, int s, int o) { return launch_op2(c, 3, s, 1, o, 1, 0); }
+int op_face_to_center(fen_ctx* c, int sf, int sc, int dir) {
+    if (dir < 0 || dir > 2 || (dir == 2 && c->g.ndim == 2))
+        return set_error(FEN_ERR_ARG, "face_to_center: direction %d (0 = x, 1 = y, 2 = z in 3-D)", dir);
+    return launch_op2(c, 4, sf, 1, sc, 1, dir);
+}
+int op_curl(fen_ctx* c, int vx, int ox) {
+    const bool d3 = c->g.ndim == 3;
+    return launch_op2(c, 5, vx, d3 ? 3 : 2, ox, d3 ? 3 : 1, 0);
 }
 
 int op_gradient(fen_ctx* c, int s, int vx) { return launch_op(c, 0, s, 1, vx); }

@@ -353,6 +353,24 @@ module fen_gpu_mod
             integer(c_int), value :: scalar_in, vector_out_x
             integer(c_int) :: ierr
         end function
+        function fen_gpu_laplacian_scalar(ctx, scalar_in, scalar_out) bind(C, name='fen_gpu_laplacian_scalar') result(ierr)
+            import :: c_int, c_ptr
+            type(c_ptr), value :: ctx
+            integer(c_int), value :: scalar_in, scalar_out
+            integer(c_int) :: ierr
+        end function
+        function fen_gpu_face_to_center(ctx, scalar_face, scalar_center, dir) bind(C, name='fen_gpu_face_to_center') result(ierr)
+            import :: c_int, c_ptr
+            type(c_ptr), value :: ctx
+            integer(c_int), value :: scalar_face, scalar_center, dir
+            integer(c_int) :: ierr
+        end function
+        function fen_gpu_curl(ctx, vector_in_x, vector_out_x) bind(C, name='fen_gpu_curl') result(ierr)
+            import :: c_int, c_ptr
+            type(c_ptr), value :: ctx
+            integer(c_int), value :: vector_in_x, vector_out_x
+            integer(c_int) :: ierr
+        end function
         function fen_gpu_poisson_variant(ctx) bind(C, name='fen_gpu_poisson_variant') result(msg)
             import :: c_ptr
             type(c_ptr), value :: ctx
@@ -873,6 +891,20 @@ contains
         integer(c_int), intent(in) :: s, vx
         call gpu_check(fen_gpu_center_to_face(ctx, s, vx), 'center_to_face')
     end subroutine gpu_center_to_face
+    !> laplacian_of_scalar (src/fields.f90:256), face_to_center (:210; face = 'x', 'y' or 'z'), curl (:347)
+    subroutine gpu_laplacian_scalar(s, o)
+        integer(c_int), intent(in) :: s, o
+        call gpu_check(fen_gpu_laplacian_scalar(ctx, s, o), 'laplacian_of_scalar')
+    end subroutine gpu_laplacian_scalar
+    subroutine gpu_face_to_center(sf, sc, face)
+        integer(c_int), intent(in) :: sf, sc
+        character(len=1), intent(in) :: face
+        call gpu_check(fen_gpu_face_to_center(ctx, sf, sc, int(index('xyz', face) - 1, c_int)), 'face_to_center')
+    end subroutine gpu_face_to_center
+    subroutine gpu_curl(vx, ox)
+        integer(c_int), intent(in) :: vx, ox
+        call gpu_check(fen_gpu_curl(ctx, vx, ox), 'curl')
+    end subroutine gpu_curl
 
     !> scalar%max_value / scalar%integral of a device field, reduced over all ranks (src/scalar.f90:179, :201)
     real(dp) function gpu_max_value(field)

@@ -138,6 +138,13 @@ int fen_gpu_gradient(fen_ctx* ctx, int scalar_in, int vector_out_x);        /* f
 int fen_gpu_divergence(fen_ctx* ctx, int vector_in_x, int scalar_out);      /* fields.f90:120 */
 int fen_gpu_laplacian(fen_ctx* ctx, int vector_in_x, int vector_out_x);     /* fields.f90:298 */
 int fen_gpu_center_to_face(fen_ctx* ctx, int scalar_in, int vector_out_x);  /* fields.f90:175 */
+/* the other operators of the module's generic interfaces, used by the callers either side of the step: laplacian(s, lap_s)
+ * (the reference's fields test, test/small_test/fields/methods.f90:326), face_to_center (save_fields, solver.f90:131-140;
+ * dir 0 / 1 / 2 = the reference's 'x' / 'y' / 'z'), curl (lid_driven.f90:86; 2-D: the z component goes to the x
+ * component of the output, fields.f90:381-384).  Inputs need ghost nodes; an output must not be an input. */
+int fen_gpu_laplacian_scalar(fen_ctx* ctx, int scalar_in, int scalar_out);             /* fields.f90:256 */
+int fen_gpu_face_to_center(fen_ctx* ctx, int scalar_face, int scalar_center, int dir);  /* fields.f90:210 */
+int fen_gpu_curl(fen_ctx* ctx, int vector_in_x, int vector_out_x);                      /* fields.f90:347 */
 
 /* ---- poisson_mod (src/poisson.f90:51-52) --------------------------------------------------- */
 int fen_gpu_init_poisson_solver(fen_ctx* ctx);                /* poisson.f90:57   */

@@ -299,6 +299,23 @@ def center_to_face(s: Scalar, v: Vector) -> None:
         v.z.I[...] = 0.5 * (s.sh(0, 0, 1) + c0)
 
 
+def face_to_center(sf: Scalar, sc: Scalar, face: str) -> None:
+    """src/fields.f90:210-252: average of a face field with its low-side neighbour."""
+    d = {"x": (-1, 0, 0), "y": (0, -1, 0), "z": (0, 0, -1)}[face]
+    sc.I[...] = 0.5 * (sf.sh() + sf.sh(*d))
+
+
+def curl(v: Vector, curl_v: Vector) -> None:
+    """src/fields.f90:347-392, defined on the top right cell vertex; in 2-D the (z) result goes to curl_v%x."""
+    idelta = 1.0 / v.G.delta
+    if v.G.ndim == 3:
+        curl_v.x.I[...] = (v.z.sh(0, 1, 0) - v.z.sh()) * idelta - (v.y.sh(0, 0, 1) - v.y.sh()) * idelta
+        curl_v.y.I[...] = (v.x.sh(0, 0, 1) - v.x.sh()) * idelta - (v.z.sh(1, 0, 0) - v.z.sh()) * idelta
+        curl_v.z.I[...] = (v.y.sh(1, 0, 0) - v.y.sh()) * idelta - (v.x.sh(0, 1, 0) - v.x.sh()) * idelta
+    else:
+        curl_v.x.I[...] = (v.y.sh(1, 0, 0) - v.y.sh()) * idelta - (v.x.sh(0, 1, 0) - v.x.sh()) * idelta
+
+
 def _lap_terms(s: Scalar):
     c0 = s.sh()
     lx = s.sh(1, 0, 0) - 2.0 * c0 + s.sh(-1, 0, 0)

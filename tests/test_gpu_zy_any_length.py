@@ -128,3 +128,46 @@ def test_steps_cavity_48x40_match_oracle():
     _compare(nso, nsg, 1e-11)
     assert abs(nsg.maxdiv) < 1e-11 and np.abs(nsg.v.x.I).max() > 1e-3
     Gg.destroy()
+
+
+@pytest.mark.parametrize("n,ndim", [((16, 12, 8), 3), ((32, 16, 1), 2)])
+def test_scalar_laplacian_face_to_center_curl(n, ndim):
+    """The operators of fields_mod's generic interfaces that the step itself does not use: laplacian(s, lap_s)
+    (the reference's fields test, methods.f90:326), face_to_center (save_fields) and curl (lid_driven.f90:86).
+    Same expressions in the same order as the oracle; the compiler contracts a*b + c into one fused operation where
+    numpy rounds twice, hence 1e-13 on the Laplacian and the curl (as tests/test_gpu_parity.py::test_field_operators
+    holds the vector Laplacian) and bit-exactness on the average."""
+    Go, Gg = make_pair(n, ndim=ndim)
+    rng = np.random.default_rng(9)
+    so, sg = fo.Scalar(Go, 1), fb.scalar(Gg, 1)
+    so.I[...] = rng.standard_normal(so.I.shape)
+    so.update_ghost_nodes()
+    sg.f[...] = so.f
+    sg.push()
+    lo, lg = fo.Scalar(Go, 0), fb.scalar(Gg, 0)
+    fo.laplacian_scalar(so, lo)
+    fb.laplacian(sg, lg)
+    lg.pull()
+    assert rel_l2(lg.I, lo.I) < 1e-13
+    for face in "xyz"[:ndim]:
+        co, cg = fo.Scalar(Go, 0), fb.scalar(Gg, 0)
+        fo.face_to_center(so, co, face)
+        fb.face_to_center(sg, cg, face)
+        cg.pull()
+        assert np.array_equal(cg.I, co.I), face
+    vo, vg = fo.Vector(Go, 1), fb.vector(Gg, 1)
+    for a, b in zip(vg.comps, vo.comps):
+        b.I[...] = rng.standard_normal(b.I.shape)
+    vo.update_ghost_nodes()
+    for a, b in zip(vg.comps, vo.comps):
+        a.f[...] = b.f
+        a.push()
+    wo, wg = fo.Vector(Go, 0), fb.vector(Gg, 0)
+    fo.curl(vo, wo)
+    fb.curl(vg, wg)
+    wg.pull()
+    for a, b in zip(wg.comps[:3 if ndim == 3 else 1], wo.comps):
+        assert rel_l2(a.I, b.I) < 1e-13
+    with pytest.raises(fb.FenError):
+        fb.laplacian(sg, sg)                      # an output must not be an input
+    Gg.destroy()

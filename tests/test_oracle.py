@@ -40,6 +40,39 @@ def test_periodic_ghosts_and_operator_convergence():
     assert _slope(N, errs_l) > 1.8
 
 
+def test_curl_and_face_to_center_known_answers():
+    """fields.f90:210-252 and :347-392: face_to_center of a field linear in the averaged direction is exact at the cell
+    centre; the curl of a discrete gradient vanishes to round-off; the curl of the Taylor-Green field converges at
+    second order to its analytic vorticity (2-D: the result sits in curl_v%x, at the top right cell vertex)."""
+    G = fo.Grid(8, 8, 8, 1.0, 1.0, 1.0)
+    for face, coord in (("x", G.x), ("y", G.y), ("z", G.z)):
+        sf, sc = fo.Scalar(G, 1, face), fo.Scalar(G, 1)
+        shape = {"x": (-1, 1, 1), "y": (1, -1, 1), "z": (1, 1, -1)}[face]
+        sf.f[...] = (3.0 * (coord + 0.5 * G.delta) - 1.0).reshape(shape)      # value on the + face of cell i
+        fo.face_to_center(sf, sc, face)
+        assert np.abs(sc.I - (3.0 * coord[1:-1] - 1.0).reshape(shape)).max() < 1e-14
+    rng = np.random.default_rng(11)
+    s = fo.Scalar(G, 1)
+    s.I[...] = rng.standard_normal(s.I.shape)
+    s.update_ghost_nodes()
+    g, c = fo.Vector(G, 1), fo.Vector(G, 0)
+    fo.gradient(s, g)
+    g.update_ghost_nodes()
+    fo.curl(g, c)
+    assert max(np.abs(q.I).max() for q in c.comps) < 1e-12
+    errs, N = [], [16, 32, 64]
+    for n in N:
+        G2 = fo.Grid(n, n, 1, 2 * PI, 2 * PI, 2 * PI / n)
+        ns = fo.NavierStokes(G2, 1.0, 1.0)
+        fo.init_tgv2d(ns)                                 # u = -cos x sin y, v = sin x cos y: omega_z = 2 cos x cos y
+        w = fo.Vector(G2, 0)
+        fo.curl(ns.v, w)
+        xv = (np.arange(1, n + 1) * G2.delta)[:, None]
+        yv = (np.arange(1, n + 1) * G2.delta)[None, :]
+        errs.append(np.abs(w.x.I[..., 0] - 2.0 * np.cos(xv) * np.cos(yv)).max())
+    assert _slope(N, errs) > 1.8
+
+
 # ---- test/small_test/poisson/convergence_rate/convergence_rate.f90:103-223 ------------------
 _CASES_2D = {
     "pp": (["Periodic"] * 4,
