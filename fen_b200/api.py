@@ -120,6 +120,18 @@ class grid:
         return self
 
     name = "grid"                                                         # grid.f90:57
+    # global.f90:23-28: offset of a location from the cell centre in units of delta; 0 centre, 1..3 x / y / z face, 4 corner
+    _STAGGER = ((0.0, 0.0, 0.0), (0.5, 0.0, 0.0), (0.0, 0.5, 0.0), (0.0, 0.0, 0.5), (0.5, 0.5, 0.5))
+
+    def closest_grid_node(self, xl, ind):
+        """grid%closest_grid_node (grid.f90:204-229): 1-based indices of the grid point of location ``ind`` closest to the
+        point ``xl`` (first minimum, as Fortran's minloc)."""
+        st = self._STAGGER[ind]
+        ie = [int(np.argmin(np.abs(self.x[1:self.Nx + 1] + st[0] * self.delta - xl[0]))) + 1,
+              int(np.argmin(np.abs(self.y[1:self.Ny + 1] + st[1] * self.delta - xl[1]))) + 1, 1]
+        if self.ndim == 3:
+            ie[2] = int(np.argmin(np.abs(self.z[1:self.Nz + 1] + st[2] * self.delta - xl[2]))) + 1
+        return ie
 
     def print_json(self, dirname="."):
         """grid%print_json (grid.f90:233-264): ``<name>.json`` with Nx, Ny, Nz, origin, Lx, Ly, Lz in the reference's
@@ -200,6 +212,23 @@ class scalar:
     def pull_async(self):
         """pull() that does not wait: ``f`` is valid after ``G.pull_wait()`` / ``G.synchronize()``."""
         check(self.G.lib.fen_gpu_pull_async(self.G.ctx, self.id, self.f.ctypes.data_as(C.c_void_p), self.gl))
+        return self
+
+    def set_from_function(self, fp, args=None):
+        """scalar%set_from_function (scalar.f90:137-164): ``f(i,j,k) = fp([x(i), y(j)(, z(k))], args)`` over the interior
+        at the grid's CELL-CENTRE coordinates (whatever the location tag, as in the reference), then the ghost update
+        when the scalar has ghost nodes.  The host array and its device twin both hold the result."""
+        G, g = self.G, self.gl
+        lo, n = G.lo, G.nloc
+        for k in range(n[2]):
+            for j in range(n[1]):
+                for i in range(n[0]):
+                    pt = [G.x[lo[0] + i], G.y[lo[1] + j]] + ([G.z[lo[2] + k]] if G.ndim == 3 else [])
+                    self.f[g + i, g + j, g + k] = fp(pt, args)
+        self.push()
+        if g > 0:
+            self.update_ghost_nodes()
+            self.pull()
         return self
 
     def setToValue(self, val):

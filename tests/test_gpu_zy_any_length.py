@@ -171,3 +171,19 @@ def test_scalar_laplacian_face_to_center_curl(n, ndim):
     with pytest.raises(fb.FenError):
         fb.laplacian(sg, sg)                      # an output must not be an input
     Gg.destroy()
+
+
+def test_set_from_function_fills_interior_and_ghosts():
+    """scalar%set_from_function (scalar.f90:137-164): interior from the cell-centre coordinates, then the ghost update."""
+    Go, Gg = make_pair((16, 8, 4))
+    sg = fb.scalar(Gg, 1)
+    sg.set_from_function(lambda x, a: a[0] * np.sin(2 * PI * x[0]) + x[1] - 2.0 * x[2], [3.0])
+    so = fo.Scalar(Go, 1)
+    X = Go.x[1:-1, None, None]; Y = Go.y[None, 1:-1, None]; Z = Go.z[None, None, 1:-1]
+    so.I[...] = 3.0 * np.sin(2 * PI * X) + Y - 2.0 * Z
+    so.update_ghost_nodes()
+    assert np.abs(sg.f - so.f).max() < 1e-14
+    sg.f[...] = 0.0
+    sg.pull()
+    assert np.abs(sg.f - so.f).max() < 1e-14
+    Gg.destroy()

@@ -142,3 +142,21 @@ def test_grid_print_json_has_the_reference_format(tmp_path):
     assert os.path.basename(path) == "grid.json" and json.load(open(path))["Grid"]["Nz"] == 16
     G.rank = 1
     assert G.print_json(str(tmp_path)) is None
+
+
+def test_closest_grid_node_matches_the_reference_rule():
+    """grid%closest_grid_node (grid.f90:204-229, exercised by test/small_test/grid/main.f90): minloc over the points of
+    the requested location; 1-based; no device needed."""
+    import numpy as np
+    from fen_b200 import api
+    G = api.grid()
+    G.Nx, G.Ny, G.Nz, G.ndim, G.delta = 8, 4, 2, 3, 0.25
+    G.x = -1.0 + (np.arange(0, G.Nx + 2) - 0.5) * G.delta
+    G.y = 0.0 + (np.arange(0, G.Ny + 2) - 0.5) * G.delta
+    G.z = 0.0 + (np.arange(0, G.Nz + 2) - 0.5) * G.delta
+    assert G.closest_grid_node([-0.9, 0.6, 0.3], 0) == [1, 3, 2]          # cell centres at -0.875, 0.625, 0.375
+    assert G.closest_grid_node([-0.76, 0.6, 0.3], 1) == [1, 3, 2]         # x faces at -0.75, -0.5, ...
+    assert G.closest_grid_node([-0.76, 0.74, 0.3], 2) == [1, 3, 2]        # y faces at 0.25, 0.5, 0.75, 1.0
+    assert G.closest_grid_node([100.0, -100.0, 0.0], 4) == [8, 1, 1]
+    G.ndim = 2
+    assert G.closest_grid_node([-0.9, 0.6], 0) == [1, 3, 1]
