@@ -73,6 +73,16 @@ struct StepGraph {
     int seen = 0;
 };
 
+// Kernel attributes (the dynamic shared-memory limit above 48 KB) belong to the device a kernel is loaded on, not to the
+// process: a caller may drive several contexts -- several GPUs -- from one process, so the one-time set-up of a launcher
+// is tracked per device.  Usage: static unsigned long long mask = 0; if (first_time_on_device(mask, c->device)) {...}
+inline bool first_time_on_device(unsigned long long& mask, int device) {
+    const unsigned long long bit = 1ull << (device & 63);
+    if (mask & bit) return false;
+    mask |= bit;
+    return true;
+}
+
 struct Poisson;   // poisson.cu
 struct Comm;      // comm.cu
 

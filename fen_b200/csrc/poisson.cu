@@ -1139,11 +1139,10 @@ const char* poisson_variant(fen_ctx* c) { return c->ps ? c->ps->variant : ""; }
 static bool tuned_len(int n, int maxn) { return pow2(n) && n <= maxn; }
 
 template <class K> static int launch_any(fen_ctx* c, const char* name, const typename K::Args& a, dim3 grid, int L, int nl) {
-    static bool attr_done = false;
-    if (!attr_done) {
+    static unsigned long long attr_mask = 0;
+    if (first_time_on_device(attr_mask, c->device)) {
         FEN_CUDA(cudaFuncSetAttribute(k_any<K>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (int)any_smem_bytes(ANY_MAX_L, 1)));
-        attr_done = true;
     }
     FEN_LAUNCH(c, name, k_any<K><<<grid, ANY_THREADS, any_smem_bytes(L, nl), c->stream>>>(a, nl * L));
     FEN_CUDA(cudaGetLastError());
@@ -1198,8 +1197,8 @@ static int x_variant(const char* name, int dflt) {
 template <int M> static int launch_x(fen_ctx* c, const XArgs& a, bool fwd, const DivArgs* dv) {
     constexpr int T = FftPlan<M>::T;
     const int bytes = (M + 1) * XIS * (int)sizeof(double2);
-    static bool attr_done = false;
-    if (!attr_done) { FEN_TRY(set_smem_x<M>()); attr_done = true; }
+    static unsigned long long attr_mask = 0;
+    if (first_time_on_device(attr_mask, c->device)) FEN_TRY(set_smem_x<M>());
     // c2r: the warp-per-row kernel wins at M = 256 (0.58 vs 0.61 ms), the staged one at M >= 512 (0.66 vs 0.71 ms)
     static const int vr2c = x_variant("FEN_X_R2C", 1), vc2r = x_variant("FEN_X_C2R", M >= 512 ? 2 : 3);
     dim3 grid((a.nrows + XR - 1) / XR), block(XR * T);
@@ -1249,8 +1248,8 @@ template <int Lf, int NL> static int launch_lines(fen_ctx* c, const LArgs& a, in
                                                   const ScArgs* sc) {
     constexpr int T = FftPlan<Lf>::T;
     const int bytes = Lf * NL * (int)sizeof(double2);
-    static bool attr_done = false;
-    if (!attr_done) {
+    static unsigned long long attr_mask = 0;
+    if (first_time_on_device(attr_mask, c->device)) {
         if (bytes > 48 * 1024) {
             if constexpr (Lf >= 64) {
                 FEN_CUDA(cudaFuncSetAttribute(k_fft_lines_r<Lf, -1, NL, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
@@ -1266,7 +1265,6 @@ template <int Lf, int NL> static int launch_lines(fen_ctx* c, const LArgs& a, in
                 FEN_CUDA(cudaFuncSetAttribute(k_fft_solve<Lf, NL, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
             }
         }
-        attr_done = true;
     }
     dim3 grid(nchunks, nouter), block(NL * T);
     ScArgs none;
@@ -1278,8 +1276,9 @@ template <int Lf, int NL> static int launch_lines(fen_ctx* c, const LArgs& a, in
         // FEN_FFT_SOLVE_PERSIST=1: the persistent, prefetching form (one rank; tuning switch until measured)
         static const bool persist = getenv("FEN_FFT_SOLVE_PERSIST") && atoi(getenv("FEN_FFT_SOLVE_PERSIST")) != 0;
         if (mode == 2 && !sc && persist) {
-            static int per_sm = 0, sms = 0;
-            if (!per_sm) {
+            static unsigned long long persist_mask = 0;
+            static int per_sm = 0, sms = 0;          // the same on every device of one box
+            if (first_time_on_device(persist_mask, c->device)) {
                 FEN_CUDA(cudaFuncSetAttribute(k_fft_solve_p<Lf, NL>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
                 FEN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_fft_solve_p<Lf, NL>, NL * T, bytes));
                 FEN_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device));
@@ -1341,13 +1340,12 @@ static int dispatch_lines(fen_ctx* c, int Lf, const LArgs& a, int mode, int PC, 
 template <int N> static int launch_dct_x(fen_ctx* c, const DArgs& a, bool fwd) {
     constexpr int T = FftPlan<N>::T;
     const int bytes = N * XIS * (int)sizeof(double2);
-    static bool attr_done = false;
-    if (!attr_done) {
+    static unsigned long long attr_mask = 0;
+    if (first_time_on_device(attr_mask, c->device)) {
         if (bytes > 48 * 1024) {
             FEN_CUDA(cudaFuncSetAttribute(k_dct_x<N, -1>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
             FEN_CUDA(cudaFuncSetAttribute(k_dct_x<N, +1>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
         }
-        attr_done = true;
     }
     dim3 grid((a.nrows + XR - 1) / XR), block(XR * T);
     if (fwd) FEN_LAUNCH(c, "dct_x_fwd", k_dct_x<N, -1><<<grid, block, bytes, c->stream>>>(a));
@@ -1371,13 +1369,12 @@ template <int Lf> static int launch_dct_lines(fen_ctx* c, const LArgs& a, const 
                                               int nouter) {
     constexpr int T = FftPlan<Lf>::T;
     const int bytes = Lf * 8 * (int)sizeof(double2);
-    static bool attr_done = false;
-    if (!attr_done) {
+    static unsigned long long attr_mask = 0;
+    if (first_time_on_device(attr_mask, c->device)) {
         if (bytes > 48 * 1024) {
             FEN_CUDA(cudaFuncSetAttribute(k_dct_lines<Lf, -1, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
             FEN_CUDA(cudaFuncSetAttribute(k_dct_lines<Lf, +1, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
         }
-        attr_done = true;
     }
     dim3 grid(nchunks, nouter), block(8 * T);
     if (fwd) FEN_LAUNCH(c, "dct_lines_fwd", k_dct_lines<Lf, -1, 8><<<grid, block, bytes, c->stream>>>(a, twq));
@@ -1547,11 +1544,10 @@ static int thomas_2d(fen_ctx* c, const TArgs& t) {
         FEN_CUDA(cudaGetLastError());
         return FEN_OK;
     }
-    static bool attr_done = false;
-    if (!attr_done) {
+    static unsigned long long attr_mask = 0;
+    if (first_time_on_device(attr_mask, c->device)) {
         FEN_CUDA(cudaFuncSetAttribute(k_thomas_lp<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LpSmem)));
         FEN_CUDA(cudaFuncSetAttribute(k_thomas_lp<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LpSmem)));
-        attr_done = true;
     }
     const double d = c->g.delta;
     const double cinv = 1.0 / (1.0 / (d * d));      // 1 / c_j, c_j = 1/delta**2 for every pipelined row (poisson.f90:219-232)

@@ -773,13 +773,12 @@ int ns_predict(fen_ctx* c, double dt) {
         // TMA-staged kernel: tensor maps of the three velocity buffers (cached per buffer)
         CUtensorMap* m[3];
         for (int q = 0; q < 3; ++q) FEN_TRY(field_tmap(c, q == 0 ? a.u : (q == 1 ? a.v : a.w), PTW, PTH, &m[q]));
-        static bool attr_done = false;
-        if (!attr_done) {
+        static unsigned long long attr_mask = 0;
+        if (first_time_on_device(attr_mask, c->device)) {
             FEN_CUDA(cudaFuncSetAttribute(k_pred_tma<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, PRED_SMEM));
             FEN_CUDA(cudaFuncSetAttribute(k_pred_tma<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, PRED_SMEM));
             FEN_CUDA(cudaFuncSetAttribute(k_pred_tma<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, PRED_SMEM));
             FEN_CUDA(cudaFuncSetAttribute(k_pred_tma<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, PRED_SMEM));
-            attr_done = true;
         }
         static const bool xg_env = !getenv("FEN_PRED_XG") || atoi(getenv("FEN_PRED_XG")) != 0;
         x_done = x_done && xg_env;
@@ -881,11 +880,10 @@ int ns_correct(fen_ctx* c, double dt, bool* checks_done) {
         CUtensorMap* m[4];
         const double* src[4] = {phi->d, u->d, v->d, w->d};
         for (int q = 0; q < 4; ++q) FEN_TRY(field_tmap(c, src[q], PTW, PTH, &m[q]));
-        static bool attr_done = false;
-        if (!attr_done) {
+        static unsigned long long attr_mask = 0;
+        if (first_time_on_device(attr_mask, c->device)) {
             FEN_CUDA(cudaFuncSetAttribute(k_corr_tma<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, CORR_SMEM));
             FEN_CUDA(cudaFuncSetAttribute(k_corr_tma<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, CORR_SMEM));
-            attr_done = true;
         }
         FEN_TRY(ensure_red(c));
         CorrTArgs a;
