@@ -289,7 +289,8 @@ def run_reference(args, rank, world):
         return
     if args.case == "wave2d":
         val, sec = cpu_port_wave2d(512, 1024, args.steps, args.warmup)
-        sample = "512 x 1024 sample of the 2048 x 4096 two-phase wave, %d steps, numpy restatement" % args.steps
+        sample = ("512 x 1024 sample of the 2048 x 4096 two-phase wave, %d steps, plain-C/OpenMP restatement "
+                  "(oracle/fen_oracle_mf_c.c)" % args.steps)
         print(json.dumps({
             "impl": "reference", "metric": "two-phase NS timestep Mcell-updates/s", "value": val,
             "unit": "Mcell-updates/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
@@ -346,11 +347,13 @@ def cpu_baseline(budget_s=20.0):
 
 
 def cpu_port_wave2d(nx, ny, steps, warmup=1):
-    """The numpy restatement of the reference's two-phase step (oracle/fen_oracle_mf.py) on an nx x ny sample of the
-    wave2d workload.  Returns (Mcell-updates/s, seconds per step)."""
+    """The plain-C/OpenMP restatement of the reference's two-phase step (oracle/fen_oracle_mf_c.c, all host threads) on
+    an nx x ny sample of the wave2d workload; the numpy restatement only builds the initial state.  Returns
+    (Mcell-updates/s, seconds per step)."""
     import math
     from oracle import fen_oracle as fo
     from oracle import fen_oracle_mf as mf
+    from oracle import fen_oracle_mf_c as mfc
     fo.set_workers(os.cpu_count() or 1)
     Lx, Ly = 1.0, float(ny) / nx
     G = fo.Grid(nx, ny, 1, Lx, Ly, Lx / nx, bc=["Periodic", "Periodic", "Wall", "Wall"])
@@ -360,24 +363,26 @@ def cpu_port_wave2d(nx, ny, steps, warmup=1):
                                    distance=lambda x, y: y - 0.02 * np.cos(2.0 * PI * x / Lx) - Ly / 2.0)
     ns.g[1] = -g
     dt = 0.1 * ns.set_timestep(1.0)
+    c = mfc.MultiphaseC.from_oracle(ns, threads=os.cpu_count() or 1)
     for s in range(warmup):
-        ns.navier_stokes_solver(s + 1, dt)
+        c.navier_stokes_solver(s + 1, dt)
     t0 = time.perf_counter()
     for s in range(steps):
-        ns.navier_stokes_solver(warmup + s + 1, dt)
+        c.navier_stokes_solver(warmup + s + 1, dt)
     t = time.perf_counter() - t0
+    assert abs(c.maxdiv) < 1e-6
+    c.destroy()
     return nx * ny * steps / t / 1e6, t / steps
 
 
 def cpu_baseline_wave2d(budget_s=15.0):
     nx, ny = 512, 1024
     _, sec = cpu_port_wave2d(nx, ny, 1, 1)
-    steps = int(max(2, min(30, budget_s / max(sec, 1e-3))))
+    steps = int(max(2, min(200, budget_s / max(sec, 1e-3))))
     val, sec = cpu_port_wave2d(nx, ny, steps, 1)
     return {"value": val, "unit": "Mcell-updates/s", "cores": os.cpu_count() or 1, "kind": "port",
-            "sample": "%d steps of the same two-phase wave at %d x %d (1 warm-up), numpy restatement of the "
-                      "reference's -DMF step (oracle/fen_oracle_mf.py; whole-array numpy, effectively one core "
-                      "outside scipy.fft)" % (steps, nx, ny)}
+            "sample": "%d steps of the same two-phase wave at %d x %d (1 warm-up), plain-C/OpenMP restatement of the "
+                      "reference's -DMF step (oracle/fen_oracle_mf_c.c)" % (steps, nx, ny)}
 
 
 def run_wave2d(args, local_rank):

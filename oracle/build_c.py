@@ -1,4 +1,5 @@
-"""Builds oracle/_build/libfen_oracle_c.so from oracle/fen_oracle_c.c with gcc (C99 + OpenMP).
+"""Builds oracle/_build/libfen_oracle_c.so from oracle/fen_oracle_c.c and libfen_oracle_mf_c.so from
+oracle/fen_oracle_mf_c.c with gcc (C99 + OpenMP).
 
 Test infrastructure: the C restatement is the second checker and the CPU baseline of bench.py; the product
 (fen_b200/) never links it.  Usage: python -m oracle.build_c [-f]"""
@@ -16,7 +17,16 @@ LIB = os.path.join(OUT_DIR, "libfen_oracle_c.so")
 FLAGS = ["-std=c99", "-O3", "-fopenmp", "-fPIC", "-shared", "-ffp-contract=off", "-fno-fast-math"]
 
 
-def build(force: bool = False) -> str:
+SRC_MF = os.path.join(HERE, "fen_oracle_mf_c.c")
+LIB_MF = os.path.join(OUT_DIR, "libfen_oracle_mf_c.so")
+
+
+def build_mf(force: bool = False) -> str:
+    """oracle/_build/libfen_oracle_mf_c.so from oracle/fen_oracle_mf_c.c (the two-phase restatement)."""
+    return build(force, SRC_MF, LIB_MF)
+
+
+def build(force: bool = False, SRC: str = SRC, LIB: str = LIB) -> str:
     os.makedirs(OUT_DIR, exist_ok=True)
     if not force and os.path.exists(LIB) and os.path.getmtime(LIB) >= os.path.getmtime(SRC):
         return LIB
@@ -35,3 +45,4 @@ def build(force: bool = False) -> str:
 
 if __name__ == "__main__":
     print(build(force="-f" in sys.argv))
+    print(build_mf(force="-f" in sys.argv))

@@ -14,6 +14,9 @@ against travel as small .npz files.  They are data, not code:
                               velocities of the lid-driven cavity at Re = 1000 (17 points each, coordinate - 0.5), the
                               points lid_driven/postpro.py:57-78 plots its profiles against.
 
+  (lid3d_re1000_64.npz, written by make_lid3d.py, carries test/large_test/lid3D/Uref.csv and Vref.csv -- Ku et al.'s
+   centreline velocities of the cubic cavity at Re = 1000 -- next to the oracle run they are compared with.)
+
 Usage (in the build container, where /root/reference is mounted):  python tests/golden/make_reference_data.py
 """
 import os

@@ -141,3 +141,36 @@ def test_persistent_fft_solve_matches_oracle():
                         "one_step_tgv3d or tgv2d_matches_oracle_config1 or projection_makes"], cwd=root, env=env,
                        capture_output=True, text=True, timeout=800)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+def test_lid3d_to_steady_state_matches_ku_and_the_oracle_run():
+    """test/large_test/lid3D/main.f90 on the GPU: 64^3, Re = 1000, nnn Poisson, 7 680 steps to t = 60 (a few seconds
+    here, 25 minutes for the numpy oracle, whose run is the committed fixture).  The centrelines must reproduce the
+    oracle's to 1e-8 (round-off differences do not grow in this steady laminar flow) and lie within the same distance
+    of the Ku et al. points the reference plots them against."""
+    import os
+    from tests.test_oracle import LID3D_TOL, _ku_deviation
+    ref = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "lid3d_re1000_64.npz"))
+    N = 64
+    Gg = fb.grid().setup(N, N, N, 1.0, 1.0, 1.0 / N, bc=["Wall"] * 6)
+    ns = fb.Solver(Gg, 1.0, 1.0e-3).init_solver()
+    assert ns.poisson_variant == "nnn"
+    ns.v.x.set_bc("top", 1.0)
+    dt = ns.set_timestep(1.0) / 2.0
+    assert dt == float(ref["dt"])
+    for step in range(1, int(ref["steps"]) + 1):
+        ns.navier_stokes_solver(step, dt)
+        if step == 50:
+            ns.v.x.pull(); ns.p.pull()
+            for got, want in ((ns.v.x.I[:, :, N // 2], ref["u50_mid"]), (ns.p.I[:, :, N // 2], ref["p50_mid"])):
+                assert np.linalg.norm(got - want) <= 1e-11 * np.linalg.norm(want)
+    ns.v.pull()
+    u, v = ns.v.x.I, ns.v.y.I
+    uc = 0.5 * (u[N // 2, :, N // 2] + u[N // 2 - 1, :, N // 2])          # postpro.py:48-52
+    vc = 0.5 * (v[:, N // 2, N // 2] + v[:, N // 2 - 1, N // 2])
+    assert np.abs(uc - ref["uc"]).max() < 1e-8 and np.abs(vc - ref["vc"]).max() < 1e-8
+    eu, ev = _ku_deviation(uc, vc, ref["uref"], ref["vref"])
+    assert eu < LID3D_TOL and ev < LID3D_TOL
+    md, _ = ns.status()
+    assert abs(md) < 1e-11
+    Gg.destroy()

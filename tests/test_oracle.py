@@ -327,3 +327,42 @@ def test_lid_driven_cavity_matches_ghia():
     vx = np.concatenate(([0.0], 0.5 * (v[:, N // 2] + v[:, N // 2 - 1]), [0.0]))
     assert np.abs(np.interp(ref["uref"][:, 0] + 0.5, Y, uy) - ref["uref"][:, 1]).max() < 0.025
     assert np.abs(np.interp(ref["vref"][:, 0] + 0.5, Y, vx) - ref["vref"][:, 1]).max() < 0.025
+
+
+def _ku_deviation(uc, vc, uref, vref):
+    """Largest distance between the centreline profiles of a 64^3 run (postpro.py:48-52) and the Ku et al. points the
+    reference plots them against (Uref.csv: u, y; Vref.csv: x, v), the wall values closing the profiles."""
+    N = len(uc)
+    Y = np.concatenate(([0.0], (np.arange(N) + 0.5) / N, [1.0]))
+    U = np.concatenate(([0.0], uc, [1.0]))
+    V = np.concatenate(([0.0], vc, [0.0]))
+    return (float(np.abs(np.interp(uref[:, 1], Y, U) - uref[:, 0]).max()),
+            float(np.abs(np.interp(vref[:, 0], Y, V) - vref[:, 1]).max()))
+
+
+@pytest.mark.slow
+def test_lid3d_centrelines_match_ku():
+    """test/large_test/lid3D/main.f90 (64^3 cubic cavity, Re = 1000, nnn Poisson), the fourth data set the reference
+    ships for this path: Ku et al.'s centreline velocities (Uref.csv, Vref.csv), which postpro.py only plots over.
+    The oracle run is stored in tests/golden/lid3d_re1000_64.npz (tests/golden/make_lid3d.py: 25 minutes of numpy);
+    here (1) its centrelines must lie within LID3D_TOL of the Ku points and (2) the fixture must be THIS oracle's run:
+    the first 50 steps are replayed and compared with the stored mid-plane fields."""
+    import os
+    ref = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "lid3d_re1000_64.npz"))
+    assert int(ref["N"]) == 64 and float(ref["time"]) >= 59.9 and abs(float(ref["maxdiv"])) < 1e-12
+    eu, ev = _ku_deviation(ref["uc"], ref["vc"], ref["uref"], ref["vref"])
+    assert eu < LID3D_TOL and ev < LID3D_TOL, (eu, ev)
+    N = 64
+    G = fo.Grid(N, N, N, 1.0, 1.0, 1.0 / N, bc=["Wall"] * 6)
+    ns = fo.NavierStokes(G, 1.0, 1.0e-3)
+    assert ns.poisson.variant == "nnn"
+    ns.v.x.bc["top"][...] = 1.0                              # main.f90:52
+    dt = ns.set_timestep(1.0) / 2.0                          # :55-56
+    assert dt == float(ref["dt"])
+    for step in range(1, 51):
+        ns.navier_stokes_solver(step, dt)
+    for got, want in ((ns.v.x.I[:, :, N // 2], ref["u50_mid"]), (ns.p.I[:, :, N // 2], ref["p50_mid"])):
+        assert np.linalg.norm(got - want) <= 1e-12 * np.linalg.norm(want)
+
+
+LID3D_TOL = 0.05        # second-order scheme at 64^3 against digitised pseudo-spectral data: 0.044 / 0.039 measured
