@@ -485,6 +485,70 @@ k_fft_x_c2r_w(XArgs a) {
     }
 }
 
+// Persistent, register-prefetching form of k_fft_x_c2r_w (FEN_X_C2R=4; opt-in until measured): a block walks the row
+// groups blockIdx.x, blockIdx.x + gridDim.x, ... and issues the coalesced loads of its NEXT eight rows before it
+// transforms the current ones (same idea as k_fft_solve_p: the r01v capture has this pass at 55 % of HBM with the
+// load latency exposed at the top of every block).  Same arithmetic in the same order as k_fft_x_c2r_w.
+template <int M>
+__global__ void __launch_bounds__(XR* FftPlan<M>::T, (XR * FftPlan<M>::T <= 512) ? 2 : 1) k_fft_x_c2r_p(XArgs a, int ngroups) {
+    extern __shared__ double2 s[];
+    constexpr int T = FftPlan<M>::T;
+    constexpr int RS = M + M / 8 + 1;
+    const int tid = threadIdx.x;
+    const int row = tid / T, t = tid % T;
+    double2 nx_[XR], nn_ = make_double2(0.0, 0.0);
+    auto fetch = [&](int g) {
+        const int row0 = g * XR;
+#pragma unroll
+        for (int rw = 0; rw < XR; ++rw) {
+            const int r = row0 + rw;
+            nx_[rw] = r < a.nrows ? a.C[(size_t)a.PC * r + tid] : make_double2(0.0, 0.0);
+        }
+        nn_ = make_double2(0.0, 0.0);
+        if (tid < XR && row0 + tid < a.nrows) nn_ = a.C[(size_t)a.PC * (row0 + tid) + M];
+    };
+    int g = blockIdx.x;
+    if (g < ngroups) fetch(g);
+    for (; g < ngroups; g += gridDim.x) {
+        {
+            if (tid == 0) {
+#pragma unroll
+                for (int rw = 0; rw < XR; ++rw) nx_[rw].y = 0.0;   // c2r ignores the imaginary part of DC / Nyquist
+            }
+#pragma unroll
+            for (int rw = 0; rw < XR; ++rw) s[spos<true>(tid, RS, rw)] = nx_[rw];
+            if (tid < XR) s[spos<true>(M, RS, tid)] = make_double2(nn_.x, 0.0);
+        }
+        if (g + (int)gridDim.x < ngroups) fetch(g + gridDim.x);    // in flight during the pre-pass and the transform
+        __syncthreads();
+        double2 v[8];
+#pragma unroll
+        for (int m = 0; m < 8; ++m) {
+            const int k = t + m * T;
+            const double2 xk = s[spos<true>(k, RS, row)], xm = s[spos<true>(M - k, RS, row)];
+            const double2 E = make_double2(xk.x + xm.x, xk.y - xm.y);
+            const double2 D = make_double2(xk.x - xm.x, xk.y + xm.y);
+            const double2 O = cmul(cconj(__ldg(&a.twr[k])), D);
+            v[m] = make_double2(E.x - O.y, E.y + O.x);
+        }
+        __syncthreads();                          // the first stage overwrites the staged rows
+        fft_regs<M, +1, true, false, true>(v, s, RS, row, t, a.tw);
+        const int r = g * XR + row;
+        if (r < a.nrows) {
+            const int j = r % a.ny, k3 = r / a.ny;
+            double* frow = a.f + a.L.idx(1, j + 1, k3 + 1);
+#pragma unroll
+            for (int m = 0; m < 8; ++m) {
+                const int idx = t + m * T;
+                reinterpret_cast<double2*>(frow)[idx] = v[m];
+                if (idx == 0) frow[2 * M] = v[m].x;
+                if (idx == M - 1) frow[-1] = v[m].y;
+            }
+        }
+        __syncthreads();                          // the next group's staged rows overwrite the exchange buffer
+    }
+}
+
 // c2r with a coalesced staging load: rows of C -> shared memory, the pair pre-pass reads (k, M-k) from there
 // into registers, the transform runs register-to-register and the real row is stored straight from registers.
 template <int M>
@@ -1213,6 +1277,20 @@ template <int M> static int launch_x(fen_ctx* c, const XArgs& a, bool fwd, const
         if (!fwd && vc2r == 0) { FEN_LAUNCH(c, "fft_x_c2r", k_fft_x_c2r_r<M><<<grid, block, bytes, c->stream>>>(a)); done = true; }
         if (!fwd && vc2r == 2) { FEN_LAUNCH(c, "fft_x_c2r", k_fft_x_c2r_s<M><<<grid, block, bytes, c->stream>>>(a)); done = true; }
         if (!fwd && vc2r == 3) { FEN_LAUNCH(c, "fft_x_c2r", k_fft_x_c2r_w<M><<<grid, block, bytes, c->stream>>>(a)); done = true; }
+        if (!fwd && vc2r == 4 && M > 256) { FEN_LAUNCH(c, "fft_x_c2r", k_fft_x_c2r_s<M><<<grid, block, bytes, c->stream>>>(a)); done = true; }
+        if (!fwd && vc2r == 4 && M <= 256) {      // persistent prefetching form of variant 3 (tuning switch until measured)
+            static unsigned long long pmask = 0;
+            static int per_sm = 0, sms = 0;
+            if (first_time_on_device(pmask, c->device)) {
+                FEN_CUDA(cudaFuncSetAttribute(k_fft_x_c2r_p<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+                FEN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_fft_x_c2r_p<M>, XR * T, bytes));
+                FEN_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device));
+                if (per_sm < 1) per_sm = 1;
+            }
+            const int ngroups = (a.nrows + XR - 1) / XR;
+            FEN_LAUNCH(c, "fft_x_c2r", k_fft_x_c2r_p<M><<<std::min(ngroups, per_sm * sms), block, bytes, c->stream>>>(a, ngroups));
+            done = true;
+        }
         if (fwd && vr2c == 3) {
             if (dv) FEN_LAUNCH(c, "fft_x_r2c_div", k_fft_x_r2c_w<M, true><<<grid, block, bytes, c->stream>>>(a, *dv));
             else FEN_LAUNCH(c, "fft_x_r2c", k_fft_x_r2c_w<M, false><<<grid, block, bytes, c->stream>>>(a, none));

@@ -29,7 +29,9 @@ for k in ("", "_chunks4", "_chunks8"):
         print("e2e%s: no line (%r)" % (k, exc))
 PY
 FEN_FFT_SOLVE_PERSIST=1 timeout 600 python bench.py --steps 20 --warmup 3 --no-e2e --no-cpu-baseline > $OUT/bench_persist_$TAG.json 2> $OUT/bench_persist_$TAG.err
-echo "persistent fft_solve exit $?"; python scripts/show_bench.py $OUT/bench_persist_$TAG.json 2>/dev/null | head -12
+FEN_X_C2R=4 timeout 600 python bench.py --steps 20 --warmup 3 --no-e2e --no-cpu-baseline > $OUT/bench_c2rp_$TAG.json 2> $OUT/bench_c2rp_$TAG.err
+echo "persistent c2r exit $?"; python scripts/show_bench.py $OUT/bench_c2rp_$TAG.json 2>/dev/null | head -12
+echo "persistent fft_solve exit"; python scripts/show_bench.py $OUT/bench_persist_$TAG.json 2>/dev/null | head -12
 timeout 600 python bench.py --grid 384,384,384 --steps 10 --warmup 3 --no-e2e --no-cpu-baseline > $OUT/bench_any384_$TAG.json 2> $OUT/bench_any384_$TAG.err
 echo "any-length 384^3 exit $?"; python scripts/show_bench.py $OUT/bench_any384_$TAG.json 2>/dev/null | head -20
 ls -la $OUT | tail -12
