@@ -187,3 +187,41 @@ def test_set_from_function_fills_interior_and_ghosts():
     sg.pull()
     assert np.abs(sg.f - so.f).max() < 1e-14
     Gg.destroy()
+
+
+def test_poiseuille_inflow_outflow_steps_match_oracle():
+    """test/small_test/navier_stokes/poiseuille_io: walls, Inflow with a parabolic boundary-value PLANE on the normal
+    velocity, Outflow -- the nn variant with the Inflow/Outflow tridiagonal (poisson.f90:226-231).  Forty steps against
+    the oracle, then on to the driver's steady state on the GPU alone and the reference's own comparison with the
+    parabola at its coarsest resolution."""
+    from tests.test_oracle import poiseuille_io_case
+    nx = 8
+    Go, nso, plane = poiseuille_io_case(nx, fo.Grid, fo.NavierStokes)
+    Gg, nsg, _ = poiseuille_io_case(nx, lambda *a, **k: fb.grid().setup(*a, **k), lambda G: fb.Solver(G).init_solver())
+    assert nsg.poisson_variant == "nn"
+    for face in fo.FACES[:4]:
+        for a, b in ((nsg.v.x, nso.v.x), (nsg.v.y, nso.v.y), (nsg.p, nso.p), (nsg.phi, nso.phi)):
+            assert a.get_bc_type(face) == b.bc_type[face], face
+    nso.v.y.bc["bottom"][...] = plane
+    nsg.v.y.set_bc("bottom", plane)
+    dt = nso.set_timestep(1.0)
+    assert nsg.set_timestep(1.0) == dt
+    for step in range(1, 41):
+        nso.navier_stokes_solver(step, dt)
+        nsg.navier_stokes_solver(step, dt)
+        if step == 1:
+            _compare(nso, nsg, 1e-12)
+    _compare(nso, nsg, 1e-11)
+    uo = nsg.v.y.f.copy()
+    step = 40
+    while True:
+        step += 1
+        nsg.navier_stokes_solver(step, dt)
+        nsg.v.y.pull()
+        if (nsg.v.y.f - uo).max() < 1e-8:
+            break
+        uo = nsg.v.y.f.copy()
+        assert step < 2000
+    Xf = (np.arange(nx) + 0.5) * (1.0 / nx)
+    assert np.abs(nsg.v.y.I[:, 2, 0] + (Xf ** 2 - Xf) / 2.0).max() < 2e-3          # 1.1e-3 for the oracle at nx = 8
+    Gg.destroy()

@@ -253,6 +253,47 @@ def test_poiseuille_convergence():
     assert _slope(N, e) > 1.8                            # postpro.py:62
 
 
+# ---- test/small_test/navier_stokes/poiseuille_io ---------------------------------------------
+def poiseuille_io_case(nx, make_grid, make_solver):
+    """poiseuille_io.f90:27-59: walls left and right, Inflow at the bottom with the parabolic profile written into
+    v%y%bc%bottom (interior columns only), Outflow at the top, nn Poisson with the Inflow/Outflow tridiagonal."""
+    ny = 4 * nx
+    Ly = 4.0
+    Lx = Ly * fo._f32(nx) / fo._f32(ny)                   # :44
+    G = make_grid(nx, ny, 1, Lx, Ly, Ly * fo._f32(1) / fo._f32(ny), bc=["Wall", "Wall", "Inflow", "Outflow"])
+    ns = make_solver(G)
+    x = G.x
+    plane = np.zeros((nx + 2, 3), order="F")
+    plane[1:-1, :] = (-0.5 * (x[1:-1] ** 2 - x[1:-1]))[:, None]          # :58-60
+    return G, ns, plane
+
+
+def test_poiseuille_inflow_outflow_convergence():
+    """The reference's criterion (poiseuille_io/postpro.py:36-58): third row of v against the parabola, slope > 1.8
+    over the resolutions (8, 16, 32 here; the reference adds 64), each run to its own steady-state test (:77-82)."""
+    N, e = [8, 16, 32], []
+    for nx in N:
+        G, ns, plane = poiseuille_io_case(nx, fo.Grid, fo.NavierStokes)
+        assert ns.poisson.variant == "nn"
+        assert [ns.v.y.bc_type[f] for f in fo.FACES[:4]] == [1, 1, 1, 2]         # Inflow: Dirichlet, Outflow: Neumann
+        assert [ns.p.bc_type[f] for f in fo.FACES[:4]] == [2, 2, 2, 1]
+        ns.v.y.bc["bottom"][...] = plane
+        dt = ns.set_timestep(1.0)
+        uo = np.zeros_like(ns.v.y.f)
+        step = 0
+        while True:
+            step += 1
+            dt = ns.navier_stokes_solver(step, dt)
+            if (ns.v.y.f - uo).max() < 1e-8 and step > 2:
+                break
+            uo = ns.v.y.f.copy()
+            assert step < 20000
+        assert abs(ns.maxdiv) < 1e-12
+        Xf = (np.arange(nx) + 0.5) * (1.0 / nx)
+        e.append(np.abs(ns.v.y.I[:, 2, 0] + (Xf ** 2 - Xf) / 2.0).max())       # postpro.py:47-52
+    assert _slope(N, e) > 1.8
+
+
 # ---- test/large_test/ABC/ABC.f90 -------------------------------------------------------------
 def test_abc_flow_divergence_free_and_decay():
     errs, N = [], [16, 32]
