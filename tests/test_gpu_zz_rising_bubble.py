@@ -174,3 +174,44 @@ def test_lid3d_to_steady_state_matches_ku_and_the_oracle_run():
     md, _ = ns.status()
     assert abs(md) < 1e-11
     Gg.destroy()
+
+
+def test_zalesak_disk_on_a_50x50_grid():
+    """test/small_test/volume_of_fluid/Zalesak, case 1: a 50 x 50 grid (no transform on this path, so any size),
+    prescribed rigid rotation, 1600 advect_vof calls.  The first 20 calls against the oracle (1e-12; over a whole
+    revolution last-bit differences flip the x/y-dominant branch of single cells, so the end state is compared through
+    the reference's own picture: the field after one revolution lies within 3 % of the disk area of the initial one)."""
+    from tests.test_oracle_mf import zalesak_distance, zalesak_velocity
+    N = 50
+    Lz = 1.0 * fo._f32(1) / fo._f32(N)
+    Go = fo.Grid(N, N, 1, 1.0, 1.0, Lz)
+    Gg = fb.grid().setup(N, N, 1, 1.0, 1.0, Lz)
+    vo, vg = mf.VoF(Go), fb.VoF(Gg)
+    vo.distance = zalesak_distance
+    vo.get_vof_from_distance()
+    vg.get_vof_from_distance(lambda x, y: float(zalesak_distance(x, y)))
+    uo, ug = fo.Vector(Go, 1), fb.vector(Gg, 1)
+    zalesak_velocity(Go, uo)
+    uo.update_ghost_nodes()
+    for a, b in zip(ug.comps, uo.comps):
+        a.f[...] = b.f
+        a.push()
+    vg.vof.pull()
+    assert np.abs(vg.vof.f - vo.vof.f).max() < 1e-14
+    f0 = vg.vof.I.copy()
+    m0 = vg.check_vof_integral()[0]
+    dt, t, step = 0.00125 * fo.PI, 0.0, 0
+    while t < 2.0 * fo.PI:
+        step += 1
+        t += dt
+        vg.advect_vof(ug, dt)
+        if step <= 20:
+            vo.advect_vof(uo, dt)
+            if step in (1, 20):
+                vg.vof.pull()
+                assert np.abs(vg.vof.f - vo.vof.f).max() < 1e-12, step
+    assert step == 1600
+    vg.vof.pull()
+    assert abs(vg.check_vof_integral()[0] / m0 - 1.0) < 1e-12
+    assert np.abs(vg.vof.I - f0).sum() / f0.sum() < 0.03
+    Gg.destroy()
