@@ -35,6 +35,7 @@ typedef struct FoMF {
     double *mwn_x, *ta, *tb, *tc, *c1;
     cplx* tw;
     double maxdiv, maxvel;
+    double ubc[2];                   /* uniform Dirichlet values of u on the bottom / top wall */
 } FoMF;
 
 #define AT(s, i, j) ((long)(i) + (s)->sy * (long)(j))
@@ -144,6 +145,7 @@ static double* field(FoMF* s, int id) {
 void fomf_set_field(FoMF* s, int id, const double* src) { memcpy(field(s, id), src, sizeof(double) * (size_t)s->n); }
 void fomf_get_field(FoMF* s, int id, double* dst) { memcpy(dst, field(s, id), sizeof(double) * (size_t)s->n); }
 void fomf_set_params(FoMF* s, double dt_o, double g0, double g1) { s->dt_o = dt_o; s->g[0] = g0; s->g[1] = g1; }
+void fomf_set_wall_velocity(FoMF* s, double bottom, double top) { s->ubc[0] = bottom; s->ubc[1] = top; }
 int fomf_x_first(const FoMF* s) { return s->x_first; }
 void fomf_set_vof_state(FoMF* s, int x_first, int vof_bc_y) { s->x_first = x_first; s->vof_bc_y = vof_bc_y; }
 int fomf_vof_bc_y(const FoMF* s) { return s->vof_bc_y; }
@@ -153,26 +155,28 @@ double fomf_maxcfl(const FoMF* s, double dt) { return dt * s->maxvel / s->delta;
 /* scalar%update_ghost_nodes (src/scalar.f90:255-345), x periodic; bottom / top of type ty: 0 periodic (prow = 1), 1
  * Dirichlet with value 0 -- loc 'y' (the wall-normal staggered component): ghost = bc and the last interior face = bc
  * too; otherwise ghost = 2 bc - f -- and 2 Neumann.  The x faces go first over the whole (j) extent, then the y faces over
- * the whole (i) extent: this order fills the corner ghosts the stencils read (hazard H3). */
-static void ghosts(const FoMF* s, double* f, char loc, int ty) {
+ * the whole (i) extent: this order fills the corner ghosts the stencils read (hazard H3).  vb / vt: the (uniform)
+ * boundary values bc%bottom / bc%top. */
+static void ghosts_v(const FoMF* s, double* f, char loc, int ty, double vb, double vt) {
     const int nx = s->nx, ny = s->ny;
     for (int j = 0; j <= ny + 1; ++j) f[AT(s, 0, j)] = f[AT(s, nx, j)];
     for (int j = 0; j <= ny + 1; ++j) f[AT(s, nx + 1, j)] = f[AT(s, 1, j)];
     for (int i = 0; i <= nx + 1; ++i) {                                /* bottom */
         if (ty == 0) f[AT(s, i, 0)] = f[AT(s, i, ny)];
-        else if (ty == 1) f[AT(s, i, 0)] = (loc == 'y') ? 0.0 : 2.0 * 0.0 - f[AT(s, i, 1)];
+        else if (ty == 1) f[AT(s, i, 0)] = (loc == 'y') ? vb : 2.0 * vb - f[AT(s, i, 1)];
         else f[AT(s, i, 0)] = f[AT(s, i, 1)];
     }
     for (int i = 0; i <= nx + 1; ++i) {                                /* top */
         if (ty == 0) f[AT(s, i, ny + 1)] = f[AT(s, i, 1)];
         else if (ty == 1) {
-            if (loc == 'y') { f[AT(s, i, ny)] = 0.0; f[AT(s, i, ny + 1)] = 0.0; }
-            else f[AT(s, i, ny + 1)] = 2.0 * 0.0 - f[AT(s, i, ny)];
+            if (loc == 'y') { f[AT(s, i, ny)] = vt; f[AT(s, i, ny + 1)] = vt; }
+            else f[AT(s, i, ny + 1)] = 2.0 * vt - f[AT(s, i, ny)];
         } else f[AT(s, i, ny + 1)] = f[AT(s, i, ny)];
     }
 }
+static void ghosts(const FoMF* s, double* f, char loc, int ty) { ghosts_v(s, f, loc, ty, 0.0, 0.0); }
 static void ghosts_velocity(const FoMF* s) {      /* vector%update_ghost_nodes, vector.f90:82-109: walls -> Dirichlet */
-    ghosts(s, s->u, 'x', 1);
+    ghosts_v(s, s->u, 'x', 1, s->ubc[0], s->ubc[1]);   /* v%x%bc%bottom / top: moving walls (shear_drop.f90:77-78) */
     ghosts(s, s->v, 'y', 1);
 }
 

@@ -28,6 +28,7 @@ def load():
         lib.fomf_get_field.argtypes = [p, i, p]
         lib.fomf_set_params.argtypes = [p, d, d, d]
         lib.fomf_set_vof_state.argtypes = [p, i, i]
+        lib.fomf_set_wall_velocity.argtypes = [p, d, d]
         lib.fomf_x_first.argtypes = [p]
         lib.fomf_vof_bc_y.argtypes = [p]
         lib.fomf_step.argtypes = [p, d]
@@ -78,6 +79,10 @@ class MultiphaseC:
         c.dt_o = ns.dt_o
         c.g = [float(ns.g[0]), float(ns.g[1])]
         c.lib.fomf_set_vof_state(c.h, 1 if ns.vf.x_first else 0, int(ns.vf.vof.bc_type["bottom"]))
+        bot, top = ns.v.x.bc["bottom"], ns.v.x.bc["top"]          # uniform wall velocities only
+        assert (bot == bot.flat[0]).all() and (top == top.flat[0]).all()
+        assert not ns.v.y.bc["bottom"].any() and not ns.v.y.bc["top"].any()
+        c.lib.fomf_set_wall_velocity(c.h, float(bot.flat[0]), float(top.flat[0]))
         return c
 
     @property

@@ -17,6 +17,10 @@ against travel as small .npz files.  They are data, not code:
   (lid3d_re1000_64.npz, written by make_lid3d.py, carries test/large_test/lid3D/Uref.csv and Vref.csv -- Ku et al.'s
    centreline velocities of the cubic cavity at Re = 1000 -- next to the oracle run they are compared with.)
 
+  shear_drop_basilisk.npz     test/small_test/multiphase/shear_drop/reference/Re1Ca02b.csv, Re1Ca04b.csv, Re1Ca09b.csv --
+                              the Basilisk deformation curves D(t) of a drop in shear flow at Re = 1, Ca = 0.2, 0.4,
+                              0.9 (columns t, D), the points shear_drop/postpro.py:44-52 plots its curves against.
+
 Usage (in the build container, where /root/reference is mounted):  python tests/golden/make_reference_data.py
 """
 import os
@@ -37,4 +41,9 @@ if __name__ == "__main__":
     uref, vref = np.genfromtxt(os.path.join(lid, "uref")), np.genfromtxt(os.path.join(lid, "vref"))
     assert uref.shape == (17, 2) and vref.shape == (17, 2)
     np.savez_compressed(os.path.join(HERE, "ghia_cavity_re1000.npz"), uref=uref, vref=vref)
-    print("wrote", curve.shape, com.shape, uref.shape, vref.shape)
+    sd = os.path.join(REF, "shear_drop", "reference")
+    drops = {"D_Ca%s" % ca: np.genfromtxt(os.path.join(sd, "Re1Ca%sb.csv" % ca), delimiter=",", skip_header=1)
+             for ca in ("02", "04", "09")}
+    assert drops["D_Ca02"].shape == (11, 2) and drops["D_Ca04"].shape == (21, 2) and drops["D_Ca09"].shape == (31, 2)
+    np.savez_compressed(os.path.join(HERE, "shear_drop_basilisk.npz"), **drops)
+    print("wrote", curve.shape, com.shape, uref.shape, vref.shape, {k: v.shape for k, v in drops.items()})

@@ -215,3 +215,46 @@ def test_zalesak_disk_on_a_50x50_grid():
     assert abs(vg.check_vof_integral()[0] / m0 - 1.0) < 1e-12
     assert np.abs(vg.vof.I - f0).sum() / f0.sum() < 0.03
     Gg.destroy()
+
+
+def test_shear_drop_deformation_follows_basilisk():
+    """test/small_test/multiphase/shear_drop, case 1 (Ca = 0.2): x periodic, walls MOVING at -U / +U (Dirichlet values
+    on v%x), surface tension; five steps against the oracle, then the whole run to t = 1 (8193 steps) and the
+    deformation curve against the Basilisk points the reference ships (tests/golden/shear_drop_basilisk.npz)."""
+    import os
+    from tests.test_oracle_mf import deformation, shear_drop_case
+    ref = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "shear_drop_basilisk.npz"))["D_Ca02"]
+    Go, ons, dt = shear_drop_case(0.2)
+    N = Go.Nx
+    Gg = fb.grid().setup(N, N, 1, 2.0, 2.0, 2.0 * fo._f32(1) / fo._f32(N), bc=["Periodic", "Periodic", "Wall", "Wall"])
+    gns = fb.MultiphaseSolver(Gg)
+    gns.rho_0, gns.rho_1, gns.mu_0, gns.mu_1, gns.sigma, gns.beta = ons.rho_0, ons.rho_1, ons.mu_0, ons.mu_1, ons.sigma, 1.0
+    gns.init_solver(lambda x, y: float(-(np.sqrt((x - 1.0) ** 2 + (y - 1.0) ** 2) - 0.5)))
+    assert gns.set_timestep(1.0) == dt
+    gns.v.x.set_bc("top", 1.0)
+    gns.v.x.set_bc("bottom", -1.0)
+    # the initial shear profile is the oracle's (interior and ghosts)
+    for a, b in zip(gns.v.comps, ons.v.comps):
+        a.f[...] = b.f
+        a.push()
+    t, step, D = 0.0, 0, []
+    while t <= 1.0:
+        step += 1
+        t += dt
+        gns.navier_stokes_solver(step, dt)
+        if step <= 5:
+            ons.navier_stokes_solver(step, dt)
+            gns.v.pull(); gns.p.pull(); gns.vof.pull()
+            for a, b in ((gns.v.x, ons.v.x), (gns.v.y, ons.v.y), (gns.p, ons.p)):
+                assert np.abs(a.I - b.I).max() <= 1e-12 * max(1.0, np.abs(b.I).max()), step
+            assert np.abs(gns.vof.I - ons.vof.I).max() < 1e-12
+        if step % 64 == 0:
+            gns.vof.pull()
+            D.append((t, deformation(gns.vof.I[..., 0], Go.delta)))
+    assert step == 8193
+    D = np.array(D)
+    mine = np.interp(ref[1:, 0], D[:, 0], D[:, 1])
+    assert np.abs(mine - ref[1:, 1]).max() < 0.002
+    md, _ = gns.status()
+    assert abs(md) < 1e-11
+    Gg.destroy()
