@@ -3,12 +3,12 @@
 // src/poisson.f90:148-151, 635-674; its own drivers use 96 x 96, 16 x 48, 3072 x 4608 --
 // test/small_test/fsi/Pan_Eulerian/Pan.f90:33-34, test/small_test/io/test_MF.f90, test/large_test/
 // startup_flow_cylinder/main.f90:37-38).  The power-of-two lengths keep the tuned register-path kernels of
-// poisson.cu / fft_core.cuh; this path is the coverage path: every length whose prime factors are <= 31, up to
+// poisson.cu / fft_core.cuh; this path is the coverage path: every length whose prime factors are <= 61, up to
 // ANY_MAX_L points, one rank.
 //
 // Structure.  Every kernel is a sequence of PHASES separated by block barriers:
 //     load (global -> shared, with the r2c / Hermitian / DCT reordering of the variant)
-//     one phase per Stockham stage (radix 4, 2, 3, 5, then the remaining primes), ping-pong between two shared buffers
+//     one phase per Stockham stage (radix 4, 2, 3, 5, then the remaining primes up to 61), ping-pong between two shared buffers
 //     [spectral divide, then the inverse stages]                                   (fused solve)
 //     store (shared -> global, with the scaling / post-twiddle of the variant)
 // A phase is a __host__ __device__ function of (arguments, shared buffers, block index, thread index, block size), so
@@ -27,7 +27,7 @@
 namespace fen {
 
 constexpr int ANY_MAX_L = 6144;          // two ping-pong lines of 16-byte elements: 2 * 6144 * 16 B = 192 KB of shared memory
-constexpr int ANY_MAX_RADIX = 31;
+constexpr int ANY_MAX_RADIX = 61;
 constexpr int ANY_MAX_STAGES = 16;
 constexpr int ANY_THREADS = 256;
 

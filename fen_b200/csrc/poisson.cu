@@ -1509,7 +1509,7 @@ int poisson_init(fen_ctx* c) {
     const bool thomas_last = var[g.ndim - 1] == 'n';
     const bool y_fft = !(g.ndim == 2 && thomas_last), z_fft = g.ndim == 3 && !thomas_last;
     // Transformed directions: powers of two up to 2048 (cosine transforms: 1024) run the tuned register-path kernels,
-    // on any number of ranks; every other length whose prime factors are <= 31, up to 6144 points, runs the
+    // on any number of ranks; every other length whose prime factors are <= 61, up to 6144 points, runs the
     // any-length kernels of fft_any.cuh on one rank (the reference's FFTW plans take any n, poisson.f90:148-151)
     const bool multi_rank = g.nranks > 1 && g.ndim == 3;
     const bool tx = tuned_len(g.nx, dctx ? 1024 : 2048), ty = !y_fft || tuned_len(g.ny, dcty ? 1024 : 2048),

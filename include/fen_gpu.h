@@ -37,7 +37,7 @@ enum fen_status {
     FEN_OK = 0,
     FEN_ERR_ARG = 1,          /* bad argument / unknown field */
     FEN_ERR_CUDA = 2,         /* CUDA runtime error */
-    FEN_ERR_UNSUPPORTED = 3,  /* outside the hot-path scope (BC combo, transform length with a prime factor > 31 ...) */
+    FEN_ERR_UNSUPPORTED = 3,  /* outside the hot-path scope (BC combo, transform length with a prime factor > 61 ...) */
     FEN_ERR_STATE = 4,        /* call order (e.g. step before init_solver) */
     FEN_ERR_COMM = 5          /* multi-GPU exchange set-up */
 };

@@ -274,13 +274,14 @@ static void check_lines_dct(int L) {
 int main() {
     // plans: supported / rejected lengths
     if (!any_supported(96) || !any_supported(4608) || !any_supported(3072) || !any_supported(1) ||
-        !any_supported(31 * 29) || any_supported(37) || any_supported(2 * 6144) || any_supported(0)) {
+        !any_supported(31 * 29) || !any_supported(2 * 61) || any_supported(67) || any_supported(2 * 6144) ||
+        any_supported(0)) {
         printf("plan support table wrong\n");
         return 1;
     }
     { AnyPlan p = any_plan(4608); int prod = 1; for (int s = 0; s < p.nst; ++s) prod *= p.radix[s];
       if (prod != 4608) { printf("plan product %d\n", prod); return 1; } }
-    const int small[] = {1, 2, 3, 4, 5, 6, 7, 9, 10, 12, 15, 16, 22, 48, 58, 62, 96, 100, 124, 243, 1001};
+    const int small[] = {1, 2, 3, 4, 5, 6, 7, 9, 10, 12, 15, 16, 22, 37, 48, 58, 62, 96, 100, 106, 122, 124, 243, 1001};
     for (int L : small) { check_lines(L, 0); check_lines(L, 1); check_lines(L, 2); }
     check_lines(3072, 0, 5);
     check_lines(4608, 2, 7);

@@ -3,7 +3,7 @@
 The reference has no size restriction (FFTW plans of any n) and its own drivers use such grids: 96 x 96
 (test/small_test/fsi/Pan_Eulerian/Pan.f90:33-34), 16 x 48 (test/small_test/io/test_MF.f90), 3072 x 4608
 (test/large_test/startup_flow_cylinder/main.f90:37-38), 10^3 (test/small_test/fields/memory.f90).  Powers of two run
-the tuned register-path kernels; every other length whose prime factors are <= 31 runs the mixed-radix kernels, whose
+the tuned register-path kernels; every other length whose prime factors are <= 61 runs the mixed-radix kernels, whose
 phases are executed on the CPU by tests/cpu/test_fft_any.cu (global indexing included).  Oracle: the numpy restatement,
 which takes any n like FFTW does.
 
@@ -35,6 +35,7 @@ ANY_CASES = [
     ("ppp", (10, 10, 10), P6, 3),                     # memory.f90's grid
     ("ppp", (32, 6, 16), P6, 3),                      # only y goes through the any-length kernels
     ("ppp", (16, 8, 22), P6, 3),                      # only the fused z solve does (prime factor 11)
+    ("pp", (74, 6, 1), P4, 2),                        # prime factor 37: the generic radix butterfly
     ("ppn", (12, 24, 10), P4 + ["Wall", "Wall"], 3),
     ("npn", (10, 6, 8), ["Wall", "Wall", "Periodic", "Periodic", "Wall", "Wall"], 3),
     ("nnn", (12, 20, 6), ["Wall"] * 6, 3),
@@ -65,9 +66,9 @@ def test_poisson_any_length_matches_oracle(variant, n, bc, ndim):
 
 
 def test_unsupported_lengths_are_rejected_loudly():
-    """A prime factor above 31, or more than 6144 points, has no kernel: init_poisson_solver must say so (no silent
+    """A prime factor above 61, or more than 6144 points, has no kernel: init_poisson_solver must say so (no silent
     fallback), as must an any-length grid on several ranks (tests/test_gpu_multirank.py keeps to powers of two)."""
-    for n in ((74, 16, 1), (16, 2 * 37, 1)):
+    for n in ((134, 16, 1), (16, 2 * 67, 1)):
         Gg = fb.grid().setup(n[0], n[1], 1, 1.0, 1.0 * n[1] / n[0], 1.0, bc=P4, ndim=2)
         with pytest.raises(fb.FenError) as e:
             fb.PoissonSolver(fb.scalar(Gg, 1))

@@ -68,7 +68,7 @@ def test_any_length_kernels_run_on_cpu():
     """fen_b200/csrc/fft_any.cuh: the any-length Poisson kernels (non-power-of-two grids) are sequences of
     __host__ __device__ phases; tests/cpu/test_fft_any.cu runs them with blocks and threads as loops against direct
     O(n^2) DFT / DCT-II / DCT-III sums -- strided lines (forward, backward, fused solve with the singular mode), r2c /
-    c2r rows with the periodic ghosts, cosine transforms, lengths 1 ... 6144 with factors 2, 3, 5, 7, 11, 13, 29, 31."""
+    c2r rows with the periodic ghosts, cosine transforms, lengths 1 ... 6144 with factors 2, 3, 5, 7, 11, 13, 29, 31, 37, 53, 61."""
     exe = os.path.join(ROOT, "build", "test_fft_any")
     os.makedirs(os.path.dirname(exe), exist_ok=True)
     subprocess.run(["nvcc", "-std=c++17", "-O2", "-gencode", "arch=compute_100a,code=sm_100a", "-o", exe,
