@@ -124,3 +124,78 @@ def test_enum_constants_carry_the_headers_values():
     assert len(fvals) >= 15
     for k, v in fvals.items():
         assert cvals.get(k) == v, (k, v, cvals.get(k))
+
+
+def _code_lines():
+    """Source lines without comments and strings, continuation lines joined, lower case."""
+    out, cur = [], ""
+    for raw in F90.splitlines():
+        line = re.sub(r"'[^']*'|\"[^\"]*\"", "''", raw)          # strings first: they may hold '!'
+        line = line.split("!")[0].rstrip()
+        if not line.strip():
+            continue
+        if cur:
+            line = cur + " " + line.strip().lstrip("&")
+            cur = ""
+        if line.rstrip().endswith("&"):
+            cur = line.rstrip()[:-1]
+            continue
+        out.append(line.strip().lower())
+    assert not cur
+    return out
+
+
+def test_shim_block_structure_is_balanced():
+    """What a compiler's parser would reject first in a file that has never been compiled: every module / interface /
+    type / function / subroutine / if-then / do / select / block construct is closed by the matching END, in order, and no
+    line exceeds the 132 columns of free-form Fortran."""
+    assert max(len(line) for line in F90.splitlines()) <= 132
+    stack = []
+    opener = re.compile(r"^(?:(?:pure|elemental|recursive)\s+)*(?:[\w\(\)=, ]*?\s)?(function|subroutine)\s+\w+")
+    for n, line in enumerate(_code_lines(), 1):
+        m_end = re.match(r"^end\s*(module|interface|type|function|subroutine|if|do|select|block|program)?\b", line)
+        if m_end:
+            kind = m_end.group(1)
+            assert stack, "END without an open construct: %r" % line
+            top = stack.pop()
+            assert kind is None or kind == top, "%r closes %r" % (line, top)
+            continue
+        if re.match(r"^module\s+(?!procedure)\w+", line):
+            stack.append("module")
+        elif re.match(r"^(abstract\s+)?interface\b", line):
+            stack.append("interface")
+        elif re.match(r"^type\s*(,[^:]*)?::\s*\w+", line) or re.match(r"^type\s+\w+\s*$", line):
+            stack.append("type")
+        elif opener.match(line) and not line.startswith(("procedure", "call ", "use ")) and "::" not in line.split("function")[0].split("subroutine")[0]:
+            stack.append(opener.match(line).group(1))
+        elif re.match(r"^(\w+\s*:\s*)?if\s*\(.*\)\s*then$", line):
+            stack.append("if")
+        elif re.match(r"^(\w+\s*:\s*)?do\b", line):
+            stack.append("do")
+        elif re.match(r"^(\w+\s*:\s*)?select\s+(case|type)\b", line):
+            stack.append("select")
+        elif re.match(r"^(\w+\s*:\s*)?block$", line):
+            stack.append("block")
+    assert stack == [], "unclosed constructs: %r" % stack
+
+
+def test_shim_dummy_arguments_are_declared():
+    """Every dummy argument of every procedure in the shim has a declaration in that procedure (implicit none is in
+    force: an undeclared dummy is a compile error), and every result variable too."""
+    src = "\n".join(_code_lines())
+    pat = re.compile(r"^(?:[\w\(\)=\*, ]*?\s)?(function|subroutine)\s+(\w+)\s*\(([^)]*)\)([^\n]*)\n(.*?)^end\s*(?:function|subroutine)",
+                     re.S | re.M)
+    checked = 0
+    for m in pat.finditer(src):
+        kind, name, args, tail, body = m.group(1), m.group(2), m.group(3), m.group(4), m.group(5)
+        names = [a.strip() for a in args.split(",") if a.strip()]
+        res = re.search(r"result\s*\((\w+)\)", tail)
+        if res:
+            names.append(res.group(1))
+        elif kind == "function" and not re.match(r"^\s*(real|integer|logical|type|character)", m.group(0)):
+            names.append(name)
+        decl = " ".join(line for line in body.splitlines() if "::" in line or line.strip().startswith("procedure"))
+        for a in names:
+            assert re.search(r"\b%s\b" % re.escape(a), decl), "%s: dummy %r is not declared" % (name, a)
+        checked += 1
+    assert checked > 100
