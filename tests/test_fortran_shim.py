@@ -199,3 +199,34 @@ def test_shim_dummy_arguments_are_declared():
             assert re.search(r"\b%s\b" % re.escape(a), decl), "%s: dummy %r is not declared" % (name, a)
         checked += 1
     assert checked > 100
+
+
+def test_shim_calls_pass_the_declared_number_of_arguments():
+    """Part 2 of the shim calls the bind(C) functions of part 1: every call site passes as many actual arguments as the
+    interface (and so the C prototype) declares."""
+    ifaces = f90_interfaces()
+    lines = _code_lines()
+    end_iface = max(i for i, l in enumerate(lines) if re.match(r"^end\s*interface", l))
+    body = "\n".join(lines[end_iface + 1:])
+    calls = 0
+    for m in re.finditer(r"\b(fen_gpu_\w+)\s*\(", body):
+        name = m.group(1)
+        depth, i, nargs, seen = 1, m.end(), 0, False
+        while depth:
+            ch = body[i]
+            if ch == "(":
+                depth += 1
+            elif ch == ")":
+                depth -= 1
+            elif ch == "," and depth == 1:
+                nargs += 1
+            elif not ch.isspace():
+                seen = True
+            i += 1
+        nargs = nargs + 1 if seen else 0
+        lowered = {k.lower(): v for k, v in ifaces.items()}
+        assert name in lowered, "%s is called but has no interface" % name
+        assert nargs == len(lowered[name][0]), "%s called with %d arguments, interface has %d" % (
+            name, nargs, len(lowered[name][0]))
+        calls += 1
+    assert calls >= 50                       # most entry points are wrapped at least once (the rest are bound only)
