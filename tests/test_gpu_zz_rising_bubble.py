@@ -258,3 +258,17 @@ def test_shear_drop_deformation_follows_basilisk():
     md, _ = gns.status()
     assert abs(md) < 1e-11
     Gg.destroy()
+
+
+def test_two_phase_c_driver_runs():
+    """examples/shear_drop_driver.c: the shear-drop case driven from plain C through the two-phase entry points of the C
+    ABI; the deformation at t = 1 against the Basilisk value the reference ships (0.1204)."""
+    import re
+    import subprocess
+    from tests.test_host_logic import _build_c_driver
+    exe = _build_c_driver("shear_drop_driver")
+    r = subprocess.run([exe, "0.2", "1.0"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr
+    m = re.search(r"steps (\d+)  deformation ([0-9.]+)", r.stdout)
+    assert m and int(m.group(1)) == 8193
+    assert abs(float(m.group(2)) - 0.1204) < 0.002

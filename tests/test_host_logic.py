@@ -77,15 +77,27 @@ def test_any_length_kernels_run_on_cpu():
     assert r.returncode == 0 and r.stdout.strip().endswith("OK") and "FAIL" not in r.stdout, r.stdout[-2000:]
 
 
-def _build_c_driver():
-    exe = os.path.join(ROOT, "build", "tgv_driver")
+def _build_c_driver(name="tgv_driver"):
+    exe = os.path.join(ROOT, "build", name)
     os.makedirs(os.path.dirname(exe), exist_ok=True)
     from fen_b200 import _lib
     libdir = os.path.dirname(_lib.LIB_PATH)
     subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(ROOT, "include"),
-                    os.path.join(ROOT, "examples", "tgv_driver.c"), "-L", libdir, "-lfen_gpu",
+                    os.path.join(ROOT, "examples", name + ".c"), "-L", libdir, "-lfen_gpu",
                     "-Wl,-rpath," + libdir, "-lm", "-o", exe], check=True)
     return exe
+
+
+def test_two_phase_c_driver_links(lib):
+    """examples/shear_drop_driver.c: the reference's shear-drop driver (-DMF build) through the two-phase entry points
+    of the C ABI -- module parameters, init_solver with a distance callback, moving-wall values -- compiles as C99 with
+    -pedantic -Werror and links; without a device it stops at fen_gpu_create (the run is a GPU test)."""
+    import torch
+    exe = _build_c_driver("shear_drop_driver")
+    if torch.cuda.is_available():
+        pytest.skip("a device is present: the run itself is tests/test_gpu_zz_rising_bubble.py")
+    r = subprocess.run([exe], capture_output=True, text=True)
+    assert r.returncode == 2 and "no CPU fallback" in r.stderr
 
 
 def test_c_abi_header_is_plain_c_and_a_c_driver_links(lib):
