@@ -5,6 +5,7 @@
 #   3. A/B of the opt-in chunked host copies on the e2e figure (FEN_COPY_CHUNKS=4 vs default);
 #   4. A/B of the persistent prefetching z-solve (FEN_FFT_SOLVE_PERSIST=1): the fft_solve row of the kernel table;
 #   5. the any-length Poisson path on a 384^3 grid (3 x 2^7 in every direction) next to 512^3: ms/step and kernels.
+#   6. compute-sanitizer memcheck of the never-run kernels.
 # Usage (repo root, on the GPU box):  bash scripts/gpu_r02_first.sh [tag]
 TAG=${1:-r02a}
 OUT=gpurun_out
@@ -34,4 +35,8 @@ echo "persistent c2r exit $?"; python scripts/show_bench.py $OUT/bench_c2rp_$TAG
 echo "persistent fft_solve exit"; python scripts/show_bench.py $OUT/bench_persist_$TAG.json 2>/dev/null | head -12
 timeout 600 python bench.py --grid 384,384,384 --steps 10 --warmup 3 --no-e2e --no-cpu-baseline > $OUT/bench_any384_$TAG.json 2> $OUT/bench_any384_$TAG.err
 echo "any-length 384^3 exit $?"; python scripts/show_bench.py $OUT/bench_any384_$TAG.json 2>/dev/null | head -20
+# memcheck of the kernels that have never run: the any-length suite and the new operators under compute-sanitizer
+timeout 900 compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest tests/test_gpu_zy_any_length.py -q -rxX \
+    -k "poisson_any_length or scalar_laplacian or cavity_48x40" > $OUT/memcheck_any_$TAG.log 2>&1
+echo "memcheck exit $?"; tail -5 $OUT/memcheck_any_$TAG.log
 ls -la $OUT | tail -12
