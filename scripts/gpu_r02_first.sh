@@ -36,7 +36,7 @@ echo "persistent fft_solve exit"; python scripts/show_bench.py $OUT/bench_persis
 timeout 600 python bench.py --grid 384,384,384 --steps 10 --warmup 3 --no-e2e --no-cpu-baseline > $OUT/bench_any384_$TAG.json 2> $OUT/bench_any384_$TAG.err
 echo "any-length 384^3 exit $?"; python scripts/show_bench.py $OUT/bench_any384_$TAG.json 2>/dev/null | head -20
 # memcheck of the kernels that have never run: the any-length suite and the new operators under compute-sanitizer
-timeout 900 compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest tests/test_gpu_zy_any_length.py -q -rxX \
+timeout 900 compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest tests/test_gpu_zy_any_length.py -q --runxfail \
     -k "poisson_any_length or scalar_laplacian or cavity_48x40" > $OUT/memcheck_any_$TAG.log 2>&1
 echo "memcheck exit $?"; tail -5 $OUT/memcheck_any_$TAG.log
 ls -la $OUT | tail -12
