@@ -503,6 +503,8 @@ def run_wave2d(args, local_rank):
                "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": nbytes + 16, "ms_per_step": ms_e / args.e2e_steps,
                "what": "push the interiors of u, v, p, vof from pinned host arrays + ghost updates + two-phase step + "
                        "status + asynchronous pull of the four interiors, every step"}
+    if getattr(args, "affinity_before", None):
+        os.sched_setaffinity(0, args.affinity_before)       # the CPU baseline sees every core
     print(json.dumps({
         "metric": "two-phase NS timestep Mcell-updates/s", "value": ncell * args.steps / (ms * 1e-3) / 1e6,
         "unit": "Mcell-updates/s", "n_gpus": 1, "steps": args.steps, "warmup": max(args.warmup, 6),
@@ -522,6 +524,40 @@ def run_wave2d(args, local_rank):
         "cpu_baseline": None if args.no_cpu_baseline else cpu_baseline_wave2d(), "kernels": kernels,
         "check": {"maxdiv": maxdiv, "maxCFL": maxcfl, "phase_integrals": [i1, i2]}}))
     G.destroy()
+
+
+def bind_to_gpu_cpus(local_rank):
+    """Pin this process to the CPUs NVML reports as local to its GPU (the socket the GPU's PCIe root hangs off), so
+    that the pinned host arrays of the e2e loop are allocated on that NUMA node -- the usual placement rule for
+    host<->device copies (NCCL does the same for its proxy threads).  Returns (previous mask, description); the caller
+    restores the mask before the CPU baseline, which must see every core.  FEN_BENCH_NO_AFFINITY=1 leaves it alone."""
+    try:
+        old = os.sched_getaffinity(0)
+    except (AttributeError, OSError):
+        return None, "unchanged (no sched_getaffinity)"
+    if os.environ.get("FEN_BENCH_NO_AFFINITY"):
+        return old, "unchanged (FEN_BENCH_NO_AFFINITY)"
+    try:
+        import pynvml
+        import torch
+        pynvml.nvmlInit()
+        try:
+            uuid = str(torch.cuda.get_device_properties(local_rank).uuid)
+            h = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + uuid if not uuid.startswith("GPU-") else uuid).encode())
+        except Exception:
+            h = pynvml.nvmlDeviceGetHandleByIndex(local_rank)
+        ncpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (max(ncpu, max(old) + 1) + 63) // 64)
+        cpus = {64 * w + b for w, word in enumerate(words) for b in range(64) if (int(word) >> b) & 1}
+        local = cpus & set(old)
+        if not local:
+            return old, "unchanged (NVML reports no usable local CPUs)"
+        if local == set(old):
+            return old, "unchanged (all %d CPUs are local to the GPU)" % len(old)
+        os.sched_setaffinity(0, local)
+        return old, "GPU-local CPUs (%d of %d) while the host arrays are allocated and copied" % (len(local), len(old))
+    except Exception as exc:            # a placement hint, never a reason to lose the bench line
+        return old, "unchanged (%s)" % repr(exc)[:80]
 
 
 def nccl_alltoall_reference(nx, ny, nz, world, x_periodic=True, iters=5):
@@ -591,6 +627,7 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device (the B200 path has no CPU fallback)")
     torch.cuda.set_device(local_rank)
+    args.affinity_before, args.affinity = bind_to_gpu_cpus(local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
@@ -838,6 +875,8 @@ def main():
                        "download is on the host (dv_o stays on the device: no driver touches it)"}
 
     cpu = None
+    if args.affinity_before:
+        os.sched_setaffinity(0, args.affinity_before)       # the CPU baseline sees every core
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         if channel:
             _, sec, _ = cpu_port_channel(64, 1, 1)
@@ -861,7 +900,8 @@ def main():
                                     "(BASELINE configs[1])" % n), "grid": [nx, ny, nz],
                        "decomposition": "z-slabs x%d" % world,
                        "nu": 1.0e-3 if channel else 0.01, "CFL": 0.25, "dt": dt,
-                       "l2": "working set (>= 12 GB) exceeds the 126 MB L2; no flush needed"},
+                       "l2": "working set (>= 12 GB) exceeds the 126 MB L2; no flush needed",
+                       "cpu_affinity": args.affinity},
             "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
             "cpu_baseline": cpu, "kernels": kernels, "nvlink": nvlink,
             "poisson_solve_ms": poisson_ms,
