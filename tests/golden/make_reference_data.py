@@ -8,7 +8,8 @@ against travel as small .npz files.  They are data, not code:
                               curve capillary_wave/postpro.py:92-101 measures its result against.
   rising_bubble_com_ref.npz   test/small_test/multiphase/rising_bubble/com_ref.txt -- the benchmark solution of the
                               rising-bubble test case 1 (Hysing et al.): time, centre-of-mass height and rise velocity
-                              (columns 0, 3, 4), the curves rising_bubble/postpro.py:55-75 plots its result against.
+                              (columns 0, 3, 4), the curves rising_bubble/postpro.py:55-75 plots its result against; t2, yc2, uc2: the same
+                              columns of com_ref_2.txt, test case 2 (density ratio 1000, sigma = 1.96; postpro_2.py).
 
   ghia_cavity_re1000.npz      test/small_test/navier_stokes/lid_driven/uref, vref -- Ghia, Ghia & Shin's centreline
                               velocities of the lid-driven cavity at Re = 1000 (17 points each, coordinate - 0.5), the
@@ -36,7 +37,10 @@ if __name__ == "__main__":
     np.savez_compressed(os.path.join(HERE, "prosperetti_capillary.npz"), curve=curve)
     com = np.genfromtxt(os.path.join(REF, "rising_bubble", "com_ref.txt"))
     assert com.shape == (2102, 5)
-    np.savez_compressed(os.path.join(HERE, "rising_bubble_com_ref.npz"), t=com[:, 0], yc=com[:, 3], uc=com[:, 4])
+    com2 = np.genfromtxt(os.path.join(REF, "rising_bubble", "com_ref_2.txt"))      # test case 2 (density ratio 1000)
+    assert com2.shape == (800, 5)
+    np.savez_compressed(os.path.join(HERE, "rising_bubble_com_ref.npz"), t=com[:, 0], yc=com[:, 3], uc=com[:, 4],
+                        t2=com2[:, 0], yc2=com2[:, 3], uc2=com2[:, 4])
     lid = "/root/reference/test/small_test/navier_stokes/lid_driven"
     uref, vref = np.genfromtxt(os.path.join(lid, "uref")), np.genfromtxt(os.path.join(lid, "vref"))
     assert uref.shape == (17, 2) and vref.shape == (17, 2)
