@@ -275,3 +275,48 @@ def test_two_phase_c_driver_runs():
     m = re.search(r"steps (\d+)  deformation ([0-9.]+)", r.stdout)
     assert m and int(m.group(1)) == 8193
     assert abs(float(m.group(2)) - 0.1204) < 0.002
+
+
+@pytest.mark.parametrize("case,Nx", [(1, 64), (2, 128)])
+def test_rising_bubble_at_the_reference_resolution(case, Nx):
+    """rising_bubble.f90 at the resolutions the reference itself runs (case 1: 64 x 128, case 2 -- density ratio 1000 --
+    128 x 256, 39 000 steps: seconds here, an hour for the numpy oracle) against the benchmark curves it ships: centre of
+    mass and rise velocity over the whole run, bubble volume conserved."""
+    import os
+    ref = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "rising_bubble_com_ref.npz"))
+    tr, yr, ur = (ref["t"], ref["yc"], ref["uc"]) if case == 1 else (ref["t2"], ref["yc2"], ref["uc2"])
+    Ny = 2 * Nx
+    Gg = fb.grid().setup(Nx, Ny, 1, 1.0, 2.0, 1.0 / Nx, bc=["Wall"] * 4)
+    gns = fb.MultiphaseSolver(Gg)
+    props = (1000.0, 100.0, 10.0, 1.0, 24.5) if case == 1 else (1000.0, 1.0, 10.0, 0.1, 1.96)
+    gns.rho_0, gns.rho_1, gns.mu_0, gns.mu_1, gns.sigma = props
+    gns.g = [0.0, -0.98, 0.0]
+    gns.init_solver(lambda x, y: float(bubble(x, y)))
+    dt = gns.set_timestep(0.25)
+    gns.beta = 2.0
+    for f in ("left", "right"):
+        gns.v.y.set_bc_type(f, 2)
+    d = Gg.delta
+    y = ((np.arange(1, Ny + 1) - 0.5) * d)[None, :]
+    t, step, out = 0.0, 0, []
+    every = max(1, int(0.01 / dt))
+    while t <= 3.0:
+        step += 1
+        t += dt
+        gns.navier_stokes_solver(step, dt)
+        if step % every == 0:
+            gns.vof.pull(); gns.v.y.pull()
+            f = gns.vof.I[..., 0]
+            fy = 0.5 * (gns.vof.f[1:-1, 2:, 1] + f)                       # rising_bubble.f90:145: vof(i,j+1) + vof(i,j)
+            iv = f.sum() * d * d
+            out.append((t, (y * f).sum() * d * d / iv, (gns.v.y.I[..., 0] * fy).sum() * d * d / iv, iv))
+    o = np.array(out)
+    yref, uref = np.interp(o[:, 0], tr, yr), np.interp(o[:, 0], tr, ur)
+    # the oracle at 64 x 128: centre of mass within 0.011 (case 1) / 0.036 (case 2), peak velocity 1.1 % / 0.5 % low
+    tol_y, tol_u = (0.015, 0.025) if case == 1 else (0.045, 0.02)
+    assert np.abs(o[:, 1] - yref).max() < tol_y
+    assert abs(o[:, 2].max() - uref.max()) < tol_u * uref.max()
+    assert abs(o[-1, 3] / o[0, 3] - 1.0) < 1e-10
+    md, _ = gns.status()
+    assert abs(md) < 1e-9
+    Gg.destroy()
