@@ -320,3 +320,55 @@ def test_rising_bubble_at_the_reference_resolution(case, Nx):
     md, _ = gns.status()
     assert abs(md) < 1e-9
     Gg.destroy()
+
+
+def test_viscous_decay_of_a_gravity_wave():
+    """test/small_test/multiphase/viscous_decay/viscous_decay.f90 -- the reference's one surface-gravity-wave case, the
+    2-D analogue of BASELINE configs[4] -- at its own 128 x 256 resolution for its own 33 144 steps (t = 5, six
+    periods).  (1) the potential energy of the initial water column reproduces the constant the reference's postpro.py
+    carries (Ep0 = 4903.0289577702924, a number computed by the reference itself); (2) the first three steps match the
+    oracle; (3) the wave energy decays at 1.13 times the single-fluid rate exp(-2 gamma t) the script plots it against
+    (the C restatement's value for this run; bounds 1.0 .. 1.25), in equipartition."""
+    from tests.test_oracle_mf import VD_EP0, viscous_decay_case, wave_energy
+    Nx = 128
+    Go, ons, dt, om, gamma = viscous_decay_case(Nx)
+    Gg = fb.grid().setup(Nx, 2 * Nx, 1, 1.0, 2.0, fo._f32(1) / fo._f32(Nx), bc=["Periodic", "Periodic", "Wall", "Wall"])
+    gns = fb.MultiphaseSolver(Gg)
+    gns.rho_0, gns.rho_1, gns.mu_0, gns.mu_1, gns.sigma = ons.rho_0, ons.rho_1, ons.mu_0, ons.mu_1, 0.0
+    gns.g = [0.0, -mf.GRAVITY, 0.0]
+    gns.init_solver(lambda x, y: float(y - 0.005 * np.cos(2.0 * fo.PI * x) - 1.0))
+    assert gns.set_timestep(1.0) * 0.1 == dt
+    for a, b in zip(gns.v.comps, ons.v.comps):
+        a.f[...] = b.f
+        a.push()
+    # (1) flat-interface potential energy from the device's own get_vof_from_distance
+    flat = fb.VoF(fb.grid().setup(Nx, 2 * Nx, 1, 1.0, 2.0, fo._f32(1) / fo._f32(Nx),
+                                  bc=["Periodic", "Periodic", "Wall", "Wall"]))
+    flat.get_vof_from_distance(lambda x, y: float(y - 1.0))
+    flat.vof.pull()
+    z = np.zeros_like(flat.vof.f[:, :, 1])
+    ep_flat = wave_energy(Go, z, z, flat.vof.f[:, :, 1])[1]
+    assert abs(ep_flat + VD_EP0) < 1e-8 * VD_EP0
+    t, step, out = 0.0, 0, []
+    while t < 5.0:
+        step += 1
+        t += dt
+        gns.navier_stokes_solver(step, dt)
+        if step <= 3:
+            ons.navier_stokes_solver(step, dt)
+            gns.v.pull(); gns.p.pull(); gns.vof.pull()
+            for a, b in ((gns.v.x, ons.v.x), (gns.v.y, ons.v.y), (gns.p, ons.p)):
+                assert np.abs(a.I - b.I).max() <= 1e-11 * max(1.0, np.abs(b.I).max()), step
+            assert np.abs(gns.vof.I - ons.vof.I).max() < 1e-12
+        if step % 100 == 0:
+            gns.v.pull(); gns.vof.pull()
+            ek, ep = wave_energy(Go, gns.v.x.f[:, :, 1], gns.v.y.f[:, :, 1], gns.vof.f[:, :, 1])
+            out.append((t, ek, ep - ep_flat))
+    assert step == 33144
+    o = np.array(out)
+    rate = -np.polyfit(o[:, 0], np.log(o[:, 1] + o[:, 2]), 1)[0]
+    assert 1.0 < rate / (2.0 * gamma) < 1.25, rate / (2.0 * gamma)
+    assert 0.93 < (o[:, 1] / o[:, 2]).mean() < 1.05
+    md, _ = gns.status()
+    assert abs(md) < 1e-9
+    Gg.destroy()
