@@ -6,6 +6,9 @@ import pytest
 # kernels of different ranks must be able to start while a flag-wait kernel spins (tests/ranks.py runs several
 # ranks on one device): no lazy module loading.  Must be set before the CUDA runtime initialises.
 os.environ.setdefault("CUDA_MODULE_LOADING", "EAGER")
+# the C/OpenMP oracles: threads sleep at barriers instead of spinning, so a busy neighbour on the machine (or pytest-xdist)
+# costs a little instead of a factor of fifty.  Must be set before libgomp is loaded (numpy / torch pull it in).
+os.environ.setdefault("OMP_WAIT_POLICY", "PASSIVE")
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if ROOT not in sys.path:

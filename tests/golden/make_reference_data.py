@@ -20,7 +20,8 @@ against travel as small .npz files.  They are data, not code:
 
   shear_drop_basilisk.npz     test/small_test/multiphase/shear_drop/reference/Re1Ca02b.csv, Re1Ca04b.csv, Re1Ca09b.csv --
                               the Basilisk deformation curves D(t) of a drop in shear flow at Re = 1, Ca = 0.2, 0.4,
-                              0.9 (columns t, D), the points shear_drop/postpro.py:44-52 plots its curves against.
+                              0.9 (columns t, D), the points shear_drop/postpro.py:44-52 plots its curves against, and the drop
+                              contours shapeRe1Ca0*b.txt it draws its final vof = 0.5 contours over (:62-69).
 
 Usage (in the build container, where /root/reference is mounted):  python tests/golden/make_reference_data.py
 """
@@ -39,8 +40,11 @@ if __name__ == "__main__":
     assert com.shape == (2102, 5)
     com2 = np.genfromtxt(os.path.join(REF, "rising_bubble", "com_ref_2.txt"))      # test case 2 (density ratio 1000)
     assert com2.shape == (800, 5)
+    shape1 = np.genfromtxt(os.path.join(REF, "rising_bubble", "shape_ref.txt"))     # bubble contour of case 1 at t = 3
+    shape1 = shape1[~np.isnan(shape1).any(axis=1)]
+    assert shape1.shape == (650, 2)
     np.savez_compressed(os.path.join(HERE, "rising_bubble_com_ref.npz"), t=com[:, 0], yc=com[:, 3], uc=com[:, 4],
-                        t2=com2[:, 0], yc2=com2[:, 3], uc2=com2[:, 4])
+                        t2=com2[:, 0], yc2=com2[:, 3], uc2=com2[:, 4], shape1=shape1)
     lid = "/root/reference/test/small_test/navier_stokes/lid_driven"
     uref, vref = np.genfromtxt(os.path.join(lid, "uref")), np.genfromtxt(os.path.join(lid, "vref"))
     assert uref.shape == (17, 2) and vref.shape == (17, 2)
@@ -49,5 +53,7 @@ if __name__ == "__main__":
     drops = {"D_Ca%s" % ca: np.genfromtxt(os.path.join(sd, "Re1Ca%sb.csv" % ca), delimiter=",", skip_header=1)
              for ca in ("02", "04", "09")}
     assert drops["D_Ca02"].shape == (11, 2) and drops["D_Ca04"].shape == (21, 2) and drops["D_Ca09"].shape == (31, 2)
+    for ca in ("02", "04", "09"):        # Basilisk's drop contours at the end of each case, box-centred coordinates
+        drops["shape_Ca%s" % ca] = np.genfromtxt(os.path.join(sd, "shapeRe1Ca%sb.txt" % ca))
     np.savez_compressed(os.path.join(HERE, "shear_drop_basilisk.npz"), **drops)
-    print("wrote", curve.shape, com.shape, uref.shape, vref.shape, {k: v.shape for k, v in drops.items()})
+    print("wrote", curve.shape, com.shape, shape1.shape, uref.shape, vref.shape, {k: v.shape for k, v in drops.items()})

@@ -192,6 +192,7 @@ def _rising_bubble(Nx, case=1):
         out.append((t, (y * f).sum() * d * d / iv,
                     (0.5 * ns.v.y.I[..., 0] * (ns.vof.sh(0, 1)[..., 0] + f)).sum() * d * d / iv, iv))
     assert abs(ns.maxdiv) < 1e-12
+    _rising_bubble.last = (G, ns.vof.I[..., 0].copy())
     return np.array(out)
 
 
@@ -209,6 +210,10 @@ def test_rising_bubble_follows_the_benchmark(Nx):
     assert abs(o[:, 2].max() - uref.max()) < 0.025 * uref.max()
     assert np.abs(o[:, 2] - uref).max() < (0.012 if Nx == 32 else 0.007)        # and it tightens with resolution
     assert abs(o[-1, 3] / o[0, 3] - 1.0) < 1e-12
+    # the bubble contour at t = 3 against the benchmark contour postpro.py:38-48 draws it over (shape_ref.txt): within
+    # 1.3 cells at 64 x 128 (0.0177), 0.63 cells at 32 x 64 (0.0195)
+    G, vof = _rising_bubble.last
+    assert shape_distance(ref["shape1"], contour_points(vof, G.delta)) < max(0.0205, 1.3 * G.delta)
 
 
 # ---- test/small_test/volume_of_fluid/Zalesak --------------------------------------------------------------------------
@@ -275,6 +280,26 @@ def deformation(vof, delta, centre=(1.0, 1.0)):
     return float((d.max() - d.min()) / (d.max() + d.min()))
 
 
+def contour_points(vof, delta):
+    """The points of the vof = 0.5 contour that matplotlib's contour (the reference's postpro scripts) would draw: linear
+    interpolation on the lines joining neighbouring cell centres."""
+    cx = (np.arange(vof.shape[0]) + 0.5) * delta
+    cy = (np.arange(vof.shape[1]) + 0.5) * delta
+    f = vof - 0.5
+    i, j = np.nonzero(f[:-1, :] * f[1:, :] < 0)
+    px = np.stack([cx[i] + f[i, j] / (f[i, j] - f[i + 1, j]) * delta, cy[j]], 1)
+    i, j = np.nonzero(f[:, :-1] * f[:, 1:] < 0)
+    py = np.stack([cx[i], cy[j] + f[i, j] / (f[i, j] - f[i, j + 1]) * delta], 1)
+    return np.concatenate([px, py])
+
+
+def shape_distance(ref, pts):
+    """Largest distance from a point of one contour to the nearest point of the other, both ways (the point sets are
+    sampled at about one grid spacing, so half a spacing is the floor)."""
+    d = np.sqrt(((ref[:, None, :] - pts[None, :, :]) ** 2).sum(-1))
+    return float(max(d.min(1).max(), d.min(0).max()))
+
+
 def shear_drop_case(Ca, N=64):
     """shear_drop.f90:36-95: neutrally buoyant drop of radius 0.5 in a 2 x 2 box, x periodic, walls moving at -U / +U,
     Re = 1, viscosity ratio 1, surface tension from the capillary number, linear shear as the initial velocity."""
@@ -323,6 +348,9 @@ def test_shear_drop_deformation_follows_basilisk(Ca, key, Tmax, tol):
     mine = np.interp(ref[1:, 0], D[:, 0], D[:, 1])
     assert np.abs(mine - ref[1:, 1]).max() < tol, np.abs(mine - ref[1:, 1]).max()
     assert abs(D[-1, 1] - ref[-1, 1]) < tol
+    # the final drop contour against the Basilisk contour postpro.py:62-69 draws it over (box-centred coordinates)
+    shape = np.load(os.path.join(GOLD, "shear_drop_basilisk.npz"))[key.replace("D_", "shape_")]
+    assert shape_distance(shape, contour_points(c.get(mfc.VOF)[1:-1, 1:-1], G.delta) - 1.0) < 0.8 * G.delta
     c.destroy()
 
 
