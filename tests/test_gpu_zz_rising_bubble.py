@@ -258,6 +258,11 @@ def test_shear_drop_deformation_follows_basilisk(Ca, key, Tmax, tol):
     D = np.array(D)
     mine = np.interp(ref[1:, 0], D[:, 0], D[:, 1])
     assert np.abs(mine - ref[1:, 1]).max() < tol
+    from tests.test_oracle_mf import contour_points, shape_distance
+    shape = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden",
+                                 "shear_drop_basilisk.npz"))[key.replace("D_", "shape_")]
+    gns.vof.pull()
+    assert shape_distance(shape, contour_points(gns.vof.I[..., 0], Go.delta) - 1.0) < 0.8 * Go.delta
     md, _ = gns.status()
     assert abs(md) < 1e-11
     Gg.destroy()
@@ -317,6 +322,10 @@ def test_rising_bubble_at_the_reference_resolution(case, Nx):
     assert np.abs(o[:, 1] - yref).max() < tol_y
     assert abs(o[:, 2].max() - uref.max()) < tol_u * uref.max()
     assert abs(o[-1, 3] / o[0, 3] - 1.0) < 1e-10
+    if case == 1:           # the contour at t = 3 against shape_ref.txt (the oracle at this resolution: 0.0177)
+        from tests.test_oracle_mf import contour_points, shape_distance
+        gns.vof.pull()
+        assert shape_distance(ref["shape1"], contour_points(gns.vof.I[..., 0], d)) < 0.0205
     md, _ = gns.status()
     assert abs(md) < 1e-9
     Gg.destroy()
