@@ -317,8 +317,9 @@ def test_rising_bubble_at_the_reference_resolution(case, Nx):
             out.append((t, (y * f).sum() * d * d / iv, (gns.v.y.I[..., 0] * fy).sum() * d * d / iv, iv))
     o = np.array(out)
     yref, uref = np.interp(o[:, 0], tr, yr), np.interp(o[:, 0], tr, ur)
-    # the oracle at 64 x 128: centre of mass within 0.011 (case 1) / 0.036 (case 2), peak velocity 1.1 % / 0.5 % low
-    tol_y, tol_u = (0.015, 0.025) if case == 1 else (0.045, 0.02)
+    # the oracle at these very resolutions: centre of mass within 0.011 (case 1, 64 x 128) / 0.0253 (case 2, 128 x 256: 45
+    # minutes of numpy, run once), peak velocity 1.1 % / 0.3 % low
+    tol_y, tol_u = (0.015, 0.025) if case == 1 else (0.032, 0.01)
     assert np.abs(o[:, 1] - yref).max() < tol_y
     assert abs(o[:, 2].max() - uref.max()) < tol_u * uref.max()
     assert abs(o[-1, 3] / o[0, 3] - 1.0) < 1e-10
