@@ -3,6 +3,7 @@ include/fen_gpu.h declares, fails loudly without a device, and the FFT index log
 import os
 import re
 import subprocess
+import sys
 
 import pytest
 
@@ -172,3 +173,25 @@ def test_closest_grid_node_matches_the_reference_rule():
     assert G.closest_grid_node([100.0, -100.0, 0.0], 4) == [8, 1, 1]
     G.ndim = 2
     assert G.closest_grid_node([-0.9, 0.6], 0) == [1, 3, 1]
+
+
+@pytest.mark.parametrize("case", ["tgv", "channel", "wave2d"])
+def test_bench_reference_arm_prints_the_contract_line(case):
+    """bench.py --impl reference (the CPU restatement timed on the host cores, no GPU needed): one JSON line with the
+    keys of the contract -- metric, value, unit, n_gpus, steps, warmup, ms_per_step, higher_is_better, scaling,
+    vs_baseline, dtype, data, config.workload, impl, cpu_baseline{value, unit, cores, kind, sample}, e2e{value, unit,
+    h2d_bytes_per_step = d2h_bytes_per_step = 0} -- for each bench case, on a small sample."""
+    import json
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--case", case, "--steps",
+                        "1", "--warmup", "1", "--cpu-size", "32"], capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert r.returncode == 0, r.stderr[-2000:]
+    line = json.loads(r.stdout.strip().splitlines()[-1])
+    for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+                "vs_baseline", "dtype", "data", "config", "impl", "cpu_baseline", "e2e"):
+        assert key in line, key
+    assert line["impl"] == "reference" and line["dtype"] == "f64" and line["vs_baseline"] is None
+    assert line["value"] > 0 and "workload" in line["config"]
+    cb = line["cpu_baseline"]
+    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == line["value"] and cb["sample"]
+    e = line["e2e"]
+    assert e["value"] == line["value"] and e["h2d_bytes_per_step"] == 0 and e["d2h_bytes_per_step"] == 0
