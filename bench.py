@@ -554,6 +554,8 @@ def bind_to_gpu_cpus(local_rank):
             return old, "unchanged (NVML reports no usable local CPUs)"
         if local == set(old):
             return old, "unchanged (all %d CPUs are local to the GPU)" % len(old)
+        if len(local) < 4 or 4 * len(local) < len(old):      # a sliver of the allowed CPUs (cgroup cpuset): not worth it
+            return old, "unchanged (only %d of the %d allowed CPUs are local to the GPU)" % (len(local), len(old))
         os.sched_setaffinity(0, local)
         return old, "GPU-local CPUs (%d of %d) while the host arrays are allocated and copied" % (len(local), len(old))
     except Exception as exc:            # a placement hint, never a reason to lose the bench line
