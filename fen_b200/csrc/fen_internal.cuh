@@ -173,6 +173,7 @@ int field_check(fen_ctx* c, int id, Field** out, bool alloc = true);
 int field_alloc(fen_ctx* c, Field& f);
 void init_field(fen_ctx* c, int id, int gl, int loc);     // scalar%allocate defaults (scalar.f90:63-133)
 void free_field(Field& f);
+void step_graphs_clear(fen_ctx* c);                        // drops the captured step graphs (they bake buffer addresses)
 int fetch_red(fen_ctx* c, int n);                          // async copy of d_red[0..n) to h_red
 
 // tma.cu

@@ -1184,6 +1184,9 @@ static std::vector<double2> half_phases(int n) {
 void poisson_destroy(fen_ctx* c) {
     Poisson* p = c->ps;
     if (!p) return;
+    // a captured step bakes this object's device buffers into its kernel arguments: a replay after the buffers are
+    // gone (and a new Poisson object at the same heap address) would run on freed memory
+    step_graphs_clear(c);
     if (!p->multi) {
         if (p->Cz && p->Cz != p->C) cudaFree(p->Cz);
         if (p->C) cudaFree(p->C);
@@ -1481,8 +1484,15 @@ static int dispatch_dct_lines(fen_ctx* c, int Lf, const LArgs& a, const double2*
 
 static int log2i(int n) { int s = 0; while ((1 << s) < n) ++s; return s; }
 
+static int poisson_build(fen_ctx* c);
 int poisson_init(fen_ctx* c) {
     if (c->ps) poisson_destroy(c);
+    step_graphs_clear(c);
+    const int r = poisson_build(c);
+    if (r != FEN_OK) poisson_destroy(c);      // never leave a half-built solver behind (null twiddles, C == nullptr)
+    return r;
+}
+static int poisson_build(fen_ctx* c) {
     const fen_grid_desc& g = c->g;
     // variant from periodic_bc only (poisson.f90:68-111)
     bool per[3];
@@ -1533,8 +1543,8 @@ int poisson_init(fen_ctx* c) {
             return set_error(FEN_ERR_UNSUPPORTED, "slab transposes need a power-of-two number of ranks and "
                                                   "power-of-two ny / nranks, nz / nranks (got %d, %d, %d)",
                              g.nranks, g.ny, g.nz);
+        p->multi = true;                      // before any arena pointer is stored: poisson_destroy must not free them
         FEN_TRY(comm_spectral(c, p->peerC, p->peerCz));
-        p->multi = true;
         p->nyl = g.ny / g.nranks;
         p->C = p->peerC[g.rank];
         p->Cz = p->peerCz[g.rank];

@@ -7,9 +7,7 @@ the tuned register-path kernels; every other length whose prime factors are <= 6
 phases are executed on the CPU by tests/cpu/test_fft_any.cu (global indexing included).  Oracle: the numpy restatement,
 which takes any n like FFTW does.
 
-FIRST-RUN STATUS: written after the round's GPU budget was spent, so these tests have not executed on a B200 yet; they
-are marked xfail(strict=False) for that reason alone (an XPASS is the expected outcome) and sort after every other GPU
-file.  The mark goes away with the first GPU session of the next round."""
+First run on a B200: the driver's round-1 GPU tier (19/19) and round 2's first session (profiles/r02a_pytest_firstrun.log)."""
 import numpy as np
 import pytest
 
@@ -17,9 +15,7 @@ import fen_b200 as fb
 from oracle import fen_oracle as fo
 from tests.test_gpu_parity import PI, _compare, _setup_ns, make_pair, rel_l2
 
-pytestmark = [pytest.mark.gpu, pytest.mark.timeout(900),
-              pytest.mark.xfail(strict=False, reason="not yet run on a GPU (written after the round's GPU budget was "
-                                                     "spent): first run is round 2")]
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(900)]
 
 P4, P6 = ["Periodic"] * 4, ["Periodic"] * 6
 ANY_CASES = [

@@ -3,10 +3,14 @@ the only two-phase case of the reference with walls all round, i.e. the two-phas
 (DCT in x, Thomas in y) with free-slip side walls.  Oracle: oracle/fen_oracle_mf.py, pinned against the benchmark
 data the reference ships (tests/test_oracle_mf.py::test_rising_bubble_follows_the_benchmark).
 
-FIRST-RUN STATUS: this file was written after the round's GPU budget was spent, so it has not executed on a B200 yet.
-It is marked xfail(strict=False) for that reason alone -- an XPASS in the report is the expected outcome, and the mark
-goes away with the first GPU session of the next round.  It sorts last among the GPU files so that nothing runs after
-it in the same process."""
+Early-step parity against the oracle uses set-ups SHIFTED off the grid symmetry: a drop or bubble centred on a grid node
+makes the reconstruction's x/y-dominant branch |n_x| == max(|n_x|, |n_y|) a tie on the diagonals, and the oracle then
+amplifies a 1e-16 perturbation of ITS OWN input to 6e-6 (shear drop, one step) / 4e-4 (bubble, six steps) -- asserted
+on the CPU by tests/test_oracle_mf.py::test_grid_centred_interfaces_are_ill_conditioned.  Shifted by (0.0137, 0.0071)
+the same perturbation stays at 1e-15, and the parity bounds below (1e-12 after one step, 1e-10 after a few) are kept.
+The whole-run physics (deformation curves, centre of mass) uses the reference's own centred set-ups.  (Round 2's first
+GPU session: profiles/r02a_pytest_firstrun.log holds the tracebacks of the five centred-parity failures this replaces.)
+It sorts last among the GPU files so that nothing runs after it in the same process."""
 import numpy as np
 import pytest
 
@@ -14,9 +18,8 @@ import fen_b200 as fb
 from oracle import fen_oracle as fo
 from oracle import fen_oracle_mf as mf
 
-pytestmark = [pytest.mark.gpu, pytest.mark.timeout(900),
-              pytest.mark.xfail(strict=False, reason="not yet run on a GPU (written after the round's GPU budget was "
-                                                     "spent): first run is round 2")]
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(900)]
+SHIFT = (0.0137, 0.0071)            # off every grid symmetry (see the module docstring)
 
 
 def rel_l2(a, b):
@@ -24,8 +27,8 @@ def rel_l2(a, b):
     return np.linalg.norm((a - b).ravel()) / (n if n > 0 else 1.0)
 
 
-def bubble(x, y):                       # rising_bubble.f90:104-116 (positive inside the light phase)
-    return -(np.sqrt((x - 0.5) ** 2 + (y - 0.5) ** 2) - 0.25)
+def bubble(x, y, shift=(0.0, 0.0)):     # rising_bubble.f90:104-116 (positive inside the light phase)
+    return -(np.sqrt((x - 0.5 - shift[0]) ** 2 + (y - 0.5 - shift[1]) ** 2) - 0.25)
 
 
 def point_quantities(vof, vy, d):       # rising_bubble.f90:131-165: volume, centre of mass, rise velocity
@@ -37,17 +40,17 @@ def point_quantities(vof, vy, d):       # rising_bubble.f90:131-165: volume, cen
     return iv, (y * vof).sum() * d * d / iv, fy
 
 
-def bubble_pair(Nx):
+def bubble_pair(Nx, shift=(0.0, 0.0)):
     Ny = 2 * Nx
     bc = ["Wall"] * 4
     Go = fo.Grid(Nx, Ny, 1, 1.0, 2.0, 1.0 / Nx, bc=bc)
     Gg = fb.grid().setup(Nx, Ny, 1, 1.0, 2.0, 1.0 / Nx, bc=bc)
-    ons = mf.MultiphaseNavierStokes(Go, 1000.0, 100.0, 10.0, 1.0, 24.5, distance=bubble)
+    ons = mf.MultiphaseNavierStokes(Go, 1000.0, 100.0, 10.0, 1.0, 24.5, distance=lambda x, y: bubble(x, y, shift))
     ons.g[1] = -0.98
     gns = fb.MultiphaseSolver(Gg)
     gns.rho_0, gns.rho_1, gns.mu_0, gns.mu_1, gns.sigma = 1000.0, 100.0, 10.0, 1.0, 24.5
     gns.g = [0.0, -0.98, 0.0]
-    gns.init_solver(lambda x, y: float(bubble(x, y)))
+    gns.init_solver(lambda x, y: float(bubble(x, y, shift)))
     odt = ons.set_timestep(0.25)
     gdt = gns.set_timestep(0.25)
     assert gdt == odt
@@ -60,7 +63,7 @@ def bubble_pair(Nx):
 
 
 def test_rising_bubble_steps_match_oracle():
-    Go, Gg, ons, gns, dt = bubble_pair(16)
+    Go, Gg, ons, gns, dt = bubble_pair(16, SHIFT)
     assert gns.poisson_variant == "nn" and ons.poisson.variant == "nn"
     for face in fo.FACES[:4]:
         for a, b in ((gns.vof, ons.vof), (gns.p, ons.p), (gns.p_hat, ons.p_hat), (gns.rho, ons.rho),
@@ -227,30 +230,39 @@ def test_shear_drop_deformation_follows_basilisk(Ca, key, Tmax, tol):
     import os
     from tests.test_oracle_mf import deformation, shear_drop_case
     ref = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "shear_drop_basilisk.npz"))[key]
-    Go, ons, dt = shear_drop_case(Ca)
-    N = Go.Nx
-    Gg = fb.grid().setup(N, N, 1, 2.0, 2.0, 2.0 * fo._f32(1) / fo._f32(N), bc=["Periodic", "Periodic", "Wall", "Wall"])
-    gns = fb.MultiphaseSolver(Gg)
-    gns.rho_0, gns.rho_1, gns.mu_0, gns.mu_1, gns.sigma, gns.beta = ons.rho_0, ons.rho_1, ons.mu_0, ons.mu_1, ons.sigma, 1.0
-    gns.init_solver(lambda x, y: float(-(np.sqrt((x - 1.0) ** 2 + (y - 1.0) ** 2) - 0.5)))
-    assert gns.set_timestep(1.0) == dt
-    gns.v.x.set_bc("top", 1.0)
-    gns.v.x.set_bc("bottom", -1.0)
-    # the initial shear profile is the oracle's (interior and ghosts)
-    for a, b in zip(gns.v.comps, ons.v.comps):
-        a.f[...] = b.f
-        a.push()
+    def pair(shift):
+        Go, ons, dt = shear_drop_case(Ca, shift=shift)
+        N = Go.Nx
+        Gg = fb.grid().setup(N, N, 1, 2.0, 2.0, 2.0 * fo._f32(1) / fo._f32(N), bc=["Periodic", "Periodic", "Wall", "Wall"])
+        gns = fb.MultiphaseSolver(Gg)
+        gns.rho_0, gns.rho_1, gns.mu_0, gns.mu_1, gns.sigma, gns.beta = ons.rho_0, ons.rho_1, ons.mu_0, ons.mu_1, ons.sigma, 1.0
+        gns.init_solver(lambda x, y: float(-(np.sqrt((x - 1.0 - shift[0]) ** 2 + (y - 1.0 - shift[1]) ** 2) - 0.5)))
+        assert gns.set_timestep(1.0) == dt
+        gns.v.x.set_bc("top", 1.0)
+        gns.v.x.set_bc("bottom", -1.0)
+        # the initial shear profile is the oracle's (interior and ghosts)
+        for a, b in zip(gns.v.comps, ons.v.comps):
+            a.f[...] = b.f
+            a.push()
+        return Go, Gg, ons, gns, dt
+
+    # (1) five steps against the oracle, drop shifted off the grid symmetry (module docstring)
+    Go, Gg, ons, gns, dt = pair(SHIFT)
+    for step in range(1, 6):
+        gns.navier_stokes_solver(step, dt)
+        ons.navier_stokes_solver(step, dt)
+        gns.v.pull(); gns.p.pull(); gns.vof.pull()
+        for a, b in ((gns.v.x, ons.v.x), (gns.v.y, ons.v.y), (gns.p, ons.p)):
+            assert np.abs(a.I - b.I).max() <= 1e-12 * max(1.0, np.abs(b.I).max()), step
+        assert np.abs(gns.vof.I - ons.vof.I).max() < 1e-12
+    Gg.destroy()
+    # (2) the reference's own (centred) case for its whole run
+    Go, Gg, ons, gns, dt = pair((0.0, 0.0))
     t, step, D = 0.0, 0, []
     while t <= Tmax:
         step += 1
         t += dt
         gns.navier_stokes_solver(step, dt)
-        if step <= 5:
-            ons.navier_stokes_solver(step, dt)
-            gns.v.pull(); gns.p.pull(); gns.vof.pull()
-            for a, b in ((gns.v.x, ons.v.x), (gns.v.y, ons.v.y), (gns.p, ons.p)):
-                assert np.abs(a.I - b.I).max() <= 1e-12 * max(1.0, np.abs(b.I).max()), step
-            assert np.abs(gns.vof.I - ons.vof.I).max() < 1e-12
         if step % 64 == 0:
             gns.vof.pull()
             D.append((t, deformation(gns.vof.I[..., 0], Go.delta)))
@@ -334,7 +346,7 @@ def test_rising_bubble_at_the_reference_resolution(case, Nx):
 
 def test_viscous_decay_of_a_gravity_wave():
     """test/small_test/multiphase/viscous_decay/viscous_decay.f90 -- the reference's one surface-gravity-wave case, the
-    2-D analogue of BASELINE configs[4] -- at its own 128 x 256 resolution for its own 33 144 steps (t = 5, six
+    2-D analogue of BASELINE configs[4] -- at its own 128 x 256 resolution for its own 33 145 steps (t = 5, six
     periods).  (1) the potential energy of the initial water column reproduces the constant the reference's postpro.py
     carries (Ep0 = 4903.0289577702924, a number computed by the reference itself); (2) the first three steps match the
     oracle; (3) the wave energy decays at 1.13 times the single-fluid rate exp(-2 gamma t) the script plots it against
@@ -374,7 +386,7 @@ def test_viscous_decay_of_a_gravity_wave():
             gns.v.pull(); gns.vof.pull()
             ek, ep = wave_energy(Go, gns.v.x.f[:, :, 1], gns.v.y.f[:, :, 1], gns.vof.f[:, :, 1])
             out.append((t, ek, ep - ep_flat))
-    assert step == 33144
+    assert step == 33145                # ceil(5 / dt) = ceil(33144.6): viscous_decay.f90:68-71 (do while time < Tmax)
     o = np.array(out)
     rate = -np.polyfit(o[:, 0], np.log(o[:, 1] + o[:, 2]), 1)[0]
     assert 1.0 < rate / (2.0 * gamma) < 1.25, rate / (2.0 * gamma)
