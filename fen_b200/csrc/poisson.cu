@@ -26,6 +26,7 @@
 #include "fen_internal.cuh"
 #include "fft_core.cuh"
 #include "fft_any.cuh"
+#include "slab_bulk.cuh"
 
 namespace fen {
 
@@ -46,6 +47,10 @@ struct Poisson {
     double* c1 = nullptr;           // Thomas c1 table, indexed like the line layout
     int tri_n = 0;
     bool multi = false;             // C / Cz live in the comm arena and the transposes are peer stores
+    // multi-rank ppp / ppn with 64..1024-point lines: granule-blocked transposed layouts + bulk stores (slab_bulk.cuh)
+    bool blocked = false;
+    double2* Cr = nullptr;          // blocked path: row-layout output of the y inverse (input of the x c2r pass) and,
+                                    // for ppn, the [g][jl][k][8] staging of the back substitution; local memory
     double2* peerC[FEN_MAX_RANKS] = {};
     double2* peerCz[FEN_MAX_RANKS] = {};
 };
@@ -819,7 +824,32 @@ struct TArgs {
     const double* lx; const double* lo;     // lo == nullptr in 2-D
     int form2d;
     int mean;              // subtract the mean of phi (pn, ppn): see k_thomas_bwd
+    // blocked z-pencil layout (slab_bulk.cuh): thread e of granule g = blockIdx.y owns system kx = 8 g + e % 8,
+    // jl = e / 8 at C + so * g + e (so = granule stride, sl = plane stride nyl * 8); the back substitution writes
+    // its solution to `out` laid out [g][jl][k][8]
+    int blocked = 0;
+    double2* out = nullptr;
+    long long out_gs = 0;
 };
+struct TSys {              // one thread's system
+    long long off;         // offset of its first element in C / c1
+    int kx, lo_idx;
+    bool valid;
+};
+__device__ __forceinline__ TSys thomas_sys(const TArgs& g) {
+    TSys s;
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (!g.blocked) {
+        s.kx = e; s.lo_idx = g.o0 + blockIdx.y;
+        s.off = e + g.so * blockIdx.y;
+        s.valid = e < g.npc;
+    } else {
+        s.kx = blockIdx.y * 8 + (e & 7); s.lo_idx = g.o0 + (e >> 3);
+        s.off = g.so * blockIdx.y + e;
+        s.valid = e < g.nouter * 8;
+    }
+    return s;
+}
 
 // pivot term shared by both sweeps: 3-D: ((b + lx) + lo) - a*c1prev ; 2-D uses its own groupings
 __device__ __forceinline__ double piv3(double b, double lx, double lo, double a, double c1p) {
@@ -828,12 +858,11 @@ __device__ __forceinline__ double piv3(double b, double lx, double lo, double a,
 
 // c1 table (depends only on the grid): computed once at init with the reference's arithmetic
 __global__ void k_thomas_c1(TArgs g) {
-    const int kx = blockIdx.x * blockDim.x + threadIdx.x;
-    const int o = blockIdx.y;
-    if (kx >= g.npc) return;
-    double* c1 = g.c1 + kx + g.so * o;
-    const double lx = g.lx[kx];
-    const double lo = g.lo ? g.lo[g.o0 + o] : 0.0;
+    const TSys sy = thomas_sys(g);
+    if (!sy.valid) return;
+    double* c1 = g.c1 + sy.off;
+    const double lx = g.lx[sy.kx];
+    const double lo = g.lo ? g.lo[sy.lo_idx] : 0.0;
     double c1p;
     if (g.form2d) c1p = __ddiv_rn(g.c[0], __dadd_rn(g.b[0], lx));                       // :350
     else c1p = __dmul_rn(g.c[0], __ddiv_rn(1.0, __dadd_rn(__dadd_rn(g.b[0], lx), lo)));  // :1096-1097
@@ -859,13 +888,12 @@ __device__ __forceinline__ double2 c_sub_ad(double2 r, double a, double2 d) {   
 }
 
 __global__ void __launch_bounds__(128) k_thomas_fwd(TArgs g) {
-    const int kx = blockIdx.x * blockDim.x + threadIdx.x;
-    const int o = blockIdx.y;
-    if (kx >= g.npc) return;
-    double2* C = g.C + kx + g.so * o;
-    const double* c1t = g.c1 + kx + g.so * o;
-    const double lx = g.lx[kx];
-    const double lo = g.lo ? g.lo[g.o0 + o] : 0.0;
+    const TSys sy = thomas_sys(g);
+    if (!sy.valid) return;
+    double2* C = g.C + sy.off;
+    const double* c1t = g.c1 + sy.off;
+    const double lx = g.lx[sy.kx];
+    const double lo = g.lo ? g.lo[sy.lo_idx] : 0.0;
     const int n = g.n;
     double2 d;
     {
@@ -911,24 +939,23 @@ __global__ void __launch_bounds__(128) k_thomas_fwd(TArgs g) {
     }
 }
 
-// Back substitution.  SC: the solution is stored straight into the rank that owns the z plane (fused
-// transpose_z_to_y).  Mean removal (poisson.f90:1159-1171, :398-410): the mean of phi over the domain
+// Back substitution.  Mean removal (poisson.f90:1159-1171, :398-410): the mean of phi over the domain
 // equals the average along the last direction of the (kx, ky) = (0, 0) spectral line, so the one thread
 // that owns that line subtracts it there -- O(n) work instead of two sweeps over the real field
-// (hazard H4).
-template <bool SC>
-__global__ void __launch_bounds__(128) k_thomas_bwd(TArgs g, ScArgs q) {
-    const int kx = blockIdx.x * blockDim.x + threadIdx.x;
-    const int o = blockIdx.y;
-    if (kx >= g.npc) return;
-    double2* C = g.C + kx + g.so * o;
-    const double* c1t = g.c1 + kx + g.so * o;
+// (hazard H4).  Blocked layout: the solution goes to g.out ([g][jl][k][8]) instead of in place.
+__global__ void __launch_bounds__(128) k_thomas_bwd(TArgs g) {
+    const TSys sy = thomas_sys(g);
+    if (!sy.valid) return;
+    const double2* C = g.C + sy.off;
+    const double* c1t = g.c1 + sy.off;
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    double2* O = g.blocked ? g.out + g.out_gs * blockIdx.y + (long long)(e >> 3) * g.n * 8 + (e & 7) : g.C + sy.off;
+    const long long osl = g.blocked ? 8 : g.sl;
     const int n = g.n;
-    const bool mean_line = g.mean && kx == 0 && (g.o0 + o) == 0;
-    const bool direct = SC && !mean_line;
+    const bool mean_line = g.mean && sy.kx == 0 && sy.lo_idx == 0;
     double2 x = C[g.sl * (n - 1)];                                  // :1124-1128
     double acc = x.x;
-    if (direct) *sc_dst(q, kx, n - 1, o) = x;
+    O[osl * (n - 1)] = x;
     constexpr int U = 8;
     for (int l0 = n - 2; l0 >= 0; l0 -= U) {
         double2 d[U];
@@ -945,17 +972,15 @@ __global__ void __launch_bounds__(128) k_thomas_bwd(TArgs g, ScArgs q) {
                 x = make_double2(__dsub_rn(d[r].x, __dmul_rn(cc[r], x.x)),
                                  __dsub_rn(d[r].y, __dmul_rn(cc[r], x.y)));
                 acc += x.x;
-                if (direct) *sc_dst(q, kx, l0 - r, o) = x;
-                else C[g.sl * (l0 - r)] = x;
+                O[osl * (l0 - r)] = x;
             }
     }
     if (mean_line) {
         const double mean = acc / (double)n;
         for (int l = 0; l < n; ++l) {
-            double2 v = C[g.sl * l];
+            double2 v = O[osl * l];
             v.x -= mean;
-            if (SC) *sc_dst(q, kx, l, o) = v;
-            else C[g.sl * l] = v;
+            O[osl * l] = v;
         }
     }
 }
@@ -1135,6 +1160,7 @@ __global__ void __launch_bounds__(256) k_a2a_scatter(const double2* __restrict__
 // host side
 // =================================================================================================
 static bool pow2(int n) { return n > 0 && (n & (n - 1)) == 0; }
+static bool blocked_len(int n) { return pow2(n) && n >= 64 && n <= 1024; }   // line lengths of the blocked slab path
 
 template <typename T> static int upload(T** dptr, const std::vector<T>& h) {
     FEN_CUDA(cudaMalloc(dptr, h.size() * sizeof(T)));
@@ -1191,6 +1217,7 @@ void poisson_destroy(fen_ctx* c) {
         if (p->Cz && p->Cz != p->C) cudaFree(p->Cz);
         if (p->C) cudaFree(p->C);
     }
+    if (p->Cr) cudaFree(p->Cr);
     for (void* q : {(void*)p->tw_x, (void*)p->twr_x, (void*)p->tw_y, (void*)p->tw_z, (void*)p->twq_x, (void*)p->twq_y,
                     (void*)p->mwn_x, (void*)p->mwn_y, (void*)p->mwn_z, (void*)p->ta, (void*)p->tb,
                     (void*)p->tc, (void*)p->c1, (void*)p->tw_xa})
@@ -1548,6 +1575,16 @@ static int poisson_build(fen_ctx* c) {
         p->nyl = g.ny / g.nranks;
         p->C = p->peerC[g.rank];
         p->Cz = p->peerCz[g.rank];
+        // ppp / ppn with 64..1024-point transform lines: blocked transposed layouts + bulk stores (slab_bulk.cuh);
+        // FEN_SLAB_BULK=0 keeps the register-store epilogues (A/B switch)
+        static const bool bulk_off = getenv("FEN_SLAB_BULK") && atoi(getenv("FEN_SLAB_BULK")) == 0;
+        const bool is_ppp = !strcmp(var, "ppp"), is_ppn = !strcmp(var, "ppn");
+        p->blocked = !bulk_off && (is_ppp || is_ppn) && blocked_len(g.ny) && (is_ppn || blocked_len(g.nz));
+        if (p->blocked) {
+            const size_t nC = (size_t)p->PC * g.ny * p->nzl;
+            FEN_CUDA(cudaMalloc(&p->Cr, nC * sizeof(double2)));
+            FEN_CUDA(cudaMemsetAsync(p->Cr, 0, nC * sizeof(double2), c->stream));
+        }
     } else {
         const size_t nC = (size_t)p->PC * g.ny * p->nzl;
         FEN_CUDA(cudaMalloc(&p->C, nC * sizeof(double2)));
@@ -1604,9 +1641,11 @@ static int poisson_build(fen_ctx* c) {
             t.sl = (long long)p->PC * p->nyl; t.so = p->PC; t.nouter = p->nyl; t.o0 = g.rank * p->nyl;
             t.lo = p->mwn_y; t.form2d = 0;
             FEN_CUDA(cudaMalloc(&p->c1, (size_t)p->PC * p->nyl * n * sizeof(double)));
+            if (p->blocked) { t.blocked = 1; t.sl = (long long)p->nyl * 8; t.so = (long long)n * p->nyl * 8; }
         }
         t.c1 = p->c1;
         dim3 grid((p->PC + 127) / 128, t.nouter), block(128);
+        if (p->blocked) grid = dim3((p->nyl * 8 + 127) / 128, p->PC / 8);
         FEN_LAUNCH(c, "thomas_c1", k_thomas_c1<<<grid, block, 0, c->stream>>>(t));
         FEN_CUDA(cudaGetLastError());
     }
@@ -1628,7 +1667,7 @@ static int thomas_2d(fen_ctx* c, const TArgs& t) {
         ScArgs none;
         memset(&none, 0, sizeof(none));
         FEN_LAUNCH(c, "thomas_fwd", k_thomas_fwd<<<grid, block, 0, c->stream>>>(t));
-        FEN_LAUNCH(c, "thomas_bwd", k_thomas_bwd<false><<<grid, block, 0, c->stream>>>(t, none));
+        FEN_LAUNCH(c, "thomas_bwd", k_thomas_bwd<<<grid, block, 0, c->stream>>>(t));
         FEN_CUDA(cudaGetLastError());
         return FEN_OK;
     }
@@ -1645,6 +1684,79 @@ static int thomas_2d(fen_ctx* c, const TArgs& t) {
     FEN_LAUNCH(c, "thomas_bwd", k_thomas_lp<true><<<grid, block, sizeof(LpSmem), c->stream>>>(t, cinv, amid));
     FEN_CUDA(cudaGetLastError());
     return FEN_OK;
+}
+
+// ---- blocked slab path (slab_bulk.cuh): ppp / ppn on several ranks, 64..1024-point transform lines ----------------
+template <int Lf> static int launch_bs(fen_ctx* c, int what, const BAddr& in, const BAddr& out, const double2* tw,
+                                       double scale, const SolveArgs* sa, const BulkDst* d, dim3 grid) {
+    const int bytes = Lf * 8 * (int)sizeof(double2);
+    static unsigned long long attr_mask = 0;
+    if (first_time_on_device(attr_mask, c->device)) {
+        FEN_CUDA(cudaFuncSetAttribute(k_fft_lines_bs<Lf, -1>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+        FEN_CUDA(cudaFuncSetAttribute(k_fft_solve_bs<Lf>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+        FEN_CUDA(cudaFuncSetAttribute(k_fft_lines_io<Lf, +1>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    }
+    if (what == 0) FEN_LAUNCH(c, "fft_lines_fwd_a2a", k_fft_lines_bs<Lf, -1><<<grid, Lf, bytes, c->stream>>>(in, tw, scale, *d));
+    if (what == 1) FEN_LAUNCH(c, "fft_lines_inv", k_fft_lines_io<Lf, +1><<<grid, Lf, bytes, c->stream>>>(in, out, tw, scale));
+    if (what == 2) FEN_LAUNCH(c, "fft_solve_a2a", k_fft_solve_bs<Lf><<<grid, Lf, bytes, c->stream>>>(in, *sa, *d));
+    FEN_CUDA(cudaGetLastError());
+    return FEN_OK;
+}
+static int dispatch_bs(fen_ctx* c, int Lf, int what, const BAddr& in, const BAddr& out, const double2* tw, double scale,
+                       const SolveArgs* sa, const BulkDst* d, dim3 grid) {
+    switch (Lf) {
+#define FEN_CASE(l) case l: return launch_bs<l>(c, what, in, out, tw, scale, sa, d, grid);
+        FEN_CASE(64) FEN_CASE(128) FEN_CASE(256) FEN_CASE(512) FEN_CASE(1024)
+#undef FEN_CASE
+    }
+    return set_error(FEN_ERR_STATE, "blocked slab path: line length %d", Lf);
+}
+
+// y forward -> (bulk stores) -> z solve or Thomas -> (bulk stores) -> y inverse into the row array Cr
+static int solve_blocked(fen_ctx* c, Poisson* p, bool ppp) {
+    const fen_grid_desc& g = c->g;
+    const int NG = p->PC / 8, P = g.nranks;
+    const long long ny = g.ny, nz = g.nz, nyl = p->nyl, nzl = p->nzl;
+    BAddr rows_in{p->C, 8, (long long)p->PC * ny, p->PC};                  // C[kx + PC*(j + ny*zl)]: lines over j
+    BAddr none{nullptr, 0, 0, 0};
+    BulkDst df;                                                           // -> Cz[((g*nz + k)*nyl + jl)*8 + kxi]
+    memset(&df, 0, sizeof(df));
+    for (int r = 0; r < P; ++r) df.peer[r] = p->peerCz[r];
+    df.gs = nz * nyl * 8; df.os = nyl * 8; df.o0 = g.rank * (int)nzl; df.blk = (int)nyl; df.P = P; df.rank = g.rank;
+    const double sy = ppp ? 1.0 : 1.0 / f32(g.ny);                        // poisson.f90:1087
+    FEN_TRY(dispatch_bs(c, g.ny, 0, rows_in, none, p->tw_y, sy, nullptr, &df, dim3(NG, (unsigned)nzl)));
+    FEN_TRY(comm_transpose_fwd(c));                                       // transpose_y_to_z (:982 / :1090)
+    BulkDst db;                                                           // -> Cy[((g*ny + j)*nzl + zl)*8 + kxi]
+    memset(&db, 0, sizeof(db));
+    for (int r = 0; r < P; ++r) db.peer[r] = p->peerC[r];
+    db.gs = ny * nzl * 8; db.os = nzl * 8; db.o0 = g.rank * (int)nyl; db.blk = (int)nzl; db.P = P; db.rank = g.rank;
+    if (ppp) {
+        BAddr zin{p->Cz, nz * nyl * 8, 8, nyl * 8};                       // lines over k
+        SolveArgs sa;
+        sa.tw = p->tw_z; sa.lx = p->mwn_x; sa.lo = p->mwn_y; sa.ll = p->mwn_z;
+        sa.norm = f32((long long)g.nx * g.ny * g.nz); sa.ow0 = g.rank * (int)nyl;
+        FEN_TRY(dispatch_bs(c, g.nz, 2, zin, none, nullptr, 1.0, &sa, &db, dim3(NG, (unsigned)nyl)));
+    } else {
+        TArgs t;
+        t.C = p->Cz; t.c1 = p->c1; t.sl = nyl * 8; t.so = nz * nyl * 8; t.n = g.nz; t.npc = p->PC; t.nouter = (int)nyl;
+        t.o0 = g.rank * (int)nyl;
+        t.a = p->ta; t.b = p->tb; t.c = p->tc; t.lx = p->mwn_x; t.lo = p->mwn_y; t.form2d = 0; t.mean = 1;
+        t.blocked = 1; t.out = p->Cr; t.out_gs = nyl * nz * 8;
+        dim3 grid(((unsigned)nyl * 8 + 127) / 128, NG), block(128);
+        FEN_LAUNCH(c, "thomas_fwd", k_thomas_fwd<<<grid, block, 0, c->stream>>>(t));
+        FEN_LAUNCH(c, "thomas_bwd", k_thomas_bwd<<<grid, block, 0, c->stream>>>(t));
+        const int bytes = (int)nzl * 8 * (int)sizeof(double2);
+        static unsigned long long attr_mask = 0;
+        if (first_time_on_device(attr_mask, c->device))
+            FEN_CUDA(cudaFuncSetAttribute(k_bulk_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024));
+        FEN_LAUNCH(c, "a2a_scatter", k_bulk_rows<<<dim3((unsigned)(P * nyl), NG), 256, bytes, c->stream>>>(
+                                         p->Cr, nyl * nz * 8, nz * 8, db, (int)nyl));
+        FEN_CUDA(cudaGetLastError());
+    }
+    FEN_TRY(comm_transpose_bwd(c));                                       // transpose_z_to_y (:1015 / :1138)
+    BAddr yin{p->C, ny * nzl * 8, 8, nzl * 8};                            // Cy lives in C's memory: lines over j
+    BAddr rows_out{p->Cr, 8, (long long)p->PC * ny, p->PC};
+    return dispatch_bs(c, g.ny, 1, yin, rows_out, p->tw_y, 1.0, nullptr, nullptr, dim3(NG, (unsigned)nzl));
 }
 
 int poisson_solve(fen_ctx* c, double* f, bool fuse_rhs, double dt) {
@@ -1718,7 +1830,7 @@ int poisson_solve(fen_ctx* c, double* f, bool fuse_rhs, double dt) {
         } else {
             dim3 tgrid((p->PC + 127) / 128, t.nouter), tblock(128);
             FEN_LAUNCH(c, "thomas_fwd", k_thomas_fwd<<<tgrid, tblock, 0, c->stream>>>(t));
-            FEN_LAUNCH(c, "thomas_bwd", k_thomas_bwd<false><<<tgrid, tblock, 0, c->stream>>>(t, none));
+            FEN_LAUNCH(c, "thomas_bwd", k_thomas_bwd<<<tgrid, tblock, 0, c->stream>>>(t));
             if (multi)
                 FEN_LAUNCH(c, "a2a_scatter", k_a2a_scatter<<<dim3(g.nz, p->nyl), 256, 0, c->stream>>>(
                                                  p->Cz, (long long)p->PC * p->nyl, (long long)p->PC, p->PC, g.nranks,
@@ -1766,6 +1878,10 @@ int poisson_solve(fen_ctx* c, double* f, bool fuse_rhs, double dt) {
             sb.sh = log2i(p->nzl); sb.mask = p->nzl - 1;
             sb.dsl = (long long)p->PC * g.ny; sb.dso = p->PC; sb.o0 = g.rank * p->nyl;
         }
+        if (p->blocked) {
+            FEN_TRY(solve_blocked(c, p, ppp));
+            xa.C = p->Cr;                                      // the y inverse left the rows there
+        } else {
         la.C = p->C; la.sl = p->PC; la.so = (long long)p->PC * g.ny; la.tw = p->tw_y;
         la.scale = ppn ? 1.0 / f32(g.ny) : 1.0;
         FEN_TRY(dispatch_lines(c, g.ny, la, 0, p->PC, p->nzl, multi ? &sf : nullptr));
@@ -1783,16 +1899,11 @@ int poisson_solve(fen_ctx* c, double* f, bool fuse_rhs, double dt) {
             t.a = p->ta; t.b = p->tb; t.c = p->tc; t.lx = p->mwn_x; t.lo = p->mwn_y; t.form2d = 0; t.mean = 1;
             dim3 grid((p->PC + 127) / 128, p->nyl), block(128);
             FEN_LAUNCH(c, "thomas_fwd", k_thomas_fwd<<<grid, block, 0, c->stream>>>(t));
-            // FEN_THOMAS_FUSED_A2A=1: the back substitution stores straight to the peers (kept for A/B measurements)
-            static const bool fused_a2a = getenv("FEN_THOMAS_FUSED_A2A") && atoi(getenv("FEN_THOMAS_FUSED_A2A")) != 0;
-            if (multi && fused_a2a) {
-                FEN_LAUNCH(c, "thomas_bwd_a2a", k_thomas_bwd<true><<<grid, block, 0, c->stream>>>(t, sb));
-            } else {
-                FEN_LAUNCH(c, "thomas_bwd", k_thomas_bwd<false><<<grid, block, 0, c->stream>>>(t, sb));
-                if (multi)
-                    FEN_LAUNCH(c, "a2a_scatter", k_a2a_scatter<<<dim3(g.nz, p->nyl), 256, 0, c->stream>>>(
-                                                     Z, slz, (long long)p->PC, p->PC, g.nranks, g.rank, p->nzl, sb));
-            }
+            // the back substitution stays in local HBM and a staggered row copy ships it (see k_a2a_scatter)
+            FEN_LAUNCH(c, "thomas_bwd", k_thomas_bwd<<<grid, block, 0, c->stream>>>(t));
+            if (multi)
+                FEN_LAUNCH(c, "a2a_scatter", k_a2a_scatter<<<dim3(g.nz, p->nyl), 256, 0, c->stream>>>(
+                                                 Z, slz, (long long)p->PC, p->PC, g.nranks, g.rank, p->nzl, sb));
         }
         FEN_CUDA(cudaGetLastError());
         if (multi) FEN_TRY(comm_transpose_bwd(c));             // transpose_z_to_y (:1015 / :1138)
@@ -1800,6 +1911,7 @@ int poisson_solve(fen_ctx* c, double* f, bool fuse_rhs, double dt) {
         la.C = p->C; la.sl = p->PC; la.so = (long long)p->PC * g.ny; la.tw = p->tw_y; la.scale = 1.0;
         la.lo = nullptr; la.ll = nullptr;
         FEN_TRY(dispatch_lines(c, g.ny, la, 1, p->PC, p->nzl));
+        }
     }
     FEN_CUDA(cudaGetLastError());
     xa.scale = 1.0;

@@ -114,6 +114,46 @@ def test_poisson_matches_single_rank_and_oracle(P, bc, variant, n, L):
     assert np.linalg.norm(got - ref) <= 1e-12 * np.linalg.norm(ref)
 
 
+@pytest.mark.parametrize("bc,variant", [(None, "ppp"), (ZWALLS, "ppn")])
+def test_poisson_1024_point_lines_on_8_ranks(bc, variant):
+    """The line lengths and rank count of the 8-GPU bench (1024-point y and z lines, 128 lines / planes per rank: the
+    blocked slab path of slab_bulk.cuh with 16 KB bulk stores to 8 destinations), x shrunk to 16 cells so that the case
+    fits one device and the oracle: same bits as one rank, and the oracle's answer."""
+    n, L = (16, 1024, 1024), (0.125, 8.0, 8.0)
+    rng = np.random.default_rng(17)
+    rhs = np.zeros((n[0] + 2, n[1] + 2, n[2] + 2), order="F")
+    rhs[1:-1, 1:-1, 1:-1] = rng.standard_normal(n)
+    rhs[1:-1, 1:-1, 1:-1] -= rhs[1:-1, 1:-1, 1:-1].mean()
+    prog = _poisson_program(n, L, bc, rhs)
+    one = run_ranks(1, prog)[0]
+    many = run_ranks(8, prog)
+    assert one[1] == variant and all(m[1] == variant for m in many)
+    got = gather_interior([m[0] for m in many], 1)
+    assert np.array_equal(got, one[0][1:-1, 1:-1, 1:-1])
+    Go = fo.Grid(n[0], n[1], n[2], L[0], L[1], L[2], bc=bc)
+    po = fo.Scalar(Go, 1)
+    if bc is not None:
+        po.bc_type["front"] = po.bc_type["back"] = 2
+    po.f[...] = rhs
+    fo.PoissonSolver(po).solve(po)
+    ref = po.I
+    assert np.linalg.norm(got - ref) <= 1e-12 * np.linalg.norm(ref)
+
+
+def test_slab_bulk_switch_gives_the_same_bits():
+    """FEN_SLAB_BULK=0 (the register-store epilogues of round 1) and the default blocked layouts + bulk stores deliver
+    the same coefficients: the switch is read per process, so the old path runs in a child."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, FEN_SLAB_BULK="0")
+    r = subprocess.run([sys.executable, "-m", "pytest", "-q", "-x", "-m", "gpu", "tests/test_gpu_multirank.py", "-k",
+                        "test_poisson_matches_single_rank_and_oracle or test_ns_steps_tgv3d"], cwd=root, env=env,
+                       capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+
+
 XZWALLS = ["Wall", "Wall", "Periodic", "Periodic", "Wall", "Wall"]
 ALLWALLS = ["Wall"] * 6
 
@@ -201,10 +241,11 @@ def test_ns_steps_tgv3d_rank_count_invariant(P, n):
         assert np.linalg.norm(got - a.I) <= 1e-12 * max(nrm, 1.0)
 
 
-@pytest.mark.parametrize("P", [2, 4])
-def test_ns_steps_channel_ppn_rank_count_invariant(P):
-    n = (32, 16, 16)
-    prog, _ = _ns_program(n, (2.0, 1.0, 1.0), ZWALLS, 0.05, fo.init_channel, 1.0, (1.0, 0.0, 0.0), 0.05, 6)
+@pytest.mark.parametrize("P,n", [(2, (32, 16, 16)), (4, (32, 16, 16)), (4, (64, 64, 32))])
+def test_ns_steps_channel_ppn_rank_count_invariant(P, n):
+    # (64, 64, 32): 64-point y lines -> blocked slab path (bulk-store transposes, Thomas on the blocked layout)
+    L = (2.0, 2.0 * n[1] / n[0], 2.0 * n[2] / n[0])
+    prog, _ = _ns_program(n, L, ZWALLS, 0.05, fo.init_channel, 1.0, (1.0, 0.0, 0.0), 0.05, 6)
     one = run_ranks(1, prog)[0]
     many = run_ranks(P, prog)
     nzl = n[2] // P

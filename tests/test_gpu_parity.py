@@ -515,6 +515,49 @@ def test_full_size_512_properties():
     Gg.destroy()
 
 
+@pytest.mark.parametrize("n", [64, 512])
+def test_one_step_512_matches_c_oracle(n):
+    """BASELINE configs[1] at its FULL size (and at 64^3, the size the CPU logic check runs) against the oracle: one navier_stokes_solver step of a 512^3 periodic box
+    (Taylor-Green u, v, p plus an O(1) w so that every component carries signal; the projection removes its divergence)
+    on the GPU and by the plain-C restatement (oracle/fen_oracle_c.c, ~1 s per step on the box's host cores), north_star's
+    bound: relative L2 <= 1e-12 on u, v, w and p, divergence at machine precision."""
+    from oracle import fen_oracle_c as foc
+    Gg = fb.grid().setup(n, n, n, 2 * PI, 2 * PI, 2 * PI)
+    delta = Gg.delta
+    assert delta == 2 * PI / float(np.float32(n))
+    i = np.arange(0, n + 2, dtype=np.float64)
+    s_f, c_c = np.sin(i * delta), np.cos((i - 0.5) * delta)
+    c2 = np.cos(2.0 * (i - 0.5) * delta)
+    ns = fb.Solver(Gg, 1.0, 0.01).init_solver()
+    ns.CFL = 0.25
+    dt = ns.set_timestep(1.0)
+    co = foc.NavierStokesC(n, n, n, delta, 1.0, 0.01)
+    co.dt_o = dt
+    # fields are built once, plane by plane, straight into the GPU side's host arrays (ghosts analytic: periodic)
+    for kk in range(n + 2):
+        ns.v.x.f[:, :, kk] = (s_f[:, None] * c_c[None, :]) * c_c[kk]
+        ns.v.y.f[:, :, kk] = -(c_c[:, None] * s_f[None, :]) * c_c[kk]
+        ns.v.z.f[:, :, kk] = 0.5 * (c_c[:, None] * c_c[None, :]) * s_f[kk]
+        ns.p.f[:, :, kk] = (1.0 / 16.0) * (c2[:, None] + c2[None, :]) * (c2[kk] + 2.0)
+    for fid, a in ((foc.U, ns.v.x), (foc.V, ns.v.y), (foc.W, ns.v.z), (foc.P, ns.p)):
+        co.set(fid, a.f)
+        a.push()
+    ns.navier_stokes_solver(1, dt)
+    co.navier_stokes_solver(1, dt)
+    md, mc = ns.status()
+    assert abs(md) < 1e-11 and abs(co.maxdiv) < 1e-11
+    errs = {}
+    for name, fid, a in (("u", foc.U, ns.v.x), ("v", foc.V, ns.v.y), ("w", foc.W, ns.v.z), ("p", foc.P, ns.p)):
+        a.pull()
+        ref = co.get(fid)[1:-1, 1:-1, 1:-1]
+        errs[name] = rel_l2(a.I, ref)
+        del ref
+    assert max(errs.values()) <= 1e-12, errs
+    assert abs(mc - co.maxCFL(dt)) <= 1e-12 * mc
+    co.destroy()
+    Gg.destroy()
+
+
 def test_c_driver_runs():
     """examples/tgv_driver.c: the 2-D Taylor-Green case driven from plain C through the C ABI; the error against the
     analytic solution is the second-order one the reference's test plots (postpro.py:48-62)."""
