@@ -320,13 +320,18 @@ def run_reference(args, rank, world):
         return
     n = args.cpu_size
     val, sec, cores, what = cpu_port(n, args.steps, args.warmup)
-    sample = "%d^3 sample of the 512^3 Taylor-Green case, %d steps, %s" % (n, args.steps, what)
+    sample = ("the whole %d^3 Taylor-Green case, %d steps, %s" % (n, args.steps, what)) if n == args.size else \
+        ("%d^3 sample of the %d^3 Taylor-Green case, %d steps, %s" % (n, args.size, args.steps, what))
     line = {
         "impl": "reference", "metric": "NS timestep Mcell-updates/s", "value": val, "unit": "Mcell-updates/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sec,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "3D periodic Taylor-Green vortex 512^3 fp64, ppp Poisson (CPU arm: bounded %d^3 "
-                               "sample)" % n, "grid": [n, n, n], "nu": 0.01, "CFL": 0.25},
+        # the GPU arm's own configuration when n == --size (default: 512^3, the whole workload, not a sample)
+        "config": {"workload": ("3D periodic Taylor-Green vortex %d^3 per GPU fp64, ppp FFT Poisson (BASELINE "
+                                "configs[1])" % n) if n == args.size else
+                               ("3D periodic Taylor-Green vortex %d^3 fp64, ppp Poisson (CPU arm: bounded %d^3 sample)"
+                                % (args.size, n)), "grid": [n, n, n], "nu": 0.01, "CFL": 0.25,
+                   "decomposition": "host threads (OpenMP), one process"},
         "cpu_baseline": {"value": val, "unit": "Mcell-updates/s", "cores": cores, "kind": "port", "sample": sample,
                          "note": "restatement of the reference's CPU path (oracle/), not the gfortran/FFTW/2decomp "
                                  "binary (no Fortran toolchain in this image)"},

@@ -116,7 +116,8 @@ __global__ void __launch_bounds__(256) k_repitch(double* padded, double* flat, L
     }
 }
 
-// FEN_COPY_CHUNKS = K (1..8, default 1): asynchronous pulls leave in K pieces with one event each, and a push of the same
+// FEN_COPY_CHUNKS = K (1..8, default 8 -- measured on a B200 box, profiles/r02a_bench*.json: 127 / 116 / 111 ms per
+// end-to-end 512^3 step at K = 1 / 4 / 8): asynchronous pulls leave in K pieces with one event each, and a push of the same
 // host array follows them piece by piece instead of waiting for the whole download -- in a loop that downloads and
 // re-uploads every field each step (bench.py's e2e region) the upload then trails the download by 1/K of an array
 // instead of a whole one.  Piece q covers elements [chunk_lo(n, K, q), chunk_lo(n, K, q + 1)).
@@ -124,7 +125,7 @@ static int copy_chunks() {
     static int k = 0;
     if (!k) {
         const char* e = getenv("FEN_COPY_CHUNKS");
-        k = e ? atoi(e) : 1;
+        k = e ? atoi(e) : 8;
         k = std::max(1, std::min(8, k));
     }
     return k;

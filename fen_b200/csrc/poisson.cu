@@ -490,70 +490,6 @@ k_fft_x_c2r_w(XArgs a) {
     }
 }
 
-// Persistent, register-prefetching form of k_fft_x_c2r_w (FEN_X_C2R=4; opt-in until measured): a block walks the row
-// groups blockIdx.x, blockIdx.x + gridDim.x, ... and issues the coalesced loads of its NEXT eight rows before it
-// transforms the current ones (same idea as k_fft_solve_p: the r01v capture has this pass at 55 % of HBM with the
-// load latency exposed at the top of every block).  Same arithmetic in the same order as k_fft_x_c2r_w.
-template <int M>
-__global__ void __launch_bounds__(XR* FftPlan<M>::T, (XR * FftPlan<M>::T <= 512) ? 2 : 1) k_fft_x_c2r_p(XArgs a, int ngroups) {
-    extern __shared__ double2 s[];
-    constexpr int T = FftPlan<M>::T;
-    constexpr int RS = M + M / 8 + 1;
-    const int tid = threadIdx.x;
-    const int row = tid / T, t = tid % T;
-    double2 nx_[XR], nn_ = make_double2(0.0, 0.0);
-    auto fetch = [&](int g) {
-        const int row0 = g * XR;
-#pragma unroll
-        for (int rw = 0; rw < XR; ++rw) {
-            const int r = row0 + rw;
-            nx_[rw] = r < a.nrows ? a.C[(size_t)a.PC * r + tid] : make_double2(0.0, 0.0);
-        }
-        nn_ = make_double2(0.0, 0.0);
-        if (tid < XR && row0 + tid < a.nrows) nn_ = a.C[(size_t)a.PC * (row0 + tid) + M];
-    };
-    int g = blockIdx.x;
-    if (g < ngroups) fetch(g);
-    for (; g < ngroups; g += gridDim.x) {
-        {
-            if (tid == 0) {
-#pragma unroll
-                for (int rw = 0; rw < XR; ++rw) nx_[rw].y = 0.0;   // c2r ignores the imaginary part of DC / Nyquist
-            }
-#pragma unroll
-            for (int rw = 0; rw < XR; ++rw) s[spos<true>(tid, RS, rw)] = nx_[rw];
-            if (tid < XR) s[spos<true>(M, RS, tid)] = make_double2(nn_.x, 0.0);
-        }
-        if (g + (int)gridDim.x < ngroups) fetch(g + gridDim.x);    // in flight during the pre-pass and the transform
-        __syncthreads();
-        double2 v[8];
-#pragma unroll
-        for (int m = 0; m < 8; ++m) {
-            const int k = t + m * T;
-            const double2 xk = s[spos<true>(k, RS, row)], xm = s[spos<true>(M - k, RS, row)];
-            const double2 E = make_double2(xk.x + xm.x, xk.y - xm.y);
-            const double2 D = make_double2(xk.x - xm.x, xk.y + xm.y);
-            const double2 O = cmul(cconj(__ldg(&a.twr[k])), D);
-            v[m] = make_double2(E.x - O.y, E.y + O.x);
-        }
-        __syncthreads();                          // the first stage overwrites the staged rows
-        fft_regs<M, +1, true, false, true>(v, s, RS, row, t, a.tw);
-        const int r = g * XR + row;
-        if (r < a.nrows) {
-            const int j = r % a.ny, k3 = r / a.ny;
-            double* frow = a.f + a.L.idx(1, j + 1, k3 + 1);
-#pragma unroll
-            for (int m = 0; m < 8; ++m) {
-                const int idx = t + m * T;
-                reinterpret_cast<double2*>(frow)[idx] = v[m];
-                if (idx == 0) frow[2 * M] = v[m].x;
-                if (idx == M - 1) frow[-1] = v[m].y;
-            }
-        }
-        __syncthreads();                          // the next group's staged rows overwrite the exchange buffer
-    }
-}
-
 // c2r with a coalesced staging load: rows of C -> shared memory, the pair pre-pass reads (k, M-k) from there
 // into registers, the transform runs register-to-register and the real row is stored straight from registers.
 template <int M>
@@ -669,56 +605,6 @@ __global__ void __launch_bounds__(NL* FftPlan<Lf>::T, (NL * FftPlan<Lf>::T <= 10
         const int idx = t + m * T;
         if (SC) *sc_dst(q, kx, idx, blockIdx.y) = v[m];
         else base[a.sl * idx] = v[m];
-    }
-}
-
-// Persistent, register-prefetching form of k_fft_solve_r (FEN_FFT_SOLVE_PERSIST=1; opt-in until measured): a block walks
-// the tiles blockIdx.x, blockIdx.x + gridDim.x, ... and issues the eight 16-byte loads of its NEXT tile before it
-// transforms the current one, so the HBM latency of a tile is hidden behind the two transforms of the previous tile
-// instead of being exposed at the top of every block (the r01v capture shows the fp64 pipe and DRAM each ~36 % busy:
-// the phases of the two resident blocks do not overlap well).  Same arithmetic in the same order as k_fft_solve_r.
-template <int Lf, int NL>
-__global__ void __launch_bounds__(NL* FftPlan<Lf>::T, 1) k_fft_solve_p(LArgs a, int nchunks, int ntiles) {
-    extern __shared__ double2 s[];
-    constexpr int T = FftPlan<Lf>::T;
-    const int tid = threadIdx.x;
-    const int line = tid % NL, t = tid / NL;
-    const double inorm = 1.0 / a.norm;
-    double2 nxt[8];
-    int tile = blockIdx.x;
-    if (tile < ntiles) {
-        const double2* b = a.C + ((tile % nchunks + a.cx0) * NL + line) + a.so * (tile / nchunks);
-#pragma unroll
-        for (int m = 0; m < 8; ++m) nxt[m] = b[a.sl * (t + m * T)];
-    }
-    for (; tile < ntiles; tile += gridDim.x) {
-        double2 v[8];
-#pragma unroll
-        for (int m = 0; m < 8; ++m) v[m] = nxt[m];
-        const int ahead = tile + gridDim.x;
-        if (ahead < ntiles) {
-            const double2* b = a.C + ((ahead % nchunks + a.cx0) * NL + line) + a.so * (ahead / nchunks);
-#pragma unroll
-            for (int m = 0; m < 8; ++m) nxt[m] = b[a.sl * (t + m * T)];
-        }
-        const int bx = tile % nchunks, by = tile / nchunks;
-        const int kx = (bx + a.cx0) * NL + line;
-        fft_regs<Lf, -1, true>(v, s, NL, line, t, a.tw);
-        {
-            double lxo = __ldg(&a.lx[kx]);
-            if (a.lo) lxo = lxo + __ldg(&a.lo[a.o0 + by]);
-#pragma unroll
-            for (int m = 0; m < 8; ++m) {
-                const double lam = lxo + __ldg(&a.ll[t + m * T]);
-                const double rl = lam == 0.0 ? 0.0 : inorm / lam;
-                v[m].x *= rl;
-                v[m].y *= rl;
-            }
-        }
-        fft_regs<Lf, +1, true>(v, s, NL, line, t, a.tw);
-        double2* base = a.C + kx + a.so * by;
-#pragma unroll
-        for (int m = 0; m < 8; ++m) base[a.sl * (t + m * T)] = v[m];
     }
 }
 
@@ -1307,20 +1193,6 @@ template <int M> static int launch_x(fen_ctx* c, const XArgs& a, bool fwd, const
         if (!fwd && vc2r == 0) { FEN_LAUNCH(c, "fft_x_c2r", k_fft_x_c2r_r<M><<<grid, block, bytes, c->stream>>>(a)); done = true; }
         if (!fwd && vc2r == 2) { FEN_LAUNCH(c, "fft_x_c2r", k_fft_x_c2r_s<M><<<grid, block, bytes, c->stream>>>(a)); done = true; }
         if (!fwd && vc2r == 3) { FEN_LAUNCH(c, "fft_x_c2r", k_fft_x_c2r_w<M><<<grid, block, bytes, c->stream>>>(a)); done = true; }
-        if (!fwd && vc2r == 4 && M > 256) { FEN_LAUNCH(c, "fft_x_c2r", k_fft_x_c2r_s<M><<<grid, block, bytes, c->stream>>>(a)); done = true; }
-        if (!fwd && vc2r == 4 && M <= 256) {      // persistent prefetching form of variant 3 (tuning switch until measured)
-            static unsigned long long pmask = 0;
-            static int per_sm = 0, sms = 0;
-            if (first_time_on_device(pmask, c->device)) {
-                FEN_CUDA(cudaFuncSetAttribute(k_fft_x_c2r_p<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-                FEN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_fft_x_c2r_p<M>, XR * T, bytes));
-                FEN_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device));
-                if (per_sm < 1) per_sm = 1;
-            }
-            const int ngroups = (a.nrows + XR - 1) / XR;
-            FEN_LAUNCH(c, "fft_x_c2r", k_fft_x_c2r_p<M><<<std::min(ngroups, per_sm * sms), block, bytes, c->stream>>>(a, ngroups));
-            done = true;
-        }
         if (fwd && vr2c == 3) {
             if (dv) FEN_LAUNCH(c, "fft_x_r2c_div", k_fft_x_r2c_w<M, true><<<grid, block, bytes, c->stream>>>(a, *dv));
             else FEN_LAUNCH(c, "fft_x_r2c", k_fft_x_r2c_w<M, false><<<grid, block, bytes, c->stream>>>(a, none));
@@ -1381,23 +1253,6 @@ template <int Lf, int NL> static int launch_lines(fen_ctx* c, const LArgs& a, in
         if (mode == 0 && !sc) FEN_LAUNCH(c, "fft_lines_fwd", k_fft_lines_r<Lf, -1, NL, false><<<grid, block, bytes, c->stream>>>(a, none));
         if (mode == 0 && sc) FEN_LAUNCH(c, "fft_lines_fwd_a2a", k_fft_lines_r<Lf, -1, NL, true><<<grid, block, bytes, c->stream>>>(a, *sc));
         if (mode == 1) FEN_LAUNCH(c, "fft_lines_inv", k_fft_lines_r<Lf, +1, NL, false><<<grid, block, bytes, c->stream>>>(a, none));
-        // FEN_FFT_SOLVE_PERSIST=1: the persistent, prefetching form (one rank; tuning switch until measured)
-        static const bool persist = getenv("FEN_FFT_SOLVE_PERSIST") && atoi(getenv("FEN_FFT_SOLVE_PERSIST")) != 0;
-        if (mode == 2 && !sc && persist) {
-            static unsigned long long persist_mask = 0;
-            static int per_sm = 0, sms = 0;          // the same on every device of one box
-            if (first_time_on_device(persist_mask, c->device)) {
-                FEN_CUDA(cudaFuncSetAttribute(k_fft_solve_p<Lf, NL>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-                FEN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_fft_solve_p<Lf, NL>, NL * T, bytes));
-                FEN_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device));
-                if (per_sm < 1) per_sm = 1;
-            }
-            const int ntiles = nchunks * nouter;
-            const int nblocks = std::min(ntiles, per_sm * sms);
-            FEN_LAUNCH(c, "fft_solve", k_fft_solve_p<Lf, NL><<<nblocks, block, bytes, c->stream>>>(a, nchunks, ntiles));
-            FEN_CUDA(cudaGetLastError());
-            return FEN_OK;
-        }
         if (mode == 2 && !sc) FEN_LAUNCH(c, "fft_solve", k_fft_solve_r<Lf, NL, false><<<grid, block, bytes, c->stream>>>(a, none));
         if (mode == 2 && sc) FEN_LAUNCH(c, "fft_solve_a2a", k_fft_solve_r<Lf, NL, true><<<grid, block, bytes, c->stream>>>(a, *sc));
     } else {
@@ -1422,23 +1277,17 @@ static int dispatch_lines(fen_ctx* c, int Lf, const LArgs& a, int mode, int PC, 
         return launch_any<AnyLines>(c, mode == 0 ? "fft_lines_fwd_any" : (mode == 1 ? "fft_lines_inv_any" : "fft_solve_any"),
                                     q, dim3(PC / q.NL, nouter), Lf, q.NL);
     }
-    // tuning switch: 4 lines (64 B) per block instead of 8 -- more, smaller blocks per SM
-    static const bool nl4 = getenv("FEN_FFT_NL4") != nullptr;
-    static const bool nl4_1024 = getenv("FEN_FFT_NL4_1024") != nullptr;
-    // 1024-point lines: 8 columns per block need 1024 threads and the whole register file (one block per SM);
+    // 1024-point lines: 8 columns per block would need 1024 threads and the whole register file (one block per SM);
     // 4 columns give two 512-thread blocks per SM -- measured 0.59 vs 0.62 ms on a 1024x1024x128 slab
-    static const bool nl8_1024 = getenv("FEN_FFT_NL8_1024") != nullptr;
-    (void)nl4_1024;
-    if ((nl4 && Lf == 512) || (Lf == 1024 && !nl8_1024)) {
+    if (Lf == 1024) {
         LArgs b = a;
         b.cx0 = a.cx0 * 2;       // cx0 counts blocks of NL columns
-        if (Lf == 512) return launch_lines<512, 4>(c, b, mode, PC / 4, nouter, sc);
         return launch_lines<1024, 4>(c, b, mode, PC / 4, nouter, sc);
     }
     switch (Lf) {
 #define FEN_CASE(l) case l: return launch_lines<l, 8>(c, a, mode, PC / 8, nouter, sc);
         FEN_CASE(1) FEN_CASE(2) FEN_CASE(4) FEN_CASE(8) FEN_CASE(16) FEN_CASE(32) FEN_CASE(64)
-        FEN_CASE(128) FEN_CASE(256) FEN_CASE(512) FEN_CASE(1024)
+        FEN_CASE(128) FEN_CASE(256) FEN_CASE(512)
 #undef FEN_CASE
         case 2048: return launch_lines<2048, 4>(c, a, mode, PC / 4, nouter, sc);
     }

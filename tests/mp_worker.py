@@ -31,6 +31,9 @@ def main():
     two_pi = 2.0 * fo.PI
     if case == "ppp":
         n, L, bc, nu, g, U, cfl, init = (128, 64, 64), (two_pi, two_pi / 2, two_pi / 2), None, 0.01, None, 1.0, 0.25, fo.init_tgv3d
+    elif case == "ppp1024":
+        # the y / z line lengths of the 8-GPU bench (1024 points, 128 per rank at world = 8), x shrunk to 16 cells
+        n, L, bc, nu, g, U, cfl, init = (16, 1024, 1024), (two_pi / 64, two_pi, two_pi), None, 0.01, None, 1.0, 0.25, fo.init_tgv3d
     else:
         n, L, bc, nu, g, U, cfl, init = (32, 32, 16), (2.0, 2.0, 1.0), ["Periodic"] * 4 + ["Wall", "Wall"], 0.05, (1.0, 0.0, 0.0), 1.0, 0.05, fo.init_channel
     Go = fo.Grid(n[0], n[1], n[2], L[0], L[1], L[2], bc=bc)
@@ -39,7 +42,7 @@ def main():
         nso.g = list(g)
     init(nso)
     state = [a.f.copy() for a in (nso.v.x, nso.v.y, nso.v.z, nso.p)]
-    steps = 5
+    steps = 2 if case == "ppp1024" else 5
 
     def advance(P, r, connect):
         G = fb.grid().setup(n[0], n[1], n[2], L[0], L[1], L[2], pcol=P, rank=r, bc=bc, device=dev)

@@ -117,32 +117,17 @@ def test_rising_bubble_rises_and_keeps_its_volume():
 
 
 def test_chunked_async_pull_and_push_ordering():
-    """FEN_COPY_CHUNKS=4 (context.cu: downloads leave in pieces and a push of the same host array follows them piece by
-    piece): the ordering test of tests/test_gpu_io.py, in a child process because the switch is read once per process.
-    Opt-in until it has been measured: the default (1) is the path every other test runs."""
+    """FEN_COPY_CHUNKS=1 (context.cu: the download of a field leaves as ONE copy and a later push of the same host array
+    waits for all of it; the default, 8 pieces, is what every other test runs): the ordering test of tests/test_gpu_io.py
+    in a child process, because the switch is read once per process."""
     import os
     import subprocess
     import sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    env = dict(os.environ, FEN_COPY_CHUNKS="4")
+    env = dict(os.environ, FEN_COPY_CHUNKS="1")
     r = subprocess.run([sys.executable, "-m", "pytest", "-q", "-x", "-m", "gpu",
                         "tests/test_gpu_io.py::test_pull_async_and_push_ordering"], cwd=root, env=env,
                        capture_output=True, text=True, timeout=600)
-    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
-
-
-def test_persistent_fft_solve_matches_oracle():
-    """FEN_FFT_SOLVE_PERSIST=1 and FEN_X_C2R=4 (poisson.cu: k_fft_solve_p, k_fft_x_c2r_p, the persistent
-    register-prefetching forms of the fused z-solve and of the x c2r pass): the one-step Taylor-Green parity tests whose last direction has >= 64 points, and the 2-D config-1 run,
-    in a child process because the switch is read once per process.  Opt-in until it has been measured."""
-    import os
-    import subprocess
-    import sys
-    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    env = dict(os.environ, FEN_FFT_SOLVE_PERSIST="1", FEN_X_C2R="4")      # and the persistent c2r (k_fft_x_c2r_p)
-    r = subprocess.run([sys.executable, "-m", "pytest", "-q", "-x", "-m", "gpu", "tests/test_gpu_parity.py", "-k",
-                        "one_step_tgv3d or tgv2d_matches_oracle_config1 or projection_makes"], cwd=root, env=env,
-                       capture_output=True, text=True, timeout=800)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
 
 
