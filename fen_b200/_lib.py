@@ -9,7 +9,8 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libfen_gpu.so")
+# FEN_GPU_LIB: load an A/B build variant of the library (fen_b200/build.py) instead of the default one
+LIB_PATH = os.environ.get("FEN_GPU_LIB") or os.path.join(HERE, "libfen_gpu.so")
 
 
 class FenError(RuntimeError):

@@ -8,12 +8,16 @@ from concurrent.futures import ThreadPoolExecutor
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-OBJ = os.path.join(HERE, "csrc", "_obj")
-LIB = os.path.join(HERE, "libfen_gpu.so")
+# FEN_BUILD_DEFS / FEN_BUILD_TAG: an A/B variant of the library (e.g. FEN_BUILD_DEFS=-DFEN_STRIDED_TWP=1 FEN_BUILD_TAG=twp
+# builds fen_b200/libfen_gpu_twp.so, which FEN_GPU_LIB=... makes fen_b200/_lib.py load instead of the default)
+TAG = os.environ.get("FEN_BUILD_TAG", "")
+EXTRA = os.environ.get("FEN_BUILD_DEFS", "").split()
+OBJ = os.path.join(HERE, "csrc", "_obj" + ("_" + TAG if TAG else ""))
+LIB = os.path.join(HERE, "libfen_gpu%s.so" % ("_" + TAG if TAG else ""))
 SOURCES = ["context.cu", "ghost.cu", "stencil.cu", "poisson.cu", "comm.cu", "tma.cu", "io.cu", "multiphase.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-std=c++17", "-O3", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
-         "-Xcompiler", "-fPIC", "-Xptxas", "-v"]
+         "-Xcompiler", "-fPIC", "-Xptxas", "-v"] + EXTRA
 
 
 def _deps():

@@ -38,7 +38,9 @@ static unsigned long long spin_limit_ns() {
     return v;
 }
 constexpr int kSigPerChannel = FEN_MAX_RANKS;
-enum Channel { CH_HALO = 0, CH_A2A_FWD = 1, CH_A2A_BWD = 2, CH_RED = 3, CH_COUNT = 4 };
+// CH_A2A_CHUNK + q: chunk q of a chunked z -> y transpose (poisson.cu: solve_blocked signals each chunk of granules
+// as soon as its stores are out, so that the y inverse of that chunk overlaps the next chunk's transfer)
+enum Channel { CH_HALO = 0, CH_A2A_FWD = 1, CH_A2A_BWD = 2, CH_RED = 3, CH_A2A_CHUNK = 4, CH_COUNT = 4 + FEN_MAX_CHUNKS };
 constexpr int kRedWidth = 8;     // doubles per allreduce
 
 struct HandleBlob {              // what fen_gpu_comm_export writes (fen_gpu_comm_handle_bytes() bytes)
@@ -62,7 +64,7 @@ struct Comm {
     size_t off_sig = 0, off_err = 0, off_red = 0, off_mail = 0, off_C = 0, off_Cz = 0;
     size_t plane = 0;            // doubles per z plane of a field (Layout::sz)
     size_t nC = 0, nCz = 0;      // complex elements
-    unsigned long long epoch[CH_COUNT] = {0, 0, 0, 0};
+    unsigned long long epoch[CH_COUNT] = {};
     int* h_err = nullptr;        // pinned mirror of the error word
 };
 
@@ -296,11 +298,13 @@ int comm_allreduce(fen_ctx* c, double* d_vals, int n, int op) {
 }
 
 // the data of a transpose is pushed by the epilogue of the producing kernel (poisson.cu); this raises
-// "my part is complete" on every peer and waits for theirs.
-static int a2a_sync(fen_ctx* c, int ch) {
+// "my part is complete" on every peer and waits for theirs.  what: 1 = raise only, 2 = wait only (for the epoch the
+// last raise of this channel used), 3 = both in one launch.
+static int a2a_sync(fen_ctx* c, int ch, int what, cudaStream_t st, const char* name) {
     Comm* m;
     FEN_TRY(need_comm(c, &m));
-    const unsigned long long e = ++m->epoch[ch];
+    if (what & 1) ++m->epoch[ch];
+    const unsigned long long e = m->epoch[ch];
     SigArgs s;
     memset(&s, 0, sizeof(s));
     s.epoch = e;
@@ -308,15 +312,23 @@ static int a2a_sync(fen_ctx* c, int ch) {
     s.err = err_ptr(m);
     for (int r = 0; r < m->P; ++r) {
         if (r == m->rank) continue;
-        s.send_flag[s.nsend++] = sig_ptr(m, r, ch, m->rank);
-        s.wait_flag[s.nwait++] = sig_ptr(m, m->rank, ch, r);
+        if (what & 1) s.send_flag[s.nsend++] = sig_ptr(m, r, ch, m->rank);
+        if (what & 2) s.wait_flag[s.nwait++] = sig_ptr(m, m->rank, ch, r);
     }
-    FEN_LAUNCH(c, ch == CH_A2A_FWD ? "a2a_fwd_sync" : "a2a_bwd_sync", k_sigwait<<<1, 32, 0, c->stream>>>(s));
+    FEN_LAUNCH(c, name, k_sigwait<<<1, 32, 0, st>>>(s));
     FEN_CUDA(cudaGetLastError());
     return FEN_OK;
 }
-int comm_transpose_fwd(fen_ctx* c) { return a2a_sync(c, CH_A2A_FWD); }
-int comm_transpose_bwd(fen_ctx* c) { return a2a_sync(c, CH_A2A_BWD); }
+int comm_transpose_fwd(fen_ctx* c) { return a2a_sync(c, CH_A2A_FWD, 3, c->stream, "a2a_fwd_sync"); }
+int comm_transpose_bwd(fen_ctx* c) { return a2a_sync(c, CH_A2A_BWD, 3, c->stream, "a2a_bwd_sync"); }
+int comm_chunk_signal(fen_ctx* c, int q, cudaStream_t st) {
+    if (q < 0 || q >= FEN_MAX_CHUNKS) return set_error(FEN_ERR_ARG, "transpose chunk %d", q);
+    return a2a_sync(c, CH_A2A_CHUNK + q, 1, st, "a2a_bwd_sync");
+}
+int comm_chunk_wait(fen_ctx* c, int q, cudaStream_t st) {
+    if (q < 0 || q >= FEN_MAX_CHUNKS) return set_error(FEN_ERR_ARG, "transpose chunk %d", q);
+    return a2a_sync(c, CH_A2A_CHUNK + q, 2, st, "a2a_bwd_sync");
+}
 
 int comm_spectral(fen_ctx* c, double2** peerC, double2** peerCz) {
     Comm* m;

@@ -4,6 +4,8 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <atomic>
+#include <mutex>
 #include <tuple>
 #include <map>
 #include <string>
@@ -12,6 +14,7 @@
 #include "../../include/fen_gpu.h"
 
 #define FEN_MAX_RANKS 16
+#define FEN_MAX_CHUNKS 8      // pieces of a chunked slab transpose (comm.cu: one flag channel each)
 
 namespace fen {
 
@@ -74,14 +77,43 @@ struct StepGraph {
 };
 
 // Kernel attributes (the dynamic shared-memory limit above 48 KB) belong to the device a kernel is loaded on, not to the
-// process: a caller may drive several contexts -- several GPUs -- from one process, so the one-time set-up of a launcher
-// is tracked per device.  Usage: static unsigned long long mask = 0; if (first_time_on_device(mask, c->device)) {...}
-inline bool first_time_on_device(unsigned long long& mask, int device) {
-    const unsigned long long bit = 1ull << (device & 63);
-    if (mask & bit) return false;
-    mask |= bit;
-    return true;
-}
+// process: a caller may drive several contexts -- several GPUs, or several ranks on one GPU -- from one process, each
+// from its own thread.  The one-time set-up of a launcher is therefore tracked per device AND serialised: the thread
+// that finds the bit clear holds the lock until it leaves the launcher's scope, so no other thread can launch the kernel
+// before its attributes are set (a bare check-and-set let a second rank launch with 128 KB of dynamic shared memory a
+// moment before the first had raised the limit: "invalid argument", seen with 8 ranks as threads).
+// Usage:  FEN_ONCE_PER_DEVICE(c) { FEN_CUDA(cudaFuncSetAttribute(...)); }
+struct OnceState {
+    std::mutex m;
+    std::atomic<unsigned long long> done{0};
+};
+class OnceLock {
+   public:
+    OnceLock(OnceState& st, int device) : st_(st), bit_(1ull << (device & 63)) {
+        if (st_.done.load(std::memory_order_acquire) & bit_) return;
+        st_.m.lock();
+        if (st_.done.load(std::memory_order_acquire) & bit_) { st_.m.unlock(); return; }
+        first_ = true;
+    }
+    ~OnceLock() {
+        if (first_) {
+            st_.done.fetch_or(bit_, std::memory_order_release);
+            st_.m.unlock();
+        }
+    }
+    bool first() const { return first_; }
+    OnceLock(const OnceLock&) = delete;
+    OnceLock& operator=(const OnceLock&) = delete;
+
+   private:
+    OnceState& st_;
+    unsigned long long bit_;
+    bool first_ = false;
+};
+#define FEN_ONCE_PER_DEVICE(ctx)                            \
+    static fen::OnceState once_state__;                     \
+    fen::OnceLock once_lock__(once_state__, (ctx)->device); \
+    if (once_lock__.first())
 
 struct Poisson;   // poisson.cu
 struct Comm;      // comm.cu
@@ -187,6 +219,8 @@ int comm_allreduce(fen_ctx* c, double* d_vals, int n, int op /*0 max, 1 sum*/);
 void comm_destroy(fen_ctx* c);
 int comm_transpose_fwd(fen_ctx* c);   // completes the y-slab -> z-pencil transpose pushed by the y FFT
 int comm_transpose_bwd(fen_ctx* c);   // completes the z-pencil -> y-slab transpose pushed by the z stage
+int comm_chunk_signal(fen_ctx* c, int q, cudaStream_t st);   // chunk q of a chunked z -> y transpose: my stores are out
+int comm_chunk_wait(fen_ctx* c, int q, cudaStream_t st);     // ... and everybody else's have arrived
 int comm_spectral(fen_ctx* c, double2** peerC, double2** peerCz);   // mapped spectral arrays of all ranks
 int comm_check(fen_ctx* c);           // FEN_ERR_COMM if a peer wait timed out (call after a stream sync)
 int spectral_pitch(int nx);           // complex row pitch of the half-spectrum arrays

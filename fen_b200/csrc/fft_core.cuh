@@ -20,7 +20,15 @@
 #define FEN_HD __host__ __device__ __forceinline__
 #endif
 
+// FEN_STRIDED_TWP=1 (build-time A/B switch): the strided y / z passes also form w^3, w^5, w^6, w^7 of a radix-8 stage
+// as products of three table entries instead of loading seven
+#ifndef FEN_STRIDED_TWP
+#define FEN_STRIDED_TWP 0
+#endif
+
 namespace fen {
+
+constexpr bool kStridedTwp = FEN_STRIDED_TWP != 0;
 
 FEN_HD double2 cadd(double2 a, double2 b) { return make_double2(a.x + b.x, a.y + b.y); }
 FEN_HD double2 csub(double2 a, double2 b) { return make_double2(a.x - b.x, a.y - b.y); }
@@ -217,7 +225,20 @@ __device__ __forceinline__ void fft_lines(double2* s, int IS, int line, int t, b
 // in registers, so a 512-point transform costs 4 shared-memory passes and 3 block barriers instead of 8 and 8.
 // On return no thread still reads shared memory written before the call's last barrier, so the caller may start
 // the next transform (e.g. the inverse of the fused solve) without another barrier.
-template <int L, int DIR, bool OUT_REG, bool TWP = false, bool PR = false>
+// RSYNC: the barriers of the exchange only involve the T threads of one line -- valid when each line's shared-memory
+// region is private to its T threads, which are whole warps or parts of one warp (thread = line * T + t, padded-row
+// layout): __syncwarp when a line fits a warp, a named barrier (id 1 + line, T threads) otherwise.  The warps of a block
+// then run through the transform independently instead of meeting at ~6 block-wide barriers.
+template <int L, bool RSYNC> __device__ __forceinline__ void fft_sync(int line) {
+    if constexpr (!RSYNC) {
+        __syncthreads();
+    } else if constexpr (FftPlan<L>::T <= 32) {
+        __syncwarp();
+    } else {
+        asm volatile("bar.sync %0, %1;" ::"r"(line + 1), "n"(FftPlan<L>::T) : "memory");
+    }
+}
+template <int L, int DIR, bool OUT_REG, bool TWP = false, bool PR = false, bool RSYNC = false>
 __device__ __forceinline__ void fft_regs(double2 (&v)[8], double2* s, int IS, int line, int t, const double2* tw) {
     static_assert(L >= 64, "fft_regs needs T = L / 8 >= 8 threads per line");
     constexpr int N8 = FftPlan<L>::N8, REM = FftPlan<L>::REM;
@@ -227,23 +248,23 @@ __device__ __forceinline__ void fft_regs(double2 (&v)[8], double2* s, int IS, in
     for (int st = 0; st < N8; ++st) {
         if (st > 0) {
             stage_load<L, 8, DIR, PR>(v, s, IS, line, t);
-            __syncthreads();
+            fft_sync<L, RSYNC>(line);
         }
         stage_compute<L, 8, DIR, TWP>(v, t, Ns, tw);
         if (OUT_REG && st == NST - 1) return;
         stage_write<L, 8, PR>(v, s, IS, line, t, Ns);
-        __syncthreads();
+        fft_sync<L, RSYNC>(line);
         Ns *= 8;
     }
     if constexpr (REM > 1) {
         stage_load<L, REM, DIR, PR>(v, s, IS, line, t);
-        __syncthreads();
+        fft_sync<L, RSYNC>(line);
         stage_compute<L, REM, DIR>(v, t, Ns, tw);
         if (OUT_REG) {
             last_permute<REM>(v);
         } else {
             stage_write<L, REM, PR>(v, s, IS, line, t, Ns);
-            __syncthreads();
+            fft_sync<L, RSYNC>(line);
         }
     }
 }

@@ -51,6 +51,13 @@ struct Poisson {
     bool blocked = false;
     double2* Cr = nullptr;          // blocked path: row-layout output of the y inverse (input of the x c2r pass) and,
                                     // for ppn, the [g][jl][k][8] staging of the back substitution; local memory
+    // chunked overlap of the blocked path (solve_blocked): the link-bound transposing kernels run on `aux` (forward)
+    // / the main stream (backward) in nchunk pieces while the HBM-bound x pass / y inverse of the neighbouring piece
+    // runs on the other stream
+    cudaStream_t aux = nullptr;
+    cudaEvent_t ev_piece[FEN_MAX_CHUNKS] = {};
+    cudaEvent_t ev_join = nullptr;
+    int nchunk = 1;
     double2* peerC[FEN_MAX_RANKS] = {};
     double2* peerCz[FEN_MAX_RANKS] = {};
 };
@@ -81,6 +88,7 @@ struct XArgs {
     const double2* tw;    // exp(-2 pi i m / M), m < M
     const double2* twr;   // exp(-2 pi i k / N), k <= M
     double scale;         // applied to the r2c output (1/float(nx) in ppn/pn, else 1)
+    int r0;               // first row of this launch (rows r0 .. nrows-1; 0 unless a caller launches the rows in pieces)
 };
 
 // Poisson right-hand side computed on the fly by the x pass (navier_stokes.f90:111-121 fused into
@@ -114,7 +122,7 @@ __global__ void __launch_bounds__(XR* FftPlan<M>::T) k_fft_x_r2c(XArgs a, DivArg
     constexpr int T = FftPlan<M>::T;
     constexpr int NT = XR * T;
     const int tid = threadIdx.x;
-    const int row0 = blockIdx.x * XR;
+    const int row0 = a.r0 + blockIdx.x * XR;
     // load: thread e -> (row, idx), consecutive threads read consecutive 16-byte pairs of a row
     for (int e = tid; e < XR * M; e += NT) {
         const int row = e / M, idx = e - row * M;
@@ -172,7 +180,7 @@ __global__ void __launch_bounds__(XR* FftPlan<M>::T) k_fft_x_c2r(XArgs a) {
     constexpr int T = FftPlan<M>::T;
     constexpr int NT = XR * T;
     const int tid = threadIdx.x;
-    const int row0 = blockIdx.x * XR;
+    const int row0 = a.r0 + blockIdx.x * XR;
     for (int e = tid; e < XR * (M + 1); e += NT) {
         const int row = e / (M + 1), k = e - row * (M + 1);
         const int r = row0 + row;
@@ -303,7 +311,7 @@ __global__ void __launch_bounds__(XR* FftPlan<M>::T, (XR * FftPlan<M>::T <= 1024
     constexpr int NT = XR * T;
     const int tid = threadIdx.x;
     const int row = tid % XR, t = tid / XR;
-    const int row0 = blockIdx.x * XR;
+    const int row0 = a.r0 + blockIdx.x * XR;
     double2 v[8];
     {
         const int r = row0 + row;
@@ -354,7 +362,7 @@ __global__ void __launch_bounds__(XR* FftPlan<M>::T, (XR * FftPlan<M>::T <= 1024
     constexpr int T = FftPlan<M>::T;
     const int tid = threadIdx.x;
     const int row = tid % XR, t = tid / XR;
-    const int r = blockIdx.x * XR + row;
+    const int r = a.r0 + blockIdx.x * XR + row;
     const bool valid = r < a.nrows;
     const double2* X = a.C + (size_t)a.PC * (valid ? r : 0);
     double2 v[8];
@@ -395,7 +403,7 @@ k_fft_x_r2c_w(XArgs a, DivArgs dv) {
     constexpr int RS = M + M / 8 + 1;
     const int tid = threadIdx.x;
     const int row = tid / T, t = tid % T;
-    const int row0 = blockIdx.x * XR;
+    const int row0 = a.r0 + blockIdx.x * XR;
     double2 v[8];
     {
         const int r = row0 + row;
@@ -437,6 +445,58 @@ k_fft_x_r2c_w(XArgs a, DivArgs dv) {
     if (tid < XR) pair_out(tid, M / 2);
 }
 
+// Row-private r2c: as k_fft_x_r2c_w, but the transform runs with row-level barriers (RSYNC) and twiddle products
+// (TWP), and the pair post-pass is done by the row's own threads -- thread t takes the pairs k = t + m T, m < 4
+// (k < M/2), thread 0 also the self-paired k = M/2 -- so that no block-wide barrier remains.  With one warp per row
+// the stage twiddles of a warp are 32 different table entries per load instruction (the x passes are bound by the
+// L1 / shared-memory data path: 91 % in the r01v capture of the c2r pass), hence the products.
+template <int M, bool DIV, bool TWP>
+__global__ void __launch_bounds__(XR* FftPlan<M>::T, (XR * FftPlan<M>::T <= 1024) ? 1024 / (XR * FftPlan<M>::T) : 1)
+k_fft_x_r2c_v(XArgs a, DivArgs dv) {
+    extern __shared__ double2 s[];
+    constexpr int T = FftPlan<M>::T;
+    constexpr int RS = M + M / 8 + 1;
+    const int tid = threadIdx.x;
+    const int row = tid / T, t = tid % T;
+    const int r = a.r0 + blockIdx.x * XR + row;
+    const bool valid = r < a.nrows;
+    double2 v[8];
+    {
+        const int j = valid ? r % a.ny : 0, k = valid ? r / a.ny : 0;
+        const long long c0 = a.L.idx(1, j + 1, k + 1);
+#pragma unroll
+        for (int m = 0; m < 8; ++m) {
+            if (DIV) v[m] = div_pair(dv, a.L, c0 + 2 * (t + m * T));
+            else v[m] = reinterpret_cast<const double2*>(a.f + c0)[t + m * T];
+            if (!valid) v[m] = make_double2(0.0, 0.0);
+        }
+    }
+    fft_regs<M, -1, false, TWP, true, true>(v, s, RS, row, t, a.tw);
+    if (!valid) return;
+    // pairs (k, M-k):  X[k] = (Zk + conj Zm)/2 + w_k (Zk - conj Zm)/(2i)
+    double2* dst = a.C + (size_t)a.PC * r;
+    auto pair_out = [&](int k) {
+        const int km = M - k;
+        const double2 zk = s[spos<true>(k % M, RS, row)];
+        const double2 zm = s[spos<true>(km % M, RS, row)];
+        {
+            const double2 E = make_double2(0.5 * (zk.x + zm.x), 0.5 * (zk.y - zm.y));
+            const double2 O = make_double2(0.5 * (zk.y + zm.y), -0.5 * (zk.x - zm.x));
+            const double2 X = cadd(E, cmul(__ldg(&a.twr[k]), O));
+            dst[k] = make_double2(X.x * a.scale, X.y * a.scale);
+        }
+        if (km != k) {
+            const double2 E = make_double2(0.5 * (zm.x + zk.x), 0.5 * (zm.y - zk.y));
+            const double2 O = make_double2(0.5 * (zm.y + zk.y), -0.5 * (zm.x - zk.x));
+            const double2 X = cadd(E, cmul(__ldg(&a.twr[km]), O));
+            dst[km] = make_double2(X.x * a.scale, X.y * a.scale);
+        }
+    };
+#pragma unroll
+    for (int m = 0; m < 4; ++m) pair_out(t + m * T);
+    if (t == 0) pair_out(M / 2);
+}
+
 template <int M>
 __global__ void __launch_bounds__(XR* FftPlan<M>::T, (XR * FftPlan<M>::T <= 1024) ? 1024 / (XR * FftPlan<M>::T) : 1)
 k_fft_x_c2r_w(XArgs a) {
@@ -444,7 +504,7 @@ k_fft_x_c2r_w(XArgs a) {
     constexpr int T = FftPlan<M>::T;
     constexpr int RS = M + M / 8 + 1;
     const int tid = threadIdx.x;
-    const int row0 = blockIdx.x * XR;
+    const int row0 = a.r0 + blockIdx.x * XR;
     {
         double2 x[XR];
 #pragma unroll
@@ -490,6 +550,105 @@ k_fft_x_c2r_w(XArgs a) {
     }
 }
 
+// Row-private form of k_fft_x_c2r_w: the T threads of a row (one warp at M = 256, two at M = 512) load THEIR row,
+// stage it in their own padded shared-memory row, take the (k, M-k) pairs from it and run the transform with
+// row-level barriers only (fft_core.cuh: RSYNC) -- no block-wide barrier anywhere, so the eight rows of a block and
+// the blocks of an SM drift apart and their load, transform and store phases overlap.  (The r01v capture of
+// k_fft_x_c2r_w: 0.59 ms = 55 % of HBM with 26 % issue activity, stall samples spread evenly over the phases between
+// seven block-wide barriers.)  Same arithmetic in the same order.
+template <int M>
+__global__ void __launch_bounds__(XR* FftPlan<M>::T, (XR * FftPlan<M>::T <= 1024) ? 1024 / (XR * FftPlan<M>::T) : 1)
+k_fft_x_c2r_v(XArgs a) {
+    extern __shared__ double2 s[];
+    constexpr int T = FftPlan<M>::T;
+    constexpr int RS = M + M / 8 + 1;
+    const int tid = threadIdx.x;
+    const int row = tid / T, t = tid % T;
+    const int r = a.r0 + blockIdx.x * XR + row;
+    const bool valid = r < a.nrows;
+    {
+        const double2* X = a.C + (size_t)a.PC * (valid ? r : a.r0);
+        double2 x[8];
+#pragma unroll
+        for (int m = 0; m < 8; ++m) x[m] = X[t + m * T];
+        double2 xn = make_double2(0.0, 0.0);
+        if (t == 0) { xn = X[M]; x[0].y = 0.0; xn.y = 0.0; }      // c2r ignores the imaginary part of DC / Nyquist
+#pragma unroll
+        for (int m = 0; m < 8; ++m) s[spos<true>(t + m * T, RS, row)] = x[m];
+        if (t == 0) s[spos<true>(M, RS, row)] = xn;
+    }
+    fft_sync<M, true>(row);
+    double2 v[8];
+#pragma unroll
+    for (int m = 0; m < 8; ++m) {
+        // Z[k] = (Xk + conj Xm) + i conj(w_k) (Xk - conj Xm),  m = M - k, w_k = exp(-2 pi i k / N)
+        const int k = t + m * T;
+        const double2 xk = s[spos<true>(k, RS, row)], xm = s[spos<true>(M - k, RS, row)];
+        const double2 E = make_double2(xk.x + xm.x, xk.y - xm.y);
+        const double2 D = make_double2(xk.x - xm.x, xk.y + xm.y);
+        const double2 O = cmul(cconj(__ldg(&a.twr[k])), D);
+        v[m] = make_double2(E.x - O.y, E.y + O.x);
+    }
+    fft_sync<M, true>(row);                       // the first stage overwrites the staged row
+    fft_regs<M, +1, true, false, true, true>(v, s, RS, row, t, a.tw);
+    if (!valid) return;
+    const int j = r % a.ny, k3 = r / a.ny;
+    double* frow = a.f + a.L.idx(1, j + 1, k3 + 1);
+#pragma unroll
+    for (int m = 0; m < 8; ++m) {
+        const int idx = t + m * T;
+        reinterpret_cast<double2*>(frow)[idx] = v[m];
+        if (idx == 0) frow[2 * M] = v[m].x;       // periodic x ghosts (scalar.f90:257,276)
+        if (idx == M - 1) frow[-1] = v[m].y;
+    }
+}
+
+// Row-private c2r WITHOUT staging: the T threads of a row read X[k] (ascending) and X[M-k] (descending) of their own
+// row straight from global memory -- both are whole 512-byte runs per warp, the second hits the lines the first just
+// brought into L1 -- so the pair pre-pass needs no shared-memory pass and no barrier at all; the transform then runs
+// with row-level barriers (RSYNC).  One shared-memory store and two loads per element fewer than k_fft_x_c2r_w.
+template <int M, bool TWP>
+__global__ void __launch_bounds__(XR* FftPlan<M>::T, (XR * FftPlan<M>::T <= 1024) ? 1024 / (XR * FftPlan<M>::T) : 1)
+k_fft_x_c2r_d(XArgs a) {
+    extern __shared__ double2 s[];
+    constexpr int T = FftPlan<M>::T;
+    constexpr int RS = M + M / 8 + 1;
+    const int tid = threadIdx.x;
+    const int row = tid / T, t = tid % T;
+    const int r = a.r0 + blockIdx.x * XR + row;
+    const bool valid = r < a.nrows;
+    const double2* X = a.C + (size_t)a.PC * (valid ? r : a.r0);
+    double2 v[8];
+    {
+        double2 xk[8], xm[8];
+#pragma unroll
+        for (int m = 0; m < 8; ++m) {
+            xk[m] = X[t + m * T];
+            xm[m] = X[M - (t + m * T)];
+        }
+        if (t == 0) { xk[0].y = 0.0; xm[0].y = 0.0; }            // c2r ignores the imaginary part of DC / Nyquist
+#pragma unroll
+        for (int m = 0; m < 8; ++m) {
+            // Z[k] = (Xk + conj Xm) + i conj(w_k) (Xk - conj Xm),  m = M - k, w_k = exp(-2 pi i k / N)
+            const double2 E = make_double2(xk[m].x + xm[m].x, xk[m].y - xm[m].y);
+            const double2 D = make_double2(xk[m].x - xm[m].x, xk[m].y + xm[m].y);
+            const double2 O = cmul(cconj(__ldg(&a.twr[t + m * T])), D);
+            v[m] = make_double2(E.x - O.y, E.y + O.x);
+        }
+    }
+    fft_regs<M, +1, true, TWP, true, true>(v, s, RS, row, t, a.tw);
+    if (!valid) return;
+    const int j = r % a.ny, k3 = r / a.ny;
+    double* frow = a.f + a.L.idx(1, j + 1, k3 + 1);
+#pragma unroll
+    for (int m = 0; m < 8; ++m) {
+        const int idx = t + m * T;
+        reinterpret_cast<double2*>(frow)[idx] = v[m];
+        if (idx == 0) frow[2 * M] = v[m].x;       // periodic x ghosts (scalar.f90:257,276)
+        if (idx == M - 1) frow[-1] = v[m].y;
+    }
+}
+
 // c2r with a coalesced staging load: rows of C -> shared memory, the pair pre-pass reads (k, M-k) from there
 // into registers, the transform runs register-to-register and the real row is stored straight from registers.
 template <int M>
@@ -499,7 +658,7 @@ k_fft_x_c2r_s(XArgs a) {
     constexpr int T = FftPlan<M>::T;
     constexpr int NT = XR * T;
     const int tid = threadIdx.x;
-    const int row0 = blockIdx.x * XR;
+    const int row0 = a.r0 + blockIdx.x * XR;
     {
         // NT == M threads: thread k loads X[k] of the 8 rows (8 independent coalesced loads in flight), thread q < 8
         // also the Nyquist element X[M] of row q
@@ -557,7 +716,7 @@ __global__ void __launch_bounds__(NL* FftPlan<Lf>::T, (NL * FftPlan<Lf>::T <= 10
     double2 v[8];
 #pragma unroll
     for (int m = 0; m < 8; ++m) v[m] = base[a.sl * (t + m * T)];
-    fft_regs<Lf, DIR, true>(v, s, NL, line, t, a.tw);
+    fft_regs<Lf, DIR, true, kStridedTwp>(v, s, NL, line, t, a.tw);
     const double sc = a.scale;
 #pragma unroll
     for (int m = 0; m < 8; ++m) {
@@ -568,7 +727,7 @@ __global__ void __launch_bounds__(NL* FftPlan<Lf>::T, (NL * FftPlan<Lf>::T <= 10
     }
 }
 
-template <int Lf, int NL, bool SC, bool TWP = false>
+template <int Lf, int NL, bool SC, bool TWP = kStridedTwp>
 __global__ void __launch_bounds__(NL* FftPlan<Lf>::T, (NL * FftPlan<Lf>::T <= 1024) ? 1024 / (NL * FftPlan<Lf>::T) : 1) k_fft_solve_r(LArgs a, ScArgs q) {
     extern __shared__ double2 s[];
     constexpr int T = FftPlan<Lf>::T;
@@ -711,11 +870,9 @@ struct TArgs {
     int form2d;
     int mean;              // subtract the mean of phi (pn, ppn): see k_thomas_bwd
     // blocked z-pencil layout (slab_bulk.cuh): thread e of granule g = blockIdx.y owns system kx = 8 g + e % 8,
-    // jl = e / 8 at C + so * g + e (so = granule stride, sl = plane stride nyl * 8); the back substitution writes
-    // its solution to `out` laid out [g][jl][k][8]
+    // jl = e / 8 at C + so * g + e (so = granule stride, sl = plane stride nyl * 8)
     int blocked = 0;
-    double2* out = nullptr;
-    long long out_gs = 0;
+    int g0 = 0;            // first granule of this launch (blocked layout; chunked launches)
 };
 struct TSys {              // one thread's system
     long long off;         // offset of its first element in C / c1
@@ -730,8 +887,8 @@ __device__ __forceinline__ TSys thomas_sys(const TArgs& g) {
         s.off = e + g.so * blockIdx.y;
         s.valid = e < g.npc;
     } else {
-        s.kx = blockIdx.y * 8 + (e & 7); s.lo_idx = g.o0 + (e >> 3);
-        s.off = g.so * blockIdx.y + e;
+        s.kx = (g.g0 + blockIdx.y) * 8 + (e & 7); s.lo_idx = g.o0 + (e >> 3);
+        s.off = g.so * (g.g0 + blockIdx.y) + e;
         s.valid = e < g.nouter * 8;
     }
     return s;
@@ -828,15 +985,14 @@ __global__ void __launch_bounds__(128) k_thomas_fwd(TArgs g) {
 // Back substitution.  Mean removal (poisson.f90:1159-1171, :398-410): the mean of phi over the domain
 // equals the average along the last direction of the (kx, ky) = (0, 0) spectral line, so the one thread
 // that owns that line subtracts it there -- O(n) work instead of two sweeps over the real field
-// (hazard H4).  Blocked layout: the solution goes to g.out ([g][jl][k][8]) instead of in place.
+// (hazard H4).
 __global__ void __launch_bounds__(128) k_thomas_bwd(TArgs g) {
     const TSys sy = thomas_sys(g);
     if (!sy.valid) return;
     const double2* C = g.C + sy.off;
     const double* c1t = g.c1 + sy.off;
-    const int e = blockIdx.x * blockDim.x + threadIdx.x;
-    double2* O = g.blocked ? g.out + g.out_gs * blockIdx.y + (long long)(e >> 3) * g.n * 8 + (e & 7) : g.C + sy.off;
-    const long long osl = g.blocked ? 8 : g.sl;
+    double2* O = g.C + sy.off;
+    const long long osl = g.sl;
     const int n = g.n;
     const bool mean_line = g.mean && sy.kx == 0 && sy.lo_idx == 0;
     double2 x = C[g.sl * (n - 1)];                                  // :1124-1128
@@ -1104,6 +1260,9 @@ void poisson_destroy(fen_ctx* c) {
         if (p->C) cudaFree(p->C);
     }
     if (p->Cr) cudaFree(p->Cr);
+    if (p->aux) { cudaStreamSynchronize(p->aux); cudaStreamDestroy(p->aux); }
+    for (int q = 0; q < FEN_MAX_CHUNKS; ++q) if (p->ev_piece[q]) cudaEventDestroy(p->ev_piece[q]);
+    if (p->ev_join) cudaEventDestroy(p->ev_join);
     for (void* q : {(void*)p->tw_x, (void*)p->twr_x, (void*)p->tw_y, (void*)p->tw_z, (void*)p->twq_x, (void*)p->twq_y,
                     (void*)p->mwn_x, (void*)p->mwn_y, (void*)p->mwn_z, (void*)p->ta, (void*)p->tb,
                     (void*)p->tc, (void*)p->c1, (void*)p->tw_xa})
@@ -1119,8 +1278,7 @@ const char* poisson_variant(fen_ctx* c) { return c->ps ? c->ps->variant : ""; }
 static bool tuned_len(int n, int maxn) { return pow2(n) && n <= maxn; }
 
 template <class K> static int launch_any(fen_ctx* c, const char* name, const typename K::Args& a, dim3 grid, int L, int nl) {
-    static unsigned long long attr_mask = 0;
-    if (first_time_on_device(attr_mask, c->device)) {
+    FEN_ONCE_PER_DEVICE(c) {
         FEN_CUDA(cudaFuncSetAttribute(k_any<K>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (int)any_smem_bytes(ANY_MAX_L, 1)));
     }
@@ -1158,6 +1316,13 @@ template <int M> static int set_smem_x() {
             FEN_CUDA(cudaFuncSetAttribute(k_fft_x_r2c_w<M, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
             FEN_CUDA(cudaFuncSetAttribute(k_fft_x_r2c_w<M, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
             FEN_CUDA(cudaFuncSetAttribute(k_fft_x_c2r_w<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+            FEN_CUDA(cudaFuncSetAttribute((k_fft_x_r2c_v<M, false, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+            FEN_CUDA(cudaFuncSetAttribute((k_fft_x_r2c_v<M, true, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+            FEN_CUDA(cudaFuncSetAttribute((k_fft_x_r2c_v<M, false, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+            FEN_CUDA(cudaFuncSetAttribute((k_fft_x_r2c_v<M, true, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+            FEN_CUDA(cudaFuncSetAttribute(k_fft_x_c2r_v<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+            FEN_CUDA(cudaFuncSetAttribute(k_fft_x_c2r_d<M, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+            FEN_CUDA(cudaFuncSetAttribute(k_fft_x_c2r_d<M, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
         }
     }
     return FEN_OK;
@@ -1177,11 +1342,12 @@ static int x_variant(const char* name, int dflt) {
 template <int M> static int launch_x(fen_ctx* c, const XArgs& a, bool fwd, const DivArgs* dv) {
     constexpr int T = FftPlan<M>::T;
     const int bytes = (M + 1) * XIS * (int)sizeof(double2);
-    static unsigned long long attr_mask = 0;
-    if (first_time_on_device(attr_mask, c->device)) FEN_TRY(set_smem_x<M>());
+    FEN_ONCE_PER_DEVICE(c) FEN_TRY(set_smem_x<M>());
     // c2r: the warp-per-row kernel wins at M = 256 (0.58 vs 0.61 ms), the staged one at M >= 512 (0.66 vs 0.71 ms)
-    static const int vr2c = x_variant("FEN_X_R2C", 1), vc2r = x_variant("FEN_X_C2R", M >= 512 ? 2 : 3);
-    dim3 grid((a.nrows + XR - 1) / XR), block(XR * T);
+    // c2r: 7 = row-private, no staging, twiddle products (0.47 ms at M = 256 against 0.60 for the staged warp-per-row
+    // kernel; 0.52 against 0.67 at M = 512: profiles/r02f_*.json)
+    static const int vr2c = x_variant("FEN_X_R2C", 1), vc2r = x_variant("FEN_X_C2R", 7);
+    dim3 grid((a.nrows - a.r0 + XR - 1) / XR), block(XR * T);
     DivArgs none{};
     bool done = false;
     if constexpr (M >= 64) {
@@ -1193,6 +1359,16 @@ template <int M> static int launch_x(fen_ctx* c, const XArgs& a, bool fwd, const
         if (!fwd && vc2r == 0) { FEN_LAUNCH(c, "fft_x_c2r", k_fft_x_c2r_r<M><<<grid, block, bytes, c->stream>>>(a)); done = true; }
         if (!fwd && vc2r == 2) { FEN_LAUNCH(c, "fft_x_c2r", k_fft_x_c2r_s<M><<<grid, block, bytes, c->stream>>>(a)); done = true; }
         if (!fwd && vc2r == 3) { FEN_LAUNCH(c, "fft_x_c2r", k_fft_x_c2r_w<M><<<grid, block, bytes, c->stream>>>(a)); done = true; }
+        if (!fwd && vc2r == 5) { FEN_LAUNCH(c, "fft_x_c2r", k_fft_x_c2r_v<M><<<grid, block, bytes, c->stream>>>(a)); done = true; }
+        if (!fwd && vc2r == 6) { FEN_LAUNCH(c, "fft_x_c2r", k_fft_x_c2r_d<M, false><<<grid, block, bytes, c->stream>>>(a)); done = true; }
+        if (!fwd && vc2r == 7) { FEN_LAUNCH(c, "fft_x_c2r", k_fft_x_c2r_d<M, true><<<grid, block, bytes, c->stream>>>(a)); done = true; }
+        if (fwd && (vr2c == 5 || vr2c == 6)) {     // row-private; 6: with twiddle products
+            if (dv && vr2c == 5) FEN_LAUNCH(c, "fft_x_r2c_div", k_fft_x_r2c_v<M, true, false><<<grid, block, bytes, c->stream>>>(a, *dv));
+            else if (dv) FEN_LAUNCH(c, "fft_x_r2c_div", k_fft_x_r2c_v<M, true, true><<<grid, block, bytes, c->stream>>>(a, *dv));
+            else if (vr2c == 5) FEN_LAUNCH(c, "fft_x_r2c", k_fft_x_r2c_v<M, false, false><<<grid, block, bytes, c->stream>>>(a, none));
+            else FEN_LAUNCH(c, "fft_x_r2c", k_fft_x_r2c_v<M, false, true><<<grid, block, bytes, c->stream>>>(a, none));
+            done = true;
+        }
         if (fwd && vr2c == 3) {
             if (dv) FEN_LAUNCH(c, "fft_x_r2c_div", k_fft_x_r2c_w<M, true><<<grid, block, bytes, c->stream>>>(a, *dv));
             else FEN_LAUNCH(c, "fft_x_r2c", k_fft_x_r2c_w<M, false><<<grid, block, bytes, c->stream>>>(a, none));
@@ -1228,8 +1404,7 @@ template <int Lf, int NL> static int launch_lines(fen_ctx* c, const LArgs& a, in
                                                   const ScArgs* sc) {
     constexpr int T = FftPlan<Lf>::T;
     const int bytes = Lf * NL * (int)sizeof(double2);
-    static unsigned long long attr_mask = 0;
-    if (first_time_on_device(attr_mask, c->device)) {
+    FEN_ONCE_PER_DEVICE(c) {
         if (bytes > 48 * 1024) {
             if constexpr (Lf >= 64) {
                 FEN_CUDA(cudaFuncSetAttribute(k_fft_lines_r<Lf, -1, NL, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
@@ -1297,8 +1472,7 @@ static int dispatch_lines(fen_ctx* c, int Lf, const LArgs& a, int mode, int PC, 
 template <int N> static int launch_dct_x(fen_ctx* c, const DArgs& a, bool fwd) {
     constexpr int T = FftPlan<N>::T;
     const int bytes = N * XIS * (int)sizeof(double2);
-    static unsigned long long attr_mask = 0;
-    if (first_time_on_device(attr_mask, c->device)) {
+    FEN_ONCE_PER_DEVICE(c) {
         if (bytes > 48 * 1024) {
             FEN_CUDA(cudaFuncSetAttribute(k_dct_x<N, -1>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
             FEN_CUDA(cudaFuncSetAttribute(k_dct_x<N, +1>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
@@ -1326,8 +1500,7 @@ template <int Lf> static int launch_dct_lines(fen_ctx* c, const LArgs& a, const 
                                               int nouter) {
     constexpr int T = FftPlan<Lf>::T;
     const int bytes = Lf * 8 * (int)sizeof(double2);
-    static unsigned long long attr_mask = 0;
-    if (first_time_on_device(attr_mask, c->device)) {
+    FEN_ONCE_PER_DEVICE(c) {
         if (bytes > 48 * 1024) {
             FEN_CUDA(cudaFuncSetAttribute(k_dct_lines<Lf, -1, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
             FEN_CUDA(cudaFuncSetAttribute(k_dct_lines<Lf, +1, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
@@ -1433,6 +1606,19 @@ static int poisson_build(fen_ctx* c) {
             const size_t nC = (size_t)p->PC * g.ny * p->nzl;
             FEN_CUDA(cudaMalloc(&p->Cr, nC * sizeof(double2)));
             FEN_CUDA(cudaMemsetAsync(p->Cr, 0, nC * sizeof(double2), c->stream));
+            // FEN_SLAB_CHUNKS = pieces of the overlapped transposes (1 = no overlap, one stream); default 4
+            const char* e = getenv("FEN_SLAB_CHUNKS");
+            p->nchunk = std::max(1, std::min(FEN_MAX_CHUNKS, e ? atoi(e) : 4));
+            p->nchunk = std::min(p->nchunk, std::min(p->nzl, p->PC / 8));
+            if (p->nchunk > 1) {
+                int lo = 0, hi = 0;
+                FEN_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+                // the link-bound pieces get the higher priority: their blocks mostly wait, the HBM-bound pass fills in
+                FEN_CUDA(cudaStreamCreateWithPriority(&p->aux, cudaStreamNonBlocking, hi));
+            }
+            for (int q = 0; q < FEN_MAX_CHUNKS; ++q)
+                FEN_CUDA(cudaEventCreateWithFlags(&p->ev_piece[q], cudaEventDisableTiming));
+            FEN_CUDA(cudaEventCreateWithFlags(&p->ev_join, cudaEventDisableTiming));
         }
     } else {
         const size_t nC = (size_t)p->PC * g.ny * p->nzl;
@@ -1520,8 +1706,7 @@ static int thomas_2d(fen_ctx* c, const TArgs& t) {
         FEN_CUDA(cudaGetLastError());
         return FEN_OK;
     }
-    static unsigned long long attr_mask = 0;
-    if (first_time_on_device(attr_mask, c->device)) {
+    FEN_ONCE_PER_DEVICE(c) {
         FEN_CUDA(cudaFuncSetAttribute(k_thomas_lp<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LpSmem)));
         FEN_CUDA(cudaFuncSetAttribute(k_thomas_lp<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LpSmem)));
     }
@@ -1537,75 +1722,118 @@ static int thomas_2d(fen_ctx* c, const TArgs& t) {
 
 // ---- blocked slab path (slab_bulk.cuh): ppp / ppn on several ranks, 64..1024-point transform lines ----------------
 template <int Lf> static int launch_bs(fen_ctx* c, int what, const BAddr& in, const BAddr& out, const double2* tw,
-                                       double scale, const SolveArgs* sa, const BulkDst* d, dim3 grid) {
+                                       double scale, const SolveArgs* sa, const BulkDst* d, dim3 grid, cudaStream_t st) {
     const int bytes = Lf * 8 * (int)sizeof(double2);
-    static unsigned long long attr_mask = 0;
-    if (first_time_on_device(attr_mask, c->device)) {
+    FEN_ONCE_PER_DEVICE(c) {
         FEN_CUDA(cudaFuncSetAttribute(k_fft_lines_bs<Lf, -1>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
         FEN_CUDA(cudaFuncSetAttribute(k_fft_solve_bs<Lf>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
         FEN_CUDA(cudaFuncSetAttribute(k_fft_lines_io<Lf, +1>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
     }
-    if (what == 0) FEN_LAUNCH(c, "fft_lines_fwd_a2a", k_fft_lines_bs<Lf, -1><<<grid, Lf, bytes, c->stream>>>(in, tw, scale, *d));
-    if (what == 1) FEN_LAUNCH(c, "fft_lines_inv", k_fft_lines_io<Lf, +1><<<grid, Lf, bytes, c->stream>>>(in, out, tw, scale));
-    if (what == 2) FEN_LAUNCH(c, "fft_solve_a2a", k_fft_solve_bs<Lf><<<grid, Lf, bytes, c->stream>>>(in, *sa, *d));
+    if (what == 0) FEN_LAUNCH(c, "fft_lines_fwd_a2a", k_fft_lines_bs<Lf, -1><<<grid, Lf, bytes, st>>>(in, tw, scale, *d));
+    if (what == 1) FEN_LAUNCH(c, "fft_lines_inv", k_fft_lines_io<Lf, +1><<<grid, Lf, bytes, st>>>(in, out, tw, scale));
+    if (what == 2) FEN_LAUNCH(c, "fft_solve_a2a", k_fft_solve_bs<Lf><<<grid, Lf, bytes, st>>>(in, *sa, *d));
     FEN_CUDA(cudaGetLastError());
     return FEN_OK;
 }
 static int dispatch_bs(fen_ctx* c, int Lf, int what, const BAddr& in, const BAddr& out, const double2* tw, double scale,
-                       const SolveArgs* sa, const BulkDst* d, dim3 grid) {
+                       const SolveArgs* sa, const BulkDst* d, dim3 grid, cudaStream_t st) {
     switch (Lf) {
-#define FEN_CASE(l) case l: return launch_bs<l>(c, what, in, out, tw, scale, sa, d, grid);
+#define FEN_CASE(l) case l: return launch_bs<l>(c, what, in, out, tw, scale, sa, d, grid, st);
         FEN_CASE(64) FEN_CASE(128) FEN_CASE(256) FEN_CASE(512) FEN_CASE(1024)
 #undef FEN_CASE
     }
     return set_error(FEN_ERR_STATE, "blocked slab path: line length %d", Lf);
 }
 
-// y forward -> (bulk stores) -> z solve or Thomas -> (bulk stores) -> y inverse into the row array Cr
-static int solve_blocked(fen_ctx* c, Poisson* p, bool ppp) {
+// x r2c -> y forward -> (bulk stores) -> z solve or Thomas -> (bulk stores) -> y inverse into the row array Cr.
+//
+// The two transposing stages are bound by the link (941 MB out per GPU at 1024^3 on 8: >= 1.2 ms each at the 770 GB/s a
+// peer copy reaches), their blocks spend most of their life waiting for bulk stores to drain, and the passes either
+// side of them are bound by local HBM.  So the work is cut in nchunk pieces and pipelined over two streams:
+//   forward   piece q = z planes:  x r2c(q) on the main stream, y forward + stores(q) on `aux` behind it -- the x pass
+//             of piece q+1 runs while piece q's stores travel;
+//   backward  piece q = granules:  z solve (or Thomas + row shipping) + stores(q) on the main stream, then "piece q is
+//             out" is raised on every peer; `aux` waits until every peer has raised it and runs the y inverse of those
+//             granules while piece q+1 is solved and shipped.
+// With per-kernel profiling on (bench.py's kernel table) everything runs on the main stream, piece by piece, so that
+// the event brackets mean what they say; the timed region of the bench runs overlapped.
+static int solve_blocked(fen_ctx* c, Poisson* p, bool ppp, XArgs xa, bool fuse_rhs, const DivArgs* dv) {
     const fen_grid_desc& g = c->g;
     const int NG = p->PC / 8, P = g.nranks;
     const long long ny = g.ny, nz = g.nz, nyl = p->nyl, nzl = p->nzl;
-    BAddr rows_in{p->C, 8, (long long)p->PC * ny, p->PC};                  // C[kx + PC*(j + ny*zl)]: lines over j
-    BAddr none{nullptr, 0, 0, 0};
+    cudaStream_t S = c->stream, T = (c->profiling || !p->aux) ? c->stream : p->aux;
+    const bool two = T != S;
+    const int nq = p->nchunk;
+    BAddr none{nullptr, 0, 0, 0, 0, 0};
     BulkDst df;                                                           // -> Cz[((g*nz + k)*nyl + jl)*8 + kxi]
     memset(&df, 0, sizeof(df));
     for (int r = 0; r < P; ++r) df.peer[r] = p->peerCz[r];
     df.gs = nz * nyl * 8; df.os = nyl * 8; df.o0 = g.rank * (int)nzl; df.blk = (int)nyl; df.P = P; df.rank = g.rank;
     const double sy = ppp ? 1.0 : 1.0 / f32(g.ny);                        // poisson.f90:1087
-    FEN_TRY(dispatch_bs(c, g.ny, 0, rows_in, none, p->tw_y, sy, nullptr, &df, dim3(NG, (unsigned)nzl)));
+    // ---- forward: pieces of z planes ----
+    for (int q = 0; q < nq; ++q) {
+        const int z0 = (int)(nzl * q / nq), z1 = (int)(nzl * (q + 1) / nq);
+        if (z1 <= z0) continue;
+        XArgs xq = xa;
+        xq.r0 = z0 * (int)ny; xq.nrows = z1 * (int)ny;
+        FEN_TRY(dispatch_x(c, p->M, xq, true, fuse_rhs ? dv : nullptr)); // :965-969 (+ :111-121 when fused)
+        if (two) {
+            FEN_CUDA(cudaEventRecord(p->ev_piece[q], S));
+            FEN_CUDA(cudaStreamWaitEvent(T, p->ev_piece[q], 0));
+        }
+        BAddr rows_in{p->C, 8, (long long)p->PC * ny, p->PC, 0, z0};      // C[kx + PC*(j + ny*zl)]: lines over j
+        FEN_TRY(dispatch_bs(c, g.ny, 0, rows_in, none, p->tw_y, sy, nullptr, &df, dim3(NG, (unsigned)(z1 - z0)), T));
+    }
+    if (two) {
+        FEN_CUDA(cudaEventRecord(p->ev_join, T));
+        FEN_CUDA(cudaStreamWaitEvent(S, p->ev_join, 0));
+    }
     FEN_TRY(comm_transpose_fwd(c));                                       // transpose_y_to_z (:982 / :1090)
+    // ---- backward: pieces of granules ----
     BulkDst db;                                                           // -> Cy[((g*ny + j)*nzl + zl)*8 + kxi]
     memset(&db, 0, sizeof(db));
     for (int r = 0; r < P; ++r) db.peer[r] = p->peerC[r];
     db.gs = ny * nzl * 8; db.os = nzl * 8; db.o0 = g.rank * (int)nyl; db.blk = (int)nzl; db.P = P; db.rank = g.rank;
-    if (ppp) {
-        BAddr zin{p->Cz, nz * nyl * 8, 8, nyl * 8};                       // lines over k
-        SolveArgs sa;
-        sa.tw = p->tw_z; sa.lx = p->mwn_x; sa.lo = p->mwn_y; sa.ll = p->mwn_z;
-        sa.norm = f32((long long)g.nx * g.ny * g.nz); sa.ow0 = g.rank * (int)nyl;
-        FEN_TRY(dispatch_bs(c, g.nz, 2, zin, none, nullptr, 1.0, &sa, &db, dim3(NG, (unsigned)nyl)));
-    } else {
-        TArgs t;
-        t.C = p->Cz; t.c1 = p->c1; t.sl = nyl * 8; t.so = nz * nyl * 8; t.n = g.nz; t.npc = p->PC; t.nouter = (int)nyl;
-        t.o0 = g.rank * (int)nyl;
-        t.a = p->ta; t.b = p->tb; t.c = p->tc; t.lx = p->mwn_x; t.lo = p->mwn_y; t.form2d = 0; t.mean = 1;
-        t.blocked = 1; t.out = p->Cr; t.out_gs = nyl * nz * 8;
-        dim3 grid(((unsigned)nyl * 8 + 127) / 128, NG), block(128);
-        FEN_LAUNCH(c, "thomas_fwd", k_thomas_fwd<<<grid, block, 0, c->stream>>>(t));
-        FEN_LAUNCH(c, "thomas_bwd", k_thomas_bwd<<<grid, block, 0, c->stream>>>(t));
-        const int bytes = (int)nzl * 8 * (int)sizeof(double2);
-        static unsigned long long attr_mask = 0;
-        if (first_time_on_device(attr_mask, c->device))
-            FEN_CUDA(cudaFuncSetAttribute(k_bulk_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024));
-        FEN_LAUNCH(c, "a2a_scatter", k_bulk_rows<<<dim3((unsigned)(P * nyl), NG), 256, bytes, c->stream>>>(
-                                         p->Cr, nyl * nz * 8, nz * 8, db, (int)nyl));
-        FEN_CUDA(cudaGetLastError());
+    for (int q = 0; q < nq; ++q) {
+        const int g0 = NG * q / nq, g1 = NG * (q + 1) / nq;
+        if (g1 <= g0) continue;
+        if (ppp) {
+            BAddr zin{p->Cz, nz * nyl * 8, 8, nyl * 8, g0, 0};            // lines over k
+            SolveArgs sa;
+            sa.tw = p->tw_z; sa.lx = p->mwn_x; sa.lo = p->mwn_y; sa.ll = p->mwn_z;
+            sa.norm = f32((long long)g.nx * g.ny * g.nz); sa.ow0 = g.rank * (int)nyl;
+            FEN_TRY(dispatch_bs(c, g.nz, 2, zin, none, nullptr, 1.0, &sa, &db, dim3(g1 - g0, (unsigned)nyl), S));
+        } else {
+            TArgs t;
+            t.C = p->Cz; t.c1 = p->c1; t.sl = nyl * 8; t.so = nz * nyl * 8; t.n = g.nz; t.npc = p->PC;
+            t.nouter = (int)nyl; t.o0 = g.rank * (int)nyl;
+            t.a = p->ta; t.b = p->tb; t.c = p->tc; t.lx = p->mwn_x; t.lo = p->mwn_y; t.form2d = 0; t.mean = 1;
+            t.blocked = 1; t.g0 = g0;
+            dim3 grid(((unsigned)nyl * 8 + 127) / 128, g1 - g0), block(128);
+            FEN_LAUNCH(c, "thomas_fwd", k_thomas_fwd<<<grid, block, 0, S>>>(t));
+            FEN_LAUNCH(c, "thomas_bwd", k_thomas_bwd<<<grid, block, 0, S>>>(t));
+            const int bytes = (int)nzl * 8 * (int)sizeof(double2);
+            FEN_ONCE_PER_DEVICE(c)
+                FEN_CUDA(cudaFuncSetAttribute(k_bulk_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024));
+            FEN_LAUNCH(c, "a2a_scatter", k_bulk_rows<<<dim3((unsigned)(P * nyl), g1 - g0), 256, bytes, S>>>(
+                                             p->Cz, nz * nyl * 8, nyl * 8, 8, db, (int)nyl, g0));
+            FEN_CUDA(cudaGetLastError());
+        }
+        FEN_TRY(comm_chunk_signal(c, q, S));                              // my piece q is out ...
+        if (two) {
+            FEN_CUDA(cudaEventRecord(p->ev_piece[q], S));
+            FEN_CUDA(cudaStreamWaitEvent(T, p->ev_piece[q], 0));
+        }
+        FEN_TRY(comm_chunk_wait(c, q, T));                                // ... and everybody's has arrived (:1015 / :1138)
+        BAddr yin{p->C, ny * nzl * 8, 8, nzl * 8, g0, 0};                 // Cy lives in C's memory: lines over j
+        BAddr rows_out{p->Cr, 8, (long long)p->PC * ny, p->PC, g0, 0};
+        FEN_TRY(dispatch_bs(c, g.ny, 1, yin, rows_out, p->tw_y, 1.0, nullptr, nullptr, dim3(g1 - g0, (unsigned)nzl), T));
     }
-    FEN_TRY(comm_transpose_bwd(c));                                       // transpose_z_to_y (:1015 / :1138)
-    BAddr yin{p->C, ny * nzl * 8, 8, nzl * 8};                            // Cy lives in C's memory: lines over j
-    BAddr rows_out{p->Cr, 8, (long long)p->PC * ny, p->PC};
-    return dispatch_bs(c, g.ny, 1, yin, rows_out, p->tw_y, 1.0, nullptr, nullptr, dim3(NG, (unsigned)nzl));
+    if (two) {
+        FEN_CUDA(cudaEventRecord(p->ev_join, T));
+        FEN_CUDA(cudaStreamWaitEvent(S, p->ev_join, 0));
+    }
+    return FEN_OK;
 }
 
 int poisson_solve(fen_ctx* c, double* f, bool fuse_rhs, double dt) {
@@ -1700,7 +1928,8 @@ int poisson_solve(fen_ctx* c, double* f, bool fuse_rhs, double dt) {
     xa.L = c->L; xa.f = f; xa.C = p->C; xa.PC = p->PC; xa.ny = g.ny; xa.nrows = g.ny * p->nzl;
     xa.tw = p->tw_x; xa.twr = p->twr_x;
     xa.scale = (ppn || pn) ? 1.0 / f32(g.nx) : 1.0;           // poisson.f90:1074, :341
-    FEN_TRY(dispatch_x(c, p->M, xa, true, fuse_rhs ? &dv : nullptr));
+    xa.r0 = 0;
+    if (!p->blocked) FEN_TRY(dispatch_x(c, p->M, xa, true, fuse_rhs ? &dv : nullptr));   // blocked: in pieces, below
 
     LArgs la;
     la.lx = p->mwn_x; la.lo = nullptr; la.ll = nullptr; la.norm = 1.0; la.o0 = 0; la.cx0 = 0;
@@ -1728,7 +1957,7 @@ int poisson_solve(fen_ctx* c, double* f, bool fuse_rhs, double dt) {
             sb.dsl = (long long)p->PC * g.ny; sb.dso = p->PC; sb.o0 = g.rank * p->nyl;
         }
         if (p->blocked) {
-            FEN_TRY(solve_blocked(c, p, ppp));
+            FEN_TRY(solve_blocked(c, p, ppp, xa, fuse_rhs, &dv));
             xa.C = p->Cr;                                      // the y inverse left the rows there
         } else {
         la.C = p->C; la.sl = p->PC; la.so = (long long)p->PC * g.ny; la.tw = p->tw_y;

@@ -26,10 +26,12 @@
 
 namespace fen {
 
-// element (g, o, idx, line) of an array:  p + gs*g + os*o + is*idx + line
+// element (g, o, idx, line) of an array:  p + gs*g + os*o + is*idx + line.  A launch covers the granules g0 + blockIdx.x
+// and the outer indices ob + blockIdx.y (the chunked, overlapped form of the solve launches pieces of the range)
 struct BAddr {
     double2* p;
     long long gs, os, is;
+    int g0, ob;
 };
 // destination of a tile: rank r receives idx in [r*blk, (r+1)*blk) as one run at peer[r] + gs*g + os*(o0 + o)
 struct BulkDst {
@@ -67,12 +69,12 @@ k_fft_lines_bs(BAddr in, const double2* tw, double scale, BulkDst d) {
     constexpr int T = Lf / 8;
     const int tid = threadIdx.x;
     const int line = tid & 7, t = tid >> 3;
-    const int g = blockIdx.x, o = blockIdx.y;
+    const int g = in.g0 + blockIdx.x, o = in.ob + blockIdx.y;
     const double2* base = in.p + in.gs * g + in.os * o + line;
     double2 v[8];
 #pragma unroll
     for (int m = 0; m < 8; ++m) v[m] = base[in.is * (t + m * T)];
-    fft_regs<Lf, DIR, true>(v, s, 8, line, t, tw);
+    fft_regs<Lf, DIR, true, kStridedTwp>(v, s, 8, line, t, tw);
 #pragma unroll
     for (int m = 0; m < 8; ++m) s[(t + m * T) * 8 + line] = make_double2(v[m].x * scale, v[m].y * scale);
     bulk_scatter_tile(s, d, g, o, tid);
@@ -92,14 +94,14 @@ k_fft_solve_bs(BAddr in, SolveArgs a, BulkDst d) {
     constexpr int T = Lf / 8;
     const int tid = threadIdx.x;
     const int line = tid & 7, t = tid >> 3;
-    const int g = blockIdx.x, o = blockIdx.y;
+    const int g = in.g0 + blockIdx.x, o = in.ob + blockIdx.y;
     double2 v[8];
     {
         const double2* base = in.p + in.gs * g + in.os * o + line;
 #pragma unroll
         for (int m = 0; m < 8; ++m) v[m] = base[in.is * (t + m * T)];
     }
-    fft_regs<Lf, -1, true>(v, s, 8, line, t, a.tw);
+    fft_regs<Lf, -1, true, kStridedTwp>(v, s, 8, line, t, a.tw);
     {   // poisson.f90:992 then :998-1001; see k_fft_solve_r for the rounding argument (power-of-two norm)
         double lxo = __ldg(&a.lx[g * 8 + line]);
         if (a.lo) lxo = lxo + __ldg(&a.lo[a.ow0 + o]);
@@ -112,7 +114,7 @@ k_fft_solve_bs(BAddr in, SolveArgs a, BulkDst d) {
             v[m].y *= rl;
         }
     }
-    fft_regs<Lf, +1, true>(v, s, 8, line, t, a.tw);
+    fft_regs<Lf, +1, true, kStridedTwp>(v, s, 8, line, t, a.tw);
 #pragma unroll
     for (int m = 0; m < 8; ++m) s[(t + m * T) * 8 + line] = v[m];
     bulk_scatter_tile(s, d, g, o, tid);
@@ -126,31 +128,32 @@ k_fft_lines_io(BAddr in, BAddr out, const double2* tw, double scale) {
     constexpr int T = Lf / 8;
     const int tid = threadIdx.x;
     const int line = tid & 7, t = tid >> 3;
-    const int g = blockIdx.x, o = blockIdx.y;
+    const int g = in.g0 + blockIdx.x, o = in.ob + blockIdx.y;
     const double2* base = in.p + in.gs * g + in.os * o + line;
     double2 v[8];
 #pragma unroll
     for (int m = 0; m < 8; ++m) v[m] = base[in.is * (t + m * T)];
-    fft_regs<Lf, DIR, true>(v, s, 8, line, t, tw);
+    fft_regs<Lf, DIR, true, kStridedTwp>(v, s, 8, line, t, tw);
     double2* ob = out.p + out.gs * g + out.os * o + line;
 #pragma unroll
     for (int m = 0; m < 8; ++m) ob[out.is * (t + m * T)] = make_double2(v[m].x * scale, v[m].y * scale);
 }
 
-// Thomas path (ppn): the back substitution leaves the solution in a local staging array laid out [g][jl][k][8], in
-// which the part of a (g, jl) column that belongs to rank r -- k in [r*nzl, (r+1)*nzl) -- is one contiguous run, as
-// it is in the destination Cy.  One block ships one run: global -> shared (coalesced 16-byte loads) -> one bulk store.
-// Consecutive blocks cycle over the destination ranks, starting one past the sender.
-__global__ void __launch_bounds__(256) k_bulk_rows(const double2* __restrict__ src, long long s_gs, long long s_os,
-                                                   BulkDst d, int nouter) {
+// Thomas path (ppn): the back substitution leaves the solution in place in Cz ([g][k][jl][8]).  One block ships the
+// part of one (g, jl) column that belongs to rank r -- the nzl granules k in [r*nzl, (r+1)*nzl), 128 bytes each at a
+// stride of nyl * 128 bytes -- by gathering it into shared memory (every warp instruction reads four whole granules)
+// and issuing one bulk store of nzl * 128 bytes to the run it occupies in the destination Cy.  Consecutive blocks
+// cycle over the destination ranks, starting one past the sender.
+__global__ void __launch_bounds__(256) k_bulk_rows(const double2* __restrict__ src, long long s_gs, long long s_ks,
+                                                   long long s_os, BulkDst d, int nouter, int g0) {
     extern __shared__ __align__(128) double2 s[];
     const int r = (d.rank + 1 + blockIdx.x % d.P) % d.P;
     const int o = blockIdx.x / d.P;                   // jl
-    const int g = blockIdx.y;
+    const int g = g0 + blockIdx.y;
     if (o >= nouter) return;
     const int n = d.blk * 8;
-    const double2* sp = src + s_gs * g + s_os * o + (size_t)r * n;
-    for (int e = threadIdx.x; e < n; e += blockDim.x) s[e] = sp[e];
+    const double2* sp = src + s_gs * g + s_os * o + s_ks * ((long long)r * d.blk);
+    for (int e = threadIdx.x; e < n; e += blockDim.x) s[e] = sp[s_ks * (e >> 3) + (e & 7)];
     fence_async_smem();
     __syncthreads();
     if (threadIdx.x == 0) {

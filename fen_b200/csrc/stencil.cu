@@ -773,8 +773,7 @@ int ns_predict(fen_ctx* c, double dt) {
         // TMA-staged kernel: tensor maps of the three velocity buffers (cached per buffer)
         CUtensorMap* m[3];
         for (int q = 0; q < 3; ++q) FEN_TRY(field_tmap(c, q == 0 ? a.u : (q == 1 ? a.v : a.w), PTW, PTH, &m[q]));
-        static unsigned long long attr_mask = 0;
-        if (first_time_on_device(attr_mask, c->device)) {
+        FEN_ONCE_PER_DEVICE(c) {
             FEN_CUDA(cudaFuncSetAttribute(k_pred_tma<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, PRED_SMEM));
             FEN_CUDA(cudaFuncSetAttribute(k_pred_tma<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, PRED_SMEM));
             FEN_CUDA(cudaFuncSetAttribute(k_pred_tma<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, PRED_SMEM));
@@ -880,8 +879,7 @@ int ns_correct(fen_ctx* c, double dt, bool* checks_done) {
         CUtensorMap* m[4];
         const double* src[4] = {phi->d, u->d, v->d, w->d};
         for (int q = 0; q < 4; ++q) FEN_TRY(field_tmap(c, src[q], PTW, PTH, &m[q]));
-        static unsigned long long attr_mask = 0;
-        if (first_time_on_device(attr_mask, c->device)) {
+        FEN_ONCE_PER_DEVICE(c) {
             FEN_CUDA(cudaFuncSetAttribute(k_corr_tma<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, CORR_SMEM));
             FEN_CUDA(cudaFuncSetAttribute(k_corr_tma<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, CORR_SMEM));
         }

@@ -12,6 +12,11 @@ import threading
 from concurrent.futures import ThreadPoolExecutor
 
 os.environ.setdefault("FEN_GPU_SPIN_LIMIT_MS", "3000")    # a missed flag fails the test in seconds
+# Every rank drives two streams (the blocked slab path overlaps its transposes on an auxiliary one).  With all ranks on
+# ONE device the default 8 hardware work queues would alias 16 streams: a rank's solve kernel could sit in a queue behind
+# another rank's spinning flag wait and never start (seen: 8 ranks, "peer wait timed out").  One process per GPU -- the
+# production layout -- has three streams per device and cannot alias.  Must be set before the CUDA context exists.
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
 
 import numpy as np
 
