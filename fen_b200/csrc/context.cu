@@ -346,6 +346,7 @@ int fen_gpu_destroy(fen_ctx* c) {
         cudaStreamDestroy(c->d2h);
     }
     if (c->h_red) cudaFreeHost(c->h_red);
+    if (c->io_host) cudaFreeHost(c->io_host);
     for (auto& e : c->prof_entries) { cudaEventDestroy(e.e0); cudaEventDestroy(e.e1); }
     cudaStreamDestroy(c->stream);
     delete c;

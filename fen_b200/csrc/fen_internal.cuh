@@ -154,6 +154,11 @@ struct fen_ctx {
     bool ev_free_set[4] = {false, false, false, false};
     cudaEvent_t ev_chunk[4][8] = {};   // per staging buffer: piece q of its host copy is out (d2h stream)
     int out_next = 0;
+    // io.cu: pinned staging of one slab interior and the cell-centred temporary of save_fields, allocated on first use
+    // and kept -- so that the I/O entry points do not allocate (a device-wide synchronisation) on every call
+    double* io_host = nullptr;
+    size_t io_host_n = 0;
+    int io_tmp = -1;
     double* d_red = nullptr;     // device scratch for reductions (partials + results)
     double* h_red = nullptr;     // pinned host mirror of the results
     int red_blocks = 0;

@@ -20,10 +20,12 @@
 #define FEN_HD __host__ __device__ __forceinline__
 #endif
 
-// FEN_STRIDED_TWP=1 (build-time A/B switch): the strided y / z passes also form w^3, w^5, w^6, w^7 of a radix-8 stage
-// as products of three table entries instead of loading seven
+// FEN_STRIDED_TWP (build-time A/B switch, default on): the strided y / z passes also form w^3, w^5, w^6, w^7 of a
+// radix-8 stage as products of three table entries instead of loading seven (within ~2 ulp of the table values).
+// Measured (profiles/r02g_twp.json, r02g_slab_twp.json): 512-point passes 0.38 -> 0.37 ms, 1024-point passes of the
+// 8-GPU slab 0.59 / 0.61 / 0.58 -> 0.56 / 0.55 / 0.54 ms.
 #ifndef FEN_STRIDED_TWP
-#define FEN_STRIDED_TWP 0
+#define FEN_STRIDED_TWP 1
 #endif
 
 namespace fen {

@@ -21,10 +21,9 @@
 
 namespace fen {
 
-struct IoBuf {     // pinned host staging for one slab interior, freed when the call ends
+struct IoBuf {     // view of the context's pinned host staging for one slab interior (allocated once, fen_ctx::io_host)
     double* h = nullptr;
     size_t n = 0;
-    ~IoBuf() { if (h) cudaFreeHost(h); }
 };
 
 static size_t slab_elems(fen_ctx* c) { return (size_t)c->L.nx * c->L.ny * c->L.nzl; }
@@ -61,7 +60,16 @@ static int io_begin(fen_ctx* c, const char* path, bool write, int nfields, int* 
     if (!c || !path) return set_error(FEN_ERR_ARG, "null argument");
     FEN_CUDA(cudaSetDevice(c->device));
     b.n = slab_elems(c);
-    FEN_CUDA(cudaMallocHost(&b.h, b.n * sizeof(double)));
+    if (c->io_host_n < b.n) {
+        // first I/O call of this context (or a larger slab): the only allocation the I/O path ever makes.  Like every
+        // allocation it synchronises the device, so on several ranks call the first save / load between steps, after a
+        // caller-side barrier -- as the reference's collective MPI-IO calls are (solver.f90:160, :244)
+        if (c->io_host) cudaFreeHost(c->io_host);
+        c->io_host = nullptr; c->io_host_n = 0;
+        FEN_CUDA(cudaMallocHost(&c->io_host, b.n * sizeof(double)));
+        c->io_host_n = b.n;
+    }
+    b.h = c->io_host;
     *fd = write ? open(path, O_CREAT | O_WRONLY, 0644) : open(path, O_RDONLY);
     if (*fd < 0) return set_error(FEN_ERR_ARG, "cannot open %s: %s", path, strerror(errno));
     if (write && c->g.rank == 0) {
@@ -156,8 +164,8 @@ int fen_gpu_load_state(fen_ctx* c, const char* filename) {
 int fen_gpu_save_fields(fen_ctx* c, int step, const char* dir) {
     if (!c || !c->solver_init) return set_error(FEN_ERR_STATE, "init_solver has not been called");
     if (!dir) dir = "data";
-    int tmp = -1;
-    FEN_TRY(fen_gpu_scalar_allocate(c, 1, FEN_LOC_C, &tmp));
+    if (c->io_tmp < 0) FEN_TRY(fen_gpu_scalar_allocate(c, 1, FEN_LOC_C, &c->io_tmp));   // kept for the next call
+    const int tmp = c->io_tmp;
     const char* names[3] = {"vx", "vy", "vz"};
     const Layout& L = c->L;
     const long long back[3] = {1, L.sy, L.sz};
@@ -181,7 +189,6 @@ int fen_gpu_save_fields(fen_ctx* c, int step, const char* dir) {
         snprintf(path, sizeof(path), "%s/vof_%07d.raw", dir, step);
         r = fen_gpu_scalar_write(c, FEN_VOF, path);
     }
-    fen_gpu_scalar_destroy(c, tmp);
     return r;
 }
 

@@ -304,149 +304,12 @@ __global__ void __launch_bounds__(NL* FftPlan<Lf>::T) k_fft_solve(LArgs a, ScArg
 // flight before the first butterfly.
 // =================================================================================================
 
-template <int M, bool DIV>
-__global__ void __launch_bounds__(XR* FftPlan<M>::T, (XR * FftPlan<M>::T <= 1024) ? 1024 / (XR * FftPlan<M>::T) : 1) k_fft_x_r2c_r(XArgs a, DivArgs dv) {
-    extern __shared__ double2 s[];
-    constexpr int T = FftPlan<M>::T;
-    constexpr int NT = XR * T;
-    const int tid = threadIdx.x;
-    const int row = tid % XR, t = tid / XR;
-    const int row0 = a.r0 + blockIdx.x * XR;
-    double2 v[8];
-    {
-        const int r = row0 + row;
-        const bool valid = r < a.nrows;
-        const int j = valid ? r % a.ny : 0, k = valid ? r / a.ny : 0;
-        const long long c0 = a.L.idx(1, j + 1, k + 1);
-        if (DIV) {
-#pragma unroll
-            for (int m = 0; m < 8; ++m)
-                v[m] = valid ? div_pair(dv, a.L, c0 + 2 * (t + m * T)) : make_double2(0.0, 0.0);
-        } else {
-            const double2* src = reinterpret_cast<const double2*>(a.f + c0);
-#pragma unroll
-            for (int m = 0; m < 8; ++m) v[m] = valid ? src[t + m * T] : make_double2(0.0, 0.0);
-        }
-    }
-    fft_regs<M, -1, false>(v, s, XIS, row, t, a.tw);
-    // post-process pairs (k, M-k) and write X[0..M]
-    constexpr int NP = M / 2 + 1;
-    for (int e = tid; e < XR * NP; e += NT) {
-        const int rw = e / NP, k = e - rw * NP;
-        const int r = row0 + rw;
-        if (r >= a.nrows) continue;
-        const int km = M - k;
-        const double2 zk = s[(k % M) * XIS + rw];
-        const double2 zm = s[(km % M) * XIS + rw];
-        double2* dst = a.C + (size_t)a.PC * r;
-        {   // X[k] = (Zk + conj Zm)/2 + w_k (Zk - conj Zm)/(2i)
-            const double2 E = make_double2(0.5 * (zk.x + zm.x), 0.5 * (zk.y - zm.y));
-            const double2 O = make_double2(0.5 * (zk.y + zm.y), -0.5 * (zk.x - zm.x));
-            const double2 w = __ldg(&a.twr[k]);
-            const double2 X = cadd(E, cmul(w, O));
-            dst[k] = make_double2(X.x * a.scale, X.y * a.scale);
-        }
-        if (km != k) {
-            const double2 E = make_double2(0.5 * (zm.x + zk.x), 0.5 * (zm.y - zk.y));
-            const double2 O = make_double2(0.5 * (zm.y + zk.y), -0.5 * (zm.x - zk.x));
-            const double2 w = __ldg(&a.twr[km]);
-            const double2 X = cadd(E, cmul(w, O));
-            dst[km] = make_double2(X.x * a.scale, X.y * a.scale);
-        }
-    }
-}
-
-template <int M>
-__global__ void __launch_bounds__(XR* FftPlan<M>::T, (XR * FftPlan<M>::T <= 1024) ? 1024 / (XR * FftPlan<M>::T) : 1) k_fft_x_c2r_r(XArgs a) {
-    extern __shared__ double2 s[];
-    constexpr int T = FftPlan<M>::T;
-    const int tid = threadIdx.x;
-    const int row = tid % XR, t = tid / XR;
-    const int r = a.r0 + blockIdx.x * XR + row;
-    const bool valid = r < a.nrows;
-    const double2* X = a.C + (size_t)a.PC * (valid ? r : 0);
-    double2 v[8];
-#pragma unroll
-    for (int m = 0; m < 8; ++m) {
-        // Z[k] = (Xk + conj Xm) + i conj(w_k) (Xk - conj Xm),  m = M - k, w_k = exp(-2 pi i k / N)
-        const int k = t + m * T;
-        double2 xk = X[k], xm = X[M - k];
-        if (k == 0) { xk.y = 0.0; xm.y = 0.0; }        // c2r ignores the imaginary part of DC / Nyquist
-        const double2 E = make_double2(xk.x + xm.x, xk.y - xm.y);
-        const double2 D = make_double2(xk.x - xm.x, xk.y + xm.y);
-        const double2 O = cmul(cconj(__ldg(&a.twr[k])), D);
-        v[m] = make_double2(E.x - O.y, E.y + O.x);
-    }
-    fft_regs<M, +1, true>(v, s, XIS, row, t, a.tw);
-    if (!valid) return;
-    const int j = r % a.ny, k3 = r / a.ny;
-    double* frow = a.f + a.L.idx(1, j + 1, k3 + 1);
-#pragma unroll
-    for (int m = 0; m < 8; ++m) {
-        const int idx = t + m * T;
-        reinterpret_cast<double2*>(frow)[idx] = v[m];
-        // periodic x ghosts of the row (scalar.f90:257,276): every variant built here is periodic in x
-        if (idx == 0) frow[2 * M] = v[m].x;
-        if (idx == M - 1) frow[-1] = v[m].y;
-    }
-}
-
 // ---- x passes with one warp per row ("padded rows", fft_core.cuh: spos<true>) --------------------------------
 // Thread (row, t) owns elements t + m*T of its row, so every global access of a warp is one contiguous 512-byte
 // run AND the transform runs on the register path; the line-major padded shared-memory layout keeps the Stockham
-// exchanges bank-conflict free (proved by tests/cpu/test_fft_core.cu).
-template <int M, bool DIV>
-__global__ void __launch_bounds__(XR* FftPlan<M>::T, (XR * FftPlan<M>::T <= 1024) ? 1024 / (XR * FftPlan<M>::T) : 1)
-k_fft_x_r2c_w(XArgs a, DivArgs dv) {
-    extern __shared__ double2 s[];
-    constexpr int T = FftPlan<M>::T;
-    constexpr int RS = M + M / 8 + 1;
-    const int tid = threadIdx.x;
-    const int row = tid / T, t = tid % T;
-    const int row0 = a.r0 + blockIdx.x * XR;
-    double2 v[8];
-    {
-        const int r = row0 + row;
-        const bool valid = r < a.nrows;
-        const int j = valid ? r % a.ny : 0, k = valid ? r / a.ny : 0;
-        const long long c0 = a.L.idx(1, j + 1, k + 1);
-#pragma unroll
-        for (int m = 0; m < 8; ++m) {
-            if (DIV) v[m] = div_pair(dv, a.L, c0 + 2 * (t + m * T));
-            else v[m] = reinterpret_cast<const double2*>(a.f + c0)[t + m * T];
-            if (!valid) v[m] = make_double2(0.0, 0.0);
-        }
-    }
-    fft_regs<M, -1, false, false, true>(v, s, RS, row, t, a.tw);
-    // pairs (k, M-k):  X[k] = (Zk + conj Zm)/2 + w_k (Zk - conj Zm)/(2i)
-    auto pair_out = [&](int rw, int k) {
-        const int r = row0 + rw;
-        if (r >= a.nrows) return;
-        const int km = M - k;
-        const double2 zk = s[spos<true>(k % M, RS, rw)];
-        const double2 zm = s[spos<true>(km % M, RS, rw)];
-        double2* dst = a.C + (size_t)a.PC * r;
-        {
-            const double2 E = make_double2(0.5 * (zk.x + zm.x), 0.5 * (zk.y - zm.y));
-            const double2 O = make_double2(0.5 * (zk.y + zm.y), -0.5 * (zk.x - zm.x));
-            const double2 X = cadd(E, cmul(__ldg(&a.twr[k]), O));
-            dst[k] = make_double2(X.x * a.scale, X.y * a.scale);
-        }
-        if (km != k) {
-            const double2 E = make_double2(0.5 * (zm.x + zk.x), 0.5 * (zm.y - zk.y));
-            const double2 O = make_double2(0.5 * (zm.y + zk.y), -0.5 * (zm.x - zk.x));
-            const double2 X = cadd(E, cmul(__ldg(&a.twr[km]), O));
-            dst[km] = make_double2(X.x * a.scale, X.y * a.scale);
-        }
-    };
-    const int k = tid % (M / 2), rg = tid / (M / 2);
-#pragma unroll
-    for (int q = 0; q < XR / 2; ++q) pair_out(rg + 2 * q, k);
-    if (tid < XR) pair_out(tid, M / 2);
-}
-
-// Row-private r2c: as k_fft_x_r2c_w, but the transform runs with row-level barriers (RSYNC) and twiddle products
-// (TWP), and the pair post-pass is done by the row's own threads -- thread t takes the pairs k = t + m T, m < 4
+// exchanges bank-conflict free (proved by tests/cpu/test_fft_core.cu) and private to the row's threads.
+// Row-private r2c: thread (row, t) computes / loads the elements t + m T of its row (one 512-byte run per warp), the
+// transform runs on the register path with row-level barriers (RSYNC) and twiddle products (TWP), and the pair post-pass is done by the row's own threads -- thread t takes the pairs k = t + m T, m < 4
 // (k < M/2), thread 0 also the self-paired k = M/2 -- so that no block-wide barrier remains.  With one warp per row
 // the stage twiddles of a warp are 32 different table entries per load instruction (the x passes are bound by the
 // L1 / shared-memory data path: 91 % in the r01v capture of the c2r pass), hence the products.
@@ -497,116 +360,10 @@ k_fft_x_r2c_v(XArgs a, DivArgs dv) {
     if (t == 0) pair_out(M / 2);
 }
 
-template <int M>
-__global__ void __launch_bounds__(XR* FftPlan<M>::T, (XR * FftPlan<M>::T <= 1024) ? 1024 / (XR * FftPlan<M>::T) : 1)
-k_fft_x_c2r_w(XArgs a) {
-    extern __shared__ double2 s[];
-    constexpr int T = FftPlan<M>::T;
-    constexpr int RS = M + M / 8 + 1;
-    const int tid = threadIdx.x;
-    const int row0 = a.r0 + blockIdx.x * XR;
-    {
-        double2 x[XR];
-#pragma unroll
-        for (int rw = 0; rw < XR; ++rw) {
-            const int r = row0 + rw;
-            x[rw] = r < a.nrows ? a.C[(size_t)a.PC * r + tid] : make_double2(0.0, 0.0);
-        }
-        double2 xn = make_double2(0.0, 0.0);
-        if (tid < XR && row0 + tid < a.nrows) xn = a.C[(size_t)a.PC * (row0 + tid) + M];
-        if (tid == 0) {
-#pragma unroll
-            for (int rw = 0; rw < XR; ++rw) x[rw].y = 0.0;     // c2r ignores the imaginary part of DC / Nyquist
-        }
-#pragma unroll
-        for (int rw = 0; rw < XR; ++rw) s[spos<true>(tid, RS, rw)] = x[rw];
-        if (tid < XR) s[spos<true>(M, RS, tid)] = make_double2(xn.x, 0.0);
-    }
-    __syncthreads();
-    const int row = tid / T, t = tid % T;
-    double2 v[8];
-#pragma unroll
-    for (int m = 0; m < 8; ++m) {
-        // Z[k] = (Xk + conj Xm) + i conj(w_k) (Xk - conj Xm),  m = M - k, w_k = exp(-2 pi i k / N)
-        const int k = t + m * T;
-        const double2 xk = s[spos<true>(k, RS, row)], xm = s[spos<true>(M - k, RS, row)];
-        const double2 E = make_double2(xk.x + xm.x, xk.y - xm.y);
-        const double2 D = make_double2(xk.x - xm.x, xk.y + xm.y);
-        const double2 O = cmul(cconj(__ldg(&a.twr[k])), D);
-        v[m] = make_double2(E.x - O.y, E.y + O.x);
-    }
-    __syncthreads();                              // the first stage overwrites the staged rows
-    fft_regs<M, +1, true, false, true>(v, s, RS, row, t, a.tw);
-    const int r = row0 + row;
-    if (r >= a.nrows) return;
-    const int j = r % a.ny, k3 = r / a.ny;
-    double* frow = a.f + a.L.idx(1, j + 1, k3 + 1);
-#pragma unroll
-    for (int m = 0; m < 8; ++m) {
-        const int idx = t + m * T;
-        reinterpret_cast<double2*>(frow)[idx] = v[m];
-        if (idx == 0) frow[2 * M] = v[m].x;       // periodic x ghosts (scalar.f90:257,276)
-        if (idx == M - 1) frow[-1] = v[m].y;
-    }
-}
-
-// Row-private form of k_fft_x_c2r_w: the T threads of a row (one warp at M = 256, two at M = 512) load THEIR row,
-// stage it in their own padded shared-memory row, take the (k, M-k) pairs from it and run the transform with
-// row-level barriers only (fft_core.cuh: RSYNC) -- no block-wide barrier anywhere, so the eight rows of a block and
-// the blocks of an SM drift apart and their load, transform and store phases overlap.  (The r01v capture of
-// k_fft_x_c2r_w: 0.59 ms = 55 % of HBM with 26 % issue activity, stall samples spread evenly over the phases between
-// seven block-wide barriers.)  Same arithmetic in the same order.
-template <int M>
-__global__ void __launch_bounds__(XR* FftPlan<M>::T, (XR * FftPlan<M>::T <= 1024) ? 1024 / (XR * FftPlan<M>::T) : 1)
-k_fft_x_c2r_v(XArgs a) {
-    extern __shared__ double2 s[];
-    constexpr int T = FftPlan<M>::T;
-    constexpr int RS = M + M / 8 + 1;
-    const int tid = threadIdx.x;
-    const int row = tid / T, t = tid % T;
-    const int r = a.r0 + blockIdx.x * XR + row;
-    const bool valid = r < a.nrows;
-    {
-        const double2* X = a.C + (size_t)a.PC * (valid ? r : a.r0);
-        double2 x[8];
-#pragma unroll
-        for (int m = 0; m < 8; ++m) x[m] = X[t + m * T];
-        double2 xn = make_double2(0.0, 0.0);
-        if (t == 0) { xn = X[M]; x[0].y = 0.0; xn.y = 0.0; }      // c2r ignores the imaginary part of DC / Nyquist
-#pragma unroll
-        for (int m = 0; m < 8; ++m) s[spos<true>(t + m * T, RS, row)] = x[m];
-        if (t == 0) s[spos<true>(M, RS, row)] = xn;
-    }
-    fft_sync<M, true>(row);
-    double2 v[8];
-#pragma unroll
-    for (int m = 0; m < 8; ++m) {
-        // Z[k] = (Xk + conj Xm) + i conj(w_k) (Xk - conj Xm),  m = M - k, w_k = exp(-2 pi i k / N)
-        const int k = t + m * T;
-        const double2 xk = s[spos<true>(k, RS, row)], xm = s[spos<true>(M - k, RS, row)];
-        const double2 E = make_double2(xk.x + xm.x, xk.y - xm.y);
-        const double2 D = make_double2(xk.x - xm.x, xk.y + xm.y);
-        const double2 O = cmul(cconj(__ldg(&a.twr[k])), D);
-        v[m] = make_double2(E.x - O.y, E.y + O.x);
-    }
-    fft_sync<M, true>(row);                       // the first stage overwrites the staged row
-    fft_regs<M, +1, true, false, true, true>(v, s, RS, row, t, a.tw);
-    if (!valid) return;
-    const int j = r % a.ny, k3 = r / a.ny;
-    double* frow = a.f + a.L.idx(1, j + 1, k3 + 1);
-#pragma unroll
-    for (int m = 0; m < 8; ++m) {
-        const int idx = t + m * T;
-        reinterpret_cast<double2*>(frow)[idx] = v[m];
-        if (idx == 0) frow[2 * M] = v[m].x;       // periodic x ghosts (scalar.f90:257,276)
-        if (idx == M - 1) frow[-1] = v[m].y;
-    }
-}
-
 // Row-private c2r WITHOUT staging: the T threads of a row read X[k] (ascending) and X[M-k] (descending) of their own
 // row straight from global memory -- both are whole 512-byte runs per warp, the second hits the lines the first just
 // brought into L1 -- so the pair pre-pass needs no shared-memory pass and no barrier at all; the transform then runs
-// with row-level barriers (RSYNC).  One shared-memory store and two loads per element fewer than k_fft_x_c2r_w.
+// with row-level barriers (RSYNC).  One shared-memory store and two loads per element fewer than a staged pre-pass.
 template <int M, bool TWP>
 __global__ void __launch_bounds__(XR* FftPlan<M>::T, (XR * FftPlan<M>::T <= 1024) ? 1024 / (XR * FftPlan<M>::T) : 1)
 k_fft_x_c2r_d(XArgs a) {
@@ -638,62 +395,6 @@ k_fft_x_c2r_d(XArgs a) {
     }
     fft_regs<M, +1, true, TWP, true, true>(v, s, RS, row, t, a.tw);
     if (!valid) return;
-    const int j = r % a.ny, k3 = r / a.ny;
-    double* frow = a.f + a.L.idx(1, j + 1, k3 + 1);
-#pragma unroll
-    for (int m = 0; m < 8; ++m) {
-        const int idx = t + m * T;
-        reinterpret_cast<double2*>(frow)[idx] = v[m];
-        if (idx == 0) frow[2 * M] = v[m].x;       // periodic x ghosts (scalar.f90:257,276)
-        if (idx == M - 1) frow[-1] = v[m].y;
-    }
-}
-
-// c2r with a coalesced staging load: rows of C -> shared memory, the pair pre-pass reads (k, M-k) from there
-// into registers, the transform runs register-to-register and the real row is stored straight from registers.
-template <int M>
-__global__ void __launch_bounds__(XR* FftPlan<M>::T, (XR * FftPlan<M>::T <= 1024) ? 1024 / (XR * FftPlan<M>::T) : 1)
-k_fft_x_c2r_s(XArgs a) {
-    extern __shared__ double2 s[];
-    constexpr int T = FftPlan<M>::T;
-    constexpr int NT = XR * T;
-    const int tid = threadIdx.x;
-    const int row0 = a.r0 + blockIdx.x * XR;
-    {
-        // NT == M threads: thread k loads X[k] of the 8 rows (8 independent coalesced loads in flight), thread q < 8
-        // also the Nyquist element X[M] of row q
-        double2 x[XR];
-#pragma unroll
-        for (int rw = 0; rw < XR; ++rw) {
-            const int r = row0 + rw;
-            x[rw] = r < a.nrows ? a.C[(size_t)a.PC * r + tid] : make_double2(0.0, 0.0);
-        }
-        double2 xn = make_double2(0.0, 0.0);
-        if (tid < XR && row0 + tid < a.nrows) xn = a.C[(size_t)a.PC * (row0 + tid) + M];
-        if (tid == 0) {
-#pragma unroll
-            for (int rw = 0; rw < XR; ++rw) x[rw].y = 0.0;     // c2r ignores the imaginary part of DC / Nyquist
-        }
-#pragma unroll
-        for (int rw = 0; rw < XR; ++rw) s[tid * XIS + rw] = x[rw];
-        if (tid < XR) s[M * XIS + tid] = make_double2(xn.x, 0.0);
-    }
-    __syncthreads();
-    const int row = tid % XR, t = tid / XR;
-    double2 v[8];
-#pragma unroll
-    for (int m = 0; m < 8; ++m) {
-        const int k = t + m * T;
-        const double2 xk = s[k * XIS + row], xm = s[(M - k) * XIS + row];
-        const double2 E = make_double2(xk.x + xm.x, xk.y - xm.y);
-        const double2 D = make_double2(xk.x - xm.x, xk.y + xm.y);
-        const double2 O = cmul(cconj(__ldg(&a.twr[k])), D);
-        v[m] = make_double2(E.x - O.y, E.y + O.x);
-    }
-    __syncthreads();                              // the first stage overwrites the staged rows
-    fft_regs<M, +1, true>(v, s, XIS, row, t, a.tw);
-    const int r = row0 + row;
-    if (r >= a.nrows) return;
     const int j = r % a.ny, k3 = r / a.ny;
     double* frow = a.f + a.L.idx(1, j + 1, k3 + 1);
 #pragma unroll
@@ -1309,31 +1010,24 @@ template <int M> static int set_smem_x() {
         FEN_CUDA(cudaFuncSetAttribute(k_fft_x_r2c<M, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
         FEN_CUDA(cudaFuncSetAttribute(k_fft_x_c2r<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
         if constexpr (M >= 64) {
-            FEN_CUDA(cudaFuncSetAttribute(k_fft_x_r2c_r<M, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-            FEN_CUDA(cudaFuncSetAttribute(k_fft_x_r2c_r<M, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-            FEN_CUDA(cudaFuncSetAttribute(k_fft_x_c2r_r<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-            FEN_CUDA(cudaFuncSetAttribute(k_fft_x_c2r_s<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-            FEN_CUDA(cudaFuncSetAttribute(k_fft_x_r2c_w<M, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-            FEN_CUDA(cudaFuncSetAttribute(k_fft_x_r2c_w<M, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-            FEN_CUDA(cudaFuncSetAttribute(k_fft_x_c2r_w<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-            FEN_CUDA(cudaFuncSetAttribute((k_fft_x_r2c_v<M, false, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-            FEN_CUDA(cudaFuncSetAttribute((k_fft_x_r2c_v<M, true, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
             FEN_CUDA(cudaFuncSetAttribute((k_fft_x_r2c_v<M, false, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
             FEN_CUDA(cudaFuncSetAttribute((k_fft_x_r2c_v<M, true, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-            FEN_CUDA(cudaFuncSetAttribute(k_fft_x_c2r_v<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-            FEN_CUDA(cudaFuncSetAttribute(k_fft_x_c2r_d<M, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-            FEN_CUDA(cudaFuncSetAttribute(k_fft_x_c2r_d<M, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+            FEN_CUDA(cudaFuncSetAttribute((k_fft_x_c2r_d<M, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
         }
     }
     return FEN_OK;
 }
 
-// tuning switches; defaults = the fastest measured at 512^3 (profiles/r01f_variants.txt):
-//   FEN_X_R2C: 0 register path   1 staged (coalesced load / rhs compute into shared memory)   [1: 0.91 vs 1.69 ms]
-//   FEN_X_C2R: 0 register path   1 fully staged   2 staged load + register output            [2: 0.72 vs 0.95 ms]
-//   3 (both): one warp per row, padded-row shared-memory layout -- coalesced AND register path  [c2r 0.58 ms; r2c 0.89]
-// Rows are contiguous, so a cooperative coalesced load (one 512-byte run per warp) beats the register path's
-// 64-byte-per-row gathers; the strided y/z passes are the other way round (86 % of HBM with the register path).
+// The x passes, rows contiguous.  M >= 64 (x lengths >= 128): the row-private kernels -- one warp (two at M = 512) owns
+// a row from its coalesced global loads to its coalesced stores, row-level barriers only, stage twiddles as products of
+// three table entries.  History (512^3, one B200; profiles/r01f_variants.txt, r02e/f/g_*.json): the x passes are bound
+// by the L1 / shared-memory data path (91 % busy in the r01v capture of the c2r pass), not by HBM or the barriers:
+//   c2r  staged block-wide 0.72 ms -> warp per row, staged 0.60 -> row-level barriers 0.57 -> no staging (X[k] and
+//        X[M-k] straight from global) 0.55 -> twiddle products 0.47 ms (0.71 of HBM);  M = 512: 0.67 -> 0.52 ms
+//   r2c  staged block-wide 0.87 ms -> row-private + twiddle products 0.86;              M = 512: 0.97 -> 0.90 ms
+// The register path with eight rows interleaved in a warp (64-byte gathers per row: 1.69 ms), a persistent prefetching
+// c2r (0.63 ms) and the fully staged c2r were measured and deleted.
+// FEN_X_R2C=1 / FEN_X_C2R=1 select the block-wide staged kernels (the ones every M < 64 uses) for cross-checks.
 static int x_variant(const char* name, int dflt) {
     const char* e = getenv(name);
     return e ? atoi(e) : dflt;
@@ -1343,35 +1037,18 @@ template <int M> static int launch_x(fen_ctx* c, const XArgs& a, bool fwd, const
     constexpr int T = FftPlan<M>::T;
     const int bytes = (M + 1) * XIS * (int)sizeof(double2);
     FEN_ONCE_PER_DEVICE(c) FEN_TRY(set_smem_x<M>());
-    // c2r: the warp-per-row kernel wins at M = 256 (0.58 vs 0.61 ms), the staged one at M >= 512 (0.66 vs 0.71 ms)
-    // c2r: 7 = row-private, no staging, twiddle products (0.47 ms at M = 256 against 0.60 for the staged warp-per-row
-    // kernel; 0.52 against 0.67 at M = 512: profiles/r02f_*.json)
-    static const int vr2c = x_variant("FEN_X_R2C", 1), vc2r = x_variant("FEN_X_C2R", 7);
+    static const int vr2c = x_variant("FEN_X_R2C", 6), vc2r = x_variant("FEN_X_C2R", 7);
     dim3 grid((a.nrows - a.r0 + XR - 1) / XR), block(XR * T);
     DivArgs none{};
     bool done = false;
     if constexpr (M >= 64) {
-        if (fwd && vr2c == 0) {
-            if (dv) FEN_LAUNCH(c, "fft_x_r2c_div", k_fft_x_r2c_r<M, true><<<grid, block, bytes, c->stream>>>(a, *dv));
-            else FEN_LAUNCH(c, "fft_x_r2c", k_fft_x_r2c_r<M, false><<<grid, block, bytes, c->stream>>>(a, none));
+        if (!fwd && vc2r != 1) {
+            FEN_LAUNCH(c, "fft_x_c2r", k_fft_x_c2r_d<M, true><<<grid, block, bytes, c->stream>>>(a));
             done = true;
         }
-        if (!fwd && vc2r == 0) { FEN_LAUNCH(c, "fft_x_c2r", k_fft_x_c2r_r<M><<<grid, block, bytes, c->stream>>>(a)); done = true; }
-        if (!fwd && vc2r == 2) { FEN_LAUNCH(c, "fft_x_c2r", k_fft_x_c2r_s<M><<<grid, block, bytes, c->stream>>>(a)); done = true; }
-        if (!fwd && vc2r == 3) { FEN_LAUNCH(c, "fft_x_c2r", k_fft_x_c2r_w<M><<<grid, block, bytes, c->stream>>>(a)); done = true; }
-        if (!fwd && vc2r == 5) { FEN_LAUNCH(c, "fft_x_c2r", k_fft_x_c2r_v<M><<<grid, block, bytes, c->stream>>>(a)); done = true; }
-        if (!fwd && vc2r == 6) { FEN_LAUNCH(c, "fft_x_c2r", k_fft_x_c2r_d<M, false><<<grid, block, bytes, c->stream>>>(a)); done = true; }
-        if (!fwd && vc2r == 7) { FEN_LAUNCH(c, "fft_x_c2r", k_fft_x_c2r_d<M, true><<<grid, block, bytes, c->stream>>>(a)); done = true; }
-        if (fwd && (vr2c == 5 || vr2c == 6)) {     // row-private; 6: with twiddle products
-            if (dv && vr2c == 5) FEN_LAUNCH(c, "fft_x_r2c_div", k_fft_x_r2c_v<M, true, false><<<grid, block, bytes, c->stream>>>(a, *dv));
-            else if (dv) FEN_LAUNCH(c, "fft_x_r2c_div", k_fft_x_r2c_v<M, true, true><<<grid, block, bytes, c->stream>>>(a, *dv));
-            else if (vr2c == 5) FEN_LAUNCH(c, "fft_x_r2c", k_fft_x_r2c_v<M, false, false><<<grid, block, bytes, c->stream>>>(a, none));
+        if (fwd && vr2c != 1) {
+            if (dv) FEN_LAUNCH(c, "fft_x_r2c_div", k_fft_x_r2c_v<M, true, true><<<grid, block, bytes, c->stream>>>(a, *dv));
             else FEN_LAUNCH(c, "fft_x_r2c", k_fft_x_r2c_v<M, false, true><<<grid, block, bytes, c->stream>>>(a, none));
-            done = true;
-        }
-        if (fwd && vr2c == 3) {
-            if (dv) FEN_LAUNCH(c, "fft_x_r2c_div", k_fft_x_r2c_w<M, true><<<grid, block, bytes, c->stream>>>(a, *dv));
-            else FEN_LAUNCH(c, "fft_x_r2c", k_fft_x_r2c_w<M, false><<<grid, block, bytes, c->stream>>>(a, none));
             done = true;
         }
     }
@@ -1764,6 +1441,13 @@ static int solve_blocked(fen_ctx* c, Poisson* p, bool ppp, XArgs xa, bool fuse_r
     cudaStream_t S = c->stream, T = (c->profiling || !p->aux) ? c->stream : p->aux;
     const bool two = T != S;
     const int nq = p->nchunk;
+    // grid cap of the persistent transposing kernels while they share the GPU with the pass on the other stream
+    // (FEN_SLAB_SMS = SMs' worth of their blocks, default 64: ~50 blocks of 1024-point tiles keep the link full)
+    static const int cap_sms = getenv("FEN_SLAB_SMS") ? std::max(1, atoi(getenv("FEN_SLAB_SMS"))) : 64;
+    auto cap = [&](int Lf, long long ntiles) {
+        const long long per_sm = Lf >= 1024 ? 1 : 1024 / Lf;
+        return (unsigned)std::min<long long>(ntiles, two ? cap_sms * per_sm : ntiles);
+    };
     BAddr none{nullptr, 0, 0, 0, 0, 0};
     BulkDst df;                                                           // -> Cz[((g*nz + k)*nyl + jl)*8 + kxi]
     memset(&df, 0, sizeof(df));
@@ -1782,7 +1466,9 @@ static int solve_blocked(fen_ctx* c, Poisson* p, bool ppp, XArgs xa, bool fuse_r
             FEN_CUDA(cudaStreamWaitEvent(T, p->ev_piece[q], 0));
         }
         BAddr rows_in{p->C, 8, (long long)p->PC * ny, p->PC, 0, z0};      // C[kx + PC*(j + ny*zl)]: lines over j
-        FEN_TRY(dispatch_bs(c, g.ny, 0, rows_in, none, p->tw_y, sy, nullptr, &df, dim3(NG, (unsigned)(z1 - z0)), T));
+        df.ng = NG; df.no = z1 - z0;
+        FEN_TRY(dispatch_bs(c, g.ny, 0, rows_in, none, p->tw_y, sy, nullptr, &df,
+                            dim3(cap(g.ny, (long long)NG * (z1 - z0))), T));
     }
     if (two) {
         FEN_CUDA(cudaEventRecord(p->ev_join, T));
@@ -1802,7 +1488,9 @@ static int solve_blocked(fen_ctx* c, Poisson* p, bool ppp, XArgs xa, bool fuse_r
             SolveArgs sa;
             sa.tw = p->tw_z; sa.lx = p->mwn_x; sa.lo = p->mwn_y; sa.ll = p->mwn_z;
             sa.norm = f32((long long)g.nx * g.ny * g.nz); sa.ow0 = g.rank * (int)nyl;
-            FEN_TRY(dispatch_bs(c, g.nz, 2, zin, none, nullptr, 1.0, &sa, &db, dim3(g1 - g0, (unsigned)nyl), S));
+            db.ng = g1 - g0; db.no = (int)nyl;
+            FEN_TRY(dispatch_bs(c, g.nz, 2, zin, none, nullptr, 1.0, &sa, &db,
+                                dim3(cap(g.nz, (long long)(g1 - g0) * nyl)), S));
         } else {
             TArgs t;
             t.C = p->Cz; t.c1 = p->c1; t.sl = nyl * 8; t.so = nz * nyl * 8; t.n = g.nz; t.npc = p->PC;

@@ -33,11 +33,16 @@ struct BAddr {
     long long gs, os, is;
     int g0, ob;
 };
-// destination of a tile: rank r receives idx in [r*blk, (r+1)*blk) as one run at peer[r] + gs*g + os*(o0 + o)
+// destination of a tile: rank r receives idx in [r*blk, (r+1)*blk) as one run at peer[r] + gs*g + os*(o0 + o).
+// The transposing kernels are PERSISTENT: gridDim.x blocks walk the ng x no tiles of a launch (tile = granule fastest).
+// Their blocks spend most of their life waiting for the link, and a block of 1024 threads with 128 KB of shared memory
+// owns its SM; capping the grid (a few dozen blocks keep the link full) leaves the other SMs to the HBM-bound pass of
+// the neighbouring piece that runs beside it on the second stream (poisson.cu: solve_blocked).
 struct BulkDst {
     double2* peer[FEN_MAX_RANKS];
     long long gs, os;
     int o0, blk, P, rank;
+    int ng, no;            // tiles of this launch: granules x outer indices
 };
 
 __device__ __forceinline__ void bulk_store(void* gdst, const void* ssrc, unsigned bytes) {
@@ -50,7 +55,14 @@ __device__ __forceinline__ void bulk_commit_wait() {
 }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
-// the tile sits in shared memory as s[idx * 8 + line]; threads 0 .. P-1 each ship one destination's run
+__device__ __forceinline__ void bulk_commit_wait_read() {
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // the source has been read: the tile may be reused
+}
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
+// the tile sits in shared memory as s[idx * 8 + line]; threads 0 .. P-1 each ship one destination's run and wait until
+// the copy engine has read it; the barrier at the end releases the tile for the block's next one
 __device__ __forceinline__ void bulk_scatter_tile(const double2* s, const BulkDst& d, int g, int o, int tid) {
     fence_async_smem();
     __syncthreads();
@@ -58,8 +70,9 @@ __device__ __forceinline__ void bulk_scatter_tile(const double2* s, const BulkDs
         const int r = (d.rank + 1 + tid) % d.P;                  // own rank last
         double2* dst = d.peer[r] + d.gs * g + d.os * (d.o0 + o);
         bulk_store(dst, s + (size_t)r * d.blk * 8, (unsigned)(d.blk * 8 * sizeof(double2)));
-        bulk_commit_wait();
+        bulk_commit_wait_read();
     }
+    __syncthreads();
 }
 
 template <int Lf, int DIR>
@@ -69,15 +82,18 @@ k_fft_lines_bs(BAddr in, const double2* tw, double scale, BulkDst d) {
     constexpr int T = Lf / 8;
     const int tid = threadIdx.x;
     const int line = tid & 7, t = tid >> 3;
-    const int g = in.g0 + blockIdx.x, o = in.ob + blockIdx.y;
-    const double2* base = in.p + in.gs * g + in.os * o + line;
-    double2 v[8];
+    for (int tile = blockIdx.x; tile < d.ng * d.no; tile += gridDim.x) {
+        const int g = in.g0 + tile % d.ng, o = in.ob + tile / d.ng;
+        const double2* base = in.p + in.gs * g + in.os * o + line;
+        double2 v[8];
 #pragma unroll
-    for (int m = 0; m < 8; ++m) v[m] = base[in.is * (t + m * T)];
-    fft_regs<Lf, DIR, true, kStridedTwp>(v, s, 8, line, t, tw);
+        for (int m = 0; m < 8; ++m) v[m] = base[in.is * (t + m * T)];
+        fft_regs<Lf, DIR, true, kStridedTwp>(v, s, 8, line, t, tw);
 #pragma unroll
-    for (int m = 0; m < 8; ++m) s[(t + m * T) * 8 + line] = make_double2(v[m].x * scale, v[m].y * scale);
-    bulk_scatter_tile(s, d, g, o, tid);
+        for (int m = 0; m < 8; ++m) s[(t + m * T) * 8 + line] = make_double2(v[m].x * scale, v[m].y * scale);
+        bulk_scatter_tile(s, d, g, o, tid);
+    }
+    if (tid < d.P) bulk_wait_all();          // every write of this block has landed before the block retires
 }
 
 struct SolveArgs {
@@ -94,30 +110,33 @@ k_fft_solve_bs(BAddr in, SolveArgs a, BulkDst d) {
     constexpr int T = Lf / 8;
     const int tid = threadIdx.x;
     const int line = tid & 7, t = tid >> 3;
-    const int g = in.g0 + blockIdx.x, o = in.ob + blockIdx.y;
-    double2 v[8];
-    {
-        const double2* base = in.p + in.gs * g + in.os * o + line;
+    const double inorm = 1.0 / a.norm;
+    for (int tile = blockIdx.x; tile < d.ng * d.no; tile += gridDim.x) {
+        const int g = in.g0 + tile % d.ng, o = in.ob + tile / d.ng;
+        double2 v[8];
+        {
+            const double2* base = in.p + in.gs * g + in.os * o + line;
 #pragma unroll
-        for (int m = 0; m < 8; ++m) v[m] = base[in.is * (t + m * T)];
-    }
-    fft_regs<Lf, -1, true, kStridedTwp>(v, s, 8, line, t, a.tw);
-    {   // poisson.f90:992 then :998-1001; see k_fft_solve_r for the rounding argument (power-of-two norm)
-        double lxo = __ldg(&a.lx[g * 8 + line]);
-        if (a.lo) lxo = lxo + __ldg(&a.lo[a.ow0 + o]);
-        const double inorm = 1.0 / a.norm;
-#pragma unroll
-        for (int m = 0; m < 8; ++m) {
-            const double lam = lxo + __ldg(&a.ll[t + m * T]);
-            const double rl = lam == 0.0 ? 0.0 : inorm / lam;
-            v[m].x *= rl;
-            v[m].y *= rl;
+            for (int m = 0; m < 8; ++m) v[m] = base[in.is * (t + m * T)];
         }
-    }
-    fft_regs<Lf, +1, true, kStridedTwp>(v, s, 8, line, t, a.tw);
+        fft_regs<Lf, -1, true, kStridedTwp>(v, s, 8, line, t, a.tw);
+        {   // poisson.f90:992 then :998-1001; see k_fft_solve_r for the rounding argument (power-of-two norm)
+            double lxo = __ldg(&a.lx[g * 8 + line]);
+            if (a.lo) lxo = lxo + __ldg(&a.lo[a.ow0 + o]);
 #pragma unroll
-    for (int m = 0; m < 8; ++m) s[(t + m * T) * 8 + line] = v[m];
-    bulk_scatter_tile(s, d, g, o, tid);
+            for (int m = 0; m < 8; ++m) {
+                const double lam = lxo + __ldg(&a.ll[t + m * T]);
+                const double rl = lam == 0.0 ? 0.0 : inorm / lam;
+                v[m].x *= rl;
+                v[m].y *= rl;
+            }
+        }
+        fft_regs<Lf, +1, true, kStridedTwp>(v, s, 8, line, t, a.tw);
+#pragma unroll
+        for (int m = 0; m < 8; ++m) s[(t + m * T) * 8 + line] = v[m];
+        bulk_scatter_tile(s, d, g, o, tid);
+    }
+    if (tid < d.P) bulk_wait_all();
 }
 
 // transform with separate source and destination arrays (y inverse: blocked y-slab in, row layout out)

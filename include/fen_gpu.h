@@ -191,7 +191,10 @@ int fen_gpu_update_pressure(fen_ctx* ctx);                             /* navier
 int fen_gpu_checks(fen_ctx* ctx, double dt);                           /* navier_stokes.f90:570 */
 
 /* ---- raw field files in the reference's on-disk format (global interior array, x fastest, real(dp), no header;
- * 2decomp MPI-IO).  Collective over the ranks; every rank reads / writes its own z-slab byte range. ------------- */
+ * 2decomp MPI-IO).  Collective over the ranks; every rank reads / writes its own z-slab byte range.  As with the
+ * reference's MPI-IO calls the caller synchronises around them: a file written by save_* is complete for the OTHER
+ * ranks only after a caller-side barrier, and the first I/O call of a context allocates its (kept) staging buffers,
+ * which synchronises the device -- make it between steps, when no rank is inside a collective. ------------------ */
 int fen_gpu_scalar_write(fen_ctx* ctx, int field, const char* filename);   /* scalar%write, scalar.f90:428 */
 int fen_gpu_scalar_read(fen_ctx* ctx, int field, const char* filename);    /* scalar%read,  scalar.f90:400 */
 /* save_state / load_state (solver.f90:160, :244): p, v_x, v_y, dv_o_x, dv_o_y, [v_z, dv_o_z] in one file; load also

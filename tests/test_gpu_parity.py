@@ -558,6 +558,22 @@ def test_one_step_512_matches_c_oracle(n):
     Gg.destroy()
 
 
+def test_staged_x_passes_match_oracle():
+    """FEN_X_R2C=1 FEN_X_C2R=1: the block-wide staged x kernels (what every x length below 128 uses) at the sizes where
+    the row-private kernels are the default -- the cross-check switch of poisson.cu: launch_x -- in a child process,
+    because the switches are read once per process."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, FEN_X_R2C="1", FEN_X_C2R="1")
+    r = subprocess.run([sys.executable, "-m", "pytest", "-q", "-x", "-m", "gpu", "tests/test_gpu_parity.py", "-k",
+                        "test_one_step_tgv3d_matches_oracle or test_poisson_variants_match_oracle or "
+                        "test_steps_tgv2d_matches_oracle_config1"], cwd=root, env=env, capture_output=True, text=True,
+                       timeout=900)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+
+
 def test_c_driver_runs():
     """examples/tgv_driver.c: the 2-D Taylor-Green case driven from plain C through the C ABI; the error against the
     analytic solution is the second-order one the reference's test plots (postpro.py:48-62)."""
