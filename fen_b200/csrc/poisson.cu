@@ -58,6 +58,15 @@ struct Poisson {
     cudaEvent_t ev_piece[FEN_MAX_CHUNKS] = {};
     cudaEvent_t ev_join = nullptr;
     int nchunk = 1;
+    // copy-engine form (FEN_SLAB_DMA): the kernels write a local send buffer laid out like the receivers' regions and
+    // pitched peer copies on `cp` streams move it while the SMs work on the next piece
+    bool dma = false;
+    double2* Sx = nullptr;          // send buffer (forward: [r][g][zl][jl][8], backward: [r][g][jl][zl][8])
+    static constexpr int kCopyStreams = 4;
+    int ncp = kCopyStreams;         // copy streams in use (FEN_SLAB_COPY_STREAMS)
+    cudaStream_t cp[kCopyStreams] = {};
+    cudaEvent_t ev_cp[kCopyStreams] = {};
+    cudaEvent_t ev_sig[FEN_MAX_CHUNKS] = {};
     double2* peerC[FEN_MAX_RANKS] = {};
     double2* peerCz[FEN_MAX_RANKS] = {};
 };
@@ -574,6 +583,8 @@ struct TArgs {
     // jl = e / 8 at C + so * g + e (so = granule stride, sl = plane stride nyl * 8)
     int blocked = 0;
     int g0 = 0;            // first granule of this launch (blocked layout; chunked launches)
+    int to_send = 0;       // back substitution: the solution goes to send_dst(sd, ...) (copy-engine transposes)
+    SendDst sd;
 };
 struct TSys {              // one thread's system
     long long off;         // offset of its first element in C / c1
@@ -692,13 +703,17 @@ __global__ void __launch_bounds__(128) k_thomas_bwd(TArgs g) {
     if (!sy.valid) return;
     const double2* C = g.C + sy.off;
     const double* c1t = g.c1 + sy.off;
-    double2* O = g.C + sy.off;
-    const long long osl = g.sl;
+    // where element l of the solution goes: in place, or (copy-engine transposes) to the slot of the send buffer /
+    // of this rank's own y-slab array that the transposed layout assigns to it
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    auto out = [&](int l) -> double2* {
+        return g.to_send ? send_dst(g.sd, g.g0 + blockIdx.y, e >> 3, l, e & 7) : g.C + sy.off + g.sl * l;
+    };
     const int n = g.n;
     const bool mean_line = g.mean && sy.kx == 0 && sy.lo_idx == 0;
     double2 x = C[g.sl * (n - 1)];                                  // :1124-1128
     double acc = x.x;
-    O[osl * (n - 1)] = x;
+    *out(n - 1) = x;
     constexpr int U = 8;
     for (int l0 = n - 2; l0 >= 0; l0 -= U) {
         double2 d[U];
@@ -715,15 +730,15 @@ __global__ void __launch_bounds__(128) k_thomas_bwd(TArgs g) {
                 x = make_double2(__dsub_rn(d[r].x, __dmul_rn(cc[r], x.x)),
                                  __dsub_rn(d[r].y, __dmul_rn(cc[r], x.y)));
                 acc += x.x;
-                O[osl * (l0 - r)] = x;
+                *out(l0 - r) = x;
             }
     }
     if (mean_line) {
         const double mean = acc / (double)n;
         for (int l = 0; l < n; ++l) {
-            double2 v = O[osl * l];
+            double2 v = *out(l);
             v.x -= mean;
-            O[osl * l] = v;
+            *out(l) = v;
         }
     }
 }
@@ -961,6 +976,12 @@ void poisson_destroy(fen_ctx* c) {
         if (p->C) cudaFree(p->C);
     }
     if (p->Cr) cudaFree(p->Cr);
+    for (int k = 0; k < Poisson::kCopyStreams; ++k) {
+        if (p->cp[k]) { cudaStreamSynchronize(p->cp[k]); cudaStreamDestroy(p->cp[k]); }
+        if (p->ev_cp[k]) cudaEventDestroy(p->ev_cp[k]);
+    }
+    for (int q = 0; q < FEN_MAX_CHUNKS; ++q) if (p->ev_sig[q]) cudaEventDestroy(p->ev_sig[q]);
+    if (p->Sx) cudaFree(p->Sx);
     if (p->aux) { cudaStreamSynchronize(p->aux); cudaStreamDestroy(p->aux); }
     for (int q = 0; q < FEN_MAX_CHUNKS; ++q) if (p->ev_piece[q]) cudaEventDestroy(p->ev_piece[q]);
     if (p->ev_join) cudaEventDestroy(p->ev_join);
@@ -1283,19 +1304,36 @@ static int poisson_build(fen_ctx* c) {
             const size_t nC = (size_t)p->PC * g.ny * p->nzl;
             FEN_CUDA(cudaMalloc(&p->Cr, nC * sizeof(double2)));
             FEN_CUDA(cudaMemsetAsync(p->Cr, 0, nC * sizeof(double2), c->stream));
-            // FEN_SLAB_CHUNKS = pieces of the overlapped transposes (1 = no overlap, one stream); default 4
+            // FEN_SLAB_DMA: 1 = the transposes travel by the copy engines, 0 = bulk stores by the kernels' own blocks;
+            // default: copy engines from 4 ranks on (solve_blocked's header)
+            const char* ed = getenv("FEN_SLAB_DMA");
+            p->dma = ed ? atoi(ed) != 0 : g.nranks >= 4;
+            // FEN_SLAB_CHUNKS = pieces of the overlapped transposes (1 = no overlap); default 4 from 4 ranks on, else 1
+            // (bulk-store form on 2 ranks: nothing to gain from overlap there, profiles/r02h_*.json)
             const char* e = getenv("FEN_SLAB_CHUNKS");
-            p->nchunk = std::max(1, std::min(FEN_MAX_CHUNKS, e ? atoi(e) : 4));
+            p->nchunk = std::max(1, std::min(FEN_MAX_CHUNKS, e ? atoi(e) : (g.nranks >= 4 ? 4 : 1)));
             p->nchunk = std::min(p->nchunk, std::min(p->nzl, p->PC / 8));
-            if (p->nchunk > 1) {
+            if (p->nchunk > 1 && !p->dma) {
                 int lo = 0, hi = 0;
                 FEN_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
                 // the link-bound pieces get the higher priority: their blocks mostly wait, the HBM-bound pass fills in
                 FEN_CUDA(cudaStreamCreateWithPriority(&p->aux, cudaStreamNonBlocking, hi));
             }
-            for (int q = 0; q < FEN_MAX_CHUNKS; ++q)
+            for (int q = 0; q < FEN_MAX_CHUNKS; ++q) {
                 FEN_CUDA(cudaEventCreateWithFlags(&p->ev_piece[q], cudaEventDisableTiming));
+                FEN_CUDA(cudaEventCreateWithFlags(&p->ev_sig[q], cudaEventDisableTiming));
+            }
             FEN_CUDA(cudaEventCreateWithFlags(&p->ev_join, cudaEventDisableTiming));
+            if (p->dma) {
+                FEN_CUDA(cudaMalloc(&p->Sx, nC * sizeof(double2)));
+                FEN_CUDA(cudaMemsetAsync(p->Sx, 0, nC * sizeof(double2), c->stream));
+                const char* es = getenv("FEN_SLAB_COPY_STREAMS");
+                p->ncp = std::max(1, std::min(Poisson::kCopyStreams, es ? atoi(es) : Poisson::kCopyStreams));
+                for (int k = 0; k < p->ncp; ++k) {
+                    FEN_CUDA(cudaStreamCreateWithFlags(&p->cp[k], cudaStreamNonBlocking));
+                    FEN_CUDA(cudaEventCreateWithFlags(&p->ev_cp[k], cudaEventDisableTiming));
+                }
+            }
         }
     } else {
         const size_t nC = (size_t)p->PC * g.ny * p->nzl;
@@ -1398,61 +1436,112 @@ static int thomas_2d(fen_ctx* c, const TArgs& t) {
 }
 
 // ---- blocked slab path (slab_bulk.cuh): ppp / ppn on several ranks, 64..1024-point transform lines ----------------
-template <int Lf> static int launch_bs(fen_ctx* c, int what, const BAddr& in, const BAddr& out, const double2* tw,
-                                       double scale, const SolveArgs* sa, const BulkDst* d, dim3 grid, cudaStream_t st) {
+// what: 0 y forward + transpose, 1 y inverse (blocked in, rows out), 2 z solve + transpose; bulk: stores by the block
+// itself (cp.async.bulk to the peers), else into the send buffer for the copy engines
+template <int Lf> static int launch_bs(fen_ctx* c, int what, bool bulk, const BAddr& in, const BAddr& out, const double2* tw,
+                                       double scale, const SolveArgs* sa, const BulkDst* d, const SendDst* sd, dim3 grid,
+                                       cudaStream_t st) {
     const int bytes = Lf * 8 * (int)sizeof(double2);
     FEN_ONCE_PER_DEVICE(c) {
-        FEN_CUDA(cudaFuncSetAttribute(k_fft_lines_bs<Lf, -1>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-        FEN_CUDA(cudaFuncSetAttribute(k_fft_solve_bs<Lf>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-        FEN_CUDA(cudaFuncSetAttribute(k_fft_lines_io<Lf, +1>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+        FEN_CUDA(cudaFuncSetAttribute((k_fft_lines_bs<Lf, -1, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+        FEN_CUDA(cudaFuncSetAttribute((k_fft_lines_bs<Lf, -1, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+        FEN_CUDA(cudaFuncSetAttribute((k_fft_solve_bs<Lf, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+        FEN_CUDA(cudaFuncSetAttribute((k_fft_solve_bs<Lf, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+        FEN_CUDA(cudaFuncSetAttribute((k_fft_lines_io<Lf, +1>), cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
     }
-    if (what == 0) FEN_LAUNCH(c, "fft_lines_fwd_a2a", k_fft_lines_bs<Lf, -1><<<grid, Lf, bytes, st>>>(in, tw, scale, *d));
-    if (what == 1) FEN_LAUNCH(c, "fft_lines_inv", k_fft_lines_io<Lf, +1><<<grid, Lf, bytes, st>>>(in, out, tw, scale));
-    if (what == 2) FEN_LAUNCH(c, "fft_solve_a2a", k_fft_solve_bs<Lf><<<grid, Lf, bytes, st>>>(in, *sa, *d));
+    if (what == 0 && bulk) FEN_LAUNCH(c, "fft_lines_fwd_a2a", (k_fft_lines_bs<Lf, -1, true><<<grid, Lf, bytes, st>>>(in, tw, scale, *d, *sd)));
+    if (what == 0 && !bulk) FEN_LAUNCH(c, "fft_lines_fwd", (k_fft_lines_bs<Lf, -1, false><<<grid, Lf, bytes, st>>>(in, tw, scale, *d, *sd)));
+    if (what == 1) FEN_LAUNCH(c, "fft_lines_inv", (k_fft_lines_io<Lf, +1><<<grid, Lf, bytes, st>>>(in, out, tw, scale)));
+    if (what == 2 && bulk) FEN_LAUNCH(c, "fft_solve_a2a", (k_fft_solve_bs<Lf, true><<<grid, Lf, bytes, st>>>(in, *sa, *d, *sd)));
+    if (what == 2 && !bulk) FEN_LAUNCH(c, "fft_solve", (k_fft_solve_bs<Lf, false><<<grid, Lf, bytes, st>>>(in, *sa, *d, *sd)));
     FEN_CUDA(cudaGetLastError());
     return FEN_OK;
 }
-static int dispatch_bs(fen_ctx* c, int Lf, int what, const BAddr& in, const BAddr& out, const double2* tw, double scale,
-                       const SolveArgs* sa, const BulkDst* d, dim3 grid, cudaStream_t st) {
+static int dispatch_bs(fen_ctx* c, int Lf, int what, bool bulk, const BAddr& in, const BAddr& out, const double2* tw,
+                       double scale, const SolveArgs* sa, const BulkDst* d, const SendDst* sd, dim3 grid, cudaStream_t st) {
     switch (Lf) {
-#define FEN_CASE(l) case l: return launch_bs<l>(c, what, in, out, tw, scale, sa, d, grid, st);
+#define FEN_CASE(l) case l: return launch_bs<l>(c, what, bulk, in, out, tw, scale, sa, d, sd, grid, st);
         FEN_CASE(64) FEN_CASE(128) FEN_CASE(256) FEN_CASE(512) FEN_CASE(1024)
 #undef FEN_CASE
     }
     return set_error(FEN_ERR_STATE, "blocked slab path: line length %d", Lf);
 }
 
-// x r2c -> y forward -> (bulk stores) -> z solve or Thomas -> (bulk stores) -> y inverse into the row array Cr.
+// One piece of a copy-engine transpose: to every peer r one pitched device-to-device copy of `height` rows of `width`
+// bytes (row h of peer r: src0 + r*src_rank + h*spitch  ->  dst[r] + h*dpitch), spread over the copy streams, which first
+// wait for `ready` (the kernel that filled the send buffer).  With per-kernel profiling on, the copies run on the main
+// stream inside one event bracket named `name`.
+static int dma_piece(fen_ctx* c, Poisson* p, const char* name, const char* src0, size_t src_rank, size_t spitch,
+                     char* const* dst, size_t dpitch, size_t width, size_t height, cudaEvent_t ready) {
+    const int P = c->g.nranks, me = c->g.rank;
+    const bool serial = c->profiling;
+    if (!serial) FEN_CUDA(cudaEventRecord(ready, c->stream));
+    int tok = serial ? prof_begin(c, name) : -1;
+    if (!serial) c->launches++;
+    for (int k = 0; k < p->ncp && !serial; ++k) FEN_CUDA(cudaStreamWaitEvent(p->cp[k], ready, 0));
+    for (int q = 1; q < P; ++q) {
+        const int r = (me + q) % P;                                     // staggered: rank + 1 first
+        cudaStream_t st = serial ? c->stream : p->cp[(q - 1) % p->ncp];
+        FEN_CUDA(cudaMemcpy2DAsync(dst[r], dpitch, src0 + (size_t)r * src_rank, spitch, width, height,
+                                   cudaMemcpyDeviceToDevice, st));
+    }
+    if (serial) prof_end(c, tok);
+    return FEN_OK;
+}
+// the copy streams' work so far is a dependency of stream `st`
+static int dma_join(fen_ctx* c, Poisson* p, cudaStream_t st) {
+    if (c->profiling) return FEN_OK;                                    // the copies ran on the main stream
+    for (int k = 0; k < p->ncp; ++k) {
+        FEN_CUDA(cudaEventRecord(p->ev_cp[k], p->cp[k]));
+        FEN_CUDA(cudaStreamWaitEvent(st, p->ev_cp[k], 0));
+    }
+    return FEN_OK;
+}
+
+// x r2c -> y forward -> transpose -> z solve or Thomas -> transpose -> y inverse into the row array Cr.
 //
-// The two transposing stages are bound by the link (941 MB out per GPU at 1024^3 on 8: >= 1.2 ms each at the 770 GB/s a
-// peer copy reaches), their blocks spend most of their life waiting for bulk stores to drain, and the passes either
-// side of them are bound by local HBM.  So the work is cut in nchunk pieces and pipelined over two streams:
-//   forward   piece q = z planes:  x r2c(q) on the main stream, y forward + stores(q) on `aux` behind it -- the x pass
-//             of piece q+1 runs while piece q's stores travel;
-//   backward  piece q = granules:  z solve (or Thomas + row shipping) + stores(q) on the main stream, then "piece q is
-//             out" is raised on every peer; `aux` waits until every peer has raised it and runs the y inverse of those
-//             granules while piece q+1 is solved and shipped.
+// The two transposes are bound by the link (941 MB out per GPU at 1024^3 on 8: >= 1.2 ms each at the 770 GB/s a peer
+// copy reaches), the passes either side of them by local HBM.  Two forms, both cut in nchunk pieces (forward: z planes,
+// backward: granules of 8 kx):
+//
+// (a) copy engines (p->dma, the default on >= 4 ranks).  The kernels stay local: the y forward pass and the z solve
+//     write a send buffer laid out like the regions the receivers will hold (SendDst), and one pitched peer copy per
+//     destination moves each piece over NVLink on its own streams -- no SM is involved, so the x pass and y transform
+//     of piece q+1 run at full speed while piece q travels; on the way back the solves of all pieces are queued first
+//     and the y inverse of piece q waits, on the same stream, for "piece q has arrived from everybody".
+// (b) bulk stores (slab_bulk.cuh): the transposing kernel's own blocks ship their tile with cp.async.bulk.  Used on 2
+//     ranks (681 / 671 GB/s, nothing to overlap: the kernels are as much HBM- as link-bound there) and as the A/B
+//     reference of (a): FEN_SLAB_DMA=0.  With nchunk > 1 its pieces overlap with the neighbouring pass on an auxiliary
+//     stream, but at 8 ranks the persistent transposing blocks need >= 96 of the 148 SMs to keep the link full
+//     (profiles/r02i_*.json: 9.26 ms unchunked, 9.07 / 10.13 / 11.14 ms at caps of 96 / 64 / 48 SMs), which is why (a).
 // With per-kernel profiling on (bench.py's kernel table) everything runs on the main stream, piece by piece, so that
 // the event brackets mean what they say; the timed region of the bench runs overlapped.
 static int solve_blocked(fen_ctx* c, Poisson* p, bool ppp, XArgs xa, bool fuse_rhs, const DivArgs* dv) {
     const fen_grid_desc& g = c->g;
     const int NG = p->PC / 8, P = g.nranks;
     const long long ny = g.ny, nz = g.nz, nyl = p->nyl, nzl = p->nzl;
-    cudaStream_t S = c->stream, T = (c->profiling || !p->aux) ? c->stream : p->aux;
+    const bool dma = p->dma;
+    cudaStream_t S = c->stream, T = (c->profiling || !p->aux || dma) ? c->stream : p->aux;
     const bool two = T != S;
     const int nq = p->nchunk;
-    // grid cap of the persistent transposing kernels while they share the GPU with the pass on the other stream
-    // (FEN_SLAB_SMS = SMs' worth of their blocks, default 64: ~50 blocks of 1024-point tiles keep the link full)
-    static const int cap_sms = getenv("FEN_SLAB_SMS") ? std::max(1, atoi(getenv("FEN_SLAB_SMS"))) : 64;
+    // grid cap of the persistent bulk-store kernels while they share the GPU with the pass on the other stream
+    static const int cap_sms = getenv("FEN_SLAB_SMS") ? std::max(1, atoi(getenv("FEN_SLAB_SMS"))) : 96;
     auto cap = [&](int Lf, long long ntiles) {
         const long long per_sm = Lf >= 1024 ? 1 : 1024 / Lf;
         return (unsigned)std::min<long long>(ntiles, two ? cap_sms * per_sm : ntiles);
     };
     BAddr none{nullptr, 0, 0, 0, 0, 0};
+    const size_t GB = 8 * sizeof(double2);                                // bytes of a granule
+    char* dstF[FEN_MAX_RANKS];
+    char* dstB[FEN_MAX_RANKS];
     BulkDst df;                                                           // -> Cz[((g*nz + k)*nyl + jl)*8 + kxi]
     memset(&df, 0, sizeof(df));
     for (int r = 0; r < P; ++r) df.peer[r] = p->peerCz[r];
     df.gs = nz * nyl * 8; df.os = nyl * 8; df.o0 = g.rank * (int)nzl; df.blk = (int)nyl; df.P = P; df.rank = g.rank;
+    SendDst sf;                                                           // send buffer [r][g][zl][jl][8]
+    memset(&sf, 0, sizeof(sf));
+    sf.self = p->Cz; sf.send = p->Sx; sf.gs_self = df.gs; sf.os_self = df.os; sf.o0 = df.o0; sf.sh = log2i((int)nyl);
+    sf.mask = (int)nyl - 1; sf.rank = g.rank; sf.ng_tot = NG; sf.no_tot = (int)nzl;
     const double sy = ppp ? 1.0 : 1.0 / f32(g.ny);                        // poisson.f90:1087
     // ---- forward: pieces of z planes ----
     for (int q = 0; q < nq; ++q) {
@@ -1461,16 +1550,29 @@ static int solve_blocked(fen_ctx* c, Poisson* p, bool ppp, XArgs xa, bool fuse_r
         XArgs xq = xa;
         xq.r0 = z0 * (int)ny; xq.nrows = z1 * (int)ny;
         FEN_TRY(dispatch_x(c, p->M, xq, true, fuse_rhs ? dv : nullptr)); // :965-969 (+ :111-121 when fused)
-        if (two) {
-            FEN_CUDA(cudaEventRecord(p->ev_piece[q], S));
-            FEN_CUDA(cudaStreamWaitEvent(T, p->ev_piece[q], 0));
-        }
         BAddr rows_in{p->C, 8, (long long)p->PC * ny, p->PC, 0, z0};      // C[kx + PC*(j + ny*zl)]: lines over j
         df.ng = NG; df.no = z1 - z0;
-        FEN_TRY(dispatch_bs(c, g.ny, 0, rows_in, none, p->tw_y, sy, nullptr, &df,
-                            dim3(cap(g.ny, (long long)NG * (z1 - z0))), T));
+        if (dma) {
+            FEN_TRY(dispatch_bs(c, g.ny, 0, false, rows_in, none, p->tw_y, sy, nullptr, &df, &sf,
+                                dim3((unsigned)(NG * (z1 - z0))), S));
+            // piece of rank r: rows g = 0 .. NG-1 of (z1 - z0) * nyl granules, at plane rank*nzl + z0 of r's Cz
+            for (int r = 0; r < P; ++r)
+                dstF[r] = reinterpret_cast<char*>(p->peerCz[r]) + ((size_t)(g.rank * nzl + z0) * nyl) * GB;
+            FEN_TRY(dma_piece(c, p, "a2a_fwd_dma", reinterpret_cast<const char*>(p->Sx) + (size_t)z0 * nyl * GB,
+                              (size_t)NG * nzl * nyl * GB, (size_t)nzl * nyl * GB, dstF, (size_t)nz * nyl * GB,
+                              (size_t)(z1 - z0) * nyl * GB, NG, p->ev_piece[q]));
+        } else {
+            if (two) {
+                FEN_CUDA(cudaEventRecord(p->ev_piece[q], S));
+                FEN_CUDA(cudaStreamWaitEvent(T, p->ev_piece[q], 0));
+            }
+            FEN_TRY(dispatch_bs(c, g.ny, 0, true, rows_in, none, p->tw_y, sy, nullptr, &df, &sf,
+                                dim3(cap(g.ny, (long long)NG * (z1 - z0))), T));
+        }
     }
-    if (two) {
+    if (dma) {
+        FEN_TRY(dma_join(c, p, S));
+    } else if (two) {
         FEN_CUDA(cudaEventRecord(p->ev_join, T));
         FEN_CUDA(cudaStreamWaitEvent(S, p->ev_join, 0));
     }
@@ -1480,6 +1582,16 @@ static int solve_blocked(fen_ctx* c, Poisson* p, bool ppp, XArgs xa, bool fuse_r
     memset(&db, 0, sizeof(db));
     for (int r = 0; r < P; ++r) db.peer[r] = p->peerC[r];
     db.gs = ny * nzl * 8; db.os = nzl * 8; db.o0 = g.rank * (int)nyl; db.blk = (int)nzl; db.P = P; db.rank = g.rank;
+    SendDst sb;                                                           // send buffer [r][g][jl][zl][8]
+    memset(&sb, 0, sizeof(sb));
+    sb.self = p->C; sb.send = p->Sx; sb.gs_self = db.gs; sb.os_self = db.os; sb.o0 = db.o0; sb.sh = log2i((int)nzl);
+    sb.mask = (int)nzl - 1; sb.rank = g.rank; sb.ng_tot = NG; sb.no_tot = (int)nyl;
+    auto y_inverse = [&](int g0, int g1, cudaStream_t st) {
+        BAddr yin{p->C, ny * nzl * 8, 8, nzl * 8, g0, 0};                 // Cy lives in C's memory: lines over j
+        BAddr rows_out{p->Cr, 8, (long long)p->PC * ny, p->PC, g0, 0};
+        return dispatch_bs(c, g.ny, 1, true, yin, rows_out, p->tw_y, 1.0, nullptr, nullptr, nullptr,
+                           dim3(g1 - g0, (unsigned)nzl), st);
+    };
     for (int q = 0; q < nq; ++q) {
         const int g0 = NG * q / nq, g1 = NG * (q + 1) / nq;
         if (g1 <= g0) continue;
@@ -1489,35 +1601,57 @@ static int solve_blocked(fen_ctx* c, Poisson* p, bool ppp, XArgs xa, bool fuse_r
             sa.tw = p->tw_z; sa.lx = p->mwn_x; sa.lo = p->mwn_y; sa.ll = p->mwn_z;
             sa.norm = f32((long long)g.nx * g.ny * g.nz); sa.ow0 = g.rank * (int)nyl;
             db.ng = g1 - g0; db.no = (int)nyl;
-            FEN_TRY(dispatch_bs(c, g.nz, 2, zin, none, nullptr, 1.0, &sa, &db,
-                                dim3(cap(g.nz, (long long)(g1 - g0) * nyl)), S));
+            FEN_TRY(dispatch_bs(c, g.nz, 2, !dma, zin, none, nullptr, 1.0, &sa, &db, &sb,
+                                dim3(dma ? (unsigned)((g1 - g0) * nyl) : cap(g.nz, (long long)(g1 - g0) * nyl)), S));
         } else {
             TArgs t;
             t.C = p->Cz; t.c1 = p->c1; t.sl = nyl * 8; t.so = nz * nyl * 8; t.n = g.nz; t.npc = p->PC;
             t.nouter = (int)nyl; t.o0 = g.rank * (int)nyl;
             t.a = p->ta; t.b = p->tb; t.c = p->tc; t.lx = p->mwn_x; t.lo = p->mwn_y; t.form2d = 0; t.mean = 1;
-            t.blocked = 1; t.g0 = g0;
+            t.blocked = 1; t.g0 = g0; t.to_send = dma ? 1 : 0; t.sd = sb;
             dim3 grid(((unsigned)nyl * 8 + 127) / 128, g1 - g0), block(128);
             FEN_LAUNCH(c, "thomas_fwd", k_thomas_fwd<<<grid, block, 0, S>>>(t));
             FEN_LAUNCH(c, "thomas_bwd", k_thomas_bwd<<<grid, block, 0, S>>>(t));
-            const int bytes = (int)nzl * 8 * (int)sizeof(double2);
-            FEN_ONCE_PER_DEVICE(c)
-                FEN_CUDA(cudaFuncSetAttribute(k_bulk_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024));
-            FEN_LAUNCH(c, "a2a_scatter", k_bulk_rows<<<dim3((unsigned)(P * nyl), g1 - g0), 256, bytes, S>>>(
-                                             p->Cz, nz * nyl * 8, nyl * 8, 8, db, (int)nyl, g0));
+            if (!dma) {
+                const int bytes = (int)nzl * 8 * (int)sizeof(double2);
+                FEN_ONCE_PER_DEVICE(c)
+                    FEN_CUDA(cudaFuncSetAttribute(k_bulk_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024));
+                FEN_LAUNCH(c, "a2a_scatter", k_bulk_rows<<<dim3((unsigned)(P * nyl), g1 - g0), 256, bytes, S>>>(
+                                                 p->Cz, nz * nyl * 8, nyl * 8, 8, db, (int)nyl, g0));
+            }
             FEN_CUDA(cudaGetLastError());
         }
-        FEN_TRY(comm_chunk_signal(c, q, S));                              // my piece q is out ...
-        if (two) {
-            FEN_CUDA(cudaEventRecord(p->ev_piece[q], S));
-            FEN_CUDA(cudaStreamWaitEvent(T, p->ev_piece[q], 0));
+        if (dma) {
+            // piece of rank r: rows g = g0 .. g1-1 of nyl * nzl granules, at line rank*nyl of r's Cy
+            for (int r = 0; r < P; ++r)
+                dstB[r] = reinterpret_cast<char*>(p->peerC[r]) + ((size_t)g0 * ny + (size_t)g.rank * nyl) * nzl * GB;
+            FEN_TRY(dma_piece(c, p, "a2a_bwd_dma", reinterpret_cast<const char*>(p->Sx) + (size_t)g0 * nyl * nzl * GB,
+                              (size_t)NG * nyl * nzl * GB, (size_t)nyl * nzl * GB, dstB, (size_t)ny * nzl * GB,
+                              (size_t)nyl * nzl * GB, (size_t)(g1 - g0), p->ev_piece[q]));
+            cudaStream_t sig = c->profiling ? S : p->cp[0];
+            FEN_TRY(dma_join(c, p, sig));
+            FEN_TRY(comm_chunk_signal(c, q, sig));                        // my piece q has landed everywhere
+            if (!c->profiling) FEN_CUDA(cudaEventRecord(p->ev_sig[q], sig));
+        } else {
+            FEN_TRY(comm_chunk_signal(c, q, S));                          // my piece q is out ...
+            if (two) {
+                FEN_CUDA(cudaEventRecord(p->ev_piece[q], S));
+                FEN_CUDA(cudaStreamWaitEvent(T, p->ev_piece[q], 0));
+            }
+            FEN_TRY(comm_chunk_wait(c, q, T));                            // ... and everybody's has arrived (:1015 / :1138)
+            FEN_TRY(y_inverse(g0, g1, T));
         }
-        FEN_TRY(comm_chunk_wait(c, q, T));                                // ... and everybody's has arrived (:1015 / :1138)
-        BAddr yin{p->C, ny * nzl * 8, 8, nzl * 8, g0, 0};                 // Cy lives in C's memory: lines over j
-        BAddr rows_out{p->Cr, 8, (long long)p->PC * ny, p->PC, g0, 0};
-        FEN_TRY(dispatch_bs(c, g.ny, 1, yin, rows_out, p->tw_y, 1.0, nullptr, nullptr, dim3(g1 - g0, (unsigned)nzl), T));
     }
-    if (two) {
+    if (dma) {
+        // every solve is queued; now the y inverse of each piece, as soon as that piece has arrived from everybody
+        for (int q = 0; q < nq; ++q) {
+            const int g0 = NG * q / nq, g1 = NG * (q + 1) / nq;
+            if (g1 <= g0) continue;
+            if (!c->profiling) FEN_CUDA(cudaStreamWaitEvent(S, p->ev_sig[q], 0));
+            FEN_TRY(comm_chunk_wait(c, q, S));                            // transpose_z_to_y complete for piece q
+            FEN_TRY(y_inverse(g0, g1, S));
+        }
+    } else if (two) {
         FEN_CUDA(cudaEventRecord(p->ev_join, T));
         FEN_CUDA(cudaStreamWaitEvent(S, p->ev_join, 0));
     }
