@@ -62,8 +62,8 @@ struct Poisson {
     // pitched peer copies on `cp` streams move it while the SMs work on the next piece
     bool dma = false;
     double2* Sx = nullptr;          // send buffer (forward: [r][g][zl][jl][8], backward: [r][g][jl][zl][8])
-    static constexpr int kCopyStreams = 4;
-    int ncp = kCopyStreams;         // copy streams in use (FEN_SLAB_COPY_STREAMS)
+    static constexpr int kCopyStreams = 8;
+    int ncp = 4;                    // copy streams in use (FEN_SLAB_COPY_STREAMS, default 4)
     cudaStream_t cp[kCopyStreams] = {};
     cudaEvent_t ev_cp[kCopyStreams] = {};
     cudaEvent_t ev_sig[FEN_MAX_CHUNKS] = {};
@@ -1328,7 +1328,7 @@ static int poisson_build(fen_ctx* c) {
                 FEN_CUDA(cudaMalloc(&p->Sx, nC * sizeof(double2)));
                 FEN_CUDA(cudaMemsetAsync(p->Sx, 0, nC * sizeof(double2), c->stream));
                 const char* es = getenv("FEN_SLAB_COPY_STREAMS");
-                p->ncp = std::max(1, std::min(Poisson::kCopyStreams, es ? atoi(es) : Poisson::kCopyStreams));
+                p->ncp = std::max(1, std::min(Poisson::kCopyStreams, es ? atoi(es) : 4));
                 for (int k = 0; k < p->ncp; ++k) {
                     FEN_CUDA(cudaStreamCreateWithFlags(&p->cp[k], cudaStreamNonBlocking));
                     FEN_CUDA(cudaEventCreateWithFlags(&p->ev_cp[k], cudaEventDisableTiming));
@@ -1479,11 +1479,19 @@ static int dma_piece(fen_ctx* c, Poisson* p, const char* name, const char* src0,
     int tok = serial ? prof_begin(c, name) : -1;
     if (!serial) c->launches++;
     for (int k = 0; k < p->ncp && !serial; ++k) FEN_CUDA(cudaStreamWaitEvent(p->cp[k], ready, 0));
+    // with fewer peers than copy streams every peer's rows are split over several streams (one copy engine alone
+    // reaches ~500 GB/s to one peer: profiles/r02k_bench_n2_dma4.json)
+    const int nsplit = serial ? 1 : std::max(1, std::min<int>((int)height, p->ncp / std::max(1, P - 1)));
+    int slot = 0;
     for (int q = 1; q < P; ++q) {
         const int r = (me + q) % P;                                     // staggered: rank + 1 first
-        cudaStream_t st = serial ? c->stream : p->cp[(q - 1) % p->ncp];
-        FEN_CUDA(cudaMemcpy2DAsync(dst[r], dpitch, src0 + (size_t)r * src_rank, spitch, width, height,
-                                   cudaMemcpyDeviceToDevice, st));
+        for (int sp = 0; sp < nsplit; ++sp, ++slot) {
+            const size_t h0 = height * sp / nsplit, h1 = height * (sp + 1) / nsplit;
+            if (h1 <= h0) continue;
+            cudaStream_t st = serial ? c->stream : p->cp[slot % p->ncp];
+            FEN_CUDA(cudaMemcpy2DAsync(dst[r] + h0 * dpitch, dpitch, src0 + (size_t)r * src_rank + h0 * spitch, spitch,
+                                       width, h1 - h0, cudaMemcpyDeviceToDevice, st));
+        }
     }
     if (serial) prof_end(c, tok);
     return FEN_OK;
