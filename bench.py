@@ -745,27 +745,17 @@ def nvlink_figures(args, tk, nx, ny, nz, world, nccl=True):
         return None
     from fen_b200 import decomp
     sent = decomp.alltoall_bytes_per_gpu(nx, ny, nz, world)
-    dma = "a2a_fwd_dma" in tk or "a2a_bwd_dma" in tk
-    if dma:
-        fwd = tk.get("a2a_fwd_dma", 0.0) + tk.get("a2a_fwd_sync", 0.0)
-        bwd = tk.get("a2a_bwd_dma", 0.0) + tk.get("a2a_bwd_sync", 0.0)
-        note = ("y<->z transposes by the copy engines: the y-FFT / z-solve kernels fill a local send buffer laid out like "
-                "the receivers' regions and one pitched peer copy per destination and piece moves it (cudaMemcpy2DAsync "
-                "over NVLink); time = the copies + the flag handshake, measured with the pieces SERIALISED on the main "
-                "stream (per-kernel profiling), one peer at a time; in the timed region they run on their own streams "
-                "beside the x / y passes of the next piece")
-    else:
-        fwd = tk.get("fft_lines_fwd_a2a", 0.0) + tk.get("a2a_fwd_sync", 0.0)
-        bwd = tk.get("fft_solve_a2a", 0.0) + tk.get("a2a_scatter", 0.0) + tk.get("a2a_bwd_sync", 0.0)
-        note = ("y<->z transposes = epilogues of the y-FFT / z-solve kernels: the transformed tile goes from shared "
-                "memory to the owning ranks as one bulk store (cp.async.bulk) of blk x 128 bytes per destination; "
-                "time = that kernel + the flag handshake on this rank, so the figure is a lower bound of the link "
-                "rate (it includes the transform itself)")
+    fwd = tk.get("fft_lines_fwd_a2a", 0.0) + tk.get("a2a_fwd_sync", 0.0)
+    bwd = tk.get("fft_solve_a2a", 0.0) + tk.get("a2a_scatter", 0.0) + tk.get("a2a_bwd_sync", 0.0)
     nv = {"a2a_bytes_sent_per_gpu": sent, "peak_GBs_per_dir": 900.0, "measured_peer_copy_GBs": 770.0,
-          "form": "copy engines" if dma else "bulk stores",
           "fwd_ms": fwd, "fwd_bus_GBs": sent / (fwd * 1e-3) / 1e9 if fwd else None,
           "bwd_ms": bwd, "bwd_bus_GBs": sent / (bwd * 1e-3) / 1e9 if bwd else None,
-          "note": note + "; measured_peer_copy = B200_PROFILING.md's 770 GB/s"}
+          "note": "y<->z transposes = epilogues of the y-FFT / z-solve kernels: the transformed tile goes from shared "
+                  "memory to the owning ranks as one bulk store (cp.async.bulk) of blk x 128 bytes per destination; "
+                  "time = that kernel + the flag handshake on this rank, summed over the pieces of the chunked solve and "
+                  "measured with the pieces SERIALISED on one stream (per-kernel profiling), so the figure is a lower "
+                  "bound of the link rate (it includes the transform itself); in the timed region the pieces overlap "
+                  "with the x pass / y inverse of their neighbours; measured_peer_copy = B200_PROFILING.md's 770 GB/s"}
     for kname in ("fwd", "bwd"):
         v = nv[kname + "_bus_GBs"]
         nv[kname + "_frac"] = v / 900.0 if v else None
@@ -1012,6 +1002,9 @@ def run_ns_case(args, cx, case, steps, headline):
         "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
         "cpu_baseline": cpu, "kernels": kernels, "nvlink": nvlink,
         "poisson_solve_ms": poisson_ms,
+        "poisson_solve_ms_what": "sum of the solver's kernels in the profiled steps" + (
+            " (several ranks: the pieces of the chunked solve run serialised there; the overlapped solve time is "
+            "extra.poisson_only.value)" if world > 1 else ""),
         "check": {"maxdiv": maxdiv, "maxCFL": maxcfl},
     }
 

@@ -27,6 +27,7 @@
 #include "fft_core.cuh"
 #include "fft_any.cuh"
 #include "slab_bulk.cuh"
+#include "fft_wide.cuh"
 
 namespace fen {
 
@@ -58,15 +59,6 @@ struct Poisson {
     cudaEvent_t ev_piece[FEN_MAX_CHUNKS] = {};
     cudaEvent_t ev_join = nullptr;
     int nchunk = 1;
-    // copy-engine form (FEN_SLAB_DMA): the kernels write a local send buffer laid out like the receivers' regions and
-    // pitched peer copies on `cp` streams move it while the SMs work on the next piece
-    bool dma = false;
-    double2* Sx = nullptr;          // send buffer (forward: [r][g][zl][jl][8], backward: [r][g][jl][zl][8])
-    static constexpr int kCopyStreams = 8;
-    int ncp = 4;                    // copy streams in use (FEN_SLAB_COPY_STREAMS, default 4)
-    cudaStream_t cp[kCopyStreams] = {};
-    cudaEvent_t ev_cp[kCopyStreams] = {};
-    cudaEvent_t ev_sig[FEN_MAX_CHUNKS] = {};
     double2* peerC[FEN_MAX_RANKS] = {};
     double2* peerCz[FEN_MAX_RANKS] = {};
 };
@@ -477,6 +469,38 @@ __global__ void __launch_bounds__(NL* FftPlan<Lf>::T, (NL * FftPlan<Lf>::T <= 10
     }
 }
 
+// The fused z solve of 512-point lines with 32 values per thread (fft_wide.cuh): 128 threads per tile of 8 lines, three
+// tiles per SM, one shared-memory exchange per transform.  Same operation order around the transforms as k_fft_solve_r
+// (scale by 1/norm -- an exact power of two -- and by one rounded reciprocal of lambda, zero for the singular mode).
+template <int MINB>      // resident tiles per SM the register allocation aims at: 3 (168 registers, ~350 B spilled) or 2
+__global__ void __launch_bounds__(128, MINB) k_fft_solve_w512(LArgs a) {
+    extern __shared__ double2 s[];
+    const int tid = threadIdx.x;
+    const int line = tid & 7, t = tid >> 3;
+    const int kx = (blockIdx.x + a.cx0) * 8 + line;
+    double2* base = a.C + kx + a.so * blockIdx.y;
+    double2 v[32];
+#pragma unroll
+    for (int m = 0; m < 32; ++m) v[m] = base[a.sl * (t + 16 * m)];
+    auto sync = [] { __syncthreads(); };
+    fft512_wide<-1>(v, s, 8, line, t, a.tw, sync);
+    {
+        double lxo = __ldg(&a.lx[kx]);
+        if (a.lo) lxo = lxo + __ldg(&a.lo[a.o0 + blockIdx.y]);
+        const double inorm = 1.0 / a.norm;
+#pragma unroll
+        for (int m = 0; m < 32; ++m) {
+            const double lam = lxo + __ldg(&a.ll[t + 16 * m]);
+            const double rl = lam == 0.0 ? 0.0 : inorm / lam;
+            v[m].x *= rl;
+            v[m].y *= rl;
+        }
+    }
+    fft512_wide<+1>(v, s, 8, line, t, a.tw, sync);
+#pragma unroll
+    for (int m = 0; m < 32; ++m) base[a.sl * (t + 16 * m)] = v[m];
+}
+
 // =================================================================================================
 // Neumann directions: FFTW REDFT10 / REDFT01 (DCT-II / DCT-III, poisson.f90:272-275, :801-804, :888-909)
 // through one complex transform of the same length (Makhoul's reordering):
@@ -583,8 +607,6 @@ struct TArgs {
     // jl = e / 8 at C + so * g + e (so = granule stride, sl = plane stride nyl * 8)
     int blocked = 0;
     int g0 = 0;            // first granule of this launch (blocked layout; chunked launches)
-    int to_send = 0;       // back substitution: the solution goes to send_dst(sd, ...) (copy-engine transposes)
-    SendDst sd;
 };
 struct TSys {              // one thread's system
     long long off;         // offset of its first element in C / c1
@@ -703,17 +725,13 @@ __global__ void __launch_bounds__(128) k_thomas_bwd(TArgs g) {
     if (!sy.valid) return;
     const double2* C = g.C + sy.off;
     const double* c1t = g.c1 + sy.off;
-    // where element l of the solution goes: in place, or (copy-engine transposes) to the slot of the send buffer /
-    // of this rank's own y-slab array that the transposed layout assigns to it
-    const int e = blockIdx.x * blockDim.x + threadIdx.x;
-    auto out = [&](int l) -> double2* {
-        return g.to_send ? send_dst(g.sd, g.g0 + blockIdx.y, e >> 3, l, e & 7) : g.C + sy.off + g.sl * l;
-    };
+    double2* O = g.C + sy.off;
+    const long long osl = g.sl;
     const int n = g.n;
     const bool mean_line = g.mean && sy.kx == 0 && sy.lo_idx == 0;
     double2 x = C[g.sl * (n - 1)];                                  // :1124-1128
     double acc = x.x;
-    *out(n - 1) = x;
+    O[osl * (n - 1)] = x;
     constexpr int U = 8;
     for (int l0 = n - 2; l0 >= 0; l0 -= U) {
         double2 d[U];
@@ -730,15 +748,15 @@ __global__ void __launch_bounds__(128) k_thomas_bwd(TArgs g) {
                 x = make_double2(__dsub_rn(d[r].x, __dmul_rn(cc[r], x.x)),
                                  __dsub_rn(d[r].y, __dmul_rn(cc[r], x.y)));
                 acc += x.x;
-                *out(l0 - r) = x;
+                O[osl * (l0 - r)] = x;
             }
     }
     if (mean_line) {
         const double mean = acc / (double)n;
         for (int l = 0; l < n; ++l) {
-            double2 v = *out(l);
+            double2 v = O[osl * l];
             v.x -= mean;
-            *out(l) = v;
+            O[osl * l] = v;
         }
     }
 }
@@ -976,12 +994,6 @@ void poisson_destroy(fen_ctx* c) {
         if (p->C) cudaFree(p->C);
     }
     if (p->Cr) cudaFree(p->Cr);
-    for (int k = 0; k < Poisson::kCopyStreams; ++k) {
-        if (p->cp[k]) { cudaStreamSynchronize(p->cp[k]); cudaStreamDestroy(p->cp[k]); }
-        if (p->ev_cp[k]) cudaEventDestroy(p->ev_cp[k]);
-    }
-    for (int q = 0; q < FEN_MAX_CHUNKS; ++q) if (p->ev_sig[q]) cudaEventDestroy(p->ev_sig[q]);
-    if (p->Sx) cudaFree(p->Sx);
     if (p->aux) { cudaStreamSynchronize(p->aux); cudaStreamDestroy(p->aux); }
     for (int q = 0; q < FEN_MAX_CHUNKS; ++q) if (p->ev_piece[q]) cudaEventDestroy(p->ev_piece[q]);
     if (p->ev_join) cudaEventDestroy(p->ev_join);
@@ -1126,6 +1138,18 @@ template <int Lf, int NL> static int launch_lines(fen_ctx* c, const LArgs& a, in
         if (mode == 0 && !sc) FEN_LAUNCH(c, "fft_lines_fwd", k_fft_lines_r<Lf, -1, NL, false><<<grid, block, bytes, c->stream>>>(a, none));
         if (mode == 0 && sc) FEN_LAUNCH(c, "fft_lines_fwd_a2a", k_fft_lines_r<Lf, -1, NL, true><<<grid, block, bytes, c->stream>>>(a, *sc));
         if (mode == 1) FEN_LAUNCH(c, "fft_lines_inv", k_fft_lines_r<Lf, +1, NL, false><<<grid, block, bytes, c->stream>>>(a, none));
+        // 512-point lines: the 32-values-per-thread form (FEN_SOLVE_WIDE=0 selects the radix-8 register path)
+        static const int wide = getenv("FEN_SOLVE_WIDE") ? atoi(getenv("FEN_SOLVE_WIDE")) : 3;
+        if (mode == 2 && !sc && Lf == 512 && NL == 8 && wide) {
+            FEN_ONCE_PER_DEVICE(c) {
+                FEN_CUDA(cudaFuncSetAttribute(k_fft_solve_w512<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+                FEN_CUDA(cudaFuncSetAttribute(k_fft_solve_w512<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+            }
+            if (wide == 2) FEN_LAUNCH(c, "fft_solve", k_fft_solve_w512<2><<<grid, 128, bytes, c->stream>>>(a));
+            else FEN_LAUNCH(c, "fft_solve", k_fft_solve_w512<3><<<grid, 128, bytes, c->stream>>>(a));
+            FEN_CUDA(cudaGetLastError());
+            return FEN_OK;
+        }
         if (mode == 2 && !sc) FEN_LAUNCH(c, "fft_solve", k_fft_solve_r<Lf, NL, false><<<grid, block, bytes, c->stream>>>(a, none));
         if (mode == 2 && sc) FEN_LAUNCH(c, "fft_solve_a2a", k_fft_solve_r<Lf, NL, true><<<grid, block, bytes, c->stream>>>(a, *sc));
     } else {
@@ -1304,36 +1328,21 @@ static int poisson_build(fen_ctx* c) {
             const size_t nC = (size_t)p->PC * g.ny * p->nzl;
             FEN_CUDA(cudaMalloc(&p->Cr, nC * sizeof(double2)));
             FEN_CUDA(cudaMemsetAsync(p->Cr, 0, nC * sizeof(double2), c->stream));
-            // FEN_SLAB_DMA: 1 = the transposes travel by the copy engines, 0 = bulk stores by the kernels' own blocks;
-            // default: copy engines from 4 ranks on (solve_blocked's header)
-            const char* ed = getenv("FEN_SLAB_DMA");
-            p->dma = ed ? atoi(ed) != 0 : g.nranks >= 4;
-            // FEN_SLAB_CHUNKS = pieces of the overlapped transposes (1 = no overlap); default 4 from 4 ranks on, else 1
-            // (bulk-store form on 2 ranks: nothing to gain from overlap there, profiles/r02h_*.json)
+            // FEN_SLAB_CHUNKS = pieces of the overlapped transposes (1 = no overlap, one stream); default 4 from 4 ranks
+            // on, 1 on 2 ranks (there the transposing kernels are as much HBM- as link-bound and overlap gains nothing:
+            // 7.82 ms unchunked, 7.82 - 7.96 chunked, profiles/r02h_*.json)
             const char* e = getenv("FEN_SLAB_CHUNKS");
             p->nchunk = std::max(1, std::min(FEN_MAX_CHUNKS, e ? atoi(e) : (g.nranks >= 4 ? 4 : 1)));
             p->nchunk = std::min(p->nchunk, std::min(p->nzl, p->PC / 8));
-            if (p->nchunk > 1 && !p->dma) {
+            if (p->nchunk > 1) {
                 int lo = 0, hi = 0;
                 FEN_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
                 // the link-bound pieces get the higher priority: their blocks mostly wait, the HBM-bound pass fills in
                 FEN_CUDA(cudaStreamCreateWithPriority(&p->aux, cudaStreamNonBlocking, hi));
             }
-            for (int q = 0; q < FEN_MAX_CHUNKS; ++q) {
+            for (int q = 0; q < FEN_MAX_CHUNKS; ++q)
                 FEN_CUDA(cudaEventCreateWithFlags(&p->ev_piece[q], cudaEventDisableTiming));
-                FEN_CUDA(cudaEventCreateWithFlags(&p->ev_sig[q], cudaEventDisableTiming));
-            }
             FEN_CUDA(cudaEventCreateWithFlags(&p->ev_join, cudaEventDisableTiming));
-            if (p->dma) {
-                FEN_CUDA(cudaMalloc(&p->Sx, nC * sizeof(double2)));
-                FEN_CUDA(cudaMemsetAsync(p->Sx, 0, nC * sizeof(double2), c->stream));
-                const char* es = getenv("FEN_SLAB_COPY_STREAMS");
-                p->ncp = std::max(1, std::min(Poisson::kCopyStreams, es ? atoi(es) : 4));
-                for (int k = 0; k < p->ncp; ++k) {
-                    FEN_CUDA(cudaStreamCreateWithFlags(&p->cp[k], cudaStreamNonBlocking));
-                    FEN_CUDA(cudaEventCreateWithFlags(&p->ev_cp[k], cudaEventDisableTiming));
-                }
-            }
         }
     } else {
         const size_t nC = (size_t)p->PC * g.ny * p->nzl;
@@ -1436,120 +1445,69 @@ static int thomas_2d(fen_ctx* c, const TArgs& t) {
 }
 
 // ---- blocked slab path (slab_bulk.cuh): ppp / ppn on several ranks, 64..1024-point transform lines ----------------
-// what: 0 y forward + transpose, 1 y inverse (blocked in, rows out), 2 z solve + transpose; bulk: stores by the block
-// itself (cp.async.bulk to the peers), else into the send buffer for the copy engines
-template <int Lf> static int launch_bs(fen_ctx* c, int what, bool bulk, const BAddr& in, const BAddr& out, const double2* tw,
-                                       double scale, const SolveArgs* sa, const BulkDst* d, const SendDst* sd, dim3 grid,
-                                       cudaStream_t st) {
+template <int Lf> static int launch_bs(fen_ctx* c, int what, const BAddr& in, const BAddr& out, const double2* tw,
+                                       double scale, const SolveArgs* sa, const BulkDst* d, dim3 grid, cudaStream_t st) {
     const int bytes = Lf * 8 * (int)sizeof(double2);
     FEN_ONCE_PER_DEVICE(c) {
-        FEN_CUDA(cudaFuncSetAttribute((k_fft_lines_bs<Lf, -1, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-        FEN_CUDA(cudaFuncSetAttribute((k_fft_lines_bs<Lf, -1, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-        FEN_CUDA(cudaFuncSetAttribute((k_fft_solve_bs<Lf, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-        FEN_CUDA(cudaFuncSetAttribute((k_fft_solve_bs<Lf, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-        FEN_CUDA(cudaFuncSetAttribute((k_fft_lines_io<Lf, +1>), cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+        FEN_CUDA(cudaFuncSetAttribute(k_fft_lines_bs<Lf, -1>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+        FEN_CUDA(cudaFuncSetAttribute(k_fft_solve_bs<Lf>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+        FEN_CUDA(cudaFuncSetAttribute(k_fft_lines_io<Lf, +1>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
     }
-    if (what == 0 && bulk) FEN_LAUNCH(c, "fft_lines_fwd_a2a", (k_fft_lines_bs<Lf, -1, true><<<grid, Lf, bytes, st>>>(in, tw, scale, *d, *sd)));
-    if (what == 0 && !bulk) FEN_LAUNCH(c, "fft_lines_fwd", (k_fft_lines_bs<Lf, -1, false><<<grid, Lf, bytes, st>>>(in, tw, scale, *d, *sd)));
-    if (what == 1) FEN_LAUNCH(c, "fft_lines_inv", (k_fft_lines_io<Lf, +1><<<grid, Lf, bytes, st>>>(in, out, tw, scale)));
-    if (what == 2 && bulk) FEN_LAUNCH(c, "fft_solve_a2a", (k_fft_solve_bs<Lf, true><<<grid, Lf, bytes, st>>>(in, *sa, *d, *sd)));
-    if (what == 2 && !bulk) FEN_LAUNCH(c, "fft_solve", (k_fft_solve_bs<Lf, false><<<grid, Lf, bytes, st>>>(in, *sa, *d, *sd)));
+    if (what == 0) FEN_LAUNCH(c, "fft_lines_fwd_a2a", k_fft_lines_bs<Lf, -1><<<grid, Lf, bytes, st>>>(in, tw, scale, *d));
+    if (what == 1) FEN_LAUNCH(c, "fft_lines_inv", k_fft_lines_io<Lf, +1><<<grid, Lf, bytes, st>>>(in, out, tw, scale));
+    if (what == 2) FEN_LAUNCH(c, "fft_solve_a2a", k_fft_solve_bs<Lf><<<grid, Lf, bytes, st>>>(in, *sa, *d));
     FEN_CUDA(cudaGetLastError());
     return FEN_OK;
 }
-static int dispatch_bs(fen_ctx* c, int Lf, int what, bool bulk, const BAddr& in, const BAddr& out, const double2* tw,
-                       double scale, const SolveArgs* sa, const BulkDst* d, const SendDst* sd, dim3 grid, cudaStream_t st) {
+static int dispatch_bs(fen_ctx* c, int Lf, int what, const BAddr& in, const BAddr& out, const double2* tw, double scale,
+                       const SolveArgs* sa, const BulkDst* d, dim3 grid, cudaStream_t st) {
     switch (Lf) {
-#define FEN_CASE(l) case l: return launch_bs<l>(c, what, bulk, in, out, tw, scale, sa, d, sd, grid, st);
+#define FEN_CASE(l) case l: return launch_bs<l>(c, what, in, out, tw, scale, sa, d, grid, st);
         FEN_CASE(64) FEN_CASE(128) FEN_CASE(256) FEN_CASE(512) FEN_CASE(1024)
 #undef FEN_CASE
     }
     return set_error(FEN_ERR_STATE, "blocked slab path: line length %d", Lf);
 }
 
-// One piece of a copy-engine transpose: to every peer r one pitched device-to-device copy of `height` rows of `width`
-// bytes (row h of peer r: src0 + r*src_rank + h*spitch  ->  dst[r] + h*dpitch), spread over the copy streams, which first
-// wait for `ready` (the kernel that filled the send buffer).  With per-kernel profiling on, the copies run on the main
-// stream inside one event bracket named `name`.
-static int dma_piece(fen_ctx* c, Poisson* p, const char* name, const char* src0, size_t src_rank, size_t spitch,
-                     char* const* dst, size_t dpitch, size_t width, size_t height, cudaEvent_t ready) {
-    const int P = c->g.nranks, me = c->g.rank;
-    const bool serial = c->profiling;
-    if (!serial) FEN_CUDA(cudaEventRecord(ready, c->stream));
-    int tok = serial ? prof_begin(c, name) : -1;
-    if (!serial) c->launches++;
-    for (int k = 0; k < p->ncp && !serial; ++k) FEN_CUDA(cudaStreamWaitEvent(p->cp[k], ready, 0));
-    // with fewer peers than copy streams every peer's rows are split over several streams (one copy engine alone
-    // reaches ~500 GB/s to one peer: profiles/r02k_bench_n2_dma4.json)
-    const int nsplit = serial ? 1 : std::max(1, std::min<int>((int)height, p->ncp / std::max(1, P - 1)));
-    int slot = 0;
-    for (int q = 1; q < P; ++q) {
-        const int r = (me + q) % P;                                     // staggered: rank + 1 first
-        for (int sp = 0; sp < nsplit; ++sp, ++slot) {
-            const size_t h0 = height * sp / nsplit, h1 = height * (sp + 1) / nsplit;
-            if (h1 <= h0) continue;
-            cudaStream_t st = serial ? c->stream : p->cp[slot % p->ncp];
-            FEN_CUDA(cudaMemcpy2DAsync(dst[r] + h0 * dpitch, dpitch, src0 + (size_t)r * src_rank + h0 * spitch, spitch,
-                                       width, h1 - h0, cudaMemcpyDeviceToDevice, st));
-        }
-    }
-    if (serial) prof_end(c, tok);
-    return FEN_OK;
-}
-// the copy streams' work so far is a dependency of stream `st`
-static int dma_join(fen_ctx* c, Poisson* p, cudaStream_t st) {
-    if (c->profiling) return FEN_OK;                                    // the copies ran on the main stream
-    for (int k = 0; k < p->ncp; ++k) {
-        FEN_CUDA(cudaEventRecord(p->ev_cp[k], p->cp[k]));
-        FEN_CUDA(cudaStreamWaitEvent(st, p->ev_cp[k], 0));
-    }
-    return FEN_OK;
-}
-
-// x r2c -> y forward -> transpose -> z solve or Thomas -> transpose -> y inverse into the row array Cr.
+// x r2c -> y forward -> (bulk stores) -> z solve or Thomas -> (bulk stores) -> y inverse into the row array Cr.
 //
-// The two transposes are bound by the link (941 MB out per GPU at 1024^3 on 8: >= 1.2 ms each at the 770 GB/s a peer
-// copy reaches), the passes either side of them by local HBM.  Two forms, both cut in nchunk pieces (forward: z planes,
-// backward: granules of 8 kx):
-//
-// (a) copy engines (p->dma, the default on >= 4 ranks).  The kernels stay local: the y forward pass and the z solve
-//     write a send buffer laid out like the regions the receivers will hold (SendDst), and one pitched peer copy per
-//     destination moves each piece over NVLink on its own streams -- no SM is involved, so the x pass and y transform
-//     of piece q+1 run at full speed while piece q travels; on the way back the solves of all pieces are queued first
-//     and the y inverse of piece q waits, on the same stream, for "piece q has arrived from everybody".
-// (b) bulk stores (slab_bulk.cuh): the transposing kernel's own blocks ship their tile with cp.async.bulk.  Used on 2
-//     ranks (681 / 671 GB/s, nothing to overlap: the kernels are as much HBM- as link-bound there) and as the A/B
-//     reference of (a): FEN_SLAB_DMA=0.  With nchunk > 1 its pieces overlap with the neighbouring pass on an auxiliary
-//     stream, but at 8 ranks the persistent transposing blocks need >= 96 of the 148 SMs to keep the link full
-//     (profiles/r02i_*.json: 9.26 ms unchunked, 9.07 / 10.13 / 11.14 ms at caps of 96 / 64 / 48 SMs), which is why (a).
+// The two transposing stages are bound by the link (941 MB out per GPU at 1024^3 on 8: >= 1.2 ms each at the 770 GB/s a
+// peer copy reaches), their blocks spend most of their life waiting for bulk stores to drain, and the passes either
+// side of them are bound by local HBM.  So the work is cut in nchunk pieces and pipelined over two streams:
+//   forward   piece q = z planes:  x r2c(q) on the main stream, y forward + stores(q) on `aux` behind it -- the x pass
+//             of piece q+1 runs while piece q's stores travel;
+//   backward  piece q = granules:  z solve (or Thomas + row shipping) + stores(q) on the main stream, then "piece q is
+//             out" is raised on every peer; `aux` waits until every peer has raised it and runs the y inverse of those
+//             granules while piece q+1 is solved and shipped.
 // With per-kernel profiling on (bench.py's kernel table) everything runs on the main stream, piece by piece, so that
 // the event brackets mean what they say; the timed region of the bench runs overlapped.
+//
+// Measured and not kept (round 2, records under profiles/): (i) moving the pieces with the COPY ENGINES instead -- the
+// kernels fill a local send buffer laid out like the receivers' regions, one pitched cudaMemcpy2DAsync per peer and piece
+// on separate copy streams, no SM involved -- reaches 373 / 438 GB/s at 8 GPUs against 675 / 649 GB/s for the bulk stores
+// and makes the step 11.5 ms instead of 9.3 (r02l_bench_n8_copy_engines*.json; 495 GB/s to a single peer at 2 GPUs,
+// r02k_*.json); (ii) capping the persistent transposing kernels below ~96 SMs' worth of blocks (r02i_*.json).
 static int solve_blocked(fen_ctx* c, Poisson* p, bool ppp, XArgs xa, bool fuse_rhs, const DivArgs* dv) {
     const fen_grid_desc& g = c->g;
     const int NG = p->PC / 8, P = g.nranks;
     const long long ny = g.ny, nz = g.nz, nyl = p->nyl, nzl = p->nzl;
-    const bool dma = p->dma;
-    cudaStream_t S = c->stream, T = (c->profiling || !p->aux || dma) ? c->stream : p->aux;
+    cudaStream_t S = c->stream, T = (c->profiling || !p->aux) ? c->stream : p->aux;
     const bool two = T != S;
     const int nq = p->nchunk;
-    // grid cap of the persistent bulk-store kernels while they share the GPU with the pass on the other stream
+    // grid cap of the persistent transposing kernels while they share the GPU with the pass on the other stream
+    // (FEN_SLAB_SMS = SMs' worth of their blocks, default 96.  Measured at 8 GPUs, 1024-point tiles, profiles/r02i_*.json:
+    // 9.26 ms/step unchunked, 9.07 / 10.13 / 11.14 ms with 4 pieces at caps of 96 / 64 / 48 SMs -- a block ships a tile
+    // every ~10 us, so the link needs about a hundred of them)
     static const int cap_sms = getenv("FEN_SLAB_SMS") ? std::max(1, atoi(getenv("FEN_SLAB_SMS"))) : 96;
     auto cap = [&](int Lf, long long ntiles) {
         const long long per_sm = Lf >= 1024 ? 1 : 1024 / Lf;
         return (unsigned)std::min<long long>(ntiles, two ? cap_sms * per_sm : ntiles);
     };
     BAddr none{nullptr, 0, 0, 0, 0, 0};
-    const size_t GB = 8 * sizeof(double2);                                // bytes of a granule
-    char* dstF[FEN_MAX_RANKS];
-    char* dstB[FEN_MAX_RANKS];
     BulkDst df;                                                           // -> Cz[((g*nz + k)*nyl + jl)*8 + kxi]
     memset(&df, 0, sizeof(df));
     for (int r = 0; r < P; ++r) df.peer[r] = p->peerCz[r];
     df.gs = nz * nyl * 8; df.os = nyl * 8; df.o0 = g.rank * (int)nzl; df.blk = (int)nyl; df.P = P; df.rank = g.rank;
-    SendDst sf;                                                           // send buffer [r][g][zl][jl][8]
-    memset(&sf, 0, sizeof(sf));
-    sf.self = p->Cz; sf.send = p->Sx; sf.gs_self = df.gs; sf.os_self = df.os; sf.o0 = df.o0; sf.sh = log2i((int)nyl);
-    sf.mask = (int)nyl - 1; sf.rank = g.rank; sf.ng_tot = NG; sf.no_tot = (int)nzl;
     const double sy = ppp ? 1.0 : 1.0 / f32(g.ny);                        // poisson.f90:1087
     // ---- forward: pieces of z planes ----
     for (int q = 0; q < nq; ++q) {
@@ -1558,29 +1516,16 @@ static int solve_blocked(fen_ctx* c, Poisson* p, bool ppp, XArgs xa, bool fuse_r
         XArgs xq = xa;
         xq.r0 = z0 * (int)ny; xq.nrows = z1 * (int)ny;
         FEN_TRY(dispatch_x(c, p->M, xq, true, fuse_rhs ? dv : nullptr)); // :965-969 (+ :111-121 when fused)
+        if (two) {
+            FEN_CUDA(cudaEventRecord(p->ev_piece[q], S));
+            FEN_CUDA(cudaStreamWaitEvent(T, p->ev_piece[q], 0));
+        }
         BAddr rows_in{p->C, 8, (long long)p->PC * ny, p->PC, 0, z0};      // C[kx + PC*(j + ny*zl)]: lines over j
         df.ng = NG; df.no = z1 - z0;
-        if (dma) {
-            FEN_TRY(dispatch_bs(c, g.ny, 0, false, rows_in, none, p->tw_y, sy, nullptr, &df, &sf,
-                                dim3((unsigned)(NG * (z1 - z0))), S));
-            // piece of rank r: rows g = 0 .. NG-1 of (z1 - z0) * nyl granules, at plane rank*nzl + z0 of r's Cz
-            for (int r = 0; r < P; ++r)
-                dstF[r] = reinterpret_cast<char*>(p->peerCz[r]) + ((size_t)(g.rank * nzl + z0) * nyl) * GB;
-            FEN_TRY(dma_piece(c, p, "a2a_fwd_dma", reinterpret_cast<const char*>(p->Sx) + (size_t)z0 * nyl * GB,
-                              (size_t)NG * nzl * nyl * GB, (size_t)nzl * nyl * GB, dstF, (size_t)nz * nyl * GB,
-                              (size_t)(z1 - z0) * nyl * GB, NG, p->ev_piece[q]));
-        } else {
-            if (two) {
-                FEN_CUDA(cudaEventRecord(p->ev_piece[q], S));
-                FEN_CUDA(cudaStreamWaitEvent(T, p->ev_piece[q], 0));
-            }
-            FEN_TRY(dispatch_bs(c, g.ny, 0, true, rows_in, none, p->tw_y, sy, nullptr, &df, &sf,
-                                dim3(cap(g.ny, (long long)NG * (z1 - z0))), T));
-        }
+        FEN_TRY(dispatch_bs(c, g.ny, 0, rows_in, none, p->tw_y, sy, nullptr, &df,
+                            dim3(cap(g.ny, (long long)NG * (z1 - z0))), T));
     }
-    if (dma) {
-        FEN_TRY(dma_join(c, p, S));
-    } else if (two) {
+    if (two) {
         FEN_CUDA(cudaEventRecord(p->ev_join, T));
         FEN_CUDA(cudaStreamWaitEvent(S, p->ev_join, 0));
     }
@@ -1590,16 +1535,6 @@ static int solve_blocked(fen_ctx* c, Poisson* p, bool ppp, XArgs xa, bool fuse_r
     memset(&db, 0, sizeof(db));
     for (int r = 0; r < P; ++r) db.peer[r] = p->peerC[r];
     db.gs = ny * nzl * 8; db.os = nzl * 8; db.o0 = g.rank * (int)nyl; db.blk = (int)nzl; db.P = P; db.rank = g.rank;
-    SendDst sb;                                                           // send buffer [r][g][jl][zl][8]
-    memset(&sb, 0, sizeof(sb));
-    sb.self = p->C; sb.send = p->Sx; sb.gs_self = db.gs; sb.os_self = db.os; sb.o0 = db.o0; sb.sh = log2i((int)nzl);
-    sb.mask = (int)nzl - 1; sb.rank = g.rank; sb.ng_tot = NG; sb.no_tot = (int)nyl;
-    auto y_inverse = [&](int g0, int g1, cudaStream_t st) {
-        BAddr yin{p->C, ny * nzl * 8, 8, nzl * 8, g0, 0};                 // Cy lives in C's memory: lines over j
-        BAddr rows_out{p->Cr, 8, (long long)p->PC * ny, p->PC, g0, 0};
-        return dispatch_bs(c, g.ny, 1, true, yin, rows_out, p->tw_y, 1.0, nullptr, nullptr, nullptr,
-                           dim3(g1 - g0, (unsigned)nzl), st);
-    };
     for (int q = 0; q < nq; ++q) {
         const int g0 = NG * q / nq, g1 = NG * (q + 1) / nq;
         if (g1 <= g0) continue;
@@ -1609,57 +1544,35 @@ static int solve_blocked(fen_ctx* c, Poisson* p, bool ppp, XArgs xa, bool fuse_r
             sa.tw = p->tw_z; sa.lx = p->mwn_x; sa.lo = p->mwn_y; sa.ll = p->mwn_z;
             sa.norm = f32((long long)g.nx * g.ny * g.nz); sa.ow0 = g.rank * (int)nyl;
             db.ng = g1 - g0; db.no = (int)nyl;
-            FEN_TRY(dispatch_bs(c, g.nz, 2, !dma, zin, none, nullptr, 1.0, &sa, &db, &sb,
-                                dim3(dma ? (unsigned)((g1 - g0) * nyl) : cap(g.nz, (long long)(g1 - g0) * nyl)), S));
+            FEN_TRY(dispatch_bs(c, g.nz, 2, zin, none, nullptr, 1.0, &sa, &db,
+                                dim3(cap(g.nz, (long long)(g1 - g0) * nyl)), S));
         } else {
             TArgs t;
             t.C = p->Cz; t.c1 = p->c1; t.sl = nyl * 8; t.so = nz * nyl * 8; t.n = g.nz; t.npc = p->PC;
             t.nouter = (int)nyl; t.o0 = g.rank * (int)nyl;
             t.a = p->ta; t.b = p->tb; t.c = p->tc; t.lx = p->mwn_x; t.lo = p->mwn_y; t.form2d = 0; t.mean = 1;
-            t.blocked = 1; t.g0 = g0; t.to_send = dma ? 1 : 0; t.sd = sb;
+            t.blocked = 1; t.g0 = g0;
             dim3 grid(((unsigned)nyl * 8 + 127) / 128, g1 - g0), block(128);
             FEN_LAUNCH(c, "thomas_fwd", k_thomas_fwd<<<grid, block, 0, S>>>(t));
             FEN_LAUNCH(c, "thomas_bwd", k_thomas_bwd<<<grid, block, 0, S>>>(t));
-            if (!dma) {
-                const int bytes = (int)nzl * 8 * (int)sizeof(double2);
-                FEN_ONCE_PER_DEVICE(c)
-                    FEN_CUDA(cudaFuncSetAttribute(k_bulk_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024));
-                FEN_LAUNCH(c, "a2a_scatter", k_bulk_rows<<<dim3((unsigned)(P * nyl), g1 - g0), 256, bytes, S>>>(
-                                                 p->Cz, nz * nyl * 8, nyl * 8, 8, db, (int)nyl, g0));
-            }
+            const int bytes = (int)nzl * 8 * (int)sizeof(double2);
+            FEN_ONCE_PER_DEVICE(c)
+                FEN_CUDA(cudaFuncSetAttribute(k_bulk_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024));
+            FEN_LAUNCH(c, "a2a_scatter", k_bulk_rows<<<dim3((unsigned)(P * nyl), g1 - g0), 256, bytes, S>>>(
+                                             p->Cz, nz * nyl * 8, nyl * 8, 8, db, (int)nyl, g0));
             FEN_CUDA(cudaGetLastError());
         }
-        if (dma) {
-            // piece of rank r: rows g = g0 .. g1-1 of nyl * nzl granules, at line rank*nyl of r's Cy
-            for (int r = 0; r < P; ++r)
-                dstB[r] = reinterpret_cast<char*>(p->peerC[r]) + ((size_t)g0 * ny + (size_t)g.rank * nyl) * nzl * GB;
-            FEN_TRY(dma_piece(c, p, "a2a_bwd_dma", reinterpret_cast<const char*>(p->Sx) + (size_t)g0 * nyl * nzl * GB,
-                              (size_t)NG * nyl * nzl * GB, (size_t)nyl * nzl * GB, dstB, (size_t)ny * nzl * GB,
-                              (size_t)nyl * nzl * GB, (size_t)(g1 - g0), p->ev_piece[q]));
-            cudaStream_t sig = c->profiling ? S : p->cp[0];
-            FEN_TRY(dma_join(c, p, sig));
-            FEN_TRY(comm_chunk_signal(c, q, sig));                        // my piece q has landed everywhere
-            if (!c->profiling) FEN_CUDA(cudaEventRecord(p->ev_sig[q], sig));
-        } else {
-            FEN_TRY(comm_chunk_signal(c, q, S));                          // my piece q is out ...
-            if (two) {
-                FEN_CUDA(cudaEventRecord(p->ev_piece[q], S));
-                FEN_CUDA(cudaStreamWaitEvent(T, p->ev_piece[q], 0));
-            }
-            FEN_TRY(comm_chunk_wait(c, q, T));                            // ... and everybody's has arrived (:1015 / :1138)
-            FEN_TRY(y_inverse(g0, g1, T));
+        FEN_TRY(comm_chunk_signal(c, q, S));                              // my piece q is out ...
+        if (two) {
+            FEN_CUDA(cudaEventRecord(p->ev_piece[q], S));
+            FEN_CUDA(cudaStreamWaitEvent(T, p->ev_piece[q], 0));
         }
+        FEN_TRY(comm_chunk_wait(c, q, T));                                // ... and everybody's has arrived (:1015 / :1138)
+        BAddr yin{p->C, ny * nzl * 8, 8, nzl * 8, g0, 0};                 // Cy lives in C's memory: lines over j
+        BAddr rows_out{p->Cr, 8, (long long)p->PC * ny, p->PC, g0, 0};
+        FEN_TRY(dispatch_bs(c, g.ny, 1, yin, rows_out, p->tw_y, 1.0, nullptr, nullptr, dim3(g1 - g0, (unsigned)nzl), T));
     }
-    if (dma) {
-        // every solve is queued; now the y inverse of each piece, as soon as that piece has arrived from everybody
-        for (int q = 0; q < nq; ++q) {
-            const int g0 = NG * q / nq, g1 = NG * (q + 1) / nq;
-            if (g1 <= g0) continue;
-            if (!c->profiling) FEN_CUDA(cudaStreamWaitEvent(S, p->ev_sig[q], 0));
-            FEN_TRY(comm_chunk_wait(c, q, S));                            // transpose_z_to_y complete for piece q
-            FEN_TRY(y_inverse(g0, g1, S));
-        }
-    } else if (two) {
+    if (two) {
         FEN_CUDA(cudaEventRecord(p->ev_join, T));
         FEN_CUDA(cudaStreamWaitEvent(S, p->ev_join, 0));
     }

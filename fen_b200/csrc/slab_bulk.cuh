@@ -45,25 +45,6 @@ struct BulkDst {
     int ng, no;            // tiles of this launch: granules x outer indices
 };
 
-// Copy-engine form of the same transposes (FEN_SLAB_DMA, poisson.cu: solve_blocked): the kernels stay local.  Element
-// idx of a tile belongs to rank r = idx >> sh (blk = 1 << sh);
-//   r == rank : it goes straight into this rank's own array, at self + gs_self*g + os_self*(o0 + o) + 8*(idx & mask) + line
-//   otherwise : into the block of the send buffer that rank r will receive, laid out exactly as the region it occupies
-//               in r's array -- send[((r*ng_tot + g)*no_tot + o)*blk*8 + 8*(idx & mask) + line] -- so that the transfer
-//               itself is one pitched device-to-device copy per peer (cudaMemcpy2DAsync: height = granules, width = the
-//               contiguous (o, idx) block), run by the copy engines over NVLink while the SMs work on the next piece.
-struct SendDst {
-    double2* self;
-    double2* send;
-    long long gs_self, os_self;
-    int o0, sh, mask, rank, ng_tot, no_tot;
-};
-__device__ __forceinline__ double2* send_dst(const SendDst& q, int g, int o, int idx, int line) {
-    const int r = idx >> q.sh, e = idx & q.mask;
-    if (r == q.rank) return q.self + q.gs_self * g + q.os_self * (q.o0 + o) + 8 * e + line;
-    return q.send + ((((long long)r * q.ng_tot + g) * q.no_tot + o) << (q.sh + 3)) + 8 * e + line;
-}
-
 __device__ __forceinline__ void bulk_store(void* gdst, const void* ssrc, unsigned bytes) {
     asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
                  ::"l"(gdst), "r"((unsigned)__cvta_generic_to_shared(ssrc)), "r"(bytes) : "memory");
@@ -94,9 +75,9 @@ __device__ __forceinline__ void bulk_scatter_tile(const double2* s, const BulkDs
     __syncthreads();
 }
 
-template <int Lf, int DIR, bool BULK = true>
+template <int Lf, int DIR>
 __global__ void __launch_bounds__(Lf, (Lf <= 512) ? 1024 / Lf : 1)
-k_fft_lines_bs(BAddr in, const double2* tw, double scale, BulkDst d, SendDst sd) {
+k_fft_lines_bs(BAddr in, const double2* tw, double scale, BulkDst d) {
     extern __shared__ __align__(128) double2 s[];
     constexpr int T = Lf / 8;
     const int tid = threadIdx.x;
@@ -108,19 +89,11 @@ k_fft_lines_bs(BAddr in, const double2* tw, double scale, BulkDst d, SendDst sd)
 #pragma unroll
         for (int m = 0; m < 8; ++m) v[m] = base[in.is * (t + m * T)];
         fft_regs<Lf, DIR, true, kStridedTwp>(v, s, 8, line, t, tw);
-        if constexpr (BULK) {
 #pragma unroll
-            for (int m = 0; m < 8; ++m) s[(t + m * T) * 8 + line] = make_double2(v[m].x * scale, v[m].y * scale);
-            bulk_scatter_tile(s, d, g, o, tid);
-        } else {
-#pragma unroll
-            for (int m = 0; m < 8; ++m)
-                *send_dst(sd, g, o, t + m * T, line) = make_double2(v[m].x * scale, v[m].y * scale);
-        }
+        for (int m = 0; m < 8; ++m) s[(t + m * T) * 8 + line] = make_double2(v[m].x * scale, v[m].y * scale);
+        bulk_scatter_tile(s, d, g, o, tid);
     }
-    if constexpr (BULK) {
-        if (tid < d.P) bulk_wait_all();      // every write of this block has landed before the block retires
-    }
+    if (tid < d.P) bulk_wait_all();          // every write of this block has landed before the block retires
 }
 
 struct SolveArgs {
@@ -130,9 +103,9 @@ struct SolveArgs {
     int ow0;
 };
 
-template <int Lf, bool BULK = true>
+template <int Lf>
 __global__ void __launch_bounds__(Lf, (Lf <= 512) ? 1024 / Lf : 1)
-k_fft_solve_bs(BAddr in, SolveArgs a, BulkDst d, SendDst sd) {
+k_fft_solve_bs(BAddr in, SolveArgs a, BulkDst d) {
     extern __shared__ __align__(128) double2 s[];
     constexpr int T = Lf / 8;
     const int tid = threadIdx.x;
@@ -159,18 +132,11 @@ k_fft_solve_bs(BAddr in, SolveArgs a, BulkDst d, SendDst sd) {
             }
         }
         fft_regs<Lf, +1, true, kStridedTwp>(v, s, 8, line, t, a.tw);
-        if constexpr (BULK) {
 #pragma unroll
-            for (int m = 0; m < 8; ++m) s[(t + m * T) * 8 + line] = v[m];
-            bulk_scatter_tile(s, d, g, o, tid);
-        } else {
-#pragma unroll
-            for (int m = 0; m < 8; ++m) *send_dst(sd, g, o, t + m * T, line) = v[m];
-        }
+        for (int m = 0; m < 8; ++m) s[(t + m * T) * 8 + line] = v[m];
+        bulk_scatter_tile(s, d, g, o, tid);
     }
-    if constexpr (BULK) {
-        if (tid < d.P) bulk_wait_all();
-    }
+    if (tid < d.P) bulk_wait_all();
 }
 
 // transform with separate source and destination arrays (y inverse: blocked y-slab in, row layout out)

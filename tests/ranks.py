@@ -17,7 +17,6 @@ os.environ.setdefault("FEN_GPU_SPIN_LIMIT_MS", "3000")    # a missed flag fails 
 # another rank's spinning flag wait and never start (seen: 8 ranks, "peer wait timed out").  One process per GPU -- the
 # production layout -- has three streams per device and cannot alias.  Must be set before the CUDA context exists.
 os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
-os.environ.setdefault("FEN_SLAB_COPY_STREAMS", "1")     # copy-engine transposes: 8 ranks x (main + 1 copy + d2h) <= 32 queues
 
 import numpy as np
 

@@ -140,13 +140,13 @@ def test_poisson_1024_point_lines_on_8_ranks(bc, variant):
     assert np.linalg.norm(got - ref) <= 1e-12 * np.linalg.norm(ref)
 
 
-@pytest.mark.parametrize("env", [{"FEN_SLAB_BULK": "0"}, {"FEN_SLAB_DMA": "0", "FEN_SLAB_CHUNKS": "4"},
-                                 {"FEN_SLAB_DMA": "1", "FEN_SLAB_CHUNKS": "3"}, {"FEN_SLAB_CHUNKS": "1"}])
+@pytest.mark.parametrize("env", [{"FEN_SLAB_BULK": "0"}, {"FEN_SLAB_CHUNKS": "4", "FEN_SLAB_SMS": "8"},
+                                 {"FEN_SLAB_CHUNKS": "3"}, {"FEN_SLAB_CHUNKS": "1"}])
 def test_slab_transpose_forms_give_the_same_bits(env):
     """The forms of the slab transposes deliver the same coefficients as one rank: FEN_SLAB_BULK=0 (round 1's register
-    stores into the peers' row-layout arrays), FEN_SLAB_DMA=0 (bulk stores by the transposing kernels, here in four
-    overlapped pieces), FEN_SLAB_DMA=1 (send buffer + copy engines, here in three pieces, also on 2 ranks where it is not
-    the default), and unchunked.  The switches are read per process, so each runs in a child."""
+    stores into the peers' row-layout arrays), bulk stores in four overlapped pieces with the persistent transposing
+    kernels capped at 8 SMs' worth of blocks (also on 2 ranks, where one piece is the default), in three pieces, and
+    unchunked.  The switches are read per process, so each runs in a child."""
     import os
     import subprocess
     import sys
