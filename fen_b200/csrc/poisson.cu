@@ -27,7 +27,6 @@
 #include "fft_core.cuh"
 #include "fft_any.cuh"
 #include "slab_bulk.cuh"
-#include "fft_wide.cuh"
 
 namespace fen {
 
@@ -467,38 +466,6 @@ __global__ void __launch_bounds__(NL* FftPlan<Lf>::T, (NL * FftPlan<Lf>::T <= 10
         if (SC) *sc_dst(q, kx, idx, blockIdx.y) = v[m];
         else base[a.sl * idx] = v[m];
     }
-}
-
-// The fused z solve of 512-point lines with 32 values per thread (fft_wide.cuh): 128 threads per tile of 8 lines, three
-// tiles per SM, one shared-memory exchange per transform.  Same operation order around the transforms as k_fft_solve_r
-// (scale by 1/norm -- an exact power of two -- and by one rounded reciprocal of lambda, zero for the singular mode).
-template <int MINB>      // resident tiles per SM the register allocation aims at: 3 (168 registers, ~350 B spilled) or 2
-__global__ void __launch_bounds__(128, MINB) k_fft_solve_w512(LArgs a) {
-    extern __shared__ double2 s[];
-    const int tid = threadIdx.x;
-    const int line = tid & 7, t = tid >> 3;
-    const int kx = (blockIdx.x + a.cx0) * 8 + line;
-    double2* base = a.C + kx + a.so * blockIdx.y;
-    double2 v[32];
-#pragma unroll
-    for (int m = 0; m < 32; ++m) v[m] = base[a.sl * (t + 16 * m)];
-    auto sync = [] { __syncthreads(); };
-    fft512_wide<-1>(v, s, 8, line, t, a.tw, sync);
-    {
-        double lxo = __ldg(&a.lx[kx]);
-        if (a.lo) lxo = lxo + __ldg(&a.lo[a.o0 + blockIdx.y]);
-        const double inorm = 1.0 / a.norm;
-#pragma unroll
-        for (int m = 0; m < 32; ++m) {
-            const double lam = lxo + __ldg(&a.ll[t + 16 * m]);
-            const double rl = lam == 0.0 ? 0.0 : inorm / lam;
-            v[m].x *= rl;
-            v[m].y *= rl;
-        }
-    }
-    fft512_wide<+1>(v, s, 8, line, t, a.tw, sync);
-#pragma unroll
-    for (int m = 0; m < 32; ++m) base[a.sl * (t + 16 * m)] = v[m];
 }
 
 // =================================================================================================
@@ -1138,18 +1105,6 @@ template <int Lf, int NL> static int launch_lines(fen_ctx* c, const LArgs& a, in
         if (mode == 0 && !sc) FEN_LAUNCH(c, "fft_lines_fwd", k_fft_lines_r<Lf, -1, NL, false><<<grid, block, bytes, c->stream>>>(a, none));
         if (mode == 0 && sc) FEN_LAUNCH(c, "fft_lines_fwd_a2a", k_fft_lines_r<Lf, -1, NL, true><<<grid, block, bytes, c->stream>>>(a, *sc));
         if (mode == 1) FEN_LAUNCH(c, "fft_lines_inv", k_fft_lines_r<Lf, +1, NL, false><<<grid, block, bytes, c->stream>>>(a, none));
-        // 512-point lines: the 32-values-per-thread form (FEN_SOLVE_WIDE=0 selects the radix-8 register path)
-        static const int wide = getenv("FEN_SOLVE_WIDE") ? atoi(getenv("FEN_SOLVE_WIDE")) : 3;
-        if (mode == 2 && !sc && Lf == 512 && NL == 8 && wide) {
-            FEN_ONCE_PER_DEVICE(c) {
-                FEN_CUDA(cudaFuncSetAttribute(k_fft_solve_w512<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-                FEN_CUDA(cudaFuncSetAttribute(k_fft_solve_w512<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-            }
-            if (wide == 2) FEN_LAUNCH(c, "fft_solve", k_fft_solve_w512<2><<<grid, 128, bytes, c->stream>>>(a));
-            else FEN_LAUNCH(c, "fft_solve", k_fft_solve_w512<3><<<grid, 128, bytes, c->stream>>>(a));
-            FEN_CUDA(cudaGetLastError());
-            return FEN_OK;
-        }
         if (mode == 2 && !sc) FEN_LAUNCH(c, "fft_solve", k_fft_solve_r<Lf, NL, false><<<grid, block, bytes, c->stream>>>(a, none));
         if (mode == 2 && sc) FEN_LAUNCH(c, "fft_solve_a2a", k_fft_solve_r<Lf, NL, true><<<grid, block, bytes, c->stream>>>(a, *sc));
     } else {

@@ -65,17 +65,6 @@ def test_fft_core_index_logic_on_cpu():
     assert r.returncode == 0 and "OK" in r.stdout, r.stdout
 
 
-def test_wide_fft_blocks_on_cpu():
-    """fen_b200/csrc/fft_wide.cuh (the 32-values-per-thread 512-point transform of the fused z solve): the in-register
-    16- and 32-point butterflies and both stages of the transform run on the CPU against O(n^2) DFT sums."""
-    exe = os.path.join(ROOT, "build", "test_fft_wide")
-    os.makedirs(os.path.dirname(exe), exist_ok=True)
-    subprocess.run(["nvcc", "-std=c++17", "-O1", "-Wno-deprecated-gpu-targets", "-o", exe,
-                    os.path.join(ROOT, "tests", "cpu", "test_fft_wide.cu")], check=True)
-    r = subprocess.run([exe], capture_output=True, text=True)
-    assert r.returncode == 0 and "fft512_wide" in r.stdout, r.stdout
-
-
 def test_any_length_kernels_run_on_cpu():
     """fen_b200/csrc/fft_any.cuh: the any-length Poisson kernels (non-power-of-two grids) are sequences of
     __host__ __device__ phases; tests/cpu/test_fft_any.cu runs them with blocks and threads as loops against direct
