@@ -23,6 +23,11 @@ against travel as small .npz files.  They are data, not code:
                               0.9 (columns t, D), the points shear_drop/postpro.py:44-52 plots its curves against, and the drop
                               contours shapeRe1Ca0*b.txt it draws its final vof = 0.5 contours over (:62-69).
 
+  isotropic_turbulence.npz    test/large_test/isotropic_turbulence/isotropic.basilisk, isotropic.hit3d -- kinetic energy of
+                              linearly forced isotropic turbulence (ABC flow + noise, nu = 0.01, forcing 0.1 (v - <v>)) over
+                              300 time units from Basilisk (columns t, energy) and from the spectral code hit3d (t, 1.5 x
+                              column 2), the two curves isotropic_turbulence/postpro.py:5-17 plots FEN's output.txt over.
+
 Usage (in the build container, where /root/reference is mounted):  python tests/golden/make_reference_data.py
 """
 import os
@@ -56,4 +61,9 @@ if __name__ == "__main__":
     for ca in ("02", "04", "09"):        # Basilisk's drop contours at the end of each case, box-centred coordinates
         drops["shape_Ca%s" % ca] = np.genfromtxt(os.path.join(sd, "shapeRe1Ca%sb.txt" % ca))
     np.savez_compressed(os.path.join(HERE, "shear_drop_basilisk.npz"), **drops)
+    iso = "/root/reference/test/large_test/isotropic_turbulence"
+    bas, hit = np.genfromtxt(os.path.join(iso, "isotropic.basilisk")), np.genfromtxt(os.path.join(iso, "isotropic.hit3d"))
+    assert bas.shape == (12464, 4) and hit.shape == (1438, 4)
+    np.savez_compressed(os.path.join(HERE, "isotropic_turbulence.npz"), basilisk=bas[::4, [0, 2]],
+                        hit3d=np.stack([hit[:, 0], 1.5 * hit[:, 2]], axis=1))       # postpro.py:15-16
     print("wrote", curve.shape, com.shape, shape1.shape, uref.shape, vref.shape, {k: v.shape for k, v in drops.items()})

@@ -86,6 +86,7 @@ class Solver:
     def _wrap(self):
         ns = self.ns
         self.v = _V(ns.v); self.p = _S(ns.p); self.phi = _S(ns.phi)
+        if hasattr(ns, "S"): self.S = _V(ns.S)
     @property
     def poisson_variant(self): return self.ns.poisson.variant
     def set_timestep(self, U): return self.ns.set_timestep(U)
