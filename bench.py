@@ -752,10 +752,11 @@ def nvlink_figures(args, tk, nx, ny, nz, world, nccl=True):
           "bwd_ms": bwd, "bwd_bus_GBs": sent / (bwd * 1e-3) / 1e9 if bwd else None,
           "note": "y<->z transposes = epilogues of the y-FFT / z-solve kernels: the transformed tile goes from shared "
                   "memory to the owning ranks as one bulk store (cp.async.bulk) of blk x 128 bytes per destination; "
-                  "time = that kernel + the flag handshake on this rank, summed over the pieces of the chunked solve and "
-                  "measured with the pieces SERIALISED on one stream (per-kernel profiling), so the figure is a lower "
-                  "bound of the link rate (it includes the transform itself); in the timed region the pieces overlap "
-                  "with the x pass / y inverse of their neighbours; measured_peer_copy = B200_PROFILING.md's 770 GB/s"}
+                  "time = that kernel + the flag handshake on this rank, measured in the profiled steps, where the solve "
+                  "runs in ONE piece on one stream, so the figure is a lower bound of the link rate (it includes the "
+                  "transform itself); in the timed region the solve runs in pieces that overlap with the x pass / y "
+                  "inverse of their neighbours (extra.poisson_only.value is the overlapped solve time); "
+                  "measured_peer_copy = B200_PROFILING.md's 770 GB/s"}
     for kname in ("fwd", "bwd"):
         v = nv[kname + "_bus_GBs"]
         nv[kname + "_frac"] = v / 900.0 if v else None
@@ -1003,7 +1004,7 @@ def run_ns_case(args, cx, case, steps, headline):
         "cpu_baseline": cpu, "kernels": kernels, "nvlink": nvlink,
         "poisson_solve_ms": poisson_ms,
         "poisson_solve_ms_what": "sum of the solver's kernels in the profiled steps" + (
-            " (several ranks: the pieces of the chunked solve run serialised there; the overlapped solve time is "
+            " (several ranks: the solve runs in one piece on one stream there; the overlapped solve time is "
             "extra.poisson_only.value)" if world > 1 else ""),
         "check": {"maxdiv": maxdiv, "maxCFL": maxcfl},
     }

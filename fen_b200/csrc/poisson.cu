@@ -1283,11 +1283,12 @@ static int poisson_build(fen_ctx* c) {
             const size_t nC = (size_t)p->PC * g.ny * p->nzl;
             FEN_CUDA(cudaMalloc(&p->Cr, nC * sizeof(double2)));
             FEN_CUDA(cudaMemsetAsync(p->Cr, 0, nC * sizeof(double2), c->stream));
-            // FEN_SLAB_CHUNKS = pieces of the overlapped transposes (1 = no overlap, one stream); default 4 from 4 ranks
-            // on, 1 on 2 ranks (there the transposing kernels are as much HBM- as link-bound and overlap gains nothing:
-            // 7.82 ms unchunked, 7.82 - 7.96 chunked, profiles/r02h_*.json)
+            // FEN_SLAB_CHUNKS = pieces of the overlapped transposes (1 = no overlap, one stream).  Default: 4 for ppp from
+            // 4 ranks on (8 GPUs: 9.26 -> 9.07 ms/step, 4 GPUs: 8.81 -> 8.59, profiles/r02i_*, r02n_*), 1 otherwise: on 2
+            // ranks the transposing kernels are as much HBM- as link-bound (7.82 vs 7.82 - 7.96 ms, r02h_*), and the
+            // Thomas path of ppn loses with pieces (channel at 8 GPUs: 5.71 ms unchunked, 5.98 in 4 pieces, r02d / r02o)
             const char* e = getenv("FEN_SLAB_CHUNKS");
-            p->nchunk = std::max(1, std::min(FEN_MAX_CHUNKS, e ? atoi(e) : (g.nranks >= 4 ? 4 : 1)));
+            p->nchunk = std::max(1, std::min(FEN_MAX_CHUNKS, e ? atoi(e) : (g.nranks >= 4 && is_ppp ? 4 : 1)));
             p->nchunk = std::min(p->nchunk, std::min(p->nzl, p->PC / 8));
             if (p->nchunk > 1) {
                 int lo = 0, hi = 0;
@@ -1448,7 +1449,9 @@ static int solve_blocked(fen_ctx* c, Poisson* p, bool ppp, XArgs xa, bool fuse_r
     const long long ny = g.ny, nz = g.nz, nyl = p->nyl, nzl = p->nzl;
     cudaStream_t S = c->stream, T = (c->profiling || !p->aux) ? c->stream : p->aux;
     const bool two = T != S;
-    const int nq = p->nchunk;
+    // per-kernel profiling: one piece, one stream -- the kernel table then shows whole passes (and the transposes' GB/s
+    // figures are those of the whole transfer, without the tails of four short launches)
+    const int nq = c->profiling ? 1 : p->nchunk;
     // grid cap of the persistent transposing kernels while they share the GPU with the pass on the other stream
     // (FEN_SLAB_SMS = SMs' worth of their blocks, default 96.  Measured at 8 GPUs, 1024-point tiles, profiles/r02i_*.json:
     // 9.26 ms/step unchunked, 9.07 / 10.13 / 11.14 ms with 4 pieces at caps of 96 / 64 / 48 SMs -- a block ships a tile
