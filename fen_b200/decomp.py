@@ -77,3 +77,52 @@ def gather_handles(all_gather, blob: bytes, nranks: int) -> bytes:
         if len(p) != n:
             raise ValueError("rank %d exported %d bytes, expected %d" % (r, len(p), n))
     return b"".join(parts)
+
+
+# ---- granule-blocked layouts of the slab transposes (fen_b200/csrc/slab_bulk.cuh) ---------------------------------
+# A granule is 8 consecutive kx (128 bytes of complex fp64).  The arrays the transposes WRITE keep the transposed index
+# next to the granule, so that what one rank receives from one tile is a single contiguous run.
+
+GRANULE = 8
+
+
+def zpencil_blocked_offset(g: int, k: int, jl: int, kxi: int, nz: int, nyl: int) -> int:
+    """Element offset of (granule g, global plane k, local line jl, kx % 8) in the z-pencil array
+    ``Cz[((g*nz + k)*nyl + jl)*8 + kxi]`` a rank holds after transpose_y_to_z."""
+    return ((g * nz + k) * nyl + jl) * GRANULE + kxi
+
+
+def yslab_blocked_offset(g: int, j: int, zl: int, kxi: int, ny: int, nzl: int) -> int:
+    """Element offset of (granule g, global line j, local plane zl, kx % 8) in the y-slab array
+    ``Cy[((g*ny + j)*nzl + zl)*8 + kxi]`` a rank holds after transpose_z_to_y."""
+    return ((g * ny + j) * nzl + zl) * GRANULE + kxi
+
+
+def forward_runs(ny: int, nz: int, nranks: int, rank: int, g: int, zl: int):
+    """What the y-forward kernel ships for its tile (granule g, local plane zl) -- all ny line elements of 8 kx: one run
+    per destination, in the order the kernel issues them (rank + 1 first, own rank last).  Returns a list of
+    ``(dest, j_first, n_elements, dest_offset)``: the elements j_first .. j_first + nyl - 1 (x 8 kx) of the tile, which
+    are contiguous in the tile (``tile[j*8 + kxi]``) and land contiguously at ``dest_offset`` of dest's Cz."""
+    nyl, nzl = ny // nranks, nz // nranks
+    out = []
+    for q in range(1, nranks + 1):
+        dest = (rank + q) % nranks
+        out.append((dest, dest * nyl, nyl * GRANULE, zpencil_blocked_offset(g, rank * nzl + zl, 0, 0, nz, nyl)))
+    return out
+
+
+def backward_runs(ny: int, nz: int, nranks: int, rank: int, g: int, jl: int):
+    """The same for the z-solve kernel's tile (granule g, local line jl) -- all nz plane elements of 8 kx:
+    ``(dest, k_first, n_elements, dest_offset)`` into dest's Cy."""
+    nyl, nzl = ny // nranks, nz // nranks
+    out = []
+    for q in range(1, nranks + 1):
+        dest = (rank + q) % nranks
+        out.append((dest, dest * nzl, nzl * GRANULE, yslab_blocked_offset(g, rank * nyl + jl, 0, 0, ny, nzl)))
+    return out
+
+
+def pieces(n: int, nq: int):
+    """Index ranges [lo, hi) of the nq pieces a chunked transpose cuts n planes / granules into (poisson.cu:
+    solve_blocked); empty pieces are skipped."""
+    return [(n * q // nq, n * (q + 1) // nq) for q in range(nq) if n * (q + 1) // nq > n * q // nq]

@@ -1,5 +1,6 @@
 """World-size-2 (and 4) `gloo` tests of the N > 1 HOST logic on CPU: slab / z-pencil bounds, neighbour wiring,
-transpose block map, rank-ordered handle gather, slab-wise initial condition, max-over-ranks timing rule.
+transpose block map, rank-ordered handle gather, slab-wise initial condition, max-over-ranks timing rule, and the
+granule-blocked layouts + run descriptors of the bulk-store transposes (carried out between the ranks for real).
 The device side of the multi-GPU path is covered by tests/test_gpu_multirank.py and test_gpu_multiprocess.py."""
 import os
 import socket
@@ -96,6 +97,55 @@ def _worker(rank, world, port, q):
         dist.all_gather_object(allsched, [dst for dst, _ in sched])
         for pos in range(len(sched)):
             assert len({allsched[r][pos] for r in range(world)}) == world
+        # 9. the granule-blocked transposes of slab_bulk.cuh, carried out for real between the ranks: every rank fills the
+        #    tiles its kernels would hold with a global index code, ships the runs decomp.forward_runs / backward_runs
+        #    describe (gloo all_to_all of the concatenated runs), places them at the stated offsets, and finds at every
+        #    blocked offset of its z-pencil / y-slab array exactly the element the layout formulas name -- in 1, 2 and 3
+        #    pieces of the chunked solve
+        NG, nyb, nzb = 2, 4 * world, 2 * world                    # granules, ny, nz
+        nyl, nzl = nyb // world, nzb // world
+        code = lambda g_, kxi, j, k: ((g_ * 8 + kxi) * nyb + j) * nzb + k      # noqa: E731
+        for nq in (1, 2, 3):
+            Cz = np.full(NG * nzb * nyl * 8, -1, dtype=np.int64)
+            send = [[] for _ in range(world)]
+            for (z0, z1) in decomp.pieces(nzl, nq):               # forward pieces = z planes
+                for zl in range(z0, z1):
+                    for g_ in range(NG):
+                        tile = np.array([code(g_, kxi, j, rank * nzl + zl) for j in range(nyb) for kxi in range(8)])
+                        for dest, j0, n, off in decomp.forward_runs(nyb, nzb, world, rank, g_, zl):
+                            send[dest].append((off, tile[j0 * 8: j0 * 8 + n]))
+            allsend = [None] * world
+            dist.all_gather_object(allsend, send)
+            for src in range(world):
+                for off, run in allsend[src][rank]:
+                    assert (Cz[off: off + len(run)] == -1).all()  # nobody else writes there
+                    Cz[off: off + len(run)] = run
+            for g_ in range(NG):
+                for k in range(nzb):
+                    for jl in range(nyl):
+                        for kxi in range(8):
+                            assert Cz[decomp.zpencil_blocked_offset(g_, k, jl, kxi, nzb, nyl)] == \
+                                code(g_, kxi, rank * nyl + jl, k)
+            Cy = np.full(NG * nyb * nzl * 8, -1, dtype=np.int64)
+            send = [[] for _ in range(world)]
+            for (g0, g1) in decomp.pieces(NG, nq):                # backward pieces = granules
+                for g_ in range(g0, g1):
+                    for jl in range(nyl):
+                        tile = np.array([Cz[decomp.zpencil_blocked_offset(g_, k, jl, kxi, nzb, nyl)]
+                                         for k in range(nzb) for kxi in range(8)])
+                        for dest, k0, n, off in decomp.backward_runs(nyb, nzb, world, rank, g_, jl):
+                            send[dest].append((off, tile[k0 * 8: k0 * 8 + n]))
+            dist.all_gather_object(allsend, send)
+            for src in range(world):
+                for off, run in allsend[src][rank]:
+                    assert (Cy[off: off + len(run)] == -1).all()
+                    Cy[off: off + len(run)] = run
+            for g_ in range(NG):
+                for j in range(nyb):
+                    for zl in range(nzl):
+                        for kxi in range(8):
+                            assert Cy[decomp.yslab_blocked_offset(g_, j, zl, kxi, nyb, nzl)] == \
+                                code(g_, kxi, j, rank * nzl + zl)
         q.put((rank, "ok"))
     except Exception as e:  # pragma: no cover
         import traceback
