@@ -48,7 +48,7 @@ run(ty.test_scalar_laplacian_face_to_center_curl, (32, 16, 1), 2)
 run(ty.test_poiseuille_inflow_outflow_steps_match_oracle)
 run(tz.test_rising_bubble_steps_match_oracle)
 run(tp.test_one_step_512_matches_c_oracle, 64)
-run(tx.run_case, 16, 0.5)
+run(tx.run_case, 16, 0.5, 2)
 run(tz.test_rising_bubble_rises_and_keeps_its_volume)
 print("FAILED %d" % failed if failed else "ALL PASS")
 sys.exit(1 if failed else 0)
