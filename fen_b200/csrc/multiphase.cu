@@ -90,32 +90,57 @@ struct SweepArgs {
 };
 
 // DIR 1: x, 2: y.  FINAL: second sweep fused with the update to time n+1 (:492-498 / :532-538).
+// Every face flux is evaluated ONCE (the reference's compute_flux evaluates it from both sides): the flux through the
+// + face of a cell is the flux through the - face of its neighbour, same upwind cell, same arguments, same bits.
+//   x sweep: the - face flux of cell i is the + face flux lane - 1 of the warp computed (shuffle); lane 0 evaluates its own;
+//   y sweep: a thread marches SWEEP_RY consecutive rows and carries the + face flux of row j as the - face flux of row j+1.
+constexpr int SWEEP_RY = 8;
 template <int DIR, bool FINAL>
 __global__ void __launch_bounds__(MTX* MTY) k_vof_sweep(SweepArgs a) {
     const int i = blockIdx.x * MTX + threadIdx.x + 1;
-    const int j = blockIdx.y * MTY + threadIdx.y + 1;
-    if (i > a.L.nx || j > a.L.ny) return;
-    const long long c = a.L.idx(i, j, 1);
     const long long s = DIR == 1 ? 1 : a.L.sy;
     const double* __restrict__ vel = DIR == 1 ? a.u : a.v;
-    const double up = vel[c], um = vel[c - s];
-    const long long cp = up >= 0.0 ? c : c + s;             // upwind cell of the + face (:567-581)
-    const long long cm = um >= 0.0 ? c - s : c;             // upwind cell of the - face
-    const double fp = vof_flux(DIR, up, a.dt, a.delta, a.beta, a.cut, a.src[cp], a.nx[cp], a.ny[cp], a.lx[cp],
-                               a.ly[cp], a.d[cp]);
-    const double fm = vof_flux(DIR, um, a.dt, a.delta, a.beta, a.cut, a.src[cm], a.nx[cm], a.ny[cm], a.lx[cm],
-                               a.ly[cm], a.d[cm]);
-    const double s0 = a.src[c];
-    const double val = (s0 - (fp - fm) / a.delta) / (1.0 - a.dt * (up - um) / a.delta);
-    if (!FINAL) {
-        a.out[c] = val;
-        return;
+    auto face = [&](long long c, double uf) {                // flux through the + face of cell c, face velocity uf
+        const long long cu = uf >= 0.0 ? c : c + s;          // upwind cell (:567-581)
+        return vof_flux(DIR, uf, a.dt, a.delta, a.beta, a.cut, a.src[cu], a.nx[cu], a.ny[cu], a.lx[cu], a.ly[cu], a.d[cu]);
+    };
+    auto finish = [&](long long c, double up, double um, double fp, double fm) {
+        const double s0 = a.src[c];
+        const double val = (s0 - (fp - fm) / a.delta) / (1.0 - a.dt * (up - um) / a.delta);
+        if (!FINAL) {
+            a.out[c] = val;
+            return;
+        }
+        // here src = vof1 and val = vof2
+        const double dux = a.u[c] - a.u[c - 1];
+        const double dvy = a.v[c] - a.v[c - a.L.sy];
+        if (a.x_first) a.out[c] = val - a.dt * (s0 * dux / a.delta + val * dvy / a.delta);
+        else a.out[c] = val - a.dt * (val * dux / a.delta + s0 * dvy / a.delta);
+    };
+    if (DIR == 1) {
+        const int j = blockIdx.y * MTY + threadIdx.y + 1;
+        const bool valid = i <= a.L.nx && j <= a.L.ny;
+        const long long c = a.L.idx(valid ? i : 1, valid ? j : 1, 1);
+        const double up = vel[c], um = vel[c - s];
+        const double fp = valid ? face(c, up) : 0.0;
+        double fm = __shfl_up_sync(0xffffffffu, fp, 1);      // lane - 1 holds cell i - 1 of the same row (MTX % 32 == 0)
+        if ((threadIdx.x & 31) == 0 && valid) fm = face(c - s, um);
+        if (valid) finish(c, up, um, fp, fm);
+    } else {
+        if (i > a.L.nx) return;
+        const int j0 = (blockIdx.y * MTY + threadIdx.y) * SWEEP_RY + 1;
+        if (j0 > a.L.ny) return;
+        long long c = a.L.idx(i, j0, 1);
+        double um = vel[c - s];
+        double fm = face(c - s, um);
+        for (int r = 0; r < SWEEP_RY && j0 + r <= a.L.ny; ++r, c += s) {
+            const double up = vel[c];
+            const double fp = face(c, up);
+            finish(c, up, um, fp, fm);
+            um = up;
+            fm = fp;
+        }
     }
-    // here src = vof1 and val = vof2
-    const double dux = a.u[c] - a.u[c - 1];
-    const double dvy = a.v[c] - a.v[c - a.L.sy];
-    if (a.x_first) a.out[c] = val - a.dt * (s0 * dux / a.delta + val * dvy / a.delta);
-    else a.out[c] = val - a.dt * (val * dux / a.delta + s0 * dvy / a.delta);
 }
 
 // ---- get_vof_from_distance (:676-718): tanh profile + 2x2 Gauss quadrature from host-evaluated distances ----------
@@ -287,10 +312,11 @@ static int sweep(fen_ctx* c, int dir, bool final, int src_id, int out_id, int vx
     a.src = src; a.nx = nx; a.ny = ny; a.lx = lx; a.ly = ly; a.d = d; a.u = u; a.v = v;
     a.dt = dt; a.delta = c->g.delta; a.beta = m.beta; a.cut = m.cut; a.x_first = x_first ? 1 : 0;
     const dim3 g = mf_grid(c->L), b(MTX, MTY);
+    const dim3 gy(g.x, (c->L.ny + MTY * SWEEP_RY - 1) / (MTY * SWEEP_RY), 1);   // y sweep: SWEEP_RY rows per thread
     if (dir == 1 && !final) FEN_LAUNCH(c, "vof_sweep", k_vof_sweep<1, false><<<g, b, 0, c->stream>>>(a));
-    if (dir == 2 && !final) FEN_LAUNCH(c, "vof_sweep", k_vof_sweep<2, false><<<g, b, 0, c->stream>>>(a));
+    if (dir == 2 && !final) FEN_LAUNCH(c, "vof_sweep", k_vof_sweep<2, false><<<gy, b, 0, c->stream>>>(a));
     if (dir == 1 && final) FEN_LAUNCH(c, "vof_sweep", k_vof_sweep<1, true><<<g, b, 0, c->stream>>>(a));
-    if (dir == 2 && final) FEN_LAUNCH(c, "vof_sweep", k_vof_sweep<2, true><<<g, b, 0, c->stream>>>(a));
+    if (dir == 2 && final) FEN_LAUNCH(c, "vof_sweep", k_vof_sweep<2, true><<<gy, b, 0, c->stream>>>(a));
     FEN_CUDA(cudaGetLastError());
     return FEN_OK;
 }

@@ -957,7 +957,7 @@ int ns_checks_launch(fen_ctx* c, double dt) {
     a.idelta = 1.0 / c->g.delta;
     a.partial = c->d_red + 16;
     dim3 grid = st_grid(c->L), block(TX, TY);
-    if (!d3) grid.y = std::min<unsigned>(grid.y, 32);         // 2-D: the blocks stride over the rows (k_check)
+    if (!d3) grid.y = std::min<unsigned>(grid.y, 128);        // 2-D: the blocks stride over the rows (k_check)
     const long long nblocks = (long long)grid.x * grid.y * grid.z;
     if (d3) FEN_LAUNCH(c, "check", k_check<true><<<grid, block, 0, c->stream>>>(a));
     else FEN_LAUNCH(c, "check", k_check<false><<<grid, block, 0, c->stream>>>(a));
