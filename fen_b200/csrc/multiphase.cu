@@ -27,6 +27,27 @@ constexpr int MTX = 64, MTY = 4;
 
 static dim3 mf_grid(const Layout& L) { return dim3((L.nx + MTX - 1) / MTX, (L.ny + MTY - 1) / MTY, 1); }
 
+// Periodic x ghosts written by the PRODUCING kernel (scalar.f90:257,276: f(0,j) = f(nx,j), f(nx+1,j) = f(1,j)): when
+// every field a kernel writes is periodic in x, its edge threads store the two ghost cells of their row as well and the
+// ghost update skips its x pass (ghost.cu: x_done) -- seven tiny column-strided launches less per two-phase step.  The
+// y pass still copies whole rows, x ghosts included, so corners come out in the reference's order.
+__device__ __forceinline__ void put_x(double* f, long long c, int i, int nx, double val, int xper) {
+    f[c] = val;
+    if (xper) {
+        if (i == 1) f[c + nx] = val;
+        if (i == nx) f[c - nx] = val;
+    }
+}
+static bool x_periodic(fen_ctx* c, const int* ids, int n) {
+    static const bool off = getenv("FEN_MF_XGHOST") && atoi(getenv("FEN_MF_XGHOST")) == 0;   // cross-check switch
+    if (off) return false;
+    for (int q = 0; q < n; ++q) {
+        const Field& f = c->fields[ids[q]];
+        if (f.bc_type[FEN_LEFT] != FEN_PERIODIC || f.bc_type[FEN_RIGHT] != FEN_PERIODIC) return false;
+    }
+    return true;
+}
+
 // ---- reconstruction: compute_norm + the cell loop of get_h_from_vof -----------------------------------------------
 struct ReconArgs {
     Layout L;
@@ -34,6 +55,7 @@ struct ReconArgs {
     double *nx, *ny, *lx, *ly, *curv, *h, *d;
     double delta, idelta, idelta2, beta, cut;
     int quadratic;
+    int xper;                                 // the kernel also writes the periodic x ghosts of its seven fields
 };
 
 __global__ void __launch_bounds__(MTX* MTY, 4) k_vof_recon(ReconArgs a) {
@@ -51,8 +73,10 @@ __global__ void __launch_bounds__(MTX* MTY, 4) k_vof_recon(ReconArgs a) {
     const VofRecon r = vof_norm(s, a.delta, a.idelta, a.idelta2, a.quadratic != 0);
     double h, d;
     vof_h_d(s[1][1], r.nx, r.ny, r.lx, r.ly, a.beta, a.cut, h, d);
-    a.nx[c] = r.nx; a.ny[c] = r.ny; a.lx[c] = r.lx; a.ly[c] = r.ly; a.curv[c] = r.curv;
-    a.h[c] = h; a.d[c] = d;
+    const int nx = a.L.nx;
+    put_x(a.nx, c, i, nx, r.nx, a.xper); put_x(a.ny, c, i, nx, r.ny, a.xper); put_x(a.lx, c, i, nx, r.lx, a.xper);
+    put_x(a.ly, c, i, nx, r.ly, a.xper); put_x(a.curv, c, i, nx, r.curv, a.xper);
+    put_x(a.h, c, i, nx, h, a.xper); put_x(a.d, c, i, nx, d, a.xper);
 }
 
 // The same reconstruction with the corner normals of a 64 x 4 tile computed once in shared memory: the reference
@@ -74,8 +98,10 @@ __global__ void __launch_bounds__(VT_N, 4) k_vof_recon_tile(ReconArgs a) {
     double h, d;
     vof_h_d(v00, r.nx, r.ny, r.lx, r.ly, a.beta, a.cut, h, d);
     const long long c = a.L.idx(i, j, 1);
-    a.nx[c] = r.nx; a.ny[c] = r.ny; a.lx[c] = r.lx; a.ly[c] = r.ly; a.curv[c] = r.curv;
-    a.h[c] = h; a.d[c] = d;
+    const int nx = a.L.nx;
+    put_x(a.nx, c, i, nx, r.nx, a.xper); put_x(a.ny, c, i, nx, r.ny, a.xper); put_x(a.lx, c, i, nx, r.lx, a.xper);
+    put_x(a.ly, c, i, nx, r.ly, a.xper); put_x(a.curv, c, i, nx, r.curv, a.xper);
+    put_x(a.h, c, i, nx, h, a.xper); put_x(a.d, c, i, nx, d, a.xper);
 }
 
 // ---- directional split sweeps of advect_vof (volume_of_fluid.f90:457-538) ----------------------------------------
@@ -87,6 +113,7 @@ struct SweepArgs {
     double* out;
     double dt, delta, beta, cut;
     int x_first;                              // value of x_first when advect_vof was entered
+    int xper;                                 // the kernel also writes the periodic x ghosts of `out`
 };
 
 // DIR 1: x, 2: y.  FINAL: second sweep fused with the update to time n+1 (:492-498 / :532-538).
@@ -108,14 +135,14 @@ __global__ void __launch_bounds__(MTX* MTY) k_vof_sweep(SweepArgs a) {
         const double s0 = a.src[c];
         const double val = (s0 - (fp - fm) / a.delta) / (1.0 - a.dt * (up - um) / a.delta);
         if (!FINAL) {
-            a.out[c] = val;
+            put_x(a.out, c, i, a.L.nx, val, a.xper);
             return;
         }
         // here src = vof1 and val = vof2
         const double dux = a.u[c] - a.u[c - 1];
         const double dvy = a.v[c] - a.v[c - a.L.sy];
-        if (a.x_first) a.out[c] = val - a.dt * (s0 * dux / a.delta + val * dvy / a.delta);
-        else a.out[c] = val - a.dt * (val * dux / a.delta + s0 * dvy / a.delta);
+        if (a.x_first) put_x(a.out, c, i, a.L.nx, val - a.dt * (s0 * dux / a.delta + val * dvy / a.delta), a.xper);
+        else put_x(a.out, c, i, a.L.nx, val - a.dt * (val * dux / a.delta + s0 * dvy / a.delta), a.xper);
     };
     if (DIR == 1) {
         const int j = blockIdx.y * MTY + threadIdx.y + 1;
@@ -164,6 +191,7 @@ struct PropsArgs {
     double rho_0, rho_1, mu_0, mu_1;
     const double* p; const double* p_o; double* p_hat;     // p_hat == nullptr: material properties only
     int ccfl; double dt, dt_o;
+    int xper;                                 // the kernel also writes the periodic x ghosts of rho, mu, p_hat
 };
 __global__ void __launch_bounds__(MTX* MTY) k_mf_props(PropsArgs a) {
     const int i = blockIdx.x * MTX + threadIdx.x + 1;
@@ -171,11 +199,11 @@ __global__ void __launch_bounds__(MTX* MTY) k_mf_props(PropsArgs a) {
     if (i > a.L.nx || j > a.L.ny) return;
     const long long c = a.L.idx(i, j, 1);
     const double f = a.vof[c];
-    a.rho[c] = a.rho_1 * f + a.rho_0 * (1.0 - f);
-    a.mu[c] = a.mu_1 * f + a.mu_0 * (1.0 - f);
+    put_x(a.rho, c, i, a.L.nx, a.rho_1 * f + a.rho_0 * (1.0 - f), a.xper);
+    put_x(a.mu, c, i, a.L.nx, a.mu_1 * f + a.mu_0 * (1.0 - f), a.xper);
     if (a.p_hat) {
         const double p = a.p[c], po = a.p_o[c];
-        a.p_hat[c] = a.ccfl ? po + (a.dt + a.dt_o) * (p - po) / a.dt_o : 2.0 * p - po;
+        put_x(a.p_hat, c, i, a.L.nx, a.ccfl ? po + (a.dt + a.dt_o) * (p - po) / a.dt_o : 2.0 * p - po, a.xper);
     }
 }
 
@@ -186,6 +214,7 @@ struct MfPredArgs {
     const double *sx, *sy;                    // may be null (S == 0)
     double *dvox, *dvoy, *un, *vn;
     MfPrm k;
+    int xper;                                 // the kernel also writes the periodic x ghosts of un, vn
 };
 __global__ void __launch_bounds__(MTX* MTY, 4) k_mf_pred(MfPredArgs a) {
     const int i = blockIdx.x * MTX + threadIdx.x + 1;
@@ -213,7 +242,7 @@ __global__ void __launch_bounds__(MTX* MTY, 4) k_mf_pred(MfPredArgs a) {
     q.dvox = a.dvox[c]; q.dvoy = a.dvoy[c];
     double un, vn, dvx, dvy;
     mf_predict_cell(q, a.k, un, vn, dvx, dvy);
-    a.un[c] = un; a.vn[c] = vn;
+    put_x(a.un, c, i, a.L.nx, un, a.xper); put_x(a.vn, c, i, a.L.nx, vn, a.xper);
     a.dvox[c] = dvx; a.dvoy[c] = dvy;               // dv_o = dv (:201-202)
 }
 
@@ -230,17 +259,17 @@ __global__ void __launch_bounds__(MTX* MTY) k_mf_rhs(Layout L, const double* u, 
 
 // correct_velocity_field (MF branch, :526-528) + update_pressure (:557, :561)
 __global__ void __launch_bounds__(MTX* MTY) k_mf_corr(Layout L, double* u, double* v, double* p, double* p_o,
-                                                     const double* phi, double id, double dt, double irhomin) {
+                                                     const double* phi, double id, double dt, double irhomin, int xper) {
     const int i = blockIdx.x * MTX + threadIdx.x + 1;
     const int j = blockIdx.y * MTY + threadIdx.y + 1;
     if (i > L.nx || j > L.ny) return;
     const long long c = L.idx(i, j, 1);
     const double f0 = phi[c];
-    u[c] = u[c] - ((phi[c + 1] - f0) * id) * dt * irhomin;
-    v[c] = v[c] - ((phi[c + L.sy] - f0) * id) * dt * irhomin;
+    put_x(u, c, i, L.nx, u[c] - ((phi[c + 1] - f0) * id) * dt * irhomin, xper);
+    put_x(v, c, i, L.nx, v[c] - ((phi[c + L.sy] - f0) * id) * dt * irhomin, xper);
     const double p0 = p[c];
-    p_o[c] = p0;
-    p[c] = p0 + f0;
+    put_x(p_o, c, i, L.nx, p0, xper);
+    put_x(p, c, i, L.nx, p0 + f0, xper);
 }
 
 // ---- host side ---------------------------------------------------------------------------------------------------
@@ -288,6 +317,9 @@ static int recon(fen_ctx* c, int src_id) {
     a.idelta = 1.0 / a.delta;
     a.idelta2 = 1.0 / (a.delta * a.delta);
     a.beta = m.beta; a.cut = m.cut; a.quadratic = m.quadratic;
+    const int ids[7] = {FEN_CURV, FEN_NORMX, FEN_NORMY, FEN_LX, FEN_LY, FEN_H, FEN_D};
+    const bool xp = x_periodic(c, ids, 7);
+    a.xper = xp ? 1 : 0;
     // FEN_VOF_TILE=0: one thread evaluates all four corners of its cell (the first version; cross-check switch)
     static const bool tile = !getenv("FEN_VOF_TILE") || atoi(getenv("FEN_VOF_TILE")) != 0;
     static_assert(VT_X == MTX && VT_Y == MTY, "the tiled reconstruction uses the 64 x 4 blocks of mf_grid");
@@ -295,8 +327,7 @@ static int recon(fen_ctx* c, int src_id) {
     else FEN_LAUNCH(c, "vof_recon", k_vof_recon<<<mf_grid(c->L), dim3(MTX, MTY), 0, c->stream>>>(a));
     FEN_CUDA(cudaGetLastError());
     // curv, norm, l (:392-394) and h, d (:299-300): seven fields, one launch per direction
-    const int ids[7] = {FEN_CURV, FEN_NORMX, FEN_NORMY, FEN_LX, FEN_LY, FEN_H, FEN_D};
-    return ghost_update_list(c, ids, 7);
+    return ghost_update_list(c, ids, 7, xp);
 }
 
 static int sweep(fen_ctx* c, int dir, bool final, int src_id, int out_id, int vx, double dt, bool x_first) {
@@ -311,6 +342,7 @@ static int sweep(fen_ctx* c, int dir, bool final, int src_id, int out_id, int vx
     FEN_TRY(fptr(c, out_id, &a.out));
     a.src = src; a.nx = nx; a.ny = ny; a.lx = lx; a.ly = ly; a.d = d; a.u = u; a.v = v;
     a.dt = dt; a.delta = c->g.delta; a.beta = m.beta; a.cut = m.cut; a.x_first = x_first ? 1 : 0;
+    a.xper = x_periodic(c, &out_id, 1) ? 1 : 0;       // the caller's ghost update of out_id skips its x pass then
     const dim3 g = mf_grid(c->L), b(MTX, MTY);
     const dim3 gy(g.x, (c->L.ny + MTY * SWEEP_RY - 1) / (MTY * SWEEP_RY), 1);   // y sweep: SWEEP_RY rows per thread
     if (dir == 1 && !final) FEN_LAUNCH(c, "vof_sweep", k_vof_sweep<1, false><<<g, b, 0, c->stream>>>(a));
@@ -343,11 +375,15 @@ static int advect_vof(fen_ctx* c, int vx, double dt) {
             f.bc_type[q] = t.bc_type[q]; f.bc_mode[q] = BC_ZERO; f.bc_value[q] = 0.0;
         }
     }
-    FEN_TRY(ghost_update(c, FEN_VOF1, 1));                                 // :471 (the data of vof is vof1's)
+    {
+        const int id1 = FEN_VOF1;                                          // :471 (the data of vof is vof1's)
+        FEN_TRY(ghost_update(c, FEN_VOF1, 1, x_periodic(c, &id1, 1)));
+    }
     FEN_TRY(recon(c, FEN_VOF1));                                           // :472
     FEN_TRY(sweep(c, xf ? 2 : 1, true, FEN_VOF1, FEN_VOF, vx, dt, xf));    // :478-498 / :516-538
     m.x_first = xf ? 0 : 1;                                                // :500 / :540
-    return ghost_update(c, FEN_VOF, 1);                                    // :546
+    const int id0 = FEN_VOF;
+    return ghost_update(c, FEN_VOF, 1, x_periodic(c, &id0, 1));            // :546
 }
 
 static int material_properties(fen_ctx* c, bool with_phat, double dt) {
@@ -368,10 +404,12 @@ static int material_properties(fen_ctx* c, bool with_phat, double dt) {
         a.ccfl = c->prm.constant_CFL ? 1 : 0;
     }
     a.p = p; a.p_o = po;
+    const int ids[3] = {FEN_RHO, FEN_MU, FEN_PHAT};                        // multiphase.f90:134-135, navier_stokes.f90:95
+    const bool xp = x_periodic(c, ids, with_phat ? 3 : 2);
+    a.xper = xp ? 1 : 0;
     FEN_LAUNCH(c, "mf_props", k_mf_props<<<mf_grid(c->L), dim3(MTX, MTY), 0, c->stream>>>(a));
     FEN_CUDA(cudaGetLastError());
-    const int ids[3] = {FEN_RHO, FEN_MU, FEN_PHAT};                        // multiphase.f90:134-135, navier_stokes.f90:95
-    return ghost_update_list(c, ids, with_phat ? 3 : 2);
+    return ghost_update_list(c, ids, with_phat ? 3 : 2, xp);
 }
 
 int mf_step_front(fen_ctx* c, double dt) {
@@ -404,10 +442,13 @@ int mf_predict(fen_ctx* c, double dt) {
     a.k.g0 = c->prm.g[0]; a.k.g1 = c->prm.g[1];
     a.k.sigma = m.sigma; a.k.irhomin = m.irhomin;
     a.k.has_source = c->has_source ? 1 : 0;
+    const int vids[2] = {FEN_VX, FEN_VY};
+    const bool xp = x_periodic(c, vids, 2);
+    a.xper = xp ? 1 : 0;
     FEN_LAUNCH(c, "mf_pred", k_mf_pred<<<mf_grid(c->L), dim3(MTX, MTY), 0, c->stream>>>(a));
     FEN_CUDA(cudaGetLastError());
     for (int q = 0; q < 2; ++q) std::swap(c->fields[FEN_VX + q].d, c->vnew[q]);
-    return ghost_update(c, FEN_VX, 2);                // :208
+    return ghost_update(c, FEN_VX, 2, xp);            // :208
 }
 
 int mf_poisson_rhs(fen_ctx* c, double dt) {
@@ -423,12 +464,13 @@ int mf_correct(fen_ctx* c, double dt) {
     double *u, *v, *p, *po, *phi;
     FEN_TRY(fptr(c, FEN_VX, &u)); FEN_TRY(fptr(c, FEN_VY, &v)); FEN_TRY(fptr(c, FEN_P, &p));
     FEN_TRY(fptr(c, FEN_PO, &po)); FEN_TRY(fptr(c, FEN_PHI, &phi));
-    FEN_LAUNCH(c, "corr", k_mf_corr<<<mf_grid(c->L), dim3(MTX, MTY), 0, c->stream>>>(
-                              c->L, u, v, p, po, phi, 1.0 / c->g.delta, dt, c->mf->prm.irhomin));
-    FEN_CUDA(cudaGetLastError());
     // v (:544), p (:564) and p_o (p_o%f = p%f copies p's ghosts too, :557; same boundary types as p)
     const int ids[4] = {FEN_VX, FEN_VY, FEN_PO, FEN_P};
-    return ghost_update_list(c, ids, 4);
+    const bool xp = x_periodic(c, ids, 4);
+    FEN_LAUNCH(c, "corr", k_mf_corr<<<mf_grid(c->L), dim3(MTX, MTY), 0, c->stream>>>(
+                              c->L, u, v, p, po, phi, 1.0 / c->g.delta, dt, c->mf->prm.irhomin, xp ? 1 : 0));
+    FEN_CUDA(cudaGetLastError());
+    return ghost_update_list(c, ids, 4, xp);
 }
 
 int mf_set_timestep(fen_ctx* c, double U, double* dt) {
