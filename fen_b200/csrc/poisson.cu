@@ -67,12 +67,20 @@ struct Poisson {
 // into that rank's array (mapped peer memory, comm.cu) at the position the next stage reads it from.
 struct ScArgs {
     double2* peer[FEN_MAX_RANKS];
-    int sh, mask;          // blk = 1 << sh
+    int sh, mask;          // blk = 1 << sh; sh < 0: blk is not a power of two (row-copy transposes of any-length grids)
     long long dsl, dso;    // strides of (idx % blk) and of the outer index in the destination
     int o0;                // global offset of this rank's outer index in the destination
+    int blk;
 };
 __device__ __forceinline__ double2* sc_dst(const ScArgs& q, int kx, int idx, int outer) {
-    return q.peer[idx >> q.sh] + kx + q.dsl * (idx & q.mask) + q.dso * (q.o0 + outer);
+    const int r = q.sh >= 0 ? idx >> q.sh : idx / q.blk;
+    const int e = q.sh >= 0 ? idx & q.mask : idx - r * q.blk;
+    return q.peer[r] + kx + q.dsl * e + q.dso * (q.o0 + outer);
+}
+static void sc_block(ScArgs& q, int blk) {            // host: the rank that owns idx is idx / blk
+    q.blk = blk;
+    q.sh = -1; q.mask = 0;
+    if (blk > 0 && (blk & (blk - 1)) == 0) { q.sh = 0; while ((1 << q.sh) < blk) ++q.sh; q.mask = blk - 1; }
 }
 
 static inline double f32(long long n) { return (double)(float)n; }   // Fortran float(n), hazard H1
@@ -1253,9 +1261,12 @@ static int poisson_build(fen_ctx* c) {
     if (g.nx < 2 || (!tx && !any_supported(g.nx)) || (!ty && !any_supported(g.ny)) || (!tz && !any_supported(g.nz)))
         return set_error(FEN_ERR_UNSUPPORTED, "transform sizes must be products of primes <= %d, 2..%d points "
                                               "(got %d %d %d)", ANY_MAX_RADIX, ANY_MAX_L, g.nx, g.ny, g.nz);
-    if (multi_rank && !(tx && ty && tz))
-        return set_error(FEN_ERR_UNSUPPORTED, "on several ranks the transform sizes must be powers of two up to 2048 "
-                                              "(cosine transforms: 1024); got %d %d %d", g.nx, g.ny, g.nz);
+    // several ranks: the tuned power-of-two kernels ship their lines themselves (fused epilogues / bulk stores); any
+    // other supported length runs its passes in place and the y <-> z transposes as staggered row copies
+    // (k_a2a_scatter) -- periodic x only (the cosine-transform variants on slabs stay powers of two)
+    if (multi_rank && !(tx && ty && tz) && dctx)
+        return set_error(FEN_ERR_UNSUPPORTED, "on several ranks the cosine-transform variants need powers of two up to "
+                                              "1024; got %d %d %d", g.nx, g.ny, g.nz);
     Poisson* p = new Poisson();
     c->ps = p;
     snprintf(p->variant, sizeof(p->variant), "%s", var);
@@ -1265,10 +1276,9 @@ static int poisson_build(fen_ctx* c) {
     p->nyl = g.ny;
     if (g.nranks > 1 && g.ndim == 3) {
         // the spectral arrays live in the comm arena so that the peers can store into them
-        if (g.ny % g.nranks || !pow2(g.nranks) || !pow2(g.ny / g.nranks) || !pow2(c->L.nzl))
-            return set_error(FEN_ERR_UNSUPPORTED, "slab transposes need a power-of-two number of ranks and "
-                                                  "power-of-two ny / nranks, nz / nranks (got %d, %d, %d)",
-                             g.nranks, g.ny, g.nz);
+        if (g.ny % g.nranks || g.nz % g.nranks)
+            return set_error(FEN_ERR_UNSUPPORTED, "slab transposes need ny and nz divisible by the number of ranks "
+                                                  "(got %d ranks, ny %d, nz %d)", g.nranks, g.ny, g.nz);
         p->multi = true;                      // before any arena pointer is stored: poisson_destroy must not free them
         FEN_TRY(comm_spectral(c, p->peerC, p->peerCz));
         p->nyl = g.ny / g.nranks;
@@ -1580,9 +1590,9 @@ int poisson_solve(fen_ctx* c, double* f, bool fuse_rhs, double dt) {
         memset(&sb, 0, sizeof(sb));
         if (multi) {
             for (int r = 0; r < g.nranks; ++r) { sf.peer[r] = p->peerCz[r]; sb.peer[r] = p->peerC[r]; }
-            sf.sh = log2i(p->nyl); sf.mask = p->nyl - 1;
+            sc_block(sf, p->nyl);
             sf.dsl = p->PC; sf.dso = (long long)p->PC * p->nyl; sf.o0 = g.rank * p->nzl;
-            sb.sh = log2i(p->nzl); sb.mask = p->nzl - 1;
+            sc_block(sb, p->nzl);
             sb.dsl = (long long)p->PC * g.ny; sb.dso = p->PC; sb.o0 = g.rank * p->nyl;
         }
         if (nn) {
@@ -1652,25 +1662,37 @@ int poisson_solve(fen_ctx* c, double* f, bool fuse_rhs, double dt) {
         memset(&sb, 0, sizeof(sb));
         if (multi) {
             for (int r = 0; r < g.nranks; ++r) { sf.peer[r] = p->peerCz[r]; sb.peer[r] = p->peerC[r]; }
-            sf.sh = log2i(p->nyl); sf.mask = p->nyl - 1;
+            sc_block(sf, p->nyl);
             sf.dsl = p->PC; sf.dso = (long long)p->PC * p->nyl; sf.o0 = g.rank * p->nzl;
-            sb.sh = log2i(p->nzl); sb.mask = p->nzl - 1;
+            sc_block(sb, p->nzl);
             sb.dsl = (long long)p->PC * g.ny; sb.dso = p->PC; sb.o0 = g.rank * p->nyl;
         }
         if (p->blocked) {
             FEN_TRY(solve_blocked(c, p, ppp, xa, fuse_rhs, &dv));
             xa.C = p->Cr;                                      // the y inverse left the rows there
         } else {
+        // the fused epilogues need power-of-two lines and blocks; any other length (the any-length kernels of
+        // fft_any.cuh, or an odd number of ranks) transforms in place and ships whole rows with k_a2a_scatter
+        const bool rowcopy = multi && (!tuned_len(g.ny, 2048) || (ppp && !tuned_len(g.nz, 2048)) || sf.sh < 0 || sb.sh < 0);
         la.C = p->C; la.sl = p->PC; la.so = (long long)p->PC * g.ny; la.tw = p->tw_y;
         la.scale = ppn ? 1.0 / f32(g.ny) : 1.0;
-        FEN_TRY(dispatch_lines(c, g.ny, la, 0, p->PC, p->nzl, multi ? &sf : nullptr));
+        FEN_TRY(dispatch_lines(c, g.ny, la, 0, p->PC, p->nzl, multi && !rowcopy ? &sf : nullptr));
+        if (rowcopy) {
+            FEN_LAUNCH(c, "a2a_scatter", k_a2a_scatter<<<dim3(g.ny, p->nzl), 256, 0, c->stream>>>(
+                                             p->C, (long long)p->PC, (long long)p->PC * g.ny, p->PC, g.nranks, g.rank,
+                                             p->nyl, sf));
+            FEN_CUDA(cudaGetLastError());
+        }
         if (multi) FEN_TRY(comm_transpose_fwd(c));
         double2* Z = p->Cz;
         const long long slz = (long long)p->PC * p->nyl;
         if (ppp) {
             la.C = Z; la.sl = slz; la.so = p->PC; la.tw = p->tw_z; la.scale = 1.0; la.o0 = multi ? g.rank * p->nyl : 0;
             la.lo = p->mwn_y; la.ll = p->mwn_z; la.norm = f32((long long)g.nx * g.ny * g.nz);
-            FEN_TRY(dispatch_lines(c, g.nz, la, 2, p->PC, p->nyl, multi ? &sb : nullptr));
+            FEN_TRY(dispatch_lines(c, g.nz, la, 2, p->PC, p->nyl, multi && !rowcopy ? &sb : nullptr));
+            if (rowcopy)
+                FEN_LAUNCH(c, "a2a_scatter", k_a2a_scatter<<<dim3(g.nz, p->nyl), 256, 0, c->stream>>>(
+                                                 Z, slz, (long long)p->PC, p->PC, g.nranks, g.rank, p->nzl, sb));
         } else {
             TArgs t;
             t.C = Z; t.c1 = p->c1; t.sl = slz; t.so = p->PC; t.n = g.nz; t.npc = p->PC; t.nouter = p->nyl;

@@ -158,6 +158,48 @@ def test_slab_transpose_forms_give_the_same_bits(env):
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
 
 
+@pytest.mark.parametrize("P,n", [(2, (24, 12, 12)), (3, (20, 12, 9)), (3, (32, 24, 48))])
+@pytest.mark.parametrize("bc,variant", [(None, "ppp"), (ZWALLS, "ppn")])
+def test_poisson_any_length_on_slabs(P, n, bc, variant):
+    """Grid sizes that are not powers of two (the any-length kernels of fft_any.cuh) and a rank count that is not one
+    either, on z slabs: the passes run in place and the y <-> z transposes are staggered row copies (k_a2a_scatter with
+    the owner of a line found by division) -- same bits as one rank, and the oracle's answer."""
+    L = (1.0, 1.0 * n[1] / n[0], 1.0 * n[2] / n[0])
+    rng = np.random.default_rng(19)
+    rhs = np.zeros((n[0] + 2, n[1] + 2, n[2] + 2), order="F")
+    rhs[1:-1, 1:-1, 1:-1] = rng.standard_normal(n)
+    rhs[1:-1, 1:-1, 1:-1] -= rhs[1:-1, 1:-1, 1:-1].mean()
+    prog = _poisson_program(n, L, bc, rhs)
+    one = run_ranks(1, prog)[0]
+    many = run_ranks(P, prog)
+    assert one[1] == variant and all(m[1] == variant for m in many)
+    got = gather_interior([m[0] for m in many], 1)
+    assert np.array_equal(got, one[0][1:-1, 1:-1, 1:-1])
+    Go = fo.Grid(n[0], n[1], n[2], L[0], L[1], L[2], bc=bc)
+    po = fo.Scalar(Go, 1)
+    if bc is not None:
+        po.bc_type["front"] = po.bc_type["back"] = 2
+    po.f[...] = rhs
+    fo.PoissonSolver(po).solve(po)
+    ref = po.I
+    assert np.linalg.norm(got - ref) <= 1e-12 * np.linalg.norm(ref)
+
+
+def test_ns_steps_any_length_on_three_slabs():
+    """Five Taylor-Green steps on a 24 x 12 x 18 grid split over three ranks: the whole step (halos, right-hand side,
+    any-length Poisson passes, row-copy transposes, correction, checks) against one rank, bit for bit."""
+    n = (24, 12, 18)
+    L = (2 * PI, 2 * PI * n[1] / n[0], 2 * PI * n[2] / n[0])
+    prog, _ = _ns_program(n, L, None, 0.01, fo.init_tgv3d, 1.0, None, 0.25, 5)
+    one = run_ranks(1, prog)[0]
+    many = run_ranks(3, prog)
+    nzl = n[2] // 3
+    for r in range(3):
+        for m in range(4):
+            assert np.array_equal(many[r][0][m], one[0][m][:, :, r * nzl: r * nzl + nzl + 2]), (r, m)
+        assert many[r][1] == one[1]
+
+
 XZWALLS = ["Wall", "Wall", "Periodic", "Periodic", "Wall", "Wall"]
 ALLWALLS = ["Wall"] * 6
 
