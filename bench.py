@@ -768,6 +768,35 @@ def nvlink_figures(args, tk, nx, ny, nz, world, nccl=True):
     return nv
 
 
+def cufft_crosscheck(n):
+    """Performance cross-check of the hand-written Poisson passes against cuFFT (north_star: "cuFFT used only as a
+    correctness and performance cross-check"): the time of torch.fft.rfftn + a spectral divide + torch.fft.irfftn on an
+    n^3 fp64 array -- what the ppp solve does -- timed with CUDA events after warm-up.  Library code, never on the
+    product path; the correctness half is tests/test_gpu_parity.py::test_poisson_ppp_matches_cufft."""
+    import torch
+    x = torch.randn((n, n, n), device="cuda", dtype=torch.float64)
+    lam = torch.rand((n, n, n // 2 + 1), device="cuda", dtype=torch.float64) + 1.0
+
+    def solve():
+        return torch.fft.irfftn(torch.fft.rfftn(x) / lam, s=(n, n, n))
+    for _ in range(3):
+        solve()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    k = 10
+    e0.record()
+    for _ in range(k):
+        solve()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / k
+    del x, lam
+    torch.cuda.empty_cache()
+    return {"cufft_rfftn_divide_irfftn_ms": ms, "grid": [n, n, n], "dtype": "f64",
+            "what": "torch.fft (cuFFT) 3-D r2c + elementwise divide + c2r of the same size, 10 repetitions; compare with "
+                    "extra.poisson_only.value (the hand-written solve, which also carries the real-field ghost writes)"}
+
+
 def parity_vs_oracle(args, cx, ny, nz):
     """N > 1: one navier_stokes_solver step on a grid with the SAME y / z line lengths and the same slab split as the
     timed one (so the same transpose kernels, block sizes and per-rank line counts), x shrunk to 16 cells so that the
@@ -1085,6 +1114,7 @@ def main():
                     line["check"]["rel_l2_vs_oracle"] = extra["parity"]["rel_l2_vs_oracle"]
             else:
                 attempt("wave2d", lambda: run_wave2d(args, local_rank, headline=False))   # configs[4]'s 2-D analogue
+                attempt("cufft_crosscheck", lambda: cufft_crosscheck(args.size))
             line["extra"] = extra
     if rank == 0:
         print(json.dumps(line))

@@ -574,6 +574,39 @@ def test_staged_x_passes_match_oracle():
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
 
 
+@pytest.mark.parametrize("n", [(64, 64, 64), (128, 64, 32)])
+def test_poisson_ppp_matches_cufft(n):
+    """north_star: cuFFT only as a correctness (and, in bench.py's `extra.cufft_crosscheck`, performance) cross-check of the
+    hand-written transforms.  The ppp solve of a random right-hand side against the same spectral solve done with
+    torch.fft (cuFFT): forward 3-D transform, division by the modified wavenumbers of the discrete Laplacian
+    (poisson.f90:627-629, :998-1001, singular mode zeroed), inverse transform.  Library code is on this side of the
+    comparison only; the product path never calls it (tests/test_host_logic.py checks the .so does not link cuFFT)."""
+    import torch
+    L = (2 * PI, 2 * PI * n[1] / n[0], 2 * PI * n[2] / n[0])
+    Gg = fb.grid().setup(n[0], n[1], n[2], *L)
+    d = Gg.delta
+    phi = fb.scalar(Gg, 1)
+    rng = np.random.default_rng(23)
+    rhs = rng.standard_normal(n)
+    rhs -= rhs.mean()
+    phi.I[...] = rhs
+    phi.push()
+    ps = fb.PoissonSolver(phi)
+    assert ps.variant == "ppp"
+    ps.solve(phi)
+    phi.pull()
+    t = torch.tensor(rhs, device="cuda", dtype=torch.float64)
+    R = torch.fft.fftn(t)
+    lam = [torch.tensor(2.0 * (np.cos(2.0 * PI * np.arange(m) / m) - 1.0) / (d * d), device="cuda") for m in n]
+    lam3 = lam[0][:, None, None] + lam[1][None, :, None] + lam[2][None, None, :]
+    lam3[0, 0, 0] = 1.0
+    R = R / lam3
+    R[0, 0, 0] = 0.0
+    ref = torch.fft.ifftn(R).real.cpu().numpy()
+    assert rel_l2(phi.I, ref) <= 1e-12
+    Gg.destroy()
+
+
 def test_c_driver_runs():
     """examples/tgv_driver.c: the 2-D Taylor-Green case driven from plain C through the C ABI; the error against the
     analytic solution is the second-order one the reference's test plots (postpro.py:48-62)."""
