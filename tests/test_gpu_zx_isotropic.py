@@ -4,8 +4,8 @@ over them).  The driver loop is the reference's: before every step it reads v, r
 S = 0.1 (v - <v>) on the HOST and hands it back (fen_gpu_pull of v, fen_gpu_push of S: the transfer points INTEGRATION.md
 describes for this driver), and the time step follows constant_CFL = .true., CFL = 0.9.
 
-(1) Laminar phase at the reference's own 128^3, t <= 5: the forced ABC flow grows as exp(2 (0.1 - nu) t); Basilisk, hit3d
-    and the analytic rate agree to 0.1 % there.  The GPU run must reproduce the growth between t = 1 and t = 5 to 0.5 %
+(1) Laminar phase at the reference's own 128^3, t <= 3 (t <= 5 with FEN_TEST_LONG=1, as in the recorded run): the forced ABC flow grows as exp(2 (0.1 - nu) t); Basilisk, hit3d
+    and the analytic rate agree to 0.1 % there.  The GPU run must reproduce the growth between t = 1 and the end to 0.5 %
     and the level to 2 %.
 (2) The whole run through the transition (the energy peaks near t = 15 - 20 -- the two codes differ by a few time units
     there -- and collapses by t = 35) to t = 60: the mean energy over t in [45, 60] must lie in the band of the
@@ -55,11 +55,12 @@ def run_case(n, tend, every=1):
 
 
 def test_isotropic_laminar_growth_at_128():
-    out, steps, (md, mc), bas, hit = run_case(128, 5.0, every=10)
+    tend = 5.0 if os.environ.get("FEN_TEST_LONG") else 3.0
+    out, steps, (md, mc), bas, hit = run_case(128, tend + 0.2, every=10)      # samples every 10 steps: run past tend
     ke = lambda t: float(np.interp(t, out[:, 0], out[:, 1]))
     rb = lambda t: float(np.interp(t, bas[:, 0], bas[:, 1]))
-    assert abs((ke(5.0) / ke(1.0)) / (rb(5.0) / rb(1.0)) - 1.0) < 5e-3, (ke(1.0), ke(5.0))
-    assert abs(ke(1.0) / rb(1.0) - 1.0) < 0.02 and abs(ke(5.0) / rb(5.0) - 1.0) < 0.02, (ke(1.0), ke(5.0))
+    assert abs((ke(tend) / ke(1.0)) / (rb(tend) / rb(1.0)) - 1.0) < 5e-3, (ke(1.0), ke(tend))
+    assert abs(ke(1.0) / rb(1.0) - 1.0) < 0.02 and abs(ke(tend) / rb(tend) - 1.0) < 0.02, (ke(1.0), ke(tend))
     assert abs(md) < 1e-10 and mc < 1.0
 
 
