@@ -65,6 +65,34 @@ def test_fft_core_index_logic_on_cpu():
     assert r.returncode == 0 and "OK" in r.stdout, r.stdout
 
 
+def test_sass_carries_the_copy_engine_instructions():
+    """The built library's SASS (cuobjdump, no GPU needed): the TMA tensor loads of the stencil kernels (UTMALDG), the bulk
+    shared->global copies the slab transposes ship their tiles with (UBLKCP) and the mbarrier operations (SYNCS) are
+    really there -- the evidence profiles/r02_sass_summary.txt records, kept from regressing."""
+    import shutil
+    from fen_b200 import _lib
+    if not shutil.which("cuobjdump"):
+        pytest.skip("cuobjdump not on PATH")
+    r = subprocess.run("cuobjdump -sass %s | python %s" % (_lib.LIB_PATH, os.path.join(ROOT, "scripts", "sass_count.py")),
+                       shell=True, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    rows = {}
+    hdr = None
+    for line in r.stdout.splitlines():
+        cols = line.split()
+        if line.startswith("kernel"):
+            hdr = cols[1:]
+            continue
+        n = len(hdr)
+        rows[" ".join(cols[:-n])] = dict(zip(hdr, (int(x) for x in cols[-n:])))
+    pick = lambda frag: [v for k, v in rows.items() if frag in k]
+    assert pick("k_pred_tma") and all(v["UTMALDG"] >= 3 and v["SYNCS"] >= 1 for v in pick("k_pred_tma"))
+    assert pick("k_corr_tma") and all(v["UTMALDG"] >= 4 for v in pick("k_corr_tma"))
+    for frag in ("k_fft_lines_bs<1024", "k_fft_solve_bs<1024", "k_fft_lines_bs<512", "k_fft_solve_bs<512", "k_bulk_rows"):
+        assert pick(frag) and all(v["UBLKCP"] >= 1 for v in pick(frag)), frag
+    assert all(v["LDGSTS"] > 0 for v in pick("k_thomas_lp"))
+
+
 def test_any_length_kernels_run_on_cpu():
     """fen_b200/csrc/fft_any.cuh: the any-length Poisson kernels (non-power-of-two grids) are sequences of
     __host__ __device__ phases; tests/cpu/test_fft_any.cu runs them with blocks and threads as loops against direct
