@@ -622,3 +622,19 @@ def test_c_driver_runs():
         errs.append(float(re.search(r"u_exact\| after 40 steps: ([0-9.eE+-]+)", r.stdout).group(1)))
     # the oracle gives 2.4544e-3 and 1.0255e-3 for these two runs (dt = 0.125 delta^2, so t differs with N)
     assert abs(errs[0] - 2.4544e-3) < 2e-6 and abs(errs[1] - 1.0255e-3) < 2e-6, errs
+
+
+def test_cpp_driver_runs():
+    """examples/tgv_driver.cpp: the same Taylor-Green case through include/fen_gpu.hpp, the C++ mirror of the reference's
+    API; same error figures as the C driver (the oracle gives 2.4544e-3 and 1.0255e-3)."""
+    import re
+    import subprocess
+    from tests.test_host_logic import _build_cpp_driver
+    exe = _build_cpp_driver()
+    errs = []
+    for n in (32, 64):
+        r = subprocess.run([exe, str(n), "40"], capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0, r.stderr
+        assert "maxdiv" in r.stdout and "poisson variant pp" in r.stdout
+        errs.append(float(re.search(r"u_exact\| after 40 steps: ([0-9.eE+-]+)", r.stdout).group(1)))
+    assert abs(errs[0] - 2.4544e-3) < 2e-6 and abs(errs[1] - 1.0255e-3) < 2e-6, errs

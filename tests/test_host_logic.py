@@ -117,6 +117,30 @@ def _build_c_driver(name="tgv_driver"):
     return exe
 
 
+def _build_cpp_driver(name="tgv_driver"):
+    exe = os.path.join(ROOT, "build", name + "_cpp")
+    os.makedirs(os.path.dirname(exe), exist_ok=True)
+    from fen_b200 import _lib
+    libdir = os.path.dirname(_lib.LIB_PATH)
+    subprocess.run(["g++", "-std=c++17", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(ROOT, "include"),
+                    os.path.join(ROOT, "examples", name + ".cpp"), "-L", libdir, "-lfen_gpu",
+                    "-Wl,-rpath," + libdir, "-o", exe], check=True)
+    return exe
+
+
+def test_cpp_mirror_compiles_and_a_cpp_driver_links(lib):
+    """include/fen_gpu.hpp -- the header-only C++ mirror of the reference's solver API (grid%setup, scalar / vector,
+    init_solver, set_timestep, advance_solution, print_solver_status ...) -- compiles with -Wall -Wextra -pedantic
+    -Werror, the Taylor-Green driver written against it links, and without a device it stops at grid%setup with the 'no
+    CPU fallback' message (the run itself is tests/test_gpu_parity.py::test_cpp_driver_runs)."""
+    import torch
+    exe = _build_cpp_driver()
+    if torch.cuda.is_available():
+        pytest.skip("a device is present: the run itself is tests/test_gpu_parity.py::test_cpp_driver_runs")
+    r = subprocess.run([exe, "16", "1"], capture_output=True, text=True)
+    assert r.returncode == 2 and "no CPU fallback" in r.stderr
+
+
 def test_two_phase_c_driver_links(lib):
     """examples/shear_drop_driver.c: the reference's shear-drop driver (-DMF build) through the two-phase entry points
     of the C ABI -- module parameters, init_solver with a distance callback, moving-wall values -- compiles as C99 with
