@@ -247,3 +247,34 @@ def test_bench_reference_arm_prints_the_contract_line(case):
     assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == line["value"] and cb["sample"]
     e = line["e2e"]
     assert e["value"] == line["value"] and e["h2d_bytes_per_step"] == 0 and e["d2h_bytes_per_step"] == 0
+
+
+def test_bench_host_logic():
+    """bench.py's pure host logic: the weak-scaling shapes are BASELINE configs[3]'s (512^3 per GPU: x, then y, then z
+    doubles), every timed kernel family finds its DRAM traffic in the committed ncu capture (so that no
+    kernels[].traffic_frac is left empty or above 1 for lack of a match), and the transposes' figures come out of the
+    kernel table as documented."""
+    import argparse
+    import json
+    sys.path.insert(0, ROOT)
+    import bench
+    assert [bench.weak_dims(512, w) for w in (1, 2, 4, 8)] == [[512, 512, 512], [1024, 512, 512], [1024, 1024, 512],
+                                                              [1024, 1024, 1024]]
+    with pytest.raises(SystemExit):
+        bench.weak_dims(512, 3)
+    traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+    assert traffic["size"] == 512
+    for fam, lo, hi in (("pred", 104, 112), ("corr_check", 72, 80), ("fft_x_r2c_div", 32, 34), ("fft_solve", 16, 17),
+                        ("fft_lines_fwd", 16, 17), ("fft_lines_inv", 16, 17), ("fft_x_c2r", 16, 17)):
+        b = bench.load_traffic(fam, 512)
+        assert b is not None, fam
+        assert lo <= b / 512 ** 3 <= hi, (fam, b / 512 ** 3)            # bytes per cell the kernel really moved
+        assert b <= bench.KERNEL_BYTES_PER_CELL[fam] * 512 ** 3 * 1.08  # never far above the algorithmic bytes
+    assert bench.load_traffic("pred", 256) is None                     # another size: no figure rather than a wrong one
+    args = argparse.Namespace(no_nccl_baseline=True)
+    tk = {"fft_lines_fwd_a2a": 1.0, "a2a_fwd_sync": 0.25, "fft_solve_a2a": 1.5, "a2a_bwd_sync": 0.5}
+    nv = bench.nvlink_figures(args, tk, 1024, 1024, 1024, 8, nccl=False)
+    sent = 513 * 1024 * 128 * 16 * 7 // 8
+    assert nv["a2a_bytes_sent_per_gpu"] == sent
+    assert abs(nv["fwd_bus_GBs"] - sent / 1.25e-3 / 1e9) < 1e-9 and abs(nv["bwd_bus_GBs"] - sent / 2.0e-3 / 1e9) < 1e-9
+    assert bench.nvlink_figures(args, tk, 512, 512, 512, 1) is None
