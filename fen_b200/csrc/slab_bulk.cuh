@@ -19,7 +19,7 @@
 // k_fft_lines_bs   y forward:   row layout C[kx + PC*(j + ny*zl)]  ->  transform over j  ->  peers' Cz
 // k_fft_solve_bs   z solve:     Cz (lines over k)  ->  forward, divide, inverse           ->  peers' Cy
 // k_fft_lines_io   y inverse:   Cy (lines over j)  ->  transform                          ->  row layout (local)
-// k_bulk_rows      Thomas path: contiguous runs of a local staging array                  ->  peers' Cy
+// k_bulk_rows      Thomas path: the back substitution's solution in Cz, gathered run by run    ->  peers' Cy
 #pragma once
 #include "fen_internal.cuh"
 #include "fft_core.cuh"
